@@ -1,0 +1,123 @@
+/* mtg_b200.h -- C ABI of the B200-native engine for the data-parallel core of `MindTheGap find`.
+ *
+ * Drop-in boundary. Every entry point names the reference interface it replaces
+ * (paths relative to the MindTheGap repository; G/ = thirdparty/gatb-core/gatb-core/src/gatb/).
+ * Plain pointers and sizes only; all calls are blocking and must come from one host thread per context.
+ * Functions returning int return 0 on success and a negative code on failure; mtg_last_error() then holds the
+ * message (the C++ host shim rethrows it as a gatb Exception so that `main` prints "EXCEPTION: ..." as before,
+ * src/main.cpp:96-102). There is no CPU fallback: without a CUDA device mtg_create fails.
+ */
+#ifndef MTG_B200_H
+#define MTG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mtg_ctx mtg_ctx;
+
+#define MTG_ABUNDANCE_AUTO (-1)
+
+/* mode flags = the booleans Finder::execute derives from the CLI (src/Finder.cpp:60-90, 321-398) */
+#define MTG_F_HOMO_ONLY   0x01
+#define MTG_F_HOMO_INSERT 0x02
+#define MTG_F_HETE_INSERT 0x04
+#define MTG_F_SNP         0x08
+#define MTG_F_BACKUP      0x10
+#define MTG_F_DELETION    0x20
+#define MTG_F_SMALL_HOMO  0x40
+#define MTG_F_DEFAULT (MTG_F_HOMO_INSERT | MTG_F_HETE_INSERT | MTG_F_SNP | MTG_F_DELETION | MTG_F_SMALL_HOMO)
+
+typedef struct mtg_params {
+    int32_t kmer_size;        /* -kmer-size, 5..63 (src/Finder.cpp:155)                                  */
+    int32_t abundance_min;    /* -abundance-min, MTG_ABUNDANCE_AUTO = "auto" (src/Finder.cpp:153)         */
+    int64_t abundance_max;    /* -abundance-max (src/Finder.cpp:150-151)                                  */
+    int32_t minimizer_size;   /* forced to 10 by Finder (src/Finder.cpp:246); partitioning only           */
+    int32_t max_repeat;       /* -max-rep        default 5                                                */
+    int32_t het_max_occ;      /* -het-max-occ    default 1                                                */
+    int32_t snp_min_val;      /* -snp-min-val    default 5                                                */
+    int32_t branching_filter; /* -branching-filter default 15, -1 disables                               */
+    uint32_t flags;           /* MTG_F_*                                                                  */
+    int32_t device;           /* CUDA device ordinal                                                      */
+} mtg_params;
+
+void mtg_default_params(mtg_params* p);
+
+/* Graph lifetime: replaces the `Graph` value held by Finder (src/Finder.hpp:68, Graph::create / Graph::load). */
+mtg_ctx* mtg_create(const mtg_params* p);
+void mtg_destroy(mtg_ctx* ctx);
+const char* mtg_last_error(void);
+const char* mtg_version(void);
+
+/* ---- stage 1: solid k-mers. Replaces Graph::create -> build_visitor_solid
+ *      (G/debruijn/impl/Graph.cpp:285-422: ConfigurationAlgorithm, RepartitorAlgorithm, SortingCountAlgorithm).
+ * Reads are pushed as ASCII bases; sequences are separated by any byte outside ACGTacgt (e.g. '\n').          */
+int mtg_count_reserve(mtg_ctx* ctx, uint64_t nb_bases);
+int mtg_push_reads(mtg_ctx* ctx, const char* bases, uint64_t nbytes);              /* host buffer   */
+int mtg_push_reads_device(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes);     /* device buffer */
+/* Convenience host-side parser: FASTA/FASTQ files, comma separated list (Bank::open, G/bank/impl/Bank.cpp:49-52,
+ * BankFasta.cpp:485-574). Plain text only. */
+int mtg_count_files(mtg_ctx* ctx, const char* uri);
+/* Ends the counting: histogram, auto cut-off (Histogram::compute_threshold, G/tools/misc/impl/Histogram.cpp:59-189),
+ * solidity filter (CountProcessorSolidity.hpp:182-185); then builds the membership structures of
+ * build_visitor_postsolid (Graph.cpp:428-612): Bloom, cascading cFP, BooPHF presence, + the exact table. */
+int mtg_count_finish(mtg_ctx* ctx);
+
+/* info lines of Finder::resumeParameters (src/Finder.cpp:444-467) */
+int32_t mtg_get_threshold(mtg_ctx* ctx);     /* "abundance_min (used)"           */
+int32_t mtg_get_cutoff_auto(mtg_ctx* ctx);   /* "abundance_min (auto inferred)", -1 when not auto */
+uint64_t mtg_get_nb_solid(mtg_ctx* ctx);     /* "nb_solid_kmers"                 */
+int mtg_get_histogram(mtg_ctx* ctx, uint64_t* out10001);
+/* stats: see mtg_stat_name(i); returns the number of values written (<= cap) */
+int mtg_get_stats(mtg_ctx* ctx, double* out, int cap);
+const char* mtg_stat_name(int i);
+
+/* Replaces CountProcessorDump (G/kmer/impl/CountProcessorDump.hpp:140-144): (value, abundance) of every solid k-mer,
+ * value split in two 64-bit halves (hi may be NULL when kmer_size <= 31). Order is unspecified. */
+int mtg_export_solid(mtg_ctx* ctx, uint64_t* lo, uint64_t* hi, uint32_t* abundance, uint64_t capacity);
+/* Replaces Graph::load (-graph x.h5, src/Finder.cpp:274-279): the host reads dsk/solid and uploads it. */
+int mtg_load_solid(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_t n);
+
+/* ---- stage 2: reference scan. Replaces FindBreakpoints (src/FindBreakpoints.hpp) and its observers. */
+/* fillRefBloom (src/FindBreakpoints.hpp:956-1009): all reference sequences, separated by a non-ACGT byte. */
+int mtg_set_reference(mtg_ctx* ctx, const char* bases, uint64_t nbytes);
+
+/* Graph::contains / indegree / outdegree / ref Bloom for arbitrary k-mers (src/IFindObserver.hpp:85-117).
+ * kmers are FORWARD values (any strand). contains: out bit0 = contains (bits 1..4: exact, bloom, cfp, mphf detail);
+ * degree: out = indegree | outdegree<<4 ; repeat: input = canonical (k-1)-mers, out = 0/1. */
+int mtg_contains_batch(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out);
+int mtg_degree_batch(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out);
+int mtg_ref_repeat_batch(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out);
+
+/* Dense per-position features of one sequence = the values store_kmer_info computes (FindBreakpoints.hpp:1012-1046):
+ * feat[p] = 0x80 if k-mer p is invalid, else in_graph | nb_in<<1 | nb_out<<4 ; rep[p] = suffix_rep | prefix_rep<<1.
+ * Arrays hold len-k+1 entries. counters4: valid positions, in-graph positions, table probes, Bloom-emulation calls. */
+int mtg_sequence_features(mtg_ctx* ctx, const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint64_t* counters4);
+int mtg_sequence_features_device(mtg_ctx* ctx, const void* d_seq, uint64_t len, void* d_feat, void* d_rep, uint64_t* counters4);
+
+/* One reference sequence through FindBreakpoints::operator() (src/FindBreakpoints.hpp:390-455). Records are appended to
+ * the context's two output buffers with the reference's exact formats (writeBreakpoint/writeVcfVariant/writeIndel,
+ * :641-702); the bkpt id counter is shared and runs across calls (:872-875). */
+int mtg_scan_reference(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len);
+/* Output accessors: pointers stay valid until the next scan/reset call on this context. */
+const char* mtg_breakpoints_text(mtg_ctx* ctx, uint64_t* nbytes);
+const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes);
+int mtg_reset_outputs(mtg_ctx* ctx);
+/* counters of Finder::resumeResults (src/Finder.cpp:470-511): homo_clean, homo_fuzzy, hetero_clean, hetero_fuzzy,
+ * clean_deletion, fuzzy_deletion, solo_snp, multi_snp, backup, homo_indel, hetero_indel, observer_queries */
+int mtg_get_find_counters(mtg_ctx* ctx, uint64_t* out12);
+
+/* raw membership bits for parity tests against the .h5 datasets: which = 0 bloom, 1..3 bloom2..4, 4 ref bloom,
+ * 5 BooPHF levels. Returns the byte size (copies when buf != NULL and capacity suffices). */
+int64_t mtg_copy_bits(mtg_ctx* ctx, int which, uint8_t* buf, uint64_t capacity);
+
+/* micro-benchmark used to establish the random 128-byte gather roofline on the box:
+ * returns achieved GB/s over a table of table_bytes with nprobes random probes per launch. */
+double mtg_bench_random_gather(int device, uint64_t table_bytes, uint64_t nprobes, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,304 @@
+"""ctypes binding of include/mtg_b200.h and a `Finder` class mirroring MindTheGap's Finder (src/Finder.cpp).
+
+There is NO fallback: if the CUDA library is missing or no CUDA device is present, construction fails loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libmtg_b200.so")
+
+F_HOMO_ONLY, F_HOMO_INSERT, F_HETE_INSERT, F_SNP, F_BACKUP, F_DELETION, F_SMALL_HOMO = 1, 2, 4, 8, 16, 32, 64
+F_DEFAULT = F_HOMO_INSERT | F_HETE_INSERT | F_SNP | F_DELETION | F_SMALL_HOMO
+ABUNDANCE_AUTO = -1
+
+
+class MtgError(RuntimeError):
+    pass
+
+
+class _Params(C.Structure):
+    _fields_ = [("kmer_size", C.c_int32), ("abundance_min", C.c_int32), ("abundance_max", C.c_int64),
+                ("minimizer_size", C.c_int32), ("max_repeat", C.c_int32), ("het_max_occ", C.c_int32),
+                ("snp_min_val", C.c_int32), ("branching_filter", C.c_int32), ("flags", C.c_uint32), ("device", C.c_int32)]
+
+
+u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+EXPORTS = [
+    "mtg_default_params", "mtg_create", "mtg_destroy", "mtg_last_error", "mtg_version", "mtg_count_reserve", "mtg_push_reads",
+    "mtg_push_reads_device", "mtg_count_files", "mtg_count_finish", "mtg_get_threshold", "mtg_get_cutoff_auto", "mtg_get_nb_solid",
+    "mtg_get_histogram", "mtg_get_stats", "mtg_stat_name", "mtg_export_solid", "mtg_load_solid", "mtg_set_reference",
+    "mtg_contains_batch", "mtg_degree_batch", "mtg_ref_repeat_batch", "mtg_sequence_features", "mtg_sequence_features_device",
+    "mtg_scan_reference", "mtg_breakpoints_text", "mtg_vcf_text", "mtg_reset_outputs", "mtg_get_find_counters", "mtg_copy_bits",
+    "mtg_bench_random_gather",
+]
+
+_lib = None
+
+
+def build_library():
+    """Compile the CUDA library in-tree (nvcc, sm_100a)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "csrc")], check=True)
+    return LIB_PATH
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MtgError("CUDA extension %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.mtg_default_params.argtypes = [C.POINTER(_Params)]
+    L.mtg_create.restype = vp
+    L.mtg_create.argtypes = [C.POINTER(_Params)]
+    L.mtg_destroy.argtypes = [vp]
+    L.mtg_last_error.restype = C.c_char_p
+    L.mtg_version.restype = C.c_char_p
+    L.mtg_count_reserve.argtypes = [vp, C.c_uint64]
+    L.mtg_push_reads.argtypes = [vp, vp, C.c_uint64]
+    L.mtg_push_reads_device.argtypes = [vp, vp, C.c_uint64]
+    L.mtg_count_files.argtypes = [vp, C.c_char_p]
+    L.mtg_count_finish.argtypes = [vp]
+    L.mtg_get_threshold.argtypes = [vp]
+    L.mtg_get_cutoff_auto.argtypes = [vp]
+    L.mtg_get_nb_solid.restype = C.c_uint64
+    L.mtg_get_nb_solid.argtypes = [vp]
+    L.mtg_get_histogram.argtypes = [vp, u64p]
+    L.mtg_get_stats.argtypes = [vp, f64p, C.c_int]
+    L.mtg_stat_name.restype = C.c_char_p
+    L.mtg_stat_name.argtypes = [C.c_int]
+    L.mtg_export_solid.argtypes = [vp, u64p, vp, vp, C.c_uint64]
+    L.mtg_load_solid.argtypes = [vp, u64p, vp, C.c_uint64]
+    L.mtg_set_reference.argtypes = [vp, vp, C.c_uint64]
+    for fn in (L.mtg_contains_batch, L.mtg_degree_batch, L.mtg_ref_repeat_batch):
+        fn.argtypes = [vp, u64p, vp, C.c_uint64, u8p]
+    L.mtg_sequence_features.argtypes = [vp, vp, C.c_uint64, u8p, u8p, u64p]
+    L.mtg_sequence_features_device.argtypes = [vp, vp, C.c_uint64, vp, vp, u64p]
+    L.mtg_scan_reference.argtypes = [vp, C.c_char_p, vp, C.c_uint64]
+    L.mtg_breakpoints_text.restype = vp
+    L.mtg_breakpoints_text.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mtg_vcf_text.restype = vp
+    L.mtg_vcf_text.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mtg_reset_outputs.argtypes = [vp]
+    L.mtg_get_find_counters.argtypes = [vp, u64p]
+    L.mtg_copy_bits.restype = C.c_int64
+    L.mtg_copy_bits.argtypes = [vp, C.c_int, vp, C.c_uint64]
+    L.mtg_bench_random_gather.restype = C.c_double
+    L.mtg_bench_random_gather.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int]
+    _lib = L
+    return L
+
+
+@dataclass
+class FindParams:
+    """Options of `MindTheGap find` (src/Finder.cpp:97-171); defaults are the reference's."""
+    kmer_size: int = 31
+    abundance_min: int = ABUNDANCE_AUTO  # "auto"
+    abundance_max: int = 2147483647
+    max_repeat: int = 5
+    het_max_occ: int = 1
+    snp_min_val: int = 5
+    branching_filter: int = 15
+    flags: int = F_DEFAULT
+    device: int = 0
+    minimizer_size: int = 10
+
+    @staticmethod
+    def from_cli(args):
+        """Parse `find`-style flags (subset used by the tests), same fixed evaluation order as src/Finder.cpp:321-398."""
+        p = FindParams()
+        it = iter(args)
+        seen = set()
+        for a in it:
+            if a == "-kmer-size": p.kmer_size = int(next(it))
+            elif a == "-abundance-min":
+                v = next(it); p.abundance_min = ABUNDANCE_AUTO if v == "auto" else int(v)
+            elif a == "-abundance-max": p.abundance_max = int(next(it))
+            elif a == "-max-rep": p.max_repeat = int(next(it))
+            elif a == "-het-max-occ": p.het_max_occ = max(1, int(next(it)))
+            elif a == "-snp-min-val": p.snp_min_val = int(next(it))
+            elif a == "-branching-filter": p.branching_filter = int(next(it))
+            else: seen.add(a)
+        homo_only, homo_insert, hete_insert, snp, backup, deletion, small = False, True, True, True, False, True, True
+        if "-homo-only" in seen: homo_only, homo_insert, hete_insert, snp, backup, deletion = True, True, False, True, False, True
+        if "-insert-only" in seen: homo_only, homo_insert, hete_insert, snp, backup, deletion = False, True, True, False, False, False
+        if "-snp-only" in seen: homo_only, homo_insert, hete_insert, snp, backup, deletion = True, False, False, True, False, False
+        if "-deletion-only" in seen: homo_only, homo_insert, hete_insert, snp, backup, deletion = True, False, False, False, False, True
+        if "-hete-only" in seen: homo_only, homo_insert, hete_insert, snp, backup, deletion = False, False, True, False, False, False
+        if "-backup" in seen: backup = True
+        if "-no-snp" in seen: snp = False
+        if "-no-insert" in seen: homo_insert = False
+        if "-no-deletion" in seen: deletion = False
+        if "-no-hetero" in seen: hete_insert = False
+        p.flags = (F_HOMO_ONLY * homo_only | F_HOMO_INSERT * homo_insert | F_HETE_INSERT * hete_insert | F_SNP * snp |
+                   F_BACKUP * backup | F_DELETION * deletion | F_SMALL_HOMO * small)
+        return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Finder:
+    """Host mirror of MindTheGap's Finder for the GPU path: count reads -> graph -> scan reference -> outputs."""
+
+    def __init__(self, params: FindParams = None):
+        self.L = load_library()
+        self.params = params or FindParams()
+        p = _Params()
+        self.L.mtg_default_params(C.byref(p))
+        for f, _ in _Params._fields_:
+            setattr(p, f, getattr(self.params, f))
+        self.ctx = self.L.mtg_create(C.byref(p))
+        if not self.ctx:
+            raise MtgError(self.L.mtg_last_error().decode())
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.mtg_destroy(self.ctx)
+            self.ctx = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MtgError(self.L.mtg_last_error().decode())
+
+    # ---- stage 1
+    def reserve(self, nb_bases):
+        self._check(self.L.mtg_count_reserve(self.ctx, nb_bases))
+
+    def push_reads(self, stream):
+        """stream: bytes / uint8 array of ASCII bases, reads separated by a non-ACGT byte."""
+        a = np.frombuffer(stream, dtype=np.uint8) if isinstance(stream, (bytes, bytearray)) else np.ascontiguousarray(stream, dtype=np.uint8)
+        self._check(self.L.mtg_push_reads(self.ctx, _ptr(a), a.size))
+
+    def push_reads_device(self, dev_ptr, nbytes):
+        self._check(self.L.mtg_push_reads_device(self.ctx, C.c_void_p(dev_ptr), nbytes))
+
+    def count_files(self, uri):
+        self._check(self.L.mtg_count_files(self.ctx, uri.encode()))
+
+    def finish_count(self):
+        self._check(self.L.mtg_count_finish(self.ctx))
+
+    @property
+    def threshold(self):
+        return self.L.mtg_get_threshold(self.ctx)
+
+    @property
+    def cutoff_auto(self):
+        return self.L.mtg_get_cutoff_auto(self.ctx)
+
+    @property
+    def nb_solid(self):
+        return int(self.L.mtg_get_nb_solid(self.ctx))
+
+    def histogram(self):
+        h = np.zeros(10001, dtype=np.uint64)
+        self._check(self.L.mtg_get_histogram(self.ctx, h))
+        return h
+
+    def stats(self):
+        v = np.zeros(64, dtype=np.float64)
+        n = self.L.mtg_get_stats(self.ctx, v, 64)
+        return {self.L.mtg_stat_name(i).decode(): float(v[i]) for i in range(n)}
+
+    def export_solid(self):
+        n = self.nb_solid
+        lo = np.zeros(max(n, 1), dtype=np.uint64); hi = np.zeros(max(n, 1), dtype=np.uint64)
+        ab = np.zeros(max(n, 1), dtype=np.uint32)
+        self._check(self.L.mtg_export_solid(self.ctx, lo, _ptr(hi), _ptr(ab), max(n, 1)))
+        return lo[:n], hi[:n], ab[:n]
+
+    def load_solid(self, lo, hi=None):
+        lo = np.ascontiguousarray(lo, dtype=np.uint64)
+        hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.uint64)
+        self._check(self.L.mtg_load_solid(self.ctx, lo, _ptr(hi), len(lo)))
+
+    # ---- stage 2
+    def set_reference(self, stream):
+        a = np.frombuffer(stream, dtype=np.uint8) if isinstance(stream, (bytes, bytearray)) else np.ascontiguousarray(stream, dtype=np.uint8)
+        self._check(self.L.mtg_set_reference(self.ctx, _ptr(a), a.size))
+
+    def _batch(self, fn, lo, hi):
+        lo = np.ascontiguousarray(lo, dtype=np.uint64)
+        hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.uint64)
+        out = np.zeros(max(len(lo), 1), dtype=np.uint8)
+        self._check(fn(self.ctx, lo, _ptr(hi), len(lo), out))
+        return out[:len(lo)]
+
+    def contains(self, lo, hi=None):
+        return self._batch(self.L.mtg_contains_batch, lo, hi)
+
+    def degrees(self, lo, hi=None):
+        return self._batch(self.L.mtg_degree_batch, lo, hi)
+
+    def ref_repeat(self, lo, hi=None):
+        return self._batch(self.L.mtg_ref_repeat_batch, lo, hi)
+
+    def features(self, seq):
+        a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        n = max(0, a.size - self.params.kmer_size + 1)
+        f = np.zeros(max(n, 1), dtype=np.uint8); r = np.zeros(max(n, 1), dtype=np.uint8)
+        c4 = np.zeros(4, dtype=np.uint64)
+        self._check(self.L.mtg_sequence_features(self.ctx, _ptr(a), a.size, f, r, c4))
+        return f[:n], r[:n], c4
+
+    def features_device(self, dev_seq, length, dev_feat, dev_rep):
+        c4 = np.zeros(4, dtype=np.uint64)
+        self._check(self.L.mtg_sequence_features_device(self.ctx, C.c_void_p(dev_seq), length, C.c_void_p(dev_feat), C.c_void_p(dev_rep), c4))
+        return c4
+
+    def scan_reference(self, name, seq):
+        a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        self._check(self.L.mtg_scan_reference(self.ctx, name.encode(), _ptr(a), a.size))
+
+    def breakpoints_text(self):
+        n = C.c_uint64()
+        p = self.L.mtg_breakpoints_text(self.ctx, C.byref(n))
+        return C.string_at(p, n.value).decode()
+
+    def vcf_text(self):
+        n = C.c_uint64()
+        p = self.L.mtg_vcf_text(self.ctx, C.byref(n))
+        return C.string_at(p, n.value).decode()
+
+    def reset_outputs(self):
+        self._check(self.L.mtg_reset_outputs(self.ctx))
+
+    def find_counters(self):
+        o = np.zeros(12, dtype=np.uint64)
+        self._check(self.L.mtg_get_find_counters(self.ctx, o))
+        names = ["homo_clean", "homo_fuzzy", "hetero_clean", "hetero_fuzzy", "clean_deletion", "fuzzy_deletion", "solo_snp", "multi_snp",
+                 "backup", "homo_indel", "hetero_indel", "observer_queries"]
+        return dict(zip(names, o.tolist()))
+
+    def copy_bits(self, which):
+        n = self.L.mtg_copy_bits(self.ctx, which, None, 0)
+        if n < 0:
+            raise MtgError(self.L.mtg_last_error().decode())
+        buf = np.zeros(max(n, 1), dtype=np.uint8)
+        self.L.mtg_copy_bits(self.ctx, which, _ptr(buf), n)
+        return buf[:n]
+
+    # ---- whole `find` on in-memory inputs (what bench.py and the parity tests drive)
+    def find(self, read_stream, ref_records):
+        """read_stream: '\\n'-separated bases; ref_records: list of (name, bytes). Returns (breakpoints, vcf records)."""
+        self.push_reads(read_stream)
+        self.finish_count()
+        self.set_reference(b"\n".join(s for _, s in ref_records))
+        for name, seq in ref_records:
+            self.scan_reference(name, seq)
+        return self.breakpoints_text(), self.vcf_text()

@@ -1,0 +1,360 @@
+// mtg-b200 C ABI (include/mtg_b200.h): thin glue over the CUDA engine. No CPU fallback anywhere.
+#include <memory>
+#include <mutex>
+
+#include "../../include/mtg_b200.h"
+#include "count.cuh"
+#include "graph.cuh"
+#include "replay.hpp"
+#include "seqio.hpp"
+
+using namespace mtg;
+
+static thread_local std::string g_last_error;
+
+struct mtg_ctx {
+    mtg_params p;
+    cudaStream_t stream = nullptr;
+    std::unique_ptr<ICounter> counter;   // reads, k
+    std::unique_ptr<IGraph> graph;
+    CountStats count_stats;
+    std::vector<uint64_t> histogram;
+    int threshold = 0, cutoff_auto = -1;
+    uint64_t nb_solid = 0;
+    bool graph_ready = false;
+    // solid set kept on the device for export
+    std::unique_ptr<ICounter> solid_owner;
+    std::vector<uint64_t> loaded_lo, loaded_hi;
+    // reference
+    uint64_t ref_repeated = 0;
+    CountStats ref_count_stats;
+    // replay
+    std::unique_ptr<Replayer<uint64_t>> rp64;
+    std::unique_ptr<Replayer<u128>> rp128;
+    std::vector<uint8_t> feat, rep;
+    double ms_features = 0, ms_replay = 0, ms_graph_build = 0;
+    uint64_t scan_positions = 0, scan_valid = 0, scan_in_graph = 0, scan_table_probes = 0, scan_fallback = 0;
+    std::vector<uint64_t> tmp_lo, tmp_hi;
+};
+
+#define MTG_TRY(ctx_expr) \
+    try {                 \
+        if (!(ctx_expr)) { g_last_error = "null context"; return -1; }
+#define MTG_CATCH                                                                \
+    }                                                                            \
+    catch (const mtg::Error& e) { g_last_error = e.what(); return e.code; }      \
+    catch (const std::exception& e) { g_last_error = e.what(); return -1; }      \
+    return 0;
+
+static ReplayOptions replay_options(const mtg_params& p) {
+    ReplayOptions o;
+    o.k = p.kmer_size; o.max_repeat = p.max_repeat; o.het_max_occ = p.het_max_occ; o.snp_min_val = p.snp_min_val;
+    o.branching_filter = p.branching_filter;
+    o.homo_only = p.flags & MTG_F_HOMO_ONLY; o.homo_insert = p.flags & MTG_F_HOMO_INSERT; o.hete_insert = p.flags & MTG_F_HETE_INSERT;
+    o.snp = p.flags & MTG_F_SNP; o.backup = p.flags & MTG_F_BACKUP; o.deletion = p.flags & MTG_F_DELETION; o.small_homo = p.flags & MTG_F_SMALL_HOMO;
+    return o;
+}
+
+static void make_replayers(mtg_ctx* c) {
+    ReplayOptions o = replay_options(c->p);
+    if (c->p.kmer_size <= 31) {
+        c->rp64.reset(new Replayer<uint64_t>(o, [c](const uint64_t* km, size_t n, uint8_t* out) { c->graph->observer_probe_batch(km, nullptr, n, out); }));
+    } else {
+        c->rp128.reset(new Replayer<u128>(o, [c](const u128* km, size_t n, uint8_t* out) {
+            c->tmp_lo.resize(n); c->tmp_hi.resize(n);
+            for (size_t i = 0; i < n; i++) { c->tmp_lo[i] = (uint64_t)km[i]; c->tmp_hi[i] = (uint64_t)(km[i] >> 64); }
+            c->graph->observer_probe_batch(c->tmp_lo.data(), c->tmp_hi.data(), n, out);
+        }));
+    }
+}
+
+extern "C" {
+
+const char* mtg_last_error(void) { return g_last_error.c_str(); }
+const char* mtg_version(void) { return "mtg-b200 0.1 (sm_100a)"; }
+
+void mtg_default_params(mtg_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->kmer_size = 31; p->abundance_min = MTG_ABUNDANCE_AUTO; p->abundance_max = 2147483647LL; p->minimizer_size = 10;
+    p->max_repeat = 5; p->het_max_occ = 1; p->snp_min_val = 5; p->branching_filter = 15; p->flags = MTG_F_DEFAULT; p->device = 0;
+}
+
+mtg_ctx* mtg_create(const mtg_params* p) {
+    try {
+        if (!p) throw Error(-1, "null params");
+        if (p->kmer_size < 5 || p->kmer_size > 63) throw Error(-1, "kmer size must be in [5,63] (k<=31: 64-bit keys, k<=63: 128-bit keys)");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) throw Error(-2, std::string("no CUDA device available: ") + cudaGetErrorString(e));
+        if (p->device < 0 || p->device >= ndev) throw Error(-2, "bad device ordinal");
+        MTG_CUDA(cudaSetDevice(p->device));
+        std::unique_ptr<mtg_ctx> c(new mtg_ctx());
+        c->p = *p;
+        if (c->p.het_max_occ < 1) c->p.het_max_occ = 1;  // src/Finder.cpp:317-319
+        if (c->p.minimizer_size <= 0) c->p.minimizer_size = 10;
+        MTG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->graph.reset(make_graph(c->p.kmer_size, c->stream));
+        c->histogram.assign(HISTO_MAX + 1, 0);
+        make_replayers(c.get());
+        return c.release();
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return nullptr;
+    }
+}
+
+void mtg_destroy(mtg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->p.device);
+    ctx->counter.reset(); ctx->solid_owner.reset(); ctx->graph.reset();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static ICounter* reads_counter(mtg_ctx* ctx) {
+    MTG_CUDA(cudaSetDevice(ctx->p.device));
+    if (!ctx->counter) ctx->counter.reset(make_counter(ctx->p.kmer_size, ctx->p.minimizer_size, ctx->stream));
+    return ctx->counter.get();
+}
+
+int mtg_count_reserve(mtg_ctx* ctx, uint64_t nb_bases) { MTG_TRY(ctx) reads_counter(ctx)->reserve(nb_bases); MTG_CATCH }
+int mtg_push_reads(mtg_ctx* ctx, const char* bases, uint64_t nbytes) { MTG_TRY(ctx) reads_counter(ctx)->push_host(bases, nbytes); MTG_CATCH }
+int mtg_push_reads_device(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes) {
+    MTG_TRY(ctx) reads_counter(ctx)->push_device((const uint8_t*)d_bases, nbytes); MTG_CATCH
+}
+
+int mtg_count_files(mtg_ctx* ctx, const char* uri) {
+    MTG_TRY(ctx)
+    ICounter* c = reads_counter(ctx);
+    std::string chunk;
+    const size_t CHUNK = 256u << 20;
+    chunk.reserve(CHUNK + (1 << 20));
+    for_each_sequence(uri, [&](SeqRecord& r) {
+        chunk += r.seq;
+        chunk += '\n';
+        if (chunk.size() >= CHUNK) { c->push_host(chunk.data(), chunk.size()); MTG_CUDA(cudaStreamSynchronize(ctx->stream)); chunk.clear(); }
+    });
+    if (!chunk.empty()) { c->push_host(chunk.data(), chunk.size()); MTG_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    MTG_CATCH
+}
+
+static void build_graph_from_counter(mtg_ctx* ctx, ICounter* c) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, ctx->stream);
+    ctx->graph->build(c->solid_keys_device(), c->nb_solid());
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    ctx->ms_graph_build = ms;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    ctx->graph_ready = true;
+}
+
+int mtg_count_finish(mtg_ctx* ctx) {
+    MTG_TRY(ctx)
+    ICounter* c = reads_counter(ctx);
+    c->finish(ctx->p.abundance_min, ctx->p.abundance_max);
+    ctx->count_stats = c->stats();
+    memcpy(ctx->histogram.data(), c->histogram(), (HISTO_MAX + 1) * 8);
+    ctx->threshold = c->stats().threshold;
+    ctx->cutoff_auto = c->stats().cutoff_auto;
+    ctx->nb_solid = c->nb_solid();
+    build_graph_from_counter(ctx, c);
+    ctx->solid_owner = std::move(ctx->counter);
+    ctx->loaded_lo.clear(); ctx->loaded_hi.clear();
+    MTG_CATCH
+}
+
+int32_t mtg_get_threshold(mtg_ctx* ctx) { return ctx ? ctx->threshold : -1; }
+int32_t mtg_get_cutoff_auto(mtg_ctx* ctx) { return ctx ? ctx->cutoff_auto : -1; }
+uint64_t mtg_get_nb_solid(mtg_ctx* ctx) { return ctx ? ctx->nb_solid : 0; }
+int mtg_get_histogram(mtg_ctx* ctx, uint64_t* out) { MTG_TRY(ctx) memcpy(out, ctx->histogram.data(), (HISTO_MAX + 1) * 8); MTG_CATCH }
+
+static const char* STAT_NAMES[] = {
+    "count.nb_bases", "count.nb_valid_kmers", "count.nb_records", "count.nb_groups", "count.nb_items", "count.nb_multipass_groups",
+    "count.nb_candidates", "count.nb_solid", "count.ms_pack", "count.ms_extract", "count.ms_group", "count.ms_scatter", "count.ms_count",
+    "count.ms_filter", "count.launches",
+    "graph.nbuckets", "graph.bloom_bits", "graph.nb_critical", "graph.bloom2_bits", "graph.bloom3_bits", "graph.bloom4_bits", "graph.cfp_set",
+    "graph.ms_table", "graph.ms_bloom", "graph.ms_critical", "graph.ms_cascade", "graph.ms_mphf", "graph.ms_build_total", "graph.launches",
+    "ref.nb_repeated", "ref.bloom_bits",
+    "scan.positions", "scan.valid", "scan.in_graph", "scan.table_probes", "scan.bloom_emulations", "scan.ms_features", "scan.ms_replay",
+    "scan.observer_queries", "scan.probe_batches"};
+static const int NSTATS = sizeof(STAT_NAMES) / sizeof(STAT_NAMES[0]);
+const char* mtg_stat_name(int i) { return (i >= 0 && i < NSTATS) ? STAT_NAMES[i] : nullptr; }
+
+int mtg_get_stats(mtg_ctx* ctx, double* out, int cap) {
+    if (!ctx) return 0;
+    const CountStats& c = ctx->count_stats;
+    const GraphStats& g = ctx->graph->stats();
+    uint64_t oq = ctx->rp64 ? ctx->rp64->cnt.observer_queries : ctx->rp128->cnt.observer_queries;
+    uint64_t pb = ctx->rp64 ? ctx->rp64->cnt.probe_batches : ctx->rp128->cnt.probe_batches;
+    double v[] = {(double)c.nb_bases, (double)c.nb_valid_kmers, (double)c.nb_records, (double)c.nb_groups, (double)c.nb_items,
+                  (double)c.nb_multipass_groups, (double)c.nb_candidates, (double)c.nb_solid, c.ms_pack, c.ms_extract, c.ms_group, c.ms_scatter,
+                  c.ms_count, c.ms_filter, (double)c.launches,
+                  (double)g.nbuckets, (double)g.bloom_tai, (double)g.nb_critical, (double)g.b2_tai, (double)g.b3_tai, (double)g.b4_tai, (double)g.ncfp,
+                  g.ms_table, g.ms_bloom, g.ms_critical, g.ms_cascade, g.ms_mphf, ctx->ms_graph_build, (double)g.launches,
+                  (double)g.ref_repeated, (double)g.ref_tai,
+                  (double)ctx->scan_positions, (double)ctx->scan_valid, (double)ctx->scan_in_graph, (double)ctx->scan_table_probes,
+                  (double)ctx->scan_fallback, ctx->ms_features, ctx->ms_replay, (double)oq, (double)pb};
+    int n = std::min(cap, NSTATS);
+    for (int i = 0; i < n; i++) out[i] = v[i];
+    return n;
+}
+
+int mtg_export_solid(mtg_ctx* ctx, uint64_t* lo, uint64_t* hi, uint32_t* abundance, uint64_t capacity) {
+    MTG_TRY(ctx)
+    if (capacity < ctx->nb_solid) throw Error(-1, "export buffer too small");
+    MTG_CUDA(cudaSetDevice(ctx->p.device));
+    if (ctx->solid_owner) ctx->solid_owner->export_solid(lo, hi, abundance);
+    else {
+        for (uint64_t i = 0; i < ctx->nb_solid; i++) { lo[i] = ctx->loaded_lo[i]; if (hi) hi[i] = ctx->loaded_hi.empty() ? 0 : ctx->loaded_hi[i]; if (abundance) abundance[i] = 0; }
+    }
+    MTG_CATCH
+}
+
+int mtg_load_solid(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_t n) {
+    MTG_TRY(ctx)
+    MTG_CUDA(cudaSetDevice(ctx->p.device));
+    if (ctx->p.kmer_size > 31 && !hi) throw Error(-1, "kmer_size > 31 needs the high words");
+    ctx->graph->build_from_host(lo, hi, n);
+    ctx->graph_ready = true;
+    ctx->nb_solid = n;
+    ctx->solid_owner.reset();
+    ctx->loaded_lo.assign(lo, lo + n);
+    if (hi) ctx->loaded_hi.assign(hi, hi + n); else ctx->loaded_hi.clear();
+    MTG_CATCH
+}
+
+int mtg_set_reference(mtg_ctx* ctx, const char* bases, uint64_t nbytes) {
+    MTG_TRY(ctx)
+    MTG_CUDA(cudaSetDevice(ctx->p.device));
+    const int k1 = ctx->p.kmer_size - 1;
+    std::unique_ptr<ICounter> rc(make_counter(k1, std::min(ctx->p.minimizer_size, k1), ctx->stream, ctx->p.kmer_size <= 31 ? 64 : 128));
+    rc->push_host(bases, nbytes);
+    rc->finish(ctx->p.het_max_occ + 1, 2147483647LL);
+    ctx->ref_count_stats = rc->stats();
+    ctx->graph->set_ref_repeats(rc->solid_keys_device(), rc->nb_solid());
+    ctx->ref_repeated = rc->nb_solid();
+    MTG_CATCH
+}
+
+int mtg_contains_batch(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) {
+    MTG_TRY(ctx) MTG_CUDA(cudaSetDevice(ctx->p.device)); ctx->graph->contains_batch(lo, ctx->p.kmer_size > 31 ? hi : nullptr, n, out); MTG_CATCH
+}
+int mtg_degree_batch(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) {
+    MTG_TRY(ctx) MTG_CUDA(cudaSetDevice(ctx->p.device)); ctx->graph->degree_batch(lo, ctx->p.kmer_size > 31 ? hi : nullptr, n, out); MTG_CATCH
+}
+int mtg_ref_repeat_batch(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) {
+    MTG_TRY(ctx) MTG_CUDA(cudaSetDevice(ctx->p.device)); ctx->graph->ref_repeat_batch(lo, ctx->p.kmer_size > 31 ? hi : nullptr, n, out); MTG_CATCH
+}
+
+int mtg_sequence_features(mtg_ctx* ctx, const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint64_t* counters4) {
+    MTG_TRY(ctx) MTG_CUDA(cudaSetDevice(ctx->p.device)); ctx->graph->features_host(seq, len, feat, rep, counters4); MTG_CATCH
+}
+int mtg_sequence_features_device(mtg_ctx* ctx, const void* d_seq, uint64_t len, void* d_feat, void* d_rep, uint64_t* counters4) {
+    MTG_TRY(ctx)
+    MTG_CUDA(cudaSetDevice(ctx->p.device));
+    ctx->graph->features_device((const uint8_t*)d_seq, len, (uint8_t*)d_feat, (uint8_t*)d_rep, counters4);
+    MTG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->ms_features += ctx->graph->last_features_ms();
+    MTG_CATCH
+}
+
+int mtg_scan_reference(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len) {
+    MTG_TRY(ctx)
+    MTG_CUDA(cudaSetDevice(ctx->p.device));
+    const int k = ctx->p.kmer_size;
+    if (len < (uint64_t)k) return 0;  // reference quirk (replaying the previous sequence's k-mers) deliberately not reproduced
+    const uint64_t npos = len - k + 1;
+    if (ctx->feat.size() < npos) { ctx->feat.resize(npos); ctx->rep.resize(npos); }
+    uint64_t c4[4];
+    ctx->graph->features_host(seq, len, ctx->feat.data(), ctx->rep.data(), c4);
+    ctx->ms_features += ctx->graph->last_features_ms();
+    ctx->scan_positions += npos; ctx->scan_valid += c4[0]; ctx->scan_in_graph += c4[1]; ctx->scan_table_probes += c4[2]; ctx->scan_fallback += c4[3];
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (ctx->rp64) ctx->rp64->scan(name ? name : "", seq, len, ctx->feat.data(), ctx->rep.data());
+    else ctx->rp128->scan(name ? name : "", seq, len, ctx->feat.data(), ctx->rep.data());
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    ctx->ms_replay += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+    MTG_CATCH
+}
+
+const char* mtg_breakpoints_text(mtg_ctx* ctx, uint64_t* nbytes) {
+    const std::string& s = ctx->rp64 ? ctx->rp64->bkpt_out : ctx->rp128->bkpt_out;
+    if (nbytes) *nbytes = s.size();
+    return s.c_str();
+}
+const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes) {
+    const std::string& s = ctx->rp64 ? ctx->rp64->vcf_out : ctx->rp128->vcf_out;
+    if (nbytes) *nbytes = s.size();
+    return s.c_str();
+}
+int mtg_reset_outputs(mtg_ctx* ctx) {
+    MTG_TRY(ctx)
+    make_replayers(ctx);
+    ctx->ms_features = ctx->ms_replay = 0;
+    ctx->scan_positions = ctx->scan_valid = ctx->scan_in_graph = ctx->scan_table_probes = ctx->scan_fallback = 0;
+    MTG_CATCH
+}
+int mtg_get_find_counters(mtg_ctx* ctx, uint64_t* o) {
+    MTG_TRY(ctx)
+    const ReplayCounters& c = ctx->rp64 ? ctx->rp64->cnt : ctx->rp128->cnt;
+    o[0] = c.homo_clean; o[1] = c.homo_fuzzy; o[2] = c.hetero_clean; o[3] = c.hetero_fuzzy; o[4] = c.clean_deletion; o[5] = c.fuzzy_deletion;
+    o[6] = c.solo_snp; o[7] = c.multi_snp; o[8] = c.backup; o[9] = c.homo_indel; o[10] = c.hetero_indel; o[11] = c.observer_queries;
+    MTG_CATCH
+}
+
+int64_t mtg_copy_bits(mtg_ctx* ctx, int which, uint8_t* buf, uint64_t capacity) {
+    try {
+        if (!ctx) return -1;
+        MTG_CUDA(cudaSetDevice(ctx->p.device));
+        uint64_t n = ctx->graph->copy_bits(which, nullptr);
+        if (buf) { if (capacity < n) throw Error(-1, "buffer too small"); ctx->graph->copy_bits(which, buf); }
+        return (int64_t)n;
+    } catch (const std::exception& e) { g_last_error = e.what(); return -1; }
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ gather micro-benchmark
+__global__ void __launch_bounds__(256) gather_kernel(const uint4* __restrict__ table, uint64_t nlines, uint64_t nprobes, uint64_t seed,
+                                                     unsigned long long* __restrict__ sink) {
+    // 8 lanes cooperate on one 128-byte line: every warp instruction reads 4 complete lines
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = threadIdx.x & 7;
+    unsigned long long acc = 0;
+    for (uint64_t q = gtid >> 3; q < nprobes; q += ((uint64_t)gridDim.x * blockDim.x) >> 3) {
+        uint64_t line = mix64(q + seed) % nlines;
+        uint4 v = __ldg(table + line * 8 + sub);
+        acc += v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x123456789ull) atomicAdd(sink, acc);
+}
+
+extern "C" double mtg_bench_random_gather(int device, uint64_t table_bytes, uint64_t nprobes, int iters) {
+    try {
+        MTG_CUDA(cudaSetDevice(device));
+        uint64_t nlines = table_bytes / 128;
+        DevBuf<uint4> table(nlines * 8);
+        MTG_CUDA(cudaMemset(table.p, 0x5A, nlines * 128));
+        DevBuf<unsigned long long> sink(1);
+        sink.zero();
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        float best = 1e30f;
+        for (int it = 0; it < iters + 2; it++) {
+            cudaEventRecord(a);
+            gather_kernel<<<148 * 16, 256>>>(table.p, nlines, nprobes, 0x1234567ull * (it + 1), sink.p);
+            cudaEventRecord(b);
+            MTG_CUDA(cudaEventSynchronize(b));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, a, b);
+            if (it >= 2 && ms < best) best = ms;
+        }
+        cudaEventDestroy(a); cudaEventDestroy(b);
+        return (double)nprobes * 128.0 / (best * 1e-3) / 1e9;
+    } catch (const std::exception& e) { g_last_error = e.what(); return -1.0; }
+}

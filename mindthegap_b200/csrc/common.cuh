@@ -1,0 +1,179 @@
+// mtg-b200: common device/host helpers. k-mer arithmetic follows GATB's definitions:
+//   base code A=0 C=1 T=2 G=3 = (ascii>>1)&3           (gatb-core tools/misc/api/Data.hpp:178)
+//   k-mer value = base-4 polynomial, first base most significant (kmer/impl/Model.hpp:637-657)
+//   revcomp / canonical=min(fwd,rc)                      (tools/math/LargeInt1.pri:137-155, Model.hpp:294)
+// Key type K is uint64_t for k<=31 and unsigned __int128 for 32<=k<=63 (native ATOMS/ATOMG.CAS.128 on sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace mtg {
+
+typedef unsigned __int128 u128;
+
+#define MTG_HD __host__ __device__ __forceinline__
+#define MTG_D __device__ __forceinline__
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define MTG_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            throw mtg::Error(-2, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " __FILE__ ":" + \
+                                     std::to_string(__LINE__));                                          \
+    } while (0)
+
+// Simple owning device buffer.
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t n_) { alloc(n_); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        if (n) MTG_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+    }
+    void zero(cudaStream_t s = 0) { if (n) MTG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void fill_ff(cudaStream_t s = 0) { if (n) MTG_CUDA(cudaMemsetAsync(p, 0xFF, n * sizeof(T), s)); }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// ----------------------------------------------------------------------------------------------- k-mer arithmetic
+template <class K> MTG_HD K kmask(int k) { return (K(1) << (2 * k)) - K(1); }
+
+MTG_HD uint64_t rc_word(uint64_t x) {  // reverse-complement of a full 32-nt word
+#ifdef __CUDA_ARCH__
+    x = __brevll(x);
+    x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+#else
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+    x = (x >> 32) | (x << 32);
+#endif
+    return x ^ 0xAAAAAAAAAAAAAAAAULL;
+}
+MTG_HD uint64_t revcomp(uint64_t x, int k) { return rc_word(x) >> (2 * (32 - k)); }
+MTG_HD u128 revcomp(u128 x, int k) {
+    u128 r = ((u128)rc_word((uint64_t)x) << 64) | (u128)rc_word((uint64_t)(x >> 64));
+    return r >> (2 * (64 - k));
+}
+template <class K> MTG_HD K canonical(K x, int k) { K r = revcomp(x, k); return r < x ? r : x; }
+
+MTG_HD uint64_t lo64(uint64_t x) { return x; }
+MTG_HD uint64_t hi64(uint64_t) { return 0; }
+MTG_HD uint64_t lo64(u128 x) { return (uint64_t)x; }
+MTG_HD uint64_t hi64(u128 x) { return (uint64_t)(x >> 64); }
+template <class K> MTG_HD K make_key(uint64_t lo, uint64_t hi);
+template <> MTG_HD uint64_t make_key<uint64_t>(uint64_t lo, uint64_t) { return lo; }
+template <> MTG_HD u128 make_key<u128>(uint64_t lo, uint64_t hi) { return ((u128)hi << 64) | lo; }
+
+// GATB hash1 (LargeInt1.pri:158-171); multi-word keys xor the word hashes (LargeInt.hpp:738-748)
+MTG_HD uint64_t gatb_hash64(uint64_t key, uint64_t seed) {
+    uint64_t hash = seed;
+    hash ^= (hash << 7) ^ key * (hash >> 3) ^ (~((hash << 11) + (key ^ (hash >> 5))));
+    hash = (~hash) + (hash << 21);
+    hash = hash ^ (hash >> 24);
+    hash = (hash + (hash << 3)) + (hash << 8);
+    hash = hash ^ (hash >> 14);
+    hash = (hash + (hash << 2)) + (hash << 4);
+    hash = hash ^ (hash >> 28);
+    hash = hash + (hash << 31);
+    return hash;
+}
+MTG_HD uint64_t gatb_hash1(uint64_t key, uint64_t seed) { return gatb_hash64(key, seed); }
+MTG_HD uint64_t gatb_hash1(u128 key, uint64_t seed) { return gatb_hash64((uint64_t)key, seed) ^ gatb_hash64((uint64_t)(key >> 64), seed); }
+
+// Our own mixing hash (not GATB's): murmur3 finaliser, used for table slots / buckets / pass selection.
+MTG_HD uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+MTG_HD uint64_t key_hash(uint64_t k) { return mix64(k); }
+MTG_HD uint64_t key_hash(u128 k) { return mix64((uint64_t)k ^ mix64((uint64_t)(k >> 64) + 0x9E3779B97F4A7C15ULL)); }
+
+// ----------------------------------------------------------------------------------------------- atomics
+MTG_D uint64_t cas_global(uint64_t* a, uint64_t cmp, uint64_t val) {
+    return (uint64_t)atomicCAS((unsigned long long*)a, (unsigned long long)cmp, (unsigned long long)val);
+}
+MTG_D u128 cas_global(u128* addr, u128 cmp, u128 val) {
+    uint64_t clo = (uint64_t)cmp, chi = (uint64_t)(cmp >> 64), vlo = (uint64_t)val, vhi = (uint64_t)(val >> 64), olo, ohi;
+    asm volatile(
+        "{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%3, %4};\n\tmov.b128 v, {%5, %6};\n\t"
+        "atom.global.cas.b128 o, [%2], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(olo), "=l"(ohi) : "l"(addr), "l"(clo), "l"(chi), "l"(vlo), "l"(vhi) : "memory");
+    return ((u128)ohi << 64) | olo;
+}
+MTG_D uint64_t cas_shared(uint64_t* a, uint64_t cmp, uint64_t val) {
+    return (uint64_t)atomicCAS((unsigned long long*)a, (unsigned long long)cmp, (unsigned long long)val);
+}
+MTG_D u128 cas_shared(u128* addr, u128 cmp, u128 val) {
+    uint64_t clo = (uint64_t)cmp, chi = (uint64_t)(cmp >> 64), vlo = (uint64_t)val, vhi = (uint64_t)(val >> 64), olo, ohi;
+    uint32_t sa = (uint32_t)__cvta_generic_to_shared(addr);
+    asm volatile(
+        "{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%3, %4};\n\tmov.b128 v, {%5, %6};\n\t"
+        "atom.shared.cas.b128 o, [%2], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(olo), "=l"(ohi) : "r"(sa), "l"(clo), "l"(chi), "l"(vlo), "l"(vhi) : "memory");
+    return ((u128)ohi << 64) | olo;
+}
+
+// Extract `nb` (<=32) bases starting at base position `pos` from the 2-bit packed array (32 bases per word, first
+// base in the two most significant bits). Result is right-aligned.
+MTG_D uint64_t extract_bases64(const uint64_t* __restrict__ packed, uint64_t pos, int nb) {
+    uint64_t a = pos >> 5;
+    int off = (int)(pos & 31) * 2;
+    uint64_t w0 = packed[a];
+    uint64_t x = w0 << off;
+    if (off) x |= packed[a + 1] >> (64 - off);
+    return x >> (64 - 2 * nb);
+}
+template <class K> MTG_D K extract_kmer(const uint64_t* __restrict__ packed, uint64_t pos, int k);
+template <> MTG_D uint64_t extract_kmer<uint64_t>(const uint64_t* __restrict__ packed, uint64_t pos, int k) {
+    return extract_bases64(packed, pos, k);
+}
+template <> MTG_D u128 extract_kmer<u128>(const uint64_t* __restrict__ packed, uint64_t pos, int k) {
+    uint64_t a = pos >> 5;
+    int off = (int)(pos & 31) * 2;
+    u128 x = (((u128)packed[a] << 64) | packed[a + 1]) << off;
+    if (off) x |= (u128)(packed[a + 2] >> (64 - off));
+    return x >> (128 - 2 * k);
+}
+
+// Sequential base reader over the packed array.
+struct BaseStream {
+    const uint64_t* __restrict__ p;
+    uint64_t widx, cur;
+    int left;
+    MTG_D void init(const uint64_t* __restrict__ packed, uint64_t pos) {
+        p = packed; widx = pos >> 5;
+        int o = (int)(pos & 31);
+        cur = packed[widx] << (2 * o);
+        left = 32 - o;
+    }
+    MTG_D unsigned next() {
+        if (left == 0) { cur = p[++widx]; left = 32; }
+        unsigned c = (unsigned)(cur >> 62);
+        cur <<= 2; left--;
+        return c;
+    }
+};
+
+static inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace mtg

@@ -1,0 +1,692 @@
+// mtg-b200 stage 1 kernels (hand-written CUDA for sm_100a; integer work, HBM / shared-memory bound, no tensor cores).
+//
+// Pipeline per batch of reads (ASCII bases, reads separated by any invalid byte):
+//   pack_kernel      : ASCII -> 2 bit/base words + 1 bit/base invalid mask          (Data.hpp:178 coding)
+//   superkmer_kernel : per position: minimizer of the k-mer window (GATB rule, Model.hpp:1040-1064,1220-1287) by a
+//                      shared-memory sliding minimum, window validity (Model.hpp:752-758), segmentation into
+//                      super-k-mers (Sequence2SuperKmer.hpp:83-147) -> 8-byte records {pos,len,minimizer} and a
+//                      histogram of k-mers per minimizer (the role of RepartitorAlgorithm, PartiInfo.cpp:40-86)
+// At finish():
+//   host grouping    : minimizer bins -> groups that fit one shared-memory table (Repartitor::computeDistrib role)
+//   scatter_kernel   : records -> contiguous per-group lists                       (FillPartitions role)
+//   count_kernel     : one CTA per group: expand super-k-mers from the packed bases by rolling fwd/revcomp,
+//                      canonical k-mers inserted in a shared-memory open-addressing table with ATOMS.CAS.64/128,
+//                      then the table is swept: abundance histogram + candidates with abundance >= floor
+//   filter_kernel    : candidates -> solid set at the final threshold (CountProcessorSolidity role)
+#include <algorithm>
+#include <cstring>
+
+#include "count.cuh"
+
+namespace mtg {
+
+// ------------------------------------------------------------------------------------------------------------
+int compute_auto_cutoff(const uint64_t* a, int min_auto_threshold) {
+    const size_t L = HISTO_MAX;
+    std::vector<uint64_t> sm(L + 1, 0);
+    uint64_t sum_allk = 0;
+    uint16_t cutoff = 0;
+    if (L >= 2) {
+        sm[1] = (uint64_t)(0.6 * (double)a[1] + 0.4 * (double)a[2]);
+        sum_allk += a[1] * 1;
+    }
+    int index_first_increase = -1, index_maxval = -1;
+    uint64_t max_val = 0;
+    for (size_t i = 2; i < L; i++) {
+        sum_allk += a[i] * i;
+        sm[i] = (uint64_t)(0.2 * (double)a[i - 1] + 0.6 * (double)a[i] + 0.2 * (double)a[i + 1]);
+        if (index_first_increase == -1 && sm[i - 1] < sm[i]) index_first_increase = (int)i - 1;
+        if (index_first_increase > 0 && sm[i] > max_val) { max_val = sm[i]; index_maxval = (int)i; }
+    }
+    sum_allk += a[L] * L;
+    if (index_first_increase == -1) return min_auto_threshold;
+    uint64_t min_val = 10000000000ULL;
+    int index_minval = -1;
+    for (int i = index_first_increase; i <= index_maxval; i++)
+        if (sm[i] < min_val) { min_val = sm[i]; index_minval = i; }
+    if (index_minval != -1) cutoff = (uint16_t)index_minval;
+    uint64_t sum_elim = 0;
+    int max_cutoff = 0;
+    for (size_t i = 0; i < L + 1; i++) {
+        sum_elim += a[i] * i;
+        double ratio = (double)sum_elim / sum_allk;
+        if (ratio >= 0.25) { max_cutoff = (int)i + 1; break; }
+    }
+    if (cutoff > max_cutoff) cutoff = (uint16_t)max_cutoff;
+    if (cutoff < min_auto_threshold) cutoff = (uint16_t)min_auto_threshold;
+    return cutoff;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pack: one thread per 32 bases -> one u64 (2 bit/base, first base in the top bits) + one u32 invalid mask
+// (first base = bit 31). Vectorised 128-bit loads when the input pointer is 16-byte aligned.
+// ------------------------------------------------------------------------------------------------------------
+MTG_D void pack4(uint32_t x, uint32_t& code8, uint32_t& inv4) {
+    uint32_t t = (x >> 1) & 0x03030303u;
+    code8 = ((t << 6) | (t >> 4) | (t >> 14) | (t >> 24)) & 0xFFu;
+    uint32_t u = x & 0xDFDFDFDFu;
+    uint32_t v = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+    uint32_t m = (~v) & 0x01010101u;
+    inv4 = ((m << 3) | (m >> 6) | (m >> 15) | (m >> 24)) & 0xFu;
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ packed,
+                                                   uint32_t* __restrict__ inv, uint64_t nwords, int aligned16) {
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t base = w * 32;
+        uint64_t pw = 0;
+        uint32_t iw = 0;
+        if (aligned16 && base + 32 <= n) {
+            const uint4* q = reinterpret_cast<const uint4*>(in + base);
+            uint4 a = __ldg(q), b = __ldg(q + 1);
+            uint32_t xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t c8, i4;
+                pack4(xs[j], c8, i4);
+                pw = (pw << 8) | c8;
+                iw = (iw << 4) | i4;
+            }
+        } else {
+            for (int j = 0; j < 32; j++) {
+                uint32_t c = base + j < n ? in[base + j] : (uint32_t)'\n';
+                uint32_t u = c & 0xDFu;
+                bool valid = (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T');
+                pw = (pw << 2) | ((c >> 1) & 3u);
+                iw = (iw << 1) | (valid ? 0u : 1u);
+            }
+        }
+        packed[w] = pw;
+        inv[w] = iw;
+    }
+}
+
+void launch_pack(const uint8_t* d_in, uint64_t n, uint64_t* d_packed, uint32_t* d_inv, uint64_t nwords, cudaStream_t stream) {
+    if (!nwords) return;
+    int aligned = ((uintptr_t)d_in & 15) == 0;
+    int grid = (int)std::min<uint64_t>((nwords + 255) / 256, 148ull * 16);
+    pack_kernel<<<grid, 256, 0, stream>>>(d_in, n, d_packed, d_inv, nwords, aligned);
+    MTG_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// super-k-mer extraction
+// ------------------------------------------------------------------------------------------------------------
+static const int SK_TILE = 2048;      // positions per CTA tile
+static const int SK_THREADS = 256;
+static const int SK_NV = SK_TILE + 64;
+static const int SK_MAXRUN = 32;      // max k-mers per record (6-bit length field holds up to 64)
+static const int REC_POS_SHIFT = 26, REC_LEN_SHIFT = 20;
+static const int MH_REC_SHIFT = 36;   // minimizer histogram word: nrec << 36 | nkmers
+
+MTG_HD uint64_t make_record(uint64_t pos, uint32_t len, uint32_t mini) {
+    return (pos << REC_POS_SHIFT) | ((uint64_t)(len - 1) << REC_LEN_SHIFT) | mini;
+}
+
+// LUT value of an m-mer (Model.hpp:1040-1064 + is_allowed :1220-1251), computed arithmetically.
+MTG_D uint32_t mmer_value(uint32_t mm, int m, uint32_t mmask, uint32_t mask_ma1) {
+    uint32_t r = __brev(mm) >> (32 - 2 * m);
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+    r = (r ^ 0xAAAAAAAAu) & mmask;
+    uint32_t c = min(mm, r);
+    uint32_t a1 = ~(c | (c >> 2));
+    a1 = ((a1 >> 1) & a1) & mask_ma1;
+    return a1 ? mmask : c;
+}
+
+// Window [p, p+k) contains no invalid base? `si` = invalid-mask words of the tile (first base = bit 31).
+MTG_D bool window_valid(const uint32_t* si, int p, int k) {
+    int a = p >> 5, o = p & 31;
+    uint32_t x0 = si[a], x1 = si[a + 1], x2 = si[a + 2];
+    uint32_t y0 = __funnelshift_l(x1, x0, o), y1 = __funnelshift_l(x2, x1, o);
+    if (k <= 32) return (y0 >> (32 - k)) == 0;
+    return y0 == 0 && (y1 >> (64 - k)) == 0;
+}
+
+__global__ void __launch_bounds__(SK_THREADS)
+superkmer_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ inv, uint64_t word_begin, uint64_t nwords,
+                 int k, int m, uint64_t* __restrict__ records, unsigned long long* __restrict__ nrec_global, uint64_t rec_capacity,
+                 unsigned long long* __restrict__ mhist, unsigned long long* __restrict__ nvalid_global, int* __restrict__ overflow) {
+    __shared__ uint64_t sw[SK_TILE / 32 + 4];
+    __shared__ uint32_t si[SK_TILE / 32 + 4];
+    __shared__ uint32_t va[SK_NV], vb[SK_NV];
+    __shared__ uint32_t s_brk[SK_TILE / 32], s_vld[SK_TILE / 32];
+    __shared__ uint64_t stage[SK_TILE];
+    __shared__ uint32_t s_nstage, s_nvalid, s_anyinv;
+    __shared__ unsigned long long s_gbase;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int W = k - m + 1;
+    const uint32_t mmask = (uint32_t)((1ull << (2 * m)) - 1);
+    const uint32_t mask_ma1 = 0x55555555u & (uint32_t)((1ull << (2 * (m - 2))) - 1);
+    const uint64_t ntiles = (nwords + SK_TILE / 32 - 1) / (SK_TILE / 32);
+
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t w0 = word_begin + tile * (SK_TILE / 32);
+        const int tile_words = (int)min((uint64_t)(SK_TILE / 32), word_begin + nwords - w0);
+        const int tile_pos = tile_words * 32;
+        if (tid == 0) { s_nstage = 0; s_nvalid = 0; s_anyinv = 0; }
+        __syncthreads();
+        // ---- phase 1: stage packed words + invalid masks (arrays are padded with >= 4 all-invalid words)
+        for (int i = tid; i < SK_TILE / 32 + 4; i += SK_THREADS) {
+            bool in = i < tile_words + 4;
+            uint64_t w = in ? packed[w0 + i] : 0;
+            uint32_t iv = in ? inv[w0 + i] : 0xFFFFFFFFu;
+            sw[i] = w; si[i] = iv;
+            if (iv && i < tile_words + 2) s_anyinv = 1;
+        }
+        __syncthreads();
+        const bool anyinv = s_anyinv != 0;
+        // ---- phase 2: LUT value of the m-mer starting at every position (tile + halo)
+        for (int p = tid; p < SK_NV; p += SK_THREADS) {
+            uint32_t v = 0xFFFFFFFFu;
+            if (p < tile_pos + W - 1) {
+                int a = p >> 5, off = 2 * (p & 31);
+                uint64_t x = sw[a] << off;
+                if (off) x |= sw[a + 1] >> (64 - off);
+                v = mmer_value((uint32_t)(x >> (64 - 2 * m)), m, mmask, mask_ma1);
+            }
+            va[p] = v;
+        }
+        __syncthreads();
+        // ---- phase 3: sliding minimum over W consecutive m-mers by doubling (sparse-table) passes
+        uint32_t* src = va;
+        uint32_t* dst = vb;
+        int pw = 1;
+        while (2 * pw <= W) {
+            for (int p = tid; p < SK_NV; p += SK_THREADS) dst[p] = min(src[p], src[min(p + pw, SK_NV - 1)]);
+            __syncthreads();
+            uint32_t* t = src; src = dst; dst = t;
+            pw *= 2;
+        }
+        // minimizer of window p = min(src[p], src[p + W - pw]); written to dst
+        uint32_t mini[SK_TILE / SK_THREADS];
+        bool valid[SK_TILE / SK_THREADS];
+#pragma unroll
+        for (int i = 0; i < SK_TILE / SK_THREADS; i++) {
+            int p = i * SK_THREADS + tid;
+            mini[i] = min(src[p], src[p + W - pw]);
+            valid[i] = p < tile_pos && (!anyinv || window_valid(si, p, k));
+            dst[p] = mini[i];
+            uint32_t b = __ballot_sync(0xFFFFFFFFu, valid[i]);
+            if (lane == 0) { s_vld[p >> 5] = __brev(b); if (b) atomicAdd(&s_nvalid, __popc(b)); }  // position p at bit 31-(p&31)
+        }
+        __syncthreads();
+        // ---- phase 4: break flags (new super-k-mer starts here, or position invalid)
+#pragma unroll
+        for (int i = 0; i < SK_TILE / SK_THREADS; i++) {
+            int p = i * SK_THREADS + tid;
+            bool prev_valid = p > 0 && ((s_vld[(p - 1) >> 5] >> (31 - ((p - 1) & 31))) & 1);
+            bool brk = !valid[i] || !prev_valid || dst[p - (p > 0)] != mini[i];
+            uint32_t b = __ballot_sync(0xFFFFFFFFu, brk);
+            if (lane == 0) s_brk[p >> 5] = __brev(b);  // store with position p at bit 31-(p&31)
+        }
+        __syncthreads();
+        // ---- phase 5: run starts emit records into the staging buffer
+#pragma unroll
+        for (int i = 0; i < SK_TILE / SK_THREADS; i++) {
+            int p = i * SK_THREADS + tid;
+            bool is_start = valid[i] && ((s_brk[p >> 5] >> (31 - (p & 31))) & 1);
+            if (is_start) {
+                // next break strictly after p
+                int q = p + 1, wq = q >> 5;
+                int end = tile_pos;
+                if (q < tile_pos) {
+                    uint32_t bits = s_brk[wq] & (0xFFFFFFFFu >> (q & 31));
+                    while (true) {
+                        if (bits) { end = wq * 32 + __clz(bits); break; }
+                        wq++;
+                        if (wq * 32 >= tile_pos) break;
+                        bits = s_brk[wq];
+                    }
+                    if (end > tile_pos) end = tile_pos;
+                }
+                int len = end - p;
+                int nrec = (len + SK_MAXRUN - 1) / SK_MAXRUN;
+                uint32_t slot = atomicAdd(&s_nstage, (uint32_t)nrec);
+                uint64_t gpos = (w0 - 0) * 32 + p;
+                for (int o = 0; o < len; o += SK_MAXRUN) stage[slot++] = make_record(gpos + o, (uint32_t)min(SK_MAXRUN, len - o), mini[i]);
+            }
+        }
+        __syncthreads();
+        // ---- phase 6: publish
+        const uint32_t ns = s_nstage;
+        if (tid == 0) {
+            s_gbase = atomicAdd(nrec_global, (unsigned long long)ns);
+            if (s_nvalid) atomicAdd(nvalid_global, (unsigned long long)s_nvalid);
+        }
+        __syncthreads();
+        const unsigned long long gbase = s_gbase;
+        if (gbase + ns > rec_capacity) {
+            if (tid == 0) *overflow = 1;
+        } else {
+            for (uint32_t i = tid; i < ns; i += SK_THREADS) {
+                uint64_t r = stage[i];
+                records[gbase + i] = r;
+                uint32_t len = (uint32_t)((r >> REC_LEN_SHIFT) & 63) + 1;
+                atomicAdd(&mhist[r & ((1u << REC_LEN_SHIFT) - 1)], (1ull << MH_REC_SHIFT) | len);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scatter_kernel(const uint64_t* __restrict__ records, uint64_t nrec, const uint32_t* __restrict__ group_of,
+                                                      const uint64_t* __restrict__ group_off, unsigned int* __restrict__ group_cur,
+                                                      uint64_t* __restrict__ grouped) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t r = records[i];
+        uint32_t g = group_of[r & ((1u << REC_LEN_SHIFT) - 1)];
+        unsigned int slot = atomicAdd(&group_cur[g], 1u);
+        grouped[group_off[g] + slot] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// count kernel
+// ------------------------------------------------------------------------------------------------------------
+struct WorkItem { uint64_t rec_off; uint32_t nrec; uint16_t pass, npass; };
+
+// Read-or-claim one table slot. 64-bit slots are read with a plain (atomic) 8-byte load first; 128-bit slots always go
+// through ATOMS.CAS.128 so that a concurrent claim can never be observed half-written.
+MTG_D uint64_t slot_claim(uint64_t* slot, uint64_t key) {
+    uint64_t cur = *(volatile uint64_t*)slot;
+    if (cur == ~0ull) cur = cas_shared(slot, ~0ull, key);
+    return cur;
+}
+MTG_D u128 slot_claim(u128* slot, u128 key) { return cas_shared(slot, ~(u128)0, key); }
+
+template <class K> struct CountCfg;
+template <> struct CountCfg<uint64_t> { static const int SLOTS = 8192; };
+template <> struct CountCfg<u128> { static const int SLOTS = 4096; };
+static const int COUNT_THREADS = 512;
+static const int SMEM_HIST = 256;
+
+template <class K>
+__global__ void __launch_bounds__(COUNT_THREADS, 2)
+count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ grouped, const WorkItem* __restrict__ items, uint32_t nitems,
+             unsigned int* __restrict__ item_counter, int k, uint32_t emit_min, unsigned long long* __restrict__ histo,
+             K* __restrict__ cand_keys, uint32_t* __restrict__ cand_cnt, unsigned long long* __restrict__ ncand, uint64_t cand_capacity,
+             int* __restrict__ errflag) {
+    const int S = CountCfg<K>::SLOTS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K* keys = reinterpret_cast<K*>(smem_raw);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * S);
+    uint32_t* hist_s = cnt + S;
+    __shared__ uint32_t s_item;
+    const K EMPTY = ~K(0);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const K mask = kmask<K>(k);
+    const int rcshift = 2 * (k - 1);
+
+    while (true) {
+        if (tid == 0) s_item = atomicAdd(item_counter, 1u);
+        for (int s = tid; s < S; s += COUNT_THREADS) { keys[s] = EMPTY; cnt[s] = 0; }
+        if (tid < SMEM_HIST) hist_s[tid] = 0;
+        __syncthreads();
+        const uint32_t it = s_item;
+        if (it >= nitems) break;
+        const WorkItem wi = items[it];
+        const uint64_t* recs = grouped + wi.rec_off;
+        // ---- insert
+        for (uint32_t ri = tid; ri < wi.nrec; ri += COUNT_THREADS) {
+            const uint64_t r = recs[ri];
+            const uint64_t pos = r >> REC_POS_SHIFT;
+            const int len = (int)((r >> REC_LEN_SHIFT) & 63) + 1;
+            K fwd = extract_kmer<K>(packed, pos, k);
+            K rc = revcomp(fwd, k);
+            BaseStream bs;
+            bs.init(packed, pos + k);
+            for (int j = 0; j < len; j++) {
+                if (j) {
+                    unsigned c = bs.next();
+                    fwd = ((fwd << 2) | (K)c) & mask;
+                    rc = (rc >> 2) | ((K)(c ^ 2u) << rcshift);
+                }
+                const K key = fwd < rc ? fwd : rc;
+                const uint64_t h = key_hash(key);
+                if (wi.npass > 1 && (uint32_t)((h >> 32) % wi.npass) != wi.pass) continue;
+                uint32_t slot = (uint32_t)h & (S - 1);
+                int probes = 0;
+                while (true) {
+                    const K cur = slot_claim(&keys[slot], key);
+                    if (cur == EMPTY || cur == key) { atomicAdd(&cnt[slot], 1u); break; }
+                    slot = (slot + 1) & (S - 1);
+                    if (++probes >= S) { *errflag = 1; break; }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- sweep: histogram (Histogram::inc takes a u16: CountProcessorHistogram.hpp:174-185, Histogram.hpp:92)
+        for (int s = tid; s < S; s += COUNT_THREADS) {
+            const K key = keys[s];
+            const bool occ = key != EMPTY;
+            uint32_t c = occ ? cnt[s] : 0;
+            if (occ) {
+                uint32_t hidx = c & 0xFFFFu;
+                if (hidx > HISTO_MAX) hidx = HISTO_MAX;
+                if (hidx < SMEM_HIST) atomicAdd(&hist_s[hidx], 1u); else atomicAdd(&histo[hidx], 1ull);
+            }
+            const bool emit = occ && c >= emit_min;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, emit);
+            if (b) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(ncand, (unsigned long long)__popc(b));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (emit) {
+                    unsigned long long o = base + __popc(b & ((1u << lane) - 1));
+                    if (o < cand_capacity) { cand_keys[o] = key; cand_cnt[o] = c; } else *errflag = 2;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < SMEM_HIST && hist_s[tid]) atomicAdd(&histo[tid], (unsigned long long)hist_s[tid]);
+        __syncthreads();
+    }
+}
+
+template <class K>
+__global__ void __launch_bounds__(256) filter_kernel(const K* __restrict__ cand_keys, const uint32_t* __restrict__ cand_cnt, uint64_t ncand,
+                                                     uint32_t amin, uint32_t amax, K* __restrict__ out_keys, uint32_t* __restrict__ out_cnt,
+                                                     unsigned long long* __restrict__ nout) {
+    const int lane = threadIdx.x & 31;
+    uint64_t n_round = (ncand + 31) / 32 * 32;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t c = i < ncand ? cand_cnt[i] : 0;
+        bool keep = i < ncand && c >= amin && c <= amax;
+        uint32_t b = __ballot_sync(0xFFFFFFFFu, keep);
+        if (b) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(nout, (unsigned long long)__popc(b));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (keep) {
+                unsigned long long o = base + __popc(b & ((1u << lane) - 1));
+                out_keys[o] = cand_keys[i];
+                out_cnt[o] = c;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+struct EventTimer {
+    cudaEvent_t a, b;
+    cudaStream_t s;
+    explicit EventTimer(cudaStream_t s_) : s(s_) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EventTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, s); }
+    float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+template <class K> class Counter : public ICounter {
+    int k_, m_;
+    cudaStream_t stream_;
+    int sm_count_ = 148;
+    // resident packed input
+    DevBuf<uint64_t> packed_;
+    DevBuf<uint32_t> inv_;
+    uint64_t words_used_ = 0, words_cap_ = 0;
+    static const uint64_t PAD_WORDS = 8;
+    DevBuf<uint8_t> staging_;
+    // records per batch
+    struct Batch { DevBuf<uint64_t> recs; uint64_t nrec = 0; };
+    std::vector<Batch> batches_;
+    DevBuf<unsigned long long> mhist_, mh_backup_;
+    DevBuf<unsigned long long> counters_;  // [0] nrec (per batch, reset), [1] nvalid, [2] ncand, [3] nsolid
+    DevBuf<int> flags_;                    // [0] record overflow, [1] count error
+    // results
+    DevBuf<K> solid_keys_;
+    DevBuf<uint32_t> solid_cnt_;
+    uint64_t nb_solid_ = 0;
+    std::vector<uint64_t> histo_;
+    CountStats st_;
+
+    void ensure_words(uint64_t need) {
+        if (need + PAD_WORDS <= words_cap_) return;
+        uint64_t ncap = std::max<uint64_t>(need + PAD_WORDS, words_cap_ * 2);
+        DevBuf<uint64_t> np(ncap);
+        DevBuf<uint32_t> ni(ncap);
+        MTG_CUDA(cudaMemsetAsync(np.p, 0, ncap * 8, stream_));
+        MTG_CUDA(cudaMemsetAsync(ni.p, 0xFF, ncap * 4, stream_));
+        if (words_used_) {
+            MTG_CUDA(cudaMemcpyAsync(np.p, packed_.p, words_used_ * 8, cudaMemcpyDeviceToDevice, stream_));
+            MTG_CUDA(cudaMemcpyAsync(ni.p, inv_.p, words_used_ * 4, cudaMemcpyDeviceToDevice, stream_));
+        }
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        packed_ = std::move(np);
+        inv_ = std::move(ni);
+        words_cap_ = ncap;
+    }
+
+public:
+    Counter(int k, int m, cudaStream_t s) : k_(k), m_(m), stream_(s), histo_(HISTO_MAX + 1, 0) {
+        if (m_ > k_) m_ = k_;
+        if (m_ > 10) m_ = 10;
+        if (m_ < 3) throw Error(-1, "minimizer size must be >= 3");
+        int dev = 0;
+        MTG_CUDA(cudaGetDevice(&dev));
+        MTG_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev));
+        mhist_.alloc((size_t)1 << (2 * m_));
+        mhist_.zero(stream_);
+        counters_.alloc(8);
+        counters_.zero(stream_);
+        flags_.alloc(4);
+        flags_.zero(stream_);
+        const int smem = (int)(sizeof(K) + 4) * CountCfg<K>::SLOTS + SMEM_HIST * 4;
+        MTG_CUDA(cudaFuncSetAttribute(count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    cudaStream_t stream() const override { return stream_; }
+    void reserve(uint64_t nb_bases) override { ensure_words(words_used_ + nb_bases / 32 + 2); }
+
+    void push_host(const char* bases, uint64_t n) override {
+        if (!n) return;
+        if (staging_.n < n + 64) staging_.alloc(n + 64);
+        MTG_CUDA(cudaMemcpyAsync(staging_.p, bases, n, cudaMemcpyHostToDevice, stream_));
+        push_device(staging_.p, n);
+    }
+
+    void push_device(const uint8_t* d_bases, uint64_t n) override {
+        if (!n) return;
+        const uint64_t nwords = (n + 31) / 32;
+        ensure_words(words_used_ + nwords);
+        EventTimer t(stream_);
+        t.start();
+        int aligned = ((uintptr_t)d_bases & 15) == 0;
+        int grid = std::min<uint64_t>((nwords + 255) / 256, (uint64_t)sm_count_ * 16);
+        pack_kernel<<<grid, 256, 0, stream_>>>(d_bases, n, packed_.p + words_used_, inv_.p + words_used_, nwords, aligned);
+        MTG_CUDA(cudaGetLastError());
+        st_.ms_pack += t.stop();
+        st_.launches++;
+        // records: typical ~ n/8; start with n/4 + slack, retry with n on overflow
+        uint64_t cap = n / 4 + 4096;
+        unsigned long long nvalid_before = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            Batch b;
+            b.recs.alloc(cap);
+            MTG_CUDA(cudaMemsetAsync(counters_.p, 0, sizeof(unsigned long long), stream_));
+            MTG_CUDA(cudaMemsetAsync(flags_.p, 0, sizeof(int), stream_));
+            if (attempt == 0) {  // keep a copy so that a retry does not double count
+                if (!mh_backup_.n) mh_backup_.alloc(mhist_.n);
+                MTG_CUDA(cudaMemcpyAsync(mh_backup_.p, mhist_.p, mhist_.bytes(), cudaMemcpyDeviceToDevice, stream_));
+                MTG_CUDA(cudaMemcpyAsync(&nvalid_before, counters_.p + 1, 8, cudaMemcpyDeviceToHost, stream_));
+            }
+            t.start();
+            uint64_t ntiles = (nwords + SK_TILE / 32 - 1) / (SK_TILE / 32);
+            int g2 = (int)std::min<uint64_t>(ntiles, (uint64_t)sm_count_ * 8);
+            superkmer_kernel<<<g2, SK_THREADS, 0, stream_>>>(packed_.p, inv_.p, words_used_, nwords, k_, m_, b.recs.p, counters_.p, cap,
+                                                              mhist_.p, counters_.p + 1, flags_.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.ms_extract += t.stop();
+            st_.launches++;
+            int ovf = 0;
+            unsigned long long nrec = 0;
+            MTG_CUDA(cudaMemcpyAsync(&ovf, flags_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaMemcpyAsync(&nrec, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaStreamSynchronize(stream_));
+            if (!ovf) {
+                b.nrec = nrec;
+                st_.nb_records += nrec;
+                batches_.push_back(std::move(b));
+                break;
+            }
+            if (attempt == 1) throw Error(-3, "super-k-mer record buffer overflow");
+            // restore and retry with worst-case capacity
+            MTG_CUDA(cudaMemcpyAsync(mhist_.p, mh_backup_.p, mhist_.bytes(), cudaMemcpyDeviceToDevice, stream_));
+            MTG_CUDA(cudaMemcpyAsync(counters_.p + 1, &nvalid_before, 8, cudaMemcpyHostToDevice, stream_));
+            MTG_CUDA(cudaStreamSynchronize(stream_));
+            cap = n + 4096;
+        }
+        words_used_ += nwords;
+        st_.nb_bases += n;
+    }
+
+    void finish(int abundance_min, int64_t abundance_max) override {
+        const int S = CountCfg<K>::SLOTS;
+        const uint64_t target = S / 2;
+        EventTimer t(stream_);
+        // ---- grouping of minimizer bins (host; 4^m entries)
+        t.start();
+        const size_t NM = mhist_.n;
+        std::vector<unsigned long long> mh(NM);
+        MTG_CUDA(cudaMemcpyAsync(mh.data(), mhist_.p, NM * 8, cudaMemcpyDeviceToHost, stream_));
+        unsigned long long nvalid = 0;
+        MTG_CUDA(cudaMemcpyAsync(&nvalid, counters_.p + 1, 8, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        st_.nb_valid_kmers = nvalid;
+        std::vector<uint32_t> group_of(NM, 0);
+        struct G { uint64_t nrec, nk; };
+        std::vector<G> groups;
+        {
+            uint64_t cur_k = 0, cur_r = 0;
+            bool open = false;
+            for (size_t v = 0; v < NM; v++) {
+                uint64_t nk = mh[v] & ((1ull << MH_REC_SHIFT) - 1), nr = mh[v] >> MH_REC_SHIFT;
+                if (!nr) { group_of[v] = open ? (uint32_t)groups.size() : (uint32_t)groups.size(); continue; }
+                if (open && cur_k + nk > target) { groups.push_back({cur_r, cur_k}); open = false; cur_k = cur_r = 0; }
+                group_of[v] = (uint32_t)groups.size();
+                open = true;
+                cur_k += nk; cur_r += nr;
+            }
+            if (open) groups.push_back({cur_r, cur_k});
+        }
+        const size_t NG = groups.size();
+        std::vector<uint64_t> goff(NG + 1, 0);
+        for (size_t g = 0; g < NG; g++) goff[g + 1] = goff[g] + groups[g].nrec;
+        const uint64_t total_rec = goff[NG];
+        std::vector<WorkItem> items;
+        for (size_t g = 0; g < NG; g++) {
+            uint64_t np = (groups[g].nk + target - 1) / target;
+            if (np < 1) np = 1;
+            if (np > 1) st_.nb_multipass_groups++;
+            if (np > 65535) throw Error(-4, "minimizer bin too large for the multi-pass counter");
+            if (groups[g].nrec > 0xFFFFFFFFull) throw Error(-4, "group has too many records");
+            for (uint64_t p = 0; p < np; p++) items.push_back({goff[g], (uint32_t)groups[g].nrec, (uint16_t)p, (uint16_t)np});
+        }
+        std::stable_sort(items.begin(), items.end(), [](const WorkItem& a, const WorkItem& b) { return a.nrec > b.nrec; });
+        st_.nb_groups = NG;
+        st_.nb_items = items.size();
+        DevBuf<uint32_t> d_group_of(NM);
+        DevBuf<uint64_t> d_goff(NG + 1);
+        DevBuf<unsigned int> d_gcur(std::max<size_t>(NG, 1));
+        DevBuf<WorkItem> d_items(std::max<size_t>(items.size(), 1));
+        DevBuf<uint64_t> grouped(std::max<uint64_t>(total_rec, 1));
+        MTG_CUDA(cudaMemcpyAsync(d_group_of.p, group_of.data(), NM * 4, cudaMemcpyHostToDevice, stream_));
+        MTG_CUDA(cudaMemcpyAsync(d_goff.p, goff.data(), (NG + 1) * 8, cudaMemcpyHostToDevice, stream_));
+        if (!items.empty()) MTG_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, stream_));
+        d_gcur.zero(stream_);
+        st_.ms_group += t.stop();
+        // ---- scatter records into group lists
+        t.start();
+        for (auto& b : batches_) {
+            if (!b.nrec) continue;
+            int grid = (int)std::min<uint64_t>((b.nrec + 255) / 256, (uint64_t)sm_count_ * 16);
+            scatter_kernel<<<grid, 256, 0, stream_>>>(b.recs.p, b.nrec, d_group_of.p, d_goff.p, d_gcur.p, grouped.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        st_.ms_scatter += t.stop();
+        for (auto& b : batches_) b.recs.release();
+        batches_.clear();
+        // ---- count
+        const bool is_auto = abundance_min < 0;
+        uint32_t emit_min = is_auto ? 3u : (uint32_t)std::max(abundance_min, 1);
+        uint64_t cand_cap = nvalid / emit_min + 1024;
+        DevBuf<K> cand_keys(cand_cap);
+        DevBuf<uint32_t> cand_cnt(cand_cap);
+        DevBuf<unsigned long long> d_histo(HISTO_MAX + 1);
+        DevBuf<unsigned int> d_item_counter(1);
+        d_histo.zero(stream_);
+        d_item_counter.zero(stream_);
+        MTG_CUDA(cudaMemsetAsync(counters_.p + 2, 0, 16, stream_));
+        MTG_CUDA(cudaMemsetAsync(flags_.p + 1, 0, sizeof(int), stream_));
+        t.start();
+        if (!items.empty()) {
+            const int smem = (int)(sizeof(K) + 4) * S + SMEM_HIST * 4;
+            int grid = (int)std::min<size_t>(items.size(), (size_t)sm_count_ * 2);
+            count_kernel<K><<<grid, COUNT_THREADS, smem, stream_>>>(packed_.p, grouped.p, d_items.p, (uint32_t)items.size(), d_item_counter.p, k_,
+                                                                     emit_min, d_histo.p, cand_keys.p, cand_cnt.p, counters_.p + 2, cand_cap,
+                                                                     flags_.p + 1);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        st_.ms_count += t.stop();
+        int err = 0;
+        unsigned long long ncand = 0;
+        MTG_CUDA(cudaMemcpyAsync(&err, flags_.p + 1, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaMemcpyAsync(&ncand, counters_.p + 2, 8, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaMemcpyAsync(histo_.data(), d_histo.p, (HISTO_MAX + 1) * 8, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        if (err == 1) throw Error(-5, "shared-memory count table overflow");
+        if (err == 2) throw Error(-5, "candidate buffer overflow");
+        st_.nb_candidates = ncand;
+        // ---- threshold (auto: CountProcessorCutoff::endPass, min_auto_threshold = 3) and final filter
+        int thr = abundance_min;
+        if (is_auto) { thr = compute_auto_cutoff(histo_.data(), 3); st_.cutoff_auto = thr; }
+        st_.threshold = thr;
+        uint32_t amax = abundance_max > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)std::max<int64_t>(abundance_max, 0);
+        t.start();
+        solid_keys_.alloc(std::max<uint64_t>(ncand, 1));
+        solid_cnt_.alloc(std::max<uint64_t>(ncand, 1));
+        if (ncand) {
+            int grid = (int)std::min<uint64_t>((ncand + 255) / 256, (uint64_t)sm_count_ * 16);
+            filter_kernel<K><<<grid, 256, 0, stream_>>>(cand_keys.p, cand_cnt.p, ncand, (uint32_t)std::max(thr, 0), amax, solid_keys_.p,
+                                                         solid_cnt_.p, counters_.p + 3);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        unsigned long long ns = 0;
+        MTG_CUDA(cudaMemcpyAsync(&ns, counters_.p + 3, 8, cudaMemcpyDeviceToHost, stream_));
+        st_.ms_filter += t.stop();
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        nb_solid_ = ns;
+        st_.nb_solid = ns;
+        // the packed reads are no longer needed
+        packed_.release(); inv_.release(); staging_.release();
+        words_used_ = words_cap_ = 0;
+    }
+
+    const CountStats& stats() const override { return st_; }
+    const uint64_t* histogram() const override { return histo_.data(); }
+    uint64_t nb_solid() const override { return nb_solid_; }
+    const void* solid_keys_device() const override { return solid_keys_.p; }
+    const uint32_t* solid_abundance_device() const override { return solid_cnt_.p; }
+    void export_solid(uint64_t* lo, uint64_t* hi, uint32_t* abundance) const override {
+        if (!nb_solid_) return;
+        std::vector<K> keys(nb_solid_);
+        MTG_CUDA(cudaMemcpy(keys.data(), solid_keys_.p, nb_solid_ * sizeof(K), cudaMemcpyDeviceToHost));
+        if (abundance) MTG_CUDA(cudaMemcpy(abundance, solid_cnt_.p, nb_solid_ * 4, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < nb_solid_; i++) { lo[i] = lo64(keys[i]); if (hi) hi[i] = hi64(keys[i]); }
+    }
+};
+
+ICounter* make_counter(int k, int minimizer_size, cudaStream_t stream, int key_bits) {
+    if (k < 4 || k > 63) throw Error(-1, "kmer size must be in [5,63]");
+    if (key_bits == 128) return new Counter<u128>(k, minimizer_size, stream);
+    if (k <= 31) return new Counter<uint64_t>(k, minimizer_size, stream);
+    return new Counter<u128>(k, minimizer_size, stream);
+}
+
+}  // namespace mtg

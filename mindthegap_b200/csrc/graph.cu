@@ -1,0 +1,627 @@
+// mtg-b200 stage 1b (membership structures) and stage 2 dense probes. Hand-written CUDA for sm_100a.
+// Build order mirrors build_visitor_postsolid (gatb-core debruijn/impl/Graph.cpp:428-612):
+//   exact table (ours) -> Bloom (BloomAlgorithm.cpp:155-200) -> critical FPs (DebloomMinimizerAlgorithm.cpp:196-275)
+//   -> cascading Blooms 2/3/4 + cfp set (DebloomAlgorithm.cpp:462-622) -> BooPHF levels (BooPHF.h:736-775)
+#include <math.h>
+
+#include <algorithm>
+#include <random>
+
+#include "count.cuh"
+#include "graph.cuh"
+
+namespace mtg {
+
+namespace {
+
+struct EvTimer {
+    cudaEvent_t a, b;
+    cudaStream_t s;
+    explicit EvTimer(cudaStream_t s_) : s(s_) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EvTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, s); }
+    float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+inline int grid_for(uint64_t n, int threads = 256, int cap = 148 * 16) {
+    uint64_t g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    return (int)std::min<uint64_t>(g, (uint64_t)cap);
+}
+
+uint64_t bloom_seed0_host() {  // HashFunctors::generate_hash_seed (Bloom.hpp:80-91): sequential, in place, user seed 0
+    uint64_t s[10] = {0xAAAAAAAA55555555ULL, 0x33333333CCCCCCCCULL, 0x6666666699999999ULL, 0xB5B5B5B54B4B4B4BULL,
+                      0xAA55AA5555335533ULL, 0x33CC33CCCC66CC66ULL, 0x6699669999B599B5ULL, 0xB54BB54B4BAA4BAAULL,
+                      0xAA33AA3355CC55CCULL, 0x33663366CC99CC99ULL};
+    for (int i = 0; i < 10; i++) s[i] = s[i] * s[(i + 3) % 10] + 0;
+    return s[0];
+}
+
+// Device Bloom storage with the reference's sizing rules (BloomContainer ctor Bloom.hpp:184-199, BloomCacheCoherent :437-442)
+struct BloomDev {
+    DevBuf<uint32_t> bits;
+    uint64_t tai = 0;      // reduced_tai: the modulus of the first hash
+    uint64_t nchar = 0;    // byte size of the reference's array
+    int nhash = 0;
+    void init(uint64_t tai_bloom, int nbHash, cudaStream_t s) {
+        nhash = nbHash;
+        uint64_t t = tai_bloom + 2 * 4096;
+        nchar = 1 + t / 8;
+        if (t && !(t & (t - 1))) t--;
+        tai = t - 2 * 4096;
+        bits.alloc(nchar / 4 + 2);
+        bits.zero(s);
+    }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ build kernels
+template <class K>
+__global__ void __launch_bounds__(256) table_build_kernel(const K* __restrict__ keys, uint64_t n, K* __restrict__ table, uint64_t nbuckets,
+                                                          int* __restrict__ err) {
+    const int SLOTS = BUCKET_BYTES / (int)sizeof(K);
+    const K EMPTY = ~K(0);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const K key = keys[i];
+        uint64_t b = key_hash(key) % nbuckets;
+        bool done = false;
+        for (uint64_t probe = 0; probe < nbuckets && !done; probe++) {
+            K* bucket = table + b * SLOTS;
+            for (int s = 0; s < SLOTS; s++) {
+                K cur = cas_global(&bucket[s], EMPTY, key);
+                if (cur == EMPTY || cur == key) { done = true; break; }
+            }
+            b = b + 1 == nbuckets ? 0 : b + 1;
+        }
+        if (!done) *err = 1;
+    }
+}
+
+template <class K>
+__global__ void __launch_bounds__(256) bloom_neighbor_insert_kernel(const K* __restrict__ keys, uint64_t n, GraphView<K> g, uint32_t* __restrict__ bits) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t h[8];
+        bloom_neighbor_positions<K>(g.k, g.bloom_tai, g.bloom_nhash, g.seed0, g.rnd, keys[i], h);
+        for (int j = 0; j < g.bloom_nhash; j++) atomicOr(bits + (h[j] >> 5), 1u << (h[j] & 31));
+    }
+}
+
+// critical false positives: Bloom-positive, non-solid canonical neighbours of solid k-mers, de-duplicated through an
+// open-addressing set (insert-if-absent); new members are appended to `crit_list`.
+template <class K>
+__global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ keys, uint64_t n, GraphView<K> g, K* __restrict__ set,
+                                                       uint64_t set_slots, K* __restrict__ crit_list, unsigned long long* __restrict__ ncrit,
+                                                       uint64_t list_cap, int* __restrict__ err) {
+    const K EMPTY = ~K(0);
+    const K mask = kmask<K>(g.k);
+    const uint64_t total = n * 8;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const K x = keys[t >> 3];
+        const int j = (int)(t & 7);
+        K nb = j < 4 ? (((x << 2) + (K)j) & mask) : ((x >> 2) + ((K)(j - 4) << (2 * (g.k - 1))));  // Model.hpp:524-580
+        nb = canonical(nb, g.k);
+        if (!bloom_neighbor_contains(g, nb)) continue;
+        if (table_contains(g, nb)) continue;
+        uint64_t s = key_hash(nb) % set_slots;
+        bool placed = false;
+        for (uint64_t probe = 0; probe < set_slots; probe++) {
+            K cur = cas_global(&set[s], EMPTY, nb);
+            if (cur == EMPTY) {
+                unsigned long long o = atomicAdd(ncrit, 1ull);
+                if (o < list_cap) crit_list[o] = nb; else *err = 2;
+                placed = true;
+                break;
+            }
+            if (cur == nb) { placed = true; break; }
+            s = s + 1 == set_slots ? 0 : s + 1;
+        }
+        if (!placed) *err = 1;
+    }
+}
+
+template <class K>
+__global__ void __launch_bounds__(256) bloom_cache_insert_kernel(const K* __restrict__ keys, uint64_t n, uint32_t* __restrict__ bits, uint64_t tai,
+                                                                 int nhash, uint64_t seed0, const uint64_t* __restrict__ rnd) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        bloom_cache_insert<K>(bits, tai, nhash, seed0, rnd, keys[i]);
+}
+// insert keys[i] into `dst` when `probe` contains it
+template <class K>
+__global__ void __launch_bounds__(256) bloom_cascade_kernel(const K* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ probe, uint64_t probe_tai,
+                                                            uint32_t* __restrict__ dst, uint64_t dst_tai, int nhash, uint64_t seed0,
+                                                            const uint64_t* __restrict__ rnd) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        K x = keys[i];
+        if (bloom_cache_contains<K>(probe, probe_tai, nhash, seed0, rnd, x)) bloom_cache_insert<K>(dst, dst_tai, nhash, seed0, rnd, x);
+    }
+}
+// cfp set = solid k-mers that are in B2 (i.e. T2) and in B4
+template <class K>
+__global__ void __launch_bounds__(256) cfp_set_kernel(const K* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ b2, uint64_t b2_tai,
+                                                      const uint32_t* __restrict__ b4, uint64_t b4_tai, int nhash, uint64_t seed0,
+                                                      const uint64_t* __restrict__ rnd, K* __restrict__ out, unsigned long long* __restrict__ nout,
+                                                      uint64_t cap, int* __restrict__ err) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        K x = keys[i];
+        if (bloom_cache_contains<K>(b2, b2_tai, nhash, seed0, rnd, x) && bloom_cache_contains<K>(b4, b4_tai, nhash, seed0, rnd, x)) {
+            unsigned long long o = atomicAdd(nout, 1ull);
+            if (o < cap) out[o] = x; else *err = 3;
+        }
+    }
+}
+
+// BooPHF level construction (processLevel/insertIntoLevel, BooPHF.h:842-905,1082-1092): every remaining key sets the
+// bit of its level hash; a second arrival marks a collision.
+template <class K>
+__global__ void __launch_bounds__(256) mphf_level_kernel(const K* __restrict__ keys, uint64_t n, int level, uint64_t dom, uint64_t seed,
+                                                         unsigned long long* __restrict__ bits, unsigned long long* __restrict__ coll) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        MphfState st;
+        st.init(keys[i], seed);
+        uint64_t h = 0;
+        for (int l = 0; l <= level; l++) h = st.level_hash(l);
+        uint64_t p = h % dom;
+        unsigned long long m = 1ull << (p & 63);
+        unsigned long long old = atomicOr(bits + (p >> 6), m);
+        if (old & m) atomicOr(coll + (p >> 6), m);
+    }
+}
+__global__ void __launch_bounds__(256) mphf_clear_kernel(unsigned long long* __restrict__ bits, const unsigned long long* __restrict__ coll, uint64_t nwords) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) bits[i] &= ~coll[i];
+}
+// keys whose bit was cleared (collision) go on to the next level
+template <class K>
+__global__ void __launch_bounds__(256) mphf_compact_kernel(const K* __restrict__ keys, uint64_t n, int level, uint64_t dom, uint64_t seed,
+                                                           const unsigned long long* __restrict__ bits, K* __restrict__ out,
+                                                           unsigned long long* __restrict__ nout) {
+    const int lane = threadIdx.x & 31;
+    uint64_t n_round = (n + 31) / 32 * 32;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (uint64_t)gridDim.x * blockDim.x) {
+        bool keep = false;
+        K key = 0;
+        if (i < n) {
+            key = keys[i];
+            MphfState st;
+            st.init(key, seed);
+            uint64_t h = 0;
+            for (int l = 0; l <= level; l++) h = st.level_hash(l);
+            uint64_t p = h % dom;
+            keep = !((bits[p >> 6] >> (p & 63)) & 1ull);
+        }
+        uint32_t b = __ballot_sync(0xFFFFFFFFu, keep);
+        if (b) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(nout, (unsigned long long)__popc(b));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (keep) out[base + __popc(b & ((1u << lane) - 1))] = key;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ query kernels
+template <class K>
+__global__ void __launch_bounds__(256) contains_kernel(GraphView<K> g, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, uint64_t n,
+                                                       uint8_t* __restrict__ out, int mode) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        K x = make_key<K>(lo[i], hi ? hi[i] : 0);
+        if (mode == 0) {  // contains (any strand in)
+            K c = canonical(x, g.k);
+            bool ex = table_contains(g, c);
+            bool bl = bloom_neighbor_contains(g, c);
+            bool cf = cfp_contains(g, c);
+            bool mp = mphf_found(g, c);
+            bool res = ex || (bl && !cf && mp);
+            out[i] = (res ? 1 : 0) | (ex ? 2 : 0) | (bl ? 4 : 0) | (cf ? 8 : 0) | (mp ? 16 : 0);
+        } else if (mode == 1) {  // degrees of the forward k-mer: in | out<<4
+            int din, dout;
+            graph_degrees(g, x, false, din, dout);
+            out[i] = (uint8_t)(din | (dout << 4));
+        } else if (mode == 2) {  // ref repeat test of a canonical (k-1)-mer
+            out[i] = bloom_cache_contains<K>(g.refbloom, g.ref_tai, g.ref_nhash, g.seed0, g.rnd, x) ? 1 : 0;
+        } else {  // observer probe: contains | indegree<<1 | outdegree<<4 | suffix_repeated<<7 (src/IFindObserver.hpp:85-117)
+            bool res = graph_contains(g, canonical(x, g.k));
+            int din, dout;
+            graph_degrees(g, x, false, din, dout);
+            K suffix = canonical<K>(x & kmask<K>(g.k - 1), g.k - 1);
+            bool rp = bloom_cache_contains<K>(g.refbloom, g.ref_tai, g.ref_nhash, g.seed0, g.rnd, suffix);
+            out[i] = (uint8_t)((res ? 1 : 0) | (din << 1) | (dout << 4) | (rp ? 0x80 : 0));
+        }
+    }
+}
+
+// Dense per-position features = what store_kmer_info computes for every valid reference k-mer
+// (src/FindBreakpoints.hpp:1012-1046, Graph.cpp:1482-1532):
+//   feat[p] = 0x80 when the window holds an invalid base, else in_graph | nb_in<<1 | nb_out<<4
+//   rep[p]  = bit0: canonical (k-1)-suffix repeated in the reference, bit1: canonical (k-1)-prefix repeated
+// counters: [0] valid positions [1] in-graph positions [2] exact-table probes [3] Bloom-emulation evaluations
+template <class K>
+__global__ void __launch_bounds__(256) features_kernel(GraphView<K> g, const uint64_t* __restrict__ packed, const uint32_t* __restrict__ inv,
+                                                       uint64_t npos, uint8_t* __restrict__ feat, uint8_t* __restrict__ rep,
+                                                       unsigned long long* __restrict__ counters) {
+    const int k = g.k;
+    const K mask = kmask<K>(k);
+    const K m1 = kmask<K>(k - 1);
+    unsigned long long c_valid = 0, c_in = 0, c_probe = 0, c_fb = 0;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += (uint64_t)gridDim.x * blockDim.x) {
+        // validity of the window
+        uint64_t a = p >> 5;
+        int o = (int)(p & 31);
+        uint32_t x0 = __ldg(inv + a), x1 = __ldg(inv + a + 1), x2 = __ldg(inv + a + 2);
+        uint32_t y0 = __funnelshift_l(x1, x0, o), y1 = __funnelshift_l(x2, x1, o);
+        bool valid = k <= 32 ? (y0 >> (32 - k)) == 0 : (y0 == 0 && (y1 >> (64 - k)) == 0);
+        uint8_t f = 0x80, r = 0;
+        if (valid) {
+            c_valid++;
+            const K fwd = extract_kmer<K>(packed, p, k);
+            const K can = canonical(fwd, k);
+            bool exact = table_contains(g, can);
+            c_probe++;
+            bool in = exact;
+            if (!exact) {
+                c_fb++;
+                in = bloom_neighbor_contains(g, can) && !cfp_contains(g, can) && mphf_found(g, can);
+            }
+            int din = 0, dout = 0;
+            if (in) {
+                c_in++;
+                graph_degrees(g, fwd, exact, din, dout);
+                c_probe += 8;
+                if (!exact) c_fb += 8;
+            }
+            f = (uint8_t)((in ? 1 : 0) | (din << 1) | (dout << 4));
+            K suffix = canonical<K>(fwd & m1, k - 1);
+            K prefix = canonical<K>((fwd >> 2) & m1, k - 1);
+            r = (uint8_t)((bloom_cache_contains<K>(g.refbloom, g.ref_tai, g.ref_nhash, g.seed0, g.rnd, suffix) ? 1 : 0) |
+                          (bloom_cache_contains<K>(g.refbloom, g.ref_tai, g.ref_nhash, g.seed0, g.rnd, prefix) ? 2 : 0));
+        }
+        feat[p] = f;
+        rep[p] = r;
+    }
+    (void)mask;
+    // warp reduce the counters
+    for (int off = 16; off; off >>= 1) {
+        c_valid += __shfl_down_sync(0xFFFFFFFFu, c_valid, off);
+        c_in += __shfl_down_sync(0xFFFFFFFFu, c_in, off);
+        c_probe += __shfl_down_sync(0xFFFFFFFFu, c_probe, off);
+        c_fb += __shfl_down_sync(0xFFFFFFFFu, c_fb, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (c_valid) atomicAdd(counters + 0, c_valid);
+        if (c_in) atomicAdd(counters + 1, c_in);
+        if (c_probe) atomicAdd(counters + 2, c_probe);
+        if (c_fb) atomicAdd(counters + 3, c_fb);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host class
+template <class K> class Graph : public IGraph {
+    int k_;
+    cudaStream_t stream_;
+    DevBuf<K> table_;
+    uint64_t nbuckets_ = 0;
+    BloomDev bloom_, b2_, b3_, b4_, ref_;
+    DevBuf<K> cfp_, final_;
+    uint64_t ncfp_ = 0, nfinal_ = 0;
+    bool cascading_ = true, mphf_built_ = false;
+    DevBuf<unsigned long long> mphf_bits_;
+    uint64_t mphf_off_[MPHF_LEVELS], mphf_dom_[MPHF_LEVELS];
+    uint64_t mphf_seed_ = 0, seed0_ = 0;
+    DevBuf<uint64_t> rnd_;
+    DevBuf<unsigned long long> counters_;
+    DevBuf<int> err_;
+    GraphStats st_;
+    float last_features_ms_ = 0;
+    // scratch for sequences
+    DevBuf<uint8_t> seq_stage_, d_feat_, d_rep_;
+    DevBuf<uint64_t> seq_packed_;
+    DevBuf<uint32_t> seq_inv_;
+    DevBuf<uint64_t> q_lo_, q_hi_;
+    DevBuf<uint8_t> q_out_;
+
+    GraphView<K> view() const {
+        GraphView<K> g;
+        memset(&g, 0, sizeof(g));
+        g.k = k_;
+        g.table = table_.p; g.nbuckets = nbuckets_;
+        g.bloom = bloom_.bits.p; g.bloom_tai = bloom_.tai; g.bloom_nhash = bloom_.nhash;
+        g.cascading = cascading_ ? 1 : 0;
+        g.b2 = b2_.bits.p; g.b2_tai = b2_.tai; g.b3 = b3_.bits.p; g.b3_tai = b3_.tai; g.b4 = b4_.bits.p; g.b4_tai = b4_.tai;
+        g.casc_nhash = b2_.nhash;
+        g.cfp = cfp_.p; g.ncfp = ncfp_;
+        g.mphf_built = mphf_built_ ? 1 : 0;
+        g.mphf_seed = mphf_seed_;
+        g.mphf_bits = (const uint64_t*)mphf_bits_.p;
+        for (int i = 0; i < MPHF_LEVELS; i++) { g.mphf_off[i] = mphf_off_[i]; g.mphf_dom[i] = mphf_dom_[i]; }
+        g.mphf_final = final_.p; g.nfinal = nfinal_;
+        g.refbloom = ref_.bits.p; g.ref_tai = ref_.tai; g.ref_nhash = ref_.nhash;
+        g.seed0 = seed0_;
+        g.rnd = rnd_.p;
+        return g;
+    }
+    void check_err(const char* what) {
+        int e = 0;
+        MTG_CUDA(cudaMemcpyAsync(&e, err_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        if (e) throw Error(-6, std::string(what) + " failed (device error flag " + std::to_string(e) + ")");
+    }
+    static float bits_per_kmer(int k) {  // DebloomAlgorithm::getNbBitsPerKmer, cascading (DebloomAlgorithm.cpp:628-651)
+        float v = (float)MTG_CASCADING_BITS_PER_KMER[k];
+        if (v == 0) v = 1;
+        return v;
+    }
+
+public:
+    Graph(int k, cudaStream_t s) : k_(k), stream_(s) {
+        seed0_ = bloom_seed0_host();
+        std::mt19937_64 rng(37);  // tools/collections/impl/BooPHF.hpp:246-249
+        mphf_seed_ = rng();
+        rnd_.alloc(256);
+        MTG_CUDA(cudaMemcpyAsync(rnd_.p, MTG_RANDOM_VALUES, 256 * 8, cudaMemcpyHostToDevice, stream_));
+        counters_.alloc(8);
+        err_.alloc(1);
+        err_.zero(stream_);
+        memset(mphf_off_, 0, sizeof(mphf_off_));
+        memset(mphf_dom_, 0, sizeof(mphf_dom_));
+        // an empty reference Bloom so that queries are always defined
+        ref_.init(1000, 8, stream_);
+        bloom_.init(1000, 4, stream_);
+        b2_.init(1000, 4, stream_); b3_.init(1000, 4, stream_); b4_.init(1000, 4, stream_);
+        nbuckets_ = 1;
+        table_.alloc(BUCKET_BYTES / sizeof(K));
+        table_.fill_ff(stream_);
+    }
+    int kmer_size() const override { return k_; }
+    const GraphStats& stats() const override { return st_; }
+    float last_features_ms() const override { return last_features_ms_; }
+
+    void build_from_host(const uint64_t* lo, const uint64_t* hi, uint64_t n) override {
+        std::vector<K> keys(n);
+        for (uint64_t i = 0; i < n; i++) keys[i] = make_key<K>(lo[i], hi ? hi[i] : 0);
+        DevBuf<K> d(std::max<uint64_t>(n, 1));
+        if (n) MTG_CUDA(cudaMemcpyAsync(d.p, keys.data(), n * sizeof(K), cudaMemcpyHostToDevice, stream_));
+        build(d.p, n);
+    }
+
+    void build(const void* d_solid, uint64_t N) override {
+        const K* keys = (const K*)d_solid;
+        EvTimer t(stream_);
+        st_.nb_solid = N;
+        // ---- exact table, load factor ~0.55, 128-byte buckets
+        t.start();
+        const int SLOTS = BUCKET_BYTES / (int)sizeof(K);
+        nbuckets_ = std::max<uint64_t>((uint64_t)((double)N / 0.55 / SLOTS) + 1, 1);
+        table_.alloc(nbuckets_ * SLOTS);
+        table_.fill_ff(stream_);
+        err_.zero(stream_);
+        if (N) {
+            table_build_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, table_.p, nbuckets_, err_.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        st_.ms_table = t.stop();
+        check_err("exact table build");
+        st_.nbuckets = nbuckets_;
+        // ---- main Bloom (BloomAlgorithm.cpp:161-165: u64 * float multiply)
+        t.start();
+        const float NBITS = bits_per_kmer(k_);
+        uint64_t est = (uint64_t)(N * NBITS);
+        const int nbHash = (int)floorf(0.7 * NBITS);
+        if (est == 0) est = 1000;
+        bloom_.init(est, nbHash, stream_);
+        if (N) {
+            GraphView<K> g = view();
+            bloom_neighbor_insert_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, g, bloom_.bits.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        st_.ms_bloom = t.stop();
+        st_.bloom_tai = bloom_.tai;
+        // ---- critical false positives (set de-duplication; retried with a larger set if it fills up)
+        t.start();
+        uint64_t ncrit = 0;
+        DevBuf<K> crit_list;
+        for (uint64_t mult = 1; N && mult <= 16; mult *= 2) {
+            uint64_t slots = N * mult + 1024;
+            uint64_t cap = slots * 7 / 10;
+            DevBuf<K> set(slots);
+            set.fill_ff(stream_);
+            crit_list.alloc(cap);
+            MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 8, stream_));
+            err_.zero(stream_);
+            GraphView<K> g = view();
+            critical_kernel<K><<<grid_for(N * 8), 256, 0, stream_>>>(keys, N, g, set.p, slots, crit_list.p, counters_.p, cap, err_.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+            int e = 0;
+            unsigned long long nc = 0;
+            MTG_CUDA(cudaMemcpyAsync(&e, err_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaMemcpyAsync(&nc, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaStreamSynchronize(stream_));
+            if (!e) { ncrit = nc; break; }
+            if (mult == 16) throw Error(-6, "critical false positive set overflow");
+        }
+        st_.ms_critical = t.stop();
+        st_.nb_critical = ncrit;
+        // ---- cascading Blooms (createCFP, DebloomAlgorithm.cpp:462-622); BLOOM_CACHE kind is forced there (:497)
+        t.start();
+        cascading_ = ncrit != 0;  // no critical FP -> DEBLOOM_ORIGINAL with an empty set (:478-479)
+        ncfp_ = 0;
+        cfp_.alloc(1);
+        if (cascading_) {
+            int64_t estT2 = std::max((int)ceilf(N * (double)powf((double)0.62, (double)NBITS)), 1);
+            int64_t estT3 = std::max((int)ceilf(ncrit * (double)powf((double)0.62, (double)NBITS)), 1);
+            const int nh = (int)floorf(0.7 * NBITS);
+            b2_.init((uint64_t)(ncrit * NBITS), nh, stream_);
+            b3_.init((uint64_t)(estT2 * NBITS), nh, stream_);
+            b4_.init((uint64_t)(estT3 * NBITS), nh, stream_);
+            bloom_cache_insert_kernel<K><<<grid_for(ncrit), 256, 0, stream_>>>(crit_list.p, ncrit, b2_.bits.p, b2_.tai, nh, seed0_, rnd_.p);
+            bloom_cascade_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, b2_.bits.p, b2_.tai, b3_.bits.p, b3_.tai, nh, seed0_, rnd_.p);
+            bloom_cascade_kernel<K><<<grid_for(ncrit), 256, 0, stream_>>>(crit_list.p, ncrit, b3_.bits.p, b3_.tai, b4_.bits.p, b4_.tai, nh, seed0_, rnd_.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches += 3;
+            for (uint64_t cap = N / 16 + 1024;; cap = N + 1024) {
+                cfp_.alloc(cap);
+                MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 8, stream_));
+                err_.zero(stream_);
+                cfp_set_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, b2_.bits.p, b2_.tai, b4_.bits.p, b4_.tai, nh, seed0_, rnd_.p, cfp_.p,
+                                                                     counters_.p, cap, err_.p);
+                MTG_CUDA(cudaGetLastError());
+                st_.launches++;
+                int e = 0;
+                unsigned long long nc = 0;
+                MTG_CUDA(cudaMemcpyAsync(&e, err_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+                MTG_CUDA(cudaMemcpyAsync(&nc, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
+                MTG_CUDA(cudaStreamSynchronize(stream_));
+                if (!e) { ncfp_ = nc; break; }
+                if (cap >= N + 1024) throw Error(-6, "cfp set overflow");
+            }
+            if (ncfp_) {  // small: sort on the host (std::sort of cfpItems, DebloomAlgorithm.cpp:561)
+                std::vector<K> h(ncfp_);
+                MTG_CUDA(cudaMemcpy(h.data(), cfp_.p, ncfp_ * sizeof(K), cudaMemcpyDeviceToHost));
+                std::sort(h.begin(), h.end());
+                MTG_CUDA(cudaMemcpy(cfp_.p, h.data(), ncfp_ * sizeof(K), cudaMemcpyHostToDevice));
+            }
+        }
+        st_.ms_cascade = t.stop();
+        st_.b2_tai = b2_.tai; st_.b3_tai = b3_.tai; st_.b4_tai = b4_.tai; st_.ncfp = ncfp_;
+        // ---- BooPHF levels (sizes: mphf::setup, BooPHF.h:1015-1041, double arithmetic on the host)
+        t.start();
+        mphf_built_ = false;
+        nfinal_ = 0;
+        final_.alloc(1);
+        if (N) {
+            const double gamma = 3.0;
+            const uint64_t hash_domain = (size_t)(ceil(double(N) * gamma));
+            const double proba = 1.0 - pow(((gamma * (double)N - 1) / (gamma * (double)N)), N - 1);
+            uint64_t off = 0;
+            for (int i = 0; i < MPHF_LEVELS; i++) {
+                uint64_t d = (((uint64_t)(hash_domain * pow(proba, i)) + 63) / 64) * 64;
+                if (d == 0) d = 64;
+                mphf_dom_[i] = d;
+                mphf_off_[i] = off;
+                off += d / 64;
+            }
+            mphf_bits_.alloc(off);
+            mphf_bits_.zero(stream_);
+            st_.mphf_words = off;
+            DevBuf<unsigned long long> coll(mphf_dom_[0] / 64);
+            DevBuf<K> bufA(N), bufB(N);
+            const K* cur = keys;
+            uint64_t ncur = N;
+            for (int lvl = 0; lvl < MPHF_LEVELS - 1 && ncur; lvl++) {
+                const uint64_t words = mphf_dom_[lvl] / 64;
+                MTG_CUDA(cudaMemsetAsync(coll.p, 0, words * 8, stream_));
+                mphf_level_kernel<K><<<grid_for(ncur), 256, 0, stream_>>>(cur, ncur, lvl, mphf_dom_[lvl], mphf_seed_, mphf_bits_.p + mphf_off_[lvl], coll.p);
+                mphf_clear_kernel<<<grid_for(words), 256, 0, stream_>>>(mphf_bits_.p + mphf_off_[lvl], coll.p, words);
+                K* out = (cur == bufA.p) ? bufB.p : bufA.p;
+                MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 8, stream_));
+                mphf_compact_kernel<K><<<grid_for(ncur), 256, 0, stream_>>>(cur, ncur, lvl, mphf_dom_[lvl], mphf_seed_, mphf_bits_.p + mphf_off_[lvl], out, counters_.p);
+                MTG_CUDA(cudaGetLastError());
+                st_.launches += 3;
+                unsigned long long nn = 0;
+                MTG_CUDA(cudaMemcpyAsync(&nn, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
+                MTG_CUDA(cudaStreamSynchronize(stream_));
+                cur = out;
+                ncur = nn;
+            }
+            if (ncur) {  // keys that survive 24 levels go to the final exact map (practically never)
+                std::vector<K> h(ncur);
+                MTG_CUDA(cudaMemcpy(h.data(), cur, ncur * sizeof(K), cudaMemcpyDeviceToHost));
+                std::sort(h.begin(), h.end());
+                final_.alloc(ncur);
+                MTG_CUDA(cudaMemcpy(final_.p, h.data(), ncur * sizeof(K), cudaMemcpyHostToDevice));
+                nfinal_ = ncur;
+            }
+            mphf_built_ = true;
+        }
+        st_.ms_mphf = t.stop();
+    }
+
+    void set_ref_repeats(const void* d_keys, uint64_t n) override {
+        // fillRefBloom (src/FindBreakpoints.hpp:984-1003): 12*2 bits per repeated (k-1)-mer, 8 hashes, BLOOM_CACHE
+        float NBITS_PER_KMER = 12;
+        uint64_t est = (uint64_t)((double)n * NBITS_PER_KMER * 2);
+        if (est == 0) est = 1000;
+        int nbHash = (int)floorf(0.7 * NBITS_PER_KMER);
+        ref_.init(est, nbHash, stream_);
+        if (n) {
+            bloom_cache_insert_kernel<K><<<grid_for(n), 256, 0, stream_>>>((const K*)d_keys, n, ref_.bits.p, ref_.tai, nbHash, seed0_, rnd_.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        st_.ref_repeated = n;
+        st_.ref_tai = ref_.tai;
+    }
+
+    void run_query(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out, int mode) {
+        if (!n) return;
+        if (q_lo_.n < n) { q_lo_.alloc(n * 2); q_hi_.alloc(n * 2); q_out_.alloc(n * 2); }
+        MTG_CUDA(cudaMemcpyAsync(q_lo_.p, lo, n * 8, cudaMemcpyHostToDevice, stream_));
+        if (hi) MTG_CUDA(cudaMemcpyAsync(q_hi_.p, hi, n * 8, cudaMemcpyHostToDevice, stream_));
+        contains_kernel<K><<<grid_for(n, 128), 128, 0, stream_>>>(view(), q_lo_.p, hi ? q_hi_.p : nullptr, n, q_out_.p, mode);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches++;
+        MTG_CUDA(cudaMemcpyAsync(out, q_out_.p, n, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+    }
+    void contains_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) override { run_query(lo, hi, n, out, 0); }
+    void degree_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) override { run_query(lo, hi, n, out, 1); }
+    void ref_repeat_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) override { run_query(lo, hi, n, out, 2); }
+    void observer_probe_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) override { run_query(lo, hi, n, out, 3); }
+
+    void features_device(const uint8_t* d_seq, uint64_t len, uint8_t* d_feat, uint8_t* d_rep, uint64_t* counters_host4) override {
+        if (counters_host4) memset(counters_host4, 0, 32);
+        last_features_ms_ = 0;
+        if (len < (uint64_t)k_) return;
+        const uint64_t npos = len - k_ + 1;
+        const uint64_t nwords = (len + 31) / 32;
+        if (seq_packed_.n < nwords + 8) { seq_packed_.alloc(nwords + 8 + nwords / 4); seq_inv_.alloc(nwords + 8 + nwords / 4); }
+        MTG_CUDA(cudaMemsetAsync(seq_packed_.p + nwords, 0, 8 * 8, stream_));
+        MTG_CUDA(cudaMemsetAsync(seq_inv_.p + nwords, 0xFF, 8 * 4, stream_));
+        launch_pack(d_seq, len, seq_packed_.p, seq_inv_.p, nwords, stream_);
+        MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 32, stream_));
+        EvTimer t(stream_);
+        t.start();
+        features_kernel<K><<<grid_for(npos, 256, 148 * 32), 256, 0, stream_>>>(view(), seq_packed_.p, seq_inv_.p, npos, d_feat, d_rep, counters_.p);
+        MTG_CUDA(cudaGetLastError());
+        last_features_ms_ = t.stop();
+        st_.launches += 2;
+        if (counters_host4) {
+            MTG_CUDA(cudaMemcpyAsync(counters_host4, counters_.p, 32, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaStreamSynchronize(stream_));
+        }
+    }
+    void features_host(const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint64_t* counters_host4) override {
+        if (counters_host4) memset(counters_host4, 0, 32);
+        if (len < (uint64_t)k_) return;
+        const uint64_t npos = len - k_ + 1;
+        if (seq_stage_.n < len + 64) { seq_stage_.alloc(len + 64 + len / 4); d_feat_.alloc(len + 64 + len / 4); d_rep_.alloc(len + 64 + len / 4); }
+        MTG_CUDA(cudaMemcpyAsync(seq_stage_.p, seq, len, cudaMemcpyHostToDevice, stream_));
+        features_device(seq_stage_.p, len, d_feat_.p, d_rep_.p, counters_host4);
+        MTG_CUDA(cudaMemcpyAsync(feat, d_feat_.p, npos, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaMemcpyAsync(rep, d_rep_.p, npos, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    uint64_t copy_bits(int which, uint8_t* host_buf) const override {
+        const BloomDev* b = which == 0 ? &bloom_ : which == 1 ? &b2_ : which == 2 ? &b3_ : which == 3 ? &b4_ : which == 4 ? &ref_ : nullptr;
+        if (b) {
+            if ((which >= 1 && which <= 3) && !cascading_) return 0;
+            if (host_buf) MTG_CUDA(cudaMemcpy(host_buf, b->bits.p, b->nchar, cudaMemcpyDeviceToHost));
+            return b->nchar;
+        }
+        if (!mphf_built_) return 0;
+        if (host_buf) MTG_CUDA(cudaMemcpy(host_buf, mphf_bits_.p, st_.mphf_words * 8, cudaMemcpyDeviceToHost));
+        return st_.mphf_words * 8;
+    }
+};
+
+IGraph* make_graph(int k, cudaStream_t stream) {
+    if (k < 5 || k > 63) throw Error(-1, "kmer size must be in [5,63]");
+    if (k <= 31) return new Graph<uint64_t>(k, stream);
+    return new Graph<u128>(k, stream);
+}
+
+}  // namespace mtg

@@ -1,0 +1,271 @@
+// mtg-b200 stage 1b + probes: device-resident structures that answer Graph::contains() exactly like the reference
+// (gatb-core debruijn/impl/Graph.hpp:1249-1272 = Bloom "neighbor" && !cascading-cFP && BooPHF-found), fronted by an
+// exact bucketised table of the solid k-mers (128-byte buckets) that answers solid k-mers and their neighbours.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "gatb_tables.h"
+
+namespace mtg {
+
+static const int MPHF_LEVELS = 25;  // BooPHF: _nb_levels = 25 (thirdparty/BooPHF/BooPHF.h:1026)
+
+// POD view passed by value to kernels.
+template <class K> struct GraphView {
+    int k;
+    // exact table: nbuckets buckets of 128 bytes (16 u64 keys or 8 u128 keys); empty slot = all ones
+    const K* table;
+    uint64_t nbuckets;
+    // Bloom filters as little-endian u32 words (bit pos -> word pos>>5, bit pos&31 == byte pos>>3, bit pos&7)
+    const uint32_t* bloom; uint64_t bloom_tai; int bloom_nhash;      // BloomNeighborCoherent (main)
+    int cascading;                                                   // 0 -> cFP is the plain sorted set `cfp`
+    const uint32_t* b2; uint64_t b2_tai;                             // BloomCacheCoherent x3
+    const uint32_t* b3; uint64_t b3_tai;
+    const uint32_t* b4; uint64_t b4_tai;
+    int casc_nhash;
+    const K* cfp; uint64_t ncfp;                                     // sorted
+    // BooPHF presence
+    int mphf_built;
+    uint64_t mphf_seed;
+    const uint64_t* mphf_bits;
+    uint64_t mphf_off[MPHF_LEVELS];   // word offset of each level
+    uint64_t mphf_dom[MPHF_LEVELS];   // hash domain of each level
+    const K* mphf_final; uint64_t nfinal;  // sorted (practically always empty)
+    // reference repeat Bloom (BloomCacheCoherent over canonical (k-1)-mers)
+    const uint32_t* refbloom; uint64_t ref_tai; int ref_nhash;
+    // hash constants
+    uint64_t seed0;               // HashFunctors seed_tab[0]
+    const uint64_t* rnd;          // random_values[256]
+};
+
+static const int BUCKET_BYTES = 128;
+
+// ------------------------------------------------------------------------------------------------ device functions
+MTG_D uint64_t simplehash16_dev(const uint64_t* __restrict__ rnd, uint64_t key, int shift) {  // LargeInt1.pri:190-213
+    uint64_t input = key >> shift;
+    uint64_t res = __ldg(rnd + (input & 255));
+    input >>= 8;
+    res ^= __ldg(rnd + (input & 255));
+    res ^= __ldg(rnd + (key & 255));
+    return res;
+}
+MTG_D uint64_t simplehash16_dev(const uint64_t* __restrict__ rnd, u128 key128, int shift) {   // LargeInt.hpp:792-800
+    uint64_t key = (uint64_t)key128;
+    uint64_t input = key >> shift;
+    uint64_t res = __ldg(rnd + (input & 255));
+    input >>= 8;
+    res ^= __ldg(rnd + (input & 255));
+    return res;
+}
+MTG_D bool bit_get(const uint32_t* __restrict__ bits, uint64_t pos) { return (__ldg(bits + (pos >> 5)) >> (pos & 31)) & 1u; }
+
+// BloomCacheCoherent::contains (Bloom.hpp:468-489)
+template <class K> MTG_D bool bloom_cache_contains(const uint32_t* __restrict__ bits, uint64_t tai, int nhash, uint64_t seed0,
+                                                   const uint64_t* __restrict__ rnd, K item) {
+    uint64_t h0 = gatb_hash1(item, seed0) % tai;
+    if (!bit_get(bits, h0)) return false;
+    for (int i = 1; i < nhash; i++)
+        if (!bit_get(bits, h0 + (simplehash16_dev(rnd, item, i) & 4095))) return false;
+    return true;
+}
+template <class K> MTG_D void bloom_cache_insert(uint32_t* __restrict__ bits, uint64_t tai, int nhash, uint64_t seed0,
+                                                 const uint64_t* __restrict__ rnd, K item) {
+    uint64_t h0 = gatb_hash1(item, seed0) % tai;
+    atomicOr(bits + (h0 >> 5), 1u << (h0 & 31));
+    for (int i = 1; i < nhash; i++) {
+        uint64_t h = h0 + (simplehash16_dev(rnd, item, i) & 4095);
+        atomicOr(bits + (h >> 5), 1u << (h & 31));
+    }
+}
+// BloomNeighborCoherent positions (Bloom.hpp:553-636)
+MTG_D unsigned cano2_dev(unsigned i) {
+    // {0,1,2,3,4,5,3,7,8,9,0,4,9,13,1,5} packed 4 bits each (Bloom.hpp:526-541)
+    const uint64_t tab = (0ull) | (1ull << 4) | (2ull << 8) | (3ull << 12) | (4ull << 16) | (5ull << 20) | (3ull << 24) | (7ull << 28) |
+                         (8ull << 32) | (9ull << 36) | (0ull << 40) | (4ull << 44) | (9ull << 48) | (13ull << 52) | (1ull << 56) | (5ull << 60);
+    return (unsigned)((tab >> (4 * i)) & 15);
+}
+template <class K> MTG_D void bloom_neighbor_positions(int k, uint64_t tai, int nhash, uint64_t seed0, const uint64_t* __restrict__ rnd,
+                                                       K item, uint64_t* h) {
+    unsigned suffix = (unsigned)(item & 3);
+    unsigned prefix = (unsigned)((item >> (2 * (k - 1))) & 3) << 2;
+    unsigned pref_val = cano2_dev((prefix + suffix) & 15);
+    K hashpart = (item >> 2) & kmask<K>(k - 2);
+    K rev = revcomp(hashpart, k - 2);
+    if (rev < hashpart) hashpart = rev;
+    uint64_t racine = gatb_hash1(hashpart, seed0) % tai;
+    h[0] = racine + pref_val;
+    for (int i = 1; i < nhash; i++) h[i] = h[0] + (simplehash16_dev(rnd, hashpart, i) & 4095);
+}
+template <class K> MTG_D bool bloom_neighbor_contains(const GraphView<K>& g, K item) {
+    uint64_t h[8];
+    bloom_neighbor_positions<K>(g.k, g.bloom_tai, g.bloom_nhash, g.seed0, g.rnd, item, h);
+    for (int i = 0; i < g.bloom_nhash; i++)
+        if (!bit_get(g.bloom, h[i])) return false;
+    return true;
+}
+
+template <class K> MTG_D bool sorted_contains(const K* __restrict__ a, uint64_t n, K x) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        K v = a[mid];
+        if (v < x) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && a[lo] == x;
+}
+
+// ContainerNodeCascading::containsCFP (ContainerNode.hpp:173-184)
+template <class K> MTG_D bool cfp_contains(const GraphView<K>& g, K x) {
+    if (!g.cascading) return sorted_contains(g.cfp, g.ncfp, x);
+    if (bloom_cache_contains<K>(g.b2, g.b2_tai, g.casc_nhash, g.seed0, g.rnd, x)) {
+        if (!bloom_cache_contains<K>(g.b3, g.b3_tai, g.casc_nhash, g.seed0, g.rnd, x)) return true;
+        if (bloom_cache_contains<K>(g.b4, g.b4_tai, g.casc_nhash, g.seed0, g.rnd, x) && !sorted_contains(g.cfp, g.ncfp, x)) return true;
+    }
+    return false;
+}
+
+// BooPHF hashing: jenkins lookup8 over the raw key bytes (tools/collections/impl/BooPHF.hpp:100-199), then xorshift128*
+MTG_HD void jenkins_mix(uint64_t& a, uint64_t& b, uint64_t& c) {
+    a -= b; a -= c; a ^= (c >> 43);
+    b -= c; b -= a; b ^= (a << 9);
+    c -= a; c -= b; c ^= (b >> 8);
+    a -= b; a -= c; a ^= (c >> 38);
+    b -= c; b -= a; b ^= (a << 23);
+    c -= a; c -= b; c ^= (b >> 5);
+    a -= b; a -= c; a ^= (c >> 35);
+    b -= c; b -= a; b ^= (a << 49);
+    c -= a; c -= b; c ^= (b >> 11);
+    a -= b; a -= c; a ^= (c >> 12);
+    b -= c; b -= a; b ^= (a << 18);
+    c -= a; c -= b; c ^= (b >> 22);
+}
+struct MphfState {
+    uint64_t s0, s1;
+    MTG_HD void init(uint64_t key, uint64_t seed) {
+        uint64_t a = seed, b = seed, c = 0x9e3779b97f4a7c13ULL;
+        c += 8; a += key;
+        jenkins_mix(a, b, c);
+        s0 = a; s1 = c;
+    }
+    MTG_HD void init(u128 key, uint64_t seed) {
+        uint64_t a = seed, b = seed, c = 0x9e3779b97f4a7c13ULL;
+        c += 16; b += (uint64_t)(key >> 64); a += (uint64_t)key;
+        jenkins_mix(a, b, c);
+        s0 = a; s1 = c;
+    }
+    MTG_HD uint64_t next() {  // XorshiftHashFunctors::next (BooPHF.h:352-360)
+        uint64_t x1 = s0;
+        const uint64_t x0 = s1;
+        s0 = x0;
+        x1 ^= x1 << 23;
+        s1 = x1 ^ x0 ^ (x1 >> 17) ^ (x0 >> 26);
+        return s1 + x0;
+    }
+    // hash of level `lvl` when called for lvl = 0,1,2,... in order
+    MTG_HD uint64_t level_hash(int lvl) { return lvl == 0 ? s0 : (lvl == 1 ? s1 : next()); }
+};
+// mphf::lookup(x) != ULLONG_MAX (BooPHF.h:787-815, getLevel :1045-1079)
+template <class K> MTG_D bool mphf_found(const GraphView<K>& g, K x) {
+    if (!g.mphf_built) return false;
+    MphfState st;
+    st.init(x, g.mphf_seed);
+    for (int lvl = 0; lvl < MPHF_LEVELS - 1; lvl++) {
+        uint64_t p = st.level_hash(lvl) % g.mphf_dom[lvl];
+        if ((__ldg(g.mphf_bits + g.mphf_off[lvl] + (p >> 6)) >> (p & 63)) & 1ull) return true;
+    }
+    return sorted_contains(g.mphf_final, g.nfinal, x);
+}
+
+// Exact table probe by one thread: reads whole 128-byte buckets with 128-bit loads.
+template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key) {
+    const int SLOTS = BUCKET_BYTES / (int)sizeof(K);
+    uint64_t b = key_hash(key) % g.nbuckets;
+    const K EMPTY = ~K(0);
+    for (uint64_t probe = 0; probe < g.nbuckets; probe++) {
+        const uint4* q = reinterpret_cast<const uint4*>(g.table + b * SLOTS);
+        bool has_empty = false, found = false;
+#pragma unroll
+        for (int i = 0; i < BUCKET_BYTES / 16; i++) {
+            uint4 v = __ldg(q + i);
+            if (sizeof(K) == 8) {
+                uint64_t a0 = ((uint64_t)v.y << 32) | v.x, a1 = ((uint64_t)v.w << 32) | v.z;
+                found |= (a0 == lo64(key)) | (a1 == lo64(key));
+                has_empty |= (a0 == ~0ull) | (a1 == ~0ull);
+            } else {
+                uint64_t a0 = ((uint64_t)v.y << 32) | v.x, a1 = ((uint64_t)v.w << 32) | v.z;
+                found |= (a0 == lo64(key)) & (a1 == hi64(key));
+                has_empty |= (a0 == ~0ull) & (a1 == ~0ull);
+            }
+        }
+        if (found) return true;
+        if (has_empty) return false;
+        b = b + 1 == g.nbuckets ? 0 : b + 1;
+    }
+    (void)EMPTY;
+    return false;
+}
+
+// Graph::contains for a CANONICAL k-mer. *used_fallback is set when the exact table missed and the Bloom emulation
+// had to answer (counted separately from the roofline probes).
+template <class K> MTG_D bool graph_contains(const GraphView<K>& g, K x, bool exact_only = false) {
+    if (table_contains(g, x)) return true;
+    if (exact_only) return false;
+    if (!bloom_neighbor_contains(g, x)) return false;
+    if (cfp_contains(g, x)) return false;
+    return mphf_found(g, x);
+}
+
+// countNeighbors_visitor without adjacency (Graph.cpp:1466-1532); graine = k-mer in node orientation (forward strand)
+template <class K> MTG_D void graph_degrees(const GraphView<K>& g, K graine, bool exact_only, int& indeg, int& outdeg) {
+    const K mask = kmask<K>(g.k);
+    indeg = outdeg = 0;
+#pragma unroll 1
+    for (int nt = 0; nt < 4; nt++) {
+        K f = ((graine << 2) + (K)nt) & mask;
+        if (graph_contains(g, canonical(f, g.k), exact_only)) outdeg++;
+    }
+#pragma unroll 1
+    for (int nt = 0; nt < 4; nt++) {
+        K f = ((graine >> 2) + ((K)nt << (2 * (g.k - 1)))) & mask;
+        if (graph_contains(g, canonical(f, g.k), exact_only)) indeg++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host class
+struct GraphStats {
+    uint64_t nb_solid = 0, nbuckets = 0, bloom_tai = 0, nb_critical = 0, b2_tai = 0, b3_tai = 0, b4_tai = 0, ncfp = 0;
+    uint64_t ref_repeated = 0, ref_tai = 0, mphf_words = 0;
+    float ms_table = 0, ms_bloom = 0, ms_critical = 0, ms_cascade = 0, ms_mphf = 0;
+    uint64_t launches = 0;
+};
+
+class IGraph {
+public:
+    virtual ~IGraph() {}
+    virtual int kmer_size() const = 0;
+    // build everything from the solid set (device array of K, not necessarily sorted)
+    virtual void build(const void* d_solid_keys, uint64_t n) = 0;
+    virtual void build_from_host(const uint64_t* lo, const uint64_t* hi, uint64_t n) = 0;
+    // repeated (k-1)-mers of the reference (device array of canonical K values with abundance >= het_max_occ+1)
+    virtual void set_ref_repeats(const void* d_keys, uint64_t n) = 0;
+    // batch queries on host arrays of FORWARD k-mers (any strand); out[i] bit0 = contains
+    virtual void contains_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) = 0;
+    // out[i] = indegree | outdegree<<4 of the forward k-mers
+    virtual void degree_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) = 0;
+    // (k-1)-mer repeat test on canonical values
+    virtual void ref_repeat_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) = 0;
+    // combined probe used by the host replay: contains | indegree<<1 | outdegree<<4 | suffix_repeated<<7
+    virtual void observer_probe_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) = 0;
+    // dense per-position features of a sequence given as ASCII on the device; see features kernel for the layout.
+    virtual void features_device(const uint8_t* d_seq, uint64_t len, uint8_t* d_feat, uint8_t* d_rep, uint64_t* counters_host4) = 0;
+    virtual void features_host(const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint64_t* counters_host4) = 0;
+    // raw copies for parity tests: which = 0 bloom,1..3 bloom2..4, 4 refbloom, 5 mphf levels; returns byte size
+    virtual uint64_t copy_bits(int which, uint8_t* host_buf) const = 0;
+    virtual const GraphStats& stats() const = 0;
+    virtual float last_features_ms() const = 0;
+};
+
+IGraph* make_graph(int k, cudaStream_t stream);
+
+}  // namespace mtg

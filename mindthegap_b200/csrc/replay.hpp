@@ -1,0 +1,456 @@
+// mtg-b200 stage 2, host part: event replay of the reference scan over GPU-computed dense features.
+//
+// The GPU computes, for every reference position, what FindBreakpoints::store_kmer_info would compute
+// (src/FindBreakpoints.hpp:1012-1046): in_graph, nb_in, nb_out, suffix/prefix repeat bits. This class then runs the
+// gap state machine of FindBreakpoints::notify (:561-622) and the observers (src/Find*.hpp, order of
+// src/Finder.cpp:543-586) over those arrays. All data-dependent membership queries of the observers (mutated k-mers,
+// micro-assemblies, deletion junctions, correct_history) are answered by the GPU through batched probe calls
+// (ProbeFn); nothing here consults a CPU copy of the graph.
+//
+// Quirks kept on purpose: ring indices are unsigned char and drift after a partial FindMultiSNPrev;
+// kmer_begin_is_repeated is the flag of the first gap k-mer; right k-mers of fuzzy/hetero sites are raw reference text.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <functional>
+#include <string>
+#include <vector>
+
+namespace mtg {
+
+struct ReplayOptions {
+    int k = 31, max_repeat = 5, het_max_occ = 1, snp_min_val = 5, branching_filter = 15;
+    bool homo_only = false, homo_insert = true, hete_insert = true, snp = true, backup = false, deletion = true, small_homo = true;
+};
+
+struct ReplayCounters {
+    uint64_t homo_clean = 0, homo_fuzzy = 0, hetero_clean = 0, hetero_fuzzy = 0, clean_deletion = 0, fuzzy_deletion = 0, solo_snp = 0,
+             multi_snp = 0, backup = 0, homo_indel = 0, hetero_indel = 0, observer_queries = 0, probe_batches = 0;
+};
+
+// Probe answer for a forward k-mer: bit0 contains, bits1-3 indegree, bits4-6 outdegree, bit7 (k-1)-suffix repeated.
+template <class K> using ProbeFn = std::function<void(const K* kmers, size_t n, uint8_t* out)>;
+
+template <class K> class Replayer {
+public:
+    Replayer(const ReplayOptions& o, ProbeFn<K> probe) : opt(o), k(o.k), probe_(probe) {
+        mask_ = (K(1) << (2 * k)) - K(1);
+        memset(ring, 0, sizeof(ring));
+    }
+    std::string bkpt_out, vcf_out;
+    ReplayCounters cnt;
+    uint64_t next_id = 1;  // shared bkpt id counter (src/FindBreakpoints.hpp:872-875)
+
+    // One reference sequence (FindBreakpoints::operator(), :390-455). feat/rep hold len-k+1 entries.
+    void scan(const std::string& name, const char* seq, size_t len, const uint8_t* feat, const uint8_t* rep) {
+        chrom = name; text = seq; text_len = len;
+        begin_valid = end_valid = false;
+        solid_stretch = gap_stretch = 0;
+        memset(ring, 0, sizeof(ring));
+        end_idx = (unsigned char)(k + 1);
+        begin_idx = 1;
+        recent_hetero = 0;
+        pos = 0;
+        if (len < (size_t)k) return;
+        const size_t npos = len - k + 1;
+        K fwd = 0;
+        for (int i = 0; i < k - 1; i++) fwd = (fwd << 2) | (K)code(seq[i]);
+        for (size_t p = 0; p < npos; p++) {
+            fwd = ((fwd << 2) | (K)code(seq[p + k - 1])) & mask_;
+            const uint8_t f = feat[p];
+            if (f & 0x80) {
+                solid_stretch = gap_stretch = 0;
+                begin_valid = end_valid = false;
+            } else {
+                cur_fwd = fwd;
+                const uint64_t save = pos;
+                notify(f, rep[p]);
+                pos = save;
+                prev_fwd = fwd; prev_valid = true;
+            }
+            pos++; begin_idx++; end_idx++;
+        }
+    }
+
+private:
+    struct Info { K kmer; int nb_in, nb_out; bool is_repeated; };
+    ReplayOptions opt;
+    int k;
+    ProbeFn<K> probe_;
+    K mask_;
+    // scan state
+    std::string chrom;
+    const char* text = nullptr;
+    size_t text_len = 0;
+    uint64_t pos = 0, solid_stretch = 0, gap_stretch = 0;
+    K cur_fwd = 0, prev_fwd = 0, begin_fwd = 0, end_fwd = 0;
+    bool prev_valid = false, begin_valid = false, end_valid = false;
+    Info ring[256];
+    unsigned char begin_idx = 1, end_idx = 0;
+    Info cur_info;
+    int recent_hetero = 0;
+    bool end_is_repeated = false, begin_is_repeated = false;
+
+    static int code(char c) { return ((unsigned char)c >> 1) & 3; }
+    static bool valid_nt(char c) { c &= (char)0xDF; return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+    K rc(K x) const { return revcomp_host(x, k); }
+    static uint64_t rcw(uint64_t x) {
+        x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+        x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+        x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+        x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+        x = (x >> 32) | (x << 32);
+        return x ^ 0xAAAAAAAAAAAAAAAAULL;
+    }
+    static uint64_t revcomp_host(uint64_t x, int kk) { return rcw(x) >> (2 * (32 - kk)); }
+    static unsigned __int128 revcomp_host(unsigned __int128 x, int kk) {
+        unsigned __int128 r = ((unsigned __int128)rcw((uint64_t)x) << 64) | rcw((uint64_t)(x >> 64));
+        return r >> (2 * (64 - kk));
+    }
+    std::string str(K v) const {
+        std::string s(k, 'A');
+        for (int i = k - 1; i >= 0; i--) { s[i] = "ACTG"[(int)(v & 3)]; v >>= 2; }
+        return s;
+    }
+    std::string raw(uint64_t p, size_t n) const {
+        if (p >= text_len) return std::string();
+        return std::string(text + p, std::min(n, text_len - (size_t)p));
+    }
+    bool seed_valid(uint64_t p) const {
+        if (p + k > text_len) return false;
+        for (int i = 0; i < k; i++) if (!valid_nt(text[p + i])) return false;
+        return true;
+    }
+    // ---- GPU probes
+    std::vector<uint8_t> ans_;
+    const uint8_t* probe(const std::vector<K>& q) {
+        ans_.resize(q.size());
+        if (!q.empty()) { probe_(q.data(), q.size(), ans_.data()); cnt.probe_batches++; cnt.observer_queries += q.size(); }
+        return ans_.data();
+    }
+    uint8_t probe1(K x) { std::vector<K> q(1, x); return probe(q)[0]; }
+    // forward k-mers of a nucleotide string
+    void kmers_of(const std::string& s, std::vector<K>& out) const {
+        if (s.size() < (size_t)k) return;
+        K f = 0;
+        for (size_t i = 0; i < s.size(); i++) {
+            f = ((f << 2) | (K)code(s[i])) & mask_;
+            if (i + 1 >= (size_t)k) out.push_back(f);
+        }
+    }
+
+    // ---- writers (src/FindBreakpoints.hpp:641-702)
+    void write_breakpoint(const std::string& chrom_name, uint64_t p, const std::string& kb, const std::string& ke, int repeat, const char* type,
+                          bool rep_b = false, bool rep_e = false) {
+        char hdr[1200];
+        for (int side = 0; side < 2; side++) {
+            snprintf(hdr, sizeof hdr, ">bkpt%i_%s_pos_%lli_fuzzy_%i_%s %s %s\n", (int)next_id, chrom_name.c_str(), (long long)(p + 1), repeat, type,
+                     (side == 0 ? rep_b : rep_e) ? "REPEATED" : "", side == 0 ? "left_kmer" : "right_kmer");
+            bkpt_out += hdr;
+            bkpt_out += side == 0 ? kb : ke;
+            bkpt_out += '\n';
+        }
+    }
+    void write_vcf(uint64_t p, const std::string& ref, const std::string& alt, int repeat, const char* type) {
+        int variant_size = strcmp(type, "DEL") == 0 ? (int)ref.size() - 1 : 1;
+        char buf[1200];
+        snprintf(buf, sizeof buf, "%s\t%lli\tbkpt%i\t", chrom.c_str(), (long long)(p + 1), (int)next_id);
+        vcf_out += buf; vcf_out += ref; vcf_out += '\t'; vcf_out += alt;
+        snprintf(buf, sizeof buf, "\t.\tPASS\tTYPE=%s;LEN=%i;FUZZY=%i\tGT\t1/1\n", type, variant_size, repeat);
+        vcf_out += buf;
+    }
+    void write_indel(uint64_t p, const std::string& ref, const std::string& alt, int repeat, const char* type) {
+        const char* gt = !strcmp(type, "HOM") ? "1/1" : (!strcmp(type, "HET") ? "0/1" : "./.");
+        char buf[1200];
+        snprintf(buf, sizeof buf, "%s\t%lli\tbkpt%i\t", chrom.c_str(), (long long)(p + 1), (int)next_id);
+        vcf_out += buf; vcf_out += ref; vcf_out += '\t'; vcf_out += alt;
+        snprintf(buf, sizeof buf, "\t.\tPASS\tTYPE=INS;LEN=%i;FUZZY=%i\tGT\t%s\n", (int)alt.size() - 1, repeat, gt);
+        vcf_out += buf;
+    }
+
+    // ---- micro-assembly of the 20 candidate 1-2 bp insertions (FindSmallInsertion.hpp:77-106, FindHeteroInsertion.hpp:80-115).
+    // All candidate k-mers are probed in one GPU batch, then the reference's sequential rule is applied:
+    // walk the k-mers in order until the first miss; success iff at least k k-mers were contained.
+    bool micro_assembly(const std::string& kb, const std::string& ke, std::string& ins) {
+        static const char* nucleo[20] = {"A", "C", "G", "T", "AA", "AC", "AG", "AT", "CA", "CC", "CG", "CT", "GA", "GC", "GG", "GT", "TA", "TC", "TG", "TT"};
+        std::vector<K> q;
+        size_t start[21];
+        for (int a = 0; a < 20; a++) { start[a] = q.size(); kmers_of(kb + nucleo[a] + ke, q); }
+        start[20] = q.size();
+        const uint8_t* ans = probe(q);
+        for (int a = 0; a < 20; a++) {
+            int ok = 0;
+            for (size_t i = start[a]; i < start[a + 1] && (ans[i] & 1); i++) ok++;
+            if (ok >= k) { ins = nucleo[a]; return true; }
+        }
+        return false;
+    }
+
+    // ---- SNP walk (FindSNP::snp_at_end / snp_at_begin, src/FindSNP.hpp:133-293). The 3*k mutated k-mers are probed in
+    // one batch; the elimination loop (std::map iterated in numeric nucleotide order) is then replayed on the answers.
+    K mutate(K kmer, K nuc, size_t p1) const {  // mutate_kmer: position p1 is 1-based from the left
+        size_t p = k - p1;
+        return (kmer & ~((K)3 << (2 * p))) | (nuc << (2 * p));
+    }
+    bool snp_walk(bool at_end, unsigned char* beginpos, size_t limit, K* ret_nuc, K* ref_nuc, unsigned* nb_val) {
+        const unsigned char init = *beginpos;
+        *ref_nuc = at_end ? (ring[init].kmer & 3) : ((ring[init].kmer >> (2 * (k - 1))) & 3);
+        std::vector<K> q;
+        q.reserve(4 * k);
+        for (int j = 0; j < k; j++) {
+            unsigned char idx = at_end ? (unsigned char)(init + j) : (unsigned char)(init - j);
+            for (int nt = 0; nt < 4; nt++) q.push_back(mutate(ring[idx].kmer, (K)nt, at_end ? (size_t)(k - j) : (size_t)(j + 1)));
+        }
+        const uint8_t* ans = probe(q);
+        bool present[4] = {true, true, true, true};
+        unsigned count[4] = {0, 0, 0, 0};
+        int size = 3;
+        present[(int)*ref_nuc] = false;
+        bool end = false;
+        for (unsigned char j = 0; !end && j != (unsigned char)k; (at_end ? (*beginpos)++ : (*beginpos)--), j++) {
+            for (int nt = 0; nt < 4; nt++) {
+                if (!present[nt]) continue;
+                if (ans[4 * j + nt] & 1) { count[nt]++; continue; }
+                if (size == 1) { end = true; if (at_end) (*beginpos) -= 1; else (*beginpos) += 1; break; }
+                present[nt] = false; size--;
+            }
+        }
+        int best = -1;
+        for (int nt = 0; nt < 4; nt++) if (present[nt] && (best < 0 || count[nt] > count[best])) best = nt;
+        if (count[best] >= limit) { *ret_nuc = (K)best; *nb_val = count[best]; return true; }
+        *beginpos = init;
+        return false;
+    }
+    void correct_history(unsigned char p0, K nuc) {  // src/FindSNP.hpp:360-381 (identical in the three SNP finders)
+        std::vector<K> q(k);
+        for (int i = 0; i < k; i++) q[i] = mutate(ring[(unsigned char)(p0 + i)].kmer, nuc, k - i);
+        const uint8_t* ans = probe(q);
+        for (int i = 0; i < k; i++) {
+            Info& h = ring[(unsigned char)(p0 + i)];
+            h.kmer = q[i];
+            if (ans[i] & 1) { h.nb_in = (ans[i] >> 1) & 7; h.nb_out = (ans[i] >> 4) & 7; h.is_repeated = (ans[i] >> 7) & 1; }
+        }
+    }
+    static char nt_char(K n) { return n == 0 ? 'A' : n == 1 ? 'C' : n == 2 ? 'T' : 'G'; }
+    bool ends_ok() const { return begin_valid && end_valid; }
+
+    // ---- gap observers
+    bool solo_snp() {  // FindSoloSNP::update, src/FindSNP.hpp:319-358
+        if (!ends_ok() || gap_stretch != (uint64_t)k) return false;
+        K ref_nuc, nuc; unsigned nv;
+        unsigned char p0 = begin_idx - 1, save = p0;
+        if (!snp_walk(true, &p0, k, &nuc, &ref_nuc, &nv)) return false;
+        correct_history(save, nuc);
+        write_vcf(pos - 2, std::string(1, nt_char(ref_nuc)), std::string(1, nt_char(nuc)), 0, "SNP");
+        next_id++; cnt.solo_snp++;
+        return true;
+    }
+    bool multi_snp() {  // FindMultiSNP::update, src/FindSNP.hpp:459-545
+        if (!ends_ok()) return false;
+        const int thr = opt.snp_min_val;
+        if (!(gap_stretch > (uint64_t)(k + thr))) return false;
+        size_t bp = pos - 1 - gap_stretch + k - 1, bp0 = bp;
+        unsigned char index_end = begin_idx + k - 1;
+        unsigned char index_pos = index_end - gap_stretch;
+        while (index_pos != index_end) {
+            unsigned char save = index_pos;
+            unsigned nv = 0; K ref_nuc, nuc;
+            if (!snp_walk(true, &index_pos, thr, &nuc, &ref_nuc, &nv)) break;
+            if (bp + nv - bp0 > gap_stretch) break;
+            correct_history(save, nuc);
+            write_vcf(bp, std::string(1, nt_char(ref_nuc)), std::string(1, nt_char(nuc)), 0, "SNP");
+            next_id++; cnt.multi_snp++;
+            bp += nv;
+        }
+        unsigned fixed = (unsigned)(bp - bp0);
+        if (fixed == 0) return false;
+        if (fixed != gap_stretch) {
+            gap_stretch -= fixed;
+            solid_stretch += fixed;
+            begin_fwd = ring[(unsigned char)(index_pos - 1)].kmer;  // KmerCanonical::set(fwd, rc): validity untouched
+            return false;
+        }
+        return true;
+    }
+    bool multi_snp_rev() {  // FindMultiSNPrev::update, src/FindSNP.hpp:593-690
+        if (!ends_ok()) return false;
+        const int thr = opt.snp_min_val;
+        if (!(gap_stretch > (uint64_t)(k + thr))) return false;
+        size_t bp = pos - 2, bp0 = bp;
+        unsigned char index_limit = end_idx - 2 - gap_stretch;
+        unsigned char index_pos = end_idx - 2;
+        while (index_pos != index_limit) {
+            unsigned char save = index_pos;
+            unsigned nv = 0; K ref_nuc, nuc;
+            if (!snp_walk(false, &index_pos, thr, &nuc, &ref_nuc, &nv)) break;
+            if (bp0 - (bp - nv) > gap_stretch) break;
+            correct_history((unsigned char)(save - (k - 1)), nuc);
+            write_vcf(bp, std::string(1, nt_char(ref_nuc)), std::string(1, nt_char(nuc)), 0, "SNP");
+            next_id++; cnt.multi_snp++;
+            bp -= nv;
+        }
+        unsigned fixed = (unsigned)(bp0 - bp);
+        if (fixed == 0) return false;
+        if (fixed != gap_stretch) {
+            pos -= fixed;            // restored by the caller after notify (:441-446)
+            end_idx -= fixed;        // never restored: ring-index drift (quirk)
+            begin_idx -= fixed;
+            gap_stretch -= fixed;
+            end_fwd = ring[(unsigned char)(index_pos + 1)].kmer;
+            return false;
+        }
+        return true;
+    }
+    bool all_contained(const std::string& s) {
+        std::vector<K> q;
+        kmers_of(s, q);
+        const uint8_t* ans = probe(q);
+        for (size_t i = 0; i < q.size(); i++) if (!(ans[i] & 1)) return false;
+        return true;
+    }
+    bool deletion() {  // FindDeletion::update, src/FindDeletion.hpp:62-171
+        if (!ends_ok()) return false;
+        if (gap_stretch < (uint64_t)((size_t)k - (size_t)opt.max_repeat)) return false;
+        std::string b = str(begin_fwd), e = str(end_fwd);
+        unsigned rep = 0;
+        for (unsigned i = opt.max_repeat; i != 0; i--)  // fuzzy_site (:178-188): longest suffix(begin) == prefix(end)
+            if (i <= b.size() && b.compare(b.size() - i, i, e, 0, i) == 0) { rep = i; break; }
+        if (rep) b = b.substr(0, b.size() - rep);
+        int del_size = (int)gap_stretch - k + (int)rep + 1;
+        if (!all_contained(b + e)) {
+            if (rep == 0) return false;
+            if (!all_contained(str(begin_fwd) + e)) return false;
+            del_size -= rep;
+            rep = 0;
+        }
+        if (del_size <= 0) return false;
+        size_t start = pos - 2 - del_size;
+        std::string del_seq = raw(start, del_size + 1);
+        write_vcf(start, del_seq, del_seq.substr(0, 1), rep, "DEL");
+        next_id++;
+        if (rep) cnt.fuzzy_deletion++; else cnt.clean_deletion++;
+        return true;
+    }
+    bool is_clean_gap() const { return gap_stretch == (uint64_t)(k - 1); }
+    bool is_fuzzy_gap() const { return gap_stretch < (uint64_t)(k - 1) && gap_stretch >= (uint64_t)(k - 1 - opt.max_repeat); }
+    // degree test shared by the insertion finders: outdegree(kmer_begin) != 0 && indegree(kmer_end) != 0
+    bool ends_connected() {
+        std::vector<K> q = {begin_fwd, end_fwd};
+        const uint8_t* a = probe(q);
+        return ((a[0] >> 4) & 7) != 0 && ((a[1] >> 1) & 7) != 0;
+    }
+    bool small_clean_insertion() {  // src/FindSmallInsertion.hpp:56-116
+        if (!ends_ok() || !is_clean_gap()) return false;
+        std::string kb = str(begin_fwd), ke = str(end_fwd), ins;
+        if (!micro_assembly(kb, ke, ins)) return false;
+        std::string ref = kb.substr(kb.size() - 1, 1);
+        write_indel(pos - 2, ref, ref + ins, 0, "HOM");
+        cnt.homo_indel++; next_id++;
+        return true;
+    }
+    bool small_fuzzy_insertion() {  // src/FindSmallInsertion.hpp:147-212
+        if (!ends_ok() || !is_fuzzy_gap()) return false;
+        int rep = k - 1 - (int)gap_stretch;
+        uint64_t rp = pos - 1 + rep;
+        if (!ends_connected() || !seed_valid(rp)) return false;
+        std::string kb = str(begin_fwd), ke = raw(rp, k), ins;
+        if (!micro_assembly(kb, ke, ins)) return false;
+        std::string ref = kb.substr(kb.size() - 1 - rep, 1);
+        write_indel(pos - 2, ref, ref + ins, rep, "HOM");
+        cnt.homo_indel++; next_id++;
+        return true;
+    }
+    bool clean_insertion() {  // src/FindInsertion.hpp:46-80
+        if (!ends_ok() || !is_clean_gap()) return false;
+        if (!ends_connected()) return false;
+        write_breakpoint(chrom, pos - 2, str(begin_fwd), str(end_fwd), 0, "HOM", begin_is_repeated, end_is_repeated);
+        next_id++; cnt.homo_clean++;
+        return true;
+    }
+    bool fuzzy_insertion() {  // src/FindInsertion.hpp:100-133
+        if (!ends_ok() || !is_fuzzy_gap()) return false;
+        int rep = k - 1 - (int)gap_stretch;
+        uint64_t rp = pos - 1 + rep;
+        if (!ends_connected() || !seed_valid(rp)) return false;
+        write_breakpoint(chrom, pos - 2 + rep, str(begin_fwd), raw(rp, k), rep, "HOM", begin_is_repeated, end_is_repeated);
+        next_id++; cnt.homo_fuzzy++;
+        return true;
+    }
+    bool backup() {  // src/FindBackup.hpp:46-67
+        if (!ends_ok() || !(gap_stretch > (uint64_t)(k / 2))) return false;
+        write_breakpoint(chrom + "_backup", pos - 1, str(begin_fwd), str(end_fwd), 0, "BACKUP");
+        next_id++; cnt.backup++;
+        return true;
+    }
+    // ---- k-mer observer (src/FindHeteroInsertion.hpp:48-174)
+    void hetero() {
+        if (opt.homo_only) return;
+        int max_branching = opt.branching_filter;
+        bool filtering = true;
+        if (opt.branching_filter < 0) { filtering = false; max_branching = 100; }
+        if (!end_is_repeated && cur_info.nb_in == 2 && !recent_hetero) {
+            for (int i = 0; i <= opt.max_repeat; i++) {
+                const Info h = ring[(unsigned char)(begin_idx + i)];
+                if (!(h.nb_out == 2 && !h.is_repeated)) continue;
+                std::string kb = str(h.kmer), ke = raw(pos + i, k);
+                if (!seed_valid(pos + i)) return;  // returns without touching recent_hetero (:91-94)
+                std::string ref = kb.substr(kb.size() - 1 - i, 1), ins;
+                if (micro_assembly(kb, ke, ins)) {
+                    write_indel(pos - 1, ref, ref + ins, i, "HET");
+                    cnt.hetero_indel++; next_id++;
+                    return;
+                }
+                int nb_branching = 0;
+                if (filtering) {
+                    unsigned char bi = begin_idx - 1;
+                    for (int prev = 0; nb_branching <= max_branching && prev < 100; prev++) {
+                        const Info& w = ring[(unsigned char)(bi - prev)];
+                        if (w.nb_out > 1 || w.nb_in > 1) nb_branching++;
+                    }
+                }
+                if (nb_branching <= max_branching) {
+                    write_breakpoint(chrom, pos - 1 + i, kb, ke, i, "HET", h.is_repeated, end_is_repeated);
+                    next_id++;
+                    if (i == 0) cnt.hetero_clean++; else cnt.hetero_fuzzy++;
+                    recent_hetero = opt.max_repeat;
+                    return;
+                }
+                recent_hetero = std::max(0, recent_hetero - 1);
+                return;
+            }
+        }
+        recent_hetero = std::max(0, recent_hetero - 1);
+    }
+
+    void notify(uint8_t f, uint8_t r) {  // FindBreakpoints::notify + store_kmer_info
+        const bool in_graph = f & 1;
+        cur_info.kmer = cur_fwd;
+        cur_info.nb_in = (f >> 1) & 7;
+        cur_info.nb_out = (f >> 4) & 7;
+        cur_info.is_repeated = r & 1;
+        ring[end_idx] = cur_info;
+        end_is_repeated = (r >> 1) & 1;
+        if (opt.hete_insert) hetero();
+        if (in_graph) {
+            solid_stretch++;
+            if (solid_stretch > 1 && gap_stretch > 0) {
+                bool done = false;
+                if (opt.snp) done = solo_snp() || multi_snp() || multi_snp_rev();
+                if (!done && opt.deletion) done = deletion();
+                if (!done && opt.small_homo) done = small_clean_insertion() || small_fuzzy_insertion();
+                if (!done && opt.homo_insert) done = clean_insertion() || fuzzy_insertion();
+                if (!done && opt.backup) done = backup();
+                gap_stretch = 0;
+            }
+            if (solid_stretch == 1) { end_fwd = cur_fwd; end_valid = true; }
+        } else {
+            if (solid_stretch == 1) gap_stretch += solid_stretch;
+            if (solid_stretch > 1 && prev_valid) { begin_fwd = prev_fwd; begin_valid = true; begin_is_repeated = cur_info.is_repeated; }
+            gap_stretch++;
+            solid_stretch = 0;
+        }
+    }
+};
+
+}  // namespace mtg

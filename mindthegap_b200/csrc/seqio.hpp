@@ -1,0 +1,102 @@
+// mtg-b200 host input: FASTA/FASTQ reader in the style of kseq, mirroring the behaviour of gatb's BankFasta
+// (thirdparty/gatb-core/gatb-core/src/gatb/bank/impl/BankFasta.cpp:485-574): '>' or '@' headers, multi-line sequences,
+// FASTQ quality skipped by length; comma separated file lists (README.md:166). Plain text only.
+// getCommentShort = header up to the first whitespace (gatb/bank/api/Sequence.hpp:88).
+#pragma once
+#include <stdio.h>
+
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace mtg {
+
+struct SeqRecord { std::string name, seq; };
+
+class SeqReader {
+    FILE* f_ = nullptr;
+    std::vector<char> buf_;
+    size_t b_ = 0, e_ = 0;
+    bool eof_ = false;
+    int last_ = 0;
+    int getc_() {
+        if (b_ >= e_) {
+            if (eof_) return -1;
+            e_ = fread(buf_.data(), 1, buf_.size(), f_);
+            b_ = 0;
+            if (e_ < buf_.size()) eof_ = true;
+            if (e_ == 0) return -1;
+        }
+        return (unsigned char)buf_[b_++];
+    }
+    // append up to '\n' to s; returns false at EOF with nothing read
+    bool getline_(std::string& s, bool append) {
+        if (!append) s.clear();
+        bool any = false;
+        while (true) {
+            if (b_ >= e_) { if (getc_() < 0) break; b_--; }
+            size_t i = b_;
+            while (i < e_ && buf_[i] != '\n') i++;
+            s.append(buf_.data() + b_, i - b_);
+            any = true;
+            if (i < e_) { b_ = i + 1; break; }
+            b_ = e_;
+        }
+        if (!s.empty() && s.back() == '\r') s.pop_back();
+        return any;
+    }
+
+public:
+    explicit SeqReader(const std::string& path) : buf_(1 << 22) {
+        f_ = fopen(path.c_str(), "rb");
+        if (!f_) throw std::runtime_error("Cannot open file " + path);
+    }
+    ~SeqReader() { if (f_) fclose(f_); }
+    bool next(SeqRecord& r) {
+        int c;
+        if (last_ == 0) {
+            while ((c = getc_()) != -1 && c != '>' && c != '@') {}
+            if (c == -1) return false;
+            last_ = c;
+        }
+        std::string header;
+        if (!getline_(header, false)) return false;
+        size_t sp = 0;
+        while (sp < header.size() && !isspace((unsigned char)header[sp])) sp++;
+        r.name.assign(header, 0, sp);
+        r.seq.clear();
+        while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@') {
+            if (c == '\n') continue;
+            r.seq.push_back((char)c);
+            getline_(r.seq, true);
+        }
+        if (c == '>' || c == '@') last_ = c;
+        if (c == '+') {
+            std::string q;
+            getline_(q, false);  // rest of the '+' line
+            size_t qlen = 0;
+            while (qlen < r.seq.size() && getline_(q, false)) qlen += q.size();
+            last_ = 0;
+        }
+        if (c == -1) last_ = 0;
+        return true;
+    }
+};
+
+inline void for_each_sequence(const std::string& uri, const std::function<void(SeqRecord&)>& fn) {
+    size_t start = 0;
+    while (start <= uri.size()) {
+        size_t c = uri.find(',', start);
+        std::string path = uri.substr(start, c == std::string::npos ? std::string::npos : c - start);
+        if (!path.empty()) {
+            SeqReader rd(path);
+            SeqRecord r;
+            while (rd.next(r)) fn(r);
+        }
+        if (c == std::string::npos) break;
+        start = c + 1;
+    }
+}
+
+}  // namespace mtg

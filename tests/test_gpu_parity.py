@@ -1,0 +1,202 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path through the C ABI (mindthegap_b200.Finder ->
+libmtg_b200.so) against the oracle (oracle/, pinned by tests/test_oracle_golden.py) and against the committed outputs of
+the unmodified reference binary (tests/golden/ref_outputs) and the reference's own gold files (tests/golden/full)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import oracle_py
+from tests.cases import CASES, GOLD, case_paths, expected
+
+pytestmark = pytest.mark.gpu
+
+
+def _finder(case_or_k, flags=()):
+    import mindthegap_b200 as m
+    if isinstance(case_or_k, dict):
+        p = m.FindParams.from_cli(["-kmer-size", str(case_or_k["k"])] + list(case_or_k["flags"]))
+    else:
+        p = m.FindParams.from_cli(["-kmer-size", str(case_or_k)] + list(flags))
+    return m.Finder(p)
+
+
+def _stream(uri):
+    recs = oracle_py.read_sequences(uri)
+    return b"\n".join(s for _, s in recs) + b"\n", recs
+
+
+def _sorted_solid(lo, hi, ab):
+    order = np.lexsort((lo, hi))
+    return lo[order], hi[order], ab[order]
+
+
+COUNT_CASES = ["full", "full_k63", "full_k21_amin3", "inserts_ref10k", "hetero_insert", "syn_tiny_k31", "syn_tiny_k32", "syn_tiny_k63",
+               "syn_small_k31", "syn_small_k47_homo"]
+
+
+@pytest.mark.parametrize("name", COUNT_CASES)
+def test_count_matches_oracle(name):
+    case = CASES[name]
+    reads, _ = case_paths(case)
+    stream, _ = _stream(reads)
+    f = _finder(case)
+    f.push_reads(stream)
+    f.finish_count()
+    o = oracle_py.count_stream(stream, case["k"], abundance_min=f.params.abundance_min, abundance_max=f.params.abundance_max, nthreads=4)
+    assert f.threshold == o["threshold"]
+    assert f.cutoff_auto == o["cutoff_auto"]
+    assert (f.histogram() == o["histogram"]).all()
+    assert f.nb_solid == len(o["lo"])
+    lo, hi, ab = _sorted_solid(*f.export_solid())
+    assert (lo == o["lo"]).all() and (hi == o["hi"]).all() and (ab == o["abundance"]).all()
+    st = f.stats()
+    assert int(st["count.nb_valid_kmers"]) == o["nb_kmers_valid"]
+    f.close()
+
+
+def test_count_multiple_batches_and_ragged_input():
+    """Reads pushed in several batches, with N's, lower case, reads shorter than k, empty reads, and an empty batch."""
+    rng = np.random.default_rng(11)
+    alphabet = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    reads = []
+    for i in range(4000):
+        n = int(rng.integers(0, 180))
+        reads.append(bytes(rng.choice(alphabet, size=n, p=[.2, .2, .2, .2, .045, .045, .045, .045, .02])))
+    reads += reads[:2500] + reads[:1200]
+    for k in (17, 31, 33, 63):
+        f = _finder(k, ["-abundance-min", "2"])
+        parts = [reads[:1000], [], reads[1000:1001], reads[1001:]]
+        for part in parts:
+            if part:
+                f.push_reads(b"\n".join(part) + b"\n")
+        f.finish_count()
+        o = oracle_py.count_stream(b"\n".join(reads), k, abundance_min=2, nthreads=4)
+        lo, hi, ab = _sorted_solid(*f.export_solid())
+        assert f.nb_solid == len(o["lo"])
+        assert (lo == o["lo"]).all() and (hi == o["hi"]).all() and (ab == o["abundance"]).all()
+        assert (f.histogram() == o["histogram"]).all()
+        f.close()
+
+
+def test_count_heavy_minimizer_multipass():
+    """A low-complexity dataset: one minimizer bin far larger than a shared-memory table -> multi-pass groups."""
+    rng = np.random.default_rng(3)
+    core = b"ACACACACACACACACACACAC"
+    reads = []
+    for i in range(6000):
+        tail = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=60))
+        reads.append(core + tail + core)
+    reads = reads + reads
+    stream = b"\n".join(reads) + b"\n"
+    f = _finder(31, ["-abundance-min", "2"])
+    f.push_reads(stream)
+    f.finish_count()
+    assert f.stats()["count.nb_multipass_groups"] >= 1
+    o = oracle_py.count_stream(stream, 31, abundance_min=2, nthreads=4)
+    lo, hi, ab = _sorted_solid(*f.export_solid())
+    assert (lo == o["lo"]).all() and (ab == o["abundance"]).all()
+    f.close()
+
+
+def test_count_empty_input():
+    f = _finder(31)
+    f.push_reads(b"ACGT\nNNNN\n")
+    f.finish_count()
+    assert f.nb_solid == 0 and f.threshold == 3
+    f.close()
+
+
+@pytest.mark.parametrize("name", ["full", "full_k63", "syn_tiny_k32", "syn_small_k31"])
+def test_membership_structures_bit_exact(name):
+    """Bloom, cascading Blooms, BooPHF level bits and the reference-repeat Bloom equal the oracle's byte for byte."""
+    case = CASES[name]
+    reads, ref = case_paths(case)
+    stream, _ = _stream(reads)
+    rstream, rrecs = _stream(ref)
+    f = _finder(case)
+    f.push_reads(stream)
+    f.finish_count()
+    f.set_reference(rstream)
+    lo, hi, ab = f.export_solid()
+    g = oracle_py.Graph(lo, hi, case["k"])
+    g.set_reference(rstream, f.params.het_max_occ)
+    info = g.info()
+    st = f.stats()
+    assert int(st["graph.bloom_bits"]) == info["bloom"]
+    assert int(st["graph.nb_critical"]) == info["nb_critical"]
+    assert int(st["graph.bloom2_bits"]) == info["bloom2"] and int(st["graph.bloom3_bits"]) == info["bloom3"] and int(st["graph.bloom4_bits"]) == info["bloom4"]
+    assert int(st["graph.cfp_set"]) == info["cfp_set"]
+    assert int(st["ref.nb_repeated"]) == info["ref_repeated"]
+    for which in range(6):
+        a, b = f.copy_bits(which), g.bits(which)
+        assert len(a) == len(b), which
+        assert (a == b).all(), which
+    # contains on solid k-mers, their 8 neighbours and random k-mers
+    rng = np.random.default_rng(1)
+    k = case["k"]
+    n = 20000
+    if k <= 31:
+        qlo = rng.integers(0, 1 << (2 * k), size=n, dtype=np.uint64); qhi = np.zeros(n, dtype=np.uint64)
+    else:
+        qlo = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * 2 + rng.integers(0, 2, size=n, dtype=np.uint64)
+        qhi = rng.integers(0, 1 << (2 * k - 64), size=n, dtype=np.uint64)
+    sel = rng.integers(0, len(lo), size=5000)
+    qlo = np.concatenate([qlo, lo[sel]]); qhi = np.concatenate([qhi, hi[sel]])
+    got = f.contains(qlo, qhi if k > 31 else None)
+    # oracle takes canonical k-mers: canonicalise through the oracle's revcomp
+    import ctypes as C
+    L = oracle_py.load()
+    clo = qlo.copy(); chi = qhi.copy()
+    for i in range(len(qlo)):
+        a, b = C.c_uint64(), C.c_uint64()
+        L.mtgo_revcomp(int(qlo[i]), int(qhi[i]), k, C.byref(a), C.byref(b))
+        if (b.value, a.value) < (int(qhi[i]), int(qlo[i])):
+            clo[i], chi[i] = a.value, b.value
+    exp = g.query(clo, chi)
+    assert ((got & 1) == (exp & 1)).all()
+    assert ((got & 2) == (exp & 2)).all()
+    # dense features of every reference sequence
+    for nm, seq in rrecs:
+        if len(seq) < k:
+            continue
+        ft, rp, c4 = f.features(seq)
+        eft, erp = g.features(seq)
+        assert (ft == eft).all() and (rp == erp).all()
+    g.close(); f.close()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_find_outputs_equal_reference(name):
+    """End to end through the C ABI: same .breakpoints text and VCF records as the unmodified reference binary."""
+    case = CASES[name]
+    reads, ref = case_paths(case)
+    stream, _ = _stream(reads)
+    _, rrecs = _stream(ref)
+    f = _finder(case)
+    bk, vcf = f.find(stream, rrecs)
+    ebk, evcf, einfo = expected(name)
+    assert bk == ebk
+    assert vcf == evcf
+    if name == "full":
+        assert bk == open(os.path.join(GOLD, "full", "gold.breakpoints")).read()
+        assert f.cutoff_auto == 7 and f.nb_solid == 7419
+    f.close()
+
+
+def test_load_solid_gives_same_scan():
+    """`-graph` path: uploading an exported solid set reproduces the outputs (src/Finder.cpp:274-279)."""
+    case = CASES["full"]
+    reads, ref = case_paths(case)
+    stream, _ = _stream(reads)
+    _, rrecs = _stream(ref)
+    f = _finder(case)
+    bk, vcf = f.find(stream, rrecs)
+    lo, hi, ab = f.export_solid()
+    g = _finder(case)
+    g.load_solid(lo)
+    g.set_reference(b"\n".join(s for _, s in rrecs))
+    for nm, seq in rrecs:
+        g.scan_reference(nm, seq)
+    assert g.breakpoints_text() == bk and g.vcf_text() == vcf
+    f.close(); g.close()
