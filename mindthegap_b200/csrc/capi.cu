@@ -9,6 +9,7 @@
 #include "seqio.hpp"
 
 using namespace mtg;
+typedef unsigned __int128 hu128;  // host-only 128-bit integer for the replay (g++); device code uses mtg::u128
 
 static thread_local std::string g_last_error;
 
@@ -30,7 +31,7 @@ struct mtg_ctx {
     CountStats ref_count_stats;
     // replay
     std::unique_ptr<Replayer<uint64_t>> rp64;
-    std::unique_ptr<Replayer<u128>> rp128;
+    std::unique_ptr<Replayer<hu128>> rp128;
     std::vector<uint8_t> feat, rep;
     double ms_features = 0, ms_replay = 0, ms_graph_build = 0;
     uint64_t scan_positions = 0, scan_valid = 0, scan_in_graph = 0, scan_table_probes = 0, scan_fallback = 0;
@@ -60,7 +61,7 @@ static void make_replayers(mtg_ctx* c) {
     if (c->p.kmer_size <= 31) {
         c->rp64.reset(new Replayer<uint64_t>(o, [c](const uint64_t* km, size_t n, uint8_t* out) { c->graph->observer_probe_batch(km, nullptr, n, out); }));
     } else {
-        c->rp128.reset(new Replayer<u128>(o, [c](const u128* km, size_t n, uint8_t* out) {
+        c->rp128.reset(new Replayer<hu128>(o, [c](const hu128* km, size_t n, uint8_t* out) {
             c->tmp_lo.resize(n); c->tmp_hi.resize(n);
             for (size_t i = 0; i < n; i++) { c->tmp_lo[i] = (uint64_t)km[i]; c->tmp_hi[i] = (uint64_t)(km[i] >> 64); }
             c->graph->observer_probe_batch(c->tmp_lo.data(), c->tmp_hi.data(), n, out);

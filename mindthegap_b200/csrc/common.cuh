@@ -2,7 +2,7 @@
 //   base code A=0 C=1 T=2 G=3 = (ascii>>1)&3           (gatb-core tools/misc/api/Data.hpp:178)
 //   k-mer value = base-4 polynomial, first base most significant (kmer/impl/Model.hpp:637-657)
 //   revcomp / canonical=min(fwd,rc)                      (tools/math/LargeInt1.pri:137-155, Model.hpp:294)
-// Key type K is uint64_t for k<=31 and unsigned __int128 for 32<=k<=63 (native ATOMS/ATOMG.CAS.128 on sm_100a).
+// Key type K is uint64_t for k<=31 and mtg::u128 (two 64-bit words) for 32<=k<=63 (native ATOMS/ATOMG.CAS.128 on sm_100a).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,7 +13,44 @@
 
 namespace mtg {
 
-typedef unsigned __int128 u128;
+// 128-bit key as two explicit 64-bit words. We deliberately do NOT use `unsigned __int128` in device code: nvcc 12.9
+// miscompiled a (x >> 2) & mask -> brev-based revcomp chain on __int128 for sm_100a (observed on the B200: one wrong
+// bit when bit 63 of the low word was set), so every 128-bit operation is spelled out on 64-bit words here.
+struct __align__(16) u128 {
+    uint64_t lo, hi;
+    u128() = default;
+    __host__ __device__ constexpr u128(uint64_t l) : lo(l), hi(0) {}
+    __host__ __device__ constexpr u128(uint64_t l, uint64_t h) : lo(l), hi(h) {}
+    __host__ __device__ constexpr u128(int v) : lo((uint64_t)(int64_t)v), hi(v < 0 ? ~0ull : 0ull) {}
+    __host__ __device__ constexpr u128(unsigned v) : lo(v), hi(0) {}
+    __host__ __device__ explicit operator uint64_t() const { return lo; }
+    __host__ __device__ explicit operator unsigned() const { return (unsigned)lo; }
+    __host__ __device__ explicit operator int() const { return (int)lo; }
+};
+#define MTG_HD_ __host__ __device__ __forceinline__
+MTG_HD_ u128 operator<<(u128 a, int s) {
+    if (s == 0) return a;
+    if (s >= 128) return u128(0ull, 0ull);
+    if (s >= 64) return u128(0ull, a.lo << (s - 64));
+    return u128(a.lo << s, (a.hi << s) | (a.lo >> (64 - s)));
+}
+MTG_HD_ u128 operator>>(u128 a, int s) {
+    if (s == 0) return a;
+    if (s >= 128) return u128(0ull, 0ull);
+    if (s >= 64) return u128(a.hi >> (s - 64), 0ull);
+    return u128((a.lo >> s) | (a.hi << (64 - s)), a.hi >> s);
+}
+MTG_HD_ u128 operator&(u128 a, u128 b) { return u128(a.lo & b.lo, a.hi & b.hi); }
+MTG_HD_ u128 operator|(u128 a, u128 b) { return u128(a.lo | b.lo, a.hi | b.hi); }
+MTG_HD_ u128 operator^(u128 a, u128 b) { return u128(a.lo ^ b.lo, a.hi ^ b.hi); }
+MTG_HD_ u128 operator~(u128 a) { return u128(~a.lo, ~a.hi); }
+MTG_HD_ u128 operator+(u128 a, u128 b) { uint64_t l = a.lo + b.lo; return u128(l, a.hi + b.hi + (l < a.lo ? 1ull : 0ull)); }
+MTG_HD_ u128 operator-(u128 a, u128 b) { uint64_t l = a.lo - b.lo; return u128(l, a.hi - b.hi - (a.lo < b.lo ? 1ull : 0ull)); }
+MTG_HD_ bool operator==(u128 a, u128 b) { return a.lo == b.lo && a.hi == b.hi; }
+MTG_HD_ bool operator!=(u128 a, u128 b) { return !(a == b); }
+MTG_HD_ bool operator<(u128 a, u128 b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+MTG_HD_ u128& operator>>=(u128& a, int s) { a = a >> s; return a; }
+MTG_HD_ u128& operator<<=(u128& a, int s) { a = a << s; return a; }
 
 #define MTG_HD __host__ __device__ __forceinline__
 #define MTG_D __device__ __forceinline__
@@ -54,7 +91,11 @@ template <class T> struct DevBuf {
 };
 
 // ----------------------------------------------------------------------------------------------- k-mer arithmetic
-template <class K> MTG_HD K kmask(int k) { return (K(1) << (2 * k)) - K(1); }
+template <class K> MTG_HD K kmask(int k);
+template <> MTG_HD uint64_t kmask<uint64_t>(int k) { return k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull); }
+template <> MTG_HD u128 kmask<u128>(int k) {
+    return k >= 64 ? u128(~0ull, ~0ull) : (k >= 32 ? u128(~0ull, k == 32 ? 0ull : ((1ull << (2 * k - 64)) - 1ull)) : u128((1ull << (2 * k)) - 1ull, 0ull));
+}
 
 MTG_HD uint64_t rc_word(uint64_t x) {  // reverse-complement of a full 32-nt word
 #ifdef __CUDA_ARCH__
@@ -70,19 +111,16 @@ MTG_HD uint64_t rc_word(uint64_t x) {  // reverse-complement of a full 32-nt wor
     return x ^ 0xAAAAAAAAAAAAAAAAULL;
 }
 MTG_HD uint64_t revcomp(uint64_t x, int k) { return rc_word(x) >> (2 * (32 - k)); }
-MTG_HD u128 revcomp(u128 x, int k) {
-    u128 r = ((u128)rc_word((uint64_t)x) << 64) | (u128)rc_word((uint64_t)(x >> 64));
-    return r >> (2 * (64 - k));
-}
+MTG_HD u128 revcomp(u128 x, int k) { return u128(rc_word(x.hi), rc_word(x.lo)) >> (2 * (64 - k)); }
 template <class K> MTG_HD K canonical(K x, int k) { K r = revcomp(x, k); return r < x ? r : x; }
 
 MTG_HD uint64_t lo64(uint64_t x) { return x; }
 MTG_HD uint64_t hi64(uint64_t) { return 0; }
-MTG_HD uint64_t lo64(u128 x) { return (uint64_t)x; }
-MTG_HD uint64_t hi64(u128 x) { return (uint64_t)(x >> 64); }
+MTG_HD uint64_t lo64(u128 x) { return x.lo; }
+MTG_HD uint64_t hi64(u128 x) { return x.hi; }
 template <class K> MTG_HD K make_key(uint64_t lo, uint64_t hi);
 template <> MTG_HD uint64_t make_key<uint64_t>(uint64_t lo, uint64_t) { return lo; }
-template <> MTG_HD u128 make_key<u128>(uint64_t lo, uint64_t hi) { return ((u128)hi << 64) | lo; }
+template <> MTG_HD u128 make_key<u128>(uint64_t lo, uint64_t hi) { return u128(lo, hi); }
 
 // GATB hash1 (LargeInt1.pri:158-171); multi-word keys xor the word hashes (LargeInt.hpp:738-748)
 MTG_HD uint64_t gatb_hash64(uint64_t key, uint64_t seed) {
@@ -98,7 +136,7 @@ MTG_HD uint64_t gatb_hash64(uint64_t key, uint64_t seed) {
     return hash;
 }
 MTG_HD uint64_t gatb_hash1(uint64_t key, uint64_t seed) { return gatb_hash64(key, seed); }
-MTG_HD uint64_t gatb_hash1(u128 key, uint64_t seed) { return gatb_hash64((uint64_t)key, seed) ^ gatb_hash64((uint64_t)(key >> 64), seed); }
+MTG_HD uint64_t gatb_hash1(u128 key, uint64_t seed) { return gatb_hash64(key.lo, seed) ^ gatb_hash64(key.hi, seed); }
 
 // Our own mixing hash (not GATB's): murmur3 finaliser, used for table slots / buckets / pass selection.
 MTG_HD uint64_t mix64(uint64_t x) {
@@ -106,31 +144,31 @@ MTG_HD uint64_t mix64(uint64_t x) {
     return x;
 }
 MTG_HD uint64_t key_hash(uint64_t k) { return mix64(k); }
-MTG_HD uint64_t key_hash(u128 k) { return mix64((uint64_t)k ^ mix64((uint64_t)(k >> 64) + 0x9E3779B97F4A7C15ULL)); }
+MTG_HD uint64_t key_hash(u128 k) { return mix64(k.lo ^ mix64(k.hi + 0x9E3779B97F4A7C15ULL)); }
 
 // ----------------------------------------------------------------------------------------------- atomics
 MTG_D uint64_t cas_global(uint64_t* a, uint64_t cmp, uint64_t val) {
     return (uint64_t)atomicCAS((unsigned long long*)a, (unsigned long long)cmp, (unsigned long long)val);
 }
 MTG_D u128 cas_global(u128* addr, u128 cmp, u128 val) {
-    uint64_t clo = (uint64_t)cmp, chi = (uint64_t)(cmp >> 64), vlo = (uint64_t)val, vhi = (uint64_t)(val >> 64), olo, ohi;
+    uint64_t clo = cmp.lo, chi = cmp.hi, vlo = val.lo, vhi = val.hi, olo, ohi;
     asm volatile(
         "{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%3, %4};\n\tmov.b128 v, {%5, %6};\n\t"
         "atom.global.cas.b128 o, [%2], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
         : "=l"(olo), "=l"(ohi) : "l"(addr), "l"(clo), "l"(chi), "l"(vlo), "l"(vhi) : "memory");
-    return ((u128)ohi << 64) | olo;
+    return u128(olo, ohi);
 }
 MTG_D uint64_t cas_shared(uint64_t* a, uint64_t cmp, uint64_t val) {
     return (uint64_t)atomicCAS((unsigned long long*)a, (unsigned long long)cmp, (unsigned long long)val);
 }
 MTG_D u128 cas_shared(u128* addr, u128 cmp, u128 val) {
-    uint64_t clo = (uint64_t)cmp, chi = (uint64_t)(cmp >> 64), vlo = (uint64_t)val, vhi = (uint64_t)(val >> 64), olo, ohi;
+    uint64_t clo = cmp.lo, chi = cmp.hi, vlo = val.lo, vhi = val.hi, olo, ohi;
     uint32_t sa = (uint32_t)__cvta_generic_to_shared(addr);
     asm volatile(
         "{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%3, %4};\n\tmov.b128 v, {%5, %6};\n\t"
         "atom.shared.cas.b128 o, [%2], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
         : "=l"(olo), "=l"(ohi) : "r"(sa), "l"(clo), "l"(chi), "l"(vlo), "l"(vhi) : "memory");
-    return ((u128)ohi << 64) | olo;
+    return u128(olo, ohi);
 }
 
 // Extract `nb` (<=32) bases starting at base position `pos` from the 2-bit packed array (32 bases per word, first
@@ -150,8 +188,9 @@ template <> MTG_D uint64_t extract_kmer<uint64_t>(const uint64_t* __restrict__ p
 template <> MTG_D u128 extract_kmer<u128>(const uint64_t* __restrict__ packed, uint64_t pos, int k) {
     uint64_t a = pos >> 5;
     int off = (int)(pos & 31) * 2;
-    u128 x = (((u128)packed[a] << 64) | packed[a + 1]) << off;
-    if (off) x |= (u128)(packed[a + 2] >> (64 - off));
+    uint64_t w0 = packed[a], w1 = packed[a + 1];
+    u128 x(w1, w0);
+    if (off) x = u128((w1 << off) | (packed[a + 2] >> (64 - off)), (w0 << off) | (w1 >> (64 - off)));
     return x >> (128 - 2 * k);
 }
 

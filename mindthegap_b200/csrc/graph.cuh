@@ -51,7 +51,7 @@ MTG_D uint64_t simplehash16_dev(const uint64_t* __restrict__ rnd, uint64_t key, 
     return res;
 }
 MTG_D uint64_t simplehash16_dev(const uint64_t* __restrict__ rnd, u128 key128, int shift) {   // LargeInt.hpp:792-800
-    uint64_t key = (uint64_t)key128;
+    uint64_t key = key128.lo;
     uint64_t input = key >> shift;
     uint64_t res = __ldg(rnd + (input & 255));
     input >>= 8;
@@ -150,7 +150,7 @@ struct MphfState {
     }
     MTG_HD void init(u128 key, uint64_t seed) {
         uint64_t a = seed, b = seed, c = 0x9e3779b97f4a7c13ULL;
-        c += 16; b += (uint64_t)(key >> 64); a += (uint64_t)key;
+        c += 16; b += key.hi; a += key.lo;
         jenkins_mix(a, b, c);
         s0 = a; s1 = c;
     }
