@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- `MindTheGap find` hot path on B200 (contract: see DESIGN.md "Measurement").
+
+One "step" = one whole `find` over the workload: count the read k-mers (solid set, auto threshold), build the
+membership structures, scan every reference k-mer and replay the gap finders -> .breakpoints + .vcf text.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]        our CUDA engine through the C ABI (libmtg_b200.so)
+  python bench.py --impl reference ...                        the CPU implementation (oracle port, all host threads)
+
+Workload (BASELINE.json configs[1]): synthetic 4.6 Mbp genome, 50x 2x150 bp reads, 200 planted homozygous insertions,
+k=31, generated deterministically in memory by tools/synth.py (seed 20241). Under torchrun (N>1) the reads are sharded
+across ranks (weak scaling: every rank brings its own 50x read set of its own 4.6 Mbp genome segment).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+K = 31
+SEED = 20241
+METRIC = "read+reference k-mers processed per second by one whole find (count + graph + scan)"
+UNIT = "kmers/s"
+
+
+# ---------------------------------------------------------------------------------------------------- workload
+def make_workload(scale=1.0, seed=SEED, genome_mult=1):
+    """cfg2 (optionally scaled): returns dict(refs=[(name, uint8 array)], stream=uint8 array of '\\n'-separated reads,
+    mats, n_reads, read_len, read_kmers, ref_kmers)."""
+    import synth
+    cfg = dict(synth.CONFIGS["cfg2"])
+    cfg["genome_len"] = int(cfg["genome_len"] * scale * genome_mult)
+    cfg["n_hom"] = max(1, int(cfg["n_hom"] * scale * genome_mult))
+    refs, mats, truth = synth.reads_in_memory(cfg, seed)
+    L = cfg["read_len"]
+    tot = sum(m.shape[0] for m in mats)
+    buf = np.empty((tot, L + 1), dtype=np.uint8)
+    buf[:, L] = 10
+    o = 0
+    for m in mats:
+        buf[o:o + len(m), :L] = m
+        o += len(m)
+    return dict(cfg=cfg, refs=refs, stream=buf.reshape(-1), n_reads=tot, read_len=L, read_kmers=tot * max(0, L - K + 1),
+                ref_kmers=sum(max(0, len(s) - K + 1) for _, s in refs), truth=truth,
+                name="cfg2: synthetic %.2f Mbp genome, %dx 2x%dbp reads, %d planted homozygous insertions, k=%d" % (
+                    cfg["genome_len"] / 1e6, cfg["coverage"], L, cfg["n_hom"], K))
+
+
+def write_inputs(wl, d):
+    """Write the workload as FASTA files for the CPU implementation; returns (reads_uri, ref_path)."""
+    import synth
+    os.makedirs(d, exist_ok=True)
+    L = wl["read_len"]
+    rows = wl["stream"].reshape(-1, L + 1)
+    out = np.empty((rows.shape[0], L + 4), dtype=np.uint8)
+    out[:, 0] = ord(">"); out[:, 1] = ord("r"); out[:, 2] = 10
+    out[:, 3:] = rows
+    reads = os.path.join(d, "reads.fa")
+    with open(reads, "wb") as f:
+        f.write(out.tobytes())
+    ref = os.path.join(d, "ref.fa")
+    synth.write_fasta(ref, wl["refs"])
+    return reads, ref
+
+
+# ---------------------------------------------------------------------------------------------------- CPU implementation
+def run_cpu_find(wl, cores, workdir, tag="cpu"):
+    """Time the CPU implementation of the path (oracle port; the reference itself cannot be built without its cmake
+    build system) on `wl` with `cores` threads. Returns dict(seconds, value, breakpoints, vcf, info)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    exe = os.path.join(ROOT, "oracle", "_build", "oracle_find")
+    reads, ref = write_inputs(wl, workdir)
+    out = os.path.join(workdir, tag)
+    r = subprocess.run([exe, "find", "-in", reads, "-ref", ref, "-kmer-size", str(K), "-out", out, "-nb-cores", str(cores)],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, check=True)
+    info = dict(l.split(" ", 1) for l in r.stdout.strip().splitlines())
+    secs = sum(float(info[k]) for k in ("time_count", "time_graph", "time_refbloom", "time_scan"))
+    bk = open(out + ".breakpoints").read()
+    vcf = "".join(l for l in open(out + ".othervariants.vcf") if not l.startswith("#"))
+    return dict(seconds=secs, value=(wl["read_kmers"] + wl["ref_kmers"]) / secs, breakpoints=bk, vcf=vcf, info=info)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    wl = make_workload(scale=args.cpu_scale)
+    times = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for i in range(args.warmup + args.steps):
+            r = run_cpu_find(wl, cores, tmp)
+            if i >= args.warmup:
+                times.append(r["seconds"])
+    t = sum(times) / len(times)
+    value = (wl["read_kmers"] + wl["ref_kmers"]) / t
+    sample = "%s (scale %.3g of the 4.6 Mbp workload; compute time of count+graph+refbloom+scan, file parsing excluded)" % (
+        wl["name"], args.cpu_scale)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": wl["name"], "kmer_size": K, "abundance_min": "auto", "sample_scale": args.cpu_scale},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "read_kmers_counted_per_s": wl["read_kmers"] / float(r["info"]["time_count"]),
+            "ref_kmers_queried_per_s": wl["ref_kmers"] / float(r["info"]["time_scan"])}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / power / throttle reasons of one GPU during the timed region (NVML in a thread, 50 ms period)."""
+
+    def __init__(self, index=0, period=0.05):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.stop_flag = threading.Event()
+        self.th = None
+        self.err = None
+
+    def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = "nvml unavailable: %s" % e
+            return
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def _run(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                r = int(get_reasons(self.h))
+                self.samples.append((sm, pw))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                break
+            self.stop_flag.wait(self.period)
+
+    def stop(self):
+        if self.th is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "not sampled"]}
+        self.stop_flag.set()
+        self.th.join(timeout=2)
+        sm = [x[0] for x in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "power_w_max": max(x[1] for x in self.samples) if self.samples else None, "samples": len(sm),
+                "reasons": sorted(self.reasons), "how": "NVML, %d ms period, during the timed resident steps" % int(self.period * 1e3)}
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+def own_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import mindthegap_b200 as m
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = m.load_library()
+
+    # every rank brings the read set of its own genome segment (weak scaling); N=1 is exactly cfg2
+    wl = make_workload(scale=args.scale, seed=SEED + 1000 * rank)
+    params = m.FindParams(kmer_size=K, device=local_rank)
+    stream_host = torch.from_numpy(wl["stream"]).pin_memory()
+    stream_np = stream_host.numpy()
+    ref_stream = np.concatenate([np.concatenate([s, np.array([10], dtype=np.uint8)]) for _, s in wl["refs"]])
+    ref_host = torch.from_numpy(ref_stream).pin_memory()
+    stream_dev = stream_host.cuda()
+    ref_dev = ref_host.cuda()
+    ref_offsets = np.cumsum([0] + [len(s) + 1 for _, s in wl["refs"]])
+    nbytes = int(stream_np.size)
+
+    def one_find(resident):
+        f = m.Finder(params)
+        f.reserve(nbytes)
+        if resident:
+            f.push_reads_device(stream_dev.data_ptr(), nbytes)
+        else:
+            f.push_reads(stream_np)
+        f.finish_count()
+        if resident:
+            f.set_reference_device(ref_dev.data_ptr(), int(ref_stream.size))
+        else:
+            f.set_reference(ref_host.numpy())
+        for i, (name, seq) in enumerate(wl["refs"]):
+            if resident:
+                f.scan_reference_device(name, seq, ref_dev.data_ptr() + int(ref_offsets[i]))
+            else:
+                f.scan_reference(name, seq)
+        bk, vcf = f.breakpoints_text(), f.vcf_text()
+        st = f.stats()
+        st["nb_solid"] = f.nb_solid
+        st["threshold"] = f.threshold
+        st.update({"find." + k: v for k, v in f.find_counters().items()})
+        f.close()
+        return bk, vcf, st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident, steps, warmup):
+        for _ in range(warmup):
+            out = one_find(resident)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        stats = []
+        for _ in range(steps):
+            out = one_find(resident)
+            stats.append(out[2])
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, wall / steps, out, stats
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, wall_res, out_res, stats = timed(True, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, wall_e2e, out_e2e, _ = timed(False, args.steps, max(1, args.warmup // 2))
+    assert out_res[0] == out_e2e[0] and out_res[1] == out_e2e[1], "resident and host-buffer runs disagree"
+
+    tot_kmers = wl["read_kmers"] + wl["ref_kmers"]
+    if world > 1:
+        t = torch.tensor([wl["read_kmers"], wl["ref_kmers"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        read_kmers, ref_kmers = float(t[0].item()), float(t[1].item())
+        tot_kmers = read_kmers + ref_kmers
+    else:
+        read_kmers, ref_kmers = float(wl["read_kmers"]), float(wl["ref_kmers"])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- per-kernel roofline (CUDA-event times measured inside the library on its own stream, averaged over the steps)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    avg = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
+    nk = wl["read_kmers"]
+    count_stage_ms = avg["count.ms_pack"] + avg["count.ms_extract"] + avg["count.ms_scatter"] + avg["count.ms_count"] + avg["count.ms_filter"]
+    probes = avg["scan.table_probes"]
+    kernels = [
+        {"kernel": "count stage (pack+superkmer+scatter+count+filter)", "ms": count_stage_ms, "bytes": 16.25 * nk,
+         "note": "SURVEY 8d: 2*sizeof(kmer)+0.25 B per read k-mer"},
+        {"kernel": "count_kernel", "ms": avg["count.ms_count"], "bytes": 16.25 * nk, "note": "same bytes, count kernel alone"},
+        {"kernel": "superkmer_kernel", "ms": avg["count.ms_extract"], "bytes": 0.375 * nbytes + 8.0 * avg["count.nb_records"],
+         "note": "packed bases + invalid mask in, 8-byte records out"},
+        {"kernel": "pack_kernel", "ms": avg["count.ms_pack"], "bytes": 1.375 * nbytes, "note": "ASCII in, 2-bit words + mask out"},
+        {"kernel": "features_kernel (probe)", "ms": avg["scan.ms_features"], "bytes": 128.0 * probes,
+         "note": "SURVEY 8d: 128 B x (R + 8 R_solid) table probes"},
+    ]
+    for kq in kernels:
+        kq["achieved_gbs"] = kq["bytes"] / (kq["ms"] * 1e-3) / 1e9 if kq["ms"] > 0 else None
+        kq["frac"] = kq["achieved_gbs"] / hbm if kq["achieved_gbs"] else None
+    dom = max([kernels[0], kernels[4]], key=lambda q: q["ms"])
+    gather_peak = lib.mtg_bench_random_gather(local_rank, 8 << 30, 1 << 26, 3)
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": None, "peak_source": peak_src, "ms_per_launch": dom["ms"],
+                "algorithmic_bytes_per_launch": dom["bytes"], "random_128B_gather_peak_gbs": gather_peak,
+                "probe_frac_of_gather_peak": (kernels[4]["achieved_gbs"] / gather_peak) if gather_peak > 0 and kernels[4]["achieved_gbs"] else None}
+
+    # ---- CPU baseline on a bounded sample + parity of the outputs on that sample
+    cpu = None
+    parity = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        swl = wl if args.cpu_scale >= args.scale else make_workload(scale=args.cpu_scale)
+        with tempfile.TemporaryDirectory() as tmp:
+            r = run_cpu_find(swl, cores, tmp)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%s, one whole find (scale %.3g), compute time %.2f s, file parsing excluded" % (swl["name"], args.cpu_scale, r["seconds"]),
+               "read_kmers_counted_per_s": swl["read_kmers"] / float(r["info"]["time_count"]),
+               "ref_kmers_queried_per_s": swl["ref_kmers"] / float(r["info"]["time_scan"])}
+        # parity on the same sample: GPU outputs vs the oracle's
+        f = m.Finder(params)
+        bk, vcf = f.find(swl["stream"], [(n, s) for n, s in swl["refs"]])
+        nsolid = f.nb_solid
+        f.close()
+        parity = {"sample_breakpoints_equal": bk == r["breakpoints"], "sample_vcf_equal": vcf == r["vcf"],
+                  "sample_nb_solid_equal": nsolid == int(r["info"]["nb_solid"]), "breakpoint_records": len(bk.splitlines()) // 4}
+        if not (parity["sample_breakpoints_equal"] and parity["sample_vcf_equal"] and parity["sample_nb_solid_equal"]):
+            raise SystemExit("bench.py: GPU outputs differ from the oracle on the sample: %s" % parity)
+
+    launches = int(sum(s["count.launches"] + s["graph.launches"] for s in stats))
+    line = {"metric": METRIC, "value": tot_kmers / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": wl["name"], "kmer_size": K, "abundance_min": "auto (inferred %d)" % int(avg["threshold"]),
+                       "per_gpu_read_bytes": nbytes, "l2_policy": "inputs (%.0f MB reads per GPU) larger than the 126 MB L2; every step starts from a fresh context" % (nbytes / 1e6),
+                       "parallelism": "1 process per GPU; reads sharded" if world > 1 else "single GPU"},
+            "e2e": {"value": tot_kmers / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes + ref_stream.size),
+                    "d2h_bytes_per_step": int(2 * wl["ref_kmers"] + len(out_e2e[0]) + len(out_e2e[1])), "ms_per_step": ms_e2e},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity": parity,
+            "read_kmers_counted_per_s": read_kmers / (1e-3 * (count_stage_ms + avg["count.ms_group"])),
+            "ref_kmers_queried_per_s": ref_kmers / (1e-3 * (avg["scan.ms_features"] + avg["scan.ms_replay"])),
+            "find_wall_s": wall_e2e,
+            "stage_ms": {k: avg[k] for k in sorted(avg) if ".ms_" in k},
+            "counts": {"read_kmers": read_kmers, "ref_kmers": ref_kmers, "nb_solid": avg["nb_solid"], "table_probes": probes,
+                       "bloom_emulations": avg["scan.bloom_emulations"], "observer_queries": avg["scan.observer_queries"],
+                       "breakpoint_records": len(out_res[0].splitlines()) // 4, "vcf_records": len(out_res[1].splitlines())}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the GPU workload (1.0 = cfg2)")
+    ap.add_argument("--cpu-scale", type=float, default=0.25, help="genome scale of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return own_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

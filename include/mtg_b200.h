@@ -83,6 +83,7 @@ int mtg_load_solid(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_
 /* ---- stage 2: reference scan. Replaces FindBreakpoints (src/FindBreakpoints.hpp) and its observers. */
 /* fillRefBloom (src/FindBreakpoints.hpp:956-1009): all reference sequences, separated by a non-ACGT byte. */
 int mtg_set_reference(mtg_ctx* ctx, const char* bases, uint64_t nbytes);
+int mtg_set_reference_device(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes);  /* same, bases already in HBM */
 
 /* Graph::contains / indegree / outdegree / ref Bloom for arbitrary k-mers (src/IFindObserver.hpp:85-117).
  * kmers are FORWARD values (any strand). contains: out bit0 = contains (bits 1..4: exact, bloom, cfp, mphf detail);
@@ -101,6 +102,9 @@ int mtg_sequence_features_device(mtg_ctx* ctx, const void* d_seq, uint64_t len, 
  * the context's two output buffers with the reference's exact formats (writeBreakpoint/writeVcfVariant/writeIndel,
  * :641-702); the bkpt id counter is shared and runs across calls (:872-875). */
 int mtg_scan_reference(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len);
+/* same with the sequence also resident in HBM (d_seq): no host->device copy; `seq` (host text) is still needed by the
+ * writers, which print raw reference text (src/FindInsertion.hpp:100-133, src/FindDeletion.hpp:62-171). */
+int mtg_scan_reference_device(mtg_ctx* ctx, const char* name, const char* seq, const void* d_seq, uint64_t len);
 /* Output accessors: pointers stay valid until the next scan/reset call on this context. */
 const char* mtg_breakpoints_text(mtg_ctx* ctx, uint64_t* nbytes);
 const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes);

@@ -37,7 +37,7 @@ EXPORTS = [
     "mtg_push_reads_device", "mtg_count_files", "mtg_count_finish", "mtg_get_threshold", "mtg_get_cutoff_auto", "mtg_get_nb_solid",
     "mtg_get_histogram", "mtg_get_stats", "mtg_stat_name", "mtg_export_solid", "mtg_load_solid", "mtg_set_reference",
     "mtg_contains_batch", "mtg_degree_batch", "mtg_ref_repeat_batch", "mtg_sequence_features", "mtg_sequence_features_device",
-    "mtg_scan_reference", "mtg_breakpoints_text", "mtg_vcf_text", "mtg_reset_outputs", "mtg_get_find_counters", "mtg_copy_bits",
+    "mtg_scan_reference", "mtg_scan_reference_device", "mtg_set_reference_device", "mtg_breakpoints_text", "mtg_vcf_text", "mtg_reset_outputs", "mtg_get_find_counters", "mtg_copy_bits",
     "mtg_bench_random_gather",
 ]
 
@@ -86,6 +86,8 @@ def load_library():
     L.mtg_sequence_features.argtypes = [vp, vp, C.c_uint64, u8p, u8p, u64p]
     L.mtg_sequence_features_device.argtypes = [vp, vp, C.c_uint64, vp, vp, u64p]
     L.mtg_scan_reference.argtypes = [vp, C.c_char_p, vp, C.c_uint64]
+    L.mtg_scan_reference_device.argtypes = [vp, C.c_char_p, vp, vp, C.c_uint64]
+    L.mtg_set_reference_device.argtypes = [vp, vp, C.c_uint64]
     L.mtg_breakpoints_text.restype = vp
     L.mtg_breakpoints_text.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mtg_vcf_text.restype = vp
@@ -231,6 +233,13 @@ class Finder:
     def set_reference(self, stream):
         a = np.frombuffer(stream, dtype=np.uint8) if isinstance(stream, (bytes, bytearray)) else np.ascontiguousarray(stream, dtype=np.uint8)
         self._check(self.L.mtg_set_reference(self.ctx, _ptr(a), a.size))
+
+    def set_reference_device(self, dev_ptr, nbytes):
+        self._check(self.L.mtg_set_reference_device(self.ctx, C.c_void_p(dev_ptr), nbytes))
+
+    def scan_reference_device(self, name, seq, dev_ptr):
+        a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        self._check(self.L.mtg_scan_reference_device(self.ctx, name.encode(), _ptr(a), C.c_void_p(dev_ptr), a.size))
 
     def _batch(self, fn, lo, hi):
         lo = np.ascontiguousarray(lo, dtype=np.uint64)

@@ -13,6 +13,32 @@ typedef unsigned __int128 hu128;  // host-only 128-bit integer for the replay (g
 
 static thread_local std::string g_last_error;
 
+// ---- process-wide cache of pinned host buffers (PinnedBuf, common.cuh)
+namespace {
+std::mutex g_pin_mu;
+std::vector<std::pair<void*, size_t>> g_pin_free;
+}
+void mtg::PinnedBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    release();
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        size_t best = g_pin_free.size();
+        for (size_t i = 0; i < g_pin_free.size(); i++)
+            if (g_pin_free[i].second >= bytes && (best == g_pin_free.size() || g_pin_free[i].second < g_pin_free[best].second)) best = i;
+        if (best != g_pin_free.size()) { p = g_pin_free[best].first; cap = g_pin_free[best].second; g_pin_free.erase(g_pin_free.begin() + best); return; }
+    }
+    size_t want = bytes + bytes / 4 + 4096;
+    MTG_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+    cap = want;
+}
+void mtg::PinnedBuf::release() {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin_free.push_back({p, cap});
+    p = nullptr; cap = 0;
+}
+
 struct mtg_ctx {
     mtg_params p;
     cudaStream_t stream = nullptr;
@@ -32,20 +58,27 @@ struct mtg_ctx {
     // replay
     std::unique_ptr<Replayer<uint64_t>> rp64;
     std::unique_ptr<Replayer<hu128>> rp128;
-    std::vector<uint8_t> feat, rep;
+    PinnedBuf feat, rep, interest;
     double ms_features = 0, ms_replay = 0, ms_graph_build = 0;
     uint64_t scan_positions = 0, scan_valid = 0, scan_in_graph = 0, scan_table_probes = 0, scan_fallback = 0;
     std::vector<uint64_t> tmp_lo, tmp_hi;
 };
 
+static void enter(mtg_ctx* c);
 #define MTG_TRY(ctx_expr) \
     try {                 \
-        if (!(ctx_expr)) { g_last_error = "null context"; return -1; }
+        if (!(ctx_expr)) { g_last_error = "null context"; return -1; } \
+        enter(ctx_expr);
 #define MTG_CATCH                                                                \
     }                                                                            \
     catch (const mtg::Error& e) { g_last_error = e.what(); return e.code; }      \
     catch (const std::exception& e) { g_last_error = e.what(); return -1; }      \
     return 0;
+
+static void enter(mtg_ctx* c) {  // every entry point: select the device, order allocations on the context's stream
+    MTG_CUDA(cudaSetDevice(c->p.device));
+    current_stream() = c->stream;
+}
 
 static ReplayOptions replay_options(const mtg_params& p) {
     ReplayOptions o;
@@ -94,6 +127,13 @@ mtg_ctx* mtg_create(const mtg_params* p) {
         if (c->p.het_max_occ < 1) c->p.het_max_occ = 1;  // src/Finder.cpp:317-319
         if (c->p.minimizer_size <= 0) c->p.minimizer_size = 10;
         MTG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        current_stream() = c->stream;
+        {   // keep freed device memory in the default pool: later allocations (and later contexts) cost no driver call
+            cudaMemPool_t pool;
+            MTG_CUDA(cudaDeviceGetDefaultMemPool(&pool, p->device));
+            uint64_t thr = ~0ull;
+            MTG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        }
         c->graph.reset(make_graph(c->p.kmer_size, c->stream));
         c->histogram.assign(HISTO_MAX + 1, 0);
         make_replayers(c.get());
@@ -107,8 +147,10 @@ mtg_ctx* mtg_create(const mtg_params* p) {
 void mtg_destroy(mtg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->p.device);
+    current_stream() = ctx->stream;
     ctx->counter.reset(); ctx->solid_owner.reset(); ctx->graph.reset();
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    current_stream() = nullptr;
     delete ctx;
 }
 
@@ -181,7 +223,7 @@ static const char* STAT_NAMES[] = {
     "graph.ms_table", "graph.ms_bloom", "graph.ms_critical", "graph.ms_cascade", "graph.ms_mphf", "graph.ms_build_total", "graph.launches",
     "ref.nb_repeated", "ref.bloom_bits",
     "scan.positions", "scan.valid", "scan.in_graph", "scan.table_probes", "scan.bloom_emulations", "scan.ms_features", "scan.ms_replay",
-    "scan.observer_queries", "scan.probe_batches"};
+    "scan.observer_queries", "scan.probe_batches", "scan.prefetched_queries", "scan.unforeseen_queries"};
 static const int NSTATS = sizeof(STAT_NAMES) / sizeof(STAT_NAMES[0]);
 const char* mtg_stat_name(int i) { return (i >= 0 && i < NSTATS) ? STAT_NAMES[i] : nullptr; }
 
@@ -190,7 +232,8 @@ int mtg_get_stats(mtg_ctx* ctx, double* out, int cap) {
     const CountStats& c = ctx->count_stats;
     const GraphStats& g = ctx->graph->stats();
     uint64_t oq = ctx->rp64 ? ctx->rp64->cnt.observer_queries : ctx->rp128->cnt.observer_queries;
-    uint64_t pb = ctx->rp64 ? ctx->rp64->cnt.probe_batches : ctx->rp128->cnt.probe_batches;
+    const ReplayCounters& rc = ctx->rp64 ? ctx->rp64->cnt : ctx->rp128->cnt;
+    uint64_t pb = rc.probe_batches;
     double v[] = {(double)c.nb_bases, (double)c.nb_valid_kmers, (double)c.nb_records, (double)c.nb_groups, (double)c.nb_items,
                   (double)c.nb_multipass_groups, (double)c.nb_candidates, (double)c.nb_solid, c.ms_pack, c.ms_extract, c.ms_group, c.ms_scatter,
                   c.ms_count, c.ms_filter, (double)c.launches,
@@ -198,7 +241,8 @@ int mtg_get_stats(mtg_ctx* ctx, double* out, int cap) {
                   g.ms_table, g.ms_bloom, g.ms_critical, g.ms_cascade, g.ms_mphf, ctx->ms_graph_build, (double)g.launches,
                   (double)g.ref_repeated, (double)g.ref_tai,
                   (double)ctx->scan_positions, (double)ctx->scan_valid, (double)ctx->scan_in_graph, (double)ctx->scan_table_probes,
-                  (double)ctx->scan_fallback, ctx->ms_features, ctx->ms_replay, (double)oq, (double)pb};
+                  (double)ctx->scan_fallback, ctx->ms_features, ctx->ms_replay, (double)oq, (double)pb, (double)rc.prefetched_queries,
+                  (double)rc.unforeseen_queries};
     int n = std::min(cap, NSTATS);
     for (int i = 0; i < n; i++) out[i] = v[i];
     return n;
@@ -228,18 +272,18 @@ int mtg_load_solid(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_
     MTG_CATCH
 }
 
-int mtg_set_reference(mtg_ctx* ctx, const char* bases, uint64_t nbytes) {
-    MTG_TRY(ctx)
+static void set_reference_impl(mtg_ctx* ctx, const char* bases, const void* d_bases, uint64_t nbytes) {
     MTG_CUDA(cudaSetDevice(ctx->p.device));
     const int k1 = ctx->p.kmer_size - 1;
     std::unique_ptr<ICounter> rc(make_counter(k1, std::min(ctx->p.minimizer_size, k1), ctx->stream, ctx->p.kmer_size <= 31 ? 64 : 128));
-    rc->push_host(bases, nbytes);
+    if (d_bases) rc->push_device((const uint8_t*)d_bases, nbytes); else rc->push_host(bases, nbytes);
     rc->finish(ctx->p.het_max_occ + 1, 2147483647LL);
     ctx->ref_count_stats = rc->stats();
     ctx->graph->set_ref_repeats(rc->solid_keys_device(), rc->nb_solid());
     ctx->ref_repeated = rc->nb_solid();
-    MTG_CATCH
 }
+int mtg_set_reference(mtg_ctx* ctx, const char* bases, uint64_t nbytes) { MTG_TRY(ctx) set_reference_impl(ctx, bases, nullptr, nbytes); MTG_CATCH }
+int mtg_set_reference_device(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes) { MTG_TRY(ctx) set_reference_impl(ctx, nullptr, d_bases, nbytes); MTG_CATCH }
 
 int mtg_contains_batch(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) {
     MTG_TRY(ctx) MTG_CUDA(cudaSetDevice(ctx->p.device)); ctx->graph->contains_batch(lo, ctx->p.kmer_size > 31 ? hi : nullptr, n, out); MTG_CATCH
@@ -252,35 +296,43 @@ int mtg_ref_repeat_batch(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, u
 }
 
 int mtg_sequence_features(mtg_ctx* ctx, const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint64_t* counters4) {
-    MTG_TRY(ctx) MTG_CUDA(cudaSetDevice(ctx->p.device)); ctx->graph->features_host(seq, len, feat, rep, counters4); MTG_CATCH
+    MTG_TRY(ctx) ctx->graph->features_host(seq, len, feat, rep, nullptr, counters4); MTG_CATCH
 }
 int mtg_sequence_features_device(mtg_ctx* ctx, const void* d_seq, uint64_t len, void* d_feat, void* d_rep, uint64_t* counters4) {
     MTG_TRY(ctx)
     MTG_CUDA(cudaSetDevice(ctx->p.device));
-    ctx->graph->features_device((const uint8_t*)d_seq, len, (uint8_t*)d_feat, (uint8_t*)d_rep, counters4);
+    ctx->graph->features_device((const uint8_t*)d_seq, len, (uint8_t*)d_feat, (uint8_t*)d_rep, nullptr, counters4);
     MTG_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->ms_features += ctx->graph->last_features_ms();
     MTG_CATCH
 }
 
-int mtg_scan_reference(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len) {
-    MTG_TRY(ctx)
+static void scan_reference_impl(mtg_ctx* ctx, const char* name, const char* seq, const void* d_seq, uint64_t len) {
     MTG_CUDA(cudaSetDevice(ctx->p.device));
     const int k = ctx->p.kmer_size;
-    if (len < (uint64_t)k) return 0;  // reference quirk (replaying the previous sequence's k-mers) deliberately not reproduced
+    if (len < (uint64_t)k) return;  // reference quirk (replaying the previous sequence's k-mers) deliberately not reproduced
     const uint64_t npos = len - k + 1;
-    if (ctx->feat.size() < npos) { ctx->feat.resize(npos); ctx->rep.resize(npos); }
+    ctx->feat.reserve(npos); ctx->rep.reserve(npos); ctx->interest.reserve((npos + 31) / 32 * 4 + 8);
+    uint8_t* feat = ctx->feat.as<uint8_t>();
+    uint8_t* rep = ctx->rep.as<uint8_t>();
+    uint32_t* interest = ctx->interest.as<uint32_t>();
     uint64_t c4[4];
-    ctx->graph->features_host(seq, len, ctx->feat.data(), ctx->rep.data(), c4);
+    if (d_seq) ctx->graph->features_to_host((const uint8_t*)d_seq, len, feat, rep, interest, c4);
+    else ctx->graph->features_host(seq, len, feat, rep, interest, c4);
     ctx->ms_features += ctx->graph->last_features_ms();
     ctx->scan_positions += npos; ctx->scan_valid += c4[0]; ctx->scan_in_graph += c4[1]; ctx->scan_table_probes += c4[2]; ctx->scan_fallback += c4[3];
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    if (ctx->rp64) ctx->rp64->scan(name ? name : "", seq, len, ctx->feat.data(), ctx->rep.data());
-    else ctx->rp128->scan(name ? name : "", seq, len, ctx->feat.data(), ctx->rep.data());
+    if (ctx->rp64) ctx->rp64->scan(name ? name : "", seq, len, feat, rep, interest);
+    else ctx->rp128->scan(name ? name : "", seq, len, feat, rep, interest);
     clock_gettime(CLOCK_MONOTONIC, &t1);
     ctx->ms_replay += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
-    MTG_CATCH
+}
+int mtg_scan_reference(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len) {
+    MTG_TRY(ctx) scan_reference_impl(ctx, name, seq, nullptr, len); MTG_CATCH
+}
+int mtg_scan_reference_device(mtg_ctx* ctx, const char* name, const char* seq, const void* d_seq, uint64_t len) {
+    MTG_TRY(ctx) if (!d_seq) throw Error(-1, "null device sequence"); scan_reference_impl(ctx, name, seq, d_seq, len); MTG_CATCH
 }
 
 const char* mtg_breakpoints_text(mtg_ctx* ctx, uint64_t* nbytes) {
@@ -311,7 +363,7 @@ int mtg_get_find_counters(mtg_ctx* ctx, uint64_t* o) {
 int64_t mtg_copy_bits(mtg_ctx* ctx, int which, uint8_t* buf, uint64_t capacity) {
     try {
         if (!ctx) return -1;
-        MTG_CUDA(cudaSetDevice(ctx->p.device));
+        enter(ctx);
         uint64_t n = ctx->graph->copy_bits(which, nullptr);
         if (buf) { if (capacity < n) throw Error(-1, "buffer too small"); ctx->graph->copy_bits(which, buf); }
         return (int64_t)n;

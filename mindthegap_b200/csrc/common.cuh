@@ -68,7 +68,15 @@ struct Error : std::runtime_error {
                                      std::to_string(__LINE__));                                          \
     } while (0)
 
-// Simple owning device buffer.
+// Stream every allocation of the calling thread is ordered on (set by the C ABI entry points; one stream per context).
+inline cudaStream_t& current_stream() {
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
+
+// Owning device buffer, stream-ordered (cudaMallocAsync / cudaFreeAsync on current_stream()). The device's default
+// memory pool is configured by mtg_create to keep freed memory (release threshold = max), so that after the first
+// `find` of a process allocation costs no driver round trip.
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
@@ -79,15 +87,28 @@ template <class T> struct DevBuf {
     DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFreeAsync(p, current_stream()); p = nullptr; n = 0; }
     void alloc(size_t n_) {
         release();
         n = n_;
-        if (n) MTG_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+        if (n) MTG_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), current_stream()));
     }
-    void zero(cudaStream_t s = 0) { if (n) MTG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
-    void fill_ff(cudaStream_t s = 0) { if (n) MTG_CUDA(cudaMemsetAsync(p, 0xFF, n * sizeof(T), s)); }
+    void zero(cudaStream_t s = 0) { if (n) MTG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s ? s : current_stream())); }
+    void fill_ff(cudaStream_t s = 0) { if (n) MTG_CUDA(cudaMemsetAsync(p, 0xFF, n * sizeof(T), s ? s : current_stream())); }
     size_t bytes() const { return n * sizeof(T); }
+};
+
+// Pinned host buffer taken from a process-wide cache (cudaHostAlloc costs milliseconds; contexts come and go).
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    PinnedBuf() {}
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() { release(); }
+    void reserve(size_t bytes);   // grows (contents are not preserved)
+    void release();
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
 // ----------------------------------------------------------------------------------------------- k-mer arithmetic

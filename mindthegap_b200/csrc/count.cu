@@ -272,6 +272,115 @@ superkmer_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// grouping of minimizer bins into work items (the role of Repartitor::computeDistrib, PartiInfo.cpp:40-86), on the device:
+//   bin v (k-mer instances nk[v], records nr[v]) -> group floor(P[v] / GROUP_TARGET), P = exclusive prefix sum of nk;
+//   a group whose load exceeds GROUP_CAP instances is counted in ceil(load / GROUP_CAP) hash-selected passes.
+// ------------------------------------------------------------------------------------------------------------
+static const int GP_THREADS = 256, GP_PER_THREAD = 16, GP_TILE = GP_THREADS * GP_PER_THREAD;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* s_warp, unsigned long long& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned long long x = v;
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        unsigned long long t = lane < nw ? s_warp[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
+        if (lane < nw) s_warp[lane] = t;
+    }
+    __syncthreads();
+    total = s_warp[nw - 1];
+    unsigned long long res = x - v + (w ? s_warp[w - 1] : 0);
+    __syncthreads();
+    return res;
+}
+
+// tile sums of nk
+__global__ void __launch_bounds__(GP_THREADS) group_tile_sum_kernel(const unsigned long long* __restrict__ mhist, uint32_t nbins,
+                                                                    unsigned long long* __restrict__ tile_sum) {
+    __shared__ unsigned long long s_warp[32];
+    unsigned long long acc = 0;
+    const uint32_t base = blockIdx.x * GP_TILE + threadIdx.x * GP_PER_THREAD;
+    for (int i = 0; i < GP_PER_THREAD; i++) if (base + i < nbins) acc += mhist[base + i] & ((1ull << MH_REC_SHIFT) - 1);
+    unsigned long long total;
+    block_exclusive_scan(acc, s_warp, total);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+// exclusive scan of up to 1024*... values by one CTA (in place)
+__global__ void __launch_bounds__(1024) scan_one_cta_kernel(unsigned long long* __restrict__ a, uint32_t n, unsigned long long* __restrict__ total_out) {
+    __shared__ unsigned long long s_warp[32];
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = threadIdx.x * per, e = min(n, b + per);
+    unsigned long long acc = 0;
+    for (uint32_t i = b; i < e; i++) acc += a[i];
+    unsigned long long total;
+    unsigned long long run = block_exclusive_scan(acc, s_warp, total);
+    for (uint32_t i = b; i < e; i++) { unsigned long long v = a[i]; a[i] = run; run += v; }
+    if (threadIdx.x == 0 && total_out) *total_out = total;
+}
+// group id of every bin + per-group record count and load
+__global__ void __launch_bounds__(GP_THREADS) group_assign_kernel(const unsigned long long* __restrict__ mhist, uint32_t nbins,
+                                                                  const unsigned long long* __restrict__ tile_off, uint32_t group_target,
+                                                                  uint32_t* __restrict__ group_of, unsigned long long* __restrict__ grp_nrec,
+                                                                  unsigned long long* __restrict__ grp_load) {
+    __shared__ unsigned long long s_warp[32];
+    const uint32_t base = blockIdx.x * GP_TILE + threadIdx.x * GP_PER_THREAD;
+    unsigned long long nk[GP_PER_THREAD], acc = 0;
+    for (int i = 0; i < GP_PER_THREAD; i++) {
+        nk[i] = base + i < nbins ? mhist[base + i] : 0;
+        acc += nk[i] & ((1ull << MH_REC_SHIFT) - 1);
+    }
+    unsigned long long total;
+    unsigned long long run = tile_off[blockIdx.x] + block_exclusive_scan(acc, s_warp, total);
+    uint32_t cur_g = 0xFFFFFFFFu;
+    unsigned long long a_nrec = 0, a_load = 0;
+    for (int i = 0; i < GP_PER_THREAD; i++) {
+        if (base + i >= nbins) break;
+        const unsigned long long k_i = nk[i] & ((1ull << MH_REC_SHIFT) - 1), r_i = nk[i] >> MH_REC_SHIFT;
+        const uint32_t g = (uint32_t)(run / group_target);
+        group_of[base + i] = g;
+        if (r_i) {
+            if (g != cur_g) {
+                if (a_nrec) { atomicAdd(&grp_nrec[cur_g], a_nrec); atomicAdd(&grp_load[cur_g], a_load); }
+                cur_g = g; a_nrec = 0; a_load = 0;
+            }
+            a_nrec += r_i; a_load += k_i;
+        }
+        run += k_i;
+    }
+    if (a_nrec) { atomicAdd(&grp_nrec[cur_g], a_nrec); atomicAdd(&grp_load[cur_g], a_load); }
+}
+// passes per group (in place of the load): 0 for empty groups
+__global__ void __launch_bounds__(256) group_passes_kernel(const unsigned long long* __restrict__ grp_nrec, unsigned long long* __restrict__ grp_load,
+                                                           uint32_t ngroups, uint32_t group_cap, unsigned long long* __restrict__ stats3) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    unsigned long long np = 0;
+    if (grp_nrec[g]) {
+        const unsigned long long load = grp_load[g];
+        np = load <= group_cap ? 1 : (load + group_cap / 2 - 1) / (group_cap / 2);  // oversized bins: generous pass count
+        atomicAdd(&stats3[0], 1ull);
+        if (np > 1) atomicAdd(&stats3[1], 1ull);
+        if (np > 65535 || grp_nrec[g] > 0xFFFFFFFFull) atomicAdd(&stats3[2], 1ull);
+    }
+    grp_load[g] = np;
+}
+struct WorkItem { uint64_t rec_off; uint32_t nrec; uint16_t pass, npass; };
+// items of every group: grp_off = exclusive scan of records, item_off = exclusive scan of passes
+__global__ void __launch_bounds__(256) group_items_kernel(const unsigned long long* __restrict__ grp_nrec_orig, const unsigned long long* __restrict__ grp_off,
+                                                          const unsigned long long* __restrict__ item_off, uint32_t ngroups,
+                                                          WorkItem* __restrict__ items) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const unsigned long long nrec = grp_nrec_orig[g];
+    if (!nrec) return;
+    const unsigned long long first = item_off[g];
+    const unsigned long long np = item_off[g + 1] - first;  // both scans run over ngroups+1 entries (last one = total)
+    for (unsigned long long p = 0; p < np; p++) items[first + p] = {grp_off[g], (uint32_t)nrec, (uint16_t)p, (uint16_t)np};
+}
+
+// ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) scatter_kernel(const uint64_t* __restrict__ records, uint64_t nrec, const uint32_t* __restrict__ group_of,
                                                       const uint64_t* __restrict__ group_off, unsigned int* __restrict__ group_cur,
                                                       uint64_t* __restrict__ grouped) {
@@ -286,8 +395,6 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint64_t* __restrict
 // ------------------------------------------------------------------------------------------------------------
 // count kernel
 // ------------------------------------------------------------------------------------------------------------
-struct WorkItem { uint64_t rec_off; uint32_t nrec; uint16_t pass, npass; };
-
 // Read-or-claim one table slot. 64-bit slots are read with a plain (atomic) 8-byte load first; 128-bit slots always go
 // through ATOMS.CAS.128 so that a concurrent claim can never be observed half-written.
 MTG_D uint64_t slot_claim(uint64_t* slot, uint64_t key) {
@@ -305,7 +412,8 @@ static const int SMEM_HIST = 256;
 
 template <class K>
 __global__ void __launch_bounds__(COUNT_THREADS, 2)
-count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ grouped, const WorkItem* __restrict__ items, uint32_t nitems,
+count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ grouped, const WorkItem* __restrict__ items,
+             const unsigned long long* __restrict__ nitems_ptr,
              unsigned int* __restrict__ item_counter, int k, uint32_t emit_min, unsigned long long* __restrict__ histo,
              K* __restrict__ cand_keys, uint32_t* __restrict__ cand_cnt, unsigned long long* __restrict__ ncand, uint64_t cand_capacity,
              int* __restrict__ errflag) {
@@ -319,6 +427,7 @@ count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ g
     const int tid = threadIdx.x, lane = tid & 31;
     const K mask = kmask<K>(k);
     const int rcshift = 2 * (k - 1);
+    const uint32_t nitems = (uint32_t)*nitems_ptr;
 
     while (true) {
         if (tid == 0) s_item = atomicAdd(item_counter, 1u);
@@ -545,65 +654,40 @@ public:
 
     void finish(int abundance_min, int64_t abundance_max) override {
         const int S = CountCfg<K>::SLOTS;
-        const uint64_t target = S / 2;
+        const uint32_t group_target = S * 7 / 16, group_cap = S * 5 / 8;
         EventTimer t(stream_);
-        // ---- grouping of minimizer bins (host; 4^m entries)
+        // ---- grouping of minimizer bins into work items, entirely on the device (no host round trip)
         t.start();
-        const size_t NM = mhist_.n;
-        std::vector<unsigned long long> mh(NM);
-        MTG_CUDA(cudaMemcpyAsync(mh.data(), mhist_.p, NM * 8, cudaMemcpyDeviceToHost, stream_));
-        unsigned long long nvalid = 0;
-        MTG_CUDA(cudaMemcpyAsync(&nvalid, counters_.p + 1, 8, cudaMemcpyDeviceToHost, stream_));
-        MTG_CUDA(cudaStreamSynchronize(stream_));
-        st_.nb_valid_kmers = nvalid;
-        std::vector<uint32_t> group_of(NM, 0);
-        struct G { uint64_t nrec, nk; };
-        std::vector<G> groups;
-        {
-            uint64_t cur_k = 0, cur_r = 0;
-            bool open = false;
-            for (size_t v = 0; v < NM; v++) {
-                uint64_t nk = mh[v] & ((1ull << MH_REC_SHIFT) - 1), nr = mh[v] >> MH_REC_SHIFT;
-                if (!nr) { group_of[v] = open ? (uint32_t)groups.size() : (uint32_t)groups.size(); continue; }
-                if (open && cur_k + nk > target) { groups.push_back({cur_r, cur_k}); open = false; cur_k = cur_r = 0; }
-                group_of[v] = (uint32_t)groups.size();
-                open = true;
-                cur_k += nk; cur_r += nr;
-            }
-            if (open) groups.push_back({cur_r, cur_k});
-        }
-        const size_t NG = groups.size();
-        std::vector<uint64_t> goff(NG + 1, 0);
-        for (size_t g = 0; g < NG; g++) goff[g + 1] = goff[g] + groups[g].nrec;
-        const uint64_t total_rec = goff[NG];
-        std::vector<WorkItem> items;
-        for (size_t g = 0; g < NG; g++) {
-            uint64_t np = (groups[g].nk + target - 1) / target;
-            if (np < 1) np = 1;
-            if (np > 1) st_.nb_multipass_groups++;
-            if (np > 65535) throw Error(-4, "minimizer bin too large for the multi-pass counter");
-            if (groups[g].nrec > 0xFFFFFFFFull) throw Error(-4, "group has too many records");
-            for (uint64_t p = 0; p < np; p++) items.push_back({goff[g], (uint32_t)groups[g].nrec, (uint16_t)p, (uint16_t)np});
-        }
-        std::stable_sort(items.begin(), items.end(), [](const WorkItem& a, const WorkItem& b) { return a.nrec > b.nrec; });
-        st_.nb_groups = NG;
-        st_.nb_items = items.size();
+        const uint32_t NM = (uint32_t)mhist_.n;
+        const uint32_t ntiles = (NM + GP_TILE - 1) / GP_TILE;
+        const uint64_t pos_upper = words_used_ * 32;                       // upper bound of the k-mer instances
+        const uint32_t max_groups = (uint32_t)(pos_upper / group_target + 2);
+        const uint64_t max_items = (uint64_t)max_groups + pos_upper / (group_cap / 2) + 2;
+        uint64_t total_rec = 0;
+        for (auto& b : batches_) total_rec += b.nrec;
+        DevBuf<unsigned long long> tile_off(ntiles + 1), grp_nrec(max_groups + 1), grp_off(max_groups + 1), item_off(max_groups + 1), gstats(4);
         DevBuf<uint32_t> d_group_of(NM);
-        DevBuf<uint64_t> d_goff(NG + 1);
-        DevBuf<unsigned int> d_gcur(std::max<size_t>(NG, 1));
-        DevBuf<WorkItem> d_items(std::max<size_t>(items.size(), 1));
+        DevBuf<unsigned int> d_gcur(max_groups + 1);
+        DevBuf<WorkItem> d_items(max_items);
         DevBuf<uint64_t> grouped(std::max<uint64_t>(total_rec, 1));
-        MTG_CUDA(cudaMemcpyAsync(d_group_of.p, group_of.data(), NM * 4, cudaMemcpyHostToDevice, stream_));
-        MTG_CUDA(cudaMemcpyAsync(d_goff.p, goff.data(), (NG + 1) * 8, cudaMemcpyHostToDevice, stream_));
-        if (!items.empty()) MTG_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, stream_));
-        d_gcur.zero(stream_);
+        grp_nrec.zero(stream_); item_off.zero(stream_); gstats.zero(stream_); d_gcur.zero(stream_);
+        group_tile_sum_kernel<<<ntiles, GP_THREADS, 0, stream_>>>(mhist_.p, NM, tile_off.p);
+        scan_one_cta_kernel<<<1, 1024, 0, stream_>>>(tile_off.p, ntiles, nullptr);
+        group_assign_kernel<<<ntiles, GP_THREADS, 0, stream_>>>(mhist_.p, NM, tile_off.p, group_target, d_group_of.p, grp_nrec.p, item_off.p);
+        group_passes_kernel<<<(max_groups + 255) / 256, 256, 0, stream_>>>(grp_nrec.p, item_off.p, max_groups, group_cap, gstats.p);
+        MTG_CUDA(cudaMemcpyAsync(grp_off.p, grp_nrec.p, (size_t)(max_groups + 1) * 8, cudaMemcpyDeviceToDevice, stream_));
+        scan_one_cta_kernel<<<1, 1024, 0, stream_>>>(grp_off.p, max_groups + 1, nullptr);
+        scan_one_cta_kernel<<<1, 1024, 0, stream_>>>(item_off.p, max_groups + 1, gstats.p + 3);
+        group_items_kernel<<<(max_groups + 255) / 256, 256, 0, stream_>>>(grp_nrec.p, grp_off.p, item_off.p, max_groups, d_items.p);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches += 7;
         st_.ms_group += t.stop();
         // ---- scatter records into group lists
         t.start();
         for (auto& b : batches_) {
             if (!b.nrec) continue;
             int grid = (int)std::min<uint64_t>((b.nrec + 255) / 256, (uint64_t)sm_count_ * 16);
-            scatter_kernel<<<grid, 256, 0, stream_>>>(b.recs.p, b.nrec, d_group_of.p, d_goff.p, d_gcur.p, grouped.p);
+            scatter_kernel<<<grid, 256, 0, stream_>>>(b.recs.p, b.nrec, d_group_of.p, (const uint64_t*)grp_off.p, d_gcur.p, grouped.p);
             MTG_CUDA(cudaGetLastError());
             st_.launches++;
         }
@@ -613,7 +697,7 @@ public:
         // ---- count
         const bool is_auto = abundance_min < 0;
         uint32_t emit_min = is_auto ? 3u : (uint32_t)std::max(abundance_min, 1);
-        uint64_t cand_cap = nvalid / emit_min + 1024;
+        uint64_t cand_cap = pos_upper / emit_min + 1024;
         DevBuf<K> cand_keys(cand_cap);
         DevBuf<uint32_t> cand_cnt(cand_cap);
         DevBuf<unsigned long long> d_histo(HISTO_MAX + 1);
@@ -623,22 +707,27 @@ public:
         MTG_CUDA(cudaMemsetAsync(counters_.p + 2, 0, 16, stream_));
         MTG_CUDA(cudaMemsetAsync(flags_.p + 1, 0, sizeof(int), stream_));
         t.start();
-        if (!items.empty()) {
+        if (total_rec) {
             const int smem = (int)(sizeof(K) + 4) * S + SMEM_HIST * 4;
-            int grid = (int)std::min<size_t>(items.size(), (size_t)sm_count_ * 2);
-            count_kernel<K><<<grid, COUNT_THREADS, smem, stream_>>>(packed_.p, grouped.p, d_items.p, (uint32_t)items.size(), d_item_counter.p, k_,
-                                                                     emit_min, d_histo.p, cand_keys.p, cand_cnt.p, counters_.p + 2, cand_cap,
-                                                                     flags_.p + 1);
+            count_kernel<K><<<sm_count_ * 2, COUNT_THREADS, smem, stream_>>>(packed_.p, grouped.p, d_items.p, gstats.p + 3, d_item_counter.p, k_,
+                                                                            emit_min, d_histo.p, cand_keys.p, cand_cnt.p, counters_.p + 2, cand_cap,
+                                                                            flags_.p + 1);
             MTG_CUDA(cudaGetLastError());
             st_.launches++;
         }
         st_.ms_count += t.stop();
+        unsigned long long gs[4] = {0, 0, 0, 0}, nvalid = 0;
+        MTG_CUDA(cudaMemcpyAsync(gs, gstats.p, 32, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaMemcpyAsync(&nvalid, counters_.p + 1, 8, cudaMemcpyDeviceToHost, stream_));
         int err = 0;
         unsigned long long ncand = 0;
         MTG_CUDA(cudaMemcpyAsync(&err, flags_.p + 1, sizeof(int), cudaMemcpyDeviceToHost, stream_));
         MTG_CUDA(cudaMemcpyAsync(&ncand, counters_.p + 2, 8, cudaMemcpyDeviceToHost, stream_));
         MTG_CUDA(cudaMemcpyAsync(histo_.data(), d_histo.p, (HISTO_MAX + 1) * 8, cudaMemcpyDeviceToHost, stream_));
         MTG_CUDA(cudaStreamSynchronize(stream_));
+        st_.nb_valid_kmers = nvalid;
+        st_.nb_groups = gs[0]; st_.nb_multipass_groups = gs[1]; st_.nb_items = gs[3];
+        if (gs[2]) throw Error(-4, "minimizer bin too large for the multi-pass counter");
         if (err == 1) throw Error(-5, "shared-memory count table overflow");
         if (err == 2) throw Error(-5, "candidate buffer overflow");
         st_.nb_candidates = ncand;

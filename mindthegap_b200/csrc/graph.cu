@@ -238,19 +238,22 @@ __global__ void __launch_bounds__(256) contains_kernel(GraphView<K> g, const uin
 template <class K>
 __global__ void __launch_bounds__(256) features_kernel(GraphView<K> g, const uint64_t* __restrict__ packed, const uint32_t* __restrict__ inv,
                                                        uint64_t npos, uint8_t* __restrict__ feat, uint8_t* __restrict__ rep,
-                                                       unsigned long long* __restrict__ counters) {
+                                                       uint32_t* __restrict__ interest, unsigned long long* __restrict__ counters) {
     const int k = g.k;
-    const K mask = kmask<K>(k);
     const K m1 = kmask<K>(k - 1);
     unsigned long long c_valid = 0, c_in = 0, c_probe = 0, c_fb = 0;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += (uint64_t)gridDim.x * blockDim.x) {
-        // validity of the window
-        uint64_t a = p >> 5;
-        int o = (int)(p & 31);
-        uint32_t x0 = __ldg(inv + a), x1 = __ldg(inv + a + 1), x2 = __ldg(inv + a + 2);
-        uint32_t y0 = __funnelshift_l(x1, x0, o), y1 = __funnelshift_l(x2, x1, o);
-        bool valid = k <= 32 ? (y0 >> (32 - k)) == 0 : (y0 == 0 && (y1 >> (64 - k)) == 0);
+    const uint64_t npos32 = (npos + 31) & ~31ull;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos32; p += (uint64_t)gridDim.x * blockDim.x) {
         uint8_t f = 0x80, r = 0;
+        bool valid = false;
+        if (p < npos) {
+            // validity of the window
+            uint64_t a = p >> 5;
+            int o = (int)(p & 31);
+            uint32_t x0 = __ldg(inv + a), x1 = __ldg(inv + a + 1), x2 = __ldg(inv + a + 2);
+            uint32_t y0 = __funnelshift_l(x1, x0, o), y1 = __funnelshift_l(x2, x1, o);
+            valid = k <= 32 ? (y0 >> (32 - k)) == 0 : (y0 == 0 && (y1 >> (64 - k)) == 0);
+        }
         if (valid) {
             c_valid++;
             const K fwd = extract_kmer<K>(packed, p, k);
@@ -275,10 +278,12 @@ __global__ void __launch_bounds__(256) features_kernel(GraphView<K> g, const uin
             r = (uint8_t)((bloom_cache_contains<K>(g.refbloom, g.ref_tai, g.ref_nhash, g.seed0, g.rnd, suffix) ? 1 : 0) |
                           (bloom_cache_contains<K>(g.refbloom, g.ref_tai, g.ref_nhash, g.seed0, g.rnd, prefix) ? 2 : 0));
         }
-        feat[p] = f;
-        rep[p] = r;
+        if (p < npos) { feat[p] = f; rep[p] = r; }
+        // interest bit (host replay skip-ahead): invalid, not in the graph, or hetero pre-condition nb_in == 2 && !prefix_repeated
+        const bool interesting = p < npos && ((f & 0x80) || !(f & 1) || ((((f >> 1) & 7) == 2) && !(r & 2)));
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, interesting);
+        if ((threadIdx.x & 31) == 0) interest[p >> 5] = b;
     }
-    (void)mask;
     // warp reduce the counters
     for (int off = 16; off; off >>= 1) {
         c_valid += __shfl_down_sync(0xFFFFFFFFu, c_valid, off);
@@ -314,6 +319,9 @@ template <class K> class Graph : public IGraph {
     float last_features_ms_ = 0;
     // scratch for sequences
     DevBuf<uint8_t> seq_stage_, d_feat_, d_rep_;
+    DevBuf<uint32_t> d_interest_;
+    cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr;
+    bool features_timed_ = false;
     DevBuf<uint64_t> seq_packed_;
     DevBuf<uint32_t> seq_inv_;
     DevBuf<uint64_t> q_lo_, q_hi_;
@@ -354,6 +362,8 @@ template <class K> class Graph : public IGraph {
 public:
     Graph(int k, cudaStream_t s) : k_(k), stream_(s) {
         seed0_ = bloom_seed0_host();
+        MTG_CUDA(cudaEventCreate(&ev_a_));
+        MTG_CUDA(cudaEventCreate(&ev_b_));
         std::mt19937_64 rng(37);  // tools/collections/impl/BooPHF.hpp:246-249
         mphf_seed_ = rng();
         rnd_.alloc(256);
@@ -371,9 +381,13 @@ public:
         table_.alloc(BUCKET_BYTES / sizeof(K));
         table_.fill_ff(stream_);
     }
+    ~Graph() override { if (ev_a_) cudaEventDestroy(ev_a_); if (ev_b_) cudaEventDestroy(ev_b_); }
     int kmer_size() const override { return k_; }
     const GraphStats& stats() const override { return st_; }
-    float last_features_ms() const override { return last_features_ms_; }
+    float last_features_ms() override {
+        if (features_timed_) { cudaEventSynchronize(ev_b_); cudaEventElapsedTime(&last_features_ms_, ev_a_, ev_b_); features_timed_ = false; }
+        return last_features_ms_;
+    }
 
     void build_from_host(const uint64_t* lo, const uint64_t* hi, uint64_t n) override {
         std::vector<K> keys(n);
@@ -571,37 +585,49 @@ public:
     void ref_repeat_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) override { run_query(lo, hi, n, out, 2); }
     void observer_probe_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) override { run_query(lo, hi, n, out, 3); }
 
-    void features_device(const uint8_t* d_seq, uint64_t len, uint8_t* d_feat, uint8_t* d_rep, uint64_t* counters_host4) override {
+    void features_device(const uint8_t* d_seq, uint64_t len, uint8_t* d_feat, uint8_t* d_rep, uint32_t* d_interest, uint64_t* counters_host4) override {
         if (counters_host4) memset(counters_host4, 0, 32);
         last_features_ms_ = 0;
         if (len < (uint64_t)k_) return;
         const uint64_t npos = len - k_ + 1;
         const uint64_t nwords = (len + 31) / 32;
         if (seq_packed_.n < nwords + 8) { seq_packed_.alloc(nwords + 8 + nwords / 4); seq_inv_.alloc(nwords + 8 + nwords / 4); }
+        if (!d_interest) {
+            if (d_interest_.n < nwords + 8) d_interest_.alloc(nwords + 8 + nwords / 4);
+            d_interest = d_interest_.p;
+        }
         MTG_CUDA(cudaMemsetAsync(seq_packed_.p + nwords, 0, 8 * 8, stream_));
         MTG_CUDA(cudaMemsetAsync(seq_inv_.p + nwords, 0xFF, 8 * 4, stream_));
         launch_pack(d_seq, len, seq_packed_.p, seq_inv_.p, nwords, stream_);
         MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 32, stream_));
-        EvTimer t(stream_);
-        t.start();
-        features_kernel<K><<<grid_for(npos, 256, 148 * 32), 256, 0, stream_>>>(view(), seq_packed_.p, seq_inv_.p, npos, d_feat, d_rep, counters_.p);
+        MTG_CUDA(cudaEventRecord(ev_a_, stream_));
+        features_kernel<K><<<grid_for(npos, 256, 148 * 32), 256, 0, stream_>>>(view(), seq_packed_.p, seq_inv_.p, npos, d_feat, d_rep, d_interest, counters_.p);
         MTG_CUDA(cudaGetLastError());
-        last_features_ms_ = t.stop();
+        MTG_CUDA(cudaEventRecord(ev_b_, stream_));
+        features_timed_ = true;
         st_.launches += 2;
         if (counters_host4) {
             MTG_CUDA(cudaMemcpyAsync(counters_host4, counters_.p, 32, cudaMemcpyDeviceToHost, stream_));
             MTG_CUDA(cudaStreamSynchronize(stream_));
         }
     }
-    void features_host(const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint64_t* counters_host4) override {
+    void features_host(const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint32_t* interest, uint64_t* counters_host4) override {
+        if (counters_host4) memset(counters_host4, 0, 32);
+        if (len < (uint64_t)k_) return;
+        if (seq_stage_.n < len + 64) seq_stage_.alloc(len + 64 + len / 4);
+        MTG_CUDA(cudaMemcpyAsync(seq_stage_.p, seq, len, cudaMemcpyHostToDevice, stream_));
+        features_to_host(seq_stage_.p, len, feat, rep, interest, counters_host4);
+    }
+    void features_to_host(const uint8_t* d_seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint32_t* interest, uint64_t* counters_host4) override {
         if (counters_host4) memset(counters_host4, 0, 32);
         if (len < (uint64_t)k_) return;
         const uint64_t npos = len - k_ + 1;
-        if (seq_stage_.n < len + 64) { seq_stage_.alloc(len + 64 + len / 4); d_feat_.alloc(len + 64 + len / 4); d_rep_.alloc(len + 64 + len / 4); }
-        MTG_CUDA(cudaMemcpyAsync(seq_stage_.p, seq, len, cudaMemcpyHostToDevice, stream_));
-        features_device(seq_stage_.p, len, d_feat_.p, d_rep_.p, counters_host4);
+        if (d_feat_.n < len + 64) { d_feat_.alloc(len + 64 + len / 4); d_rep_.alloc(len + 64 + len / 4); }
+        features_device(d_seq, len, d_feat_.p, d_rep_.p, nullptr, nullptr);
         MTG_CUDA(cudaMemcpyAsync(feat, d_feat_.p, npos, cudaMemcpyDeviceToHost, stream_));
         MTG_CUDA(cudaMemcpyAsync(rep, d_rep_.p, npos, cudaMemcpyDeviceToHost, stream_));
+        if (interest) MTG_CUDA(cudaMemcpyAsync(interest, d_interest_.p, ((npos + 31) / 32) * 4, cudaMemcpyDeviceToHost, stream_));
+        if (counters_host4) MTG_CUDA(cudaMemcpyAsync(counters_host4, counters_.p, 32, cudaMemcpyDeviceToHost, stream_));
         MTG_CUDA(cudaStreamSynchronize(stream_));
     }
 

@@ -258,12 +258,15 @@ public:
     // combined probe used by the host replay: contains | indegree<<1 | outdegree<<4 | suffix_repeated<<7
     virtual void observer_probe_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) = 0;
     // dense per-position features of a sequence given as ASCII on the device; see features kernel for the layout.
-    virtual void features_device(const uint8_t* d_seq, uint64_t len, uint8_t* d_feat, uint8_t* d_rep, uint64_t* counters_host4) = 0;
-    virtual void features_host(const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint64_t* counters_host4) = 0;
+    // d_interest (may be null): bitmap of the positions the host replay must walk one by one.
+    virtual void features_device(const uint8_t* d_seq, uint64_t len, uint8_t* d_feat, uint8_t* d_rep, uint32_t* d_interest, uint64_t* counters_host4) = 0;
+    virtual void features_host(const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint32_t* interest, uint64_t* counters_host4) = 0;
+    // same, sequence already on the device, features copied to host arrays
+    virtual void features_to_host(const uint8_t* d_seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint32_t* interest, uint64_t* counters_host4) = 0;
     // raw copies for parity tests: which = 0 bloom,1..3 bloom2..4, 4 refbloom, 5 mphf levels; returns byte size
     virtual uint64_t copy_bits(int which, uint8_t* host_buf) const = 0;
     virtual const GraphStats& stats() const = 0;
-    virtual float last_features_ms() const = 0;
+    virtual float last_features_ms() = 0;
 };
 
 IGraph* make_graph(int k, cudaStream_t stream);

@@ -7,6 +7,16 @@
 // micro-assemblies, deletion junctions, correct_history) are answered by the GPU through batched probe calls
 // (ProbeFn); nothing here consults a CPU copy of the graph.
 //
+// Two things keep the host part cheap (both exact):
+//  * skip-ahead: the GPU also returns an "interest" bitmap (position invalid, not in the graph, or hetero pre-condition
+//    nb_in==2 && !prefix_repeated). While the gap machine is in its steady state (solid stretch >= 2, no open gap) a run of
+//    uninteresting positions only advances counters and the 256-entry history ring, so it is applied in O(256) instead of
+//    being walked position by position.
+//  * probe cache + collect pass: every segment is first replayed on a scratch copy of the state in "collect" mode, where
+//    observers only enumerate the k-mers they may ask about; those are answered by ONE batched GPU probe and memoised
+//    (answers are pure functions of the k-mer), then the real replay runs against the memo and falls back to immediate
+//    GPU batches only for the rare queries the collect pass could not foresee.
+//
 // Quirks kept on purpose: ring indices are unsigned char and drift after a partial FindMultiSNPrev;
 // kmer_begin_is_repeated is the flag of the first gap k-mer; right k-mers of fuzzy/hetero sites are raw reference text.
 #pragma once
@@ -26,11 +36,18 @@ struct ReplayOptions {
 
 struct ReplayCounters {
     uint64_t homo_clean = 0, homo_fuzzy = 0, hetero_clean = 0, hetero_fuzzy = 0, clean_deletion = 0, fuzzy_deletion = 0, solo_snp = 0,
-             multi_snp = 0, backup = 0, homo_indel = 0, hetero_indel = 0, observer_queries = 0, probe_batches = 0;
+             multi_snp = 0, backup = 0, homo_indel = 0, hetero_indel = 0, observer_queries = 0, probe_batches = 0, prefetched_queries = 0,
+             unforeseen_queries = 0;
 };
 
 // Probe answer for a forward k-mer: bit0 contains, bits1-3 indegree, bits4-6 outdegree, bit7 (k-1)-suffix repeated.
 template <class K> using ProbeFn = std::function<void(const K* kmers, size_t n, uint8_t* out)>;
+
+// Positions the replay must walk one by one (the features kernel computes the same predicate, graph.cu): invalid k-mer,
+// k-mer not in the graph, or the hetero pre-condition nb_in == 2 && !prefix_repeated (src/FindHeteroInsertion.hpp:62).
+inline bool replay_interesting(uint8_t feat, uint8_t rep) {
+    return (feat & 0x80) || !(feat & 1) || ((((feat >> 1) & 7) == 2) && !(rep & 2));
+}
 
 template <class K> class Replayer {
 public:
@@ -41,36 +58,31 @@ public:
     std::string bkpt_out, vcf_out;
     ReplayCounters cnt;
     uint64_t next_id = 1;  // shared bkpt id counter (src/FindBreakpoints.hpp:872-875)
+    size_t segment_positions = (size_t)1 << 22;  // collect/prefetch granularity
+    size_t skip_min = 512;                        // shortest uninteresting run worth skipping
 
-    // One reference sequence (FindBreakpoints::operator(), :390-455). feat/rep hold len-k+1 entries.
-    void scan(const std::string& name, const char* seq, size_t len, const uint8_t* feat, const uint8_t* rep) {
-        chrom = name; text = seq; text_len = len;
-        begin_valid = end_valid = false;
-        solid_stretch = gap_stretch = 0;
-        memset(ring, 0, sizeof(ring));
-        end_idx = (unsigned char)(k + 1);
-        begin_idx = 1;
-        recent_hetero = 0;
-        pos = 0;
+    // One reference sequence (FindBreakpoints::operator(), :390-455). feat/rep hold len-k+1 entries; `interest` is the
+    // GPU's bitmap (bit p&31 of word p>>5 set when position p needs the full state machine), or null to walk everything.
+    void scan(const std::string& name, const char* seq, size_t len, const uint8_t* feat, const uint8_t* rep, const uint32_t* interest = nullptr) {
+        begin_sequence(name, seq, len);
         if (len < (size_t)k) return;
         const size_t npos = len - k + 1;
-        K fwd = 0;
-        for (int i = 0; i < k - 1; i++) fwd = (fwd << 2) | (K)code(seq[i]);
-        for (size_t p = 0; p < npos; p++) {
-            fwd = ((fwd << 2) | (K)code(seq[p + k - 1])) & mask_;
-            const uint8_t f = feat[p];
-            if (f & 0x80) {
-                solid_stretch = gap_stretch = 0;
-                begin_valid = end_valid = false;
-            } else {
-                cur_fwd = fwd;
-                const uint64_t save = pos;
-                notify(f, rep[p]);
-                pos = save;
-                prev_fwd = fwd; prev_valid = true;
-            }
-            pos++; begin_idx++; end_idx++;
+        for (size_t p0 = 0; p0 < npos; p0 += segment_positions) {
+            const size_t p1 = std::min(npos, p0 + segment_positions);
+            // collect pass on a scratch copy of the state, one batched GPU probe, then the real pass
+            Saved sv;
+            save(sv);
+            collecting_ = true;
+            calls_.clear(); log_keys_.clear();
+            run_range(p0, p1, feat, rep, interest);
+            collecting_ = false;
+            restore(sv);
+            log_ans_.resize(log_keys_.size());
+            if (!log_keys_.empty()) { probe_(log_keys_.data(), log_keys_.size(), log_ans_.data()); cnt.probe_batches++; cnt.prefetched_queries += log_keys_.size(); }
+            cursor_ = 0;
+            run_range(p0, p1, feat, rep, interest);
         }
+        calls_.clear(); log_keys_.clear(); log_ans_.clear();
     }
 
 private:
@@ -84,13 +96,128 @@ private:
     const char* text = nullptr;
     size_t text_len = 0;
     uint64_t pos = 0, solid_stretch = 0, gap_stretch = 0;
-    K cur_fwd = 0, prev_fwd = 0, begin_fwd = 0, end_fwd = 0;
+    K cur_fwd = 0, prev_fwd = 0, begin_fwd = 0, end_fwd = 0, roll_fwd = 0;
     bool prev_valid = false, begin_valid = false, end_valid = false;
     Info ring[256];
     unsigned char begin_idx = 1, end_idx = 0;
     Info cur_info;
     int recent_hetero = 0;
     bool end_is_repeated = false, begin_is_repeated = false;
+    // collect pass / probe log
+    struct LogCall { uint64_t p; size_t off; uint32_t n; };
+    bool collecting_ = false;
+    std::vector<LogCall> calls_;
+    std::vector<K> log_keys_;
+    std::vector<uint8_t> log_ans_;
+    size_t cursor_ = 0;
+    uint64_t loop_p_ = 0;  // position of the scan loop (monotonic, unlike `pos`)
+
+    struct Saved {
+        uint64_t pos, solid_stretch, gap_stretch, next_id;
+        K cur_fwd, prev_fwd, begin_fwd, end_fwd, roll_fwd;
+        bool prev_valid, begin_valid, end_valid, end_is_repeated, begin_is_repeated;
+        Info ring[256];
+        unsigned char begin_idx, end_idx;
+        Info cur_info;
+        int recent_hetero;
+        ReplayCounters cnt;
+    };
+    void save(Saved& v) const {
+        v.pos = pos; v.solid_stretch = solid_stretch; v.gap_stretch = gap_stretch; v.next_id = next_id;
+        v.cur_fwd = cur_fwd; v.prev_fwd = prev_fwd; v.begin_fwd = begin_fwd; v.end_fwd = end_fwd; v.roll_fwd = roll_fwd;
+        v.prev_valid = prev_valid; v.begin_valid = begin_valid; v.end_valid = end_valid;
+        v.end_is_repeated = end_is_repeated; v.begin_is_repeated = begin_is_repeated;
+        memcpy(v.ring, ring, sizeof(ring));
+        v.begin_idx = begin_idx; v.end_idx = end_idx; v.cur_info = cur_info; v.recent_hetero = recent_hetero; v.cnt = cnt;
+    }
+    void restore(const Saved& v) {
+        pos = v.pos; solid_stretch = v.solid_stretch; gap_stretch = v.gap_stretch; next_id = v.next_id;
+        cur_fwd = v.cur_fwd; prev_fwd = v.prev_fwd; begin_fwd = v.begin_fwd; end_fwd = v.end_fwd; roll_fwd = v.roll_fwd;
+        prev_valid = v.prev_valid; begin_valid = v.begin_valid; end_valid = v.end_valid;
+        end_is_repeated = v.end_is_repeated; begin_is_repeated = v.begin_is_repeated;
+        memcpy(ring, v.ring, sizeof(ring));
+        begin_idx = v.begin_idx; end_idx = v.end_idx; cur_info = v.cur_info; recent_hetero = v.recent_hetero;
+        uint64_t batches = cnt.probe_batches, pre = cnt.prefetched_queries;
+        cnt = v.cnt; cnt.probe_batches = batches; cnt.prefetched_queries = pre;
+    }
+
+    void begin_sequence(const std::string& name, const char* seq, size_t len) {
+        chrom = name; text = seq; text_len = len;
+        begin_valid = end_valid = false;
+        prev_valid = false;
+        solid_stretch = gap_stretch = 0;
+        memset(ring, 0, sizeof(ring));
+        end_idx = (unsigned char)(k + 1);
+        begin_idx = 1;
+        recent_hetero = 0;
+        pos = 0;
+        roll_fwd = 0;
+        for (int i = 0; i < k - 1 && (size_t)i < len; i++) roll_fwd = (roll_fwd << 2) | (K)code(seq[i]);
+    }
+
+    static size_t next_interesting(const uint32_t* bits, size_t p, size_t end) {
+        if (p >= end) return end;
+        size_t w = p >> 5;
+        uint32_t cur = bits[w] & (0xFFFFFFFFu << (p & 31));
+        const size_t wend = (end + 31) >> 5;
+        while (true) {
+            if (cur) { size_t q = (w << 5) + (size_t)__builtin_ctz(cur); return q < end ? q : end; }
+            if (++w >= wend) return end;
+            cur = bits[w];
+        }
+    }
+    K kmer_at(size_t p) const {
+        K f = 0;
+        for (int i = 0; i < k; i++) f = (f << 2) | (K)code(text[p + i]);
+        return f & mask_;
+    }
+    // Apply positions [p, q) -- all valid, in the graph and without the hetero pre-condition -- while the gap machine is
+    // steady (solid_stretch >= 2, gap_stretch == 0): per position notify() would only store the history entry, decrement
+    // recent_hetero and increment solid_stretch; the scan loop then advances pos and both ring indices.
+    void skip_run(size_t p, size_t q, const uint8_t* feat, const uint8_t* rep) {
+        const size_t n = q - p;
+        solid_stretch += n;
+        if (opt.hete_insert && !opt.homo_only) recent_hetero = (size_t)recent_hetero > n ? recent_hetero - (int)n : 0;
+        const size_t start = n > 256 ? q - 256 : p;
+        const size_t adv = start - p;
+        pos += adv; begin_idx = (unsigned char)(begin_idx + adv); end_idx = (unsigned char)(end_idx + adv);
+        K fwd = start == p ? roll_fwd : (start > 0 ? kmer_at(start - 1) : K(0));
+        for (size_t t = start; t < q; t++) {
+            fwd = ((fwd << 2) | (K)code(text[t + k - 1])) & mask_;
+            const uint8_t f = feat[t];
+            Info& h = ring[end_idx];
+            h.kmer = fwd; h.nb_in = (f >> 1) & 7; h.nb_out = (f >> 4) & 7; h.is_repeated = rep[t] & 1;
+            pos++; begin_idx++; end_idx++;
+        }
+        roll_fwd = fwd;
+        cur_fwd = prev_fwd = fwd; prev_valid = true;
+        cur_info = ring[(unsigned char)(end_idx - 1)];
+        end_is_repeated = (rep[q - 1] >> 1) & 1;
+    }
+    void run_range(size_t p0, size_t p1, const uint8_t* feat, const uint8_t* rep, const uint32_t* interest) {
+        size_t p = p0;
+        while (p < p1) {
+            if (interest && solid_stretch >= 2 && gap_stretch == 0) {
+                const size_t q = next_interesting(interest, p, p1);
+                if (q - p >= skip_min) { skip_run(p, q, feat, rep); p = q; continue; }
+            }
+            roll_fwd = ((roll_fwd << 2) | (K)code(text[p + k - 1])) & mask_;
+            const uint8_t f = feat[p];
+            loop_p_ = p;
+            if (f & 0x80) {
+                solid_stretch = gap_stretch = 0;
+                begin_valid = end_valid = false;
+            } else {
+                cur_fwd = roll_fwd;
+                const uint64_t save_pos = pos;
+                notify(f, rep[p]);
+                pos = save_pos;
+                prev_fwd = roll_fwd; prev_valid = true;
+            }
+            pos++; begin_idx++; end_idx++;
+            p++;
+        }
+    }
 
     static int code(char c) { return ((unsigned char)c >> 1) & 3; }
     static bool valid_nt(char c) { c &= (char)0xDF; return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
@@ -122,14 +249,27 @@ private:
         for (int i = 0; i < k; i++) if (!valid_nt(text[p + i])) return false;
         return true;
     }
-    // ---- GPU probes
+    // ---- GPU probes. Collect mode: log the call, answer zeros. Real mode: take the answers from the log when the same
+    // call (same loop position, same k-mers) was foreseen by the collect pass, else ask the GPU now.
     std::vector<uint8_t> ans_;
     const uint8_t* probe(const std::vector<K>& q) {
-        ans_.resize(q.size());
-        if (!q.empty()) { probe_(q.data(), q.size(), ans_.data()); cnt.probe_batches++; cnt.observer_queries += q.size(); }
+        const size_t n = q.size();
+        if (collecting_) {
+            calls_.push_back({loop_p_, log_keys_.size(), (uint32_t)n});
+            log_keys_.insert(log_keys_.end(), q.begin(), q.end());
+            ans_.assign(n, 0);
+            return ans_.data();
+        }
+        cnt.observer_queries += n;
+        if (!n) return ans_.data();
+        while (cursor_ < calls_.size() && calls_[cursor_].p < loop_p_) cursor_++;
+        for (size_t c = cursor_; c < calls_.size() && calls_[c].p == loop_p_; c++)  // any call foreseen at this position
+            if (calls_[c].n == n && memcmp(&log_keys_[calls_[c].off], q.data(), n * sizeof(K)) == 0) return &log_ans_[calls_[c].off];
+        ans_.resize(n);
+        probe_(q.data(), n, ans_.data());
+        cnt.probe_batches++; cnt.unforeseen_queries += n;
         return ans_.data();
     }
-    uint8_t probe1(K x) { std::vector<K> q(1, x); return probe(q)[0]; }
     // forward k-mers of a nucleotide string
     void kmers_of(const std::string& s, std::vector<K>& out) const {
         if (s.size() < (size_t)k) return;
@@ -143,6 +283,7 @@ private:
     // ---- writers (src/FindBreakpoints.hpp:641-702)
     void write_breakpoint(const std::string& chrom_name, uint64_t p, const std::string& kb, const std::string& ke, int repeat, const char* type,
                           bool rep_b = false, bool rep_e = false) {
+        if (collecting_) return;
         char hdr[1200];
         for (int side = 0; side < 2; side++) {
             snprintf(hdr, sizeof hdr, ">bkpt%i_%s_pos_%lli_fuzzy_%i_%s %s %s\n", (int)next_id, chrom_name.c_str(), (long long)(p + 1), repeat, type,
@@ -153,6 +294,7 @@ private:
         }
     }
     void write_vcf(uint64_t p, const std::string& ref, const std::string& alt, int repeat, const char* type) {
+        if (collecting_) return;
         int variant_size = strcmp(type, "DEL") == 0 ? (int)ref.size() - 1 : 1;
         char buf[1200];
         snprintf(buf, sizeof buf, "%s\t%lli\tbkpt%i\t", chrom.c_str(), (long long)(p + 1), (int)next_id);
@@ -161,6 +303,7 @@ private:
         vcf_out += buf;
     }
     void write_indel(uint64_t p, const std::string& ref, const std::string& alt, int repeat, const char* type) {
+        if (collecting_) return;
         const char* gt = !strcmp(type, "HOM") ? "1/1" : (!strcmp(type, "HET") ? "0/1" : "./.");
         char buf[1200];
         snprintf(buf, sizeof buf, "%s\t%lli\tbkpt%i\t", chrom.c_str(), (long long)(p + 1), (int)next_id);
@@ -203,6 +346,7 @@ private:
             for (int nt = 0; nt < 4; nt++) q.push_back(mutate(ring[idx].kmer, (K)nt, at_end ? (size_t)(k - j) : (size_t)(j + 1)));
         }
         const uint8_t* ans = probe(q);
+        walk_q_ = q; walk_ans_.assign(ans, ans + q.size());  // correct_history asks about a subset of these k-mers
         bool present[4] = {true, true, true, true};
         unsigned count[4] = {0, 0, 0, 0};
         int size = 3;
@@ -222,14 +366,28 @@ private:
         *beginpos = init;
         return false;
     }
+    std::vector<K> walk_q_;
+    std::vector<uint8_t> walk_ans_;
     void correct_history(unsigned char p0, K nuc) {  // src/FindSNP.hpp:360-381 (identical in the three SNP finders)
         std::vector<K> q(k);
         for (int i = 0; i < k; i++) q[i] = mutate(ring[(unsigned char)(p0 + i)].kmer, nuc, k - i);
-        const uint8_t* ans = probe(q);
+        // the k mutated k-mers are those of the preceding snp walk for this nucleotide (forward walk: j = i; backward
+        // walk: j = k-1-i); reuse its answers when they match, else probe
+        std::vector<uint8_t> a(k);
+        bool reuse = walk_q_.size() == (size_t)(4 * k);
+        if (reuse) {
+            const bool fwd_order = walk_q_[4 * 0 + (int)nuc] == q[0];
+            for (int i = 0; i < k && reuse; i++) {
+                const size_t j = 4 * (size_t)(fwd_order ? i : k - 1 - i) + (size_t)nuc;
+                if (walk_q_[j] == q[i]) a[i] = walk_ans_[j]; else reuse = false;
+            }
+        }
+        if (!reuse) { const uint8_t* ans = probe(q); for (int i = 0; i < k; i++) a[i] = ans[i]; }
+        else cnt.observer_queries += k;
         for (int i = 0; i < k; i++) {
             Info& h = ring[(unsigned char)(p0 + i)];
             h.kmer = q[i];
-            if (ans[i] & 1) { h.nb_in = (ans[i] >> 1) & 7; h.nb_out = (ans[i] >> 4) & 7; h.is_repeated = (ans[i] >> 7) & 1; }
+            if (a[i] & 1) { h.nb_in = (a[i] >> 1) & 7; h.nb_out = (a[i] >> 4) & 7; h.is_repeated = (a[i] >> 7) & 1; }
         }
     }
     static char nt_char(K n) { return n == 0 ? 'A' : n == 1 ? 'C' : n == 2 ? 'T' : 'G'; }
@@ -338,6 +496,7 @@ private:
     bool ends_connected() {
         std::vector<K> q = {begin_fwd, end_fwd};
         const uint8_t* a = probe(q);
+        if (collecting_) return true;  // let the caller enumerate the queries that follow
         return ((a[0] >> 4) & 7) != 0 && ((a[1] >> 1) & 7) != 0;
     }
     bool small_clean_insertion() {  // src/FindSmallInsertion.hpp:56-116
@@ -413,7 +572,7 @@ private:
                     write_breakpoint(chrom, pos - 1 + i, kb, ke, i, "HET", h.is_repeated, end_is_repeated);
                     next_id++;
                     if (i == 0) cnt.hetero_clean++; else cnt.hetero_fuzzy++;
-                    recent_hetero = opt.max_repeat;
+                    if (!collecting_) recent_hetero = opt.max_repeat;  // collect pass: keep enumerating the next candidates
                     return;
                 }
                 recent_hetero = std::max(0, recent_hetero - 1);

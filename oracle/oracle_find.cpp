@@ -4,6 +4,7 @@
 #include <chrono>
 #include <map>
 
+#include "count_mt.hpp"
 #include "scan_oracle.hpp"
 
 using namespace mtgo;
@@ -15,6 +16,7 @@ struct Args {
     int64_t abundance_max = 2147483647LL;
     FindOptions opt;
     bool dump = false, count_only = false;
+    int nb_cores = 1;
 };
 
 static void write_file(const std::string& path, const void* p, size_t n) {
@@ -43,7 +45,12 @@ template <class K> static int run(const Args& a) {
         std::vector<SeqRecord> reads;
         if (!load_bank(a.in, reads)) { fprintf(stderr, "cannot read %s\n", a.in.c_str()); return 1; }
         int amin = a.abundance_min == "auto" ? -1 : atoi(a.abundance_min.c_str());
-        count_bank<K>(reads, k, amin, a.abundance_max, cr);
+        if (a.nb_cores > 1) {  // stands in for the reference's -nb-cores threading of the DSK stage
+            std::string stream;
+            for (auto& r : reads) { stream += r.seq; stream += '\n'; }
+            count_stream<K>(stream.data(), stream.size(), k, amin, a.abundance_max, a.nb_cores, cr);
+        } else
+            count_bank<K>(reads, k, amin, a.abundance_max, cr);
     }
     double t1 = now_s();
     std::vector<K> solid;
@@ -135,7 +142,8 @@ int main(int argc, char** argv) {
         else if (o == "-het-max-occ") a.opt.het_max_occ = std::max(1, atoi(val().c_str()));
         else if (o == "-snp-min-val") a.opt.snp_min_val = atoi(val().c_str());
         else if (o == "-branching-filter") a.opt.branching_threshold = atoi(val().c_str());
-        else if (o == "-nb-cores" || o == "-max-memory" || o == "-max-disk" || o == "-verbose" || o == "-out-tmp") val();
+        else if (o == "-nb-cores") a.nb_cores = std::max(1, atoi(val().c_str()));
+        else if (o == "-max-memory" || o == "-max-disk" || o == "-verbose" || o == "-out-tmp") val();
         else if (o == "-dump") a.dump = true;
         else if (o == "-count-only") a.count_only = true;
         // mode flags, same order/semantics as M/Finder.cpp:321-398

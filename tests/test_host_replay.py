@@ -1,0 +1,56 @@
+"""Host logic of the product (no GPU): mindthegap_b200/csrc/replay.hpp -- gap state machine, observers, skip-ahead over
+uninteresting runs and the collect-pass / probe-log prefetch -- driven by ORACLE-computed features and probe answers
+(tests/host/replay_check.cpp) and compared with the outputs of the unmodified reference binary."""
+import os
+import subprocess
+
+import pytest
+
+from tests.cases import CASES, ROOT, case_paths, expected
+
+EXE = os.path.join(ROOT, "tests", "host", "_build", "replay_check")
+
+
+@pytest.fixture(scope="module")
+def replay_check():
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "host", "replay_check.cpp")
+    deps = [src, os.path.join(ROOT, "mindthegap_b200", "csrc", "replay.hpp")] + [
+        os.path.join(ROOT, "oracle", f) for f in ("scan_oracle.hpp", "graph_oracle.hpp", "kmer_oracle.hpp")]
+    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-o", EXE, src], check=True)
+    return EXE
+
+
+def run(exe, name, tmp_path, extra):
+    import mindthegap_b200 as m
+    case = CASES[name]
+    reads, ref = case_paths(case)
+    p = m.FindParams.from_cli(["-kmer-size", str(case["k"])] + list(case["flags"]))
+    out = str(tmp_path / name)
+    amin = "auto" if p.abundance_min < 0 else str(p.abundance_min)
+    r = subprocess.run([exe, "-in", reads, "-ref", ref, "-kmer-size", str(p.kmer_size), "-abundance-min", amin, "-max-rep", str(p.max_repeat),
+                        "-het-max-occ", str(p.het_max_occ), "-snp-min-val", str(p.snp_min_val), "-branching-filter", str(p.branching_filter),
+                        "-flags", str(p.flags), "-out", out] + extra, stdout=subprocess.PIPE, text=True, check=True)
+    info = dict(l.split() for l in r.stdout.strip().splitlines())
+    return open(out + ".breakpoints").read(), open(out + ".vcf").read(), {k: int(v) for k, v in info.items()}
+
+
+MODES = {"default": [], "tiny_segments": ["-seg", "777", "-skip-min", "1"], "walk_everything": ["-no-interest"]}
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_replay_equals_reference(replay_check, tmp_path, name, mode):
+    bk, vcf, info = run(replay_check, name, tmp_path, MODES[mode])
+    ebk, evcf, _ = expected(name)
+    assert bk == ebk
+    assert vcf == evcf
+
+
+def test_collect_pass_foresees_most_queries(replay_check, tmp_path):
+    """The collect pass + probe log must leave only a small share of the observer queries to immediate round trips."""
+    for name in ("full", "syn_small_k31"):
+        _, _, info = run(replay_check, name, tmp_path, [])
+        assert info["observer_queries"] > 0
+        assert info["unforeseen_queries"] <= 0.2 * info["observer_queries"], info
