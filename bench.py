@@ -121,7 +121,7 @@ def reference_arm(args):
 class ClockSampler:
     """Samples SM clock / power / throttle reasons of one GPU during the timed region (NVML in a thread, 50 ms period)."""
 
-    def __init__(self, index=0, period=0.05):
+    def __init__(self, index=0, period=0.2):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.stop_flag = threading.Event()
@@ -257,6 +257,12 @@ def own_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, wall_e2e, out_e2e, _ = timed(False, args.steps, max(1, args.warmup // 2))
     assert out_res[0] == out_e2e[0] and out_res[1] == out_e2e[1], "resident and host-buffer runs disagree"
+    if args.trace and rank == 0:  # one extra resident find with the library's stage trace on stderr
+        os.environ["MTG_TRACE"] = "1"
+        t0 = time.perf_counter()
+        one_find(True)
+        print("[bench trace] resident find %.3f ms" % ((time.perf_counter() - t0) * 1e3), file=sys.stderr)
+        os.environ["MTG_TRACE"] = "0"
 
     tot_kmers = wl["read_kmers"] + wl["ref_kmers"]
     if world > 1:
@@ -341,6 +347,10 @@ def own_arm(args):
             "stage_ms": {k: avg[k] for k in sorted(avg) if ".ms_" in k},
             "counts": {"read_kmers": read_kmers, "ref_kmers": ref_kmers, "nb_solid": avg["nb_solid"], "table_probes": probes,
                        "bloom_emulations": avg["scan.bloom_emulations"], "observer_queries": avg["scan.observer_queries"],
+                       "nb_records": avg["count.nb_records"], "nb_groups": avg["count.nb_groups"], "nb_items": avg["count.nb_items"],
+                       "nb_multipass_groups": avg["count.nb_multipass_groups"], "nb_candidates": avg["count.nb_candidates"],
+                       "prefetched_queries": avg["scan.prefetched_queries"], "unforeseen_queries": avg["scan.unforeseen_queries"],
+                       "probe_batches": avg["scan.probe_batches"],
                        "breakpoint_records": len(out_res[0].splitlines()) // 4, "vcf_records": len(out_res[1].splitlines())}}
     print(json.dumps(line))
     if world > 1:
@@ -351,12 +361,13 @@ def own_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the GPU workload (1.0 = cfg2)")
     ap.add_argument("--cpu-scale", type=float, default=0.25, help="genome scale of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--trace", action="store_true", help="print the library's per-stage wall clock for one extra find (stderr)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

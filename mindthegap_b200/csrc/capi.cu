@@ -13,6 +13,87 @@ typedef unsigned __int128 hu128;  // host-only 128-bit integer for the replay (g
 
 static thread_local std::string g_last_error;
 
+// ---- process-wide caching arena for device memory (common.cuh)
+namespace {
+struct ArenaBlock { void* p; size_t size; int device; cudaStream_t stream; cudaEvent_t ev; };
+std::mutex g_arena_mu;
+std::vector<ArenaBlock> g_arena_free;                 // cached blocks
+std::vector<ArenaBlock> g_arena_live;                 // handed out (size bookkeeping)
+std::vector<cudaEvent_t> g_arena_events;
+size_t g_arena_cached_bytes = 0, g_arena_live_bytes = 0;
+size_t arena_cache_limit() {
+    static size_t lim = [] { const char* e = getenv("MTG_ARENA_CACHE_GB"); return (size_t)((e ? atof(e) : 64.0) * (double)(1ull << 30)); }();
+    return lim;
+}
+void arena_release_block_locked(size_t i) {
+    ArenaBlock b = g_arena_free[i];
+    g_arena_free.erase(g_arena_free.begin() + i);
+    g_arena_cached_bytes -= b.size;
+    cudaEventSynchronize(b.ev);
+    g_arena_events.push_back(b.ev);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != b.device) cudaSetDevice(b.device);
+    cudaFree(b.p);
+    if (cur != b.device) cudaSetDevice(cur);
+}
+}  // namespace
+void* mtg::arena_alloc(size_t bytes, cudaStream_t s) {
+    const size_t want = (bytes + 511) & ~(size_t)511;
+    int dev = 0;
+    MTG_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < g_arena_free.size(); i++) {
+        const ArenaBlock& b = g_arena_free[i];
+        if (b.device != dev || b.size < want || b.size > want + want / 4 + 4096) continue;
+        if (best == (size_t)-1 || b.size < g_arena_free[best].size) best = i;
+    }
+    ArenaBlock blk;
+    if (best != (size_t)-1) {
+        blk = g_arena_free[best];
+        g_arena_free.erase(g_arena_free.begin() + best);
+        g_arena_cached_bytes -= blk.size;
+        if (blk.stream != s) MTG_CUDA(cudaStreamWaitEvent(s, blk.ev, 0));
+        g_arena_events.push_back(blk.ev);
+    } else {
+        blk.size = want; blk.device = dev;
+        cudaError_t e = cudaMalloc(&blk.p, want);
+        if (e != cudaSuccess) {  // out of memory: give the cache back and retry once
+            cudaGetLastError();
+            while (!g_arena_free.empty()) arena_release_block_locked(g_arena_free.size() - 1);
+            e = cudaMalloc(&blk.p, want);
+        }
+        if (e != cudaSuccess) throw mtg::Error(-2, std::string("cudaMalloc of ") + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    blk.stream = s; blk.ev = nullptr;
+    g_arena_live.push_back(blk);
+    g_arena_live_bytes += blk.size;
+    return blk.p;
+}
+void mtg::arena_free(void* p, cudaStream_t s) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    size_t i = g_arena_live.size();
+    while (i > 0 && g_arena_live[i - 1].p != p) i--;
+    if (i == 0) return;  // not ours
+    ArenaBlock blk = g_arena_live[i - 1];
+    g_arena_live.erase(g_arena_live.begin() + (i - 1));
+    g_arena_live_bytes -= blk.size;
+    if (g_arena_events.empty()) { cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); g_arena_events.push_back(ev); }
+    blk.ev = g_arena_events.back();
+    g_arena_events.pop_back();
+    blk.stream = s;
+    cudaEventRecord(blk.ev, s);
+    g_arena_free.push_back(blk);
+    g_arena_cached_bytes += blk.size;
+    while (g_arena_cached_bytes > arena_cache_limit() && !g_arena_free.empty()) arena_release_block_locked(0);  // oldest first
+}
+void mtg::arena_trim() {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    while (!g_arena_free.empty()) arena_release_block_locked(g_arena_free.size() - 1);
+}
+
 // ---- process-wide cache of pinned host buffers (PinnedBuf, common.cuh)
 namespace {
 std::mutex g_pin_mu;
@@ -62,7 +143,18 @@ struct mtg_ctx {
     double ms_features = 0, ms_replay = 0, ms_graph_build = 0;
     uint64_t scan_positions = 0, scan_valid = 0, scan_in_graph = 0, scan_table_probes = 0, scan_fallback = 0;
     std::vector<uint64_t> tmp_lo, tmp_hi;
+    // host wall-clock per entry point (ms, accumulated)
+    double wall_push = 0, wall_finish = 0, wall_set_reference = 0, wall_scan = 0;
 };
+
+namespace {
+struct WallTimer {
+    double& acc;
+    struct timespec t0;
+    explicit WallTimer(double& a) : acc(a) { clock_gettime(CLOCK_MONOTONIC, &t0); }
+    ~WallTimer() { struct timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1); acc += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6; }
+};
+}
 
 static void enter(mtg_ctx* c);
 #define MTG_TRY(ctx_expr) \
@@ -128,12 +220,6 @@ mtg_ctx* mtg_create(const mtg_params* p) {
         if (c->p.minimizer_size <= 0) c->p.minimizer_size = 10;
         MTG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         current_stream() = c->stream;
-        {   // keep freed device memory in the default pool: later allocations (and later contexts) cost no driver call
-            cudaMemPool_t pool;
-            MTG_CUDA(cudaDeviceGetDefaultMemPool(&pool, p->device));
-            uint64_t thr = ~0ull;
-            MTG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-        }
         c->graph.reset(make_graph(c->p.kmer_size, c->stream));
         c->histogram.assign(HISTO_MAX + 1, 0);
         make_replayers(c.get());
@@ -161,9 +247,11 @@ static ICounter* reads_counter(mtg_ctx* ctx) {
 }
 
 int mtg_count_reserve(mtg_ctx* ctx, uint64_t nb_bases) { MTG_TRY(ctx) reads_counter(ctx)->reserve(nb_bases); MTG_CATCH }
-int mtg_push_reads(mtg_ctx* ctx, const char* bases, uint64_t nbytes) { MTG_TRY(ctx) reads_counter(ctx)->push_host(bases, nbytes); MTG_CATCH }
+int mtg_push_reads(mtg_ctx* ctx, const char* bases, uint64_t nbytes) {
+    MTG_TRY(ctx) WallTimer w(ctx->wall_push); reads_counter(ctx)->push_host(bases, nbytes); MTG_CATCH
+}
 int mtg_push_reads_device(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes) {
-    MTG_TRY(ctx) reads_counter(ctx)->push_device((const uint8_t*)d_bases, nbytes); MTG_CATCH
+    MTG_TRY(ctx) WallTimer w(ctx->wall_push); reads_counter(ctx)->push_device((const uint8_t*)d_bases, nbytes); MTG_CATCH
 }
 
 int mtg_count_files(mtg_ctx* ctx, const char* uri) {
@@ -197,6 +285,7 @@ static void build_graph_from_counter(mtg_ctx* ctx, ICounter* c) {
 
 int mtg_count_finish(mtg_ctx* ctx) {
     MTG_TRY(ctx)
+    WallTimer w(ctx->wall_finish);
     ICounter* c = reads_counter(ctx);
     c->finish(ctx->p.abundance_min, ctx->p.abundance_max);
     ctx->count_stats = c->stats();
@@ -218,12 +307,14 @@ int mtg_get_histogram(mtg_ctx* ctx, uint64_t* out) { MTG_TRY(ctx) memcpy(out, ct
 static const char* STAT_NAMES[] = {
     "count.nb_bases", "count.nb_valid_kmers", "count.nb_records", "count.nb_groups", "count.nb_items", "count.nb_multipass_groups",
     "count.nb_candidates", "count.nb_solid", "count.ms_pack", "count.ms_extract", "count.ms_group", "count.ms_scatter", "count.ms_count",
-    "count.ms_filter", "count.launches",
+    "count.ms_filter", "count.launches", "count.retries",
     "graph.nbuckets", "graph.bloom_bits", "graph.nb_critical", "graph.bloom2_bits", "graph.bloom3_bits", "graph.bloom4_bits", "graph.cfp_set",
     "graph.ms_table", "graph.ms_bloom", "graph.ms_critical", "graph.ms_cascade", "graph.ms_mphf", "graph.ms_build_total", "graph.launches",
     "ref.nb_repeated", "ref.bloom_bits",
     "scan.positions", "scan.valid", "scan.in_graph", "scan.table_probes", "scan.bloom_emulations", "scan.ms_features", "scan.ms_replay",
-    "scan.observer_queries", "scan.probe_batches", "scan.prefetched_queries", "scan.unforeseen_queries"};
+    "scan.observer_queries", "scan.probe_batches", "scan.prefetched_queries", "scan.unforeseen_queries",
+    "api.ms_push_reads", "api.ms_count_finish", "api.ms_set_reference", "api.ms_scan_reference",
+    "mem.arena_cached_mb", "mem.arena_live_mb"};
 static const int NSTATS = sizeof(STAT_NAMES) / sizeof(STAT_NAMES[0]);
 const char* mtg_stat_name(int i) { return (i >= 0 && i < NSTATS) ? STAT_NAMES[i] : nullptr; }
 
@@ -236,13 +327,17 @@ int mtg_get_stats(mtg_ctx* ctx, double* out, int cap) {
     uint64_t pb = rc.probe_batches;
     double v[] = {(double)c.nb_bases, (double)c.nb_valid_kmers, (double)c.nb_records, (double)c.nb_groups, (double)c.nb_items,
                   (double)c.nb_multipass_groups, (double)c.nb_candidates, (double)c.nb_solid, c.ms_pack, c.ms_extract, c.ms_group, c.ms_scatter,
-                  c.ms_count, c.ms_filter, (double)c.launches,
+                  c.ms_count, c.ms_filter, (double)c.launches, (double)c.nb_count_retries,
                   (double)g.nbuckets, (double)g.bloom_tai, (double)g.nb_critical, (double)g.b2_tai, (double)g.b3_tai, (double)g.b4_tai, (double)g.ncfp,
                   g.ms_table, g.ms_bloom, g.ms_critical, g.ms_cascade, g.ms_mphf, ctx->ms_graph_build, (double)g.launches,
                   (double)g.ref_repeated, (double)g.ref_tai,
                   (double)ctx->scan_positions, (double)ctx->scan_valid, (double)ctx->scan_in_graph, (double)ctx->scan_table_probes,
                   (double)ctx->scan_fallback, ctx->ms_features, ctx->ms_replay, (double)oq, (double)pb, (double)rc.prefetched_queries,
-                  (double)rc.unforeseen_queries};
+                  (double)rc.unforeseen_queries, ctx->wall_push, ctx->wall_finish, ctx->wall_set_reference, ctx->wall_scan, 0.0, 0.0};
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        v[NSTATS - 2] = g_arena_cached_bytes / 1048576.0; v[NSTATS - 1] = g_arena_live_bytes / 1048576.0;
+    }
     int n = std::min(cap, NSTATS);
     for (int i = 0; i < n; i++) out[i] = v[i];
     return n;
@@ -273,14 +368,17 @@ int mtg_load_solid(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_
 }
 
 static void set_reference_impl(mtg_ctx* ctx, const char* bases, const void* d_bases, uint64_t nbytes) {
+    WallTimer w(ctx->wall_set_reference);
+    Trace tr(ctx->stream);
     MTG_CUDA(cudaSetDevice(ctx->p.device));
     const int k1 = ctx->p.kmer_size - 1;
-    std::unique_ptr<ICounter> rc(make_counter(k1, std::min(ctx->p.minimizer_size, k1), ctx->stream, ctx->p.kmer_size <= 31 ? 64 : 128));
+    std::unique_ptr<ICounter> rc(make_counter(k1, std::min(ctx->p.minimizer_size, k1), ctx->stream, ctx->p.kmer_size <= 31 ? 64 : 128, true));
     if (d_bases) rc->push_device((const uint8_t*)d_bases, nbytes); else rc->push_host(bases, nbytes);
     rc->finish(ctx->p.het_max_occ + 1, 2147483647LL);
     ctx->ref_count_stats = rc->stats();
     ctx->graph->set_ref_repeats(rc->solid_keys_device(), rc->nb_solid());
     ctx->ref_repeated = rc->nb_solid();
+    tr.mark("set_reference: total");
 }
 int mtg_set_reference(mtg_ctx* ctx, const char* bases, uint64_t nbytes) { MTG_TRY(ctx) set_reference_impl(ctx, bases, nullptr, nbytes); MTG_CATCH }
 int mtg_set_reference_device(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes) { MTG_TRY(ctx) set_reference_impl(ctx, nullptr, d_bases, nbytes); MTG_CATCH }
@@ -308,6 +406,8 @@ int mtg_sequence_features_device(mtg_ctx* ctx, const void* d_seq, uint64_t len, 
 }
 
 static void scan_reference_impl(mtg_ctx* ctx, const char* name, const char* seq, const void* d_seq, uint64_t len) {
+    WallTimer w(ctx->wall_scan);
+    Trace tr(ctx->stream);
     MTG_CUDA(cudaSetDevice(ctx->p.device));
     const int k = ctx->p.kmer_size;
     if (len < (uint64_t)k) return;  // reference quirk (replaying the previous sequence's k-mers) deliberately not reproduced
@@ -320,6 +420,7 @@ static void scan_reference_impl(mtg_ctx* ctx, const char* name, const char* seq,
     if (d_seq) ctx->graph->features_to_host((const uint8_t*)d_seq, len, feat, rep, interest, c4);
     else ctx->graph->features_host(seq, len, feat, rep, interest, c4);
     ctx->ms_features += ctx->graph->last_features_ms();
+    tr.mark("scan: features + copies");
     ctx->scan_positions += npos; ctx->scan_valid += c4[0]; ctx->scan_in_graph += c4[1]; ctx->scan_table_probes += c4[2]; ctx->scan_fallback += c4[3];
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
@@ -327,6 +428,7 @@ static void scan_reference_impl(mtg_ctx* ctx, const char* name, const char* seq,
     else ctx->rp128->scan(name ? name : "", seq, len, feat, rep, interest);
     clock_gettime(CLOCK_MONOTONIC, &t1);
     ctx->ms_replay += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+    tr.mark("scan: replay");
 }
 int mtg_scan_reference(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len) {
     MTG_TRY(ctx) scan_reference_impl(ctx, name, seq, nullptr, len); MTG_CATCH

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include <stdexcept>
 #include <string>
@@ -74,9 +76,16 @@ inline cudaStream_t& current_stream() {
     return s;
 }
 
-// Owning device buffer, stream-ordered (cudaMallocAsync / cudaFreeAsync on current_stream()). The device's default
-// memory pool is configured by mtg_create to keep freed memory (release threshold = max), so that after the first
-// `find` of a process allocation costs no driver round trip.
+// Process-wide caching arena for device memory (implemented in capi.cu). A `find` allocates the same few dozen buffer
+// sizes every time; freed blocks are kept and handed back on an (almost) exact size match, so that after the first find
+// of a process no allocation reaches the driver. (cudaMallocAsync's pool was tried first: under back-to-back contexts it
+// re-mapped physical memory unpredictably, adding 10-1000 ms to a 14 ms find.) Blocks carry the stream and an event of
+// their last use: reuse on another stream waits for that event, reuse on the same stream is ordered by the stream.
+void* arena_alloc(size_t bytes, cudaStream_t s);
+void arena_free(void* p, cudaStream_t s);
+void arena_trim();  // return every cached block to the driver
+
+// Owning device buffer on the arena; allocation and release are ordered on current_stream().
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
@@ -87,15 +96,31 @@ template <class T> struct DevBuf {
     DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFreeAsync(p, current_stream()); p = nullptr; n = 0; }
+    void release() { if (p) arena_free(p, current_stream()); p = nullptr; n = 0; }
     void alloc(size_t n_) {
         release();
         n = n_;
-        if (n) MTG_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), current_stream()));
+        if (n) p = (T*)arena_alloc(n * sizeof(T), current_stream());
     }
     void zero(cudaStream_t s = 0) { if (n) MTG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s ? s : current_stream())); }
     void fill_ff(cudaStream_t s = 0) { if (n) MTG_CUDA(cudaMemsetAsync(p, 0xFF, n * sizeof(T), s ? s : current_stream())); }
     size_t bytes() const { return n * sizeof(T); }
+};
+
+// Debug tracing (MTG_TRACE=1): wall-clock since the previous mark, after draining the stream. Off by default.
+struct Trace {
+    bool on;
+    cudaStream_t s;
+    struct timespec t0;
+    explicit Trace(cudaStream_t st) : s(st) { const char* e = getenv("MTG_TRACE"); on = e && *e == '1'; if (on) { cudaStreamSynchronize(s); clock_gettime(CLOCK_MONOTONIC, &t0); } }
+    void mark(const char* label) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "[mtg trace] %-28s %8.3f ms\n", label, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+        t0 = t1;
+    }
 };
 
 // Pinned host buffer taken from a process-wide cache (cudaHostAlloc costs milliseconds; contexts come and go).
@@ -163,6 +188,13 @@ MTG_HD uint64_t gatb_hash1(u128 key, uint64_t seed) { return gatb_hash64(key.lo,
 MTG_HD uint64_t mix64(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
+}
+// 32-bit hash for the shared-memory count tables (murmur3 fmix32 over the folded key): slot index = low bits, the
+// adaptive split of an oversized group consumes the bits above them.
+MTG_HD uint32_t fmix32(uint32_t x) { x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16; return x; }
+MTG_HD uint32_t key_hash32(uint64_t k) { return fmix32((uint32_t)k ^ ((uint32_t)(k >> 32) * 0x9E3779B1u)); }
+MTG_HD uint32_t key_hash32(u128 k) {
+    return fmix32((uint32_t)k.lo ^ ((uint32_t)(k.lo >> 32) * 0x9E3779B1u) ^ ((uint32_t)k.hi * 0x7FEB352Du) ^ ((uint32_t)(k.hi >> 32) * 0x846CA68Bu));
 }
 MTG_HD uint64_t key_hash(uint64_t k) { return mix64(k); }
 MTG_HD uint64_t key_hash(u128 k) { return mix64(k.lo ^ mix64(k.hi + 0x9E3779B97F4A7C15ULL)); }

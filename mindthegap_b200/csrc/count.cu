@@ -114,7 +114,8 @@ void launch_pack(const uint8_t* d_in, uint64_t n, uint64_t* d_packed, uint32_t* 
 // ------------------------------------------------------------------------------------------------------------
 static const int SK_TILE = 2048;      // positions per CTA tile
 static const int SK_THREADS = 256;
-static const int SK_NV = SK_TILE + 64;
+static const int SK_PER = SK_TILE / SK_THREADS;  // 8 consecutive positions per thread
+static const int SK_HALO = 64;        // m-mer positions computed past the tile (>= k - m)
 static const int SK_MAXRUN = 32;      // max k-mers per record (6-bit length field holds up to 64)
 static const int REC_POS_SHIFT = 26, REC_LEN_SHIFT = 20;
 static const int MH_REC_SHIFT = 36;   // minimizer histogram word: nrec << 36 | nkmers
@@ -123,130 +124,165 @@ MTG_HD uint64_t make_record(uint64_t pos, uint32_t len, uint32_t mini) {
     return (pos << REC_POS_SHIFT) | ((uint64_t)(len - 1) << REC_LEN_SHIFT) | mini;
 }
 
-// LUT value of an m-mer (Model.hpp:1040-1064 + is_allowed :1220-1251), computed arithmetically.
-MTG_D uint32_t mmer_value(uint32_t mm, int m, uint32_t mmask, uint32_t mask_ma1) {
-    uint32_t r = __brev(mm) >> (32 - 2 * m);
-    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
-    r = (r ^ 0xAAAAAAAAu) & mmask;
-    uint32_t c = min(mm, r);
-    uint32_t a1 = ~(c | (c >> 2));
-    a1 = ((a1 >> 1) & a1) & mask_ma1;
-    return a1 ? mmask : c;
-}
+// Partition function. GATB partitions k-mers by the lexicographically smallest allowed m-mer of the forward strand
+// (Model.hpp:1040-1064, 1220-1287) and a sampled bin-packing table (PartiInfo.cpp:40-86); neither choice influences the
+// counts ("only affects partitioning"). We use the random-order minimizer instead:
+// value(m-mer) = top 2m bits of (min(m-mer, revcomp) * golden-ratio constant), minimised over the k-m+1 m-mers of the
+// k-mer. It is strand-symmetric, so every instance of a canonical k-mer lands in the same bin, it needs no look-up
+// table, and random orders give longer super-k-mers (density ~2/(w+1)) and far flatter bins than lexicographic ones.
+MTG_D uint32_t mmer_hash(uint32_t fwd, uint32_t rc, int hshift) { return (min(fwd, rc) * 0x9E3779B1u) >> hshift; }
 
-// Window [p, p+k) contains no invalid base? `si` = invalid-mask words of the tile (first base = bit 31).
-MTG_D bool window_valid(const uint32_t* si, int p, int k) {
-    int a = p >> 5, o = p & 31;
-    uint32_t x0 = si[a], x1 = si[a + 1], x2 = si[a + 2];
-    uint32_t y0 = __funnelshift_l(x1, x0, o), y1 = __funnelshift_l(x2, x1, o);
-    if (k <= 32) return (y0 >> (32 - k)) == 0;
-    return y0 == 0 && (y1 >> (64 - k)) == 0;
-}
+MTG_D int sk_vidx(int q) { return q + (q >> 3); }  // padded index: threads reading element e of their 8-run hit 32 distinct banks
 
+// One tile = 2048 consecutive base positions of the packed read stream; thread t owns positions [8t, 8t+8).
+//  phase 2  hashed canonical m-mer value of every position (rolling fwd / revcomp m-mers, one 64-bit extract per thread)
+//  phase 3  minimizer = minimum over the k-m+1 values of the window: per thread suffix-min of its first 7 values,
+//           the block common to its 8 windows, prefix-min of the 7 values that follow (van Herk / Gil-Werman split)
+//  phase 4  window validity from the invalid-base mask (Model.hpp:752-758), break flags (minimizer change or invalid)
+//  phase 5  every run start emits 8-byte records {position, length <= 32, minimizer} (Sequence2SuperKmer.hpp:83-147)
+//  phase 6  records are published with one global atomic per tile; per-minimizer histogram for the grouping step
 __global__ void __launch_bounds__(SK_THREADS)
 superkmer_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ inv, uint64_t word_begin, uint64_t nwords,
                  int k, int m, uint64_t* __restrict__ records, unsigned long long* __restrict__ nrec_global, uint64_t rec_capacity,
                  unsigned long long* __restrict__ mhist, unsigned long long* __restrict__ nvalid_global, int* __restrict__ overflow) {
     __shared__ uint64_t sw[SK_TILE / 32 + 4];
     __shared__ uint32_t si[SK_TILE / 32 + 4];
-    __shared__ uint32_t va[SK_NV], vb[SK_NV];
-    __shared__ uint32_t s_brk[SK_TILE / 32], s_vld[SK_TILE / 32];
+    __shared__ uint32_t va[(SK_TILE + SK_HALO) / 8 * 9 + 8];
+    __shared__ uint32_t s_last[SK_THREADS];
+    __shared__ uint32_t s_brk[SK_TILE / 32 + 1];
     __shared__ uint64_t stage[SK_TILE];
-    __shared__ uint32_t s_nstage, s_nvalid, s_anyinv;
+    __shared__ uint32_t s_nstage, s_nvalid;
     __shared__ unsigned long long s_gbase;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int W = k - m + 1;
     const uint32_t mmask = (uint32_t)((1ull << (2 * m)) - 1);
-    const uint32_t mask_ma1 = 0x55555555u & (uint32_t)((1ull << (2 * (m - 2))) - 1);
+    const int hshift = 32 - 2 * m;
     const uint64_t ntiles = (nwords + SK_TILE / 32 - 1) / (SK_TILE / 32);
 
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t w0 = word_begin + tile * (SK_TILE / 32);
         const int tile_words = (int)min((uint64_t)(SK_TILE / 32), word_begin + nwords - w0);
         const int tile_pos = tile_words * 32;
-        if (tid == 0) { s_nstage = 0; s_nvalid = 0; s_anyinv = 0; }
-        __syncthreads();
+        if (tid == 0) { s_nstage = 0; s_nvalid = 0; s_brk[SK_TILE / 32] = 0xFFFFFFFFu; }
         // ---- phase 1: stage packed words + invalid masks (arrays are padded with >= 4 all-invalid words)
         for (int i = tid; i < SK_TILE / 32 + 4; i += SK_THREADS) {
-            bool in = i < tile_words + 4;
-            uint64_t w = in ? packed[w0 + i] : 0;
-            uint32_t iv = in ? inv[w0 + i] : 0xFFFFFFFFu;
-            sw[i] = w; si[i] = iv;
-            if (iv && i < tile_words + 2) s_anyinv = 1;
+            const bool in = i < tile_words + 4;
+            sw[i] = in ? packed[w0 + i] : 0;
+            si[i] = in ? inv[w0 + i] : 0xFFFFFFFFu;
         }
         __syncthreads();
-        const bool anyinv = s_anyinv != 0;
-        // ---- phase 2: LUT value of the m-mer starting at every position (tile + halo)
-        for (int p = tid; p < SK_NV; p += SK_THREADS) {
-            uint32_t v = 0xFFFFFFFFu;
-            if (p < tile_pos + W - 1) {
-                int a = p >> 5, off = 2 * (p & 31);
-                uint64_t x = sw[a] << off;
-                if (off) x |= sw[a + 1] >> (64 - off);
-                v = mmer_value((uint32_t)(x >> (64 - 2 * m)), m, mmask, mask_ma1);
+        // ---- phase 2: hashed m-mer values, 8 consecutive positions per thread slot (tile + halo)
+        for (int slot = tid; slot < (SK_TILE + SK_HALO) / SK_PER; slot += SK_THREADS) {
+            const int q0 = slot * SK_PER;
+            const int a = q0 >> 5, off = 2 * (q0 & 31);
+            uint64_t x = sw[a] << off;
+            if (off) x |= sw[a + 1] >> (64 - off);
+            uint32_t fwd = (uint32_t)(x >> (64 - 2 * m));
+            uint32_t rc = __brev(fwd) >> hshift;
+            rc = ((rc >> 1) & 0x55555555u) | ((rc & 0x55555555u) << 1);
+            rc = (rc ^ 0xAAAAAAAAu) & mmask;
+            uint32_t* dst = va + 9 * slot;
+            dst[0] = mmer_hash(fwd, rc, hshift);
+            x <<= 2 * m;
+#pragma unroll
+            for (int j = 1; j < SK_PER; j++) {
+                const uint32_t c = (uint32_t)(x >> 62);
+                x <<= 2;
+                fwd = ((fwd << 2) | c) & mmask;
+                rc = (rc >> 2) | ((c ^ 2u) << (2 * m - 2));
+                dst[j] = mmer_hash(fwd, rc, hshift);
             }
-            va[p] = v;
         }
         __syncthreads();
-        // ---- phase 3: sliding minimum over W consecutive m-mers by doubling (sparse-table) passes
-        uint32_t* src = va;
-        uint32_t* dst = vb;
-        int pw = 1;
-        while (2 * pw <= W) {
-            for (int p = tid; p < SK_NV; p += SK_THREADS) dst[p] = min(src[p], src[min(p + pw, SK_NV - 1)]);
-            __syncthreads();
-            uint32_t* t = src; src = dst; dst = t;
-            pw *= 2;
-        }
-        // minimizer of window p = min(src[p], src[p + W - pw]); written to dst
-        uint32_t mini[SK_TILE / SK_THREADS];
-        bool valid[SK_TILE / SK_THREADS];
+        // ---- phase 3: minimizer of the 8 windows owned by this thread
+        const int p0 = tid * SK_PER;
+        uint32_t mini[SK_PER];
+        {
+            const uint32_t* v = va + 9 * tid;  // element e of this thread's run lives at v[e + (e >> 3)]
+            if (W >= SK_PER) {
+                uint32_t suf[SK_PER];
+                uint32_t sacc = 0xFFFFFFFFu;
+                suf[SK_PER - 1] = sacc;
 #pragma unroll
-        for (int i = 0; i < SK_TILE / SK_THREADS; i++) {
-            int p = i * SK_THREADS + tid;
-            mini[i] = min(src[p], src[p + W - pw]);
-            valid[i] = p < tile_pos && (!anyinv || window_valid(si, p, k));
-            dst[p] = mini[i];
-            uint32_t b = __ballot_sync(0xFFFFFFFFu, valid[i]);
-            if (lane == 0) { s_vld[p >> 5] = __brev(b); if (b) atomicAdd(&s_nvalid, __popc(b)); }  // position p at bit 31-(p&31)
+                for (int e = SK_PER - 2; e >= 0; e--) { sacc = min(sacc, v[e]); suf[e] = sacc; }
+                uint32_t mid = 0xFFFFFFFFu;
+                for (int e = SK_PER - 1; e < W; e++) mid = min(mid, v[e + (e >> 3)]);
+                uint32_t pacc = 0xFFFFFFFFu;
+                mini[0] = min(suf[0], mid);
+#pragma unroll
+                for (int j = 1; j < SK_PER; j++) {
+                    const int e = W + j - 1;
+                    pacc = min(pacc, v[e + (e >> 3)]);
+                    mini[j] = min(min(suf[j], mid), pacc);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < SK_PER; j++) {
+                    uint32_t acc = 0xFFFFFFFFu;
+                    for (int e = j; e < j + W; e++) acc = min(acc, v[e + (e >> 3)]);
+                    mini[j] = acc;
+                }
+            }
+        }
+        // ---- phase 4: validity of the 8 windows (no invalid base in [p, p+k)), break flags
+        uint32_t vmask = 0;
+        {
+            const int a = p0 >> 5, o = p0 & 31;
+            const uint32_t x0 = si[a], x1 = si[a + 1], x2 = si[a + 2], x3 = si[a + 3];
+            const uint32_t y0 = __funnelshift_l(x1, x0, o), y1 = __funnelshift_l(x2, x1, o), y2 = __funnelshift_l(x3, x2, o);
+#pragma unroll
+            for (int j = 0; j < SK_PER; j++) {
+                const uint32_t z0 = __funnelshift_l(y1, y0, j);
+                bool ok;
+                if (k <= 32) ok = (z0 >> (32 - k)) == 0;
+                else { const uint32_t z1 = __funnelshift_l(y2, y1, j); ok = z0 == 0 && (z1 >> (64 - k)) == 0; }
+                ok = ok && (p0 + j < tile_pos);
+                vmask |= (ok ? 1u : 0u) << j;
+            }
+        }
+        s_last[tid] = mini[SK_PER - 1] | ((vmask >> (SK_PER - 1)) << 31);
+        uint32_t bmask = 0;
+#pragma unroll
+        for (int j = 1; j < SK_PER; j++) {
+            const bool brk = !((vmask >> j) & 1) || !((vmask >> (j - 1)) & 1) || mini[j] != mini[j - 1];
+            bmask |= (brk ? 1u : 0u) << j;
         }
         __syncthreads();
-        // ---- phase 4: break flags (new super-k-mer starts here, or position invalid)
-#pragma unroll
-        for (int i = 0; i < SK_TILE / SK_THREADS; i++) {
-            int p = i * SK_THREADS + tid;
-            bool prev_valid = p > 0 && ((s_vld[(p - 1) >> 5] >> (31 - ((p - 1) & 31))) & 1);
-            bool brk = !valid[i] || !prev_valid || dst[p - (p > 0)] != mini[i];
-            uint32_t b = __ballot_sync(0xFFFFFFFFu, brk);
-            if (lane == 0) s_brk[p >> 5] = __brev(b);  // store with position p at bit 31-(p&31)
+        {
+            const uint32_t prev = tid ? s_last[tid - 1] : 0u;  // no predecessor inside the tile: a run starts here
+            const bool brk0 = !(vmask & 1) || !(prev >> 31) || (prev & 0x7FFFFFFFu) != mini[0];
+            bmask |= brk0 ? 1u : 0u;
+            reinterpret_cast<uint8_t*>(s_brk)[tid] = (uint8_t)bmask;  // bit i of word w <-> position 32w + i
+        }
+        {
+            uint32_t nv = __popc(vmask);
+            for (int o = 16; o; o >>= 1) nv += __shfl_down_sync(0xFFFFFFFFu, nv, o);
+            if (lane == 0 && nv) atomicAdd(&s_nvalid, nv);
         }
         __syncthreads();
         // ---- phase 5: run starts emit records into the staging buffer
-#pragma unroll
-        for (int i = 0; i < SK_TILE / SK_THREADS; i++) {
-            int p = i * SK_THREADS + tid;
-            bool is_start = valid[i] && ((s_brk[p >> 5] >> (31 - (p & 31))) & 1);
-            if (is_start) {
-                // next break strictly after p
-                int q = p + 1, wq = q >> 5;
-                int end = tile_pos;
-                if (q < tile_pos) {
-                    uint32_t bits = s_brk[wq] & (0xFFFFFFFFu >> (q & 31));
-                    while (true) {
-                        if (bits) { end = wq * 32 + __clz(bits); break; }
-                        wq++;
-                        if (wq * 32 >= tile_pos) break;
-                        bits = s_brk[wq];
-                    }
-                    if (end > tile_pos) end = tile_pos;
-                }
-                int len = end - p;
-                int nrec = (len + SK_MAXRUN - 1) / SK_MAXRUN;
-                uint32_t slot = atomicAdd(&s_nstage, (uint32_t)nrec);
-                uint64_t gpos = (w0 - 0) * 32 + p;
-                for (int o = 0; o < len; o += SK_MAXRUN) stage[slot++] = make_record(gpos + o, (uint32_t)min(SK_MAXRUN, len - o), mini[i]);
+        uint32_t starts = vmask & bmask;
+        while (starts) {
+            const int j = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const int p = p0 + j;
+            int q = p + 1, wq = q >> 5;
+            uint32_t bits = s_brk[wq] >> (q & 31);
+            int end;
+            if (bits) end = q + __ffs(bits) - 1;
+            else {
+                do { wq++; bits = s_brk[wq]; } while (!bits);  // the sentinel word ends the search at the tile end
+                end = wq * 32 + __ffs(bits) - 1;
             }
+            const int len = end - p;
+            const int nrec = (len + SK_MAXRUN - 1) / SK_MAXRUN;
+            uint32_t slot = atomicAdd(&s_nstage, (uint32_t)nrec);
+            const uint64_t gpos = w0 * 32 + p;
+            uint32_t mv = mini[0];
+#pragma unroll
+            for (int jj = 1; jj < SK_PER; jj++) mv = j == jj ? mini[jj] : mv;  // register select (no dynamic indexing)
+            for (int o = 0; o < len; o += SK_MAXRUN) stage[slot++] = make_record(gpos + o, (uint32_t)min(SK_MAXRUN, len - o), mv);
         }
         __syncthreads();
         // ---- phase 6: publish
@@ -261,9 +297,9 @@ superkmer_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict
             if (tid == 0) *overflow = 1;
         } else {
             for (uint32_t i = tid; i < ns; i += SK_THREADS) {
-                uint64_t r = stage[i];
+                const uint64_t r = stage[i];
                 records[gbase + i] = r;
-                uint32_t len = (uint32_t)((r >> REC_LEN_SHIFT) & 63) + 1;
+                const uint32_t len = (uint32_t)((r >> REC_LEN_SHIFT) & 63) + 1;
                 atomicAdd(&mhist[r & ((1u << REC_LEN_SHIFT) - 1)], (1ull << MH_REC_SHIFT) | len);
             }
         }
@@ -273,8 +309,9 @@ superkmer_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict
 
 // ------------------------------------------------------------------------------------------------------------
 // grouping of minimizer bins into work items (the role of Repartitor::computeDistrib, PartiInfo.cpp:40-86), on the device:
-//   bin v (k-mer instances nk[v], records nr[v]) -> group floor(P[v] / GROUP_TARGET), P = exclusive prefix sum of nk;
-//   a group whose load exceeds GROUP_CAP instances is counted in ceil(load / GROUP_CAP) hash-selected passes.
+//   bin v (k-mer instances nk[v], records nr[v]) -> group floor(P[v] / group_target), P = exclusive prefix sum of nk.
+//   A group is one work item of the count kernel (records [grp_off[g], grp_off[g+1]) of the grouped list); groups whose
+//   distinct k-mers do not fit one shared-memory table are split adaptively inside the count kernel.
 // ------------------------------------------------------------------------------------------------------------
 static const int GP_THREADS = 256, GP_PER_THREAD = 16, GP_TILE = GP_THREADS * GP_PER_THREAD;
 
@@ -322,8 +359,7 @@ __global__ void __launch_bounds__(1024) scan_one_cta_kernel(unsigned long long* 
 // group id of every bin + per-group record count and load
 __global__ void __launch_bounds__(GP_THREADS) group_assign_kernel(const unsigned long long* __restrict__ mhist, uint32_t nbins,
                                                                   const unsigned long long* __restrict__ tile_off, uint32_t group_target,
-                                                                  uint32_t* __restrict__ group_of, unsigned long long* __restrict__ grp_nrec,
-                                                                  unsigned long long* __restrict__ grp_load) {
+                                                                  uint32_t* __restrict__ group_of, unsigned long long* __restrict__ grp_nrec) {
     __shared__ unsigned long long s_warp[32];
     const uint32_t base = blockIdx.x * GP_TILE + threadIdx.x * GP_PER_THREAD;
     unsigned long long nk[GP_PER_THREAD], acc = 0;
@@ -334,7 +370,7 @@ __global__ void __launch_bounds__(GP_THREADS) group_assign_kernel(const unsigned
     unsigned long long total;
     unsigned long long run = tile_off[blockIdx.x] + block_exclusive_scan(acc, s_warp, total);
     uint32_t cur_g = 0xFFFFFFFFu;
-    unsigned long long a_nrec = 0, a_load = 0;
+    unsigned long long a_nrec = 0;
     for (int i = 0; i < GP_PER_THREAD; i++) {
         if (base + i >= nbins) break;
         const unsigned long long k_i = nk[i] & ((1ull << MH_REC_SHIFT) - 1), r_i = nk[i] >> MH_REC_SHIFT;
@@ -342,44 +378,15 @@ __global__ void __launch_bounds__(GP_THREADS) group_assign_kernel(const unsigned
         group_of[base + i] = g;
         if (r_i) {
             if (g != cur_g) {
-                if (a_nrec) { atomicAdd(&grp_nrec[cur_g], a_nrec); atomicAdd(&grp_load[cur_g], a_load); }
-                cur_g = g; a_nrec = 0; a_load = 0;
+                if (a_nrec) atomicAdd(&grp_nrec[cur_g], a_nrec);
+                cur_g = g; a_nrec = 0;
             }
-            a_nrec += r_i; a_load += k_i;
+            a_nrec += r_i;
         }
         run += k_i;
     }
-    if (a_nrec) { atomicAdd(&grp_nrec[cur_g], a_nrec); atomicAdd(&grp_load[cur_g], a_load); }
+    if (a_nrec) atomicAdd(&grp_nrec[cur_g], a_nrec);
 }
-// passes per group (in place of the load): 0 for empty groups
-__global__ void __launch_bounds__(256) group_passes_kernel(const unsigned long long* __restrict__ grp_nrec, unsigned long long* __restrict__ grp_load,
-                                                           uint32_t ngroups, uint32_t group_cap, unsigned long long* __restrict__ stats3) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ngroups) return;
-    unsigned long long np = 0;
-    if (grp_nrec[g]) {
-        const unsigned long long load = grp_load[g];
-        np = load <= group_cap ? 1 : (load + group_cap / 2 - 1) / (group_cap / 2);  // oversized bins: generous pass count
-        atomicAdd(&stats3[0], 1ull);
-        if (np > 1) atomicAdd(&stats3[1], 1ull);
-        if (np > 65535 || grp_nrec[g] > 0xFFFFFFFFull) atomicAdd(&stats3[2], 1ull);
-    }
-    grp_load[g] = np;
-}
-struct WorkItem { uint64_t rec_off; uint32_t nrec; uint16_t pass, npass; };
-// items of every group: grp_off = exclusive scan of records, item_off = exclusive scan of passes
-__global__ void __launch_bounds__(256) group_items_kernel(const unsigned long long* __restrict__ grp_nrec_orig, const unsigned long long* __restrict__ grp_off,
-                                                          const unsigned long long* __restrict__ item_off, uint32_t ngroups,
-                                                          WorkItem* __restrict__ items) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ngroups) return;
-    const unsigned long long nrec = grp_nrec_orig[g];
-    if (!nrec) return;
-    const unsigned long long first = item_off[g];
-    const unsigned long long np = item_off[g + 1] - first;  // both scans run over ngroups+1 entries (last one = total)
-    for (unsigned long long p = 0; p < np; p++) items[first + p] = {grp_off[g], (uint32_t)nrec, (uint16_t)p, (uint16_t)np};
-}
-
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) scatter_kernel(const uint64_t* __restrict__ records, uint64_t nrec, const uint32_t* __restrict__ group_of,
                                                       const uint64_t* __restrict__ group_off, unsigned int* __restrict__ group_cur,
@@ -404,93 +411,140 @@ MTG_D uint64_t slot_claim(uint64_t* slot, uint64_t key) {
 }
 MTG_D u128 slot_claim(u128* slot, u128 key) { return cas_shared(slot, ~(u128)0, key); }
 
+
+// One CTA per work item = one group of minimizer bins (records [grp_off[g], grp_off[g+1]) of the grouped list).
+// Warp-cooperative expansion: a warp loads 16 records, scans their lengths and writes one (record, offset) pair per
+// k-mer instance into its shared-memory slate; then every lane takes instances round-robin, so all 32 lanes insert
+// regardless of how uneven the super-k-mer lengths are. Each instance is extracted straight from the 2-bit packed reads
+// (L1/L2-resident lines shared by neighbouring lanes), canonicalised and inserted into the CTA's open-addressing table
+// with shared-memory atomics; the table is then swept (abundance histogram + candidates).
+// The table holds DISTINCT k-mers, the grouping only bounds INSTANCES: when a probe sequence gets too long the pass is
+// abandoned and the hash class it covered is split in two (one more hash bit), recursively, so a group of mostly
+// distinct k-mers (low coverage, the reference itself) costs extra passes instead of failing.
+static const int CK_CHUNK = 16;                       // records per warp iteration
+static const int CK_SLATE = CK_CHUNK * SK_MAXRUN;     // k-mer instances per warp iteration (<= 512)
+static const int CK_MAXPROBE = 64;                    // probe length that declares the table too full
+static const int CK_STACK = 40;
+
 template <class K> struct CountCfg;
-template <> struct CountCfg<uint64_t> { static const int SLOTS = 8192; };
-template <> struct CountCfg<u128> { static const int SLOTS = 4096; };
+template <> struct CountCfg<uint64_t> { static const int SLOTS = 8192, LOG_SLOTS = 13; };
+template <> struct CountCfg<u128> { static const int SLOTS = 4096, LOG_SLOTS = 12; };
 static const int COUNT_THREADS = 512;
-static const int SMEM_HIST = 256;
+static const int SMEM_HIST = 128;
 
 template <class K>
 __global__ void __launch_bounds__(COUNT_THREADS, 2)
-count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ grouped, const WorkItem* __restrict__ items,
-             const unsigned long long* __restrict__ nitems_ptr,
-             unsigned int* __restrict__ item_counter, int k, uint32_t emit_min, unsigned long long* __restrict__ histo,
+count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ grouped, const unsigned long long* __restrict__ grp_off,
+             uint32_t ngroups, unsigned int* __restrict__ item_counter, int k, uint32_t emit_min, unsigned long long* __restrict__ histo,
              K* __restrict__ cand_keys, uint32_t* __restrict__ cand_cnt, unsigned long long* __restrict__ ncand, uint64_t cand_capacity,
-             int* __restrict__ errflag) {
-    const int S = CountCfg<K>::SLOTS;
+             unsigned long long* __restrict__ gstats, int* __restrict__ errflag) {
+    const int S = CountCfg<K>::SLOTS, LOGS = CountCfg<K>::LOG_SLOTS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K* keys = reinterpret_cast<K*>(smem_raw);
     uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * S);
     uint32_t* hist_s = cnt + S;
-    __shared__ uint32_t s_item;
+    uint16_t* slate = reinterpret_cast<uint16_t*>(hist_s + SMEM_HIST) + (threadIdx.x >> 5) * CK_SLATE;
+    __shared__ uint32_t s_item, s_overflow, s_sp;
+    __shared__ uint32_t s_stack[CK_STACK];  // (level << 24) | class prefix: keys whose hash bits [LOGS, LOGS+level) == prefix
     const K EMPTY = ~K(0);
-    const int tid = threadIdx.x, lane = tid & 31;
-    const K mask = kmask<K>(k);
-    const int rcshift = 2 * (k - 1);
-    const uint32_t nitems = (uint32_t)*nitems_ptr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     while (true) {
-        if (tid == 0) s_item = atomicAdd(item_counter, 1u);
-        for (int s = tid; s < S; s += COUNT_THREADS) { keys[s] = EMPTY; cnt[s] = 0; }
+        if (tid == 0) {
+            uint32_t it;
+            do { it = atomicAdd(item_counter, 1u); } while (it < ngroups && grp_off[it + 1] == grp_off[it]);  // skip empty groups
+            s_item = it; s_sp = 1; s_stack[0] = 0;
+        }
         if (tid < SMEM_HIST) hist_s[tid] = 0;
         __syncthreads();
         const uint32_t it = s_item;
-        if (it >= nitems) break;
-        const WorkItem wi = items[it];
-        const uint64_t* recs = grouped + wi.rec_off;
-        // ---- insert
-        for (uint32_t ri = tid; ri < wi.nrec; ri += COUNT_THREADS) {
-            const uint64_t r = recs[ri];
-            const uint64_t pos = r >> REC_POS_SHIFT;
-            const int len = (int)((r >> REC_LEN_SHIFT) & 63) + 1;
-            K fwd = extract_kmer<K>(packed, pos, k);
-            K rc = revcomp(fwd, k);
-            BaseStream bs;
-            bs.init(packed, pos + k);
-            for (int j = 0; j < len; j++) {
-                if (j) {
-                    unsigned c = bs.next();
-                    fwd = ((fwd << 2) | (K)c) & mask;
-                    rc = (rc >> 2) | ((K)(c ^ 2u) << rcshift);
+        if (it >= ngroups) break;
+        const uint64_t rec_off = grp_off[it];
+        const uint32_t nrec = (uint32_t)(grp_off[it + 1] - rec_off);
+        const uint64_t* recs = grouped + rec_off;
+        uint32_t npasses = 0;
+        while (true) {   // hash classes of this group, depth first
+            const uint32_t sp = s_sp;
+            if (sp == 0) break;
+            const uint32_t top = s_stack[sp - 1];
+            const uint32_t level = top >> 24, prefix = top & 0xFFFFFFu, cmask = (1u << level) - 1u;
+            __syncthreads();
+            if (tid == 0) { s_sp = sp - 1; s_overflow = 0; }
+            for (int s = tid; s < S; s += COUNT_THREADS) { keys[s] = EMPTY; cnt[s] = 0; }
+            __syncthreads();
+            npasses++;
+            // ---- insert
+            for (uint32_t base = warp * CK_CHUNK; base < nrec; base += (COUNT_THREADS / 32) * CK_CHUNK) {
+                if (*(volatile uint32_t*)&s_overflow) break;
+                uint64_t r = 0;
+                int len = 0;
+                if (lane < CK_CHUNK && base + lane < nrec) { r = recs[base + lane]; len = (int)((r >> REC_LEN_SHIFT) & 63) + 1; }
+                int incl = len;
+                for (int o = 1; o < CK_CHUNK; o <<= 1) { int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+                const int total = __shfl_sync(0xFFFFFFFFu, incl, CK_CHUNK - 1);
+                const int excl = incl - len;
+                for (int j = 0; j < len; j++) slate[excl + j] = (uint16_t)((lane << 8) | j);
+                const uint64_t rpos = r >> REC_POS_SHIFT;
+                const uint32_t rpos_lo = (uint32_t)rpos, rpos_hi = (uint32_t)(rpos >> 32);
+                __syncwarp();
+                for (int s = lane; s < ((total + 31) & ~31); s += 32) {
+                    const bool act = s < total;
+                    const uint32_t e = act ? slate[s] : 0;
+                    const uint32_t plo = __shfl_sync(0xFFFFFFFFu, rpos_lo, e >> 8), phi = __shfl_sync(0xFFFFFFFFu, rpos_hi, e >> 8);
+                    if (!act) continue;
+                    const uint64_t pos = (((uint64_t)phi << 32) | plo) + (e & 0xFF);
+                    const K fwd = extract_kmer<K>(packed, pos, k);
+                    const K rc = revcomp(fwd, k);
+                    const K key = fwd < rc ? fwd : rc;
+                    const uint32_t h = key_hash32(key);
+                    if (((h >> LOGS) & cmask) != prefix) continue;
+                    uint32_t slot = h & (S - 1);
+                    int probes = 0;
+                    while (true) {
+                        const K cur = slot_claim(&keys[slot], key);
+                        if (cur == EMPTY || cur == key) { atomicAdd(&cnt[slot], 1u); break; }
+                        slot = (slot + 1) & (S - 1);
+                        if (++probes >= CK_MAXPROBE) { *(volatile uint32_t*)&s_overflow = 1; break; }
+                    }
                 }
-                const K key = fwd < rc ? fwd : rc;
-                const uint64_t h = key_hash(key);
-                if (wi.npass > 1 && (uint32_t)((h >> 32) % wi.npass) != wi.pass) continue;
-                uint32_t slot = (uint32_t)h & (S - 1);
-                int probes = 0;
-                while (true) {
-                    const K cur = slot_claim(&keys[slot], key);
-                    if (cur == EMPTY || cur == key) { atomicAdd(&cnt[slot], 1u); break; }
-                    slot = (slot + 1) & (S - 1);
-                    if (++probes >= S) { *errflag = 1; break; }
+                __syncwarp();
+            }
+            __syncthreads();
+            if (*(volatile uint32_t*)&s_overflow) {   // split this class on the next hash bit and retry both halves
+                if (tid == 0) {
+                    if (level >= 32 - LOGS - 1 || sp + 1 > CK_STACK) *errflag = 1;
+                    else { s_stack[sp - 1] = ((level + 1) << 24) | prefix; s_stack[sp] = ((level + 1) << 24) | prefix | (1u << level); s_sp = sp + 1; }
+                }
+                __syncthreads();
+                if (*(volatile int*)errflag == 1) break;
+                continue;
+            }
+            // ---- sweep: histogram (Histogram::inc takes a u16: CountProcessorHistogram.hpp:174-185, Histogram.hpp:92)
+            for (int s = tid; s < S; s += COUNT_THREADS) {
+                const K key = keys[s];
+                const bool occ = key != EMPTY;
+                uint32_t c = occ ? cnt[s] : 0;
+                if (occ) {
+                    uint32_t hidx = c & 0xFFFFu;
+                    if (hidx > HISTO_MAX) hidx = HISTO_MAX;
+                    if (hidx < SMEM_HIST) atomicAdd(&hist_s[hidx], 1u); else atomicAdd(&histo[hidx], 1ull);
+                }
+                const bool emit = occ && c >= emit_min;
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, emit);
+                if (b) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(ncand, (unsigned long long)__popc(b));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (emit) {
+                        unsigned long long o = base + __popc(b & ((1u << lane) - 1));
+                        if (o < cand_capacity) { cand_keys[o] = key; cand_cnt[o] = c; } else *errflag = 2;
+                    }
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
-        // ---- sweep: histogram (Histogram::inc takes a u16: CountProcessorHistogram.hpp:174-185, Histogram.hpp:92)
-        for (int s = tid; s < S; s += COUNT_THREADS) {
-            const K key = keys[s];
-            const bool occ = key != EMPTY;
-            uint32_t c = occ ? cnt[s] : 0;
-            if (occ) {
-                uint32_t hidx = c & 0xFFFFu;
-                if (hidx > HISTO_MAX) hidx = HISTO_MAX;
-                if (hidx < SMEM_HIST) atomicAdd(&hist_s[hidx], 1u); else atomicAdd(&histo[hidx], 1ull);
-            }
-            const bool emit = occ && c >= emit_min;
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, emit);
-            if (b) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(ncand, (unsigned long long)__popc(b));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (emit) {
-                    unsigned long long o = base + __popc(b & ((1u << lane) - 1));
-                    if (o < cand_capacity) { cand_keys[o] = key; cand_cnt[o] = c; } else *errflag = 2;
-                }
-            }
-        }
-        __syncthreads();
         if (tid < SMEM_HIST && hist_s[tid]) atomicAdd(&histo[tid], (unsigned long long)hist_s[tid]);
+        if (tid == 0) { atomicAdd(&gstats[0], 1ull); atomicAdd(&gstats[3], (unsigned long long)npasses); if (npasses > 1) atomicAdd(&gstats[1], 1ull); }
         __syncthreads();
     }
 }
@@ -571,7 +625,9 @@ template <class K> class Counter : public ICounter {
     }
 
 public:
-    Counter(int k, int m, cudaStream_t s) : k_(k), m_(m), stream_(s), histo_(HISTO_MAX + 1, 0) {
+    bool distinct_hint_ = false;
+    uint64_t nvalid_total_ = 0;   // valid k-mer instances pushed so far (host copy)
+    Counter(int k, int m, cudaStream_t s, bool distinct_hint) : k_(k), m_(m), stream_(s), histo_(HISTO_MAX + 1, 0), distinct_hint_(distinct_hint) {
         if (m_ > k_) m_ = k_;
         if (m_ > 10) m_ = 10;
         if (m_ < 3) throw Error(-1, "minimizer size must be >= 3");
@@ -584,7 +640,7 @@ public:
         counters_.zero(stream_);
         flags_.alloc(4);
         flags_.zero(stream_);
-        const int smem = (int)(sizeof(K) + 4) * CountCfg<K>::SLOTS + SMEM_HIST * 4;
+        const int smem = (int)(sizeof(K) + 4) * CountCfg<K>::SLOTS + SMEM_HIST * 4 + (COUNT_THREADS / 32) * CK_SLATE * 2;
         MTG_CUDA(cudaFuncSetAttribute(count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     cudaStream_t stream() const override { return stream_; }
@@ -600,7 +656,9 @@ public:
     void push_device(const uint8_t* d_bases, uint64_t n) override {
         if (!n) return;
         const uint64_t nwords = (n + 31) / 32;
+        Trace tr(stream_);
         ensure_words(words_used_ + nwords);
+        tr.mark("push: ensure_words");
         EventTimer t(stream_);
         t.start();
         int aligned = ((uintptr_t)d_bases & 15) == 0;
@@ -609,8 +667,9 @@ public:
         MTG_CUDA(cudaGetLastError());
         st_.ms_pack += t.stop();
         st_.launches++;
+        tr.mark("push: pack");
         // records: typical ~ n/8; start with n/4 + slack, retry with n on overflow
-        uint64_t cap = n / 4 + 4096;
+        uint64_t cap = n / 8 + 4096;
         unsigned long long nvalid_before = 0;
         for (int attempt = 0; attempt < 2; attempt++) {
             Batch b;
@@ -622,6 +681,7 @@ public:
                 MTG_CUDA(cudaMemcpyAsync(mh_backup_.p, mhist_.p, mhist_.bytes(), cudaMemcpyDeviceToDevice, stream_));
                 MTG_CUDA(cudaMemcpyAsync(&nvalid_before, counters_.p + 1, 8, cudaMemcpyDeviceToHost, stream_));
             }
+            tr.mark("push: batch alloc+backup");
             t.start();
             uint64_t ntiles = (nwords + SK_TILE / 32 - 1) / (SK_TILE / 32);
             int g2 = (int)std::min<uint64_t>(ntiles, (uint64_t)sm_count_ * 8);
@@ -631,11 +691,14 @@ public:
             st_.ms_extract += t.stop();
             st_.launches++;
             int ovf = 0;
-            unsigned long long nrec = 0;
+            unsigned long long nrec = 0, nv_now = 0;
+            MTG_CUDA(cudaMemcpyAsync(&nv_now, counters_.p + 1, 8, cudaMemcpyDeviceToHost, stream_));
             MTG_CUDA(cudaMemcpyAsync(&ovf, flags_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
             MTG_CUDA(cudaMemcpyAsync(&nrec, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
             MTG_CUDA(cudaStreamSynchronize(stream_));
+            tr.mark("push: superkmer");
             if (!ovf) {
+                nvalid_total_ = nv_now;
                 b.nrec = nrec;
                 st_.nb_records += nrec;
                 batches_.push_back(std::move(b));
@@ -654,34 +717,33 @@ public:
 
     void finish(int abundance_min, int64_t abundance_max) override {
         const int S = CountCfg<K>::SLOTS;
-        const uint32_t group_target = S * 7 / 16, group_cap = S * 5 / 8;
+        // instances per group: the table holds distinct k-mers, so at sequencing coverage a group may carry about as many
+        // instances as there are slots; `distinct_hint` (reference counting: every k-mer distinct) halves that
+        const uint32_t group_target = distinct_hint_ ? S / 2 : S;
         EventTimer t(stream_);
+        Trace tr(stream_);
         // ---- grouping of minimizer bins into work items, entirely on the device (no host round trip)
         t.start();
         const uint32_t NM = (uint32_t)mhist_.n;
         const uint32_t ntiles = (NM + GP_TILE - 1) / GP_TILE;
         const uint64_t pos_upper = words_used_ * 32;                       // upper bound of the k-mer instances
         const uint32_t max_groups = (uint32_t)(pos_upper / group_target + 2);
-        const uint64_t max_items = (uint64_t)max_groups + pos_upper / (group_cap / 2) + 2;
         uint64_t total_rec = 0;
         for (auto& b : batches_) total_rec += b.nrec;
-        DevBuf<unsigned long long> tile_off(ntiles + 1), grp_nrec(max_groups + 1), grp_off(max_groups + 1), item_off(max_groups + 1), gstats(4);
+        DevBuf<unsigned long long> tile_off(ntiles + 1), grp_off(max_groups + 1), gstats(4);
         DevBuf<uint32_t> d_group_of(NM);
         DevBuf<unsigned int> d_gcur(max_groups + 1);
-        DevBuf<WorkItem> d_items(max_items);
         DevBuf<uint64_t> grouped(std::max<uint64_t>(total_rec, 1));
-        grp_nrec.zero(stream_); item_off.zero(stream_); gstats.zero(stream_); d_gcur.zero(stream_);
+        grp_off.zero(stream_); gstats.zero(stream_); d_gcur.zero(stream_);
+        tr.mark("finish: allocs");
         group_tile_sum_kernel<<<ntiles, GP_THREADS, 0, stream_>>>(mhist_.p, NM, tile_off.p);
         scan_one_cta_kernel<<<1, 1024, 0, stream_>>>(tile_off.p, ntiles, nullptr);
-        group_assign_kernel<<<ntiles, GP_THREADS, 0, stream_>>>(mhist_.p, NM, tile_off.p, group_target, d_group_of.p, grp_nrec.p, item_off.p);
-        group_passes_kernel<<<(max_groups + 255) / 256, 256, 0, stream_>>>(grp_nrec.p, item_off.p, max_groups, group_cap, gstats.p);
-        MTG_CUDA(cudaMemcpyAsync(grp_off.p, grp_nrec.p, (size_t)(max_groups + 1) * 8, cudaMemcpyDeviceToDevice, stream_));
-        scan_one_cta_kernel<<<1, 1024, 0, stream_>>>(grp_off.p, max_groups + 1, nullptr);
-        scan_one_cta_kernel<<<1, 1024, 0, stream_>>>(item_off.p, max_groups + 1, gstats.p + 3);
-        group_items_kernel<<<(max_groups + 255) / 256, 256, 0, stream_>>>(grp_nrec.p, grp_off.p, item_off.p, max_groups, d_items.p);
+        group_assign_kernel<<<ntiles, GP_THREADS, 0, stream_>>>(mhist_.p, NM, tile_off.p, group_target, d_group_of.p, grp_off.p);
+        scan_one_cta_kernel<<<1, 1024, 0, stream_>>>(grp_off.p, max_groups + 1, nullptr);  // records per group -> offsets
         MTG_CUDA(cudaGetLastError());
-        st_.launches += 7;
+        st_.launches += 4;
         st_.ms_group += t.stop();
+        tr.mark("finish: grouping");
         // ---- scatter records into group lists
         t.start();
         for (auto& b : batches_) {
@@ -694,41 +756,50 @@ public:
         st_.ms_scatter += t.stop();
         for (auto& b : batches_) b.recs.release();
         batches_.clear();
-        // ---- count
+        tr.mark("finish: scatter");
+        // ---- count. Candidates (abundance >= the smallest threshold that can apply) go to a buffer sized for typical
+        // sequencing data; the kernel keeps counting past the end, so an overflow tells the exact size for the one retry.
         const bool is_auto = abundance_min < 0;
         uint32_t emit_min = is_auto ? 3u : (uint32_t)std::max(abundance_min, 1);
-        uint64_t cand_cap = pos_upper / emit_min + 1024;
-        DevBuf<K> cand_keys(cand_cap);
-        DevBuf<uint32_t> cand_cnt(cand_cap);
+        uint64_t cand_cap = std::min<uint64_t>(pos_upper / emit_min, nvalid_total_ / (4ull * emit_min) + (1u << 20)) + 1024;
+        DevBuf<K> cand_keys;
+        DevBuf<uint32_t> cand_cnt;
         DevBuf<unsigned long long> d_histo(HISTO_MAX + 1);
         DevBuf<unsigned int> d_item_counter(1);
-        d_histo.zero(stream_);
-        d_item_counter.zero(stream_);
-        MTG_CUDA(cudaMemsetAsync(counters_.p + 2, 0, 16, stream_));
-        MTG_CUDA(cudaMemsetAsync(flags_.p + 1, 0, sizeof(int), stream_));
-        t.start();
-        if (total_rec) {
-            const int smem = (int)(sizeof(K) + 4) * S + SMEM_HIST * 4;
-            count_kernel<K><<<sm_count_ * 2, COUNT_THREADS, smem, stream_>>>(packed_.p, grouped.p, d_items.p, gstats.p + 3, d_item_counter.p, k_,
-                                                                            emit_min, d_histo.p, cand_keys.p, cand_cnt.p, counters_.p + 2, cand_cap,
-                                                                            flags_.p + 1);
-            MTG_CUDA(cudaGetLastError());
-            st_.launches++;
-        }
-        st_.ms_count += t.stop();
-        unsigned long long gs[4] = {0, 0, 0, 0}, nvalid = 0;
-        MTG_CUDA(cudaMemcpyAsync(gs, gstats.p, 32, cudaMemcpyDeviceToHost, stream_));
-        MTG_CUDA(cudaMemcpyAsync(&nvalid, counters_.p + 1, 8, cudaMemcpyDeviceToHost, stream_));
+        unsigned long long gs[4] = {0, 0, 0, 0}, nvalid = 0, ncand = 0;
         int err = 0;
-        unsigned long long ncand = 0;
-        MTG_CUDA(cudaMemcpyAsync(&err, flags_.p + 1, sizeof(int), cudaMemcpyDeviceToHost, stream_));
-        MTG_CUDA(cudaMemcpyAsync(&ncand, counters_.p + 2, 8, cudaMemcpyDeviceToHost, stream_));
-        MTG_CUDA(cudaMemcpyAsync(histo_.data(), d_histo.p, (HISTO_MAX + 1) * 8, cudaMemcpyDeviceToHost, stream_));
-        MTG_CUDA(cudaStreamSynchronize(stream_));
+        for (int attempt = 0; attempt < 2; attempt++) {
+            cand_keys.alloc(cand_cap);
+            cand_cnt.alloc(cand_cap);
+            d_histo.zero(stream_);
+            d_item_counter.zero(stream_);
+            gstats.zero(stream_);
+            MTG_CUDA(cudaMemsetAsync(counters_.p + 2, 0, 16, stream_));
+            MTG_CUDA(cudaMemsetAsync(flags_.p + 1, 0, sizeof(int), stream_));
+            tr.mark("finish: count allocs");
+            t.start();
+            if (total_rec) {
+                const int smem = (int)(sizeof(K) + 4) * S + SMEM_HIST * 4 + (COUNT_THREADS / 32) * CK_SLATE * 2;
+                count_kernel<K><<<sm_count_ * 2, COUNT_THREADS, smem, stream_>>>(packed_.p, grouped.p, grp_off.p, max_groups, d_item_counter.p, k_,
+                                                                                emit_min, d_histo.p, cand_keys.p, cand_cnt.p, counters_.p + 2,
+                                                                                cand_cap, gstats.p, flags_.p + 1);
+                MTG_CUDA(cudaGetLastError());
+                st_.launches++;
+            }
+            st_.ms_count += t.stop();
+            tr.mark("finish: count kernel");
+            MTG_CUDA(cudaMemcpyAsync(gs, gstats.p, 32, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaMemcpyAsync(&nvalid, counters_.p + 1, 8, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaMemcpyAsync(&err, flags_.p + 1, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaMemcpyAsync(&ncand, counters_.p + 2, 8, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaMemcpyAsync(histo_.data(), d_histo.p, (HISTO_MAX + 1) * 8, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaStreamSynchronize(stream_));
+            if (err == 2 && attempt == 0) { cand_cap = ncand + 1024; st_.nb_count_retries++; continue; }
+            break;
+        }
         st_.nb_valid_kmers = nvalid;
         st_.nb_groups = gs[0]; st_.nb_multipass_groups = gs[1]; st_.nb_items = gs[3];
-        if (gs[2]) throw Error(-4, "minimizer bin too large for the multi-pass counter");
-        if (err == 1) throw Error(-5, "shared-memory count table overflow");
+        if (err == 1) throw Error(-5, "shared-memory count table overflow (hash classes exhausted)");
         if (err == 2) throw Error(-5, "candidate buffer overflow");
         st_.nb_candidates = ncand;
         // ---- threshold (auto: CountProcessorCutoff::endPass, min_auto_threshold = 3) and final filter
@@ -752,6 +823,7 @@ public:
         MTG_CUDA(cudaStreamSynchronize(stream_));
         nb_solid_ = ns;
         st_.nb_solid = ns;
+        tr.mark("finish: threshold+filter");
         // the packed reads are no longer needed
         packed_.release(); inv_.release(); staging_.release();
         words_used_ = words_cap_ = 0;
@@ -771,11 +843,11 @@ public:
     }
 };
 
-ICounter* make_counter(int k, int minimizer_size, cudaStream_t stream, int key_bits) {
+ICounter* make_counter(int k, int minimizer_size, cudaStream_t stream, int key_bits, bool distinct_hint) {
     if (k < 4 || k > 63) throw Error(-1, "kmer size must be in [5,63]");
-    if (key_bits == 128) return new Counter<u128>(k, minimizer_size, stream);
-    if (k <= 31) return new Counter<uint64_t>(k, minimizer_size, stream);
-    return new Counter<u128>(k, minimizer_size, stream);
+    if (key_bits == 128) return new Counter<u128>(k, minimizer_size, stream, distinct_hint);
+    if (k <= 31) return new Counter<uint64_t>(k, minimizer_size, stream, distinct_hint);
+    return new Counter<u128>(k, minimizer_size, stream, distinct_hint);
 }
 
 }  // namespace mtg

@@ -14,7 +14,7 @@ struct CountStats {
     uint64_t nb_bases = 0;          // bases pushed (including separators / padding)
     uint64_t nb_valid_kmers = 0;    // valid k-mer instances counted
     uint64_t nb_records = 0;        // super-k-mer records
-    uint64_t nb_groups = 0, nb_items = 0, nb_multipass_groups = 0;
+    uint64_t nb_groups = 0, nb_items = 0, nb_multipass_groups = 0, nb_count_retries = 0;
     uint64_t nb_candidates = 0;     // distinct k-mers with abundance >= emit threshold
     uint64_t nb_solid = 0;
     int cutoff_auto = -1;           // -1 when abundance_min was explicit
@@ -47,6 +47,7 @@ void launch_pack(const uint8_t* d_in, uint64_t n, uint64_t* d_packed, uint32_t* 
 
 // k<=31 -> 64-bit keys, 32<=k<=63 -> 128-bit keys
 // key_bits: 0 = by k, 64 or 128 to force (the reference (k-1)-mer count uses the key type of k)
-ICounter* make_counter(int k, int minimizer_size, cudaStream_t stream, int key_bits = 0);
+// distinct_hint: most k-mers occur once (counting the reference itself) -> smaller groups per shared-memory table
+ICounter* make_counter(int k, int minimizer_size, cudaStream_t stream, int key_bits = 0, bool distinct_hint = false);
 
 }  // namespace mtg

@@ -400,6 +400,7 @@ public:
     void build(const void* d_solid, uint64_t N) override {
         const K* keys = (const K*)d_solid;
         EvTimer t(stream_);
+        Trace tr(stream_);
         st_.nb_solid = N;
         // ---- exact table, load factor ~0.55, 128-byte buckets
         t.start();
@@ -416,6 +417,7 @@ public:
         st_.ms_table = t.stop();
         check_err("exact table build");
         st_.nbuckets = nbuckets_;
+        tr.mark("graph: table");
         // ---- main Bloom (BloomAlgorithm.cpp:161-165: u64 * float multiply)
         t.start();
         const float NBITS = bits_per_kmer(k_);
@@ -431,6 +433,7 @@ public:
         }
         st_.ms_bloom = t.stop();
         st_.bloom_tai = bloom_.tai;
+        tr.mark("graph: bloom");
         // ---- critical false positives (set de-duplication; retried with a larger set if it fills up)
         t.start();
         uint64_t ncrit = 0;
@@ -457,6 +460,7 @@ public:
         }
         st_.ms_critical = t.stop();
         st_.nb_critical = ncrit;
+        tr.mark("graph: critical");
         // ---- cascading Blooms (createCFP, DebloomAlgorithm.cpp:462-622); BLOOM_CACHE kind is forced there (:497)
         t.start();
         cascading_ = ncrit != 0;  // no critical FP -> DEBLOOM_ORIGINAL with an empty set (:478-479)
@@ -498,7 +502,8 @@ public:
             }
         }
         st_.ms_cascade = t.stop();
-        st_.b2_tai = b2_.tai; st_.b3_tai = b3_.tai; st_.b4_tai = b4_.tai; st_.ncfp = ncfp_;
+        st_.b2_tai = b2_.tai;
+        tr.mark("graph: cascade"); st_.b3_tai = b3_.tai; st_.b4_tai = b4_.tai; st_.ncfp = ncfp_;
         // ---- BooPHF levels (sizes: mphf::setup, BooPHF.h:1015-1041, double arithmetic on the host)
         t.start();
         mphf_built_ = false;
@@ -550,6 +555,7 @@ public:
             mphf_built_ = true;
         }
         st_.ms_mphf = t.stop();
+        tr.mark("graph: mphf");
     }
 
     void set_ref_repeats(const void* d_keys, uint64_t n) override {

@@ -99,6 +99,40 @@ def test_count_heavy_minimizer_multipass():
     f.close()
 
 
+def test_count_candidate_buffer_retry():
+    """Every k-mer occurs exactly 3 times: far more candidates than the typical-coverage buffer -> one exact-size retry."""
+    rng = np.random.default_rng(5)
+    reads = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=300)) for _ in range(16000)]
+    stream = b"\n".join(reads * 3) + b"\n"
+    f = _finder(31)
+    f.push_reads(stream)
+    f.finish_count()
+    assert f.stats()["count.retries"] == 1
+    o = oracle_py.count_stream(stream, 31, abundance_min=-1, nthreads=4)
+    lo, hi, ab = _sorted_solid(*f.export_solid())
+    assert f.threshold == o["threshold"] and f.nb_solid == len(o["lo"])
+    assert (lo == o["lo"]).all() and (ab == o["abundance"]).all()
+    assert (f.histogram() == o["histogram"]).all()
+    f.close()
+
+
+def test_count_low_coverage_splits_hash_classes():
+    """Every k-mer distinct (1x): groups hold more distinct k-mers than a shared-memory table -> adaptive class split."""
+    rng = np.random.default_rng(6)
+    reads = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=200)) for _ in range(20000)]
+    stream = b"\n".join(reads) + b"\n"
+    for k in (31, 63):
+        f = _finder(k, ["-abundance-min", "1"])
+        f.push_reads(stream)
+        f.finish_count()
+        assert f.stats()["count.nb_multipass_groups"] >= 1
+        o = oracle_py.count_stream(stream, k, abundance_min=1, nthreads=4)
+        lo, hi, ab = _sorted_solid(*f.export_solid())
+        assert f.nb_solid == len(o["lo"])
+        assert (lo == o["lo"]).all() and (hi == o["hi"]).all() and (ab == o["abundance"]).all()
+        f.close()
+
+
 def test_count_empty_input():
     f = _finder(31)
     f.push_reads(b"ACGT\nNNNN\n")
