@@ -65,6 +65,30 @@ int mtg_count_files(mtg_ctx* ctx, const char* uri);
  * build_visitor_postsolid (Graph.cpp:428-612): Bloom, cascading cFP, BooPHF presence, + the exact table. */
 int mtg_count_finish(mtg_ctx* ctx);
 
+/* ---- multi-GPU building blocks (one context per GPU; the HOST performs the collectives between the calls, e.g. NCCL).
+ * They split Graph::create -> SortingCountAlgorithm (G/kmer/impl/SortingCountAlgorithm.cpp:600-745) along its own stages:
+ * fillPartitions (:1180-1313; here: local super-k-mer records, exchanged by minimizer owner), fillSolidKmers (:1353-1571;
+ * each GPU counts its own partition), the histogram merge before the auto cut-off (:390-403, 419-478). See DESIGN.md 6.
+ *   nwords/nrecords/nvalid: 2-bit words, super-k-mer records and valid k-mer instances this context extracted so far     */
+int mtg_count_local_info(mtg_ctx* ctx, uint64_t* nwords, uint64_t* nrecords, uint64_t* nvalid);
+/* copies the packed bases (u64/32 bases) and invalid masks (u32/32 bases) into caller buffers of capacity_words entries,
+ * padded with empty/invalid words, ready for an all-gather */
+int mtg_count_copy_packed(mtg_ctx* ctx, void* d_packed_out, void* d_inv_out, uint64_t capacity_words);
+/* writes the nrecords local records to d_out grouped by owner rank (minimizer bin % nparts), positions rebased by
+ * pos_offset_bases (= offset of this rank's words in the gathered array * 32); counts[nparts] (host) = records per owner */
+int mtg_count_partition_records(mtg_ctx* ctx, int nparts, uint64_t pos_offset_bases, void* d_out, uint64_t* counts);
+/* replaces the context's own packed reads / records by the gathered arrays and the received records (borrowed until
+ * mtg_count_run returns) */
+int mtg_count_import(mtg_ctx* ctx, const void* d_packed, const void* d_inv, uint64_t nwords, const void* d_records, uint64_t nrecords);
+/* group + count the records held: local abundance histogram (mtg_get_histogram) and candidates */
+int mtg_count_run(mtg_ctx* ctx);
+/* threshold from the merged histogram (NULL = local) + solidity filter -> this rank's share of the solid set */
+int mtg_count_filter(mtg_ctx* ctx, const uint64_t* histogram10001);
+/* device-to-device copy of the local solid share: keys (u64, or {lo,hi} u64 pairs when kmer_size > 31) and u32 abundances */
+int mtg_solid_copy(mtg_ctx* ctx, void* d_keys_out, void* d_counts_out, uint64_t capacity);
+/* build_visitor_postsolid (Graph.cpp:428-612) from a device array of solid keys (e.g. the all-gathered set) */
+int mtg_graph_build_device(mtg_ctx* ctx, const void* d_keys, uint64_t n);
+
 /* info lines of Finder::resumeParameters (src/Finder.cpp:444-467) */
 int32_t mtg_get_threshold(mtg_ctx* ctx);     /* "abundance_min (used)"           */
 int32_t mtg_get_cutoff_auto(mtg_ctx* ctx);   /* "abundance_min (auto inferred)", -1 when not auto */
@@ -97,6 +121,9 @@ int mtg_ref_repeat_batch(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, u
  * Arrays hold len-k+1 entries. counters4: valid positions, in-graph positions, table probes, Bloom-emulation calls. */
 int mtg_sequence_features(mtg_ctx* ctx, const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint64_t* counters4);
 int mtg_sequence_features_device(mtg_ctx* ctx, const void* d_seq, uint64_t len, void* d_feat, void* d_rep, uint64_t* counters4);
+/* same + d_interest: u32 bitmap (bit p&31 of word p>>5) of the positions the gap machine must walk one by one. A caller may
+ * pass any sub-range [a, b+k-1) of a sequence (a multiple of 32): positions only need a (k-1)-base halo. */
+int mtg_sequence_features_device2(mtg_ctx* ctx, const void* d_seq, uint64_t len, void* d_feat, void* d_rep, void* d_interest, uint64_t* counters4);
 
 /* One reference sequence through FindBreakpoints::operator() (src/FindBreakpoints.hpp:390-455). Records are appended to
  * the context's two output buffers with the reference's exact formats (writeBreakpoint/writeVcfVariant/writeIndel,
@@ -105,6 +132,10 @@ int mtg_scan_reference(mtg_ctx* ctx, const char* name, const char* seq, uint64_t
 /* same with the sequence also resident in HBM (d_seq): no host->device copy; `seq` (host text) is still needed by the
  * writers, which print raw reference text (src/FindInsertion.hpp:100-133, src/FindDeletion.hpp:62-171). */
 int mtg_scan_reference_device(mtg_ctx* ctx, const char* name, const char* seq, const void* d_seq, uint64_t len);
+/* Event replay of one sequence over caller-provided host feature arrays (e.g. gathered from several GPUs); observer probes
+ * are answered by this context's GPU. interest may be NULL (walk every position). */
+int mtg_replay_sequence(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len, const uint8_t* feat, const uint8_t* rep,
+                        const uint32_t* interest);
 /* Output accessors: pointers stay valid until the next scan/reset call on this context. */
 const char* mtg_breakpoints_text(mtg_ctx* ctx, uint64_t* nbytes);
 const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes);

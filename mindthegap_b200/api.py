@@ -38,7 +38,8 @@ EXPORTS = [
     "mtg_get_histogram", "mtg_get_stats", "mtg_stat_name", "mtg_export_solid", "mtg_load_solid", "mtg_set_reference",
     "mtg_contains_batch", "mtg_degree_batch", "mtg_ref_repeat_batch", "mtg_sequence_features", "mtg_sequence_features_device",
     "mtg_scan_reference", "mtg_scan_reference_device", "mtg_set_reference_device", "mtg_breakpoints_text", "mtg_vcf_text", "mtg_reset_outputs", "mtg_get_find_counters", "mtg_copy_bits",
-    "mtg_bench_random_gather",
+    "mtg_bench_random_gather", "mtg_count_local_info", "mtg_count_copy_packed", "mtg_count_partition_records", "mtg_count_import",
+    "mtg_count_run", "mtg_count_filter", "mtg_solid_copy", "mtg_graph_build_device", "mtg_sequence_features_device2", "mtg_replay_sequence",
 ]
 
 _lib = None
@@ -96,6 +97,16 @@ def load_library():
     L.mtg_get_find_counters.argtypes = [vp, u64p]
     L.mtg_copy_bits.restype = C.c_int64
     L.mtg_copy_bits.argtypes = [vp, C.c_int, vp, C.c_uint64]
+    L.mtg_count_local_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.mtg_count_copy_packed.argtypes = [vp, vp, vp, C.c_uint64]
+    L.mtg_count_partition_records.argtypes = [vp, C.c_int, C.c_uint64, vp, u64p]
+    L.mtg_count_import.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint64]
+    L.mtg_count_run.argtypes = [vp]
+    L.mtg_count_filter.argtypes = [vp, vp]
+    L.mtg_solid_copy.argtypes = [vp, vp, vp, C.c_uint64]
+    L.mtg_graph_build_device.argtypes = [vp, vp, C.c_uint64]
+    L.mtg_sequence_features_device2.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, u64p]
+    L.mtg_replay_sequence.argtypes = [vp, C.c_char_p, vp, C.c_uint64, u8p, u8p, vp]
     L.mtg_bench_random_gather.restype = C.c_double
     L.mtg_bench_random_gather.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int]
     _lib = L
@@ -301,6 +312,63 @@ class Finder:
         buf = np.zeros(max(n, 1), dtype=np.uint8)
         self.L.mtg_copy_bits(self.ctx, which, _ptr(buf), n)
         return buf[:n]
+
+    # ---- multi-GPU building blocks (device buffers are torch tensors owned by the caller; see dist.py)
+    def count_local_info(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.L.mtg_count_local_info(self.ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def count_copy_packed(self, packed_t, inv_t):
+        assert packed_t.numel() == inv_t.numel()
+        self._check(self.L.mtg_count_copy_packed(self.ctx, C.c_void_p(packed_t.data_ptr()), C.c_void_p(inv_t.data_ptr()), packed_t.numel()))
+
+    def count_partition_records(self, nparts, pos_offset_bases, out_t):
+        counts = np.zeros(nparts, dtype=np.uint64)
+        self._check(self.L.mtg_count_partition_records(self.ctx, nparts, pos_offset_bases, C.c_void_p(out_t.data_ptr()), counts))
+        return [int(x) for x in counts]
+
+    def count_import(self, packed_t, inv_t, records_t):
+        self._check(self.L.mtg_count_import(self.ctx, C.c_void_p(packed_t.data_ptr()), C.c_void_p(inv_t.data_ptr()), packed_t.numel(),
+                                            C.c_void_p(records_t.data_ptr()), records_t.numel()))
+
+    def count_run(self):
+        self._check(self.L.mtg_count_run(self.ctx))
+
+    def count_filter(self, histogram=None):
+        h = None if histogram is None else np.ascontiguousarray(histogram, dtype=np.uint64)
+        self._check(self.L.mtg_count_filter(self.ctx, _ptr(h)))
+
+    @property
+    def key_words(self):
+        """64-bit words per k-mer key: 1 (k <= 31) or 2 ({lo, hi})."""
+        return 1 if self.params.kmer_size <= 31 else 2
+
+    def solid_copy(self, keys_t, counts_t):
+        self._check(self.L.mtg_solid_copy(self.ctx, C.c_void_p(keys_t.data_ptr()), C.c_void_p(counts_t.data_ptr()) if counts_t is not None else None,
+                                          keys_t.numel() // self.key_words))
+
+    def graph_build_device(self, keys_t, n):
+        self._check(self.L.mtg_graph_build_device(self.ctx, C.c_void_p(keys_t.data_ptr()), n))
+
+    def features_segment(self, seq_t):
+        """seq_t: uint8 device tensor holding bases [a, b+k-1); returns (feat, rep, interest) device tensors for b-a positions."""
+        import torch
+        n = max(0, seq_t.numel() - self.params.kmer_size + 1)
+        feat = torch.empty(max(n, 1), dtype=torch.uint8, device=seq_t.device)
+        rep = torch.empty(max(n, 1), dtype=torch.uint8, device=seq_t.device)
+        interest = torch.zeros((n + 31) // 32 + 1, dtype=torch.int32, device=seq_t.device)
+        c4 = np.zeros(4, dtype=np.uint64)
+        if n:
+            self._check(self.L.mtg_sequence_features_device2(self.ctx, C.c_void_p(seq_t.data_ptr()), seq_t.numel(), C.c_void_p(feat.data_ptr()),
+                                                             C.c_void_p(rep.data_ptr()), C.c_void_p(interest.data_ptr()), c4))
+        return feat[:n], rep[:n], interest[:(n + 31) // 32]
+
+    def replay_sequence(self, name, seq, feat, rep, interest=None):
+        a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        feat = np.ascontiguousarray(feat, dtype=np.uint8); rep = np.ascontiguousarray(rep, dtype=np.uint8)
+        it = None if interest is None else np.ascontiguousarray(interest).view(np.uint32)
+        self._check(self.L.mtg_replay_sequence(self.ctx, name.encode(), _ptr(a), a.size, feat, rep, _ptr(it)))
 
     # ---- whole `find` on in-memory inputs (what bench.py and the parity tests drive)
     def find(self, read_stream, ref_records):

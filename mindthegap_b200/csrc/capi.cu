@@ -128,7 +128,7 @@ struct mtg_ctx {
     CountStats count_stats;
     std::vector<uint64_t> histogram;
     int threshold = 0, cutoff_auto = -1;
-    uint64_t nb_solid = 0;
+    uint64_t nb_solid = 0, nb_solid_global = 0;
     bool graph_ready = false;
     // solid set kept on the device for export
     std::unique_ptr<ICounter> solid_owner;
@@ -299,9 +299,73 @@ int mtg_count_finish(mtg_ctx* ctx) {
     MTG_CATCH
 }
 
+// ---- multi-GPU building blocks
+int mtg_count_local_info(mtg_ctx* ctx, uint64_t* nwords, uint64_t* nrecords, uint64_t* nvalid) {
+    MTG_TRY(ctx) reads_counter(ctx)->local_info(nwords, nrecords, nvalid); MTG_CATCH
+}
+int mtg_count_copy_packed(mtg_ctx* ctx, void* d_packed_out, void* d_inv_out, uint64_t capacity_words) {
+    MTG_TRY(ctx) reads_counter(ctx)->copy_packed((uint64_t*)d_packed_out, (uint32_t*)d_inv_out, capacity_words); MTG_CATCH
+}
+int mtg_count_partition_records(mtg_ctx* ctx, int nparts, uint64_t pos_offset_bases, void* d_out, uint64_t* counts) {
+    MTG_TRY(ctx) reads_counter(ctx)->partition_records(nparts, pos_offset_bases, (uint64_t*)d_out, counts); MTG_CATCH
+}
+int mtg_count_import(mtg_ctx* ctx, const void* d_packed, const void* d_inv, uint64_t nwords, const void* d_records, uint64_t nrecords) {
+    MTG_TRY(ctx) reads_counter(ctx)->import_external((const uint64_t*)d_packed, (const uint32_t*)d_inv, nwords, (const uint64_t*)d_records, nrecords); MTG_CATCH
+}
+int mtg_count_run(mtg_ctx* ctx) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_finish);
+    ICounter* c = reads_counter(ctx);
+    c->run(ctx->p.abundance_min);
+    memcpy(ctx->histogram.data(), c->histogram(), (HISTO_MAX + 1) * 8);
+    MTG_CATCH
+}
+int mtg_count_filter(mtg_ctx* ctx, const uint64_t* histogram10001) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_finish);
+    ICounter* c = reads_counter(ctx);
+    c->filter(ctx->p.abundance_min, ctx->p.abundance_max, histogram10001);
+    ctx->count_stats = c->stats();
+    memcpy(ctx->histogram.data(), c->histogram(), (HISTO_MAX + 1) * 8);
+    ctx->threshold = c->stats().threshold;
+    ctx->cutoff_auto = c->stats().cutoff_auto;
+    ctx->nb_solid = c->nb_solid();          // local share until mtg_graph_build_device installs the global set
+    ctx->solid_owner = std::move(ctx->counter);
+    ctx->loaded_lo.clear(); ctx->loaded_hi.clear();
+    MTG_CATCH
+}
+int mtg_solid_copy(mtg_ctx* ctx, void* d_keys_out, void* d_counts_out, uint64_t capacity) {
+    MTG_TRY(ctx)
+    if (!ctx->solid_owner) throw Error(-1, "no counted solid set on this context");
+    const uint64_t n = ctx->solid_owner->nb_solid();
+    if (capacity < n) throw Error(-1, "mtg_solid_copy: capacity too small");
+    const size_t ksz = ctx->p.kmer_size <= 31 ? 8 : 16;
+    if (n && d_keys_out) MTG_CUDA(cudaMemcpyAsync(d_keys_out, ctx->solid_owner->solid_keys_device(), n * ksz, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (n && d_counts_out) MTG_CUDA(cudaMemcpyAsync(d_counts_out, ctx->solid_owner->solid_abundance_device(), n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    MTG_CUDA(cudaStreamSynchronize(ctx->stream));
+    MTG_CATCH
+}
+int mtg_graph_build_device(mtg_ctx* ctx, const void* d_keys, uint64_t n) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_finish);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, ctx->stream);
+    ctx->graph->build(d_keys, n);
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    ctx->ms_graph_build = ms;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    ctx->graph_ready = true;
+    ctx->nb_solid_global = n;
+    MTG_CATCH
+}
+
 int32_t mtg_get_threshold(mtg_ctx* ctx) { return ctx ? ctx->threshold : -1; }
 int32_t mtg_get_cutoff_auto(mtg_ctx* ctx) { return ctx ? ctx->cutoff_auto : -1; }
-uint64_t mtg_get_nb_solid(mtg_ctx* ctx) { return ctx ? ctx->nb_solid : 0; }
+uint64_t mtg_get_nb_solid(mtg_ctx* ctx) { return ctx ? (ctx->nb_solid_global ? ctx->nb_solid_global : ctx->nb_solid) : 0; }
 int mtg_get_histogram(mtg_ctx* ctx, uint64_t* out) { MTG_TRY(ctx) memcpy(out, ctx->histogram.data(), (HISTO_MAX + 1) * 8); MTG_CATCH }
 
 static const char* STAT_NAMES[] = {
@@ -345,6 +409,7 @@ int mtg_get_stats(mtg_ctx* ctx, double* out, int cap) {
 
 int mtg_export_solid(mtg_ctx* ctx, uint64_t* lo, uint64_t* hi, uint32_t* abundance, uint64_t capacity) {
     MTG_TRY(ctx)
+    if (ctx->solid_owner && ctx->nb_solid_global) ctx->nb_solid = ctx->solid_owner->nb_solid();  // multi-GPU: the local share
     if (capacity < ctx->nb_solid) throw Error(-1, "export buffer too small");
     MTG_CUDA(cudaSetDevice(ctx->p.device));
     if (ctx->solid_owner) ctx->solid_owner->export_solid(lo, hi, abundance);
@@ -396,6 +461,16 @@ int mtg_ref_repeat_batch(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, u
 int mtg_sequence_features(mtg_ctx* ctx, const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint64_t* counters4) {
     MTG_TRY(ctx) ctx->graph->features_host(seq, len, feat, rep, nullptr, counters4); MTG_CATCH
 }
+int mtg_sequence_features_device2(mtg_ctx* ctx, const void* d_seq, uint64_t len, void* d_feat, void* d_rep, void* d_interest, uint64_t* counters4) {
+    MTG_TRY(ctx)
+    uint64_t c4[4];
+    ctx->graph->features_device((const uint8_t*)d_seq, len, (uint8_t*)d_feat, (uint8_t*)d_rep, (uint32_t*)d_interest, c4);
+    MTG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->ms_features += ctx->graph->last_features_ms();
+    ctx->scan_valid += c4[0]; ctx->scan_in_graph += c4[1]; ctx->scan_table_probes += c4[2]; ctx->scan_fallback += c4[3];
+    if (counters4) memcpy(counters4, c4, 32);
+    MTG_CATCH
+}
 int mtg_sequence_features_device(mtg_ctx* ctx, const void* d_seq, uint64_t len, void* d_feat, void* d_rep, uint64_t* counters4) {
     MTG_TRY(ctx)
     MTG_CUDA(cudaSetDevice(ctx->p.device));
@@ -429,6 +504,24 @@ static void scan_reference_impl(mtg_ctx* ctx, const char* name, const char* seq,
     clock_gettime(CLOCK_MONOTONIC, &t1);
     ctx->ms_replay += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
     tr.mark("scan: replay");
+}
+static void replay_impl(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len, const uint8_t* feat, const uint8_t* rep, const uint32_t* interest) {
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (ctx->rp64) ctx->rp64->scan(name ? name : "", seq, len, feat, rep, interest);
+    else ctx->rp128->scan(name ? name : "", seq, len, feat, rep, interest);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    ctx->ms_replay += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+}
+int mtg_replay_sequence(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len, const uint8_t* feat, const uint8_t* rep,
+                        const uint32_t* interest) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_scan);
+    if (len < (uint64_t)ctx->p.kmer_size) return 0;
+    if (!feat || !rep) throw Error(-1, "null feature arrays");
+    ctx->scan_positions += len - ctx->p.kmer_size + 1;
+    replay_impl(ctx, name, seq, len, feat, rep, interest);
+    MTG_CATCH
 }
 int mtg_scan_reference(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len) {
     MTG_TRY(ctx) scan_reference_impl(ctx, name, seq, nullptr, len); MTG_CATCH

@@ -573,6 +573,44 @@ __global__ void __launch_bounds__(256) filter_kernel(const K* __restrict__ cand_
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// multi-GPU building blocks: records are owned by rank (minimizer bin % nparts)
+// ------------------------------------------------------------------------------------------------------------
+static const int MAX_PARTS = 64;
+__global__ void __launch_bounds__(256) owner_count_kernel(const uint64_t* __restrict__ records, uint64_t nrec, int nparts,
+                                                          unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int s_cnt[MAX_PARTS];
+    if (threadIdx.x < MAX_PARTS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&s_cnt[(uint32_t)(records[i] & ((1u << REC_LEN_SHIFT) - 1)) % nparts], 1u);
+    __syncthreads();
+    if (threadIdx.x < nparts && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+// scatter into per-owner segments (cursor[d] starts at the segment offset), positions rebased into the gathered array
+__global__ void __launch_bounds__(256) owner_scatter_kernel(const uint64_t* __restrict__ records, uint64_t nrec, int nparts, uint64_t pos_offset,
+                                                            unsigned long long* __restrict__ cursor, uint64_t* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = records[i];
+        const uint32_t d = (uint32_t)(r & ((1u << REC_LEN_SHIFT) - 1)) % nparts;
+        const unsigned long long o = atomicAdd(&cursor[d], 1ull);
+        out[o] = r + (pos_offset << REC_POS_SHIFT);
+    }
+}
+// per-bin histogram (records << 36 | instances) and instance total of an imported record list
+__global__ void __launch_bounds__(256) mhist_from_records_kernel(const uint64_t* __restrict__ records, uint64_t nrec,
+                                                                 unsigned long long* __restrict__ mhist, unsigned long long* __restrict__ nvalid) {
+    unsigned long long acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = records[i];
+        const uint32_t len = (uint32_t)((r >> REC_LEN_SHIFT) & 63) + 1;
+        atomicAdd(&mhist[r & ((1u << REC_LEN_SHIFT) - 1)], (1ull << MH_REC_SHIFT) | len);
+        acc += len;
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(nvalid, acc);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
 struct EventTimer {
@@ -600,6 +638,12 @@ template <class K> class Counter : public ICounter {
     DevBuf<unsigned long long> mhist_, mh_backup_;
     DevBuf<unsigned long long> counters_;  // [0] nrec (per batch, reset), [1] nvalid, [2] ncand, [3] nsolid
     DevBuf<int> flags_;                    // [0] record overflow, [1] count error
+    // external (borrowed) arrays for the multi-GPU path, candidates between run() and filter()
+    const uint64_t* ext_packed_ = nullptr;
+    const uint64_t* ext_records_ = nullptr;
+    uint64_t ext_nrec_ = 0, ncand_ = 0;
+    DevBuf<K> cand_keys_;
+    DevBuf<uint32_t> cand_cnt_;
     // results
     DevBuf<K> solid_keys_;
     DevBuf<uint32_t> solid_cnt_;
@@ -716,6 +760,75 @@ public:
     }
 
     void finish(int abundance_min, int64_t abundance_max) override {
+        run(abundance_min);
+        filter(abundance_min, abundance_max, nullptr);
+    }
+
+    // ---- multi-GPU building blocks (the host does the collectives between them)
+    void local_info(uint64_t* nwords, uint64_t* nrecords, uint64_t* nvalid) const override {
+        uint64_t nr = 0;
+        for (auto& b : batches_) nr += b.nrec;
+        *nwords = words_used_; *nrecords = nr; *nvalid = nvalid_total_;
+    }
+    void copy_packed(uint64_t* d_packed_out, uint32_t* d_inv_out, uint64_t capacity_words) override {
+        if (capacity_words < words_used_) throw Error(-1, "copy_packed: capacity too small");
+        MTG_CUDA(cudaMemsetAsync(d_packed_out, 0, capacity_words * 8, stream_));
+        MTG_CUDA(cudaMemsetAsync(d_inv_out, 0xFF, capacity_words * 4, stream_));
+        if (words_used_) {
+            MTG_CUDA(cudaMemcpyAsync(d_packed_out, packed_.p, words_used_ * 8, cudaMemcpyDeviceToDevice, stream_));
+            MTG_CUDA(cudaMemcpyAsync(d_inv_out, inv_.p, words_used_ * 4, cudaMemcpyDeviceToDevice, stream_));
+        }
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+    }
+    void partition_records(int nparts, uint64_t pos_offset_bases, uint64_t* d_out, uint64_t* counts_host) override {
+        if (nparts < 1 || nparts > MAX_PARTS) throw Error(-1, "partition_records: 1..64 parts");
+        DevBuf<unsigned long long> d_counts(MAX_PARTS), d_cursor(MAX_PARTS);
+        d_counts.zero(stream_);
+        for (auto& b : batches_) {
+            if (!b.nrec) continue;
+            int grid = (int)std::min<uint64_t>((b.nrec + 255) / 256, (uint64_t)sm_count_ * 8);
+            owner_count_kernel<<<grid, 256, 0, stream_>>>(b.recs.p, b.nrec, nparts, d_counts.p);
+            st_.launches++;
+        }
+        unsigned long long cnt[MAX_PARTS], cur[MAX_PARTS];
+        MTG_CUDA(cudaMemcpyAsync(cnt, d_counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        unsigned long long off = 0;
+        for (int d = 0; d < MAX_PARTS; d++) { cur[d] = off; if (d < nparts) { counts_host[d] = cnt[d]; off += cnt[d]; } }
+        MTG_CUDA(cudaMemcpyAsync(d_cursor.p, cur, sizeof(cur), cudaMemcpyHostToDevice, stream_));
+        for (auto& b : batches_) {
+            if (!b.nrec) continue;
+            int grid = (int)std::min<uint64_t>((b.nrec + 255) / 256, (uint64_t)sm_count_ * 8);
+            owner_scatter_kernel<<<grid, 256, 0, stream_>>>(b.recs.p, b.nrec, nparts, pos_offset_bases, d_cursor.p, d_out);
+            st_.launches++;
+        }
+        MTG_CUDA(cudaGetLastError());
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+    }
+    void import_external(const uint64_t* d_packed, const uint32_t* d_inv, uint64_t nwords, const uint64_t* d_records, uint64_t nrecords) override {
+        for (auto& b : batches_) b.recs.release();
+        batches_.clear();
+        packed_.release(); inv_.release(); staging_.release();
+        words_cap_ = 0;
+        ext_packed_ = d_packed; ext_records_ = d_records; ext_nrec_ = nrecords;
+        words_used_ = nwords;
+        (void)d_inv;  // validity was settled when the records were made; counting only needs the bases
+        mhist_.zero(stream_);
+        MTG_CUDA(cudaMemsetAsync(counters_.p + 1, 0, 8, stream_));
+        if (nrecords) {
+            int grid = (int)std::min<uint64_t>((nrecords + 255) / 256, (uint64_t)sm_count_ * 8);
+            mhist_from_records_kernel<<<grid, 256, 0, stream_>>>(d_records, nrecords, mhist_.p, counters_.p + 1);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        unsigned long long nv = 0;
+        MTG_CUDA(cudaMemcpyAsync(&nv, counters_.p + 1, 8, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        nvalid_total_ = nv;
+        st_.nb_records = nrecords;
+    }
+
+    void run(int abundance_min) override {
         const int S = CountCfg<K>::SLOTS;
         // instances per group: the table holds distinct k-mers, so at sequencing coverage a group may carry about as many
         // instances as there are slots; `distinct_hint` (reference counting: every k-mer distinct) halves that
@@ -726,10 +839,12 @@ public:
         t.start();
         const uint32_t NM = (uint32_t)mhist_.n;
         const uint32_t ntiles = (NM + GP_TILE - 1) / GP_TILE;
-        const uint64_t pos_upper = words_used_ * 32;                       // upper bound of the k-mer instances
-        const uint32_t max_groups = (uint32_t)(pos_upper / group_target + 2);
-        uint64_t total_rec = 0;
+        uint64_t total_rec = ext_records_ ? ext_nrec_ : 0;
         for (auto& b : batches_) total_rec += b.nrec;
+        // upper bound of the k-mer instances
+        const uint64_t pos_upper = ext_records_ ? std::min<uint64_t>(words_used_ * 32, std::max<uint64_t>(nvalid_total_, 1)) : words_used_ * 32;
+        const uint32_t max_groups = (uint32_t)(pos_upper / group_target + 2);
+        const uint64_t* packed_ptr = ext_packed_ ? ext_packed_ : packed_.p;
         DevBuf<unsigned long long> tile_off(ntiles + 1), grp_off(max_groups + 1), gstats(4);
         DevBuf<uint32_t> d_group_of(NM);
         DevBuf<unsigned int> d_gcur(max_groups + 1);
@@ -753,6 +868,12 @@ public:
             MTG_CUDA(cudaGetLastError());
             st_.launches++;
         }
+        if (ext_records_ && ext_nrec_) {
+            int grid = (int)std::min<uint64_t>((ext_nrec_ + 255) / 256, (uint64_t)sm_count_ * 16);
+            scatter_kernel<<<grid, 256, 0, stream_>>>(ext_records_, ext_nrec_, d_group_of.p, (const uint64_t*)grp_off.p, d_gcur.p, grouped.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
         st_.ms_scatter += t.stop();
         for (auto& b : batches_) b.recs.release();
         batches_.clear();
@@ -762,8 +883,8 @@ public:
         const bool is_auto = abundance_min < 0;
         uint32_t emit_min = is_auto ? 3u : (uint32_t)std::max(abundance_min, 1);
         uint64_t cand_cap = std::min<uint64_t>(pos_upper / emit_min, nvalid_total_ / (4ull * emit_min) + (1u << 20)) + 1024;
-        DevBuf<K> cand_keys;
-        DevBuf<uint32_t> cand_cnt;
+        DevBuf<K>& cand_keys = cand_keys_;
+        DevBuf<uint32_t>& cand_cnt = cand_cnt_;
         DevBuf<unsigned long long> d_histo(HISTO_MAX + 1);
         DevBuf<unsigned int> d_item_counter(1);
         unsigned long long gs[4] = {0, 0, 0, 0}, nvalid = 0, ncand = 0;
@@ -780,7 +901,7 @@ public:
             t.start();
             if (total_rec) {
                 const int smem = (int)(sizeof(K) + 4) * S + SMEM_HIST * 4 + (COUNT_THREADS / 32) * CK_SLATE * 2;
-                count_kernel<K><<<sm_count_ * 2, COUNT_THREADS, smem, stream_>>>(packed_.p, grouped.p, grp_off.p, max_groups, d_item_counter.p, k_,
+                count_kernel<K><<<sm_count_ * 2, COUNT_THREADS, smem, stream_>>>(packed_ptr, grouped.p, grp_off.p, max_groups, d_item_counter.p, k_,
                                                                                 emit_min, d_histo.p, cand_keys.p, cand_cnt.p, counters_.p + 2,
                                                                                 cand_cap, gstats.p, flags_.p + 1);
                 MTG_CUDA(cudaGetLastError());
@@ -802,7 +923,24 @@ public:
         if (err == 1) throw Error(-5, "shared-memory count table overflow (hash classes exhausted)");
         if (err == 2) throw Error(-5, "candidate buffer overflow");
         st_.nb_candidates = ncand;
-        // ---- threshold (auto: CountProcessorCutoff::endPass, min_auto_threshold = 3) and final filter
+        ncand_ = ncand;
+        // the packed reads are no longer needed
+        packed_.release(); inv_.release(); staging_.release();
+        ext_packed_ = nullptr; ext_records_ = nullptr; ext_nrec_ = 0;
+        words_used_ = words_cap_ = 0;
+    }
+
+    // threshold (auto: CountProcessorCutoff::endPass, min_auto_threshold = 3; on the GLOBAL histogram when several
+    // GPUs counted disjoint partitions) and final filter
+    void filter(int abundance_min, int64_t abundance_max, const uint64_t* histo_global) override {
+        EventTimer t(stream_);
+        Trace tr(stream_);
+        const bool is_auto = abundance_min < 0;
+        if (histo_global) memcpy(histo_.data(), histo_global, (HISTO_MAX + 1) * 8);
+        const uint64_t ncand = ncand_;
+        DevBuf<K>& cand_keys = cand_keys_;
+        DevBuf<uint32_t>& cand_cnt = cand_cnt_;
+        MTG_CUDA(cudaMemsetAsync(counters_.p + 3, 0, 8, stream_));
         int thr = abundance_min;
         if (is_auto) { thr = compute_auto_cutoff(histo_.data(), 3); st_.cutoff_auto = thr; }
         st_.threshold = thr;
@@ -824,9 +962,7 @@ public:
         nb_solid_ = ns;
         st_.nb_solid = ns;
         tr.mark("finish: threshold+filter");
-        // the packed reads are no longer needed
-        packed_.release(); inv_.release(); staging_.release();
-        words_used_ = words_cap_ = 0;
+        cand_keys_.release(); cand_cnt_.release();
     }
 
     const CountStats& stats() const override { return st_; }

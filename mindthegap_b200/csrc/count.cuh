@@ -32,7 +32,15 @@ public:
     virtual void reserve(uint64_t nb_bases) = 0;
     virtual void push_device(const uint8_t* d_bases, uint64_t n) = 0;  // ASCII bases, sequences separated by any non-ACGT byte
     virtual void push_host(const char* bases, uint64_t n) = 0;
-    virtual void finish(int abundance_min, int64_t abundance_max) = 0;
+    virtual void finish(int abundance_min, int64_t abundance_max) = 0;   // = run + filter on the local histogram
+    // multi-GPU building blocks: run() counts whatever records this counter holds (its own or imported ones) and leaves
+    // the local abundance histogram + candidates; filter() applies the threshold derived from `histo_global` (or local)
+    virtual void run(int abundance_min) = 0;
+    virtual void filter(int abundance_min, int64_t abundance_max, const uint64_t* histo_global) = 0;
+    virtual void local_info(uint64_t* nwords, uint64_t* nrecords, uint64_t* nvalid) const = 0;
+    virtual void copy_packed(uint64_t* d_packed_out, uint32_t* d_inv_out, uint64_t capacity_words) = 0;
+    virtual void partition_records(int nparts, uint64_t pos_offset_bases, uint64_t* d_out, uint64_t* counts_host) = 0;
+    virtual void import_external(const uint64_t* d_packed, const uint32_t* d_inv, uint64_t nwords, const uint64_t* d_records, uint64_t nrecords) = 0;
     virtual const CountStats& stats() const = 0;
     virtual const uint64_t* histogram() const = 0;  // host, HISTO_MAX+1 entries, valid after finish
     virtual uint64_t nb_solid() const = 0;

@@ -1,1 +1,179 @@
-int main() { return 0; }
+// mtg_find -- drop-in for the `find` subcommand of MindTheGap (src/main.cpp:88-103, src/Finder.cpp:97-171, 192-415):
+// same options, same output files (<out>.breakpoints, <out>.othervariants.vcf), same info lines. Host C++ only; all the
+// work is done by libmtg_b200.so through the C ABI (include/mtg_b200.h). There is no CPU fallback.
+//
+//   mtg_find [find] -in reads.fq[,reads2.fq] -ref ref.fa [-out prefix] [-kmer-size 31] [-abundance-min auto] ...
+//
+// Not supported here (reported as errors, like an OptionFailure): -graph x.h5 and -bed, which need gatb-core's HDF5
+// storage / the bed-restricted scan.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mtg_b200.h"
+#include "seqio.hpp"
+
+static const char* MTG_FIND_VERSION = "2.3.0 (mtg-b200 engine)";
+
+static void fail(const std::string& msg) {
+    printf("EXCEPTION: %s\n", msg.c_str());  // src/main.cpp:96-102
+    exit(EXIT_FAILURE);
+}
+static void check(int rc) { if (rc != 0) fail(mtg_last_error()); }
+
+static void usage() {
+    fprintf(stderr,
+            "mtg_find: B200 engine behind `MindTheGap find`\n"
+            "  -in <reads[,reads...]>   FASTA/FASTQ read files (mandatory)\n"
+            "  -ref <reference.fa>      reference genome (mandatory)\n"
+            "  -out <prefix>            output prefix [MindTheGap_Expe-<date>]\n"
+            "  -kmer-size <k>           5..63 [31]\n"
+            "  -abundance-min <n|auto>  [auto]      -abundance-max <n> [2147483647]\n"
+            "  -max-rep <n> [5]   -het-max-occ <n> [1]   -snp-min-val <n> [5]   -branching-filter <n> [15]\n"
+            "  -homo-only -insert-only -snp-only -deletion-only -hete-only -backup -no-snp -no-insert -no-deletion -no-hetero\n"
+            "  -nb-cores / -max-memory / -max-disk / -out-tmp / -verbose are accepted and ignored; -device <gpu> [0]\n");
+}
+
+int main(int argc, char** argv) {
+    std::string in, ref, out, graph, bed, amin = "auto";
+    mtg_params p;
+    mtg_default_params(&p);
+    bool f_homo_only = false, f_insert_only = false, f_snp_only = false, f_deletion_only = false, f_hete_only = false, f_backup = false,
+         f_no_snp = false, f_no_insert = false, f_no_deletion = false, f_no_hetero = false;
+    int i = 1;
+    if (i < argc && !strcmp(argv[i], "find")) i++;
+    for (; i < argc; i++) {
+        std::string o = argv[i];
+        auto val = [&]() -> std::string { if (i + 1 >= argc) { usage(); fail("missing value for option " + o); } return argv[++i]; };
+        if (o == "-in") in = val();
+        else if (o == "-ref") ref = val();
+        else if (o == "-out") out = val();
+        else if (o == "-graph") graph = val();
+        else if (o == "-bed") bed = val();
+        else if (o == "-kmer-size") p.kmer_size = atoi(val().c_str());
+        else if (o == "-abundance-min") amin = val();
+        else if (o == "-abundance-max") p.abundance_max = atoll(val().c_str());
+        else if (o == "-max-rep") p.max_repeat = atoi(val().c_str());
+        else if (o == "-het-max-occ") p.het_max_occ = atoi(val().c_str());
+        else if (o == "-snp-min-val") p.snp_min_val = atoi(val().c_str());
+        else if (o == "-branching-filter") p.branching_filter = atoi(val().c_str());
+        else if (o == "-device") p.device = atoi(val().c_str());
+        else if (o == "-nb-cores" || o == "-max-memory" || o == "-max-disk" || o == "-out-tmp" || o == "-verbose") val();
+        else if (o == "-homo-only") f_homo_only = true;
+        else if (o == "-insert-only") f_insert_only = true;
+        else if (o == "-snp-only") f_snp_only = true;
+        else if (o == "-deletion-only") f_deletion_only = true;
+        else if (o == "-hete-only") f_hete_only = true;
+        else if (o == "-backup") f_backup = true;
+        else if (o == "-no-snp") f_no_snp = true;
+        else if (o == "-no-insert") f_no_insert = true;
+        else if (o == "-no-deletion") f_no_deletion = true;
+        else if (o == "-no-hetero") f_no_hetero = true;
+        else if (o == "-help" || o == "-h") { usage(); return 0; }
+        else { usage(); fail("unknown option " + o); }
+    }
+    // mandatory-option checks (src/Finder.cpp:198-207)
+    if ((!graph.empty() && !in.empty()) || (graph.empty() && in.empty()))
+        fail("ERROR: options -graph and -in are incompatible, but at least one of these is mandatory");
+    if (!graph.empty()) fail("-graph needs gatb-core's HDF5 storage: read dsk/solid on the host and call mtg_load_solid (INTEGRATION.md)");
+    if (!bed.empty()) fail("-bed is not supported by this engine yet");
+    if (ref.empty()) fail("ERROR: option -ref is mandatory");
+    if (out.empty()) {  // src/Finder.cpp:210-219
+        time_t now = time(0);
+        struct tm tstruct = *localtime(&now);
+        char buf[80];
+        strftime(buf, sizeof(buf), "%Y-%m-%d.%I:%M", &tstruct);
+        out = std::string("MindTheGap_Expe-") + buf;
+    }
+    p.abundance_min = amin == "auto" ? MTG_ABUNDANCE_AUTO : atoi(amin.c_str());
+    if (p.het_max_occ < 1) p.het_max_occ = 1;  // src/Finder.cpp:317-319
+    // mode flags, applied in the reference's fixed order (src/Finder.cpp:321-398)
+    bool homo_only = false, homo_insert = true, hete_insert = true, snp = true, backup = false, deletion = true;
+    if (f_homo_only) { homo_only = true; homo_insert = true; hete_insert = false; snp = true; backup = false; deletion = true; }
+    if (f_insert_only) { homo_only = false; homo_insert = true; hete_insert = true; snp = false; backup = false; deletion = false; }
+    if (f_snp_only) { homo_only = true; homo_insert = false; hete_insert = false; snp = true; backup = false; deletion = false; }
+    if (f_deletion_only) { homo_only = true; homo_insert = false; hete_insert = false; snp = false; backup = false; deletion = true; }
+    if (f_hete_only) { homo_only = false; homo_insert = false; hete_insert = true; snp = false; backup = false; deletion = false; }
+    if (f_backup) backup = true;
+    if (f_no_snp) snp = false;
+    if (f_no_insert) homo_insert = false;
+    if (f_no_deletion) deletion = false;
+    if (f_no_hetero) hete_insert = false;
+    p.flags = (homo_only ? MTG_F_HOMO_ONLY : 0) | (homo_insert ? MTG_F_HOMO_INSERT : 0) | (hete_insert ? MTG_F_HETE_INSERT : 0) |
+              (snp ? MTG_F_SNP : 0) | (backup ? MTG_F_BACKUP : 0) | (deletion ? MTG_F_DELETION : 0) | MTG_F_SMALL_HOMO;
+
+    struct timespec t0, t1, t2;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    mtg_ctx* g = mtg_create(&p);
+    if (!g) fail(mtg_last_error());
+    // graph construction (was Graph::create, src/Finder.cpp:266)
+    check(mtg_count_files(g, in.c_str()));
+    check(mtg_count_finish(g));
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+
+    // output files (src/Finder.cpp:287-302, header :513-541)
+    const std::string bk_name = out + ".breakpoints", vcf_name = out + ".othervariants.vcf";
+    FILE* bk = fopen(bk_name.c_str(), "w");
+    if (!bk) fail("Cannot open file " + bk_name + " for writing");
+    FILE* vcf = fopen(vcf_name.c_str(), "w");
+    if (!vcf) fail("Cannot open file " + vcf_name + " for writing");
+    time_t now = time(NULL);
+    fprintf(vcf,
+            "##fileformat=VCFv4.1\n##filedate=%s##source=MindTheGap find version %s\n##SAMPLE=file:%s\n##REF=file:%s\n"
+            "##INFO=<ID=TYPE,Number=1,Type=String,Description=\"SNP, INS, DEL or .\">\n"
+            "##INFO=<ID=LEN,Number=1,Type=Integer,Description=\"variant size\">\n"
+            "##INFO=<ID=FUZZY,Number=1,Type=Integer,Description=\"repeat size at the breakpoint, only for INS and DEL\">\n"
+            "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+            "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tG1\n",
+            ctime(&now), MTG_FIND_VERSION, in.c_str(), ref.c_str());
+
+    // reference: repeat Bloom over all sequences, then one scan per sequence in file order
+    std::vector<mtg::SeqRecord> refs;
+    try {
+        mtg::for_each_sequence(ref, [&](mtg::SeqRecord& r) { refs.push_back(r); });
+    } catch (const std::exception& e) { fail(e.what()); }
+    std::string all;
+    for (auto& r : refs) { all += r.seq; all += '\n'; }
+    check(mtg_set_reference(g, all.data(), all.size()));
+    std::string().swap(all);
+    for (auto& r : refs) check(mtg_scan_reference(g, r.name.c_str(), r.seq.data(), r.seq.size()));
+    uint64_t n = 0;
+    const char* t = mtg_breakpoints_text(g, &n);
+    fwrite(t, 1, n, bk);
+    t = mtg_vcf_text(g, &n);
+    fwrite(t, 1, n, vcf);
+    fclose(bk);
+    fclose(vcf);
+    clock_gettime(CLOCK_MONOTONIC, &t2);
+
+    // info lines (src/Finder.cpp:417-511)
+    uint64_t c[12];
+    check(mtg_get_find_counters(g, c));
+    auto secs = [](const timespec& a, const timespec& b) { return (b.tv_sec - a.tv_sec) + (b.tv_nsec - a.tv_nsec) * 1e-9; };
+    printf("Parameters\n");
+    printf("    Input data\n        Reads                    : %s\n        Reference                : %s\n", in.c_str(), ref.c_str());
+    printf("    Graph\n        kmer-size                : %d\n", p.kmer_size);
+    if (mtg_get_cutoff_auto(g) >= 0) printf("        abundance_min (auto inferred) : %d\n", mtg_get_cutoff_auto(g));
+    printf("        abundance_min (used)     : %d\n        abundance_max            : %lld\n        nb_solid_kmers           : %llu\n",
+           mtg_get_threshold(g), (long long)p.abundance_max, (unsigned long long)mtg_get_nb_solid(g));
+    printf("    Breakpoint detection options\n        max_repeat               : %d\n        hetero_max_occ           : %d\n"
+           "        homo_insertions          : %s\n        hete_insertions          : %s\n        snp                      : %s\n"
+           "        deletion                 : %s\n",
+           p.max_repeat, p.het_max_occ, homo_insert ? "yes" : "no", hete_insert ? "yes" : "no", snp ? "yes" : "no", deletion ? "yes" : "no");
+    printf("Results\n    Insertion breakpoints\n        homozygous               : %llu\n            clean                : %llu\n"
+           "            fuzzy                : %llu\n        heterozygous             : %llu\n            clean                : %llu\n"
+           "            fuzzy                : %llu\n",
+           (unsigned long long)(c[0] + c[1]), (unsigned long long)c[0], (unsigned long long)c[1], (unsigned long long)(c[2] + c[3]),
+           (unsigned long long)c[2], (unsigned long long)c[3]);
+    printf("    Other variants\n        deletions                : %llu\n        Homozygous insertions 1-2 bp size : %llu\n"
+           "        Heterozygous insertions 1-2 bp size : %llu\n        SNPs                     : %llu\n",
+           (unsigned long long)(c[4] + c[5]), (unsigned long long)c[9], (unsigned long long)c[10], (unsigned long long)(c[6] + c[7]));
+    printf("    Time                         : %.3f s (graph %.3f s, scan %.3f s)\n", secs(t0, t2), secs(t0, t1), secs(t1, t2));
+    printf("    Output files\n        breakpoint_file          : %s\n        othervariants_file       : %s\n", bk_name.c_str(), vcf_name.c_str());
+    mtg_destroy(g);
+    return EXIT_SUCCESS;
+}

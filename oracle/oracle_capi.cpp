@@ -201,4 +201,24 @@ uint64_t mtgo_graph_features(void* p, const char* seq, uint64_t len, uint8_t* fe
     return n;
 }
 
+// One reference sequence through the scan oracle (gap machine + observers), fresh state, ids from 1.
+// flags: bit0 homo_only, 1 homo_insert, 2 hete_insert, 3 snp, 4 backup, 5 deletion, 6 small_homo (= MTG_F_* of the product ABI).
+// Returns the byte sizes through out_sizes[2]; texts are copied when bk/vcf are non-null (call twice).
+void mtgo_graph_scan(void* p, const char* name, const char* seq, uint64_t len, int max_repeat, int het_max_occ, int snp_min_val,
+                     int branching, unsigned flags, char* bk, char* vcf, uint64_t* out_sizes) {
+    GraphHandle* g = (GraphHandle*)p;
+    FindOptions o;
+    o.k = g->k; o.max_repeat = max_repeat; o.het_max_occ = het_max_occ; o.snp_min_val = snp_min_val; o.branching_threshold = branching;
+    o.homo_only = flags & 1; o.homo_insert = flags & 2; o.hete_insert = flags & 4; o.snp = flags & 8; o.backup = flags & 16;
+    o.deletion = flags & 32; o.small_homo = flags & 64;
+    SeqRecord rec;
+    rec.name = name; rec.seq.assign(seq, len);
+    std::string b, v;
+    if (g->k <= 31) { ScanOracle<uint64_t> s(g->g1, g->rb1, o); s.scan_sequence(rec); b = s.out_bkpt; v = s.out_vcf; }
+    else { ScanOracle<u128> s(g->g2, g->rb2, o); s.scan_sequence(rec); b = s.out_bkpt; v = s.out_vcf; }
+    out_sizes[0] = b.size(); out_sizes[1] = v.size();
+    if (bk) memcpy(bk, b.data(), b.size());
+    if (vcf) memcpy(vcf, v.data(), v.size());
+}
+
 }  // extern "C"

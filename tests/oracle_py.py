@@ -55,6 +55,8 @@ def load():
     L.mtgo_graph_set_reference.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int]
     L.mtgo_graph_features.restype = C.c_uint64
     L.mtgo_graph_features.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, u8p, u8p]
+    L.mtgo_graph_scan.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_char_p,
+                                  C.c_char_p, u64p]
     _lib = L
     return L
 
@@ -120,6 +122,14 @@ class Graph:
 
     def set_reference(self, stream: bytes, het_max_occ=1):
         self.L.mtgo_graph_set_reference(self.h, stream, len(stream), het_max_occ)
+
+    def scan(self, name: str, seq: bytes, max_repeat=5, het_max_occ=1, snp_min_val=5, branching=15, flags=0x6E):
+        """One sequence through the scan oracle with fresh state (ids from 1): (breakpoints text, vcf records)."""
+        sizes = np.zeros(2, dtype=np.uint64)
+        self.L.mtgo_graph_scan(self.h, name.encode(), seq, len(seq), max_repeat, het_max_occ, snp_min_val, branching, flags, None, None, sizes)
+        bk = C.create_string_buffer(int(sizes[0]) + 1); vcf = C.create_string_buffer(int(sizes[1]) + 1)
+        self.L.mtgo_graph_scan(self.h, name.encode(), seq, len(seq), max_repeat, het_max_occ, snp_min_val, branching, flags, bk, vcf, sizes)
+        return bk.raw[:int(sizes[0])].decode(), vcf.raw[:int(sizes[1])].decode()
 
     def features(self, seq: bytes):
         n = max(0, len(seq) - self.k + 1)

@@ -1,0 +1,63 @@
+"""CPU checks of the boundary: the C-ABI library builds, loads and exports every symbol include/mtg_b200.h declares;
+without a CUDA device the product fails loudly (no CPU fallback); the host-side CLI flag logic mirrors Finder.cpp."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from tests.cases import ROOT
+
+HEADER = os.path.join(ROOT, "include", "mtg_b200.h")
+LIB = os.path.join(ROOT, "mindthegap_b200", "_build", "libmtg_b200.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "mindthegap_b200", "csrc")], check=True)
+    return ctypes.CDLL(LIB)
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mtg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), "libmtg_b200.so does not export %s" % s
+
+
+def test_python_mirror_lists_every_symbol():
+    import mindthegap_b200.api as api
+    assert sorted(api.EXPORTS) == declared_symbols()
+
+
+def test_no_cpu_fallback(lib):
+    """Without a GPU mtg_create must fail with a message (this container has no CUDA device)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import mindthegap_b200 as m
+    with pytest.raises(m.MtgError) as e:
+        m.Finder(m.FindParams(kmer_size=31))
+    assert "CUDA" in str(e.value)
+    exe = os.path.join(ROOT, "mindthegap_b200", "_build", "mtg_find")
+    r = subprocess.run([exe, "find", "-in", HEADER, "-ref", HEADER], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("EXCEPTION:")
+
+
+def test_mode_flags_follow_finder_order():
+    """src/Finder.cpp:321-398 applies the -x-only / -no-x flags in a fixed order, not in command-line order."""
+    import mindthegap_b200.api as api
+    p = api.FindParams.from_cli(["-no-snp", "-homo-only"])
+    assert p.flags & api.F_HOMO_ONLY and not p.flags & api.F_SNP and not p.flags & api.F_HETE_INSERT and p.flags & api.F_DELETION
+    p = api.FindParams.from_cli(["-hete-only", "-max-rep", "2"])
+    assert p.max_repeat == 2 and p.flags == (api.F_HETE_INSERT | api.F_SMALL_HOMO)
+    p = api.FindParams.from_cli(["-abundance-min", "auto", "-het-max-occ", "0"])
+    assert p.abundance_min == api.ABUNDANCE_AUTO and p.het_max_occ == 1

@@ -234,3 +234,27 @@ def test_load_solid_gives_same_scan():
         g.scan_reference(nm, seq)
     assert g.breakpoints_text() == bk and g.vcf_text() == vcf
     f.close(); g.close()
+
+
+@pytest.mark.parametrize("name", ["full", "hetero_insert", "syn_tiny_k63"])
+def test_cpp_cli_mtg_find(tmp_path, name):
+    """The C++ host (`mtg_find`, same options/output files as `MindTheGap find`) gives the reference's files."""
+    import subprocess
+    from tests.cases import ROOT
+    case = CASES[name]
+    reads, ref = case_paths(case)
+    exe = os.path.join(ROOT, "mindthegap_b200", "_build", "mtg_find")
+    out = str(tmp_path / "o")
+    r = subprocess.run([exe, "find", "-in", reads, "-ref", ref, "-kmer-size", str(case["k"]), "-out", out, "-nb-cores", "1"] + case["flags"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ebk, evcf, einfo = expected(name)
+    assert open(out + ".breakpoints").read() == ebk
+    vcf_lines = open(out + ".othervariants.vcf").read().splitlines(keepends=True)
+    assert vcf_lines[0] == "##fileformat=VCFv4.1\n" and sum(l.startswith("#") for l in vcf_lines) == 10
+    assert "".join(l for l in vcf_lines if not l.startswith("#")) == evcf
+    if name == "full":
+        assert "abundance_min (auto inferred) : 7" in r.stdout and "nb_solid_kmers           : 7419" in r.stdout
+    # error behaviour of the CLI (src/main.cpp:96-102)
+    r = subprocess.run([exe, "find", "-in", reads], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "EXCEPTION: ERROR: option -ref is mandatory" in r.stdout
