@@ -199,6 +199,17 @@ def own_arm(args):
     ref_offsets = np.cumsum([0] + [len(s) + 1 for _, s in wl["refs"]])
     nbytes = int(stream_np.size)
 
+    all_refs = None
+    if world > 1:   # every rank needs every chromosome (features are sharded by position, not by chromosome)
+        import synth
+        from mindthegap_b200.dist import DistFind
+        all_refs = []
+        for r in range(world):
+            refs_r = wl["refs"] if r == rank else synth.build(wl["cfg"], SEED + 1000 * r)[0]
+            all_refs += [("g%d_%s" % (r, n), s) for n, s in refs_r]
+        wl["ref_kmers"] = sum(max(0, len(s) - K + 1) for _, s in wl["refs"])
+        all_ref_stream = np.concatenate([np.concatenate([s, np.array([10], dtype=np.uint8)]) for _, s in all_refs])
+
     def one_find(resident):
         f = m.Finder(params)
         f.reserve(nbytes)
@@ -206,6 +217,17 @@ def own_arm(args):
             f.push_reads_device(stream_dev.data_ptr(), nbytes)
         else:
             f.push_reads(stream_np)
+        if world > 1:
+            d = DistFind(f, torch.device("cuda", local_rank))
+            bk, vcf = d.find(all_refs, all_ref_stream)
+            st = f.stats()
+            st["nb_solid"] = d.nb_solid
+            st["threshold"] = f.threshold
+            st.update({"find." + k: v for k, v in f.find_counters().items()})
+            st.update({"exchange." + k: float(v) for k, v in d.exchange_bytes.items()})
+            st.update({"dist.ms_" + k: float(v) for k, v in d.timing.items()})
+            f.close()
+            return bk, vcf, st
         f.finish_count()
         if resident:
             f.set_reference_device(ref_dev.data_ptr(), int(ref_stream.size))
@@ -257,7 +279,23 @@ def own_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, wall_e2e, out_e2e, _ = timed(False, args.steps, max(1, args.warmup // 2))
     assert out_res[0] == out_e2e[0] and out_res[1] == out_e2e[1], "resident and host-buffer runs disagree"
-    if args.trace and rank == 0:  # one extra resident find with the library's stage trace on stderr
+    if world > 1 and args.verify:   # N-rank outputs == one-GPU outputs on the union of the inputs (rank 0 does the single-GPU run)
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(wl["stream"], gathered, dst=0)
+        if rank == 0:
+            f = m.Finder(params)
+            for part in gathered:
+                f.push_reads(part)
+            bk1, vcf1 = None, None
+            f.finish_count()
+            f.set_reference(np.concatenate([np.concatenate([s, np.array([10], dtype=np.uint8)]) for _, s in all_refs]))
+            for name, seq in all_refs:
+                f.scan_reference(name, seq)
+            bk1, vcf1 = f.breakpoints_text(), f.vcf_text()
+            f.close()
+            assert bk1 == out_res[0] and vcf1 == out_res[1], "N-GPU outputs differ from the single-GPU outputs on the same inputs"
+            print("[bench verify] %d-GPU outputs identical to the single-GPU run (%d breakpoint lines)" % (world, len(bk1.splitlines())), file=sys.stderr)
+    if args.trace and world == 1:  # one extra resident find with the library's stage trace on stderr
         os.environ["MTG_TRACE"] = "1"
         t0 = time.perf_counter()
         one_find(True)
@@ -337,7 +375,7 @@ def own_arm(args):
             "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": wl["name"], "kmer_size": K, "abundance_min": "auto (inferred %d)" % int(avg["threshold"]),
                        "per_gpu_read_bytes": nbytes, "l2_policy": "inputs (%.0f MB reads per GPU) larger than the 126 MB L2; every step starts from a fresh context" % (nbytes / 1e6),
-                       "parallelism": "1 process per GPU; reads sharded" if world > 1 else "single GPU"},
+                       "parallelism": ("1 process per GPU (%d): records all-to-all by minimizer owner, solid set all-gathered, reference positions sharded" % world) if world > 1 else "single GPU"},
             "e2e": {"value": tot_kmers / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes + ref_stream.size),
                     "d2h_bytes_per_step": int(2 * wl["ref_kmers"] + len(out_e2e[0]) + len(out_e2e[1])), "ms_per_step": ms_e2e},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity": parity,
@@ -367,6 +405,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the GPU workload (1.0 = cfg2)")
     ap.add_argument("--cpu-scale", type=float, default=0.25, help="genome scale of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--verify", action="store_true", help="N>1: also run the union of the inputs on one GPU and compare the outputs")
     ap.add_argument("--trace", action="store_true", help="print the library's per-stage wall clock for one extra find (stderr)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -88,6 +88,14 @@ int mtg_count_filter(mtg_ctx* ctx, const uint64_t* histogram10001);
 int mtg_solid_copy(mtg_ctx* ctx, void* d_keys_out, void* d_counts_out, uint64_t capacity);
 /* build_visitor_postsolid (Graph.cpp:428-612) from a device array of solid keys (e.g. the all-gathered set) */
 int mtg_graph_build_device(mtg_ctx* ctx, const void* d_keys, uint64_t n);
+/* the same build in steps, so that N GPUs split the critical-false-positive search (DebloomMinimizerAlgorithm.cpp:196-275,
+ * the costliest step: 8 neighbour probes per solid k-mer) over their own solid shares:
+ *   begin(all keys): exact table + Bloom;  critical(share): candidates among the neighbours of the share (-> *n_out, copied out
+ *   with critical_copy for an all-gather);  end(all keys, gathered candidates): de-duplication, cascading Blooms, cFP set, BooPHF */
+int mtg_graph_build_begin(mtg_ctx* ctx, const void* d_keys, uint64_t n);
+int mtg_graph_critical(mtg_ctx* ctx, const void* d_keys_share, uint64_t n_share, uint64_t* n_out);
+int mtg_graph_critical_copy(mtg_ctx* ctx, void* d_out, uint64_t capacity);
+int mtg_graph_build_end(mtg_ctx* ctx, const void* d_keys, uint64_t n, const void* d_candidates, uint64_t n_candidates);
 
 /* info lines of Finder::resumeParameters (src/Finder.cpp:444-467) */
 int32_t mtg_get_threshold(mtg_ctx* ctx);     /* "abundance_min (used)"           */

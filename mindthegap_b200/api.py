@@ -40,6 +40,7 @@ EXPORTS = [
     "mtg_scan_reference", "mtg_scan_reference_device", "mtg_set_reference_device", "mtg_breakpoints_text", "mtg_vcf_text", "mtg_reset_outputs", "mtg_get_find_counters", "mtg_copy_bits",
     "mtg_bench_random_gather", "mtg_count_local_info", "mtg_count_copy_packed", "mtg_count_partition_records", "mtg_count_import",
     "mtg_count_run", "mtg_count_filter", "mtg_solid_copy", "mtg_graph_build_device", "mtg_sequence_features_device2", "mtg_replay_sequence",
+    "mtg_graph_build_begin", "mtg_graph_critical", "mtg_graph_critical_copy", "mtg_graph_build_end",
 ]
 
 _lib = None
@@ -105,6 +106,10 @@ def load_library():
     L.mtg_count_filter.argtypes = [vp, vp]
     L.mtg_solid_copy.argtypes = [vp, vp, vp, C.c_uint64]
     L.mtg_graph_build_device.argtypes = [vp, vp, C.c_uint64]
+    L.mtg_graph_build_begin.argtypes = [vp, vp, C.c_uint64]
+    L.mtg_graph_critical.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.mtg_graph_critical_copy.argtypes = [vp, vp, C.c_uint64]
+    L.mtg_graph_build_end.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64]
     L.mtg_sequence_features_device2.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, u64p]
     L.mtg_replay_sequence.argtypes = [vp, C.c_char_p, vp, C.c_uint64, u8p, u8p, vp]
     L.mtg_bench_random_gather.restype = C.c_double
@@ -339,6 +344,10 @@ class Finder:
         h = None if histogram is None else np.ascontiguousarray(histogram, dtype=np.uint64)
         self._check(self.L.mtg_count_filter(self.ctx, _ptr(h)))
 
+    def nb_solid_local(self):
+        """This rank's share of the solid set (between count_filter and graph_build_device)."""
+        return int(self.L.mtg_get_nb_solid(self.ctx))
+
     @property
     def key_words(self):
         """64-bit words per k-mer key: 1 (k <= 31) or 2 ({lo, hi})."""
@@ -350,6 +359,20 @@ class Finder:
 
     def graph_build_device(self, keys_t, n):
         self._check(self.L.mtg_graph_build_device(self.ctx, C.c_void_p(keys_t.data_ptr()), n))
+
+    def graph_build_begin(self, keys_t, n):
+        self._check(self.L.mtg_graph_build_begin(self.ctx, C.c_void_p(keys_t.data_ptr()), n))
+
+    def graph_critical(self, keys_t, n):
+        out = C.c_uint64()
+        self._check(self.L.mtg_graph_critical(self.ctx, C.c_void_p(keys_t.data_ptr()), n, C.byref(out)))
+        return out.value
+
+    def graph_critical_copy(self, out_t):
+        self._check(self.L.mtg_graph_critical_copy(self.ctx, C.c_void_p(out_t.data_ptr()), out_t.numel() // self.key_words))
+
+    def graph_build_end(self, keys_t, n, cand_t, ncand):
+        self._check(self.L.mtg_graph_build_end(self.ctx, C.c_void_p(keys_t.data_ptr()), n, C.c_void_p(cand_t.data_ptr()), ncand))
 
     def features_segment(self, seq_t):
         """seq_t: uint8 device tensor holding bases [a, b+k-1); returns (feat, rep, interest) device tensors for b-a positions."""

@@ -363,6 +363,36 @@ int mtg_graph_build_device(mtg_ctx* ctx, const void* d_keys, uint64_t n) {
     MTG_CATCH
 }
 
+int mtg_graph_build_begin(mtg_ctx* ctx, const void* d_keys, uint64_t n) {
+    MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->build_base(d_keys, n); MTG_CUDA(cudaStreamSynchronize(ctx->stream)); MTG_CATCH
+}
+int mtg_graph_critical(mtg_ctx* ctx, const void* d_keys_share, uint64_t n_share, uint64_t* n_out) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_finish);
+    ctx->graph->critical(d_keys_share, n_share);
+    if (n_out) *n_out = ctx->graph->critical_count();
+    MTG_CATCH
+}
+int mtg_graph_critical_copy(mtg_ctx* ctx, void* d_out, uint64_t capacity) {
+    MTG_TRY(ctx)
+    const uint64_t n = ctx->graph->critical_count();
+    if (capacity < n) throw Error(-1, "mtg_graph_critical_copy: capacity too small");
+    const size_t ksz = ctx->p.kmer_size <= 31 ? 8 : 16;
+    if (n) MTG_CUDA(cudaMemcpyAsync(d_out, ctx->graph->critical_device(), n * ksz, cudaMemcpyDeviceToDevice, ctx->stream));
+    MTG_CUDA(cudaStreamSynchronize(ctx->stream));
+    MTG_CATCH
+}
+int mtg_graph_build_end(mtg_ctx* ctx, const void* d_keys, uint64_t n, const void* d_candidates, uint64_t n_candidates) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_finish);
+    ctx->graph->critical_merge(d_candidates, n_candidates);
+    ctx->graph->build_rest(d_keys, n);
+    MTG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->graph_ready = true;
+    ctx->nb_solid_global = n;
+    MTG_CATCH
+}
+
 int32_t mtg_get_threshold(mtg_ctx* ctx) { return ctx ? ctx->threshold : -1; }
 int32_t mtg_get_cutoff_auto(mtg_ctx* ctx) { return ctx ? ctx->cutoff_auto : -1; }
 uint64_t mtg_get_nb_solid(mtg_ctx* ctx) { return ctx ? (ctx->nb_solid_global ? ctx->nb_solid_global : ctx->nb_solid) : 0; }
@@ -542,9 +572,7 @@ const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes) {
 }
 int mtg_reset_outputs(mtg_ctx* ctx) {
     MTG_TRY(ctx)
-    make_replayers(ctx);
-    ctx->ms_features = ctx->ms_replay = 0;
-    ctx->scan_positions = ctx->scan_valid = ctx->scan_in_graph = ctx->scan_table_probes = ctx->scan_fallback = 0;
+    make_replayers(ctx);   // texts, find counters and the bkpt id counter restart; timing / probe statistics keep accumulating
     MTG_CATCH
 }
 int mtg_get_find_counters(mtg_ctx* ctx, uint64_t* o) {

@@ -576,24 +576,56 @@ __global__ void __launch_bounds__(256) filter_kernel(const K* __restrict__ cand_
 // multi-GPU building blocks: records are owned by rank (minimizer bin % nparts)
 // ------------------------------------------------------------------------------------------------------------
 static const int MAX_PARTS = 64;
-__global__ void __launch_bounds__(256) owner_count_kernel(const uint64_t* __restrict__ records, uint64_t nrec, int nparts,
-                                                          unsigned long long* __restrict__ counts) {
+static const int OW_THREADS = 256, OW_PER = 8, OW_TILE = OW_THREADS * OW_PER;
+// Records per owner. Destinations are few (<= 64) and hot, so counts are aggregated per warp (match_any) and per block
+// before a single global atomic per destination and block.
+__global__ void __launch_bounds__(OW_THREADS) owner_count_kernel(const uint64_t* __restrict__ records, uint64_t nrec, int nparts,
+                                                                 unsigned long long* __restrict__ counts) {
     __shared__ unsigned int s_cnt[MAX_PARTS];
     if (threadIdx.x < MAX_PARTS) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(&s_cnt[(uint32_t)(records[i] & ((1u << REC_LEN_SHIFT) - 1)) % nparts], 1u);
+    const int lane = threadIdx.x & 31;
+    const uint64_t nround = (nrec + 31) & ~31ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = i < nrec ? (uint32_t)(records[i] & ((1u << REC_LEN_SHIFT) - 1)) % nparts : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        if (d != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[d], (unsigned)__popc(peers));
+    }
     __syncthreads();
     if (threadIdx.x < nparts && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
-// scatter into per-owner segments (cursor[d] starts at the segment offset), positions rebased into the gathered array
-__global__ void __launch_bounds__(256) owner_scatter_kernel(const uint64_t* __restrict__ records, uint64_t nrec, int nparts, uint64_t pos_offset,
-                                                            unsigned long long* __restrict__ cursor, uint64_t* __restrict__ out) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t r = records[i];
-        const uint32_t d = (uint32_t)(r & ((1u << REC_LEN_SHIFT) - 1)) % nparts;
-        const unsigned long long o = atomicAdd(&cursor[d], 1ull);
-        out[o] = r + (pos_offset << REC_POS_SHIFT);
+// scatter into per-owner segments (cursor[d] starts at the segment offset), positions rebased into the gathered array:
+// a block ranks its tile of records per destination in shared memory, reserves one range per destination, then writes
+__global__ void __launch_bounds__(OW_THREADS) owner_scatter_kernel(const uint64_t* __restrict__ records, uint64_t nrec, int nparts, uint64_t pos_offset,
+                                                                   unsigned long long* __restrict__ cursor, uint64_t* __restrict__ out) {
+    __shared__ unsigned int s_cnt[MAX_PARTS];
+    __shared__ unsigned long long s_base[MAX_PARTS];
+    const int lane = threadIdx.x & 31;
+    const uint64_t ntiles = (nrec + OW_TILE - 1) / OW_TILE;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x < MAX_PARTS) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint64_t r[OW_PER];
+        uint32_t rank_in[OW_PER], dest[OW_PER];
+#pragma unroll
+        for (int j = 0; j < OW_PER; j++) {
+            const uint64_t i = tile * OW_TILE + (uint64_t)j * OW_THREADS + threadIdx.x;
+            r[j] = i < nrec ? records[i] : 0;
+            dest[j] = i < nrec ? (uint32_t)(r[j] & ((1u << REC_LEN_SHIFT) - 1)) % nparts : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dest[j]);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (dest[j] != 0xFFFFFFFFu && lane == leader) base = atomicAdd(&s_cnt[dest[j]], (unsigned)__popc(peers));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            rank_in[j] = base + __popc(peers & ((1u << lane) - 1));
+        }
+        __syncthreads();
+        if (threadIdx.x < nparts && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < OW_PER; j++)
+            if (dest[j] != 0xFFFFFFFFu) out[s_base[dest[j]] + rank_in[j]] = r[j] + (pos_offset << REC_POS_SHIFT);
+        __syncthreads();
     }
 }
 // per-bin histogram (records << 36 | instances) and instance total of an imported record list
@@ -798,8 +830,8 @@ public:
         MTG_CUDA(cudaMemcpyAsync(d_cursor.p, cur, sizeof(cur), cudaMemcpyHostToDevice, stream_));
         for (auto& b : batches_) {
             if (!b.nrec) continue;
-            int grid = (int)std::min<uint64_t>((b.nrec + 255) / 256, (uint64_t)sm_count_ * 8);
-            owner_scatter_kernel<<<grid, 256, 0, stream_>>>(b.recs.p, b.nrec, nparts, pos_offset_bases, d_cursor.p, d_out);
+            int grid = (int)std::min<uint64_t>((b.nrec + OW_TILE - 1) / OW_TILE, (uint64_t)sm_count_ * 8);
+            owner_scatter_kernel<<<grid, OW_THREADS, 0, stream_>>>(b.recs.p, b.nrec, nparts, pos_offset_bases, d_cursor.p, d_out);
             st_.launches++;
         }
         MTG_CUDA(cudaGetLastError());

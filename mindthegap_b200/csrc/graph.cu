@@ -89,31 +89,80 @@ __global__ void __launch_bounds__(256) bloom_neighbor_insert_kernel(const K* __r
 
 // critical false positives: Bloom-positive, non-solid canonical neighbours of solid k-mers, de-duplicated through an
 // open-addressing set (insert-if-absent); new members are appended to `crit_list`.
+// One thread handles the 4 successors (or the 4 predecessors) of one solid k-mer: they share the middle k-2 bases, hence
+// the Bloom hash part, the root position and the simplehash offsets (the point of BloomNeighborCoherent; GATB's contains4,
+// Bloom.hpp:640-818) -- only the cano2 offset differs, so the 4 x nhash bits sit within 16 bits of each other.
 template <class K>
 __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ keys, uint64_t n, GraphView<K> g, K* __restrict__ set,
                                                        uint64_t set_slots, K* __restrict__ crit_list, unsigned long long* __restrict__ ncrit,
                                                        uint64_t list_cap, int* __restrict__ err) {
     const K EMPTY = ~K(0);
-    const K mask = kmask<K>(g.k);
-    const uint64_t total = n * 8;
+    const int k = g.k;
+    const K mask = kmask<K>(k);
+    const uint64_t total = n * 2;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-        const K x = keys[t >> 3];
-        const int j = (int)(t & 7);
-        K nb = j < 4 ? (((x << 2) + (K)j) & mask) : ((x >> 2) + ((K)(j - 4) << (2 * (g.k - 1))));  // Model.hpp:524-580
-        nb = canonical(nb, g.k);
-        if (!bloom_neighbor_contains(g, nb)) continue;
-        if (table_contains(g, nb)) continue;
-        uint64_t s = key_hash(nb) % set_slots;
+        const K x = keys[t >> 1];
+        const bool succ = !(t & 1);
+        // shared middle part of the 4 neighbours: successors y = x[1..k-1]+nt -> x[2..k-1]; predecessors y = nt+x[0..k-2] -> x[0..k-3]
+        K hashpart = succ ? (x & kmask<K>(k - 2)) : ((x >> 4) & kmask<K>(k - 2));
+        const K rev = revcomp(hashpart, k - 2);
+        if (rev < hashpart) hashpart = rev;
+        const uint64_t racine = gatb_hash1(hashpart, g.seed0) % g.bloom_tai;
+        uint64_t off[8];
+        off[0] = 0;
+        for (int i = 1; i < g.bloom_nhash; i++) off[i] = simplehash16_dev(g.rnd, hashpart, i) & 4095;
+        // fixed end of the neighbours: first base of a successor = x[1]; last base of a predecessor = x[k-2]
+        const unsigned fixed = succ ? (unsigned)((x >> (2 * (k - 2))) & 3) : (unsigned)((x >> 2) & 3);
+        unsigned alive = 0xF;
+        for (int i = 0; i < g.bloom_nhash && alive; i++) {
+            const uint64_t base = racine + off[i];   // + cano2 in [0,13]
+            const uint64_t w = base >> 5;
+            const unsigned sh = (unsigned)(base & 31);
+            uint64_t bits = (uint64_t)__ldg(g.bloom + w) | ((uint64_t)__ldg(g.bloom + w + 1) << 32);
+            bits >>= sh;
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const unsigned c2 = succ ? cano2_dev((fixed << 2) | nt) : cano2_dev((nt << 2) | fixed);
+                if (!((bits >> c2) & 1)) alive &= ~(1u << nt);
+            }
+        }
+        while (alive) {
+            const int nt = __ffs(alive) - 1;
+            alive &= alive - 1;
+            K nb = succ ? (((x << 2) + (K)nt) & mask) : ((x >> 2) + ((K)nt << (2 * (k - 1))));  // Model.hpp:524-580
+            nb = canonical(nb, k);
+            if (table_contains(g, nb)) continue;
+            uint64_t s = key_hash(nb) % set_slots;
+            bool placed = false;
+            for (uint64_t probe = 0; probe < set_slots; probe++) {
+                K cur = cas_global(&set[s], EMPTY, nb);
+                if (cur == EMPTY) {
+                    unsigned long long o = atomicAdd(ncrit, 1ull);
+                    if (o < list_cap) crit_list[o] = nb; else *err = 2;
+                    placed = true;
+                    break;
+                }
+                if (cur == nb) { placed = true; break; }
+                s = s + 1 == set_slots ? 0 : s + 1;
+            }
+            if (!placed) *err = 1;
+        }
+    }
+}
+
+// de-duplication of a (gathered) list of critical k-mers: first arrival in the set appends to `out`
+template <class K>
+__global__ void __launch_bounds__(256) dedup_kernel(const K* __restrict__ in, uint64_t n, K* __restrict__ set, uint64_t set_slots, K* __restrict__ out,
+                                                    unsigned long long* __restrict__ nout, int* __restrict__ err) {
+    const K EMPTY = ~K(0);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const K x = in[i];
+        uint64_t s = key_hash(x) % set_slots;
         bool placed = false;
         for (uint64_t probe = 0; probe < set_slots; probe++) {
-            K cur = cas_global(&set[s], EMPTY, nb);
-            if (cur == EMPTY) {
-                unsigned long long o = atomicAdd(ncrit, 1ull);
-                if (o < list_cap) crit_list[o] = nb; else *err = 2;
-                placed = true;
-                break;
-            }
-            if (cur == nb) { placed = true; break; }
+            K cur = cas_global(&set[s], EMPTY, x);
+            if (cur == EMPTY) { out[atomicAdd(nout, 1ull)] = x; placed = true; break; }
+            if (cur == x) { placed = true; break; }
             s = s + 1 == set_slots ? 0 : s + 1;
         }
         if (!placed) *err = 1;
@@ -306,7 +355,8 @@ template <class K> class Graph : public IGraph {
     DevBuf<K> table_;
     uint64_t nbuckets_ = 0;
     BloomDev bloom_, b2_, b3_, b4_, ref_;
-    DevBuf<K> cfp_, final_;
+    DevBuf<K> cfp_, final_, crit_list_;
+    uint64_t ncrit_ = 0;
     uint64_t ncfp_ = 0, nfinal_ = 0;
     bool cascading_ = true, mphf_built_ = false;
     DevBuf<unsigned long long> mphf_bits_;
@@ -398,6 +448,13 @@ public:
     }
 
     void build(const void* d_solid, uint64_t N) override {
+        build_base(d_solid, N);
+        critical(d_solid, N);
+        build_rest(d_solid, N);
+    }
+
+    // table + main Bloom from the full solid set
+    void build_base(const void* d_solid, uint64_t N) override {
         const K* keys = (const K*)d_solid;
         EvTimer t(stream_);
         Trace tr(stream_);
@@ -434,10 +491,18 @@ public:
         st_.ms_bloom = t.stop();
         st_.bloom_tai = bloom_.tai;
         tr.mark("graph: bloom");
-        // ---- critical false positives (set de-duplication; retried with a larger set if it fills up)
+    }
+
+    // critical false positives among the neighbours of `keys` (any share of the solid set), de-duplicated within the share
+    void critical(const void* d_keys, uint64_t N) override {
+        const K* keys = (const K*)d_keys;
+        EvTimer t(stream_);
+        Trace tr(stream_);
+        // ---- (set de-duplication; retried with a larger set if it fills up)
         t.start();
         uint64_t ncrit = 0;
-        DevBuf<K> crit_list;
+        DevBuf<K>& crit_list = crit_list_;
+        crit_list.alloc(1);
         for (uint64_t mult = 1; N && mult <= 16; mult *= 2) {
             uint64_t slots = N * mult + 1024;
             uint64_t cap = slots * 7 / 10;
@@ -447,7 +512,7 @@ public:
             MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 8, stream_));
             err_.zero(stream_);
             GraphView<K> g = view();
-            critical_kernel<K><<<grid_for(N * 8), 256, 0, stream_>>>(keys, N, g, set.p, slots, crit_list.p, counters_.p, cap, err_.p);
+            critical_kernel<K><<<grid_for(N * 2), 256, 0, stream_>>>(keys, N, g, set.p, slots, crit_list.p, counters_.p, cap, err_.p);
             MTG_CUDA(cudaGetLastError());
             st_.launches++;
             int e = 0;
@@ -460,7 +525,44 @@ public:
         }
         st_.ms_critical = t.stop();
         st_.nb_critical = ncrit;
+        ncrit_ = ncrit;
         tr.mark("graph: critical");
+    }
+    uint64_t critical_count() const override { return ncrit_; }
+    const void* critical_device() const override { return crit_list_.p; }
+
+    // replaces the critical list by the distinct elements of a gathered candidate list (shares overlap at their borders)
+    void critical_merge(const void* d_candidates, uint64_t n) override {
+        EvTimer t(stream_);
+        t.start();
+        DevBuf<K> out(std::max<uint64_t>(n, 1));
+        const uint64_t slots = n * 2 + 1024;
+        DevBuf<K> set(slots);
+        set.fill_ff(stream_);
+        MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 8, stream_));
+        err_.zero(stream_);
+        if (n) {
+            dedup_kernel<K><<<grid_for(n), 256, 0, stream_>>>((const K*)d_candidates, n, set.p, slots, out.p, counters_.p, err_.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        unsigned long long nc = 0;
+        MTG_CUDA(cudaMemcpyAsync(&nc, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
+        check_err("critical k-mer merge");
+        crit_list_ = std::move(out);
+        ncrit_ = nc;
+        st_.nb_critical = nc;
+        st_.ms_critical += t.stop();
+    }
+
+    // cascading Blooms + cFP set + BooPHF from the full solid set and the (global) critical list
+    void build_rest(const void* d_solid, uint64_t N) override {
+        const K* keys = (const K*)d_solid;
+        EvTimer t(stream_);
+        Trace tr(stream_);
+        const float NBITS = bits_per_kmer(k_);
+        const uint64_t ncrit = ncrit_;
+        DevBuf<K>& crit_list = crit_list_;
         // ---- cascading Blooms (createCFP, DebloomAlgorithm.cpp:462-622); BLOOM_CACHE kind is forced there (:497)
         t.start();
         cascading_ = ncrit != 0;  // no critical FP -> DEBLOOM_ORIGINAL with an empty set (:478-479)

@@ -247,6 +247,14 @@ public:
     // build everything from the solid set (device array of K, not necessarily sorted)
     virtual void build(const void* d_solid_keys, uint64_t n) = 0;
     virtual void build_from_host(const uint64_t* lo, const uint64_t* hi, uint64_t n) = 0;
+    // build() in three steps, so that several GPUs can split the critical-false-positive search over their solid shares:
+    // build_base(all) ; critical(share) -> list ; [gather lists] critical_merge(gathered) ; build_rest(all)
+    virtual void build_base(const void* d_solid_keys, uint64_t n) = 0;
+    virtual void critical(const void* d_keys, uint64_t n) = 0;
+    virtual uint64_t critical_count() const = 0;
+    virtual const void* critical_device() const = 0;
+    virtual void critical_merge(const void* d_candidates, uint64_t n) = 0;
+    virtual void build_rest(const void* d_solid_keys, uint64_t n) = 0;
     // repeated (k-1)-mers of the reference (device array of canonical K values with abundance >= het_max_occ+1)
     virtual void set_ref_repeats(const void* d_keys, uint64_t n) = 0;
     // batch queries on host arrays of FORWARD k-mers (any strand); out[i] bit0 = contains

@@ -13,6 +13,7 @@ exchanges of the path:
 `engine` is a mindthegap_b200.Finder on a GPU; the CPU tests drive the same code with a fake engine over gloo.
 """
 import re
+import time
 
 import numpy as np
 import torch
@@ -55,8 +56,24 @@ class DistFind:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.k = engine.params.kmer_size
+        self.timing = {}
+        self._t = None
+
+    def _mark(self, label):
+        """Phase wall clock (ms) after draining the device; bench.py reports it for rank 0."""
+        self._sync()
+        now = time.perf_counter()
+        if self._t is not None and label:
+            self.timing[label] = self.timing.get(label, 0.0) + (now - self._t) * 1e3
+        self._t = now
 
     # ---- small helpers
+    def _sync(self):
+        """The engine works on its own CUDA stream: torch-side copies and NCCL collectives must have finished before the
+        library touches their buffers (the library synchronises its stream before returning, so the other direction is safe)."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
     def _all_max(self, *vals):
         t = torch.tensor(list(vals), dtype=torch.int64, device=self.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
@@ -68,19 +85,38 @@ class DistFind:
         dist.all_gather_into_tensor(out, t, group=self.group)
         return [int(x) for x in out.tolist()]
 
+    def _gather_texts(self, texts):
+        """All ranks' (chromosome index, breakpoints, vcf) lists on rank 0, as one padded uint8 all-gather (gather_object
+        pickles through several small collectives, which costs milliseconds)."""
+        import json
+        blob = np.frombuffer(json.dumps(texts).encode(), dtype=np.uint8)
+        sizes = self._all_gather_i64(len(blob))
+        m = max(max(sizes), 1)
+        t = torch.zeros(m, dtype=torch.uint8, device=self.device)
+        t[:len(blob)] = torch.from_numpy(blob.copy()).to(self.device)
+        out = torch.empty(m * self.world, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        if self.rank != 0:
+            return None
+        host = out.cpu().numpy()
+        return [json.loads(host[r * m: r * m + sizes[r]].tobytes().decode()) for r in range(self.world)]
+
     # ---- stage 1: count (reads of this rank already pushed into the engine)
     def count(self):
         e, W = self.e, self.world
+        self._mark(None)
         nwords, nrec, _ = e.count_local_info()
         (maxw,) = self._all_max(nwords)
         seg = maxw + 8                                   # words per rank in the gathered array (>= 8 pad words)
         packed = torch.empty(seg, dtype=torch.int64, device=self.device)
         inv = torch.empty(seg, dtype=torch.int32, device=self.device)
+        self._sync()
         e.count_copy_packed(packed, inv)
         packed_all = torch.empty(seg * W, dtype=torch.int64, device=self.device)
         inv_all = torch.empty(seg * W, dtype=torch.int32, device=self.device)
         dist.all_gather_into_tensor(packed_all, packed, group=self.group)
         dist.all_gather_into_tensor(inv_all, inv, group=self.group)
+        self._mark("allgather_packed")
         # records -> owners
         send = torch.empty(max(nrec, 1), dtype=torch.int64, device=self.device)
         counts = e.count_partition_records(W, self.rank * seg * 32, send)
@@ -91,13 +127,17 @@ class DistFind:
         recv = torch.empty(max(sum(rcounts), 1), dtype=torch.int64, device=self.device)
         dist.all_to_all_single(recv[:sum(rcounts)], send[:nrec], output_split_sizes=rcounts, input_split_sizes=counts, group=self.group)
         self.exchange_bytes = {"allgather_packed": int(packed_all.numel() * 12), "alltoall_records": int(8 * sum(rcounts))}
+        self._mark("alltoall_records")
         # count the owned partition, merge the histograms, filter
+        self._sync()
         e.count_import(packed_all, inv_all, recv[:sum(rcounts)])
         e.count_run()
+        self._mark("count_run")
         h = torch.from_numpy(e.histogram().astype(np.int64)).to(self.device)
         dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.group)
         self.histogram = h.cpu().numpy().astype(np.uint64)
         e.count_filter(self.histogram)
+        self._mark("histogram_allreduce+filter")
         del packed_all, inv_all, recv, send
         # all-gather the solid shares, build the full graph on every rank
         kw = e.key_words
@@ -105,6 +145,7 @@ class DistFind:
         sizes = self._all_gather_i64(n_local)
         nmax = max(max(sizes), 1)
         keys = torch.zeros(nmax * kw, dtype=torch.int64, device=self.device)
+        self._sync()
         e.solid_copy(keys, None)
         keys_all = torch.empty(nmax * kw * W, dtype=torch.int64, device=self.device)
         dist.all_gather_into_tensor(keys_all, keys, group=self.group)
@@ -112,16 +153,44 @@ class DistFind:
         solid = torch.cat(parts) if sum(sizes) else torch.zeros(kw, dtype=torch.int64, device=self.device)
         self.nb_solid = sum(sizes)
         self.exchange_bytes["allgather_solid"] = int(keys_all.numel() * 8)
-        e.graph_build_device(solid, self.nb_solid)
+        self._mark("allgather_solid")
+        # membership structures: table + Bloom from the full set on every rank; the critical-false-positive search (8
+        # neighbour probes per solid k-mer) only over the own share, candidates all-gathered and merged
+        e.graph_build_begin(solid, self.nb_solid)
+        nc = e.graph_critical(keys, n_local)
+        csizes = self._all_gather_i64(nc)
+        cmax = max(max(csizes), 1)
+        cand = torch.zeros(cmax * kw, dtype=torch.int64, device=self.device)
+        self._sync()
+        e.graph_critical_copy(cand)
+        cand_all = torch.empty(cmax * kw * W, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(cand_all, cand, group=self.group)
+        cands = torch.cat([cand_all[r * cmax * kw: r * cmax * kw + csizes[r] * kw] for r in range(W)]) if sum(csizes) else cand
+        self.exchange_bytes["allgather_critical"] = int(cand_all.numel() * 8)
+        self._sync()
+        e.graph_build_end(solid, self.nb_solid, cands, sum(csizes))
+        self._mark("graph_build")
         return self.nb_solid
 
     # ---- stage 2: scan. ref_records: [(name, uint8 numpy array)] identical on every rank
-    def scan(self, ref_records):
+    def scan(self, ref_records, ref_stream=None):
+        """ref_stream (optional): all reference sequences joined by a newline, as a uint8 array (saves rebuilding it)."""
         e, W, k = self.e, self.world, self.k
-        e.set_reference(np.concatenate([np.concatenate([s, np.array([10], dtype=np.uint8)]) for _, s in ref_records]))
-        texts = []
+        self._mark(None)
+        if ref_stream is None:
+            ref_stream = np.concatenate([np.concatenate([s, np.array([10], dtype=np.uint8)]) for _, s in ref_records])
+        ref_dev = torch.from_numpy(np.ascontiguousarray(ref_stream)).to(self.device)   # the whole reference, once
+        self._sync()
+        if hasattr(e, "set_reference_device") and self.device.type == "cuda":
+            e.set_reference_device(ref_dev.data_ptr(), ref_dev.numel())
+        else:
+            e.set_reference(ref_stream)
+        self._mark("set_reference")
+        # pass 1: every rank computes its 32-aligned segment of every chromosome ((k-1)-base halo) and the segments are
+        # all-gathered as one buffer per chromosome: [feat | rep | interest words] per rank
+        offsets = np.cumsum([0] + [len(s) + 1 for _, s in ref_records])
+        mine = []
         for ci, (name, seq) in enumerate(ref_records):
-            owner = ci % W
             n = len(seq)
             if n < k:
                 continue
@@ -129,35 +198,40 @@ class DistFind:
             b = segment_bounds(npos, W)
             a0, a1 = b[self.rank], b[self.rank + 1]
             segmax = max(b[r + 1] - b[r] for r in range(W))
-            feat = torch.full((segmax,), 0x80, dtype=torch.uint8, device=self.device)
-            rep = torch.zeros(segmax, dtype=torch.uint8, device=self.device)
-            interest = torch.zeros((segmax + 31) // 32, dtype=torch.int32, device=self.device)
+            iw = (segmax + 31) // 32
+            stride = 2 * segmax + 4 * iw
+            buf = torch.zeros(stride, dtype=torch.uint8, device=self.device)
+            buf[:segmax] = 0x80
             if a1 > a0:
-                sub = torch.from_numpy(np.array(seq[a0:a1 + k - 1], dtype=np.uint8)).to(self.device)   # (k-1)-base halo
+                sub = ref_dev[int(offsets[ci]) + a0: int(offsets[ci]) + a1 + k - 1]   # device slice incl. halo
+                self._sync()
                 f, r, it = e.features_segment(sub)
-                feat[:a1 - a0] = f; rep[:a1 - a0] = r; interest[:it.numel()] = it
-            feat_all = torch.empty(segmax * W, dtype=torch.uint8, device=self.device)
-            rep_all = torch.empty(segmax * W, dtype=torch.uint8, device=self.device)
-            int_all = torch.empty(interest.numel() * W, dtype=torch.int32, device=self.device)
-            dist.all_gather_into_tensor(feat_all, feat, group=self.group)
-            dist.all_gather_into_tensor(rep_all, rep, group=self.group)
-            dist.all_gather_into_tensor(int_all, interest, group=self.group)
-            if self.rank != owner:
-                continue
-            fa, ra, ia = feat_all.cpu().numpy(), rep_all.cpu().numpy(), int_all.cpu().numpy()
-            iw = interest.numel()
-            feat_h = np.concatenate([fa[r * segmax: r * segmax + (b[r + 1] - b[r])] for r in range(W)])
-            rep_h = np.concatenate([ra[r * segmax: r * segmax + (b[r + 1] - b[r])] for r in range(W)])
-            int_h = np.concatenate([ia[r * iw: r * iw + ((b[r + 1] - b[r]) + 31) // 32] for r in range(W)] + [np.zeros(1, dtype=np.int32)])
+                buf[:a1 - a0] = f
+                buf[segmax:segmax + (a1 - a0)] = r
+                buf[2 * segmax:2 * segmax + 4 * it.numel()] = it.view(torch.uint8)
+            allbuf = torch.empty(stride * W, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allbuf, buf, group=self.group)
+            if ci % W == self.rank:
+                mine.append((ci, name, seq, b, segmax, iw, stride, allbuf.cpu()))
+        self._mark("features+allgather")
+        # pass 2: whole chromosomes are replayed round-robin, all ranks at the same time
+        texts = []
+        for ci, name, seq, b, segmax, iw, stride, host in mine:
+            h = host.numpy()
+            feat_h = np.concatenate([h[r * stride: r * stride + (b[r + 1] - b[r])] for r in range(W)])
+            rep_h = np.concatenate([h[r * stride + segmax: r * stride + segmax + (b[r + 1] - b[r])] for r in range(W)])
+            int_h = np.concatenate([h[r * stride + 2 * segmax: r * stride + 2 * segmax + 4 * (((b[r + 1] - b[r]) + 31) // 32)] for r in range(W)]
+                                   + [np.zeros(4, dtype=np.uint8)]).view(np.int32)
             e.reset_outputs()
             e.replay_sequence(name, seq, feat_h, rep_h, int_h)
             texts.append((ci, e.breakpoints_text(), e.vcf_text()))
+        self._mark("replay")
         # merge on rank 0 in reference order, renumbering the shared ids
-        gathered = [None] * W if self.rank == 0 else None
-        dist.gather_object(texts, gathered, dst=0, group=self.group)
+        gathered = self._gather_texts(texts)
+        self._mark("gather_texts")
         if self.rank != 0:
             return None, None
-        allt = sorted(t for part in gathered for t in part)
+        allt = sorted(tuple(t) for part in gathered for t in part)
         bk_out, vcf_out, offset = [], [], 0
         for _, bk, vcf in allt:
             bk, vcf, used = renumber(bk, vcf, offset)
@@ -165,6 +239,6 @@ class DistFind:
             offset += used
         return "".join(bk_out), "".join(vcf_out)
 
-    def find(self, ref_records):
+    def find(self, ref_records, ref_stream=None):
         self.count()
-        return self.scan(ref_records)
+        return self.scan(ref_records, ref_stream)

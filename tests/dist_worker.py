@@ -110,9 +110,22 @@ class FakeEngine:
     def solid_copy(self, keys_t, counts_t):
         keys_t[:len(self.solid)] = torch.from_numpy(self.solid.view(np.int64))
 
-    def graph_build_device(self, keys_t, n):
-        lo = np.sort(keys_t.numpy().view(np.uint64)[:n])
-        self.g = oracle_py.Graph(lo, np.zeros(n, dtype=np.uint64), self.k)
+    def graph_build_begin(self, keys_t, n):
+        self._all = np.sort(keys_t.numpy().view(np.uint64)[:n])
+
+    def graph_critical(self, keys_t, n):
+        # candidates of this share: here simply the share's first/last keys, to exercise the variable-size gather + merge
+        share = keys_t.numpy().view(np.uint64)[:n]
+        self._cand = share[:min(n, 3 + dist.get_rank())].copy()
+        return len(self._cand)
+
+    def graph_critical_copy(self, out_t):
+        out_t[:len(self._cand)] = torch.from_numpy(self._cand.view(np.int64))
+
+    def graph_build_end(self, keys_t, n, cand_t, ncand):
+        assert ncand == sum(3 + r for r in range(dist.get_world_size()))
+        assert np.isin(cand_t.numpy().view(np.uint64)[:ncand], self._all).all()
+        self.g = oracle_py.Graph(self._all, np.zeros(n, dtype=np.uint64), self.k)
 
     # -- stage 2
     def set_reference(self, stream):

@@ -258,3 +258,69 @@ def test_cpp_cli_mtg_find(tmp_path, name):
     # error behaviour of the CLI (src/main.cpp:96-102)
     r = subprocess.run([exe, "find", "-in", reads], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "EXCEPTION: ERROR: option -ref is mandatory" in r.stdout
+
+
+def _dist_worker_script():
+    return """
+import json, os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from tests import oracle_py
+from tests.cases import CASES, case_paths
+import mindthegap_b200 as m
+from mindthegap_b200.dist import DistFind
+case_name, out = sys.argv[1], sys.argv[2]
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+case = CASES[case_name]
+reads, ref = case_paths(case)
+recs = oracle_py.read_sequences(reads)
+p = m.FindParams.from_cli(["-kmer-size", str(case["k"])] + list(case["flags"]))
+p.device = rank
+f = m.Finder(p)
+f.push_reads(b"\\n".join(s for _, s in recs[rank::world]) + b"\\n")
+d = DistFind(f, torch.device("cuda", rank))
+refs = [(n, np.frombuffer(s, dtype=np.uint8)) for n, s in oracle_py.read_sequences(ref)]
+bk, vcf = d.find(refs)
+if rank == 0:
+    json.dump({"bk": bk, "vcf": vcf, "nb_solid": d.nb_solid, "threshold": f.threshold}, open(out, "w"))
+f.close()
+dist.destroy_process_group()
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run_dist(tmp_path, case, world):
+    import json, socket, subprocess, sys
+    script = tmp_path / "w.py"
+    script.write_text(_dist_worker_script())
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "o.json")
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), case, out], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    return json.load(open(out))
+
+
+@pytest.mark.parametrize("case", ["syn_tiny_k31", "syn_tiny_k63", "full"])
+def test_dist_path_one_rank(tmp_path, case):
+    """The multi-GPU building blocks (partition, import, run/filter, solid gather, graph build from a device array, feature
+    segments, replay from gathered features, merge) with world_size 1 over NCCL give the reference's outputs."""
+    res = _run_dist(tmp_path, case, 1)
+    ebk, evcf, _ = expected(case)
+    assert res["bk"] == ebk and res["vcf"] == evcf
+
+
+@pytest.mark.parametrize("case", ["syn_tiny_k31", "syn_small_k31", "syn_tiny_k63"])
+def test_dist_path_two_gpus(tmp_path, case):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = _run_dist(tmp_path, case, 2)
+    ebk, evcf, einfo = expected(case)
+    assert res["bk"] == ebk and res["vcf"] == evcf
+    import re
+    assert res["nb_solid"] == int(re.search(r"nb_solid_kmers\s*:\s*(\d+)", einfo).group(1))
