@@ -33,13 +33,15 @@ UNIT = "kmers/s"
 
 
 # ---------------------------------------------------------------------------------------------------- workload
-def make_workload(scale=1.0, seed=SEED, genome_mult=1):
-    """cfg2 (optionally scaled): returns dict(refs=[(name, uint8 array)], stream=uint8 array of '\\n'-separated reads,
+def make_workload(scale=1.0, seed=SEED, genome_mult=1, config="cfg2"):
+    """cfg2 / cfg3 (optionally scaled): returns dict(refs=[(name, uint8 array)], stream=uint8 array of '\\n'-separated reads,
     mats, n_reads, read_len, read_kmers, ref_kmers)."""
     import synth
-    cfg = dict(synth.CONFIGS["cfg2"])
+    cfg = dict(synth.CONFIGS[config])
     cfg["genome_len"] = int(cfg["genome_len"] * scale * genome_mult)
-    cfg["n_hom"] = max(1, int(cfg["n_hom"] * scale * genome_mult))
+    for key in ("n_hom", "n_het", "n_snp", "n_del"):
+        if cfg.get(key):
+            cfg[key] = max(1, int(cfg[key] * scale * genome_mult))
     refs, mats, truth = synth.reads_in_memory(cfg, seed)
     L = cfg["read_len"]
     tot = sum(m.shape[0] for m in mats)
@@ -51,8 +53,9 @@ def make_workload(scale=1.0, seed=SEED, genome_mult=1):
         o += len(m)
     return dict(cfg=cfg, refs=refs, stream=buf.reshape(-1), n_reads=tot, read_len=L, read_kmers=tot * max(0, L - K + 1),
                 ref_kmers=sum(max(0, len(s) - K + 1) for _, s in refs), truth=truth,
-                name="cfg2: synthetic %.2f Mbp genome, %dx 2x%dbp reads, %d planted homozygous insertions, k=%d" % (
-                    cfg["genome_len"] / 1e6, cfg["coverage"], L, cfg["n_hom"], K))
+                name="%s: synthetic %.2f Mbp genome, %dx 2x%dbp reads, %d planted homozygous insertions%s, k=%d" % (
+                    config, cfg["genome_len"] / 1e6, cfg["coverage"], L, cfg["n_hom"],
+                    (", %d heterozygous insertions, %d SNPs, %d deletions" % (cfg["n_het"], cfg["n_snp"], cfg["n_del"])) if cfg.get("n_het") else "", K))
 
 
 def write_inputs(wl, d):
@@ -89,12 +92,17 @@ def run_cpu_find(wl, cores, workdir, tag="cpu"):
     return dict(seconds=secs, value=(wl["read_kmers"] + wl["ref_kmers"]) / secs, breakpoints=bk, vcf=vcf, info=info)
 
 
+def cpu_sample_scale(args):
+    """Genome scale of the bounded CPU sample: --cpu-scale of cfg2's 4.6 Mbp, i.e. the same number of bases for every config."""
+    return args.cpu_scale if args.config == "cfg2" else args.cpu_scale * 4.6 / 64.0
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    wl = make_workload(scale=args.cpu_scale)
+    wl = make_workload(scale=cpu_sample_scale(args), config=args.config)
     times = []
     with tempfile.TemporaryDirectory() as tmp:
         for i in range(args.warmup + args.steps):
@@ -104,11 +112,11 @@ def reference_arm(args):
     t = sum(times) / len(times)
     value = (wl["read_kmers"] + wl["ref_kmers"]) / t
     sample = "%s (scale %.3g of the 4.6 Mbp workload; compute time of count+graph+refbloom+scan, file parsing excluded)" % (
-        wl["name"], args.cpu_scale)
+        wl["name"], cpu_sample_scale(args))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic",
-            "config": {"workload": wl["name"], "kmer_size": K, "abundance_min": "auto", "sample_scale": args.cpu_scale},
+            "dtype": "u64" if K <= 31 else "u128", "data": "synthetic",
+            "config": {"workload": wl["name"], "kmer_size": K, "abundance_min": "auto", "sample_scale": cpu_sample_scale(args)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "read_kmers_counted_per_s": wl["read_kmers"] / float(r["info"]["time_count"]),
@@ -188,7 +196,7 @@ def own_arm(args):
     lib = m.load_library()
 
     # every rank brings the read set of its own genome segment (weak scaling); N=1 is exactly cfg2
-    wl = make_workload(scale=args.scale, seed=SEED + 1000 * rank)
+    wl = make_workload(scale=args.scale, seed=SEED + 1000 * rank, config=args.config)
     params = m.FindParams(kmer_size=K, device=local_rank)
     stream_host = torch.from_numpy(wl["stream"]).pin_memory()
     stream_np = stream_host.numpy()
@@ -326,12 +334,13 @@ def own_arm(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     avg = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
     nk = wl["read_kmers"]
+    bpk = 16.25 if K <= 31 else 32.25
     count_stage_ms = avg["count.ms_pack"] + avg["count.ms_extract"] + avg["count.ms_scatter"] + avg["count.ms_count"] + avg["count.ms_filter"]
     probes = avg["scan.table_probes"]
     kernels = [
-        {"kernel": "count stage (pack+superkmer+scatter+count+filter)", "ms": count_stage_ms, "bytes": 16.25 * nk,
+        {"kernel": "count stage (pack+superkmer+scatter+count+filter)", "ms": count_stage_ms, "bytes": bpk * nk,
          "note": "SURVEY 8d: 2*sizeof(kmer)+0.25 B per read k-mer"},
-        {"kernel": "count_kernel", "ms": avg["count.ms_count"], "bytes": 16.25 * nk, "note": "same bytes, count kernel alone"},
+        {"kernel": "count_kernel", "ms": avg["count.ms_count"], "bytes": bpk * nk, "note": "same bytes, count kernel alone"},
         {"kernel": "superkmer_kernel", "ms": avg["count.ms_extract"], "bytes": 0.375 * nbytes + 8.0 * avg["count.nb_records"],
          "note": "packed bases + invalid mask in, 8-byte records out"},
         {"kernel": "pack_kernel", "ms": avg["count.ms_pack"], "bytes": 1.375 * nbytes, "note": "ASCII in, 2-bit words + mask out"},
@@ -353,7 +362,8 @@ def own_arm(args):
     parity = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        swl = wl if args.cpu_scale >= args.scale else make_workload(scale=args.cpu_scale)
+        cpu_scale = cpu_sample_scale(args)
+        swl = wl if cpu_scale >= args.scale else make_workload(scale=cpu_scale, config=args.config)
         with tempfile.TemporaryDirectory() as tmp:
             r = run_cpu_find(swl, cores, tmp)
         cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
@@ -372,7 +382,7 @@ def own_arm(args):
 
     launches = int(sum(s["count.launches"] + s["graph.launches"] for s in stats))
     line = {"metric": METRIC, "value": tot_kmers / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64" if K <= 31 else "u128", "data": "synthetic",
             "config": {"workload": wl["name"], "kmer_size": K, "abundance_min": "auto (inferred %d)" % int(avg["threshold"]),
                        "per_gpu_read_bytes": nbytes, "l2_policy": "inputs (%.0f MB reads per GPU) larger than the 126 MB L2; every step starts from a fresh context" % (nbytes / 1e6),
                        "parallelism": ("1 process per GPU (%d): records all-to-all by minimizer owner, solid set all-gathered, reference positions sharded" % world) if world > 1 else "single GPU"},
@@ -402,12 +412,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the GPU workload (1.0 = cfg2)")
+    ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the GPU workload (1.0 = the named config)")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3"], help="BASELINE.json configs[1] (default, the bench line) or configs[2]")
+    ap.add_argument("--kmer-size", type=int, default=31, help="k (31 = the bench line; 63 exercises the 128-bit kernels, configs[4])")
     ap.add_argument("--cpu-scale", type=float, default=0.25, help="genome scale of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--verify", action="store_true", help="N>1: also run the union of the inputs on one GPU and compare the outputs")
     ap.add_argument("--trace", action="store_true", help="print the library's per-stage wall clock for one extra find (stderr)")
     args = ap.parse_args()
+    global K
+    K = args.kmer_size
     if args.impl == "reference":
         return reference_arm(args)
     return own_arm(args)

@@ -247,6 +247,30 @@ template <> MTG_D u128 extract_kmer<u128>(const uint64_t* __restrict__ packed, u
     return x >> (128 - 2 * k);
 }
 
+// The words that hold a k-mer, loaded unconditionally (the packed arrays are padded) so that the loads can be issued
+// ahead of use; get() is extract_kmer on the loaded words.
+template <class K> struct KmerWords;
+template <> struct KmerWords<uint64_t> {
+    uint64_t w0, w1;
+    MTG_D void load(const uint64_t* __restrict__ packed, uint64_t pos) { const uint64_t a = pos >> 5; w0 = packed[a]; w1 = packed[a + 1]; }
+    MTG_D uint64_t get(uint64_t pos, int k) const {
+        const int off = (int)(pos & 31) * 2;
+        uint64_t x = w0 << off;
+        if (off) x |= w1 >> (64 - off);
+        return x >> (64 - 2 * k);
+    }
+};
+template <> struct KmerWords<u128> {
+    uint64_t w0, w1, w2;
+    MTG_D void load(const uint64_t* __restrict__ packed, uint64_t pos) { const uint64_t a = pos >> 5; w0 = packed[a]; w1 = packed[a + 1]; w2 = packed[a + 2]; }
+    MTG_D u128 get(uint64_t pos, int k) const {
+        const int off = (int)(pos & 31) * 2;
+        u128 x(w1, w0);
+        if (off) x = u128((w1 << off) | (w2 >> (64 - off)), (w0 << off) | (w1 >> (64 - off)));
+        return x >> (128 - 2 * k);
+    }
+};
+
 // Sequential base reader over the packed array.
 struct BaseStream {
     const uint64_t* __restrict__ p;

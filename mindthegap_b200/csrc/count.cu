@@ -445,17 +445,19 @@ count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ g
     uint32_t* hist_s = cnt + S;
     uint16_t* slate = reinterpret_cast<uint16_t*>(hist_s + SMEM_HIST) + (threadIdx.x >> 5) * CK_SLATE;
     __shared__ uint32_t s_item, s_overflow, s_sp;
+    __shared__ uint32_t s_wsum[COUNT_THREADS / 32];
+    __shared__ unsigned long long s_cbase;
     __shared__ uint32_t s_stack[CK_STACK];  // (level << 24) | class prefix: keys whose hash bits [LOGS, LOGS+level) == prefix
     const K EMPTY = ~K(0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    if (tid < SMEM_HIST) hist_s[tid] = 0;   // low abundances are histogrammed in shared memory for the CTA's whole life
     while (true) {
         if (tid == 0) {
             uint32_t it;
             do { it = atomicAdd(item_counter, 1u); } while (it < ngroups && grp_off[it + 1] == grp_off[it]);  // skip empty groups
             s_item = it; s_sp = 1; s_stack[0] = 0;
         }
-        if (tid < SMEM_HIST) hist_s[tid] = 0;
         __syncthreads();
         const uint32_t it = s_item;
         if (it >= ngroups) break;
@@ -487,25 +489,42 @@ count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ g
                 const uint64_t rpos = r >> REC_POS_SHIFT;
                 const uint32_t rpos_lo = (uint32_t)rpos, rpos_hi = (uint32_t)(rpos >> 32);
                 __syncwarp();
-                for (int s = lane; s < ((total + 31) & ~31); s += 32) {
-                    const bool act = s < total;
-                    const uint32_t e = act ? slate[s] : 0;
+                // software pipeline: the packed words of the next instance are requested before the current one is inserted
+                const int round = (total + 31) & ~31;
+                bool act = lane < total;
+                uint64_t pos = 0;
+                KmerWords<K> cur;
+                {
+                    const uint32_t e = act ? slate[lane] : 0;
                     const uint32_t plo = __shfl_sync(0xFFFFFFFFu, rpos_lo, e >> 8), phi = __shfl_sync(0xFFFFFFFFu, rpos_hi, e >> 8);
-                    if (!act) continue;
-                    const uint64_t pos = (((uint64_t)phi << 32) | plo) + (e & 0xFF);
-                    const K fwd = extract_kmer<K>(packed, pos, k);
-                    const K rc = revcomp(fwd, k);
-                    const K key = fwd < rc ? fwd : rc;
-                    const uint32_t h = key_hash32(key);
-                    if (((h >> LOGS) & cmask) != prefix) continue;
-                    uint32_t slot = h & (S - 1);
-                    int probes = 0;
-                    while (true) {
-                        const K cur = slot_claim(&keys[slot], key);
-                        if (cur == EMPTY || cur == key) { atomicAdd(&cnt[slot], 1u); break; }
-                        slot = (slot + 1) & (S - 1);
-                        if (++probes >= CK_MAXPROBE) { *(volatile uint32_t*)&s_overflow = 1; break; }
+                    pos = (((uint64_t)phi << 32) | plo) + (e & 0xFF);
+                    if (act) cur.load(packed, pos);
+                }
+                for (int s = lane; s < round; s += 32) {
+                    const int sn = s + 32;
+                    const bool actn = sn < total;
+                    const uint32_t en = actn ? slate[sn] : 0;
+                    const uint32_t plo = __shfl_sync(0xFFFFFFFFu, rpos_lo, en >> 8), phi = __shfl_sync(0xFFFFFFFFu, rpos_hi, en >> 8);
+                    const uint64_t posn = (((uint64_t)phi << 32) | plo) + (en & 0xFF);
+                    KmerWords<K> nxt;
+                    if (actn) nxt.load(packed, posn);
+                    if (act) {
+                        const K fwd = cur.get(pos, k);
+                        const K rc = revcomp(fwd, k);
+                        const K key = fwd < rc ? fwd : rc;
+                        const uint32_t h = key_hash32(key);
+                        if (((h >> LOGS) & cmask) == prefix) {
+                            uint32_t slot = h & (S - 1);
+                            int probes = 0;
+                            while (true) {
+                                const K c = slot_claim(&keys[slot], key);
+                                if (c == EMPTY || c == key) { atomicAdd(&cnt[slot], 1u); break; }
+                                slot = (slot + 1) & (S - 1);
+                                if (++probes >= CK_MAXPROBE) { *(volatile uint32_t*)&s_overflow = 1; break; }
+                            }
+                        }
                     }
+                    act = actn; pos = posn; cur = nxt;
                 }
                 __syncwarp();
             }
@@ -519,34 +538,49 @@ count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ g
                 if (*(volatile int*)errflag == 1) break;
                 continue;
             }
-            // ---- sweep: histogram (Histogram::inc takes a u16: CountProcessorHistogram.hpp:174-185, Histogram.hpp:92)
-            for (int s = tid; s < S; s += COUNT_THREADS) {
-                const K key = keys[s];
-                const bool occ = key != EMPTY;
-                uint32_t c = occ ? cnt[s] : 0;
-                if (occ) {
+            // ---- sweep: histogram (Histogram::inc takes a u16: CountProcessorHistogram.hpp:174-185, Histogram.hpp:92) and
+            // candidates. Every thread owns S/COUNT_THREADS slots; the CTA reserves its output range with ONE global atomic
+            // (a per-warp atomicAdd on the single counter serialised in L2: 12 % of the stall samples, profiles r01 v3).
+            uint32_t emit_mask = 0;
+#pragma unroll
+            for (int j = 0; j < S / COUNT_THREADS; j++) {
+                const int s = tid + j * COUNT_THREADS;
+                if (keys[s] != EMPTY) {
+                    const uint32_t c = cnt[s];
                     uint32_t hidx = c & 0xFFFFu;
                     if (hidx > HISTO_MAX) hidx = HISTO_MAX;
                     if (hidx < SMEM_HIST) atomicAdd(&hist_s[hidx], 1u); else atomicAdd(&histo[hidx], 1ull);
+                    if (c >= emit_min) emit_mask |= 1u << j;
                 }
-                const bool emit = occ && c >= emit_min;
-                const uint32_t b = __ballot_sync(0xFFFFFFFFu, emit);
-                if (b) {
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(ncand, (unsigned long long)__popc(b));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (emit) {
-                        unsigned long long o = base + __popc(b & ((1u << lane) - 1));
-                        if (o < cand_capacity) { cand_keys[o] = key; cand_cnt[o] = c; } else *errflag = 2;
-                    }
+            }
+            {
+                const uint32_t mine = __popc(emit_mask);
+                uint32_t incl = mine;
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+                if (lane == 31) s_wsum[warp] = incl;
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t run = 0;
+                    for (int w = 0; w < COUNT_THREADS / 32; w++) { const uint32_t v = s_wsum[w]; s_wsum[w] = run; run += v; }
+                    s_cbase = run ? atomicAdd(ncand, (unsigned long long)run) : 0ull;
+                }
+                __syncthreads();
+                unsigned long long o = s_cbase + s_wsum[warp] + (incl - mine);
+                while (emit_mask) {
+                    const int j = __ffs(emit_mask) - 1;
+                    emit_mask &= emit_mask - 1;
+                    const int s = tid + j * COUNT_THREADS;
+                    if (o < cand_capacity) { cand_keys[o] = keys[s]; cand_cnt[o] = cnt[s]; } else *errflag = 2;
+                    o++;
                 }
             }
             __syncthreads();
         }
-        if (tid < SMEM_HIST && hist_s[tid]) atomicAdd(&histo[tid], (unsigned long long)hist_s[tid]);
         if (tid == 0) { atomicAdd(&gstats[0], 1ull); atomicAdd(&gstats[3], (unsigned long long)npasses); if (npasses > 1) atomicAdd(&gstats[1], 1ull); }
         __syncthreads();
     }
+    __syncthreads();
+    if (tid < SMEM_HIST && hist_s[tid]) atomicAdd(&histo[tid], (unsigned long long)hist_s[tid]);
 }
 
 template <class K>

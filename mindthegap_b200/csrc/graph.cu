@@ -60,14 +60,14 @@ struct BloomDev {
 template <class K>
 __global__ void __launch_bounds__(256) table_build_kernel(const K* __restrict__ keys, uint64_t n, K* __restrict__ table, uint64_t nbuckets,
                                                           int* __restrict__ err) {
-    const int SLOTS = BUCKET_BYTES / (int)sizeof(K);
+    const int SLOTS = TableCfg<K>::SLOTS, STRIDE = TableCfg<K>::STRIDE;
     const K EMPTY = ~K(0);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const K key = keys[i];
         uint64_t b = key_hash(key) % nbuckets;
         bool done = false;
         for (uint64_t probe = 0; probe < nbuckets && !done; probe++) {
-            K* bucket = table + b * SLOTS;
+            K* bucket = table + b * STRIDE;
             for (int s = 0; s < SLOTS; s++) {
                 K cur = cas_global(&bucket[s], EMPTY, key);
                 if (cur == EMPTY || cur == key) { done = true; break; }
@@ -92,38 +92,56 @@ __global__ void __launch_bounds__(256) bloom_neighbor_insert_kernel(const K* __r
 // One thread handles the 4 successors (or the 4 predecessors) of one solid k-mer: they share the middle k-2 bases, hence
 // the Bloom hash part, the root position and the simplehash offsets (the point of BloomNeighborCoherent; GATB's contains4,
 // Bloom.hpp:640-818) -- only the cano2 offset differs, so the 4 x nhash bits sit within 16 bits of each other.
-template <class K>
-__global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ keys, uint64_t n, GraphView<K> g, K* __restrict__ set,
-                                                       uint64_t set_slots, K* __restrict__ crit_list, unsigned long long* __restrict__ ncrit,
-                                                       uint64_t list_cap, int* __restrict__ err) {
+//   CRIT: collect the critical k-mers. New ones are staged in shared memory and appended with ONE global atomic per
+//         block iteration (a single-address atomicAdd per k-mer serialised in L2: 32 % of the stall samples, profiles r01 v3).
+//   ADJ : the Bloom-positive neighbours that are in the exact table are the graph neighbours of the solid k-mer; the two
+//         threads of a k-mer combine their nibbles and store the adjacency byte next to the key (graph.cuh, table layout).
+static const int CRIT_STAGE = 1024;  // 256 threads x at most 4 neighbours
+template <class K, bool ADJ, bool CRIT>
+__global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ keys, uint64_t n, GraphView<K> g, K* __restrict__ table_rw,
+                                                       K* __restrict__ set, uint64_t set_slots, K* __restrict__ crit_list,
+                                                       unsigned long long* __restrict__ ncrit, uint64_t list_cap, int* __restrict__ err) {
+    __shared__ K s_buf[CRIT ? CRIT_STAGE : 1];
+    __shared__ unsigned s_n;
+    __shared__ unsigned long long s_base;
     const K EMPTY = ~K(0);
     const int k = g.k;
     const K mask = kmask<K>(k);
     const uint64_t total = n * 2;
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-        const K x = keys[t >> 1];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t0 = (uint64_t)blockIdx.x * blockDim.x; t0 < total; t0 += stride) {
+        if (CRIT) {
+            if (threadIdx.x == 0) s_n = 0;
+            __syncthreads();
+        }
+        const uint64_t t = t0 + threadIdx.x;
+        const bool active = t < total;
+        const K x = active ? keys[t >> 1] : K(0);
         const bool succ = !(t & 1);
-        // shared middle part of the 4 neighbours: successors y = x[1..k-1]+nt -> x[2..k-1]; predecessors y = nt+x[0..k-2] -> x[0..k-3]
-        K hashpart = succ ? (x & kmask<K>(k - 2)) : ((x >> 4) & kmask<K>(k - 2));
-        const K rev = revcomp(hashpart, k - 2);
-        if (rev < hashpart) hashpart = rev;
-        const uint64_t racine = gatb_hash1(hashpart, g.seed0) % g.bloom_tai;
-        uint64_t off[8];
-        off[0] = 0;
-        for (int i = 1; i < g.bloom_nhash; i++) off[i] = simplehash16_dev(g.rnd, hashpart, i) & 4095;
-        // fixed end of the neighbours: first base of a successor = x[1]; last base of a predecessor = x[k-2]
-        const unsigned fixed = succ ? (unsigned)((x >> (2 * (k - 2))) & 3) : (unsigned)((x >> 2) & 3);
-        unsigned alive = 0xF;
-        for (int i = 0; i < g.bloom_nhash && alive; i++) {
-            const uint64_t base = racine + off[i];   // + cano2 in [0,13]
-            const uint64_t w = base >> 5;
-            const unsigned sh = (unsigned)(base & 31);
-            uint64_t bits = (uint64_t)__ldg(g.bloom + w) | ((uint64_t)__ldg(g.bloom + w + 1) << 32);
-            bits >>= sh;
+        unsigned alive = 0, adj = 0;
+        if (active) {
+            // shared middle part of the 4 neighbours: successors y = x[1..k-1]+nt -> x[2..k-1]; predecessors y = nt+x[0..k-2] -> x[0..k-3]
+            K hashpart = succ ? (x & kmask<K>(k - 2)) : ((x >> 4) & kmask<K>(k - 2));
+            const K rev = revcomp(hashpart, k - 2);
+            if (rev < hashpart) hashpart = rev;
+            const uint64_t racine = gatb_hash1(hashpart, g.seed0) % g.bloom_tai;
+            uint64_t off[8];
+            off[0] = 0;
+            for (int i = 1; i < g.bloom_nhash; i++) off[i] = simplehash16_dev(g.rnd, hashpart, i) & 4095;
+            // fixed end of the neighbours: first base of a successor = x[1]; last base of a predecessor = x[k-2]
+            const unsigned fixed = succ ? (unsigned)((x >> (2 * (k - 2))) & 3) : (unsigned)((x >> 2) & 3);
+            alive = 0xF;
+            for (int i = 0; i < g.bloom_nhash && alive; i++) {
+                const uint64_t base = racine + off[i];   // + cano2 in [0,13]
+                const uint64_t w = base >> 5;
+                const unsigned sh = (unsigned)(base & 31);
+                uint64_t bits = (uint64_t)__ldg(g.bloom + w) | ((uint64_t)__ldg(g.bloom + w + 1) << 32);
+                bits >>= sh;
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-                const unsigned c2 = succ ? cano2_dev((fixed << 2) | nt) : cano2_dev((nt << 2) | fixed);
-                if (!((bits >> c2) & 1)) alive &= ~(1u << nt);
+                for (int nt = 0; nt < 4; nt++) {
+                    const unsigned c2 = succ ? cano2_dev((fixed << 2) | nt) : cano2_dev((nt << 2) | fixed);
+                    if (!((bits >> c2) & 1)) alive &= ~(1u << nt);
+                }
             }
         }
         while (alive) {
@@ -131,21 +149,71 @@ __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ key
             alive &= alive - 1;
             K nb = succ ? (((x << 2) + (K)nt) & mask) : ((x >> 2) + ((K)nt << (2 * (k - 1))));  // Model.hpp:524-580
             nb = canonical(nb, k);
-            if (table_contains(g, nb)) continue;
+            if (table_contains(g, nb)) { adj |= 1u << nt; continue; }
+            if (!CRIT) continue;
             uint64_t s = key_hash(nb) % set_slots;
             bool placed = false;
             for (uint64_t probe = 0; probe < set_slots; probe++) {
                 K cur = cas_global(&set[s], EMPTY, nb);
-                if (cur == EMPTY) {
-                    unsigned long long o = atomicAdd(ncrit, 1ull);
-                    if (o < list_cap) crit_list[o] = nb; else *err = 2;
-                    placed = true;
-                    break;
-                }
+                if (cur == EMPTY) { s_buf[atomicAdd(&s_n, 1u)] = nb; placed = true; break; }
                 if (cur == nb) { placed = true; break; }
                 s = s + 1 == set_slots ? 0 : s + 1;
             }
             if (!placed) *err = 1;
+        }
+        if (ADJ) {
+            // the pair (successor thread, predecessor thread) of a k-mer sits in adjacent lanes; both look for the k-mer's slot,
+            // each in one half of the bucket
+            const unsigned other = __shfl_xor_sync(0xFFFFFFFFu, adj, 1);
+            const unsigned byte = succ ? (adj | (other << 4)) : (other | (adj << 4));
+            uint64_t b = key_hash(x) % g.nbuckets;
+            bool searching = active;
+            for (uint64_t probe = 0; probe < g.nbuckets; probe++) {
+                if (!__any_sync(0xFFFFFFFFu, searching)) break;
+                int slot = -1;
+                bool has_empty = false;
+                if (searching) {
+                    const uint4* q = reinterpret_cast<const uint4*>(table_rw + b * TableCfg<K>::STRIDE) + (succ ? 0 : 4);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (!succ && i == 3) break;   // chunk 7 holds the adjacency bytes
+                        const uint4 v = q[i];
+                        const uint64_t a0 = ((uint64_t)v.y << 32) | v.x, a1 = ((uint64_t)v.w << 32) | v.z;
+                        const int c = (succ ? 0 : 4) + i;
+                        if (sizeof(K) == 8) {
+                            if (a0 == lo64(x)) slot = 2 * c;
+                            if (a1 == lo64(x)) slot = 2 * c + 1;
+                            has_empty |= (a0 == ~0ull) | (a1 == ~0ull);
+                        } else {
+                            if ((a0 == lo64(x)) & (a1 == hi64(x))) slot = c;
+                            has_empty |= (a0 == ~0ull) & (a1 == ~0ull);
+                        }
+                    }
+                }
+                const int oslot = __shfl_xor_sync(0xFFFFFFFFu, slot, 1);
+                const bool oempty = __shfl_xor_sync(0xFFFFFFFFu, has_empty ? 1 : 0, 1) != 0;
+                if (searching) {
+                    const int fslot = slot >= 0 ? slot : oslot;
+                    if (fslot >= 0) {
+                        if (succ) reinterpret_cast<uint8_t*>(table_rw + b * TableCfg<K>::STRIDE)[BUCKET_ADJ_OFFSET + fslot] = (uint8_t)byte;
+                        searching = false;
+                    } else if (has_empty || oempty) {
+                        *err = 4;   // a solid k-mer must be in the table
+                        searching = false;
+                    } else b = b + 1 == g.nbuckets ? 0 : b + 1;
+                }
+            }
+        }
+        if (CRIT) {
+            __syncthreads();
+            const unsigned cnt = s_n;
+            if (threadIdx.x == 0 && cnt) s_base = atomicAdd(ncrit, (unsigned long long)cnt);
+            __syncthreads();
+            const unsigned long long gb = s_base;
+            for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) {
+                if (gb + i < list_cap) crit_list[gb + i] = s_buf[i]; else *err = 2;
+            }
+            __syncthreads();
         }
     }
 }
@@ -263,15 +331,16 @@ __global__ void __launch_bounds__(256) contains_kernel(GraphView<K> g, const uin
             bool res = ex || (bl && !cf && mp);
             out[i] = (res ? 1 : 0) | (ex ? 2 : 0) | (bl ? 4 : 0) | (cf ? 8 : 0) | (mp ? 16 : 0);
         } else if (mode == 1) {  // degrees of the forward k-mer: in | out<<4
+            bool in, ex;
             int din, dout;
-            graph_degrees(g, x, false, din, dout);
+            node_probe(g, x, true, in, ex, din, dout);
             out[i] = (uint8_t)(din | (dout << 4));
         } else if (mode == 2) {  // ref repeat test of a canonical (k-1)-mer
             out[i] = bloom_cache_contains<K>(g.refbloom, g.ref_tai, g.ref_nhash, g.seed0, g.rnd, x) ? 1 : 0;
         } else {  // observer probe: contains | indegree<<1 | outdegree<<4 | suffix_repeated<<7 (src/IFindObserver.hpp:85-117)
-            bool res = graph_contains(g, canonical(x, g.k));
+            bool res, ex;
             int din, dout;
-            graph_degrees(g, x, false, din, dout);
+            node_probe(g, x, true, res, ex, din, dout);
             K suffix = canonical<K>(x & kmask<K>(g.k - 1), g.k - 1);
             bool rp = bloom_cache_contains<K>(g.refbloom, g.ref_tai, g.ref_nhash, g.seed0, g.rnd, suffix);
             out[i] = (uint8_t)((res ? 1 : 0) | (din << 1) | (dout << 4) | (rp ? 0x80 : 0));
@@ -306,21 +375,12 @@ __global__ void __launch_bounds__(256) features_kernel(GraphView<K> g, const uin
         if (valid) {
             c_valid++;
             const K fwd = extract_kmer<K>(packed, p, k);
-            const K can = canonical(fwd, k);
-            bool exact = table_contains(g, can);
+            bool in, exact;
+            int din, dout;
+            node_probe(g, fwd, false, in, exact, din, dout);
             c_probe++;
-            bool in = exact;
-            if (!exact) {
-                c_fb++;
-                in = bloom_neighbor_contains(g, can) && !cfp_contains(g, can) && mphf_found(g, can);
-            }
-            int din = 0, dout = 0;
-            if (in) {
-                c_in++;
-                graph_degrees(g, fwd, exact, din, dout);
-                c_probe += 8;
-                if (!exact) c_fb += 8;
-            }
+            if (!exact) { c_fb++; if (in) { c_probe += 8; c_fb += 8; } }
+            if (in) c_in++;
             f = (uint8_t)((in ? 1 : 0) | (din << 1) | (dout << 4));
             K suffix = canonical<K>(fwd & m1, k - 1);
             K prefix = canonical<K>((fwd >> 2) & m1, k - 1);
@@ -359,6 +419,7 @@ template <class K> class Graph : public IGraph {
     uint64_t ncrit_ = 0;
     uint64_t ncfp_ = 0, nfinal_ = 0;
     bool cascading_ = true, mphf_built_ = false;
+    bool adj_done_ = false;   // adjacency bytes of the exact table written for the whole solid set
     DevBuf<unsigned long long> mphf_bits_;
     uint64_t mphf_off_[MPHF_LEVELS], mphf_dom_[MPHF_LEVELS];
     uint64_t mphf_seed_ = 0, seed0_ = 0;
@@ -428,7 +489,7 @@ public:
         bloom_.init(1000, 4, stream_);
         b2_.init(1000, 4, stream_); b3_.init(1000, 4, stream_); b4_.init(1000, 4, stream_);
         nbuckets_ = 1;
-        table_.alloc(BUCKET_BYTES / sizeof(K));
+        table_.alloc(TableCfg<K>::STRIDE);
         table_.fill_ff(stream_);
     }
     ~Graph() override { if (ev_a_) cudaEventDestroy(ev_a_); if (ev_b_) cudaEventDestroy(ev_b_); }
@@ -461,10 +522,13 @@ public:
         st_.nb_solid = N;
         // ---- exact table, load factor ~0.55, 128-byte buckets
         t.start();
-        const int SLOTS = BUCKET_BYTES / (int)sizeof(K);
+        const int SLOTS = TableCfg<K>::SLOTS;
         nbuckets_ = std::max<uint64_t>((uint64_t)((double)N / 0.55 / SLOTS) + 1, 1);
-        table_.alloc(nbuckets_ * SLOTS);
-        table_.fill_ff(stream_);
+        table_.alloc(nbuckets_ * TableCfg<K>::STRIDE);
+        table_.fill_ff(stream_);   // empty key slots; the 16 adjacency bytes of every bucket start at zero
+        MTG_CUDA(cudaMemset2DAsync(reinterpret_cast<uint8_t*>(table_.p) + BUCKET_ADJ_OFFSET, BUCKET_BYTES, 0, BUCKET_BYTES - BUCKET_ADJ_OFFSET,
+                                   nbuckets_, stream_));
+        adj_done_ = false;
         err_.zero(stream_);
         if (N) {
             table_build_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, table_.p, nbuckets_, err_.p);
@@ -512,7 +576,10 @@ public:
             MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 8, stream_));
             err_.zero(stream_);
             GraphView<K> g = view();
-            critical_kernel<K><<<grid_for(N * 2), 256, 0, stream_>>>(keys, N, g, set.p, slots, crit_list.p, counters_.p, cap, err_.p);
+            // the whole solid set in one call (single GPU): the same pass also writes the adjacency bytes
+            const bool with_adj = !adj_done_ && N == st_.nb_solid;
+            if (with_adj) critical_kernel<K, true, true><<<grid_for(N * 2), 256, 0, stream_>>>(keys, N, g, table_.p, set.p, slots, crit_list.p, counters_.p, cap, err_.p);
+            else critical_kernel<K, false, true><<<grid_for(N * 2), 256, 0, stream_>>>(keys, N, g, table_.p, set.p, slots, crit_list.p, counters_.p, cap, err_.p);
             MTG_CUDA(cudaGetLastError());
             st_.launches++;
             int e = 0;
@@ -520,7 +587,8 @@ public:
             MTG_CUDA(cudaMemcpyAsync(&e, err_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
             MTG_CUDA(cudaMemcpyAsync(&nc, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
             MTG_CUDA(cudaStreamSynchronize(stream_));
-            if (!e) { ncrit = nc; break; }
+            if (e == 4) throw Error(-6, "adjacency pass: solid k-mer missing from the exact table");
+            if (!e) { ncrit = nc; adj_done_ = adj_done_ || with_adj; break; }
             if (mult == 16) throw Error(-6, "critical false positive set overflow");
         }
         st_.ms_critical = t.stop();
@@ -560,6 +628,16 @@ public:
         const K* keys = (const K*)d_solid;
         EvTimer t(stream_);
         Trace tr(stream_);
+        if (!adj_done_ && N) {   // critical() only saw a share of the set (several GPUs): adjacency bytes of the whole replica
+            t.start();
+            err_.zero(stream_);
+            critical_kernel<K, true, false><<<grid_for(N * 2), 256, 0, stream_>>>(keys, N, view(), table_.p, nullptr, 0, nullptr, nullptr, 0, err_.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+            st_.ms_critical += t.stop();
+            check_err("adjacency pass");
+        }
+        adj_done_ = true;
         const float NBITS = bits_per_kmer(k_);
         const uint64_t ncrit = ncrit_;
         DevBuf<K>& crit_list = crit_list_;

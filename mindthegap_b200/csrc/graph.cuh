@@ -14,7 +14,7 @@ static const int MPHF_LEVELS = 25;  // BooPHF: _nb_levels = 25 (thirdparty/BooPH
 // POD view passed by value to kernels.
 template <class K> struct GraphView {
     int k;
-    // exact table: nbuckets buckets of 128 bytes (16 u64 keys or 8 u128 keys); empty slot = all ones
+    // exact table: nbuckets buckets of 128 bytes (14 u64 keys or 7 u128 keys + 16 adjacency bytes); empty slot = all ones
     const K* table;
     uint64_t nbuckets;
     // Bloom filters as little-endian u32 words (bit pos -> word pos>>5, bit pos&31 == byte pos>>3, bit pos&7)
@@ -177,34 +177,51 @@ template <class K> MTG_D bool mphf_found(const GraphView<K>& g, K x) {
     return sorted_contains(g.mphf_final, g.nfinal, x);
 }
 
-// Exact table probe by one thread: reads whole 128-byte buckets with 128-bit loads.
-template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key) {
-    const int SLOTS = BUCKET_BYTES / (int)sizeof(K);
-    uint64_t b = key_hash(key) % g.nbuckets;
-    const K EMPTY = ~K(0);
-    for (uint64_t probe = 0; probe < g.nbuckets; probe++) {
-        const uint4* q = reinterpret_cast<const uint4*>(g.table + b * SLOTS);
-        bool has_empty = false, found = false;
+// Exact table bucket = one 128-byte line: 112 bytes of key slots (14 u64 / 7 u128, empty = all ones) followed by 16
+// adjacency bytes, byte s = neighbours of the key in slot s that are in the graph, taking the stored (canonical) k-mer as
+// the forward string: bit nt = successor ((x<<2)+nt)&mask, bit 4+nt = predecessor (x>>2)+(nt<<2(k-1)). For solid k-mers
+// `contains` of a neighbour is plain set membership (derivation under row 16), so these 8 bits are what
+// countNeighbors_visitor (Graph.cpp:1466-1532) would find with its 8 contains() calls; they are written once, at build
+// time, by the kernel that visits the 8 neighbours of every solid k-mer anyway (critical_kernel).
+static const int BUCKET_KEY_BYTES = 112, BUCKET_ADJ_OFFSET = 112;
+template <class K> struct TableCfg { static const int SLOTS = BUCKET_KEY_BYTES / (int)sizeof(K), STRIDE = BUCKET_BYTES / (int)sizeof(K); };
+
+// Probe by one thread: the whole 128-byte bucket with eight 128-bit loads (one line, 4 sectors). Returns the slot of
+// `key` in [0, SLOTS) (and the bucket in *bucket_out) or -1; *adj receives the adjacency byte of the slot.
+template <class K> MTG_D int table_find(const K* __restrict__ table, uint64_t nbuckets, K key, uint64_t* bucket_out, unsigned* adj) {
+    uint64_t b = key_hash(key) % nbuckets;
+    for (uint64_t probe = 0; probe < nbuckets; probe++) {
+        const uint4* q = reinterpret_cast<const uint4*>(table + b * TableCfg<K>::STRIDE);
+        uint4 v[8];
 #pragma unroll
-        for (int i = 0; i < BUCKET_BYTES / 16; i++) {
-            uint4 v = __ldg(q + i);
+        for (int i = 0; i < 8; i++) v[i] = __ldg(q + i);
+        bool has_empty = false;
+        int slot = -1;
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            const uint64_t a0 = ((uint64_t)v[i].y << 32) | v[i].x, a1 = ((uint64_t)v[i].w << 32) | v[i].z;
             if (sizeof(K) == 8) {
-                uint64_t a0 = ((uint64_t)v.y << 32) | v.x, a1 = ((uint64_t)v.w << 32) | v.z;
-                found |= (a0 == lo64(key)) | (a1 == lo64(key));
+                if (a0 == lo64(key)) slot = 2 * i;
+                if (a1 == lo64(key)) slot = 2 * i + 1;
                 has_empty |= (a0 == ~0ull) | (a1 == ~0ull);
             } else {
-                uint64_t a0 = ((uint64_t)v.y << 32) | v.x, a1 = ((uint64_t)v.w << 32) | v.z;
-                found |= (a0 == lo64(key)) & (a1 == hi64(key));
+                if ((a0 == lo64(key)) & (a1 == hi64(key))) slot = i;
                 has_empty |= (a0 == ~0ull) & (a1 == ~0ull);
             }
         }
-        if (found) return true;
-        if (has_empty) return false;
-        b = b + 1 == g.nbuckets ? 0 : b + 1;
+        if (slot >= 0) {
+            const unsigned w = (slot >> 2) == 0 ? v[7].x : (slot >> 2) == 1 ? v[7].y : (slot >> 2) == 2 ? v[7].z : v[7].w;
+            if (adj) *adj = (w >> (8 * (slot & 3))) & 0xFFu;
+            if (bucket_out) *bucket_out = b;
+            return slot;
+        }
+        if (has_empty) return -1;
+        b = b + 1 == nbuckets ? 0 : b + 1;
     }
-    (void)EMPTY;
-    return false;
+    return -1;
 }
+template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key) { return table_find<K>(g.table, g.nbuckets, key, nullptr, nullptr) >= 0; }
+template <class K> MTG_D bool table_lookup(const GraphView<K>& g, K key, unsigned& adj) { return table_find<K>(g.table, g.nbuckets, key, nullptr, &adj) >= 0; }
 
 // Graph::contains for a CANONICAL k-mer. *used_fallback is set when the exact table missed and the Bloom emulation
 // had to answer (counted separately from the roofline probes).
@@ -230,6 +247,26 @@ template <class K> MTG_D void graph_degrees(const GraphView<K>& g, K graine, boo
         K f = ((graine >> 2) + ((K)nt << (2 * (g.k - 1)))) & mask;
         if (graph_contains(g, canonical(f, g.k), exact_only)) indeg++;
     }
+}
+
+// contains + degrees of the node whose forward-strand k-mer is `fwd`, with one bucket probe when its canonical k-mer is
+// solid (adjacency byte; the strand decides which nibble is "in"); everything else takes the emulation path.
+//   always_degrees: compute the degrees even when the node is not in the graph (observer probes ask for both).
+template <class K> MTG_D void node_probe(const GraphView<K>& g, K fwd, bool always_degrees, bool& in, bool& exact, int& din, int& dout) {
+    const K can = canonical(fwd, g.k);
+    unsigned adj = 0;
+    exact = table_lookup(g, can, adj);
+    din = dout = 0;
+    if (exact) {
+        in = true;
+        const int o = __popc(adj & 15u), i = __popc(adj >> 4);
+        const bool same = fwd == can;
+        dout = same ? o : i;
+        din = same ? i : o;
+        return;
+    }
+    in = bloom_neighbor_contains(g, can) && !cfp_contains(g, can) && mphf_found(g, can);
+    if (in || always_degrees) graph_degrees(g, fwd, false, din, dout);
 }
 
 // ------------------------------------------------------------------------------------------------ host class

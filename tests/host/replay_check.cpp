@@ -4,6 +4,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <chrono>
+
 #include "../../oracle/scan_oracle.hpp"
 #include "../../mindthegap_b200/csrc/replay.hpp"
 
@@ -47,7 +49,10 @@ template <class K> static int run(int argc, char** argv) {
     rb.build(refs, k, o.het_max_occ);
     const K m1 = kmask<K>(k - 1);
     uint64_t nprobe = 0;
+    double probe_ms = 0, scan_ms = 0;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     mtg::Replayer<K> rp(o, [&](const K* km, size_t n, uint8_t* ans) {
+        const double t0 = now();
         for (size_t i = 0; i < n; i++) {
             K x = km[i];
             bool c = g.contains(canonical<K>(x, k));
@@ -56,6 +61,7 @@ template <class K> static int run(int argc, char** argv) {
             ans[i] = (uint8_t)((c ? 1 : 0) | (din << 1) | (dout << 4) | (r ? 0x80 : 0));
         }
         nprobe += n;
+        probe_ms += now() - t0;
     });
     rp.segment_positions = seg;
     rp.skip_min = skip_min;
@@ -74,7 +80,9 @@ template <class K> static int run(int argc, char** argv) {
             }
             if (mtg::replay_interesting(feat[i], rep[i])) interest[i >> 5] |= 1u << (i & 31);
         });
+        const double t0 = now();
         rp.scan(rec.name, rec.seq.data(), rec.seq.size(), feat.data(), rep.data(), use_interest ? interest.data() : nullptr);
+        scan_ms += now() - t0;
     }
     FILE* f = fopen((out + ".breakpoints").c_str(), "wb");
     fwrite(rp.bkpt_out.data(), 1, rp.bkpt_out.size(), f);
@@ -85,6 +93,7 @@ template <class K> static int run(int argc, char** argv) {
     printf("observer_queries %llu\nprobe_batches %llu\nprefetched_queries %llu\nunforeseen_queries %llu\nprobe_fn_kmers %llu\n",
            (unsigned long long)rp.cnt.observer_queries, (unsigned long long)rp.cnt.probe_batches, (unsigned long long)rp.cnt.prefetched_queries,
            (unsigned long long)rp.cnt.unforeseen_queries, (unsigned long long)nprobe);
+    fprintf(stderr, "[replay_check] host replay %.3f ms (of which %.3f ms inside the probe callback)\n", scan_ms, probe_ms);
     return 0;
 }
 
