@@ -148,6 +148,10 @@ int mtg_replay_sequence(mtg_ctx* ctx, const char* name, const char* seq, uint64_
 const char* mtg_breakpoints_text(mtg_ctx* ctx, uint64_t* nbytes);
 const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes);
 int mtg_reset_outputs(mtg_ctx* ctx);
+/* -nb-cores (src/Finder.cpp:137, forwarded to Graph::create): host threads the event replay may use; the scan is cut at
+ * steady points of the gap machine and the chunks are replayed concurrently with byte-identical output (the reference's
+ * scan itself is single-threaded, src/Finder.cpp:597-600). 0 = all cores (the tool's default). */
+int mtg_set_host_threads(mtg_ctx* ctx, int32_t n);
 /* counters of Finder::resumeResults (src/Finder.cpp:470-511): homo_clean, homo_fuzzy, hetero_clean, hetero_fuzzy,
  * clean_deletion, fuzzy_deletion, solo_snp, multi_snp, backup, homo_indel, hetero_indel, observer_queries */
 int mtg_get_find_counters(mtg_ctx* ctx, uint64_t* out12);

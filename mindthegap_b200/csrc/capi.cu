@@ -137,9 +137,10 @@ struct mtg_ctx {
     uint64_t ref_repeated = 0;
     CountStats ref_count_stats;
     // replay
-    std::unique_ptr<Replayer<uint64_t>> rp64;
-    std::unique_ptr<Replayer<hu128>> rp128;
+    std::unique_ptr<ParallelReplayer<uint64_t>> rp64;
+    std::unique_ptr<ParallelReplayer<hu128>> rp128;
     PinnedBuf feat, rep, interest;
+    int host_threads = 0;  // 0 = all host cores (-nb-cores 0)
     double ms_features = 0, ms_replay = 0, ms_graph_build = 0;
     uint64_t scan_positions = 0, scan_valid = 0, scan_in_graph = 0, scan_table_probes = 0, scan_fallback = 0;
     std::vector<uint64_t> tmp_lo, tmp_hi;
@@ -183,15 +184,23 @@ static ReplayOptions replay_options(const mtg_params& p) {
 
 static void make_replayers(mtg_ctx* c) {
     ReplayOptions o = replay_options(c->p);
+    // The probe function may be called from a host-pool thread (unforeseen queries of a chunk; the replayer serialises
+    // those calls): select the context's device and stream there as an entry point would.
     if (c->p.kmer_size <= 31) {
-        c->rp64.reset(new Replayer<uint64_t>(o, [c](const uint64_t* km, size_t n, uint8_t* out) { c->graph->observer_probe_batch(km, nullptr, n, out); }));
+        c->rp64.reset(new ParallelReplayer<uint64_t>(o, [c](const uint64_t* km, size_t n, uint8_t* out) {
+            enter(c);
+            c->graph->observer_probe_batch(km, nullptr, n, out);
+        }));
     } else {
-        c->rp128.reset(new Replayer<hu128>(o, [c](const hu128* km, size_t n, uint8_t* out) {
+        c->rp128.reset(new ParallelReplayer<hu128>(o, [c](const hu128* km, size_t n, uint8_t* out) {
+            enter(c);
             c->tmp_lo.resize(n); c->tmp_hi.resize(n);
             for (size_t i = 0; i < n; i++) { c->tmp_lo[i] = (uint64_t)km[i]; c->tmp_hi[i] = (uint64_t)(km[i] >> 64); }
             c->graph->observer_probe_batch(c->tmp_lo.data(), c->tmp_hi.data(), n, out);
         }));
     }
+    if (c->rp64) c->rp64->set_threads(c->host_threads);
+    if (c->rp128) c->rp128->set_threads(c->host_threads);
 }
 
 extern "C" {
@@ -569,6 +578,13 @@ const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes) {
     const std::string& s = ctx->rp64 ? ctx->rp64->vcf_out : ctx->rp128->vcf_out;
     if (nbytes) *nbytes = s.size();
     return s.c_str();
+}
+int mtg_set_host_threads(mtg_ctx* ctx, int32_t n) {
+    MTG_TRY(ctx)
+    ctx->host_threads = n < 0 ? 0 : n;
+    if (ctx->rp64) ctx->rp64->set_threads(ctx->host_threads);
+    if (ctx->rp128) ctx->rp128->set_threads(ctx->host_threads);
+    MTG_CATCH
 }
 int mtg_reset_outputs(mtg_ctx* ctx) {
     MTG_TRY(ctx)

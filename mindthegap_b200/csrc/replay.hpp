@@ -21,10 +21,18 @@
 // kmer_begin_is_repeated is the flag of the first gap k-mer; right k-mers of fuzzy/hetero sites are raw reference text.
 #pragma once
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <exception>
 #include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace mtg {
@@ -70,20 +78,73 @@ public:
         for (size_t p0 = 0; p0 < npos; p0 += segment_positions) {
             const size_t p1 = std::min(npos, p0 + segment_positions);
             // collect pass on a scratch copy of the state, one batched GPU probe, then the real pass
-            Saved sv;
-            save(sv);
-            collecting_ = true;
-            calls_.clear(); log_keys_.clear();
-            run_range(p0, p1, feat, rep, interest);
-            collecting_ = false;
-            restore(sv);
-            log_ans_.resize(log_keys_.size());
-            if (!log_keys_.empty()) { probe_(log_keys_.data(), log_keys_.size(), log_ans_.data()); cnt.probe_batches++; cnt.prefetched_queries += log_keys_.size(); }
-            cursor_ = 0;
-            run_range(p0, p1, feat, rep, interest);
+            collect(p0, p1, feat, rep, interest);
+            ans_buf_.resize(log_keys_.size());
+            if (!log_keys_.empty()) { probe_(log_keys_.data(), log_keys_.size(), ans_buf_.data()); cnt.probe_batches++; cnt.prefetched_queries += log_keys_.size(); }
+            apply(p0, p1, feat, rep, interest, ans_buf_.data());
         }
-        calls_.clear(); log_keys_.clear(); log_ans_.clear();
+        calls_.clear(); log_keys_.clear(); ans_buf_.clear();
     }
+
+    // ---- building blocks of scan(), also used chunk-wise by ParallelReplayer
+    void begin_sequence(const std::string& name, const char* seq, size_t len) {
+        chrom = name; text = seq; text_len = len;
+        begin_valid = end_valid = false;
+        prev_valid = false;
+        solid_stretch = gap_stretch = 0;
+        memset(ring, 0, sizeof(ring));
+        end_idx = (unsigned char)(k + 1);
+        begin_idx = 1;
+        recent_hetero = 0;
+        pos = 0;
+        roll_fwd = 0;
+        for (int i = 0; i < k - 1 && (size_t)i < len; i++) roll_fwd = (roll_fwd << 2) | (K)code(seq[i]);
+    }
+    // Enter the sequence at position s, given that the `w` positions before s are all uninteresting (valid, in the graph,
+    // no hetero pre-condition) with w >= steady_window(): whatever happened before them, at s the gap machine is in its
+    // steady state (solid stretch >= 2, no open gap, recent_hetero decayed to 0) and the 256-entry ring holds exactly
+    // the infos of positions s-256 .. s-1 -- every observer reads the ring relative to begin_idx/end_idx, whose
+    // difference is always k, so their absolute values (and any earlier drift) are irrelevant. The begin/end k-mers are
+    // stale but unread: a gap entered from the steady state sets kmer_begin, its first solid k-mer sets kmer_end.
+    void begin_steady(const std::string& name, const char* seq, size_t len, size_t s, size_t w, const uint8_t* feat, const uint8_t* rep) {
+        begin_sequence(name, seq, len);
+        solid_stretch = 2; end_valid = true;
+        pos = s - w;
+        skip_run(s - w, s, feat, rep);
+    }
+    size_t steady_window() const { return 256 + 8 + (size_t)std::max(0, opt.max_repeat); }
+    // Collect pass over [p0, p1): leaves the enumerated k-mers in log_keys(); the state is untouched.
+    void collect(size_t p0, size_t p1, const uint8_t* feat, const uint8_t* rep, const uint32_t* interest) {
+        Saved sv;
+        save(sv);
+        collecting_ = true;
+        calls_.clear(); log_keys_.clear();
+        run_range(p0, p1, feat, rep, interest);
+        collecting_ = false;
+        restore(sv);
+    }
+    const std::vector<K>& log_keys() const { return log_keys_; }
+    // Real pass over [p0, p1) against the answers of the collected k-mers (same order as log_keys()).
+    void apply(size_t p0, size_t p1, const uint8_t* feat, const uint8_t* rep, const uint32_t* interest, const uint8_t* answers) {
+        log_ans_ = answers;
+        cursor_ = 0;
+        run_range(p0, p1, feat, rep, interest);
+    }
+    // Output records carry the shared `bkpt` id (src/FindBreakpoints.hpp:872-875); a chunk replayed on its own numbers
+    // from 1 and remembers where each id was printed so that the merge can renumber in reference order.
+    static size_t next_interesting(const uint32_t* bits, size_t p, size_t end) {
+        if (p >= end) return end;
+        size_t w = p >> 5;
+        uint32_t cur = bits[w] & (0xFFFFFFFFu << (p & 31));
+        const size_t wend = (end + 31) >> 5;
+        while (true) {
+            if (cur) { size_t q = (w << 5) + (size_t)__builtin_ctz(cur); return q < end ? q : end; }
+            if (++w >= wend) return end;
+            cur = bits[w];
+        }
+    }
+    struct IdPatch { size_t off; uint32_t ndigits; uint32_t id; };
+    std::vector<IdPatch> bk_ids, vcf_ids;
 
 private:
     struct Info { K kmer; int nb_in, nb_out; bool is_repeated; };
@@ -108,7 +169,8 @@ private:
     bool collecting_ = false;
     std::vector<LogCall> calls_;
     std::vector<K> log_keys_;
-    std::vector<uint8_t> log_ans_;
+    const uint8_t* log_ans_ = nullptr;
+    std::vector<uint8_t> ans_buf_;
     size_t cursor_ = 0;
     uint64_t loop_p_ = 0;  // position of the scan loop (monotonic, unlike `pos`)
 
@@ -141,31 +203,6 @@ private:
         cnt = v.cnt; cnt.probe_batches = batches; cnt.prefetched_queries = pre;
     }
 
-    void begin_sequence(const std::string& name, const char* seq, size_t len) {
-        chrom = name; text = seq; text_len = len;
-        begin_valid = end_valid = false;
-        prev_valid = false;
-        solid_stretch = gap_stretch = 0;
-        memset(ring, 0, sizeof(ring));
-        end_idx = (unsigned char)(k + 1);
-        begin_idx = 1;
-        recent_hetero = 0;
-        pos = 0;
-        roll_fwd = 0;
-        for (int i = 0; i < k - 1 && (size_t)i < len; i++) roll_fwd = (roll_fwd << 2) | (K)code(seq[i]);
-    }
-
-    static size_t next_interesting(const uint32_t* bits, size_t p, size_t end) {
-        if (p >= end) return end;
-        size_t w = p >> 5;
-        uint32_t cur = bits[w] & (0xFFFFFFFFu << (p & 31));
-        const size_t wend = (end + 31) >> 5;
-        while (true) {
-            if (cur) { size_t q = (w << 5) + (size_t)__builtin_ctz(cur); return q < end ? q : end; }
-            if (++w >= wend) return end;
-            cur = bits[w];
-        }
-    }
     K kmer_at(size_t p) const {
         K f = 0;
         for (int i = 0; i < k; i++) f = (f << 2) | (K)code(text[p + i]);
@@ -264,7 +301,7 @@ private:
         if (!n) return ans_.data();
         while (cursor_ < calls_.size() && calls_[cursor_].p < loop_p_) cursor_++;
         for (size_t c = cursor_; c < calls_.size() && calls_[c].p == loop_p_; c++)  // any call foreseen at this position
-            if (calls_[c].n == n && memcmp(&log_keys_[calls_[c].off], q.data(), n * sizeof(K)) == 0) return &log_ans_[calls_[c].off];
+            if (calls_[c].n == n && memcmp(&log_keys_[calls_[c].off], q.data(), n * sizeof(K)) == 0) return log_ans_ + calls_[c].off;
         ans_.resize(n);
         probe_(q.data(), n, ans_.data());
         cnt.probe_batches++; cnt.unforeseen_queries += n;
@@ -281,24 +318,42 @@ private:
     }
 
     // ---- writers (src/FindBreakpoints.hpp:641-702)
+    static uint32_t ndigits(uint64_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; n++; } return n; }
     void write_breakpoint(const std::string& chrom_name, uint64_t p, const std::string& kb, const std::string& ke, int repeat, const char* type,
                           bool rep_b = false, bool rep_e = false) {
         if (collecting_) return;
-        char hdr[1200];
+        char num[96];
         for (int side = 0; side < 2; side++) {
-            snprintf(hdr, sizeof hdr, ">bkpt%i_%s_pos_%lli_fuzzy_%i_%s %s %s\n", (int)next_id, chrom_name.c_str(), (long long)(p + 1), repeat, type,
-                     (side == 0 ? rep_b : rep_e) ? "REPEATED" : "", side == 0 ? "left_kmer" : "right_kmer");
-            bkpt_out += hdr;
+            bkpt_out += ">bkpt";
+            bk_ids.push_back({bkpt_out.size(), ndigits((uint64_t)(int)next_id), (uint32_t)next_id});
+            snprintf(num, sizeof num, "%i_", (int)next_id);
+            bkpt_out += num;
+            bkpt_out += chrom_name;
+            snprintf(num, sizeof num, "_pos_%lli_fuzzy_%i_", (long long)(p + 1), repeat);
+            bkpt_out += num;
+            bkpt_out += type;
+            bkpt_out += ' ';
+            if (side == 0 ? rep_b : rep_e) bkpt_out += "REPEATED";
+            bkpt_out += side == 0 ? " left_kmer\n" : " right_kmer\n";
             bkpt_out += side == 0 ? kb : ke;
             bkpt_out += '\n';
         }
+    }
+    void vcf_prefix(uint64_t p) {  // "<chrom>\t<pos>\tbkpt<id>\t"
+        char buf[64];
+        vcf_out += chrom;
+        snprintf(buf, sizeof buf, "\t%lli\tbkpt", (long long)(p + 1));
+        vcf_out += buf;
+        vcf_ids.push_back({vcf_out.size(), ndigits((uint64_t)(int)next_id), (uint32_t)next_id});
+        snprintf(buf, sizeof buf, "%i\t", (int)next_id);
+        vcf_out += buf;
     }
     void write_vcf(uint64_t p, const std::string& ref, const std::string& alt, int repeat, const char* type) {
         if (collecting_) return;
         int variant_size = strcmp(type, "DEL") == 0 ? (int)ref.size() - 1 : 1;
         char buf[1200];
-        snprintf(buf, sizeof buf, "%s\t%lli\tbkpt%i\t", chrom.c_str(), (long long)(p + 1), (int)next_id);
-        vcf_out += buf; vcf_out += ref; vcf_out += '\t'; vcf_out += alt;
+        vcf_prefix(p);
+        vcf_out += ref; vcf_out += '\t'; vcf_out += alt;
         snprintf(buf, sizeof buf, "\t.\tPASS\tTYPE=%s;LEN=%i;FUZZY=%i\tGT\t1/1\n", type, variant_size, repeat);
         vcf_out += buf;
     }
@@ -306,8 +361,8 @@ private:
         if (collecting_) return;
         const char* gt = !strcmp(type, "HOM") ? "1/1" : (!strcmp(type, "HET") ? "0/1" : "./.");
         char buf[1200];
-        snprintf(buf, sizeof buf, "%s\t%lli\tbkpt%i\t", chrom.c_str(), (long long)(p + 1), (int)next_id);
-        vcf_out += buf; vcf_out += ref; vcf_out += '\t'; vcf_out += alt;
+        vcf_prefix(p);
+        vcf_out += ref; vcf_out += '\t'; vcf_out += alt;
         snprintf(buf, sizeof buf, "\t.\tPASS\tTYPE=INS;LEN=%i;FUZZY=%i\tGT\t%s\n", (int)alt.size() - 1, repeat, gt);
         vcf_out += buf;
     }
@@ -317,9 +372,21 @@ private:
     // walk the k-mers in order until the first miss; success iff at least k k-mers were contained.
     bool micro_assembly(const std::string& kb, const std::string& ke, std::string& ins) {
         static const char* nucleo[20] = {"A", "C", "G", "T", "AA", "AC", "AG", "AT", "CA", "CC", "CG", "CT", "GA", "GC", "GG", "GT", "TA", "TC", "TG", "TT"};
-        std::vector<K> q;
+        // k-mers of kb + candidate + ke, rolled from kb (both flanks are k nucleotides, validated by the callers)
+        std::vector<K>& q = ma_q_;
+        q.clear();
+        q.reserve(20 * (size_t)(k + 3));
         size_t start[21];
-        for (int a = 0; a < 20; a++) { start[a] = q.size(); kmers_of(kb + nucleo[a] + ke, q); }
+        K kbv = 0;
+        for (int i = 0; i < k; i++) kbv = (kbv << 2) | (K)code(kb[i]);
+        const size_t ne = std::min(ke.size(), (size_t)k);
+        for (int a = 0; a < 20; a++) {
+            start[a] = q.size();
+            K f = kbv;
+            q.push_back(f);
+            for (const char* c = nucleo[a]; *c; c++) { f = ((f << 2) | (K)code(*c)) & mask_; q.push_back(f); }
+            for (size_t i = 0; i < ne; i++) { f = ((f << 2) | (K)code(ke[i])) & mask_; q.push_back(f); }
+        }
         start[20] = q.size();
         const uint8_t* ans = probe(q);
         for (int a = 0; a < 20; a++) {
@@ -329,6 +396,7 @@ private:
         }
         return false;
     }
+    std::vector<K> ma_q_;
 
     // ---- SNP walk (FindSNP::snp_at_end / snp_at_begin, src/FindSNP.hpp:133-293). The 3*k mutated k-mers are probed in
     // one batch; the elimination loop (std::map iterated in numeric nucleotide order) is then replayed on the answers.
@@ -610,6 +678,194 @@ private:
             solid_stretch = 0;
         }
     }
+};
+
+// ------------------------------------------------------------------------------------------------ host worker pool
+// Process-wide, created on first use (a context that never scans a long sequence never starts a thread).
+class HostPool {
+public:
+    static HostPool& instance() { static HostPool p; return p; }
+    int size() const { return (int)workers_.size() + 1; }
+    // fn(i) for i in [0, n), on up to `max_threads` threads including the caller; returns when all are done
+    void parallel_for(size_t n, int max_threads, const std::function<void(size_t)>& fn) {
+        if (n == 0) return;
+        if (n == 1 || max_threads <= 1 || workers_.empty()) { for (size_t i = 0; i < n; i++) fn(i); return; }
+        std::unique_lock<std::mutex> job_lock(job_mu_);  // one job at a time
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; n_ = n; next_.store(0); pending_ = 0; error_ = nullptr;
+            helpers_ = std::min<size_t>({(size_t)max_threads - 1, workers_.size(), n - 1});
+            pending_ = helpers_;
+            generation_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+        if (error_) std::rethrow_exception(error_);
+    }
+private:
+    HostPool() {
+        int n = (int)std::thread::hardware_concurrency();
+        if (const char* e = getenv("MTG_HOST_THREADS")) n = atoi(e);
+        n = std::max(1, std::min(n, 64));
+        for (int i = 1; i < n; i++) workers_.emplace_back([this, i] { loop(i); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; generation_++; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void work() {
+        try {
+            for (size_t i = next_.fetch_add(1); i < n_; i = next_.fetch_add(1)) (*fn_)(i);
+        } catch (...) {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (!error_) error_ = std::current_exception();
+            next_.store(n_);
+        }
+    }
+    void loop(int id) {
+        uint64_t seen = 0;
+        while (true) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (stop_) return;
+                if ((size_t)id > helpers_) continue;  // this job wants fewer threads
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                pending_--;
+            }
+            done_cv_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, job_mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(size_t)>* fn_ = nullptr;
+    size_t n_ = 0, helpers_ = 0, pending_ = 0;
+    std::atomic<size_t> next_{0};
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+    std::exception_ptr error_;
+};
+
+// ------------------------------------------------------------------------------------------------ chunked replay
+// The scan of one sequence is cut at *steady points* -- positions preceded by at least steady_window() uninteresting
+// positions -- where the state of the reference's sequential scan is a function of the preceding 256 positions only
+// (Replayer::begin_steady). Chunks are replayed independently on the host pool: collect passes in parallel, ONE batched
+// GPU probe for all chunks of a batch, real passes in parallel, then texts and counters are merged in reference order
+// and the shared bkpt ids renumbered. The output is byte-identical to the sequential replay (tests/test_host_replay.py).
+template <class K> class ParallelReplayer {
+public:
+    ParallelReplayer(const ReplayOptions& o, ProbeFn<K> probe, int nthreads = 0) : opt_(o), probe_(probe), nthreads_(nthreads) {
+        // unforeseen queries of concurrent chunks share the caller's probe function
+        locked_probe_ = [this](const K* km, size_t n, uint8_t* out) { std::lock_guard<std::mutex> lk(probe_mu_); probe_(km, n, out); };
+    }
+    std::string bkpt_out, vcf_out;
+    ReplayCounters cnt;
+    uint64_t next_id = 1;
+    size_t segment_positions = (size_t)1 << 26;  // positions per batch (bounds the probe log)
+    size_t chunk_positions = (size_t)1 << 17;    // target chunk length
+    size_t skip_min = 512;
+    void set_threads(int n) { nthreads_ = n; }  // 0 = every thread of the host pool
+    uint64_t nb_chunks = 0;                      // chunks replayed so far (statistics)
+
+    void scan(const std::string& name, const char* seq, size_t len, const uint8_t* feat, const uint8_t* rep, const uint32_t* interest = nullptr) {
+        const int k = opt_.k;
+        if (len < (size_t)k) return;
+        const size_t npos = len - k + 1;
+        int nt = nthreads_ > 0 ? nthreads_ : HostPool::instance().size();
+        // chunk boundaries
+        std::vector<size_t> cut{0};
+        Replayer<K> probe_only(opt_, locked_probe_);
+        const size_t w = probe_only.steady_window();
+        if (interest && npos >= 2 * chunk_positions) {
+            size_t target = chunk_positions;
+            while (target < npos) {
+                // first run of >= w uninteresting positions starting at or after `target`
+                size_t q0 = target, s = npos;
+                while (q0 + w < npos) {
+                    const size_t q1 = Replayer<K>::next_interesting(interest, q0, npos);
+                    if (q1 - q0 >= w) { s = q0 + w; break; }
+                    q0 = q1 + 1;
+                }
+                if (s >= npos) break;
+                cut.push_back(s);
+                target = s + chunk_positions;
+            }
+        }
+        cut.push_back(npos);
+        const size_t nchunks = cut.size() - 1;
+        nb_chunks += nchunks;
+        if (nchunks == 1) nt = 1;
+        // batches of chunks
+        for (size_t c0 = 0; c0 < nchunks;) {
+            size_t c1 = c0 + 1;
+            while (c1 < nchunks && cut[c1 + 1] - cut[c0] <= segment_positions) c1++;
+            const size_t nc = c1 - c0;
+            std::vector<std::unique_ptr<Replayer<K>>> rp(nc);
+            std::vector<size_t> off(nc + 1, 0);
+            HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
+                rp[i].reset(new Replayer<K>(opt_, locked_probe_));
+                Replayer<K>& r = *rp[i];
+                r.skip_min = skip_min;
+                const size_t s = cut[c0 + i];
+                if (s == 0) r.begin_sequence(name, seq, len); else r.begin_steady(name, seq, len, s, w, feat, rep);
+                r.collect(s, cut[c0 + i + 1], feat, rep, interest);
+            });
+            for (size_t i = 0; i < nc; i++) off[i + 1] = off[i] + rp[i]->log_keys().size();
+            keys_.resize(off[nc]); ans_.resize(off[nc]);
+            if (nc > 1)
+                HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
+                    const std::vector<K>& lk = rp[i]->log_keys();
+                    if (!lk.empty()) memcpy(&keys_[off[i]], lk.data(), lk.size() * sizeof(K));
+                });
+            const K* kp = nc > 1 ? keys_.data() : rp[0]->log_keys().data();
+            if (off[nc]) { probe_(kp, off[nc], ans_.data()); cnt.probe_batches++; cnt.prefetched_queries += off[nc]; }
+            HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
+                rp[i]->apply(cut[c0 + i], cut[c0 + i + 1], feat, rep, interest, ans_.data() + off[i]);
+            });
+            for (size_t i = 0; i < nc; i++) merge(*rp[i]);
+            c0 = c1;
+        }
+    }
+
+private:
+    static void append_renumbered(std::string& dst, const std::string& src, const std::vector<typename Replayer<K>::IdPatch>& ids, uint64_t base) {
+        if (base == 0) { dst += src; return; }
+        size_t at = 0;
+        char num[32];
+        for (const auto& pt : ids) {
+            dst.append(src, at, pt.off - at);
+            snprintf(num, sizeof num, "%i", (int)(pt.id + base));
+            dst += num;
+            at = pt.off + pt.ndigits;
+        }
+        dst.append(src, at, std::string::npos);
+    }
+    void merge(Replayer<K>& r) {
+        const uint64_t base = next_id - 1;
+        append_renumbered(bkpt_out, r.bkpt_out, r.bk_ids, base);
+        append_renumbered(vcf_out, r.vcf_out, r.vcf_ids, base);
+        next_id += r.next_id - 1;
+        const ReplayCounters& c = r.cnt;
+        cnt.homo_clean += c.homo_clean; cnt.homo_fuzzy += c.homo_fuzzy; cnt.hetero_clean += c.hetero_clean; cnt.hetero_fuzzy += c.hetero_fuzzy;
+        cnt.clean_deletion += c.clean_deletion; cnt.fuzzy_deletion += c.fuzzy_deletion; cnt.solo_snp += c.solo_snp; cnt.multi_snp += c.multi_snp;
+        cnt.backup += c.backup; cnt.homo_indel += c.homo_indel; cnt.hetero_indel += c.hetero_indel; cnt.observer_queries += c.observer_queries;
+        cnt.probe_batches += c.probe_batches; cnt.prefetched_queries += c.prefetched_queries; cnt.unforeseen_queries += c.unforeseen_queries;
+    }
+    ReplayOptions opt_;
+    ProbeFn<K> probe_, locked_probe_;
+    std::mutex probe_mu_;
+    int nthreads_;
+    std::vector<K> keys_;
+    std::vector<uint8_t> ans_;
 };
 
 }  // namespace mtg

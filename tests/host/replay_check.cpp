@@ -5,6 +5,8 @@
 #include <stdlib.h>
 
 #include <chrono>
+#include <mutex>
+#include <unordered_map>
 
 #include "../../oracle/scan_oracle.hpp"
 #include "../../mindthegap_b200/csrc/replay.hpp"
@@ -17,6 +19,9 @@ template <class K> static int run(int argc, char** argv) {
     std::string amin = "auto";
     size_t seg = (size_t)1 << 22, skip_min = 512;
     bool use_interest = true;
+    std::string dump, load;
+    int threads = 1, repeat = 1;
+    size_t chunk = 0;
     unsigned flags = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -32,67 +37,124 @@ template <class K> static int run(int argc, char** argv) {
         else if (a == "-seg") seg = (size_t)atoll(val().c_str());
         else if (a == "-skip-min") skip_min = (size_t)atoll(val().c_str());
         else if (a == "-no-interest") use_interest = false;
+        else if (a == "-dump") dump = val();   // write features + every probe answer (profiling aid)
+        else if (a == "-load") load = val();   // replay from such a dump: no counting, no graph
+        else if (a == "-threads") threads = atoi(val().c_str());
+        else if (a == "-repeat") repeat = atoi(val().c_str());
+        else if (a == "-chunk") chunk = (size_t)atoll(val().c_str());
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
     }
     o.homo_only = flags & 1; o.homo_insert = flags & 2; o.hete_insert = flags & 4; o.snp = flags & 8; o.backup = flags & 16;
     o.deletion = flags & 32; o.small_homo = flags & 64;
     const int k = o.k;
     std::vector<SeqRecord> reads, refs;
-    if (!load_bank(in, reads) || !load_bank(ref, refs)) { fprintf(stderr, "cannot read inputs\n"); return 1; }
-    CountResult<K> cr;
-    count_bank<K>(reads, k, amin == "auto" ? -1 : atoi(amin.c_str()), 2147483647LL, cr);
-    std::vector<K> solid;
-    for (auto& kc : cr.solid) solid.push_back(kc.value);
+    if (!load_bank(ref, refs)) { fprintf(stderr, "cannot read the reference\n"); return 1; }
     GraphOracle<K> g;
-    g.build(solid, k);
     RefBloom<K> rb;
-    rb.build(refs, k, o.het_max_occ);
+    std::vector<uint64_t> flat_keys; std::vector<uint8_t> flat_vals;
+    std::unordered_map<uint64_t, uint8_t> memo;  // -dump / -load: probe answers by k-mer (k <= 31 only)
+    if (load.empty()) {
+        if (!load_bank(in, reads)) { fprintf(stderr, "cannot read inputs\n"); return 1; }
+        CountResult<K> cr;
+        count_bank<K>(reads, k, amin == "auto" ? -1 : atoi(amin.c_str()), 2147483647LL, cr);
+        std::vector<K> solid;
+        for (auto& kc : cr.solid) solid.push_back(kc.value);
+        g.build(solid, k);
+        rb.build(refs, k, o.het_max_occ);
+    } else {
+        FILE* f = fopen((load + ".memo").c_str(), "rb");
+        uint64_t key; uint8_t a;
+        while (f && fread(&key, 8, 1, f) == 1 && fread(&a, 1, 1, f) == 1) memo[key] = a;
+        if (f) fclose(f);
+        size_t cap = 16; while (cap < memo.size() * 4) cap <<= 1;
+        flat_keys.assign(cap, ~0ull); flat_vals.assign(cap, 0);
+        for (auto& kv : memo) { size_t h = (kv.first * 0x9E3779B97F4A7C15ull) >> 20 & (cap - 1); while (flat_keys[h] != ~0ull) h = (h + 1) & (cap - 1); flat_keys[h] = kv.first; flat_vals[h] = kv.second; }
+    }
     const K m1 = kmask<K>(k - 1);
     uint64_t nprobe = 0;
     double probe_ms = 0, scan_ms = 0;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    mtg::Replayer<K> rp(o, [&](const K* km, size_t n, uint8_t* ans) {
+    std::mutex mu;
+    mtg::ProbeFn<K> probe_fn = [&](const K* km, size_t n, uint8_t* ans) {
+        std::lock_guard<std::mutex> lock(mu);
         const double t0 = now();
         for (size_t i = 0; i < n; i++) {
             K x = km[i];
+            if (!load.empty()) {
+                const size_t cap = flat_keys.size();
+                size_t h = ((uint64_t)x * 0x9E3779B97F4A7C15ull) >> 20 & (cap - 1);
+                while (flat_keys[h] != (uint64_t)x) { if (flat_keys[h] == ~0ull) { fprintf(stderr, "k-mer not in the dump\n"); exit(2); } h = (h + 1) & (cap - 1); }
+                ans[i] = flat_vals[h];
+                continue;
+            }
             bool c = g.contains(canonical<K>(x, k));
             int din = g.indegree(x), dout = g.outdegree(x);
             bool r = rb.contains(canonical<K>(x & m1, k - 1));
             ans[i] = (uint8_t)((c ? 1 : 0) | (din << 1) | (dout << 4) | (r ? 0x80 : 0));
+            if (!dump.empty()) memo[(uint64_t)x] = ans[i];
         }
         nprobe += n;
         probe_ms += now() - t0;
-    });
-    rp.segment_positions = seg;
-    rp.skip_min = skip_min;
-    for (auto& rec : refs) {
-        if (rec.seq.size() < (size_t)k) continue;
-        const size_t npos = rec.seq.size() - k + 1;
-        std::vector<uint8_t> feat(npos), rep(npos);
-        std::vector<uint32_t> interest((npos + 31) / 32 + 1, 0);
-        iterate_kmers<K>(rec.seq.data(), rec.seq.size(), k, [&](const KmerCanon<K>& km, size_t i) {
-            if (!km.valid) { feat[i] = 0x80; rep[i] = 0; }
-            else {
-                bool inn = g.contains(km.value());
-                int din = inn ? g.indegree(km.fwd) : 0, dout = inn ? g.outdegree(km.fwd) : 0;
-                feat[i] = (uint8_t)((inn ? 1 : 0) | (din << 1) | (dout << 4));
-                rep[i] = (uint8_t)((rb.contains(canonical<K>(km.fwd & m1, k - 1)) ? 1 : 0) | (rb.contains(canonical<K>((km.fwd >> 2) & m1, k - 1)) ? 2 : 0));
+    };
+    std::string bk_text, vcf_text;
+    mtg::ReplayCounters cnt;
+    uint64_t nchunks = 0;
+    for (int it = 0; it < repeat; it++) {
+        mtg::ParallelReplayer<K> rp(o, probe_fn, threads);
+        rp.segment_positions = seg;
+        rp.skip_min = skip_min;
+        if (chunk) rp.chunk_positions = chunk;
+        size_t si = 0;
+        for (auto& rec : refs) {
+            if (rec.seq.size() < (size_t)k) continue;
+            const size_t npos = rec.seq.size() - k + 1;
+            std::vector<uint8_t> feat(npos), rep(npos);
+            std::vector<uint32_t> interest((npos + 31) / 32 + 1, 0);
+            const std::string fn = (load.empty() ? dump : load) + ".feat" + std::to_string(si++);
+            if (!load.empty()) {
+                FILE* f = fopen(fn.c_str(), "rb");
+                if (!f || fread(feat.data(), 1, npos, f) != npos || fread(rep.data(), 1, npos, f) != npos) { fprintf(stderr, "bad dump\n"); return 1; }
+                fclose(f);
+                for (size_t i = 0; i < npos; i++) if (mtg::replay_interesting(feat[i], rep[i])) interest[i >> 5] |= 1u << (i & 31);
+            } else {
+                iterate_kmers<K>(rec.seq.data(), rec.seq.size(), k, [&](const KmerCanon<K>& km, size_t i) {
+                    if (!km.valid) { feat[i] = 0x80; rep[i] = 0; }
+                    else {
+                        bool inn = g.contains(km.value());
+                        int din = inn ? g.indegree(km.fwd) : 0, dout = inn ? g.outdegree(km.fwd) : 0;
+                        feat[i] = (uint8_t)((inn ? 1 : 0) | (din << 1) | (dout << 4));
+                        rep[i] = (uint8_t)((rb.contains(canonical<K>(km.fwd & m1, k - 1)) ? 1 : 0) | (rb.contains(canonical<K>((km.fwd >> 2) & m1, k - 1)) ? 2 : 0));
+                    }
+                    if (mtg::replay_interesting(feat[i], rep[i])) interest[i >> 5] |= 1u << (i & 31);
+                });
+                if (!dump.empty()) {
+                    FILE* f = fopen(fn.c_str(), "wb");
+                    fwrite(feat.data(), 1, npos, f); fwrite(rep.data(), 1, npos, f);
+                    fclose(f);
+                }
             }
-            if (mtg::replay_interesting(feat[i], rep[i])) interest[i >> 5] |= 1u << (i & 31);
-        });
-        const double t0 = now();
-        rp.scan(rec.name, rec.seq.data(), rec.seq.size(), feat.data(), rep.data(), use_interest ? interest.data() : nullptr);
-        scan_ms += now() - t0;
+            const double t0 = now();
+            rp.scan(rec.name, rec.seq.data(), rec.seq.size(), feat.data(), rep.data(), use_interest ? interest.data() : nullptr);
+            scan_ms += now() - t0;
+        }
+        bk_text = rp.bkpt_out; vcf_text = rp.vcf_out; cnt = rp.cnt; nchunks = rp.nb_chunks;
     }
+    if (!dump.empty()) {
+        FILE* f = fopen((dump + ".memo").c_str(), "wb");
+        for (auto& kv : memo) { fwrite(&kv.first, 8, 1, f); fwrite(&kv.second, 1, 1, f); }
+        fclose(f);
+    }
+    scan_ms /= repeat; probe_ms /= repeat; nprobe /= repeat;
     FILE* f = fopen((out + ".breakpoints").c_str(), "wb");
-    fwrite(rp.bkpt_out.data(), 1, rp.bkpt_out.size(), f);
+    fwrite(bk_text.data(), 1, bk_text.size(), f);
     fclose(f);
     f = fopen((out + ".vcf").c_str(), "wb");
-    fwrite(rp.vcf_out.data(), 1, rp.vcf_out.size(), f);
+    fwrite(vcf_text.data(), 1, vcf_text.size(), f);
     fclose(f);
+    printf("chunks %llu\n", (unsigned long long)nchunks);
     printf("observer_queries %llu\nprobe_batches %llu\nprefetched_queries %llu\nunforeseen_queries %llu\nprobe_fn_kmers %llu\n",
-           (unsigned long long)rp.cnt.observer_queries, (unsigned long long)rp.cnt.probe_batches, (unsigned long long)rp.cnt.prefetched_queries,
-           (unsigned long long)rp.cnt.unforeseen_queries, (unsigned long long)nprobe);
+           (unsigned long long)cnt.observer_queries, (unsigned long long)cnt.probe_batches, (unsigned long long)cnt.prefetched_queries,
+           (unsigned long long)cnt.unforeseen_queries, (unsigned long long)nprobe);
     fprintf(stderr, "[replay_check] host replay %.3f ms (of which %.3f ms inside the probe callback)\n", scan_ms, probe_ms);
     return 0;
 }

@@ -18,7 +18,7 @@ def replay_check():
     deps = [src, os.path.join(ROOT, "mindthegap_b200", "csrc", "replay.hpp")] + [
         os.path.join(ROOT, "oracle", f) for f in ("scan_oracle.hpp", "graph_oracle.hpp", "kmer_oracle.hpp")]
     if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-o", EXE, src], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", EXE, src], check=True)
     return EXE
 
 
@@ -36,7 +36,9 @@ def run(exe, name, tmp_path, extra):
     return open(out + ".breakpoints").read(), open(out + ".vcf").read(), {k: int(v) for k, v in info.items()}
 
 
-MODES = {"default": [], "tiny_segments": ["-seg", "777", "-skip-min", "1"], "walk_everything": ["-no-interest"]}
+MODES = {"default": [], "tiny_segments": ["-seg", "777", "-skip-min", "1"], "walk_everything": ["-no-interest"],
+         # chunked replay: cut at every steady point at least 64 positions after the previous cut, 4 host threads
+         "parallel_chunks": ["-chunk", "64", "-threads", "4"], "parallel_chunks_1thread": ["-chunk", "1000", "-threads", "1", "-skip-min", "8"]}
 
 
 @pytest.mark.parametrize("mode", sorted(MODES))
@@ -54,3 +56,11 @@ def test_collect_pass_foresees_most_queries(replay_check, tmp_path):
         _, _, info = run(replay_check, name, tmp_path, [])
         assert info["observer_queries"] > 0
         assert info["unforeseen_queries"] <= 0.2 * info["observer_queries"], info
+
+
+def test_chunked_replay_really_cuts(replay_check, tmp_path):
+    """The parallel modes above must exercise more than one chunk per sequence (cuts at steady points of the gap machine)."""
+    _, _, one = run(replay_check, "syn_small_k31", tmp_path, [])
+    _, _, many = run(replay_check, "syn_small_k31", tmp_path, MODES["parallel_chunks"])
+    assert one["chunks"] <= 4 and many["chunks"] > 50, (one, many)
+    assert one["observer_queries"] == many["observer_queries"]
