@@ -55,6 +55,12 @@ const char* mtg_version(void);
  *      (G/debruijn/impl/Graph.cpp:285-422: ConfigurationAlgorithm, RepartitorAlgorithm, SortingCountAlgorithm).
  * Reads are pushed as ASCII bases; sequences are separated by any byte outside ACGTacgt (e.g. '\n').          */
 int mtg_count_reserve(mtg_ctx* ctx, uint64_t nb_bases);
+/* Partitioning minimizer length (G/kmer/impl/Model.hpp:989-1326 role; Finder forces 10, src/Finder.cpp:246). It never
+ * changes the counts. By default the engine keeps mtg_params.minimizer_size below 2^30 pushed/reserved bases and uses 13
+ * above (flatter bins); forcing it is only needed when several GPUs count one read set (all must agree). Call before the
+ * first push. */
+int mtg_set_minimizer_size(mtg_ctx* ctx, int32_t m);
+int32_t mtg_get_minimizer_size(mtg_ctx* ctx);
 int mtg_push_reads(mtg_ctx* ctx, const char* bases, uint64_t nbytes);              /* host buffer   */
 int mtg_push_reads_device(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes);     /* device buffer */
 /* Convenience host-side parser: FASTA/FASTQ files, comma separated list (Bank::open, G/bank/impl/Bank.cpp:49-52,

@@ -40,7 +40,7 @@ EXPORTS = [
     "mtg_scan_reference", "mtg_scan_reference_device", "mtg_set_reference_device", "mtg_breakpoints_text", "mtg_vcf_text", "mtg_reset_outputs", "mtg_get_find_counters", "mtg_copy_bits",
     "mtg_bench_random_gather", "mtg_count_local_info", "mtg_count_copy_packed", "mtg_count_partition_records", "mtg_count_import",
     "mtg_count_run", "mtg_count_filter", "mtg_solid_copy", "mtg_graph_build_device", "mtg_sequence_features_device2", "mtg_replay_sequence",
-    "mtg_graph_build_begin", "mtg_graph_critical", "mtg_graph_critical_copy", "mtg_graph_build_end",
+    "mtg_graph_build_begin", "mtg_graph_critical", "mtg_graph_critical_copy", "mtg_graph_build_end", "mtg_set_host_threads", "mtg_set_minimizer_size", "mtg_get_minimizer_size",
 ]
 
 _lib = None
@@ -95,6 +95,10 @@ def load_library():
     L.mtg_vcf_text.restype = vp
     L.mtg_vcf_text.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mtg_reset_outputs.argtypes = [vp]
+    L.mtg_set_host_threads.argtypes = [vp, C.c_int32]
+    L.mtg_set_minimizer_size.argtypes = [vp, C.c_int32]
+    L.mtg_get_minimizer_size.argtypes = [vp]
+    L.mtg_get_minimizer_size.restype = C.c_int32
     L.mtg_get_find_counters.argtypes = [vp, u64p]
     L.mtg_copy_bits.restype = C.c_int64
     L.mtg_copy_bits.argtypes = [vp, C.c_int, vp, C.c_uint64]
@@ -302,6 +306,14 @@ class Finder:
 
     def reset_outputs(self):
         self._check(self.L.mtg_reset_outputs(self.ctx))
+
+    def set_minimizer_size(self, m):
+        """Force the partitioning minimizer length (all GPUs of one find must agree); before the first push."""
+        self._check(self.L.mtg_set_minimizer_size(self.ctx, int(m)))
+
+    def set_host_threads(self, n):
+        """-nb-cores: host threads of the chunked event replay (0 = all cores)."""
+        self._check(self.L.mtg_set_host_threads(self.ctx, int(n)))
 
     def find_counters(self):
         o = np.zeros(12, dtype=np.uint64)

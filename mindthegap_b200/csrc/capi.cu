@@ -256,6 +256,8 @@ static ICounter* reads_counter(mtg_ctx* ctx) {
 }
 
 int mtg_count_reserve(mtg_ctx* ctx, uint64_t nb_bases) { MTG_TRY(ctx) reads_counter(ctx)->reserve(nb_bases); MTG_CATCH }
+int mtg_set_minimizer_size(mtg_ctx* ctx, int32_t m) { MTG_TRY(ctx) reads_counter(ctx)->set_minimizer(m); ctx->p.minimizer_size = m; MTG_CATCH }
+int32_t mtg_get_minimizer_size(mtg_ctx* ctx) { return ctx ? (ctx->counter ? ctx->counter->minimizer() : ctx->p.minimizer_size) : -1; }
 int mtg_push_reads(mtg_ctx* ctx, const char* bases, uint64_t nbytes) {
     MTG_TRY(ctx) WallTimer w(ctx->wall_push); reads_counter(ctx)->push_host(bases, nbytes); MTG_CATCH
 }

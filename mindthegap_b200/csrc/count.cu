@@ -116,6 +116,7 @@ static const int SK_TILE = 2048;      // positions per CTA tile
 static const int SK_THREADS = 256;
 static const int SK_PER = SK_TILE / SK_THREADS;  // 8 consecutive positions per thread
 static const int SK_HALO = 64;        // m-mer positions computed past the tile (>= k - m)
+static const int SK_MAX_M = 15;       // 2m <= 31 bits of m-mer
 static const int SK_MAXRUN = 32;      // max k-mers per record (6-bit length field holds up to 64)
 static const int REC_POS_SHIFT = 26, REC_LEN_SHIFT = 20;
 static const int MH_REC_SHIFT = 36;   // minimizer histogram word: nrec << 36 | nkmers
@@ -130,7 +131,14 @@ MTG_HD uint64_t make_record(uint64_t pos, uint32_t len, uint32_t mini) {
 // value(m-mer) = top 2m bits of (min(m-mer, revcomp) * golden-ratio constant), minimised over the k-m+1 m-mers of the
 // k-mer. It is strand-symmetric, so every instance of a canonical k-mer lands in the same bin, it needs no look-up
 // table, and random orders give longer super-k-mers (density ~2/(w+1)) and far flatter bins than lexicographic ones.
-MTG_D uint32_t mmer_hash(uint32_t fwd, uint32_t rc, int hshift) { return (min(fwd, rc) * 0x9E3779B1u) >> hshift; }
+// The order uses 31 bits of the product (bit 31 is needed for a flag below); for 2m <= 31 distinct canonical m-mers almost
+// never tie, and a tie only merges two super-k-mers into one bin. The BIN of a record is a second mix of the winning value
+// folded to `bin_bits` (<= 20) bits, so that with m > 10 each bin is the union of many minimizers: a random-order
+// minimizer of rank quantile u attracts W(1-u)^(W-1) times the average load (up to W = k-m+1 times), which overflows
+// the shared-memory count table once the average bin nears its size; folding 4^m/2 minimizers into 2^20 bins averages
+// that skew out (relative sigma ~ 3.2 / sqrt(minimizers per bin)).
+MTG_D uint32_t mmer_hash(uint32_t fwd, uint32_t rc) { return (min(fwd, rc) * 0x9E3779B1u) >> 1; }
+MTG_D uint32_t mini_bin(uint32_t mini, int bin_bits) { return (mini * 0x85EBCA6Bu) >> (32 - bin_bits); }
 
 MTG_D int sk_vidx(int q) { return q + (q >> 3); }  // padded index: threads reading element e of their 8-run hit 32 distinct banks
 
@@ -143,7 +151,7 @@ MTG_D int sk_vidx(int q) { return q + (q >> 3); }  // padded index: threads read
 //  phase 6  records are published with one global atomic per tile; per-minimizer histogram for the grouping step
 __global__ void __launch_bounds__(SK_THREADS)
 superkmer_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ inv, uint64_t word_begin, uint64_t nwords,
-                 int k, int m, uint64_t* __restrict__ records, unsigned long long* __restrict__ nrec_global, uint64_t rec_capacity,
+                 int k, int m, int bin_bits, uint64_t* __restrict__ records, unsigned long long* __restrict__ nrec_global, uint64_t rec_capacity,
                  unsigned long long* __restrict__ mhist, unsigned long long* __restrict__ nvalid_global, int* __restrict__ overflow) {
     __shared__ uint64_t sw[SK_TILE / 32 + 4];
     __shared__ uint32_t si[SK_TILE / 32 + 4];
@@ -183,7 +191,7 @@ superkmer_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict
             rc = ((rc >> 1) & 0x55555555u) | ((rc & 0x55555555u) << 1);
             rc = (rc ^ 0xAAAAAAAAu) & mmask;
             uint32_t* dst = va + 9 * slot;
-            dst[0] = mmer_hash(fwd, rc, hshift);
+            dst[0] = mmer_hash(fwd, rc);
             x <<= 2 * m;
 #pragma unroll
             for (int j = 1; j < SK_PER; j++) {
@@ -191,7 +199,7 @@ superkmer_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict
                 x <<= 2;
                 fwd = ((fwd << 2) | c) & mmask;
                 rc = (rc >> 2) | ((c ^ 2u) << (2 * m - 2));
-                dst[j] = mmer_hash(fwd, rc, hshift);
+                dst[j] = mmer_hash(fwd, rc);
             }
         }
         __syncthreads();
@@ -282,7 +290,8 @@ superkmer_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict
             uint32_t mv = mini[0];
 #pragma unroll
             for (int jj = 1; jj < SK_PER; jj++) mv = j == jj ? mini[jj] : mv;  // register select (no dynamic indexing)
-            for (int o = 0; o < len; o += SK_MAXRUN) stage[slot++] = make_record(gpos + o, (uint32_t)min(SK_MAXRUN, len - o), mv);
+            const uint32_t bin = mini_bin(mv, bin_bits);
+            for (int o = 0; o < len; o += SK_MAXRUN) stage[slot++] = make_record(gpos + o, (uint32_t)min(SK_MAXRUN, len - o), bin);
         }
         __syncthreads();
         // ---- phase 6: publish
@@ -689,7 +698,9 @@ struct EventTimer {
 };
 
 template <class K> class Counter : public ICounter {
-    int k_, m_;
+    int k_, m_, bin_bits_ = 20;
+    bool m_fixed_ = false, resolved_ = false;
+    uint64_t size_hint_ = 0;
     cudaStream_t stream_;
     int sm_count_ = 148;
     // resident packed input
@@ -739,13 +750,11 @@ public:
     uint64_t nvalid_total_ = 0;   // valid k-mer instances pushed so far (host copy)
     Counter(int k, int m, cudaStream_t s, bool distinct_hint) : k_(k), m_(m), stream_(s), histo_(HISTO_MAX + 1, 0), distinct_hint_(distinct_hint) {
         if (m_ > k_) m_ = k_;
-        if (m_ > 10) m_ = 10;
+        if (m_ > SK_MAX_M) m_ = SK_MAX_M;
         if (m_ < 3) throw Error(-1, "minimizer size must be >= 3");
         int dev = 0;
         MTG_CUDA(cudaGetDevice(&dev));
         MTG_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev));
-        mhist_.alloc((size_t)1 << (2 * m_));
-        mhist_.zero(stream_);
         counters_.alloc(8);
         counters_.zero(stream_);
         flags_.alloc(4);
@@ -754,7 +763,26 @@ public:
         MTG_CUDA(cudaFuncSetAttribute(count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     cudaStream_t stream() const override { return stream_; }
-    void reserve(uint64_t nb_bases) override { ensure_words(words_used_ + nb_bases / 32 + 2); }
+    void reserve(uint64_t nb_bases) override { size_hint_ = std::max(size_hint_, nb_bases); ensure_words(words_used_ + nb_bases / 32 + 2); }
+
+    // Partitioning granularity (never influences counts). The requested m (Finder forces 10, src/Finder.cpp:246) is kept
+    // for inputs below 2^30 bases; larger inputs use m = 13 so that the 2^20 bins stay flat (see mini_bin). Fixed at the
+    // first push / import; every GPU of a multi-GPU find must use the same m (set_minimizer).
+    void set_minimizer(int m) override {
+        if (resolved_) throw Error(-1, "minimizer size must be set before the first reads are pushed");
+        if (m < 3 || m > SK_MAX_M) throw Error(-1, "minimizer size must be in [3,15]");
+        m_ = std::min(m, k_);
+        m_fixed_ = true;
+    }
+    int minimizer() const override { return m_; }
+    void resolve_partitioning(uint64_t nb_bases_hint) {
+        if (resolved_) return;
+        if (!m_fixed_ && std::max(size_hint_, nb_bases_hint) >= (1ull << 30)) m_ = std::min(std::max(m_, 13), std::min(k_, SK_MAX_M));
+        bin_bits_ = std::min(2 * m_, 20);
+        mhist_.alloc((size_t)1 << bin_bits_);
+        mhist_.zero(stream_);
+        resolved_ = true;
+    }
 
     void push_host(const char* bases, uint64_t n) override {
         if (!n) return;
@@ -767,6 +795,7 @@ public:
         if (!n) return;
         const uint64_t nwords = (n + 31) / 32;
         Trace tr(stream_);
+        resolve_partitioning(n);
         ensure_words(words_used_ + nwords);
         tr.mark("push: ensure_words");
         EventTimer t(stream_);
@@ -795,7 +824,7 @@ public:
             t.start();
             uint64_t ntiles = (nwords + SK_TILE / 32 - 1) / (SK_TILE / 32);
             int g2 = (int)std::min<uint64_t>(ntiles, (uint64_t)sm_count_ * 8);
-            superkmer_kernel<<<g2, SK_THREADS, 0, stream_>>>(packed_.p, inv_.p, words_used_, nwords, k_, m_, b.recs.p, counters_.p, cap,
+            superkmer_kernel<<<g2, SK_THREADS, 0, stream_>>>(packed_.p, inv_.p, words_used_, nwords, k_, m_, bin_bits_, b.recs.p, counters_.p, cap,
                                                               mhist_.p, counters_.p + 1, flags_.p);
             MTG_CUDA(cudaGetLastError());
             st_.ms_extract += t.stop();
@@ -879,6 +908,7 @@ public:
         ext_packed_ = d_packed; ext_records_ = d_records; ext_nrec_ = nrecords;
         words_used_ = nwords;
         (void)d_inv;  // validity was settled when the records were made; counting only needs the bases
+        resolve_partitioning(0);
         mhist_.zero(stream_);
         MTG_CUDA(cudaMemsetAsync(counters_.p + 1, 0, 8, stream_));
         if (nrecords) {

@@ -30,6 +30,8 @@ class ICounter {
 public:
     virtual ~ICounter() {}
     virtual void reserve(uint64_t nb_bases) = 0;
+    virtual void set_minimizer(int m) = 0;   // force the partitioning minimizer length (before the first push)
+    virtual int minimizer() const = 0;
     virtual void push_device(const uint8_t* d_bases, uint64_t n) = 0;  // ASCII bases, sequences separated by any non-ACGT byte
     virtual void push_host(const char* bases, uint64_t n) = 0;
     virtual void finish(int abundance_min, int64_t abundance_max) = 0;   // = run + filter on the local histogram

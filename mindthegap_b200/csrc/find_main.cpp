@@ -35,11 +35,12 @@ static void usage() {
             "  -abundance-min <n|auto>  [auto]      -abundance-max <n> [2147483647]\n"
             "  -max-rep <n> [5]   -het-max-occ <n> [1]   -snp-min-val <n> [5]   -branching-filter <n> [15]\n"
             "  -homo-only -insert-only -snp-only -deletion-only -hete-only -backup -no-snp -no-insert -no-deletion -no-hetero\n"
-            "  -nb-cores / -max-memory / -max-disk / -out-tmp / -verbose are accepted and ignored; -device <gpu> [0]\n");
+            "  -nb-cores <host threads of the event replay> [0 = all]; -max-memory / -max-disk / -out-tmp / -verbose are accepted and ignored; -device <gpu> [0]\n");
 }
 
 int main(int argc, char** argv) {
     std::string in, ref, out, graph, bed, amin = "auto";
+    int nb_cores = 0;  // 0 = all cores (src/Finder.cpp:137)
     mtg_params p;
     mtg_default_params(&p);
     bool f_homo_only = false, f_insert_only = false, f_snp_only = false, f_deletion_only = false, f_hete_only = false, f_backup = false,
@@ -62,7 +63,8 @@ int main(int argc, char** argv) {
         else if (o == "-snp-min-val") p.snp_min_val = atoi(val().c_str());
         else if (o == "-branching-filter") p.branching_filter = atoi(val().c_str());
         else if (o == "-device") p.device = atoi(val().c_str());
-        else if (o == "-nb-cores" || o == "-max-memory" || o == "-max-disk" || o == "-out-tmp" || o == "-verbose") val();
+        else if (o == "-nb-cores") nb_cores = atoi(val().c_str());
+        else if (o == "-max-memory" || o == "-max-disk" || o == "-out-tmp" || o == "-verbose") val();
         else if (o == "-homo-only") f_homo_only = true;
         else if (o == "-insert-only") f_insert_only = true;
         else if (o == "-snp-only") f_snp_only = true;
@@ -110,6 +112,7 @@ int main(int argc, char** argv) {
     clock_gettime(CLOCK_MONOTONIC, &t0);
     mtg_ctx* g = mtg_create(&p);
     if (!g) fail(mtg_last_error());
+    check(mtg_set_host_threads(g, nb_cores));
     // graph construction (was Graph::create, src/Finder.cpp:266)
     check(mtg_count_files(g, in.c_str()));
     check(mtg_count_finish(g));

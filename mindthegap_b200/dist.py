@@ -101,8 +101,23 @@ class DistFind:
         host = out.cpu().numpy()
         return [json.loads(host[r * m: r * m + sizes[r]].tobytes().decode()) for r in range(self.world)]
 
-    # ---- stage 1: count (reads of this rank already pushed into the engine)
+    # ---- stage 1: count
+    def push_reads(self, stream=None, dev_ptr=None, nbytes=None):
+        """Push this rank's reads (host bytes/array, or a device pointer + size). Records are exchanged by minimizer bin,
+        so every rank must partition with the same minimizer length: the engine's size rule (10 below 2^30 bases, 13
+        above; mtg_set_minimizer_size) is applied to the GLOBAL read volume here, before the first push."""
+        n = int(nbytes if dev_ptr is not None else len(stream))
+        t = torch.tensor([n], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        self.e.set_minimizer_size(13 if int(t.item()) >= (1 << 30) else min(10, self.k - 1))
+        if dev_ptr is not None:
+            self._sync()
+            self.e.push_reads_device(dev_ptr, n)
+        else:
+            self.e.push_reads(stream)
+
     def count(self):
+        """Reads of this rank were pushed with push_reads()."""
         e, W = self.e, self.world
         self._mark(None)
         nwords, nrec, _ = e.count_local_info()

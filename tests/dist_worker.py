@@ -31,6 +31,9 @@ class FakeEngine:
         self.bk = self.vcf = ""
 
     # -- stage 1
+    def set_minimizer_size(self, m):
+        self.minimizer_size = m
+
     def push_reads(self, stream):
         self.reads += bytes(stream)
 
@@ -170,8 +173,9 @@ def main():
     recs = oracle_py.read_sequences(reads)
     mine = recs[rank::world]                      # any split of the reads gives the same counts
     eng = FakeEngine(api.FindParams.from_cli(["-kmer-size", str(case["k"])] + list(case["flags"])))
-    eng.push_reads(b"\n".join(s for _, s in mine) + b"\n")
     d = DistFind(eng, torch.device("cpu"))
+    d.push_reads(b"\n".join(s for _, s in mine) + b"\n")
+    assert eng.minimizer_size == min(10, case["k"] - 1)
     refs = [(n, np.frombuffer(s, dtype=np.uint8)) for n, s in oracle_py.read_sequences(ref)]
     bk, vcf = d.find(refs)
     if rank == 0:

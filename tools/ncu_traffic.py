@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""DRAM bytes per launch of each profiled kernel from an `ncu --set full` report -> profiles/ncu_traffic.json
+usage: tools/ncu_traffic.py report.ncu-rep cfg2_k31   (bench.py reads the entry of its workload for roofline.traffic)"""
+import csv
+import json
+import os
+import re
+import subprocess
+import sys
+
+rep, key = sys.argv[1], sys.argv[2]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+ki, ri, wi, ti = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+best = {}
+for r in rows[2:]:
+    name = re.sub(r"[<(].*", "", r[ki]).replace("void ", "").split("::")[-1]
+    b = float(r[ri].replace(",", "")) * mult[units[ri]] + float(r[wi].replace(",", "")) * mult[units[wi]]
+    t = float(r[ti].replace(",", ""))
+    if name not in best or t > best[name][1]:   # the longest launch of each kernel = the one over the read set
+        best[name] = (b, t)
+out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+d = json.load(open(out)) if os.path.exists(out) else {}
+d[key] = {k: v[0] for k, v in best.items()}
+d[key]["_source"] = os.path.basename(rep)
+json.dump(d, open(out, "w"), indent=1, sort_keys=True)
+print(json.dumps(d[key], indent=1))
