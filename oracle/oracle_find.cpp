@@ -10,7 +10,7 @@
 using namespace mtgo;
 
 struct Args {
-    std::string in, ref, out = "oracle_out", solid_in;
+    std::string in, ref, out = "oracle_out", solid_in, bed;
     int k = 31;
     std::string abundance_min = "auto";
     int64_t abundance_max = 2147483647LL;
@@ -76,12 +76,15 @@ template <class K> static int run(const Args& a) {
     rb.build(ref, k, a.opt.het_max_occ);
     double t3 = now_s();
     ScanOracle<K> scan(g, rb, a.opt);
+    std::string bed_text;
+    if (!a.bed.empty() && !read_file(a.bed, bed_text)) { fprintf(stderr, "cannot read %s\n", a.bed.c_str()); return 1; }
     std::string trace_all, rep_all;
     uint64_t nb_ref_kmers = 0;
     for (auto& rec : ref) {
         if (rec.seq.size() < (size_t)k) continue;  // reference quirk (replays previous k-mers) deliberately not reproduced
         std::vector<uint8_t> tr, rp;
-        scan.scan_sequence(rec, a.dump ? &tr : 0, a.dump ? &rp : 0);
+        if (a.bed.empty()) scan.scan_sequence(rec, a.dump ? &tr : 0, a.dump ? &rp : 0);
+        else scan.scan_sequence_bed(rec, parse_bed(bed_text, rec.name, k));
         nb_ref_kmers += rec.seq.size() - k + 1;
         if (a.dump) { trace_all.append((const char*)tr.data(), tr.size()); rep_all.append((const char*)rp.data(), rp.size()); }
     }
@@ -134,6 +137,7 @@ int main(int argc, char** argv) {
         if (o == "-in") a.in = val();
         else if (o == "-ref") a.ref = val();
         else if (o == "-out") a.out = val();
+        else if (o == "-bed") a.bed = val();
         else if (o == "-solid-in") a.solid_in = val();
         else if (o == "-kmer-size") a.k = atoi(val().c_str());
         else if (o == "-abundance-min") a.abundance_min = val();

@@ -5,6 +5,7 @@
 #define MTG_ORACLE_SCAN_HPP
 
 #include <stdio.h>
+#include <stdexcept>
 
 #include "graph_oracle.hpp"
 
@@ -497,7 +498,78 @@ public:
         });
     }
     bool last_in_graph = false;  // trace only
+
+    // ---- operator() with -bed: M/FindBreakpoints.hpp:459-553. Intervals come from parse_bed() in file order.
+    // Quirks kept: ONE stale interval is dropped per position (:499-508); the state and the history are cleared at
+    // start-1 (never for start == 0, :520-530); positions outside the intervals still advance the ring indices; k-mers
+    // are notified from `start` on, also when the next interval starts before the current position (:533).
+    void scan_sequence_bed(const SeqRecord& rec, std::vector<std::pair<uint64_t, uint64_t>> intervals) {
+        kmer_begin = KmerCanon<K>(); kmer_end = KmerCanon<K>();
+        solid_stretch = 0; gap_stretch = 0;
+        memset(history, 0, sizeof(history));
+        end_index = (unsigned char)(k + 1); begin_index = 1;
+        recent_hetero = 0;
+        chrom_seq = rec.seq.data(); chrom_len = rec.seq.size(); chrom_name = rec.name;
+        position = 0;
+        if (intervals.empty()) return;
+        size_t cur_iv = 0;
+        uint64_t start_pos = intervals[0].first, end_pos = intervals[0].second;
+        bool stop = false;
+        iterate_kmers<K>(chrom_seq, chrom_len, k, [&](const KmerCanon<K>& km, size_t) {
+            if (stop) return;
+            if (position >= end_pos) {
+                cur_iv++;
+                if (cur_iv >= intervals.size()) { stop = true; return; }
+                start_pos = intervals[cur_iv].first; end_pos = intervals[cur_iv].second;
+            }
+            cur = km;
+            if (!km.valid) {
+                solid_stretch = 0; gap_stretch = 0;
+                kmer_begin = KmerCanon<K>(); kmer_end = KmerCanon<K>();
+            }
+            if (position == start_pos - 1) {
+                solid_stretch = 0; gap_stretch = 0;
+                kmer_begin = KmerCanon<K>(); kmer_end = KmerCanon<K>();
+                memset(history, 0, sizeof(history));
+            }
+            if (km.valid && position >= start_pos) {
+                uint64_t save_position = position;
+                notify();
+                position = save_position;
+                previous_kmer = km;
+            }
+            position++; begin_index++; end_index++;
+        });
+    }
 };
+
+// Intervals of one chromosome from the text of a bed file (M/FindBreakpoints.hpp:462-495): lines that are empty or start
+// with '#' / '@' are skipped, fields are split on tabs, field 0 must equal the sequence's short name, begin/end are read
+// with std::stoi (so "140 SNP T -> C" is 140), and the interval is kept when (end - begin) > k in unsigned arithmetic.
+inline std::vector<std::pair<uint64_t, uint64_t>> parse_bed(const std::string& text, const std::string& chrom, int k) {
+    std::vector<std::pair<uint64_t, uint64_t>> out;
+    size_t at = 0;
+    while (at < text.size()) {
+        size_t nl = text.find('\n', at);
+        if (nl == std::string::npos) nl = text.size();
+        std::string line = text.substr(at, nl - at);
+        at = nl + 1;
+        if (line.empty() || line[0] == '#' || line[0] == '@') continue;
+        std::vector<std::string> v;
+        size_t f = 0;
+        while (true) {
+            size_t t = line.find('\t', f);
+            if (t == std::string::npos) { v.push_back(line.substr(f)); break; }
+            v.push_back(line.substr(f, t - f));
+            f = t + 1;
+        }
+        if (v[0] != chrom) continue;
+        if (v.size() < 3) throw std::runtime_error("bed line with fewer than 3 tab-separated fields: " + line);
+        uint64_t b = (uint64_t)std::stoi(v[1]), e = (uint64_t)std::stoi(v[2]);
+        if ((e - b) > (uint64_t)k) out.push_back(std::make_pair(b, e));
+    }
+    return out;
+}
 
 }  // namespace mtgo
 #endif
