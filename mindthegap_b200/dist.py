@@ -42,6 +42,17 @@ def renumber(bk_text, vcf_text, offset):
     return bk_text, vcf_text, used
 
 
+def assign_chromosomes(lengths, world):
+    """Longest-processing-time assignment of whole chromosomes to ranks: (owner rank per chromosome, bases per rank)."""
+    load = [0] * world
+    owner = [0] * len(lengths)
+    for i in sorted(range(len(lengths)), key=lambda i: (-lengths[i], i)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owner[i] = r
+        load[r] += lengths[i]
+    return owner, load
+
+
 def segment_bounds(npos, world):
     """32-aligned split of npos positions into `world` contiguous segments: list of world+1 boundaries."""
     b = [min(npos, ((npos * r // world) + 31) // 32 * 32) for r in range(world)] + [npos]
@@ -49,8 +60,11 @@ def segment_bounds(npos, world):
 
 
 class DistFind:
-    def __init__(self, engine, device, group=None):
+    def __init__(self, engine, device, group=None, scan_mode="auto"):
+        """scan_mode: "chromosomes" = every rank scans whole chromosomes (no feature exchange), "segments" = every chromosome
+        is split across the ranks by position, "auto" = chromosomes when they balance within 25 %, else segments."""
         self.e = engine
+        self.scan_mode = scan_mode
         self.device = device
         self.group = group
         self.rank = dist.get_rank(group)
@@ -201,6 +215,12 @@ class DistFind:
         else:
             e.set_reference(ref_stream)
         self._mark("set_reference")
+        lengths = [len(s) if len(s) >= k else 0 for _, s in ref_records]
+        owner, load = assign_chromosomes(lengths, W)
+        by_chrom = self.scan_mode == "chromosomes" or (self.scan_mode == "auto" and max(load) * W <= 1.25 * max(sum(load), 1))
+        self.scan_mode_used = "chromosomes" if by_chrom else "segments"
+        if by_chrom:
+            return self._scan_chromosomes(ref_records, ref_dev, owner)
         # pass 1: every rank computes its 32-aligned segment of every chromosome ((k-1)-base halo) and the segments are
         # all-gathered as one buffer per chromosome: [feat | rep | interest words] per rank
         offsets = np.cumsum([0] + [len(s) + 1 for _, s in ref_records])
@@ -241,6 +261,29 @@ class DistFind:
             e.replay_sequence(name, seq, feat_h, rep_h, int_h)
             texts.append((ci, e.breakpoints_text(), e.vcf_text()))
         self._mark("replay")
+        return self._merge_texts(texts)
+
+    def _scan_chromosomes(self, ref_records, ref_dev, owner):
+        """Whole chromosomes per rank: features and replay stay on the GPU that owns the chromosome (the gap machine restarts
+        at every sequence, src/FindBreakpoints.hpp:393-418, so chromosomes are independent once the reference Bloom is global);
+        only the texts travel."""
+        e, k = self.e, self.k
+        offsets = np.cumsum([0] + [len(s) + 1 for _, s in ref_records])
+        on_gpu = hasattr(e, "scan_reference_device") and self.device.type == "cuda"
+        texts = []
+        for ci, (name, seq) in enumerate(ref_records):
+            if owner[ci] != self.rank or len(seq) < k:
+                continue
+            e.reset_outputs()
+            if on_gpu:
+                e.scan_reference_device(name, seq, ref_dev.data_ptr() + int(offsets[ci]))
+            else:
+                e.scan_reference(name, seq)
+            texts.append((ci, e.breakpoints_text(), e.vcf_text()))
+        self._mark("scan_chromosomes")
+        return self._merge_texts(texts)
+
+    def _merge_texts(self, texts):
         # merge on rank 0 in reference order, renumbering the shared ids
         gathered = self._gather_texts(texts)
         self._mark("gather_texts")

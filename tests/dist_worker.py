@@ -145,6 +145,11 @@ class FakeEngine:
     def reset_outputs(self):
         self.bk = self.vcf = ""
 
+    def scan_reference(self, name, seq):
+        p = self.params
+        bk, vcf = self.g.scan(name, bytes(seq), p.max_repeat, p.het_max_occ, p.snp_min_val, p.branching_filter, p.flags)
+        self.bk += bk; self.vcf += vcf
+
     def replay_sequence(self, name, seq, feat, rep, interest):
         seq = bytes(seq)
         f, r = self.g.features(seq)
@@ -173,13 +178,14 @@ def main():
     recs = oracle_py.read_sequences(reads)
     mine = recs[rank::world]                      # any split of the reads gives the same counts
     eng = FakeEngine(api.FindParams.from_cli(["-kmer-size", str(case["k"])] + list(case["flags"])))
-    d = DistFind(eng, torch.device("cpu"))
+    d = DistFind(eng, torch.device("cpu"), scan_mode=sys.argv[3] if len(sys.argv) > 3 else "auto")
     d.push_reads(b"\n".join(s for _, s in mine) + b"\n")
     assert eng.minimizer_size == min(10, case["k"] - 1)
     refs = [(n, np.frombuffer(s, dtype=np.uint8)) for n, s in oracle_py.read_sequences(ref)]
     bk, vcf = d.find(refs)
     if rank == 0:
-        json.dump({"bk": bk, "vcf": vcf, "nb_solid": d.nb_solid, "threshold": eng.threshold, "exchange": d.exchange_bytes}, open(out, "w"))
+        json.dump({"bk": bk, "vcf": vcf, "nb_solid": d.nb_solid, "threshold": eng.threshold, "exchange": d.exchange_bytes,
+                   "scan_mode": d.scan_mode_used}, open(out, "w"))
     dist.destroy_process_group()
 
 

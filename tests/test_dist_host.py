@@ -17,14 +17,15 @@ def free_port():
     return p
 
 
-@pytest.mark.parametrize("case,world", [("syn_tiny_k31", 2), ("full", 2), ("syn_tiny_k31", 3)])
-def test_two_rank_find_equals_reference(tmp_path, oracle, case, world):
+@pytest.mark.parametrize("case,world,mode", [("syn_tiny_k31", 2, "auto"), ("full", 2, "segments"), ("full", 2, "chromosomes"),
+                                             ("syn_tiny_k31", 3, "segments"), ("full", 3, "auto")])
+def test_two_rank_find_equals_reference(tmp_path, oracle, case, world, mode):
     out = str(tmp_path / "out.json")
     port = free_port()
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
-        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), case, out], env=env,
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), case, out, mode], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
@@ -34,10 +35,13 @@ def test_two_rank_find_equals_reference(tmp_path, oracle, case, world):
     assert res["vcf"] == evcf
     assert res["nb_solid"] == int(re.search(r"nb_solid_kmers\s*:\s*(\d+)", einfo).group(1))
     assert res["threshold"] == int(re.search(r"abundance_min \(used\)\s*:\s*(\d+)", einfo).group(1))
+    assert res["scan_mode"] == (mode if mode != "auto" else res["scan_mode"])
 
 
 def test_renumber_and_segments():
-    from mindthegap_b200.dist import renumber, segment_bounds
+    from mindthegap_b200.dist import assign_chromosomes, renumber, segment_bounds
+    owner, load = assign_chromosomes([10, 0, 7, 7, 3], 2)
+    assert sorted(load) == [13, 14] and owner[0] != owner[2] and sum(load) == 27
     bk = ">bkpt1_chr2_pos_10_fuzzy_0_HOM  left_kmer\nACGT\n>bkpt1_chr2_pos_10_fuzzy_0_HOM  right_kmer\nACGT\n" \
          ">bkpt3_chr2_bkpt9_pos_99_fuzzy_1_HET REPEATED left_kmer\nAC\n"
     vcf = "chr2\t5\tbkpt2\tA\tC\t.\tPASS\tTYPE=SNP;LEN=1;FUZZY=0\tGT\t1/1\n"
