@@ -407,7 +407,7 @@ def own_arm(args):
             "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64" if K <= 31 else "u128", "data": "synthetic",
             "config": {"workload": wl["name"], "kmer_size": K, "abundance_min": "auto (inferred %d)" % int(avg["threshold"]),
                        "per_gpu_read_bytes": nbytes, "l2_policy": "inputs (%.0f MB reads per GPU) larger than the 126 MB L2; every step starts from a fresh context" % (nbytes / 1e6),
-                       "parallelism": ("1 process per GPU (%d): records all-to-all by minimizer owner, solid set all-gathered, reference positions sharded" % world) if world > 1 else "single GPU"},
+                       "parallelism": ("1 process per GPU (%d): records all-to-all by minimizer owner; solid k-mers all-to-all by table range, ranges all-gathered, Bloom arrays OR-reduced (replica per GPU); whole chromosomes scanned per rank" % world) if world > 1 else "single GPU"},
             "e2e": {"value": tot_kmers / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes + ref_stream.size),
                     "d2h_bytes_per_step": int(2 * wl["ref_kmers"] + len(out_e2e[0]) + len(out_e2e[1])), "ms_per_step": ms_e2e},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity": parity,

@@ -103,6 +103,35 @@ int mtg_graph_critical(mtg_ctx* ctx, const void* d_keys_share, uint64_t n_share,
 int mtg_graph_critical_copy(mtg_ctx* ctx, void* d_out, uint64_t capacity);
 int mtg_graph_build_end(mtg_ctx* ctx, const void* d_keys, uint64_t n, const void* d_candidates, uint64_t n_candidates);
 
+/* ---- the same build SHARDED over N GPUs: the exact table is nshards equal ranges; a solid k-mer belongs to the
+ * range its hash selects and every rank builds ONE range, so no rank ever inserts, probes or hashes more than its share
+ * (+ the replicated BooPHF levels). Between the calls the host moves the buffers mtg_graph_buffer exposes:
+ *   mtg_solid_partition            -> all-to-all of the solid k-mers by range owner
+ *   mtg_graph_shard_begin          own table range + own share in the main Bloom   -> all-gather(table), OR-reduce(bloom)
+ *   mtg_graph_shard_critical       adjacency bytes of the own range + critical candidates of the share
+ *   mtg_graph_adj_pack / _unpack   -> all-gather(adjacency bytes, buffer 5) in between
+ *   mtg_partition_keys(buffer 7)   -> all-to-all of the candidates by owner; mtg_graph_critical_set_share de-duplicates
+ *   mtg_graph_shard_cascade 0..3   B2, B3, B4 (createCFP, DebloomAlgorithm.cpp:462-622): OR-reduce after steps 0, 1, 2;
+ *                                  step 3 leaves the rank's part of the cFP set (buffer 6) -> all-gather -> mtg_graph_set_cfp
+ *   mtg_graph_shard_finish         BooPHF levels from the gathered table; the graph answers queries from here on          */
+int mtg_solid_partition(mtg_ctx* ctx, uint32_t nshards, void* d_out, uint64_t* counts);
+int mtg_partition_keys(mtg_ctx* ctx, const void* d_keys, uint64_t n, uint32_t nshards, void* d_out, uint64_t* counts);
+int mtg_graph_shard_begin(mtg_ctx* ctx, const void* d_keys_share, uint64_t n_share, uint64_t n_total, uint64_t max_share, uint32_t nshards,
+                          uint32_t shard);
+int mtg_graph_shard_critical(mtg_ctx* ctx, uint64_t* n_out);
+int mtg_graph_adj_pack(mtg_ctx* ctx);
+int mtg_graph_adj_unpack(mtg_ctx* ctx);
+int mtg_graph_critical_set_share(mtg_ctx* ctx, const void* d_candidates, uint64_t n, uint64_t* n_out);
+int mtg_graph_shard_cascade(mtg_ctx* ctx, int step, uint64_t ncrit_total, uint64_t* n_out);
+int mtg_graph_set_cfp(mtg_ctx* ctx, const void* d_all, uint64_t n);
+int mtg_graph_shard_finish(mtg_ctx* ctx);
+/* which: 0 exact table (all ranges), 1 main Bloom, 2..4 B2..B4, 5 adjacency bytes, 6 local cFP part, 7 critical share;
+ * device pointer and byte size, valid until the next build call on this context */
+int mtg_graph_buffer(mtg_ctx* ctx, int which, void** d_ptr, uint64_t* nbytes);
+/* d_out[i] = OR over c < nchunks of d_in[c * nwords + i], 64-bit words: the reduction step of an OR-reduce-scatter (NCCL has no
+ * bitwise OR) */
+int mtg_or_chunks(mtg_ctx* ctx, const void* d_in, uint32_t nchunks, uint64_t nwords, void* d_out);
+
 /* info lines of Finder::resumeParameters (src/Finder.cpp:444-467) */
 int32_t mtg_get_threshold(mtg_ctx* ctx);     /* "abundance_min (used)"           */
 int32_t mtg_get_cutoff_auto(mtg_ctx* ctx);   /* "abundance_min (auto inferred)", -1 when not auto */

@@ -41,6 +41,8 @@ EXPORTS = [
     "mtg_bench_random_gather", "mtg_count_local_info", "mtg_count_copy_packed", "mtg_count_partition_records", "mtg_count_import",
     "mtg_count_run", "mtg_count_filter", "mtg_solid_copy", "mtg_graph_build_device", "mtg_sequence_features_device2", "mtg_replay_sequence",
     "mtg_graph_build_begin", "mtg_graph_critical", "mtg_graph_critical_copy", "mtg_graph_build_end", "mtg_set_host_threads", "mtg_set_minimizer_size", "mtg_get_minimizer_size",
+    "mtg_solid_partition", "mtg_partition_keys", "mtg_graph_shard_begin", "mtg_graph_shard_critical", "mtg_graph_adj_pack", "mtg_graph_adj_unpack",
+    "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
 ]
 
 _lib = None
@@ -114,6 +116,18 @@ def load_library():
     L.mtg_graph_critical.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.mtg_graph_critical_copy.argtypes = [vp, vp, C.c_uint64]
     L.mtg_graph_build_end.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64]
+    L.mtg_solid_partition.argtypes = [vp, C.c_uint32, vp, u64p]
+    L.mtg_partition_keys.argtypes = [vp, vp, C.c_uint64, C.c_uint32, vp, u64p]
+    L.mtg_graph_shard_begin.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+    L.mtg_graph_shard_critical.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mtg_graph_adj_pack.argtypes = [vp]
+    L.mtg_graph_adj_unpack.argtypes = [vp]
+    L.mtg_graph_critical_set_share.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.mtg_graph_shard_cascade.argtypes = [vp, C.c_int, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.mtg_graph_set_cfp.argtypes = [vp, vp, C.c_uint64]
+    L.mtg_graph_shard_finish.argtypes = [vp]
+    L.mtg_graph_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.mtg_or_chunks.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp]
     L.mtg_sequence_features_device2.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, u64p]
     L.mtg_replay_sequence.argtypes = [vp, C.c_char_p, vp, C.c_uint64, u8p, u8p, vp]
     L.mtg_bench_random_gather.restype = C.c_double
@@ -385,6 +399,62 @@ class Finder:
 
     def graph_build_end(self, keys_t, n, cand_t, ncand):
         self._check(self.L.mtg_graph_build_end(self.ctx, C.c_void_p(keys_t.data_ptr()), n, C.c_void_p(cand_t.data_ptr()), ncand))
+
+    # ---- graph build sharded over N GPUs (include/mtg_b200.h "SHARDED over N GPUs"; choreography in dist.py)
+    def solid_partition(self, nshards, out_t):
+        counts = np.zeros(nshards, dtype=np.uint64)
+        self._check(self.L.mtg_solid_partition(self.ctx, nshards, C.c_void_p(out_t.data_ptr()), counts))
+        return [int(x) for x in counts]
+
+    def partition_keys(self, keys_t, n, nshards, out_t):
+        counts = np.zeros(nshards, dtype=np.uint64)
+        self._check(self.L.mtg_partition_keys(self.ctx, C.c_void_p(keys_t.data_ptr()), n, nshards, C.c_void_p(out_t.data_ptr()), counts))
+        return [int(x) for x in counts]
+
+    def graph_shard_begin(self, keys_t, n_share, n_total, max_share, nshards, shard):
+        self._check(self.L.mtg_graph_shard_begin(self.ctx, C.c_void_p(keys_t.data_ptr()), n_share, n_total, max_share, nshards, shard))
+
+    def graph_shard_critical(self):
+        out = C.c_uint64()
+        self._check(self.L.mtg_graph_shard_critical(self.ctx, C.byref(out)))
+        return out.value
+
+    def graph_adj_pack(self):
+        self._check(self.L.mtg_graph_adj_pack(self.ctx))
+
+    def graph_adj_unpack(self):
+        self._check(self.L.mtg_graph_adj_unpack(self.ctx))
+
+    def graph_critical_set_share(self, cand_t, n):
+        out = C.c_uint64()
+        self._check(self.L.mtg_graph_critical_set_share(self.ctx, C.c_void_p(cand_t.data_ptr()), n, C.byref(out)))
+        return out.value
+
+    def graph_shard_cascade(self, step, ncrit_total):
+        out = C.c_uint64()
+        self._check(self.L.mtg_graph_shard_cascade(self.ctx, step, ncrit_total, C.byref(out)))
+        return out.value
+
+    def graph_set_cfp(self, cfp_t, n):
+        self._check(self.L.mtg_graph_set_cfp(self.ctx, C.c_void_p(cfp_t.data_ptr()), n))
+
+    def graph_shard_finish(self):
+        self._check(self.L.mtg_graph_shard_finish(self.ctx))
+
+    def graph_buffer(self, which):
+        """Zero-copy uint8 torch view of a library-owned device buffer (valid until the next build call)."""
+        import torch
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.L.mtg_graph_buffer(self.ctx, which, C.byref(p), C.byref(n)))
+        if not n.value:
+            return torch.empty(0, dtype=torch.uint8, device="cuda:%d" % self.params.device)
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "|u1", "data": (p.value, False), "version": 2}
+        return torch.as_tensor(_View(), device="cuda:%d" % self.params.device)
+
+    def or_chunks(self, in_t, nchunks, nwords, out_t):
+        self._check(self.L.mtg_or_chunks(self.ctx, C.c_void_p(in_t.data_ptr()), nchunks, nwords, C.c_void_p(out_t.data_ptr())))
 
     def features_segment(self, seq_t):
         """seq_t: uint8 device tensor holding bases [a, b+k-1); returns (feat, rep, interest) device tensors for b-a positions."""

@@ -404,6 +404,64 @@ int mtg_graph_build_end(mtg_ctx* ctx, const void* d_keys, uint64_t n, const void
     MTG_CATCH
 }
 
+// ---- graph build on N GPUs (sharded by table range)
+int mtg_solid_partition(mtg_ctx* ctx, uint32_t nshards, void* d_out, uint64_t* counts) {
+    MTG_TRY(ctx)
+    if (!ctx->solid_owner) throw Error(-1, "no counted solid set on this context");
+    ctx->graph->partition_keys(ctx->solid_owner->solid_keys_device(), ctx->solid_owner->nb_solid(), nshards, d_out, counts);
+    MTG_CATCH
+}
+int mtg_partition_keys(mtg_ctx* ctx, const void* d_keys, uint64_t n, uint32_t nshards, void* d_out, uint64_t* counts) {
+    MTG_TRY(ctx) ctx->graph->partition_keys(d_keys, n, nshards, d_out, counts); MTG_CATCH
+}
+int mtg_graph_shard_begin(mtg_ctx* ctx, const void* d_keys_share, uint64_t n_share, uint64_t n_total, uint64_t max_share, uint32_t nshards, uint32_t shard) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_finish);
+    ctx->graph_ready = false;
+    ctx->graph->shard_begin(d_keys_share, n_share, n_total, max_share, nshards, shard);
+    MTG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->nb_solid_global = n_total;
+    MTG_CATCH
+}
+int mtg_graph_shard_critical(mtg_ctx* ctx, uint64_t* n_out) {
+    MTG_TRY(ctx) WallTimer w(ctx->wall_finish); const uint64_t n = ctx->graph->shard_critical(); if (n_out) *n_out = n; MTG_CATCH
+}
+int mtg_graph_adj_pack(mtg_ctx* ctx) { MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->adj_pack(); MTG_CATCH }
+int mtg_graph_adj_unpack(mtg_ctx* ctx) { MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->adj_unpack(); MTG_CATCH }
+int mtg_graph_critical_set_share(mtg_ctx* ctx, const void* d_candidates, uint64_t n, uint64_t* n_out) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_finish);
+    ctx->graph->critical_merge(d_candidates, n);
+    if (n_out) *n_out = ctx->graph->critical_count();
+    MTG_CATCH
+}
+int mtg_graph_shard_cascade(mtg_ctx* ctx, int step, uint64_t ncrit_total, uint64_t* n_out) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_finish);
+    const uint64_t n = ctx->graph->shard_cascade(step, ncrit_total);
+    MTG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_out) *n_out = n;
+    MTG_CATCH
+}
+int mtg_graph_set_cfp(mtg_ctx* ctx, const void* d_all, uint64_t n) { MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->set_cfp(d_all, n); MTG_CATCH }
+int mtg_graph_shard_finish(mtg_ctx* ctx) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_finish);
+    ctx->graph->shard_finish();
+    MTG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->graph_ready = true;
+    MTG_CATCH
+}
+int mtg_graph_buffer(mtg_ctx* ctx, int which, void** p, uint64_t* nbytes) {
+    MTG_TRY(ctx)
+    if (!p || !nbytes) throw Error(-1, "mtg_graph_buffer: null output");
+    ctx->graph->buffer(which, p, nbytes);
+    MTG_CATCH
+}
+int mtg_or_chunks(mtg_ctx* ctx, const void* d_in, uint32_t nchunks, uint64_t nwords, void* d_out) {
+    MTG_TRY(ctx) ctx->graph->or_chunks(d_in, nchunks, nwords, d_out); MTG_CATCH
+}
+
 int32_t mtg_get_threshold(mtg_ctx* ctx) { return ctx ? ctx->threshold : -1; }
 int32_t mtg_get_cutoff_auto(mtg_ctx* ctx) { return ctx ? ctx->cutoff_auto : -1; }
 uint64_t mtg_get_nb_solid(mtg_ctx* ctx) { return ctx ? (ctx->nb_solid_global ? ctx->nb_solid_global : ctx->nb_solid) : 0; }

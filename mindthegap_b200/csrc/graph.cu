@@ -58,13 +58,15 @@ struct BloomDev {
 
 // ------------------------------------------------------------------------------------------------ build kernels
 template <class K>
-__global__ void __launch_bounds__(256) table_build_kernel(const K* __restrict__ keys, uint64_t n, K* __restrict__ table, uint64_t nbuckets,
-                                                          int* __restrict__ err) {
+__global__ void __launch_bounds__(256) table_build_kernel(const K* __restrict__ keys, uint64_t n, K* __restrict__ table_all, uint64_t nbuckets,
+                                                          uint32_t nshards, int* __restrict__ err) {
     const int SLOTS = TableCfg<K>::SLOTS, STRIDE = TableCfg<K>::STRIDE;
     const K EMPTY = ~K(0);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const K key = keys[i];
-        uint64_t b = key_hash(key) % nbuckets;
+        const uint64_t h = key_hash(key);
+        uint64_t b = h % nbuckets;
+        K* table = table_all + (uint64_t)shard_of(h, nshards) * nbuckets * STRIDE;
         bool done = false;
         for (uint64_t probe = 0; probe < nbuckets && !done; probe++) {
             K* bucket = table + b * STRIDE;
@@ -166,14 +168,16 @@ __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ key
             // each in one half of the bucket
             const unsigned other = __shfl_xor_sync(0xFFFFFFFFu, adj, 1);
             const unsigned byte = succ ? (adj | (other << 4)) : (other | (adj << 4));
-            uint64_t b = key_hash(x) % g.nbuckets;
+            const uint64_t hx = key_hash(x);
+            uint64_t b = hx % g.nbuckets;
+            K* const trw = table_rw + (uint64_t)shard_of(hx, g.nshards) * g.nbuckets * TableCfg<K>::STRIDE;   // the k-mer's range
             bool searching = active;
             for (uint64_t probe = 0; probe < g.nbuckets; probe++) {
                 if (!__any_sync(0xFFFFFFFFu, searching)) break;
                 int slot = -1;
                 bool has_empty = false;
                 if (searching) {
-                    const uint4* q = reinterpret_cast<const uint4*>(table_rw + b * TableCfg<K>::STRIDE) + (succ ? 0 : 4);
+                    const uint4* q = reinterpret_cast<const uint4*>(trw + b * TableCfg<K>::STRIDE) + (succ ? 0 : 4);
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         if (!succ && i == 3) break;   // chunk 7 holds the adjacency bytes
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ key
                 if (searching) {
                     const int fslot = slot >= 0 ? slot : oslot;
                     if (fslot >= 0) {
-                        if (succ) reinterpret_cast<uint8_t*>(table_rw + b * TableCfg<K>::STRIDE)[BUCKET_ADJ_OFFSET + fslot] = (uint8_t)byte;
+                        if (succ) reinterpret_cast<uint8_t*>(trw + b * TableCfg<K>::STRIDE)[BUCKET_ADJ_OFFSET + fslot] = (uint8_t)byte;
                         searching = false;
                     } else if (has_empty || oempty) {
                         *err = 4;   // a solid k-mer must be in the table
@@ -316,6 +320,97 @@ __global__ void __launch_bounds__(256) mphf_compact_kernel(const K* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------ N-GPU build kernels
+// keys grouped by the table range that owns them (shard_of(key_hash)): count, then scatter with one reservation per block and
+// destination (destinations are few and hot; same scheme as the super-k-mer records, count.cu)
+static const int KO_MAX = 64, KO_THREADS = 256, KO_PER = 4, KO_TILE = KO_THREADS * KO_PER;
+template <class K>
+__global__ void __launch_bounds__(KO_THREADS) key_owner_count_kernel(const K* __restrict__ keys, uint64_t n, uint32_t nshards,
+                                                                     unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int s_cnt[KO_MAX];
+    if (threadIdx.x < KO_MAX) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t nround = (n + 31) & ~31ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = i < n ? shard_of(key_hash(keys[i]), nshards) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        if (d != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[d], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < nshards && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+template <class K>
+__global__ void __launch_bounds__(KO_THREADS) key_owner_scatter_kernel(const K* __restrict__ keys, uint64_t n, uint32_t nshards,
+                                                                       unsigned long long* __restrict__ cursor, K* __restrict__ out) {
+    __shared__ unsigned int s_cnt[KO_MAX];
+    __shared__ unsigned long long s_base[KO_MAX];
+    const int lane = threadIdx.x & 31;
+    const uint64_t ntiles = (n + KO_TILE - 1) / KO_TILE;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x < KO_MAX) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        K r[KO_PER];
+        uint32_t rank_in[KO_PER], dest[KO_PER];
+#pragma unroll
+        for (int j = 0; j < KO_PER; j++) {
+            const uint64_t i = tile * KO_TILE + (uint64_t)j * KO_THREADS + threadIdx.x;
+            r[j] = i < n ? keys[i] : K(0);
+            dest[j] = i < n ? shard_of(key_hash(r[j]), nshards) : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dest[j]);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (dest[j] != 0xFFFFFFFFu && lane == leader) base = atomicAdd(&s_cnt[dest[j]], (unsigned)__popc(peers));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            rank_in[j] = base + __popc(peers & ((1u << lane) - 1));
+        }
+        __syncthreads();
+        if (threadIdx.x < nshards && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < KO_PER; j++)
+            if (dest[j] != 0xFFFFFFFFu) out[s_base[dest[j]] + rank_in[j]] = r[j];
+        __syncthreads();
+    }
+}
+// adjacency bytes (last 16 bytes of every 128-byte bucket) of buckets [b0, b1) <-> a dense array of 16-byte entries
+__global__ void __launch_bounds__(256) adj_pack_kernel(const uint4* __restrict__ table, uint64_t b0, uint64_t b1, uint4* __restrict__ adj) {
+    for (uint64_t b = b0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < b1; b += (uint64_t)gridDim.x * blockDim.x) adj[b] = table[b * 8 + 7];
+}
+__global__ void __launch_bounds__(256) adj_unpack_kernel(uint4* __restrict__ table, uint64_t nb, uint64_t skip0, uint64_t skip1, const uint4* __restrict__ adj) {
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x)
+        if (b < skip0 || b >= skip1) table[b * 8 + 7] = adj[b];
+}
+__global__ void __launch_bounds__(256) or_chunks_kernel(const unsigned long long* __restrict__ in, uint32_t nchunks, uint64_t nwords,
+                                                        unsigned long long* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long v = 0;
+        for (uint32_t c = 0; c < nchunks; c++) v |= in[(uint64_t)c * nwords + i];
+        out[i] = v;
+    }
+}
+// every key held by the (gathered) table -> a dense list, in table order
+template <class K>
+__global__ void __launch_bounds__(256) table_compact_kernel(const K* __restrict__ table, uint64_t nbuckets_total, K* __restrict__ out,
+                                                            unsigned long long* __restrict__ nout) {
+    const int SLOTS = TableCfg<K>::SLOTS, STRIDE = TableCfg<K>::STRIDE;
+    const K EMPTY = ~K(0);
+    const int lane = threadIdx.x & 31;
+    const uint64_t nslots = nbuckets_total * SLOTS, nround = (nslots + 31) & ~31ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (uint64_t)gridDim.x * blockDim.x) {
+        K key = EMPTY;
+        if (i < nslots) key = table[(i / SLOTS) * STRIDE + (i % SLOTS)];
+        const bool keep = !(key == EMPTY);
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, keep);
+        if (b) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(nout, (unsigned long long)__popc(b));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (keep) out[base + __popc(b & ((1u << lane) - 1))] = key;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ query kernels
 template <class K>
 __global__ void __launch_bounds__(256) contains_kernel(GraphView<K> g, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, uint64_t n,
@@ -413,7 +508,8 @@ template <class K> class Graph : public IGraph {
     int k_;
     cudaStream_t stream_;
     DevBuf<K> table_;
-    uint64_t nbuckets_ = 0;
+    uint64_t nbuckets_ = 0;   // buckets per range
+    uint32_t nshards_ = 1;    // ranges (= GPUs that built the table)
     BloomDev bloom_, b2_, b3_, b4_, ref_;
     DevBuf<K> cfp_, final_, crit_list_;
     uint64_t ncrit_ = 0;
@@ -442,7 +538,7 @@ template <class K> class Graph : public IGraph {
         GraphView<K> g;
         memset(&g, 0, sizeof(g));
         g.k = k_;
-        g.table = table_.p; g.nbuckets = nbuckets_;
+        g.table = table_.p; g.nbuckets = nbuckets_; g.nshards = nshards_;
         g.bloom = bloom_.bits.p; g.bloom_tai = bloom_.tai; g.bloom_nhash = bloom_.nhash;
         g.cascading = cascading_ ? 1 : 0;
         g.b2 = b2_.bits.p; g.b2_tai = b2_.tai; g.b3 = b3_.bits.p; g.b3_tai = b3_.tai; g.b4 = b4_.bits.p; g.b4_tai = b4_.tai;
@@ -524,6 +620,7 @@ public:
         t.start();
         const int SLOTS = TableCfg<K>::SLOTS;
         nbuckets_ = std::max<uint64_t>((uint64_t)((double)N / 0.55 / SLOTS) + 1, 1);
+        nshards_ = 1;
         table_.alloc(nbuckets_ * TableCfg<K>::STRIDE);
         table_.fill_ff(stream_);   // empty key slots; the 16 adjacency bytes of every bucket start at zero
         MTG_CUDA(cudaMemset2DAsync(reinterpret_cast<uint8_t*>(table_.p) + BUCKET_ADJ_OFFSET, BUCKET_BYTES, 0, BUCKET_BYTES - BUCKET_ADJ_OFFSET,
@@ -531,7 +628,7 @@ public:
         adj_done_ = false;
         err_.zero(stream_);
         if (N) {
-            table_build_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, table_.p, nbuckets_, err_.p);
+            table_build_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, table_.p, nbuckets_, 1, err_.p);
             MTG_CUDA(cudaGetLastError());
             st_.launches++;
         }
@@ -684,8 +781,217 @@ public:
         st_.ms_cascade = t.stop();
         st_.b2_tai = b2_.tai;
         tr.mark("graph: cascade"); st_.b3_tai = b3_.tai; st_.b4_tai = b4_.tai; st_.ncfp = ncfp_;
-        // ---- BooPHF levels (sizes: mphf::setup, BooPHF.h:1015-1041, double arithmetic on the host)
         t.start();
+        build_mphf(keys, N);
+        st_.ms_mphf = t.stop();
+        tr.mark("graph: mphf");
+    }
+
+    // ------------------------------------------------------------------------------------------ build on N GPUs
+    DevBuf<K> share_;            // solid k-mers of this rank's table range
+    uint64_t nshare_ = 0, ntotal_ = 0;
+    uint32_t shard_ = 0;
+    DevBuf<uint4> adjbuf_;
+    DevBuf<K> cfp_local_;
+    uint64_t ncfp_local_ = 0;
+
+    void partition_keys(const void* d_keys, uint64_t n, uint32_t nshards, void* d_out, uint64_t* counts_host) override {
+        if (nshards < 1 || nshards > (uint32_t)KO_MAX) throw Error(-1, "partition_keys: 1..64 shards");
+        DevBuf<unsigned long long> d_counts(KO_MAX), d_cursor(KO_MAX);
+        d_counts.zero(stream_);
+        const K* keys = (const K*)d_keys;
+        if (n) { key_owner_count_kernel<K><<<grid_for(n), KO_THREADS, 0, stream_>>>(keys, n, nshards, d_counts.p); st_.launches++; }
+        unsigned long long cnt[KO_MAX], cur[KO_MAX];
+        MTG_CUDA(cudaMemcpyAsync(cnt, d_counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        unsigned long long off = 0;
+        for (int d = 0; d < KO_MAX; d++) { cur[d] = off; if ((uint32_t)d < nshards) { counts_host[d] = cnt[d]; off += cnt[d]; } }
+        MTG_CUDA(cudaMemcpyAsync(d_cursor.p, cur, sizeof(cur), cudaMemcpyHostToDevice, stream_));
+        if (n) {
+            key_owner_scatter_kernel<K><<<grid_for((n + KO_PER - 1) / KO_PER, KO_THREADS), KO_THREADS, 0, stream_>>>(keys, n, nshards, d_cursor.p, (K*)d_out);
+            st_.launches++;
+        }
+        MTG_CUDA(cudaGetLastError());
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    void shard_begin(const void* d_keys_share, uint64_t n_share, uint64_t n_total, uint64_t max_share, uint32_t nshards, uint32_t shard) override {
+        if (nshards < 1 || shard >= nshards || n_share > max_share) throw Error(-1, "shard_begin: bad shard geometry");
+        EvTimer t(stream_);
+        st_.nb_solid = n_total;
+        ntotal_ = n_total; nshare_ = n_share; shard_ = shard;
+        share_.alloc(std::max<uint64_t>(n_share, 1));
+        if (n_share) MTG_CUDA(cudaMemcpyAsync(share_.p, d_keys_share, n_share * sizeof(K), cudaMemcpyDeviceToDevice, stream_));
+        // ---- all ranges allocated, own range built (same load factor as the single-GPU table, from the largest share)
+        t.start();
+        const int SLOTS = TableCfg<K>::SLOTS, STRIDE = TableCfg<K>::STRIDE;
+        nbuckets_ = std::max<uint64_t>((uint64_t)((double)max_share / 0.55 / SLOTS) + 1, 1);
+        nshards_ = nshards;
+        table_.alloc(nbuckets_ * nshards * STRIDE);
+        K* own = table_.p + (uint64_t)shard * nbuckets_ * STRIDE;
+        MTG_CUDA(cudaMemsetAsync(own, 0xFF, nbuckets_ * BUCKET_BYTES, stream_));
+        MTG_CUDA(cudaMemset2DAsync(reinterpret_cast<uint8_t*>(own) + BUCKET_ADJ_OFFSET, BUCKET_BYTES, 0, BUCKET_BYTES - BUCKET_ADJ_OFFSET, nbuckets_, stream_));
+        adj_done_ = false;
+        err_.zero(stream_);
+        if (n_share) {
+            table_build_kernel<K><<<grid_for(n_share), 256, 0, stream_>>>(share_.p, n_share, table_.p, nbuckets_, nshards, err_.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        st_.ms_table = t.stop();
+        check_err("exact table build (range)");
+        st_.nbuckets = nbuckets_ * nshards;
+        // ---- main Bloom sized for the whole set, own share inserted (the host ORs the ranks' arrays)
+        t.start();
+        const float NBITS = bits_per_kmer(k_);
+        uint64_t est = (uint64_t)(n_total * NBITS);
+        const int nbHash = (int)floorf(0.7 * NBITS);
+        if (est == 0) est = 1000;
+        bloom_.init(est, nbHash, stream_);
+        if (n_share) {
+            bloom_neighbor_insert_kernel<K><<<grid_for(n_share), 256, 0, stream_>>>(share_.p, n_share, view(), bloom_.bits.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        st_.ms_bloom = t.stop();
+        st_.bloom_tai = bloom_.tai;
+        mphf_built_ = false;
+    }
+
+    uint64_t shard_critical() override {
+        const uint64_t total = st_.nb_solid;
+        st_.nb_solid = nshare_;      // critical() writes the adjacency bytes when it is given "the whole set": here the whole range
+        critical(share_.p, nshare_);
+        st_.nb_solid = total;
+        adj_done_ = false;           // the other ranges arrive through adj_unpack
+        return ncrit_;
+    }
+    void adj_pack() override {
+        const uint64_t nb = nbuckets_ * nshards_;
+        adjbuf_.alloc(nb);
+        adj_pack_kernel<<<grid_for(nbuckets_), 256, 0, stream_>>>(reinterpret_cast<const uint4*>(table_.p), (uint64_t)shard_ * nbuckets_,
+                                                                  (uint64_t)(shard_ + 1) * nbuckets_, adjbuf_.p);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches++;
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+    }
+    void adj_unpack() override {
+        const uint64_t nb = nbuckets_ * nshards_;
+        adj_unpack_kernel<<<grid_for(nb), 256, 0, stream_>>>(reinterpret_cast<uint4*>(table_.p), nb, (uint64_t)shard_ * nbuckets_,
+                                                             (uint64_t)(shard_ + 1) * nbuckets_, adjbuf_.p);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches++;
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        adjbuf_.release();
+        adj_done_ = true;
+    }
+
+    uint64_t shard_cascade(int step, uint64_t ncrit_total) override {
+        const float NBITS = bits_per_kmer(k_);
+        const int nh = (int)floorf(0.7 * NBITS);
+        EvTimer t(stream_);
+        t.start();
+        uint64_t ret = 0;
+        if (step == 0) {
+            st_.ms_cascade = 0;
+            st_.nb_critical = ncrit_total;
+            cascading_ = ncrit_total != 0;   // DebloomAlgorithm.cpp:478-479
+            ncfp_ = 0; ncfp_local_ = 0;
+            cfp_.alloc(1);
+            if (cascading_) {
+                const uint64_t N = ntotal_;
+                int64_t estT2 = std::max((int)ceilf(N * (double)powf((double)0.62, (double)NBITS)), 1);
+                int64_t estT3 = std::max((int)ceilf(ncrit_total * (double)powf((double)0.62, (double)NBITS)), 1);
+                b2_.init((uint64_t)(ncrit_total * NBITS), nh, stream_);
+                b3_.init((uint64_t)(estT2 * NBITS), nh, stream_);
+                b4_.init((uint64_t)(estT3 * NBITS), nh, stream_);
+                if (ncrit_) bloom_cache_insert_kernel<K><<<grid_for(ncrit_), 256, 0, stream_>>>(crit_list_.p, ncrit_, b2_.bits.p, b2_.tai, nh, seed0_, rnd_.p);
+                st_.launches++;
+            }
+            st_.b2_tai = b2_.tai; st_.b3_tai = b3_.tai; st_.b4_tai = b4_.tai;
+        } else if (!cascading_) {
+            // nothing to do: plain empty cFP set
+        } else if (step == 1) {
+            if (nshare_) bloom_cascade_kernel<K><<<grid_for(nshare_), 256, 0, stream_>>>(share_.p, nshare_, b2_.bits.p, b2_.tai, b3_.bits.p, b3_.tai, nh, seed0_, rnd_.p);
+            st_.launches++;
+        } else if (step == 2) {
+            if (ncrit_) bloom_cascade_kernel<K><<<grid_for(ncrit_), 256, 0, stream_>>>(crit_list_.p, ncrit_, b3_.bits.p, b3_.tai, b4_.bits.p, b4_.tai, nh, seed0_, rnd_.p);
+            st_.launches++;
+        } else if (step == 3) {
+            for (uint64_t cap = nshare_ / 16 + 1024;; cap = nshare_ + 1024) {
+                cfp_local_.alloc(cap);
+                MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 8, stream_));
+                err_.zero(stream_);
+                if (nshare_) cfp_set_kernel<K><<<grid_for(nshare_), 256, 0, stream_>>>(share_.p, nshare_, b2_.bits.p, b2_.tai, b4_.bits.p, b4_.tai, nh, seed0_, rnd_.p,
+                                                                                      cfp_local_.p, counters_.p, cap, err_.p);
+                st_.launches++;
+                int e = 0;
+                unsigned long long nc = 0;
+                MTG_CUDA(cudaMemcpyAsync(&e, err_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+                MTG_CUDA(cudaMemcpyAsync(&nc, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
+                MTG_CUDA(cudaStreamSynchronize(stream_));
+                if (!e) { ncfp_local_ = nc; break; }
+                if (cap >= nshare_ + 1024) throw Error(-6, "cfp set overflow");
+            }
+            ret = ncfp_local_;
+        } else throw Error(-1, "shard_cascade: step 0..3");
+        MTG_CUDA(cudaGetLastError());
+        st_.ms_cascade += t.stop();
+        return ret;
+    }
+    void set_cfp(const void* d_all, uint64_t n) override {
+        ncfp_ = n;
+        cfp_.alloc(std::max<uint64_t>(n, 1));
+        if (n) {  // small: sort on the host (std::sort of cfpItems, DebloomAlgorithm.cpp:561)
+            std::vector<K> h(n);
+            MTG_CUDA(cudaMemcpyAsync(h.data(), d_all, n * sizeof(K), cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaStreamSynchronize(stream_));
+            std::sort(h.begin(), h.end());
+            MTG_CUDA(cudaMemcpyAsync(cfp_.p, h.data(), n * sizeof(K), cudaMemcpyHostToDevice, stream_));
+            MTG_CUDA(cudaStreamSynchronize(stream_));
+        }
+        st_.ncfp = n;
+        cfp_local_.release();
+    }
+    void shard_finish() override {
+        EvTimer t(stream_);
+        t.start();
+        const uint64_t N = ntotal_;
+        DevBuf<K> all(std::max<uint64_t>(N, 1));
+        MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 8, stream_));
+        const uint64_t nb = nbuckets_ * nshards_;
+        table_compact_kernel<K><<<grid_for(nb * TableCfg<K>::SLOTS), 256, 0, stream_>>>(table_.p, nb, all.p, counters_.p);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches++;
+        unsigned long long got = 0;
+        MTG_CUDA(cudaMemcpyAsync(&got, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        if (got != N) throw Error(-6, "gathered table holds " + std::to_string(got) + " k-mers, expected " + std::to_string(N));
+        build_mphf(all.p, N);
+        st_.ms_mphf = t.stop();
+        share_.release();
+        adj_done_ = true;
+    }
+    void buffer(int which, void** p, uint64_t* nbytes) override {
+        BloomDev* b = which == 1 ? &bloom_ : which == 2 ? &b2_ : which == 3 ? &b3_ : which == 4 ? &b4_ : nullptr;
+        if (b) { *p = b->bits.p; *nbytes = b->bits.n * 4; }
+        else if (which == 0) { *p = table_.p; *nbytes = nbuckets_ * nshards_ * (uint64_t)BUCKET_BYTES; }
+        else if (which == 5) { *p = adjbuf_.p; *nbytes = adjbuf_.n * 16; }
+        else if (which == 6) { *p = cfp_local_.p; *nbytes = ncfp_local_ * sizeof(K); }
+        else if (which == 7) { *p = crit_list_.p; *nbytes = ncrit_ * sizeof(K); }
+        else throw Error(-1, "buffer: which 0..7");
+    }
+    void or_chunks(const void* d_in, uint32_t nchunks, uint64_t nwords, void* d_out) override {
+        if (!nwords) return;
+        or_chunks_kernel<<<grid_for(nwords), 256, 0, stream_>>>((const unsigned long long*)d_in, nchunks, nwords, (unsigned long long*)d_out);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches++;
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    // BooPHF levels from a device list of all solid k-mers
+    void build_mphf(const K* keys, uint64_t N) {
+        // ---- BooPHF levels (sizes: mphf::setup, BooPHF.h:1015-1041, double arithmetic on the host)
         mphf_built_ = false;
         nfinal_ = 0;
         final_.alloc(1);
@@ -734,8 +1040,6 @@ public:
             }
             mphf_built_ = true;
         }
-        st_.ms_mphf = t.stop();
-        tr.mark("graph: mphf");
     }
 
     void set_ref_repeats(const void* d_keys, uint64_t n) override {

@@ -15,8 +15,11 @@ static const int MPHF_LEVELS = 25;  // BooPHF: _nb_levels = 25 (thirdparty/BooPH
 template <class K> struct GraphView {
     int k;
     // exact table: nbuckets buckets of 128 bytes (14 u64 keys or 7 u128 keys + 16 adjacency bytes); empty slot = all ones
+    // With N GPUs the table is `nshards` equal ranges of `nbuckets` buckets: range r is built by rank r from the solid k-mers
+    // whose hash selects it (shard_of) and the ranges are all-gathered; one range on a single GPU.
     const K* table;
     uint64_t nbuckets;
+    uint32_t nshards;
     // Bloom filters as little-endian u32 words (bit pos -> word pos>>5, bit pos&31 == byte pos>>3, bit pos&7)
     const uint32_t* bloom; uint64_t bloom_tai; int bloom_nhash;      // BloomNeighborCoherent (main)
     int cascading;                                                   // 0 -> cFP is the plain sorted set `cfp`
@@ -188,8 +191,11 @@ template <class K> struct TableCfg { static const int SLOTS = BUCKET_KEY_BYTES /
 
 // Probe by one thread: the whole 128-byte bucket with eight 128-bit loads (one line, 4 sectors). Returns the slot of
 // `key` in [0, SLOTS) (and the bucket in *bucket_out) or -1; *adj receives the adjacency byte of the slot.
-template <class K> MTG_D int table_find(const K* __restrict__ table, uint64_t nbuckets, K key, uint64_t* bucket_out, unsigned* adj) {
-    uint64_t b = key_hash(key) % nbuckets;
+MTG_HD uint32_t shard_of(uint64_t h, uint32_t nshards) { return (uint32_t)(((h >> 32) * (uint64_t)nshards) >> 32); }
+template <class K> MTG_D int table_find(const K* __restrict__ table, uint64_t nbuckets, uint32_t nshards, K key, uint64_t* bucket_out, unsigned* adj) {
+    const uint64_t h = key_hash(key);
+    uint64_t b = h % nbuckets;
+    table += (uint64_t)shard_of(h, nshards) * nbuckets * TableCfg<K>::STRIDE;   // linear probing stays inside the key's range
     for (uint64_t probe = 0; probe < nbuckets; probe++) {
         const uint4* q = reinterpret_cast<const uint4*>(table + b * TableCfg<K>::STRIDE);
         uint4 v[8];
@@ -212,7 +218,7 @@ template <class K> MTG_D int table_find(const K* __restrict__ table, uint64_t nb
         if (slot >= 0) {
             const unsigned w = (slot >> 2) == 0 ? v[7].x : (slot >> 2) == 1 ? v[7].y : (slot >> 2) == 2 ? v[7].z : v[7].w;
             if (adj) *adj = (w >> (8 * (slot & 3))) & 0xFFu;
-            if (bucket_out) *bucket_out = b;
+            if (bucket_out) *bucket_out = (uint64_t)shard_of(h, nshards) * nbuckets + b;
             return slot;
         }
         if (has_empty) return -1;
@@ -220,8 +226,8 @@ template <class K> MTG_D int table_find(const K* __restrict__ table, uint64_t nb
     }
     return -1;
 }
-template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key) { return table_find<K>(g.table, g.nbuckets, key, nullptr, nullptr) >= 0; }
-template <class K> MTG_D bool table_lookup(const GraphView<K>& g, K key, unsigned& adj) { return table_find<K>(g.table, g.nbuckets, key, nullptr, &adj) >= 0; }
+template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key) { return table_find<K>(g.table, g.nbuckets, g.nshards, key, nullptr, nullptr) >= 0; }
+template <class K> MTG_D bool table_lookup(const GraphView<K>& g, K key, unsigned& adj) { return table_find<K>(g.table, g.nbuckets, g.nshards, key, nullptr, &adj) >= 0; }
 
 // Graph::contains for a CANONICAL k-mer. *used_fallback is set when the exact table missed and the Bloom emulation
 // had to answer (counted separately from the roofline probes).
@@ -292,6 +298,28 @@ public:
     virtual const void* critical_device() const = 0;
     virtual void critical_merge(const void* d_candidates, uint64_t n) = 0;
     virtual void build_rest(const void* d_solid_keys, uint64_t n) = 0;
+    // ---- build on N GPUs: every rank holds the solid k-mers of ONE table range (keys routed by shard_of) and the
+    // critical k-mers of the same range; each step works on these shares only and leaves a buffer that the host all-gathers
+    // (table ranges, adjacency bytes, cFP set) or OR-reduces (Bloom bit arrays) before the next step.
+    //   partition_keys: groups n keys by shard_of(key_hash) into d_out (counts per shard on the host), for the all-to-all
+    virtual void partition_keys(const void* d_keys, uint64_t n, uint32_t nshards, void* d_out, uint64_t* counts_host) = 0;
+    //   shard_begin: allocates all ranges (sized for max_share keys each), builds range `shard` from the share, sizes the main
+    //   Bloom for n_total k-mers and inserts the share
+    virtual void shard_begin(const void* d_keys_share, uint64_t n_share, uint64_t n_total, uint64_t max_share, uint32_t nshards, uint32_t shard) = 0;
+    //   shard_critical: 8 neighbours of every k-mer of the share against the gathered table and the reduced Bloom: adjacency
+    //   bytes of the own range + the share's critical candidates (de-duplicated within the share); returns their number
+    virtual uint64_t shard_critical() = 0;
+    virtual void adj_pack() = 0;     // adjacency bytes of the own range -> buffer 5 (all ranges, for the in-place all-gather)
+    virtual void adj_unpack() = 0;   // buffer 5 -> adjacency bytes of the other ranges
+    //   shard_cascade(step): 0 sizes B2/B3/B4 from the totals and inserts the critical share into B2; 1 share(solid) in B2 -> B3;
+    //   2 share(critical) in B3 -> B4; 3 share(solid) in B2 and B4 -> local cFP list (returns its length, buffer 6)
+    virtual uint64_t shard_cascade(int step, uint64_t ncrit_total) = 0;
+    virtual void set_cfp(const void* d_all, uint64_t n) = 0;   // the gathered cFP set (sorted here)
+    virtual void shard_finish() = 0;                            // BooPHF levels from the gathered table; graph ready
+    // which: 0 table, 1 main Bloom, 2..4 B2..B4, 5 adjacency bytes, 6 local cFP list, 7 critical share; device pointer + bytes
+    virtual void buffer(int which, void** p, uint64_t* nbytes) = 0;
+    // out[i] = OR over c of in[c * nwords + i] (64-bit words): the reduction of an OR-reduce-scatter
+    virtual void or_chunks(const void* d_in, uint32_t nchunks, uint64_t nwords, void* d_out) = 0;
     // repeated (k-1)-mers of the reference (device array of canonical K values with abundance >= het_max_occ+1)
     virtual void set_ref_repeats(const void* d_keys, uint64_t n) = 0;
     // batch queries on host arrays of FORWARD k-mers (any strand); out[i] bit0 = contains

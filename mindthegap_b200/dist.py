@@ -59,16 +59,40 @@ def segment_bounds(npos, world):
     return b
 
 
-class DistFind:
-    def __init__(self, engine, device, group=None, scan_mode="auto"):
-        """scan_mode: "chromosomes" = every rank scans whole chromosomes (no feature exchange), "segments" = every chromosome
-        is split across the ranks by position, "auto" = chromosomes when they balance within 25 %, else segments."""
-        self.e = engine
-        self.scan_mode = scan_mode
-        self.device = device
+class TorchComm:
+    """The four collectives DistFind needs, over torch.distributed (NCCL on GPUs, gloo in the CPU tests). Tests may pass any
+    object with the same methods as DistFind(comm=...), e.g. an in-process emulation that runs N ranks on one GPU."""
+
+    def __init__(self, group=None):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+
+    def all_reduce(self, t, op):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self.group)
+
+    def all_gather_into_tensor(self, out, inp):
+        dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def all_to_all_single(self, out, inp, output_split_sizes=None, input_split_sizes=None):
+        dist.all_to_all_single(out, inp, output_split_sizes=output_split_sizes, input_split_sizes=input_split_sizes, group=self.group)
+
+
+class DistFind:
+    OR_SMALL_WORDS = 1 << 17   # gathered size (64-bit words) up to which _or_reduce takes the single all-gather route
+
+    def __init__(self, engine, device, group=None, scan_mode="auto", build_mode="sharded", comm=None):
+        """scan_mode: "chromosomes" = every rank scans whole chromosomes (no feature exchange), "segments" = every chromosome
+        is split across the ranks by position, "auto" = chromosomes when they balance within 25 %, else segments.
+        build_mode: "sharded" = the membership structures are built from per-rank shares (table ranges all-gathered, Bloom bit
+        arrays OR-reduced), "replicated" = every rank builds everything from the all-gathered solid set."""
+        self.e = engine
+        self.scan_mode = scan_mode
+        self.build_mode = build_mode
+        self.device = device
+        self.c = comm if comm is not None else TorchComm(group)
+        self.rank = self.c.rank
+        self.world = self.c.world
         self.k = engine.params.kmer_size
         self.timing = {}
         self._t = None
@@ -90,13 +114,13 @@ class DistFind:
 
     def _all_max(self, *vals):
         t = torch.tensor(list(vals), dtype=torch.int64, device=self.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.c.all_reduce(t, "max")
         return [int(x) for x in t.tolist()]
 
     def _all_gather_i64(self, val):
         t = torch.tensor([val], dtype=torch.int64, device=self.device)
         out = torch.empty(self.world, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(out, t, group=self.group)
+        self.c.all_gather_into_tensor(out, t)
         return [int(x) for x in out.tolist()]
 
     def _gather_texts(self, texts):
@@ -109,7 +133,7 @@ class DistFind:
         t = torch.zeros(m, dtype=torch.uint8, device=self.device)
         t[:len(blob)] = torch.from_numpy(blob.copy()).to(self.device)
         out = torch.empty(m * self.world, dtype=torch.uint8, device=self.device)
-        dist.all_gather_into_tensor(out, t, group=self.group)
+        self.c.all_gather_into_tensor(out, t)
         if self.rank != 0:
             return None
         host = out.cpu().numpy()
@@ -122,7 +146,7 @@ class DistFind:
         above; mtg_set_minimizer_size) is applied to the GLOBAL read volume here, before the first push."""
         n = int(nbytes if dev_ptr is not None else len(stream))
         t = torch.tensor([n], dtype=torch.int64, device=self.device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        self.c.all_reduce(t, "sum")
         self.e.set_minimizer_size(13 if int(t.item()) >= (1 << 30) else min(10, self.k - 1))
         if dev_ptr is not None:
             self._sync()
@@ -143,18 +167,18 @@ class DistFind:
         e.count_copy_packed(packed, inv)
         packed_all = torch.empty(seg * W, dtype=torch.int64, device=self.device)
         inv_all = torch.empty(seg * W, dtype=torch.int32, device=self.device)
-        dist.all_gather_into_tensor(packed_all, packed, group=self.group)
-        dist.all_gather_into_tensor(inv_all, inv, group=self.group)
+        self.c.all_gather_into_tensor(packed_all, packed)
+        self.c.all_gather_into_tensor(inv_all, inv)
         self._mark("allgather_packed")
         # records -> owners
         send = torch.empty(max(nrec, 1), dtype=torch.int64, device=self.device)
         counts = e.count_partition_records(W, self.rank * seg * 32, send)
         cnt_t = torch.tensor(counts, dtype=torch.int64, device=self.device)
         rcv_t = torch.empty(W, dtype=torch.int64, device=self.device)
-        dist.all_to_all_single(rcv_t, cnt_t, group=self.group)
+        self.c.all_to_all_single(rcv_t, cnt_t)
         rcounts = [int(x) for x in rcv_t.tolist()]
         recv = torch.empty(max(sum(rcounts), 1), dtype=torch.int64, device=self.device)
-        dist.all_to_all_single(recv[:sum(rcounts)], send[:nrec], output_split_sizes=rcounts, input_split_sizes=counts, group=self.group)
+        self.c.all_to_all_single(recv[:sum(rcounts)], send[:nrec], output_split_sizes=rcounts, input_split_sizes=counts)
         self.exchange_bytes = {"allgather_packed": int(packed_all.numel() * 12), "alltoall_records": int(8 * sum(rcounts))}
         self._mark("alltoall_records")
         # count the owned partition, merge the histograms, filter
@@ -163,11 +187,21 @@ class DistFind:
         e.count_run()
         self._mark("count_run")
         h = torch.from_numpy(e.histogram().astype(np.int64)).to(self.device)
-        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.group)
+        self.c.all_reduce(h, "sum")
         self.histogram = h.cpu().numpy().astype(np.uint64)
         e.count_filter(self.histogram)
         self._mark("histogram_allreduce+filter")
         del packed_all, inv_all, recv, send
+        if self.build_mode == "replicated":
+            self._build_replicated()
+        else:
+            self._build_sharded()
+        self._mark("graph_build")
+        return self.nb_solid
+
+    # ---- stage 1b, variant A: every rank builds everything from the all-gathered solid set (kept as the cross-check of B)
+    def _build_replicated(self):
+        e, W = self.e, self.world
         # all-gather the solid shares, build the full graph on every rank
         kw = e.key_words
         n_local = e.nb_solid_local()
@@ -177,7 +211,7 @@ class DistFind:
         self._sync()
         e.solid_copy(keys, None)
         keys_all = torch.empty(nmax * kw * W, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(keys_all, keys, group=self.group)
+        self.c.all_gather_into_tensor(keys_all, keys)
         parts = [keys_all[r * nmax * kw: r * nmax * kw + sizes[r] * kw] for r in range(W)]
         solid = torch.cat(parts) if sum(sizes) else torch.zeros(kw, dtype=torch.int64, device=self.device)
         self.nb_solid = sum(sizes)
@@ -193,13 +227,117 @@ class DistFind:
         self._sync()
         e.graph_critical_copy(cand)
         cand_all = torch.empty(cmax * kw * W, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(cand_all, cand, group=self.group)
+        self.c.all_gather_into_tensor(cand_all, cand)
         cands = torch.cat([cand_all[r * cmax * kw: r * cmax * kw + csizes[r] * kw] for r in range(W)]) if sum(csizes) else cand
         self.exchange_bytes["allgather_critical"] = int(cand_all.numel() * 8)
         self._sync()
         e.graph_build_end(solid, self.nb_solid, cands, sum(csizes))
-        self._mark("graph_build")
-        return self.nb_solid
+
+
+    # ---- stage 1b, variant B: the build itself is sharded by table range (include/mtg_b200.h "SHARDED over N GPUs")
+    def _all_to_all_keys(self, send, counts):
+        """Variable all-to-all of k-mer keys (counts in keys per destination); returns (received tensor, total received)."""
+        kw = self.e.key_words
+        cnt_t = torch.tensor(counts, dtype=torch.int64, device=self.device)
+        rcv_t = torch.empty(self.world, dtype=torch.int64, device=self.device)
+        self.c.all_to_all_single(rcv_t, cnt_t)
+        rcounts = [int(x) for x in rcv_t.tolist()]
+        nin, nout = sum(counts), sum(rcounts)
+        recv = torch.empty(max(nout, 1) * kw, dtype=torch.int64, device=self.device)
+        self.c.all_to_all_single(recv[:nout * kw], send[:nin * kw], output_split_sizes=[c * kw for c in rcounts],
+                               input_split_sizes=[c * kw for c in counts])
+        return recv, nout
+
+    def _all_gather_ranges(self, buf):
+        """buf (uint8 view of library memory) = W equal ranges, range `rank` filled: all-gather in place."""
+        part = buf.numel() // self.world
+        mine = buf[self.rank * part:(self.rank + 1) * part].clone()
+        self.c.all_gather_into_tensor(buf[:part * self.world], mine)
+
+    def _or_reduce(self, bits):
+        """Bitwise OR of a uint8 array over the ranks, in place. NCCL has no OR: small arrays are all-gathered and reduced
+        locally; large ones go reduce-scatter style (all-to-all of the W chunks, local OR of the chunk this rank owns,
+        all-gather of the reduced chunks), which moves 2 x size instead of W x size."""
+        e, W = self.e, self.world
+        n = bits.numel()
+        words = (n + 7) // 8
+        if words * W <= self.OR_SMALL_WORDS:
+            mine = torch.zeros(words, dtype=torch.int64, device=self.device)
+            mine.view(torch.uint8)[:n] = bits
+            allb = torch.empty(words * W, dtype=torch.int64, device=self.device)
+            self.c.all_gather_into_tensor(allb, mine)
+            self._sync()
+            e.or_chunks(allb, W, words, mine)
+            bits.copy_(mine.view(torch.uint8)[:n])
+            return
+        chunk = (words + W - 1) // W
+        send = torch.zeros(chunk * W, dtype=torch.int64, device=self.device)
+        send.view(torch.uint8)[:n] = bits
+        recv = torch.empty(chunk * W, dtype=torch.int64, device=self.device)
+        self.c.all_to_all_single(recv, send)
+        red = torch.empty(chunk, dtype=torch.int64, device=self.device)
+        self._sync()
+        e.or_chunks(recv, W, chunk, red)
+        self.c.all_gather_into_tensor(send, red)
+        bits.copy_(send.view(torch.uint8)[:n])
+
+    def _build_sharded(self):
+        e, W, kw = self.e, self.world, self.e.key_words
+        # solid k-mers -> the rank that owns their table range
+        n_local = e.nb_solid_local()
+        send = torch.empty(max(n_local, 1) * kw, dtype=torch.int64, device=self.device)
+        self._sync()
+        counts = e.solid_partition(W, send)
+        share, n_share = self._all_to_all_keys(send, counts)
+        shares = self._all_gather_i64(n_share)
+        self.nb_solid = sum(shares)
+        self.exchange_bytes["alltoall_solid"] = int(8 * kw * n_share)
+        self._mark("alltoall_solid")
+        # own table range + own share in the main Bloom; ranges all-gathered, Bloom OR-reduced
+        self._sync()
+        e.graph_shard_begin(share, n_share, self.nb_solid, max(shares), W, self.rank)
+        table = e.graph_buffer(0)
+        self._all_gather_ranges(table)
+        bloom = e.graph_buffer(1)
+        self._or_reduce(bloom)
+        self.exchange_bytes["allgather_table"] = int(table.numel())
+        self.exchange_bytes["or_reduce_bloom"] = int(bloom.numel())
+        self._mark("table+bloom")
+        # neighbours of the share: adjacency bytes of the own range (all-gathered) + critical candidates (to their owners)
+        self._sync()
+        nc = e.graph_shard_critical()
+        e.graph_adj_pack()
+        self._all_gather_ranges(e.graph_buffer(5))
+        self._sync()
+        e.graph_adj_unpack()
+        csend = torch.empty(max(nc, 1) * kw, dtype=torch.int64, device=self.device)
+        ccounts = e.partition_keys(e.graph_buffer(7), nc, W, csend)
+        crecv, ncr = self._all_to_all_keys(csend, ccounts)
+        self._sync()
+        ncrit_share = e.graph_critical_set_share(crecv, ncr)
+        ncrit_total = sum(self._all_gather_i64(ncrit_share))
+        self.nb_critical = ncrit_total
+        self._mark("critical+adjacency")
+        # cascading Blooms: every step inserts from the shares, then the bit arrays are OR-reduced
+        ncfp_local = 0
+        for step in range(4):
+            self._sync()
+            ncfp_local = e.graph_shard_cascade(step, ncrit_total)
+            if step < 3 and ncrit_total:
+                self._or_reduce(e.graph_buffer(2 + step))
+        sizes = self._all_gather_i64(ncfp_local)
+        cmax = max(max(sizes), 1)
+        part = torch.zeros(cmax * kw, dtype=torch.int64, device=self.device)
+        if ncfp_local:
+            part.view(torch.uint8)[:ncfp_local * kw * 8] = e.graph_buffer(6)
+        allp = torch.empty(cmax * kw * W, dtype=torch.int64, device=self.device)
+        self.c.all_gather_into_tensor(allp, part)
+        cfp = torch.cat([allp[r * cmax * kw: r * cmax * kw + sizes[r] * kw] for r in range(W)]) if sum(sizes) else part
+        self._sync()
+        e.graph_set_cfp(cfp, sum(sizes))
+        self._mark("cascade")
+        e.graph_shard_finish()
+        self._mark("mphf")
 
     # ---- stage 2: scan. ref_records: [(name, uint8 numpy array)] identical on every rank
     def scan(self, ref_records, ref_stream=None):
@@ -245,7 +383,7 @@ class DistFind:
                 buf[segmax:segmax + (a1 - a0)] = r
                 buf[2 * segmax:2 * segmax + 4 * it.numel()] = it.view(torch.uint8)
             allbuf = torch.empty(stride * W, dtype=torch.uint8, device=self.device)
-            dist.all_gather_into_tensor(allbuf, buf, group=self.group)
+            self.c.all_gather_into_tensor(allbuf, buf)
             if ci % W == self.rank:
                 mine.append((ci, name, seq, b, segmax, iw, stride, allbuf.cpu()))
         self._mark("features+allgather")

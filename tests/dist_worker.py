@@ -130,6 +130,103 @@ class FakeEngine:
         assert np.isin(cand_t.numpy().view(np.uint64)[:ncand], self._all).all()
         self.g = oracle_py.Graph(self._all, np.zeros(n, dtype=np.uint64), self.k)
 
+    # -- stage 1b sharded by table range (fake buffers: enough structure to check every exchange of dist.py)
+    @staticmethod
+    def _owner(keys, nshards):
+        return ((keys * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)) % np.uint64(nshards)
+
+    def _group(self, keys, nshards, out_t):
+        owner = self._owner(keys, nshards)
+        order = np.argsort(owner, kind="stable")
+        out_t[:len(keys)] = torch.from_numpy(keys[order].view(np.int64))
+        return [int((owner == d).sum()) for d in range(nshards)]
+
+    def solid_partition(self, nshards, out_t):
+        return self._group(self.solid, nshards, out_t)
+
+    def partition_keys(self, keys_t, n, nshards, out_t):
+        return self._group(keys_t.numpy().view(np.uint64)[:n].copy(), nshards, out_t)
+
+    @staticmethod
+    def _bloom_positions(keys, nbits):
+        return (keys % np.uint64(nbits)).astype(np.int64)
+
+    def graph_shard_begin(self, keys_t, n_share, n_total, max_share, nshards, shard):
+        share = np.sort(keys_t.numpy().view(np.uint64)[:n_share])
+        assert (self._owner(share, nshards) == shard).all(), "a key was routed to the wrong range owner"
+        self.share, self.n_total, self.max_share, self.W, self.shard = share, n_total, max(max_share, 1), nshards, shard
+        table = np.full((nshards, self.max_share), ~np.uint64(0), dtype=np.uint64)
+        table[shard, :n_share] = share
+        nbits = (n_total * 6 + 64) // 8 * 8 + 24          # deliberately not a multiple of 64 bits
+        bloom = np.zeros(nbits // 8, dtype=np.uint8)
+        pos = self._bloom_positions(share, nbits)
+        np.bitwise_or.at(bloom, pos >> 3, (1 << (pos & 7)).astype(np.uint8))
+        self.buf = {0: torch.from_numpy(table.reshape(-1).view(np.uint8)), 1: torch.from_numpy(bloom)}
+        self.nbits = nbits
+
+    def graph_buffer(self, which):
+        return self.buf[which]
+
+    def _cands_of(self, r):
+        sh = self._all[self._owner(self._all, self.W) == r]
+        return np.concatenate([sh[:3 + r] + np.uint64(1), np.array([12345], dtype=np.uint64)])
+
+    def graph_shard_critical(self):
+        table = self.buf[0].numpy().view(np.uint64)
+        self._all = np.sort(table[table != ~np.uint64(0)])
+        assert len(self._all) == self.n_total == len(np.unique(self._all)), "gathered table does not hold the whole solid set"
+        want = np.zeros(self.nbits // 8, dtype=np.uint8)
+        pos = self._bloom_positions(self._all, self.nbits)
+        np.bitwise_or.at(want, pos >> 3, (1 << (pos & 7)).astype(np.uint8))
+        assert (self.buf[1].numpy() == want).all(), "OR-reduced Bloom differs from the Bloom of the whole set"
+        self._crit = self._cands_of(self.shard)
+        self.buf[7] = torch.from_numpy(self._crit.view(np.uint8))
+        return len(self._crit)
+
+    def graph_adj_pack(self):
+        adj = np.zeros((self.W, self.max_share), dtype=np.uint8)
+        adj[self.shard] = self.shard + 1
+        self.buf[5] = torch.from_numpy(adj.reshape(-1))
+
+    def graph_adj_unpack(self):
+        adj = self.buf[5].numpy().reshape(self.W, self.max_share)
+        assert all((adj[c] == c + 1).all() for c in range(self.W)), "adjacency ranges were not all-gathered"
+
+    def graph_critical_set_share(self, cand_t, n):
+        got = np.unique(cand_t.numpy().view(np.uint64)[:n])
+        assert (self._owner(got, self.W) == self.shard).all()
+        allc = np.unique(np.concatenate([self._cands_of(r) for r in range(self.W)]))
+        assert (got == allc[self._owner(allc, self.W) == self.shard]).all(), "critical share differs from the expected one"
+        self._ncrit_expected = len(allc)
+        self._crit = got
+        return len(got)
+
+    def graph_shard_cascade(self, step, ncrit_total):
+        assert ncrit_total == self._ncrit_expected
+        if step >= 1:
+            prev = self.buf[2 + step - 1].numpy()
+            assert prev[0] == (1 << self.W) - 1 and prev[-1] == (1 << self.W) - 1, "cascading Bloom %d was not OR-reduced" % (step + 1)
+        if step < 3:
+            b = np.zeros(1003 if step == 0 else 40, dtype=np.uint8)   # one large-ish, two small: both OR-reduce routes at W=2..3
+            b[0] = b[-1] = 1 << self.shard
+            self.buf[2 + step] = torch.from_numpy(b)
+            return 0
+        mine = self.share[:2].copy()
+        self.buf[6] = torch.from_numpy(mine.view(np.uint8))
+        return len(mine)
+
+    def graph_set_cfp(self, cfp_t, n):
+        got = np.sort(cfp_t.numpy().view(np.uint64)[:n])
+        want = np.sort(np.concatenate([self._all[self._owner(self._all, self.W) == r][:2] for r in range(self.W)]))
+        assert (got == want).all(), "gathered cFP set differs"
+
+    def graph_shard_finish(self):
+        self.g = oracle_py.Graph(self._all, np.zeros(len(self._all), dtype=np.uint64), self.k)
+
+    def or_chunks(self, in_t, nchunks, nwords, out_t):
+        a = in_t.numpy().view(np.uint64)[:nchunks * nwords].reshape(nchunks, nwords)
+        out_t[:nwords] = torch.from_numpy(np.bitwise_or.reduce(a, axis=0).view(np.int64))
+
     # -- stage 2
     def set_reference(self, stream):
         self.g.set_reference(bytes(stream), self.params.het_max_occ)
@@ -178,7 +275,9 @@ def main():
     recs = oracle_py.read_sequences(reads)
     mine = recs[rank::world]                      # any split of the reads gives the same counts
     eng = FakeEngine(api.FindParams.from_cli(["-kmer-size", str(case["k"])] + list(case["flags"])))
-    d = DistFind(eng, torch.device("cpu"), scan_mode=sys.argv[3] if len(sys.argv) > 3 else "auto")
+    d = DistFind(eng, torch.device("cpu"), scan_mode=sys.argv[3] if len(sys.argv) > 3 else "auto",
+                 build_mode=sys.argv[4] if len(sys.argv) > 4 else "sharded")
+    d.OR_SMALL_WORDS = 64                         # the Bloom and B2 stand-ins take the reduce-scatter route, B3/B4 the small one
     d.push_reads(b"\n".join(s for _, s in mine) + b"\n")
     assert eng.minimizer_size == min(10, case["k"] - 1)
     refs = [(n, np.frombuffer(s, dtype=np.uint8)) for n, s in oracle_py.read_sequences(ref)]

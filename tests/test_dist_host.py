@@ -17,15 +17,16 @@ def free_port():
     return p
 
 
-@pytest.mark.parametrize("case,world,mode", [("syn_tiny_k31", 2, "auto"), ("full", 2, "segments"), ("full", 2, "chromosomes"),
-                                             ("syn_tiny_k31", 3, "segments"), ("full", 3, "auto")])
-def test_two_rank_find_equals_reference(tmp_path, oracle, case, world, mode):
+@pytest.mark.parametrize("case,world,mode,build", [("syn_tiny_k31", 2, "auto", "sharded"), ("full", 2, "segments", "sharded"),
+                                                   ("full", 2, "chromosomes", "replicated"), ("syn_tiny_k31", 3, "segments", "replicated"),
+                                                   ("full", 3, "auto", "sharded")])
+def test_two_rank_find_equals_reference(tmp_path, oracle, case, world, mode, build):
     out = str(tmp_path / "out.json")
     port = free_port()
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
-        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), case, out, mode], env=env,
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), case, out, mode, build], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
