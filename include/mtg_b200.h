@@ -175,6 +175,11 @@ int mtg_scan_reference(mtg_ctx* ctx, const char* name, const char* seq, uint64_t
 /* same with the sequence also resident in HBM (d_seq): no host->device copy; `seq` (host text) is still needed by the
  * writers, which print raw reference text (src/FindInsertion.hpp:100-133, src/FindDeletion.hpp:62-171). */
 int mtg_scan_reference_device(mtg_ctx* ctx, const char* name, const char* seq, const void* d_seq, uint64_t len);
+/* The same scan restricted to bed intervals (-bed, src/FindBreakpoints.hpp:459-553): begin_end holds n_intervals (begin, end)
+ * pairs of THIS chromosome in bed-file order, already filtered like the reference does ((end - begin) > k, :486); the gap
+ * machine and the history ring restart at every interval, positions outside advance the ring indices only. The host parses
+ * the bed text (csrc/seqio.hpp bed_intervals, api.py parse_bed). n_intervals == 0 scans nothing, like the reference. */
+int mtg_scan_reference_bed(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len, const uint64_t* begin_end, uint64_t n_intervals);
 /* Event replay of one sequence over caller-provided host feature arrays (e.g. gathered from several GPUs); observer probes
  * are answered by this context's GPU. interest may be NULL (walk every position). */
 int mtg_replay_sequence(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len, const uint8_t* feat, const uint8_t* rep,

@@ -4,6 +4,7 @@ There is NO fallback: if the CUDA library is missing or no CUDA device is presen
 """
 import ctypes as C
 import os
+import re
 import subprocess
 from dataclasses import dataclass, field
 
@@ -37,7 +38,7 @@ EXPORTS = [
     "mtg_push_reads_device", "mtg_count_files", "mtg_count_finish", "mtg_get_threshold", "mtg_get_cutoff_auto", "mtg_get_nb_solid",
     "mtg_get_histogram", "mtg_get_stats", "mtg_stat_name", "mtg_export_solid", "mtg_load_solid", "mtg_set_reference",
     "mtg_contains_batch", "mtg_degree_batch", "mtg_ref_repeat_batch", "mtg_sequence_features", "mtg_sequence_features_device",
-    "mtg_scan_reference", "mtg_scan_reference_device", "mtg_set_reference_device", "mtg_breakpoints_text", "mtg_vcf_text", "mtg_reset_outputs", "mtg_get_find_counters", "mtg_copy_bits",
+    "mtg_scan_reference", "mtg_scan_reference_bed", "mtg_scan_reference_device", "mtg_set_reference_device", "mtg_breakpoints_text", "mtg_vcf_text", "mtg_reset_outputs", "mtg_get_find_counters", "mtg_copy_bits",
     "mtg_bench_random_gather", "mtg_count_local_info", "mtg_count_copy_packed", "mtg_count_partition_records", "mtg_count_import",
     "mtg_count_run", "mtg_count_filter", "mtg_solid_copy", "mtg_graph_build_device", "mtg_sequence_features_device2", "mtg_replay_sequence",
     "mtg_graph_build_begin", "mtg_graph_critical", "mtg_graph_critical_copy", "mtg_graph_build_end", "mtg_set_host_threads", "mtg_set_minimizer_size", "mtg_get_minimizer_size",
@@ -91,6 +92,7 @@ def load_library():
     L.mtg_sequence_features_device.argtypes = [vp, vp, C.c_uint64, vp, vp, u64p]
     L.mtg_scan_reference.argtypes = [vp, C.c_char_p, vp, C.c_uint64]
     L.mtg_scan_reference_device.argtypes = [vp, C.c_char_p, vp, vp, C.c_uint64]
+    L.mtg_scan_reference_bed.argtypes = [vp, C.c_char_p, vp, C.c_uint64, vp, C.c_uint64]
     L.mtg_set_reference_device.argtypes = [vp, vp, C.c_uint64]
     L.mtg_breakpoints_text.restype = vp
     L.mtg_breakpoints_text.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -180,6 +182,37 @@ class FindParams:
         p.flags = (F_HOMO_ONLY * homo_only | F_HOMO_INSERT * homo_insert | F_HETE_INSERT * hete_insert | F_SNP * snp |
                    F_BACKUP * backup | F_DELETION * deletion | F_SMALL_HOMO * small)
         return p
+
+
+_STOI = re.compile(r"[ \t\n\v\f\r]*([+-]?[0-9]+)")
+
+
+def parse_bed(text, chrom, k):
+    """Intervals of one chromosome as the reference reads them (src/FindBreakpoints.hpp:462-495): skip empty lines and lines
+    starting with '#' or '@'; tab-separated; field 0 == chromosome short name; begin/end through std::stoi semantics (leading
+    blanks, sign, digits, the rest ignored); kept when (end - begin) > k in unsigned 64-bit arithmetic."""
+    if isinstance(text, bytes):
+        text = text.decode()
+    if isinstance(chrom, bytes):
+        chrom = chrom.decode()
+    out = []
+    for line in text.split("\n"):
+        if not line or line[0] in "#@":
+            continue
+        v = line.split("\t")
+        if v[0] != chrom:
+            continue
+        if len(v) < 3:
+            raise MtgError("bed: fewer than 3 tab-separated fields in line: " + line)
+        vals = []
+        for f in v[1:3]:
+            m = _STOI.match(f)
+            if not m or not -2**31 <= int(m.group(1)) < 2**31:
+                raise MtgError("bed: not a number (or out of int range) in line: " + line)
+            vals.append(int(m.group(1)))
+        if ((vals[1] - vals[0]) & 0xFFFFFFFFFFFFFFFF) > k:
+            out.append((vals[0], vals[1]))
+    return out
 
 
 def _ptr(a):
@@ -307,6 +340,12 @@ class Finder:
     def scan_reference(self, name, seq):
         a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
         self._check(self.L.mtg_scan_reference(self.ctx, name.encode(), _ptr(a), a.size))
+
+    def scan_reference_bed(self, name, seq, intervals):
+        """-bed scan of one sequence; intervals = [(begin, end), ...] of this chromosome (parse_bed)."""
+        a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        iv = np.array([x & 0xFFFFFFFFFFFFFFFF for pair in intervals for x in pair], dtype=np.uint64)
+        self._check(self.L.mtg_scan_reference_bed(self.ctx, name.encode(), _ptr(a), a.size, _ptr(iv) if iv.size else None, iv.size // 2))
 
     def breakpoints_text(self):
         n = C.c_uint64()
@@ -476,11 +515,15 @@ class Finder:
         self._check(self.L.mtg_replay_sequence(self.ctx, name.encode(), _ptr(a), a.size, feat, rep, _ptr(it)))
 
     # ---- whole `find` on in-memory inputs (what bench.py and the parity tests drive)
-    def find(self, read_stream, ref_records):
-        """read_stream: '\\n'-separated bases; ref_records: list of (name, bytes). Returns (breakpoints, vcf records)."""
+    def find(self, read_stream, ref_records, bed_text=None):
+        """read_stream: '\\n'-separated bases; ref_records: list of (name, bytes); bed_text: contents of a -bed file.
+        Returns (breakpoints, vcf records)."""
         self.push_reads(read_stream)
         self.finish_count()
         self.set_reference(b"\n".join(s for _, s in ref_records))
         for name, seq in ref_records:
-            self.scan_reference(name, seq)
+            if bed_text is None:
+                self.scan_reference(name, seq)
+            else:
+                self.scan_reference_bed(name, seq, parse_bed(bed_text, name, self.params.kmer_size))
         return self.breakpoints_text(), self.vcf_text()

@@ -579,7 +579,8 @@ int mtg_sequence_features_device(mtg_ctx* ctx, const void* d_seq, uint64_t len, 
     MTG_CATCH
 }
 
-static void scan_reference_impl(mtg_ctx* ctx, const char* name, const char* seq, const void* d_seq, uint64_t len) {
+static void scan_reference_impl(mtg_ctx* ctx, const char* name, const char* seq, const void* d_seq, uint64_t len,
+                                const std::vector<std::pair<uint64_t, uint64_t>>* bed = nullptr) {
     WallTimer w(ctx->wall_scan);
     Trace tr(ctx->stream);
     MTG_CUDA(cudaSetDevice(ctx->p.device));
@@ -598,7 +599,10 @@ static void scan_reference_impl(mtg_ctx* ctx, const char* name, const char* seq,
     ctx->scan_positions += npos; ctx->scan_valid += c4[0]; ctx->scan_in_graph += c4[1]; ctx->scan_table_probes += c4[2]; ctx->scan_fallback += c4[3];
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    if (ctx->rp64) ctx->rp64->scan(name ? name : "", seq, len, feat, rep, interest);
+    if (bed) {
+        if (ctx->rp64) ctx->rp64->scan_bed(name ? name : "", seq, len, feat, rep, *bed);
+        else ctx->rp128->scan_bed(name ? name : "", seq, len, feat, rep, *bed);
+    } else if (ctx->rp64) ctx->rp64->scan(name ? name : "", seq, len, feat, rep, interest);
     else ctx->rp128->scan(name ? name : "", seq, len, feat, rep, interest);
     clock_gettime(CLOCK_MONOTONIC, &t1);
     ctx->ms_replay += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
@@ -624,6 +628,15 @@ int mtg_replay_sequence(mtg_ctx* ctx, const char* name, const char* seq, uint64_
 }
 int mtg_scan_reference(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len) {
     MTG_TRY(ctx) scan_reference_impl(ctx, name, seq, nullptr, len); MTG_CATCH
+}
+int mtg_scan_reference_bed(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len, const uint64_t* begin_end, uint64_t n_intervals) {
+    MTG_TRY(ctx)
+    if (n_intervals && !begin_end) throw Error(-1, "null interval array");
+    if (n_intervals == 0) return 0;  // no interval on this chromosome: nothing is scanned (src/FindBreakpoints.hpp:497)
+    std::vector<std::pair<uint64_t, uint64_t>> iv(n_intervals);
+    for (uint64_t i = 0; i < n_intervals; i++) iv[i] = std::make_pair(begin_end[2 * i], begin_end[2 * i + 1]);
+    scan_reference_impl(ctx, name, seq, nullptr, len, &iv);
+    MTG_CATCH
 }
 int mtg_scan_reference_device(mtg_ctx* ctx, const char* name, const char* seq, const void* d_seq, uint64_t len) {
     MTG_TRY(ctx) if (!d_seq) throw Error(-1, "null device sequence"); scan_reference_impl(ctx, name, seq, d_seq, len); MTG_CATCH

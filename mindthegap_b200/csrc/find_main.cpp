@@ -4,8 +4,8 @@
 //
 //   mtg_find [find] -in reads.fq[,reads2.fq] -ref ref.fa [-out prefix] [-kmer-size 31] [-abundance-min auto] ...
 //
-// Not supported here (reported as errors, like an OptionFailure): -graph x.h5 and -bed, which need gatb-core's HDF5
-// storage / the bed-restricted scan.
+// Not supported here (reported as an error, like an OptionFailure): -graph x.h5, which needs gatb-core's HDF5 storage
+// (SURVEY.md 8f).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -31,6 +31,7 @@ static void usage() {
             "  -in <reads[,reads...]>   FASTA/FASTQ read files (mandatory)\n"
             "  -ref <reference.fa>      reference genome (mandatory)\n"
             "  -out <prefix>            output prefix [MindTheGap_Expe-<date>]\n"
+            "  -bed <regions.bed>       restrict the scan to these regions of the reference\n"
             "  -kmer-size <k>           5..63 [31]\n"
             "  -abundance-min <n|auto>  [auto]      -abundance-max <n> [2147483647]\n"
             "  -max-rep <n> [5]   -het-max-occ <n> [1]   -snp-min-val <n> [5]   -branching-filter <n> [15]\n"
@@ -82,7 +83,6 @@ int main(int argc, char** argv) {
     if ((!graph.empty() && !in.empty()) || (graph.empty() && in.empty()))
         fail("ERROR: options -graph and -in are incompatible, but at least one of these is mandatory");
     if (!graph.empty()) fail("-graph needs gatb-core's HDF5 storage: read dsk/solid on the host and call mtg_load_solid (INTEGRATION.md)");
-    if (!bed.empty()) fail("-bed is not supported by this engine yet");
     if (ref.empty()) fail("ERROR: option -ref is mandatory");
     if (out.empty()) {  // src/Finder.cpp:210-219
         time_t now = time(0);
@@ -143,7 +143,19 @@ int main(int argc, char** argv) {
     for (auto& r : refs) { all += r.seq; all += '\n'; }
     check(mtg_set_reference(g, all.data(), all.size()));
     std::string().swap(all);
-    for (auto& r : refs) check(mtg_scan_reference(g, r.name.c_str(), r.seq.data(), r.seq.size()));
+    if (bed.empty()) {
+        for (auto& r : refs) check(mtg_scan_reference(g, r.name.c_str(), r.seq.data(), r.seq.size()));
+    } else {  // -bed (src/FindBreakpoints.hpp:459-495): the file is re-read for every chromosome, so is its text here
+        std::string bed_text;
+        try { bed_text = mtg::read_text_file(bed); } catch (const std::exception& e) { fail(e.what()); }
+        for (auto& r : refs) {
+            std::vector<std::pair<uint64_t, uint64_t>> iv;
+            try { iv = mtg::bed_intervals(bed_text, r.name, p.kmer_size); } catch (const std::exception& e) { fail(e.what()); }
+            std::vector<uint64_t> flat;
+            for (auto& x : iv) { flat.push_back(x.first); flat.push_back(x.second); }
+            check(mtg_scan_reference_bed(g, r.name.c_str(), r.seq.data(), r.seq.size(), flat.data(), iv.size()));
+        }
+    }
     uint64_t n = 0;
     const char* t = mtg_breakpoints_text(g, &n);
     fwrite(t, 1, n, bk);

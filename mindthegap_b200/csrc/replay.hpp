@@ -86,6 +86,31 @@ public:
         calls_.clear(); log_keys_.clear(); ans_buf_.clear();
     }
 
+    // One reference sequence restricted to bed intervals (FindBreakpoints::operator() with -bed, :459-553). `iv` holds the
+    // (begin, end) pairs of this chromosome in bed-file order (parse: seqio.hpp bed_intervals). Quirks kept: one stale
+    // interval is dropped per position (:499-508); the gap state and the history ring are cleared at begin-1, so never for
+    // begin == 0 (:520-530); positions outside the intervals still advance the ring indices; k-mers are notified from
+    // `begin` on even when that interval starts before the current position (:533).
+    void scan_bed(const std::string& name, const char* seq, size_t len, const uint8_t* feat, const uint8_t* rep,
+                  const std::vector<std::pair<uint64_t, uint64_t>>& iv) {
+        begin_sequence(name, seq, len);
+        if (len < (size_t)k || iv.empty()) return;
+        const size_t npos = len - k + 1;
+        Saved sv;
+        save(sv);
+        collecting_ = true;
+        calls_.clear(); log_keys_.clear();
+        run_bed(npos, feat, rep, iv);
+        collecting_ = false;
+        restore(sv);
+        ans_buf_.resize(log_keys_.size());
+        if (!log_keys_.empty()) { probe_(log_keys_.data(), log_keys_.size(), ans_buf_.data()); cnt.probe_batches++; cnt.prefetched_queries += log_keys_.size(); }
+        log_ans_ = ans_buf_.data();
+        cursor_ = 0;
+        run_bed(npos, feat, rep, iv);
+        calls_.clear(); log_keys_.clear(); ans_buf_.clear();
+    }
+
     // ---- building blocks of scan(), also used chunk-wise by ParallelReplayer
     void begin_sequence(const std::string& name, const char* seq, size_t len) {
         chrom = name; text = seq; text_len = len;
@@ -245,6 +270,46 @@ private:
                 solid_stretch = gap_stretch = 0;
                 begin_valid = end_valid = false;
             } else {
+                cur_fwd = roll_fwd;
+                const uint64_t save_pos = pos;
+                notify(f, rep[p]);
+                pos = save_pos;
+                prev_fwd = roll_fwd; prev_valid = true;
+            }
+            pos++; begin_idx++; end_idx++;
+            p++;
+        }
+    }
+
+    void reset_gap_state() {
+        solid_stretch = gap_stretch = 0;
+        begin_valid = end_valid = false;
+    }
+    void run_bed(size_t npos, const uint8_t* feat, const uint8_t* rep, const std::vector<std::pair<uint64_t, uint64_t>>& iv) {
+        size_t ci = 0;
+        uint64_t start = iv[0].first, end = iv[0].second;
+        size_t p = 0;
+        while (p < npos) {
+            if (p >= end) {
+                if (++ci >= iv.size()) break;
+                start = iv[ci].first; end = iv[ci].second;
+            }
+            if (p + 1 < start && p < end) {
+                // nothing is notified before `start` and the state is cleared at start-1: jump there (the ring indices and
+                // the position advance as if every k-mer had been iterated; resets at invalid k-mers are subsumed)
+                const size_t q = (size_t)std::min<uint64_t>(std::min<uint64_t>(start - 1, end), npos);  // end < start: malformed line, kept by the reference
+                const size_t adv = q - p;
+                pos += adv; begin_idx = (unsigned char)(begin_idx + adv); end_idx = (unsigned char)(end_idx + adv);
+                roll_fwd = kmer_at(q - 1);
+                p = q;
+                continue;
+            }
+            roll_fwd = ((roll_fwd << 2) | (K)code(text[p + k - 1])) & mask_;
+            const uint8_t f = feat[p];
+            loop_p_ = p;
+            if (f & 0x80) reset_gap_state();
+            if (p + 1 == start) { reset_gap_state(); memset(ring, 0, sizeof(ring)); }
+            if (!(f & 0x80) && p >= start) {
                 cur_fwd = roll_fwd;
                 const uint64_t save_pos = pos;
                 notify(f, rep[p]);
@@ -834,6 +899,15 @@ public:
             for (size_t i = 0; i < nc; i++) merge(*rp[i]);
             c0 = c1;
         }
+    }
+
+    // -bed: intervals are short and their replay is sequential by construction (every interval start clears the state)
+    void scan_bed(const std::string& name, const char* seq, size_t len, const uint8_t* feat, const uint8_t* rep,
+                  const std::vector<std::pair<uint64_t, uint64_t>>& iv) {
+        Replayer<K> r(opt_, locked_probe_);
+        r.scan_bed(name, seq, len, feat, rep, iv);
+        nb_chunks++;
+        merge(r);
     }
 
 private:

@@ -3,11 +3,15 @@
 // FASTQ quality skipped by length; comma separated file lists (README.md:166). Plain text only.
 // getCommentShort = header up to the first whitespace (gatb/bank/api/Sequence.hpp:88).
 #pragma once
+#include <errno.h>
+#include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <functional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace mtg {
@@ -97,6 +101,48 @@ inline void for_each_sequence(const std::string& uri, const std::function<void(S
         if (c == std::string::npos) break;
         start = c + 1;
     }
+}
+
+// -bed (src/FindBreakpoints.hpp:462-495): the intervals of chromosome `chrom`, in file order. Lines that are empty or start
+// with '#' or '@' are ignored; fields are tab separated; field 0 must equal the sequence's short name; begin and end are read
+// like std::stoi (leading blanks, sign, then digits; anything after them is ignored, so "140 SNP T -> C" is 140); a line
+// is kept when (end - begin) > k in unsigned 64-bit arithmetic. A non-numeric field is an error, as stoi throws there.
+inline long bed_stoi(const std::string& f, const std::string& line) {
+    char* endp = nullptr;
+    errno = 0;
+    const long v = strtol(f.c_str(), &endp, 10);
+    if (endp == f.c_str()) throw std::runtime_error("bed: not a number in line: " + line);
+    if (errno == ERANGE || v > 2147483647L || v < -2147483648L) throw std::runtime_error("bed: number out of range in line: " + line);
+    return v;
+}
+inline std::vector<std::pair<uint64_t, uint64_t>> bed_intervals(const std::string& bed_text, const std::string& chrom, int k) {
+    std::vector<std::pair<uint64_t, uint64_t>> iv;
+    for (size_t a = 0; a < bed_text.size();) {
+        size_t b = bed_text.find('\n', a);
+        if (b == std::string::npos) b = bed_text.size();
+        const std::string line(bed_text, a, b - a);
+        a = b + 1;
+        if (line.empty() || line[0] == '#' || line[0] == '@') continue;
+        const size_t t1 = line.find('\t');
+        if (line.compare(0, t1 == std::string::npos ? line.size() : t1, chrom) != 0) continue;
+        const size_t t2 = t1 == std::string::npos ? t1 : line.find('\t', t1 + 1);
+        if (t2 == std::string::npos) throw std::runtime_error("bed: fewer than 3 tab-separated fields in line: " + line);
+        const size_t t3 = line.find('\t', t2 + 1);
+        const uint64_t lo = (uint64_t)bed_stoi(line.substr(t1 + 1, t2 - t1 - 1), line);
+        const uint64_t hi = (uint64_t)bed_stoi(line.substr(t2 + 1, t3 == std::string::npos ? t3 : t3 - t2 - 1), line);
+        if (hi - lo > (uint64_t)k) iv.emplace_back(lo, hi);
+    }
+    return iv;
+}
+inline std::string read_text_file(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("Cannot open file " + path);
+    std::string s;
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) s.append(buf, n);
+    fclose(f);
+    return s;
 }
 
 }  // namespace mtg

@@ -10,6 +10,7 @@
 
 #include "../../oracle/scan_oracle.hpp"
 #include "../../mindthegap_b200/csrc/replay.hpp"
+#include "../../mindthegap_b200/csrc/seqio.hpp"
 
 using namespace mtgo;
 
@@ -19,7 +20,7 @@ template <class K> static int run(int argc, char** argv) {
     std::string amin = "auto";
     size_t seg = (size_t)1 << 22, skip_min = 512;
     bool use_interest = true;
-    std::string dump, load;
+    std::string dump, load, bed;
     int threads = 1, repeat = 1;
     size_t chunk = 0;
     unsigned flags = 0;
@@ -42,6 +43,7 @@ template <class K> static int run(int argc, char** argv) {
         else if (a == "-threads") threads = atoi(val().c_str());
         else if (a == "-repeat") repeat = atoi(val().c_str());
         else if (a == "-chunk") chunk = (size_t)atoll(val().c_str());
+        else if (a == "-bed") bed = val();   // product bed parser + bed-restricted replay
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
     }
     o.homo_only = flags & 1; o.homo_insert = flags & 2; o.hete_insert = flags & 4; o.snp = flags & 8; o.backup = flags & 16;
@@ -134,7 +136,8 @@ template <class K> static int run(int argc, char** argv) {
                 }
             }
             const double t0 = now();
-            rp.scan(rec.name, rec.seq.data(), rec.seq.size(), feat.data(), rep.data(), use_interest ? interest.data() : nullptr);
+            if (bed.empty()) rp.scan(rec.name, rec.seq.data(), rec.seq.size(), feat.data(), rep.data(), use_interest ? interest.data() : nullptr);
+            else rp.scan_bed(rec.name, rec.seq.data(), rec.seq.size(), feat.data(), rep.data(), mtg::bed_intervals(mtg::read_text_file(bed), rec.name, k));
             scan_ms += now() - t0;
         }
         bk_text = rp.bkpt_out; vcf_text = rp.vcf_out; cnt = rp.cnt; nchunks = rp.nb_chunks;

@@ -61,3 +61,18 @@ def test_mode_flags_follow_finder_order():
     assert p.max_repeat == 2 and p.flags == (api.F_HETE_INSERT | api.F_SMALL_HOMO)
     p = api.FindParams.from_cli(["-abundance-min", "auto", "-het-max-occ", "0"])
     assert p.abundance_min == api.ABUNDANCE_AUTO and p.het_max_occ == 1
+
+
+def test_parse_bed_follows_reference_rules():
+    """src/FindBreakpoints.hpp:462-495: comment lines, tab fields, std::stoi numbers, unsigned (end - begin) > k filter."""
+    import mindthegap_b200.api as api
+    from tests.cases import GOLD
+    text = open(os.path.join(GOLD, "full_bed", "gold.bed")).read()
+    assert api.parse_bed(text, "Seq0", 31) == [(60, 140), (90, 150), (200, 450)]
+    assert api.parse_bed(text, "Seq1", 31) == [(300, 400), (700, 847)]
+    assert api.parse_bed(text, "Seq3", 31) == []
+    assert api.parse_bed("#x\n@y\n\nc\t10\t41\nc\t10\t42 note\nc\t400\t100\nd\t0\t99\n", "c", 31) == [(10, 42), (400, 100)]
+    with pytest.raises(api.MtgError):
+        api.parse_bed("c\tx\t10\n", "c", 31)
+    with pytest.raises(api.MtgError):
+        api.parse_bed("c\t10\n", "c", 31)

@@ -218,6 +218,53 @@ def test_find_outputs_equal_reference(name):
     f.close()
 
 
+def test_find_with_bed_equals_reference_gold_files(tmp_path):
+    """`find -bed` (src/FindBreakpoints.hpp:459-553) through the C ABI and through the C++ CLI: the reference's own gold_bed
+    files (/root/reference/test/simple_full_test.sh:79-118), byte-exact."""
+    import subprocess
+    from tests.cases import ROOT
+    case = CASES["full"]
+    reads, ref = case_paths(case)
+    stream, _ = _stream(reads)
+    _, rrecs = _stream(ref)
+    bed = os.path.join(GOLD, "full_bed", "gold.bed")
+    gold_bk = open(os.path.join(GOLD, "full_bed", "gold_bed.breakpoints")).read()
+    gold_vcf = "".join(l for l in open(os.path.join(GOLD, "full_bed", "gold_bed.othervariants.vcf")) if not l.startswith("#"))
+    f = _finder(case)
+    bk, vcf = f.find(stream, rrecs, bed_text=open(bed).read())
+    f.close()
+    assert bk == gold_bk and vcf == gold_vcf
+    exe = os.path.join(ROOT, "mindthegap_b200", "_build", "mtg_find")
+    out = str(tmp_path / "o")
+    r = subprocess.run([exe, "find", "-in", reads, "-ref", ref, "-out", out, "-bed", bed], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(out + ".breakpoints").read() == gold_bk
+    assert "".join(l for l in open(out + ".othervariants.vcf") if not l.startswith("#")) == gold_vcf
+
+
+def test_find_with_bed_edge_cases_equal_oracle(tmp_path):
+    """Interval-walk quirks (start 0, overlapping / unsorted / malformed intervals, one stale interval dropped per position)."""
+    import subprocess
+    from tests.cases import ROOT
+    case = CASES["full"]
+    reads, ref = case_paths(case)
+    stream, _ = _stream(reads)
+    _, rrecs = _stream(ref)
+    bed_text = ("#c\n@c\n\nSeq0\t0\t200\nSeq0\t100\t160\nSeq0\t50\t90\nSeq0\t300\t700 x\nother\t1\t1000\nSeq1\t400\t100\n"
+                "Seq1\t500\t100000\nSeq2\t1\t40\nSeq2\t2\t20\nSeq3\t1\t100000\n")
+    bedf = tmp_path / "x.bed"
+    bedf.write_text(bed_text)
+    out = str(tmp_path / "o")
+    subprocess.run([os.path.join(ROOT, "oracle", "_build", "oracle_find"), "find", "-in", reads, "-ref", ref, "-kmer-size", "31", "-out", out,
+                    "-bed", str(bedf)], stdout=subprocess.PIPE, check=True)
+    f = _finder(case)
+    bk, vcf = f.find(stream, rrecs, bed_text=bed_text)
+    f.close()
+    assert len(bk) > 0
+    assert bk == open(out + ".breakpoints").read()
+    assert vcf == "".join(l for l in open(out + ".othervariants.vcf") if not l.startswith("#"))
+
+
 def test_load_solid_gives_same_scan():
     """`-graph` path: uploading an exported solid set reproduces the outputs (src/Finder.cpp:274-279)."""
     case = CASES["full"]

@@ -15,7 +15,7 @@ EXE = os.path.join(ROOT, "tests", "host", "_build", "replay_check")
 def replay_check():
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     src = os.path.join(ROOT, "tests", "host", "replay_check.cpp")
-    deps = [src, os.path.join(ROOT, "mindthegap_b200", "csrc", "replay.hpp")] + [
+    deps = [src, os.path.join(ROOT, "mindthegap_b200", "csrc", "replay.hpp"), os.path.join(ROOT, "mindthegap_b200", "csrc", "seqio.hpp")] + [
         os.path.join(ROOT, "oracle", f) for f in ("scan_oracle.hpp", "graph_oracle.hpp", "kmer_oracle.hpp")]
     if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", EXE, src], check=True)
@@ -64,3 +64,37 @@ def test_chunked_replay_really_cuts(replay_check, tmp_path):
     _, _, many = run(replay_check, "syn_small_k31", tmp_path, MODES["parallel_chunks"])
     assert one["chunks"] <= 4 and many["chunks"] > 50, (one, many)
     assert one["observer_queries"] == many["observer_queries"]
+
+
+def test_bed_replay_equals_reference_gold_files(replay_check, tmp_path):
+    """-bed (src/FindBreakpoints.hpp:459-553): product bed parser + restricted replay against the reference's own gold_bed
+    files (/root/reference/test/simple_full_test.sh:79-118)."""
+    from tests.cases import GOLD
+    bed = os.path.join(GOLD, "full_bed", "gold.bed")
+    bk, vcf, _ = run(replay_check, "full", tmp_path, ["-bed", bed])
+    assert bk == open(os.path.join(GOLD, "full_bed", "gold_bed.breakpoints")).read()
+    assert vcf == "".join(l for l in open(os.path.join(GOLD, "full_bed", "gold_bed.othervariants.vcf")) if not l.startswith("#"))
+
+
+BED_CASES = {
+    # interval starting at 0 (no reset), overlapping / unsorted intervals (stale ones dropped one per position), an interval
+    # past the end, a malformed line with end < begin (kept by the unsigned test), comment lines, other chromosomes
+    "edge": "#c\n@c\n\nSeq0\t0\t200\nSeq0\t100\t160\nSeq0\t50\t90\nSeq0\t300\t700 x\nother\t1\t1000\nSeq1\t400\t100\nSeq1\t500\t100000\nSeq2\t1\t40\nSeq2\t2\t20\n",
+    "whole": "Seq0\t0\t100000\nSeq1\t0\t100000\nSeq2\t0\t100000\nSeq3\t1\t100000\n",
+}
+
+
+@pytest.mark.parametrize("bed_name", sorted(BED_CASES))
+def test_bed_replay_equals_oracle(replay_check, oracle_bin, tmp_path, bed_name):
+    """Edge cases of the interval walk: the product replay against the oracle's restatement of the reference loop."""
+    bedf = tmp_path / "x.bed"
+    bedf.write_text(BED_CASES[bed_name])
+    bk, vcf, _ = run(replay_check, "full", tmp_path, ["-bed", str(bedf)])
+    case = CASES["full"]
+    reads, ref = case_paths(case)
+    out = str(tmp_path / "o")
+    subprocess.run([oracle_bin, "find", "-in", reads, "-ref", ref, "-kmer-size", "31", "-out", out, "-bed", str(bedf)],
+                   stdout=subprocess.PIPE, check=True)
+    assert bk == open(out + ".breakpoints").read()
+    assert vcf == "".join(l for l in open(out + ".othervariants.vcf") if not l.startswith("#"))
+    assert len(bk) > 0

@@ -37,6 +37,15 @@ def test_bundled_example_equals_reference_gold_files(oracle_bin, tmp_path):
         assert int(re.search(pat, gold_out).group(1)) == int(info[key])
 
 
+def test_bundled_example_with_bed_equals_reference_gold_files(oracle_bin, tmp_path):
+    """/root/reference/test/simple_full_test.sh:79-118: `find -bed gold.bed` against the reference's own gold_bed files."""
+    bed = os.path.join(GOLD, "full_bed", "gold.bed")
+    bk, vcf, info = run_oracle(oracle_bin, "full", tmp_path, extra=["-bed", bed])
+    assert bk == open(os.path.join(GOLD, "full_bed", "gold_bed.breakpoints")).read()
+    gold_vcf = "".join(l for l in open(os.path.join(GOLD, "full_bed", "gold_bed.othervariants.vcf")) if not l.startswith("#"))
+    assert vcf == gold_vcf
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_oracle_equals_reference_binary_outputs(oracle_bin, tmp_path, name):
     bk, vcf, info = run_oracle(oracle_bin, name, tmp_path)
