@@ -33,6 +33,19 @@ UNIT = "kmers/s"
 
 
 # ---------------------------------------------------------------------------------------------------- workload
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the real stdout (fd saved by main before libraries could print to it)."""
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def make_workload(scale=1.0, seed=SEED, genome_mult=1, config="cfg2"):
     """cfg2 / cfg3 (optionally scaled): returns dict(refs=[(name, uint8 array)], stream=uint8 array of '\\n'-separated reads,
     mats, n_reads, read_len, read_kmers, ref_kmers)."""
@@ -121,7 +134,7 @@ def reference_arm(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "read_kmers_counted_per_s": wl["read_kmers"] / float(r["info"]["time_count"]),
             "ref_kmers_queried_per_s": wl["ref_kmers"] / float(r["info"]["time_scan"])}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -217,6 +230,8 @@ def own_arm(args):
             all_refs += [("g%d_%s" % (r, n), s) for n, s in refs_r]
         wl["ref_kmers"] = sum(max(0, len(s) - K + 1) for _, s in wl["refs"])
         all_ref_stream = np.concatenate([np.concatenate([s, np.array([10], dtype=np.uint8)]) for _, s in all_refs])
+        all_ref_host = torch.from_numpy(all_ref_stream).pin_memory()   # e2e: pinned host buffer, copied inside the timed region
+        all_ref_dev = all_ref_host.cuda()                              # resident: already in HBM
 
     def one_find(resident):
         f = m.Finder(params)
@@ -232,7 +247,9 @@ def own_arm(args):
         else:
             f.push_reads(stream_np)
         if world > 1:
-            bk, vcf = d.find(all_refs, all_ref_stream)
+            bk, vcf = d.find(all_refs, all_ref_dev if resident else all_ref_host)
+            if d.trace is not None and rank == 0:
+                print("[dist trace] " + json.dumps({k: [v[0], round(v[1], 3)] for k, v in sorted(d.trace.items(), key=lambda kv: -kv[1][1])}), file=sys.stderr)
             st = f.stats()
             st["nb_solid"] = d.nb_solid
             st["threshold"] = f.threshold
@@ -408,7 +425,7 @@ def own_arm(args):
             "config": {"workload": wl["name"], "kmer_size": K, "abundance_min": "auto (inferred %d)" % int(avg["threshold"]),
                        "per_gpu_read_bytes": nbytes, "l2_policy": "inputs (%.0f MB reads per GPU) larger than the 126 MB L2; every step starts from a fresh context" % (nbytes / 1e6),
                        "parallelism": ("1 process per GPU (%d): records all-to-all by minimizer owner; solid k-mers all-to-all by table range, ranges all-gathered, Bloom arrays OR-reduced (replica per GPU); whole chromosomes scanned per rank" % world) if world > 1 else "single GPU"},
-            "e2e": {"value": tot_kmers / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes + ref_stream.size),
+            "e2e": {"value": tot_kmers / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes + (all_ref_stream.size if world > 1 else ref_stream.size)),
                     "d2h_bytes_per_step": int(2 * wl["ref_kmers"] + len(out_e2e[0]) + len(out_e2e[1])), "ms_per_step": ms_e2e},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity": parity,
             "read_kmers_counted_per_s": read_kmers / (1e-3 * (count_stage_ms + avg["count.ms_group"])),
@@ -422,7 +439,7 @@ def own_arm(args):
                        "prefetched_queries": avg["scan.prefetched_queries"], "unforeseen_queries": avg["scan.unforeseen_queries"],
                        "probe_batches": avg["scan.probe_batches"],
                        "breakpoint_records": len(out_res[0].splitlines()) // 4, "vcf_records": len(out_res[1].splitlines())}}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -444,6 +461,11 @@ def main():
     args = ap.parse_args()
     global K
     K = args.kmer_size
+    # stdout carries exactly ONE JSON line: everything libraries print (NCCL's version banner, ...) goes to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return reference_arm(args)
     return own_arm(args)

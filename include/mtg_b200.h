@@ -141,6 +141,14 @@ int mtg_get_histogram(mtg_ctx* ctx, uint64_t* out10001);
 int mtg_get_stats(mtg_ctx* ctx, double* out, int cap);
 const char* mtg_stat_name(int i);
 
+/* Replaces BranchingAlgorithm::execute (G/debruijn/impl/BranchingAlgorithm.cpp:150-165, 206-310), the source of the
+ * "nb_branching_nodes" info line (src/Finder.cpp:467): solid k-mers whose (predecessors, successors) != (1, 1). Needs the
+ * graph built from counted or loaded solid k-mers. *nb_branching receives the count; topology25 (may be NULL) the
+ * [in 0..4][out 0..4] histogram; lo/hi/abundance (may be NULL: count only) the branching collection sorted by k-mer
+ * (abundance 0 after mtg_load_solid). On N GPUs every rank reports the nodes of its own solid share. */
+int mtg_graph_branching(mtg_ctx* ctx, uint64_t* nb_branching, uint64_t* topology25, uint64_t* lo, uint64_t* hi, uint32_t* abundance,
+                        uint64_t capacity);
+
 /* Replaces CountProcessorDump (G/kmer/impl/CountProcessorDump.hpp:140-144): (value, abundance) of every solid k-mer,
  * value split in two 64-bit halves (hi may be NULL when kmer_size <= 31). Order is unspecified. */
 int mtg_export_solid(mtg_ctx* ctx, uint64_t* lo, uint64_t* hi, uint32_t* abundance, uint64_t capacity);

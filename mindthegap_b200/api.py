@@ -43,7 +43,7 @@ EXPORTS = [
     "mtg_count_run", "mtg_count_filter", "mtg_solid_copy", "mtg_graph_build_device", "mtg_sequence_features_device2", "mtg_replay_sequence",
     "mtg_graph_build_begin", "mtg_graph_critical", "mtg_graph_critical_copy", "mtg_graph_build_end", "mtg_set_host_threads", "mtg_set_minimizer_size", "mtg_get_minimizer_size",
     "mtg_solid_partition", "mtg_partition_keys", "mtg_graph_shard_begin", "mtg_graph_shard_critical", "mtg_graph_adj_pack", "mtg_graph_adj_unpack",
-    "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
+    "mtg_graph_branching", "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def load_library():
     L.mtg_stat_name.argtypes = [C.c_int]
     L.mtg_export_solid.argtypes = [vp, u64p, vp, vp, C.c_uint64]
     L.mtg_load_solid.argtypes = [vp, u64p, vp, C.c_uint64]
+    L.mtg_graph_branching.argtypes = [vp, u64p, vp, vp, vp, vp, C.c_uint64]
     L.mtg_set_reference.argtypes = [vp, vp, C.c_uint64]
     for fn in (L.mtg_contains_batch, L.mtg_degree_batch, L.mtg_ref_repeat_batch):
         fn.argtypes = [vp, u64p, vp, C.c_uint64, u8p]
@@ -290,6 +291,20 @@ class Finder:
         ab = np.zeros(max(n, 1), dtype=np.uint32)
         self._check(self.L.mtg_export_solid(self.ctx, lo, _ptr(hi), _ptr(ab), max(n, 1)))
         return lo[:n], hi[:n], ab[:n]
+
+    def branching(self, nodes=True):
+        """BranchingAlgorithm (gatb-core debruijn/impl/BranchingAlgorithm.cpp:150-310): (nb_branching, topology[in][out] 5x5,
+        lo, hi, abundance) with the collection sorted by k-mer; nodes=False only counts."""
+        nb = np.zeros(1, dtype=np.uint64)
+        topo = np.zeros(25, dtype=np.uint64)
+        self._check(self.L.mtg_graph_branching(self.ctx, nb, _ptr(topo), None, None, None, 0))
+        n = int(nb[0])
+        if not nodes:
+            return n, topo.reshape(5, 5)
+        lo = np.zeros(max(n, 1), dtype=np.uint64); hi = np.zeros(max(n, 1), dtype=np.uint64)
+        ab = np.zeros(max(n, 1), dtype=np.uint32)
+        self._check(self.L.mtg_graph_branching(self.ctx, nb, _ptr(topo), _ptr(lo), _ptr(hi), _ptr(ab), max(n, 1)))
+        return n, topo.reshape(5, 5), lo[:n], hi[:n], ab[:n]
 
     def load_solid(self, lo, hi=None):
         lo = np.ascontiguousarray(lo, dtype=np.uint64)

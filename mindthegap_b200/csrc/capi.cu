@@ -518,6 +518,27 @@ int mtg_export_solid(mtg_ctx* ctx, uint64_t* lo, uint64_t* hi, uint32_t* abundan
     MTG_CATCH
 }
 
+int mtg_graph_branching(mtg_ctx* ctx, uint64_t* nb_branching, uint64_t* topology25, uint64_t* lo, uint64_t* hi, uint32_t* abundance,
+                        uint64_t capacity) {
+    MTG_TRY(ctx)
+    if (!ctx->graph_ready) throw Error(-4, "mtg_graph_branching: no graph (count reads or load solid k-mers first)");
+    if (!nb_branching) throw Error(-1, "mtg_graph_branching: nb_branching is NULL");
+    MTG_CUDA(cudaSetDevice(ctx->p.device));
+    if (ctx->solid_owner) {
+        *nb_branching = ctx->graph->branching(ctx->solid_owner->solid_keys_device(), ctx->solid_owner->solid_abundance_device(),
+                                              ctx->solid_owner->nb_solid(), topology25, lo, hi, abundance, capacity);
+    } else {   // loaded solid set: no abundances
+        const uint64_t n = ctx->loaded_lo.size();
+        const bool wide = ctx->p.kmer_size > 31;
+        std::vector<uint64_t> h(n * (wide ? 2 : 1));
+        for (uint64_t i = 0; i < n; i++) { if (wide) { h[2 * i] = ctx->loaded_lo[i]; h[2 * i + 1] = ctx->loaded_hi[i]; } else h[i] = ctx->loaded_lo[i]; }
+        DevBuf<uint64_t> d(std::max<uint64_t>(h.size(), 1));
+        if (n) MTG_CUDA(cudaMemcpyAsync(d.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        *nb_branching = ctx->graph->branching(d.p, nullptr, n, topology25, lo, hi, abundance, capacity);
+    }
+    MTG_CATCH
+}
+
 int mtg_load_solid(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_t n) {
     MTG_TRY(ctx)
     MTG_CUDA(cudaSetDevice(ctx->p.device));

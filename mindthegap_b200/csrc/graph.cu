@@ -272,11 +272,27 @@ __global__ void __launch_bounds__(256) cfp_set_kernel(const K* __restrict__ keys
     }
 }
 
+// list of cFP k-mers -> the exact set probed by cfpset_contains
+template <class K>
+__global__ void __launch_bounds__(256) cfpset_build_kernel(const K* __restrict__ in, uint64_t n, K* __restrict__ set, uint64_t slots) {
+    const K EMPTY = ~K(0);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const K x = in[i];
+        uint64_t s = key_hash(x) & (slots - 1);
+        for (uint64_t probe = 0; probe < slots; probe++) {
+            const K cur = cas_global(&set[s], EMPTY, x);
+            if (cur == EMPTY || cur == x) break;
+            s = (s + 1) & (slots - 1);
+        }
+    }
+}
+
 // BooPHF level construction (processLevel/insertIntoLevel, BooPHF.h:842-905,1082-1092): every remaining key sets the
 // bit of its level hash; a second arrival marks a collision.
 template <class K>
-__global__ void __launch_bounds__(256) mphf_level_kernel(const K* __restrict__ keys, uint64_t n, int level, uint64_t dom, uint64_t seed,
-                                                         unsigned long long* __restrict__ bits, unsigned long long* __restrict__ coll) {
+__global__ void __launch_bounds__(256) mphf_level_kernel(const K* __restrict__ keys, const unsigned long long* __restrict__ n_ptr, int level, uint64_t dom,
+                                                         uint64_t seed, unsigned long long* __restrict__ bits, unsigned long long* __restrict__ coll) {
+    const uint64_t n = *n_ptr;   // survivors of the previous level, counted on the device (no host round trip between levels)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         MphfState st;
         st.init(keys[i], seed);
@@ -293,9 +309,10 @@ __global__ void __launch_bounds__(256) mphf_clear_kernel(unsigned long long* __r
 }
 // keys whose bit was cleared (collision) go on to the next level
 template <class K>
-__global__ void __launch_bounds__(256) mphf_compact_kernel(const K* __restrict__ keys, uint64_t n, int level, uint64_t dom, uint64_t seed,
-                                                           const unsigned long long* __restrict__ bits, K* __restrict__ out,
+__global__ void __launch_bounds__(256) mphf_compact_kernel(const K* __restrict__ keys, const unsigned long long* __restrict__ n_ptr, int level, uint64_t dom,
+                                                           uint64_t seed, const unsigned long long* __restrict__ bits, K* __restrict__ out,
                                                            unsigned long long* __restrict__ nout) {
+    const uint64_t n = *n_ptr;
     const int lane = threadIdx.x & 31;
     uint64_t n_round = (n + 31) / 32 * 32;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -411,6 +428,46 @@ __global__ void __launch_bounds__(256) table_compact_kernel(const K* __restrict_
     }
 }
 
+// Branching nodes (BranchingAlgorithm FunctorNodes, gatb-core debruijn/impl/BranchingAlgorithm.cpp:150-165): the solid k-mers
+// whose (predecessors, successors) is not (1, 1), taking the canonical k-mer as the forward strand like Graph::iterator()
+// does. The degrees come from the adjacency byte written at build time (one bucket probe per solid k-mer).
+// counters[0] = number of branching nodes, counters[1 + 5*in + out] = topology histogram. out_keys == nullptr: count only.
+template <class K>
+__global__ void __launch_bounds__(256) branching_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ abund, uint64_t n, GraphView<K> g,
+                                                        K* __restrict__ out_keys, uint32_t* __restrict__ out_ab, unsigned long long* __restrict__ counters) {
+    __shared__ unsigned topo[25];
+    if (threadIdx.x < 25) topo[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t nround = (n + 31) & ~31ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (uint64_t)gridDim.x * blockDim.x) {
+        bool br = false;
+        K key = K(0);
+        if (i < n) {
+            key = keys[i];
+            unsigned adj = 0;
+            if (table_lookup(g, key, adj)) {
+                const int o = __popc(adj & 15u), in = __popc(adj >> 4);
+                br = !(o == 1 && in == 1);
+                if (br) atomicAdd(&topo[5 * in + o], 1u);
+            }
+        }
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, br);
+        if (b) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counters, (unsigned long long)__popc(b));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (br && out_keys) {
+                const uint64_t o = base + __popc(b & ((1u << lane) - 1));
+                out_keys[o] = key;
+                out_ab[o] = abund ? abund[i] : 0u;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 25 && topo[threadIdx.x]) atomicAdd(counters + 1 + threadIdx.x, (unsigned long long)topo[threadIdx.x]);
+}
+
 // ------------------------------------------------------------------------------------------------ query kernels
 template <class K>
 __global__ void __launch_bounds__(256) contains_kernel(GraphView<K> g, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, uint64_t n,
@@ -511,7 +568,8 @@ template <class K> class Graph : public IGraph {
     uint64_t nbuckets_ = 0;   // buckets per range
     uint32_t nshards_ = 1;    // ranges (= GPUs that built the table)
     BloomDev bloom_, b2_, b3_, b4_, ref_;
-    DevBuf<K> cfp_, final_, crit_list_;
+    DevBuf<K> cfp_, cfp_list_, final_, crit_list_;   // cfp_: hash set (cfp_slots_ slots); cfp_list_: the same k-mers as a list
+    uint64_t cfp_slots_ = 1;
     uint64_t ncrit_ = 0;
     uint64_t ncfp_ = 0, nfinal_ = 0;
     bool cascading_ = true, mphf_built_ = false;
@@ -543,7 +601,7 @@ template <class K> class Graph : public IGraph {
         g.cascading = cascading_ ? 1 : 0;
         g.b2 = b2_.bits.p; g.b2_tai = b2_.tai; g.b3 = b3_.bits.p; g.b3_tai = b3_.tai; g.b4 = b4_.bits.p; g.b4_tai = b4_.tai;
         g.casc_nhash = b2_.nhash;
-        g.cfp = cfp_.p; g.ncfp = ncfp_;
+        g.cfp = cfp_.p; g.ncfp = ncfp_; g.cfp_slots = cfp_slots_;
         g.mphf_built = mphf_built_ ? 1 : 0;
         g.mphf_seed = mphf_seed_;
         g.mphf_bits = (const uint64_t*)mphf_bits_.p;
@@ -594,6 +652,20 @@ public:
     float last_features_ms() override {
         if (features_timed_) { cudaEventSynchronize(ev_b_); cudaEventElapsedTime(&last_features_ms_, ev_a_, ev_b_); features_timed_ = false; }
         return last_features_ms_;
+    }
+
+    // cfp_list_[0..n) -> the device hash set (load <= 0.5)
+    void build_cfp_set(const K* d_list, uint64_t n) {
+        ncfp_ = n;
+        cfp_slots_ = 2;
+        while (cfp_slots_ < 2 * n) cfp_slots_ <<= 1;
+        cfp_.alloc(cfp_slots_);
+        cfp_.fill_ff(stream_);
+        if (n) {
+            cfpset_build_kernel<K><<<grid_for(n), 256, 0, stream_>>>(d_list, n, cfp_.p, cfp_slots_);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
     }
 
     void build_from_host(const uint64_t* lo, const uint64_t* hi, uint64_t n) override {
@@ -741,8 +813,7 @@ public:
         // ---- cascading Blooms (createCFP, DebloomAlgorithm.cpp:462-622); BLOOM_CACHE kind is forced there (:497)
         t.start();
         cascading_ = ncrit != 0;  // no critical FP -> DEBLOOM_ORIGINAL with an empty set (:478-479)
-        ncfp_ = 0;
-        cfp_.alloc(1);
+        uint64_t nlist = 0;
         if (cascading_) {
             int64_t estT2 = std::max((int)ceilf(N * (double)powf((double)0.62, (double)NBITS)), 1);
             int64_t estT3 = std::max((int)ceilf(ncrit * (double)powf((double)0.62, (double)NBITS)), 1);
@@ -756,10 +827,10 @@ public:
             MTG_CUDA(cudaGetLastError());
             st_.launches += 3;
             for (uint64_t cap = N / 16 + 1024;; cap = N + 1024) {
-                cfp_.alloc(cap);
+                cfp_list_.alloc(cap);
                 MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 8, stream_));
                 err_.zero(stream_);
-                cfp_set_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, b2_.bits.p, b2_.tai, b4_.bits.p, b4_.tai, nh, seed0_, rnd_.p, cfp_.p,
+                cfp_set_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, b2_.bits.p, b2_.tai, b4_.bits.p, b4_.tai, nh, seed0_, rnd_.p, cfp_list_.p,
                                                                      counters_.p, cap, err_.p);
                 MTG_CUDA(cudaGetLastError());
                 st_.launches++;
@@ -768,16 +839,11 @@ public:
                 MTG_CUDA(cudaMemcpyAsync(&e, err_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
                 MTG_CUDA(cudaMemcpyAsync(&nc, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
                 MTG_CUDA(cudaStreamSynchronize(stream_));
-                if (!e) { ncfp_ = nc; break; }
+                if (!e) { nlist = nc; break; }
                 if (cap >= N + 1024) throw Error(-6, "cfp set overflow");
             }
-            if (ncfp_) {  // small: sort on the host (std::sort of cfpItems, DebloomAlgorithm.cpp:561)
-                std::vector<K> h(ncfp_);
-                MTG_CUDA(cudaMemcpy(h.data(), cfp_.p, ncfp_ * sizeof(K), cudaMemcpyDeviceToHost));
-                std::sort(h.begin(), h.end());
-                MTG_CUDA(cudaMemcpy(cfp_.p, h.data(), ncfp_ * sizeof(K), cudaMemcpyHostToDevice));
-            }
         }
+        build_cfp_set(cfp_list_.p, nlist);
         st_.ms_cascade = t.stop();
         st_.b2_tai = b2_.tai;
         tr.mark("graph: cascade"); st_.b3_tai = b3_.tai; st_.b4_tai = b4_.tai; st_.ncfp = ncfp_;
@@ -896,8 +962,8 @@ public:
             st_.ms_cascade = 0;
             st_.nb_critical = ncrit_total;
             cascading_ = ncrit_total != 0;   // DebloomAlgorithm.cpp:478-479
-            ncfp_ = 0; ncfp_local_ = 0;
-            cfp_.alloc(1);
+            ncfp_local_ = 0;
+            build_cfp_set(nullptr, 0);
             if (cascading_) {
                 const uint64_t N = ntotal_;
                 int64_t estT2 = std::max((int)ceilf(N * (double)powf((double)0.62, (double)NBITS)), 1);
@@ -940,16 +1006,9 @@ public:
         return ret;
     }
     void set_cfp(const void* d_all, uint64_t n) override {
-        ncfp_ = n;
-        cfp_.alloc(std::max<uint64_t>(n, 1));
-        if (n) {  // small: sort on the host (std::sort of cfpItems, DebloomAlgorithm.cpp:561)
-            std::vector<K> h(n);
-            MTG_CUDA(cudaMemcpyAsync(h.data(), d_all, n * sizeof(K), cudaMemcpyDeviceToHost, stream_));
-            MTG_CUDA(cudaStreamSynchronize(stream_));
-            std::sort(h.begin(), h.end());
-            MTG_CUDA(cudaMemcpyAsync(cfp_.p, h.data(), n * sizeof(K), cudaMemcpyHostToDevice, stream_));
-            MTG_CUDA(cudaStreamSynchronize(stream_));
-        }
+        cfp_list_.alloc(std::max<uint64_t>(n, 1));
+        if (n) MTG_CUDA(cudaMemcpyAsync(cfp_list_.p, d_all, n * sizeof(K), cudaMemcpyDeviceToDevice, stream_));
+        build_cfp_set(cfp_list_.p, n);
         st_.ncfp = n;
         cfp_local_.release();
     }
@@ -1012,34 +1071,114 @@ public:
             st_.mphf_words = off;
             DevBuf<unsigned long long> coll(mphf_dom_[0] / 64);
             DevBuf<K> bufA(N), bufB(N);
+            DevBuf<unsigned long long> cnt(MPHF_LEVELS + 1);   // cnt[l] = keys entering level l
+            cnt.zero(stream_);
+            const unsigned long long n0 = N;
+            MTG_CUDA(cudaMemcpyAsync(cnt.p, &n0, 8, cudaMemcpyHostToDevice, stream_));
+            // The first levels run on the device back to back (sizes stay on the device); once the expected number of
+            // survivors (collision probability 1 - exp(-1/gamma) = 0.28 per level) is a few thousand, the remaining levels are
+            // finished on the host from the survivor list: one synchronisation for the whole construction.
             const K* cur = keys;
-            uint64_t ncur = N;
-            for (int lvl = 0; lvl < MPHF_LEVELS - 1 && ncur; lvl++) {
+            int glevels = 0;
+            double expect = (double)N;
+            for (int lvl = 0; lvl < MPHF_LEVELS - 1; lvl++) {
                 const uint64_t words = mphf_dom_[lvl] / 64;
+                const int grid = grid_for((uint64_t)expect + 1);
                 MTG_CUDA(cudaMemsetAsync(coll.p, 0, words * 8, stream_));
-                mphf_level_kernel<K><<<grid_for(ncur), 256, 0, stream_>>>(cur, ncur, lvl, mphf_dom_[lvl], mphf_seed_, mphf_bits_.p + mphf_off_[lvl], coll.p);
+                mphf_level_kernel<K><<<grid, 256, 0, stream_>>>(cur, cnt.p + lvl, lvl, mphf_dom_[lvl], mphf_seed_, mphf_bits_.p + mphf_off_[lvl], coll.p);
                 mphf_clear_kernel<<<grid_for(words), 256, 0, stream_>>>(mphf_bits_.p + mphf_off_[lvl], coll.p, words);
                 K* out = (cur == bufA.p) ? bufB.p : bufA.p;
-                MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 8, stream_));
-                mphf_compact_kernel<K><<<grid_for(ncur), 256, 0, stream_>>>(cur, ncur, lvl, mphf_dom_[lvl], mphf_seed_, mphf_bits_.p + mphf_off_[lvl], out, counters_.p);
+                mphf_compact_kernel<K><<<grid, 256, 0, stream_>>>(cur, cnt.p + lvl, lvl, mphf_dom_[lvl], mphf_seed_, mphf_bits_.p + mphf_off_[lvl], out, cnt.p + lvl + 1);
                 MTG_CUDA(cudaGetLastError());
                 st_.launches += 3;
-                unsigned long long nn = 0;
-                MTG_CUDA(cudaMemcpyAsync(&nn, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
-                MTG_CUDA(cudaStreamSynchronize(stream_));
                 cur = out;
-                ncur = nn;
+                glevels = lvl + 1;
+                expect *= 0.5;   // generous bound on the survivors (grid size only; the kernels read the true count)
+                if (N * pow(0.3, glevels) < 4096.0) break;
             }
-            if (ncur) {  // keys that survive 24 levels go to the final exact map (practically never)
-                std::vector<K> h(ncur);
-                MTG_CUDA(cudaMemcpy(h.data(), cur, ncur * sizeof(K), cudaMemcpyDeviceToHost));
-                std::sort(h.begin(), h.end());
-                final_.alloc(ncur);
-                MTG_CUDA(cudaMemcpy(final_.p, h.data(), ncur * sizeof(K), cudaMemcpyHostToDevice));
-                nfinal_ = ncur;
+            unsigned long long ncur = 0;
+            MTG_CUDA(cudaMemcpyAsync(&ncur, cnt.p + glevels, 8, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaStreamSynchronize(stream_));
+            if (ncur) {
+                std::vector<K> h(ncur), next;
+                MTG_CUDA(cudaMemcpyAsync(h.data(), cur, ncur * sizeof(K), cudaMemcpyDeviceToHost, stream_));
+                MTG_CUDA(cudaStreamSynchronize(stream_));
+                std::vector<unsigned long long> tail(off - mphf_off_[glevels], 0ull);   // bit arrays of levels glevels..24
+                std::vector<uint64_t> pos;
+                for (int lvl = glevels; lvl < MPHF_LEVELS - 1 && !h.empty(); lvl++) {
+                    unsigned long long* bits = tail.data() + (mphf_off_[lvl] - mphf_off_[glevels]);
+                    std::vector<unsigned long long> collh(mphf_dom_[lvl] / 64, 0ull);
+                    pos.resize(h.size());
+                    for (size_t i = 0; i < h.size(); i++) {
+                        MphfState st;
+                        st.init(h[i], mphf_seed_);
+                        uint64_t hv = 0;
+                        for (int l = 0; l <= lvl; l++) hv = st.level_hash(l);
+                        const uint64_t p = hv % mphf_dom_[lvl];
+                        pos[i] = p;
+                        const unsigned long long m = 1ull << (p & 63);
+                        if (bits[p >> 6] & m) collh[p >> 6] |= m;
+                        bits[p >> 6] |= m;
+                    }
+                    for (size_t w = 0; w < collh.size(); w++) bits[w] &= ~collh[w];
+                    next.clear();
+                    for (size_t i = 0; i < h.size(); i++)
+                        if (!((bits[pos[i] >> 6] >> (pos[i] & 63)) & 1ull)) next.push_back(h[i]);
+                    h.swap(next);
+                }
+                MTG_CUDA(cudaMemcpyAsync(mphf_bits_.p + mphf_off_[glevels], tail.data(), tail.size() * 8, cudaMemcpyHostToDevice, stream_));
+                MTG_CUDA(cudaStreamSynchronize(stream_));
+                if (!h.empty()) {  // keys that survive 24 levels go to the final exact map (practically never)
+                    std::sort(h.begin(), h.end());
+                    final_.alloc(h.size());
+                    MTG_CUDA(cudaMemcpy(final_.p, h.data(), h.size() * sizeof(K), cudaMemcpyHostToDevice));
+                    nfinal_ = h.size();
+                }
             }
             mphf_built_ = true;
         }
+    }
+
+    // nb_branching + topology + the branching collection sorted by k-mer (BranchingAlgorithm::execute, :206-310)
+    uint64_t branching(const void* d_keys, const uint32_t* d_abund, uint64_t n, uint64_t* topology25, uint64_t* lo, uint64_t* hi,
+                       uint32_t* abundance, uint64_t capacity) override {
+        if (!adj_done_) throw Error(-4, "branching: the adjacency bytes are not built (graph not ready)");
+        const K* keys = (const K*)d_keys;
+        DevBuf<unsigned long long> cnt(32);
+        unsigned long long h[26];
+        GraphView<K> g = view();
+        cnt.zero(stream_);
+        if (n) {
+            branching_kernel<K><<<grid_for(n), 256, 0, stream_>>>(keys, d_abund, n, g, nullptr, nullptr, cnt.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        MTG_CUDA(cudaMemcpyAsync(h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        const uint64_t nb = h[0];
+        if (topology25) for (int i = 0; i < 25; i++) topology25[i] = h[1 + i];
+        if (!lo || !nb) return nb;
+        if (capacity < nb) throw Error(-1, "branching: output buffers too small");
+        DevBuf<K> ok(nb);
+        DevBuf<uint32_t> oa(nb);
+        cnt.zero(stream_);
+        branching_kernel<K><<<grid_for(n), 256, 0, stream_>>>(keys, d_abund, n, g, ok.p, oa.p, cnt.p);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches++;
+        std::vector<K> hk(nb);
+        std::vector<uint32_t> ha(nb);
+        MTG_CUDA(cudaMemcpyAsync(hk.data(), ok.p, nb * sizeof(K), cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaMemcpyAsync(ha.data(), oa.p, nb * 4, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        std::vector<uint64_t> order(nb);   // the collection is sorted by k-mer (BranchingAlgorithm.cpp:232-280); off the timed path
+        for (uint64_t i = 0; i < nb; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hk[a] < hk[b]; });
+        for (uint64_t i = 0; i < nb; i++) {
+            lo[i] = lo64(hk[order[i]]);
+            if (hi) hi[i] = hi64(hk[order[i]]);
+            if (abundance) abundance[i] = ha[order[i]];
+        }
+        return nb;
     }
 
     void set_ref_repeats(const void* d_keys, uint64_t n) override {

@@ -27,7 +27,8 @@ template <class K> struct GraphView {
     const uint32_t* b3; uint64_t b3_tai;
     const uint32_t* b4; uint64_t b4_tai;
     int casc_nhash;
-    const K* cfp; uint64_t ncfp;                                     // sorted
+    const K* cfp; uint64_t ncfp;                                     // exact set, open addressing over ncfp_slots (power of two) slots, empty = all ones
+    uint64_t cfp_slots;
     // BooPHF presence
     int mphf_built;
     uint64_t mphf_seed;
@@ -118,12 +119,27 @@ template <class K> MTG_D bool sorted_contains(const K* __restrict__ a, uint64_t 
     return lo < n && a[lo] == x;
 }
 
+// The final cFP set (DebloomAlgorithm.cpp:561 keeps it as a sorted vector and binary-searches it; only membership is ever
+// asked, so the device copy is a hash set: no sort on the build path). Canonical k-mers are never all ones (2k <= 126 bits).
+template <class K> MTG_D bool cfpset_contains(const K* __restrict__ set, uint64_t slots, uint64_t n, K x) {
+    if (n == 0) return false;
+    const K EMPTY = ~K(0);
+    uint64_t s = key_hash(x) & (slots - 1);
+    for (uint64_t probe = 0; probe < slots; probe++) {
+        const K v = set[s];
+        if (v == x) return true;
+        if (v == EMPTY) return false;
+        s = (s + 1) & (slots - 1);
+    }
+    return false;
+}
+
 // ContainerNodeCascading::containsCFP (ContainerNode.hpp:173-184)
 template <class K> MTG_D bool cfp_contains(const GraphView<K>& g, K x) {
-    if (!g.cascading) return sorted_contains(g.cfp, g.ncfp, x);
+    if (!g.cascading) return cfpset_contains(g.cfp, g.cfp_slots, g.ncfp, x);
     if (bloom_cache_contains<K>(g.b2, g.b2_tai, g.casc_nhash, g.seed0, g.rnd, x)) {
         if (!bloom_cache_contains<K>(g.b3, g.b3_tai, g.casc_nhash, g.seed0, g.rnd, x)) return true;
-        if (bloom_cache_contains<K>(g.b4, g.b4_tai, g.casc_nhash, g.seed0, g.rnd, x) && !sorted_contains(g.cfp, g.ncfp, x)) return true;
+        if (bloom_cache_contains<K>(g.b4, g.b4_tai, g.casc_nhash, g.seed0, g.rnd, x) && !cfpset_contains(g.cfp, g.cfp_slots, g.ncfp, x)) return true;
     }
     return false;
 }
@@ -320,6 +336,10 @@ public:
     virtual void buffer(int which, void** p, uint64_t* nbytes) = 0;
     // out[i] = OR over c of in[c * nwords + i] (64-bit words): the reduction of an OR-reduce-scatter
     virtual void or_chunks(const void* d_in, uint32_t nchunks, uint64_t nwords, void* d_out) = 0;
+    // branching nodes of the solid k-mers `d_keys` (with optional abundances): count, 5x5 topology [in][out], and (when lo != null)
+    // the collection sorted by k-mer, as BranchingAlgorithm writes it
+    virtual uint64_t branching(const void* d_keys, const uint32_t* d_abund, uint64_t n, uint64_t* topology25, uint64_t* lo, uint64_t* hi,
+                               uint32_t* abundance, uint64_t capacity) = 0;
     // repeated (k-1)-mers of the reference (device array of canonical K values with abundance >= het_max_occ+1)
     virtual void set_ref_repeats(const void* d_keys, uint64_t n) = 0;
     // batch queries on host arrays of FORWARD k-mers (any strand); out[i] bit0 = contains

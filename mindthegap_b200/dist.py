@@ -12,6 +12,7 @@ exchanges of the path:
 
 `engine` is a mindthegap_b200.Finder on a GPU; the CPU tests drive the same code with a fake engine over gloo.
 """
+import os
 import re
 import time
 
@@ -78,6 +79,36 @@ class TorchComm:
         dist.all_to_all_single(out, inp, output_split_sizes=output_split_sizes, input_split_sizes=input_split_sizes, group=self.group)
 
 
+class _Traced:
+    """MTG_DIST_TRACE=1: every call on the wrapped object (engine or comm) is bracketed by a device synchronize and its wall
+    clock accumulated per method name -- the per-operation timeline of one N-GPU find (a debugging aid; it serialises the
+    step, so numbers taken with it are not bench values)."""
+
+    def __init__(self, obj, table, prefix, device):
+        self.__dict__.update(_o=obj, _t=table, _p=prefix, _d=device)
+
+    def __getattr__(self, name):
+        a = getattr(self._o, name)
+        if not callable(a):
+            return a
+
+        def call(*args, **kw):
+            if self._d.type == "cuda":
+                torch.cuda.synchronize(self._d)
+            t0 = time.perf_counter()
+            r = a(*args, **kw)
+            if self._d.type == "cuda":
+                torch.cuda.synchronize(self._d)
+            e = self._t.setdefault(self._p + name, [0, 0.0])
+            e[0] += 1
+            e[1] += (time.perf_counter() - t0) * 1e3
+            return r
+        return call
+
+    def __setattr__(self, name, value):
+        setattr(self._o, name, value)
+
+
 class DistFind:
     OR_SMALL_WORDS = 1 << 17   # gathered size (64-bit words) up to which _or_reduce takes the single all-gather route
 
@@ -91,9 +122,18 @@ class DistFind:
         self.build_mode = build_mode
         self.device = device
         self.c = comm if comm is not None else TorchComm(group)
+        self.trace = None
+        if os.environ.get("MTG_DIST_TRACE"):
+            self.trace = {}
+            self.e = _Traced(self.e, self.trace, "engine.", device)
+            self.c = _Traced(self.c, self.trace, "comm.", device)
         self.rank = self.c.rank
         self.world = self.c.world
         self.k = engine.params.kmer_size
+        # the ranks of one node share its host cores: the chunked event replay takes an equal share (-nb-cores)
+        if hasattr(engine, "set_host_threads") and device.type == "cuda":
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", self.world))
+            engine.set_host_threads(max(1, (os.cpu_count() or 1) // max(1, local_world)))
         self.timing = {}
         self._t = None
 
@@ -341,17 +381,21 @@ class DistFind:
 
     # ---- stage 2: scan. ref_records: [(name, uint8 numpy array)] identical on every rank
     def scan(self, ref_records, ref_stream=None):
-        """ref_stream (optional): all reference sequences joined by a newline, as a uint8 array (saves rebuilding it)."""
+        """ref_stream (optional): all reference sequences joined by a newline, as a uint8 numpy array (saves rebuilding it),
+        a pinned host tensor, or a tensor already on this rank's device."""
         e, W, k = self.e, self.world, self.k
         self._mark(None)
         if ref_stream is None:
             ref_stream = np.concatenate([np.concatenate([s, np.array([10], dtype=np.uint8)]) for _, s in ref_records])
-        ref_dev = torch.from_numpy(np.ascontiguousarray(ref_stream)).to(self.device)   # the whole reference, once
+        if isinstance(ref_stream, torch.Tensor):
+            ref_dev = ref_stream if ref_stream.device == self.device else ref_stream.to(self.device, non_blocking=True)
+        else:
+            ref_dev = torch.from_numpy(np.ascontiguousarray(ref_stream)).to(self.device)   # the whole reference, once
         self._sync()
         if hasattr(e, "set_reference_device") and self.device.type == "cuda":
             e.set_reference_device(ref_dev.data_ptr(), ref_dev.numel())
         else:
-            e.set_reference(ref_stream)
+            e.set_reference(ref_stream.cpu().numpy() if isinstance(ref_stream, torch.Tensor) else ref_stream)
         self._mark("set_reference")
         lengths = [len(s) if len(s) >= k else 0 for _, s in ref_records]
         owner, load = assign_chromosomes(lengths, W)

@@ -397,6 +397,18 @@ template <class K> struct GraphOracle {
         for (int nt = 0; nt < 4; nt++) if (contains(canonical<K>(((graine >> 2) + ((K)nt << (2 * (k - 1)))) & mask, k))) d++;
         return d;
     }
+    // BranchingAlgorithm FunctorNodes (G/debruijn/impl/BranchingAlgorithm.cpp:150-165): nodes come from Graph::iterator()
+    // (canonical k-mer, forward strand); branching iff !(successors == 1 && predecessors == 1); the collection is sorted by
+    // k-mer (:232-280). topo[5*in + out] = data.topology[(in, out)].
+    uint64_t branching(std::vector<K>* nodes, uint64_t* topo25) const {
+        uint64_t nb = 0;
+        if (topo25) for (int i = 0; i < 25; i++) topo25[i] = 0;
+        for (K x : solid) {
+            int o = outdegree(x), in = indegree(x);
+            if (!(o == 1 && in == 1)) { nb++; if (nodes) nodes->push_back(x); if (topo25) topo25[5 * in + o]++; }
+        }
+        return nb;
+    }
 };
 
 }  // namespace mtgo

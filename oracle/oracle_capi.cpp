@@ -161,6 +161,20 @@ void mtgo_graph_info(void* p, uint64_t* out8) {
         out8[4] = g->g2.bloom4.reduced_tai; out8[5] = g->g2.cfp_set.size(); out8[6] = g->rb2.nb_repeated; out8[7] = g->rb2.bloom.reduced_tai;
     }
 }
+// branching nodes: returns the count; topo25 [in][out]; lo/hi (may be NULL) receive the sorted collection
+uint64_t mtgo_graph_branching(void* p, uint64_t* topo25, uint64_t* lo, uint64_t* hi) {
+    GraphHandle* g = (GraphHandle*)p;
+    if (g->k <= 31) {
+        std::vector<uint64_t> v;
+        uint64_t nb = g->g1.branching(&v, topo25);
+        if (lo) for (size_t i = 0; i < v.size(); i++) { lo[i] = v[i]; if (hi) hi[i] = 0; }
+        return nb;
+    }
+    std::vector<u128> v;
+    uint64_t nb = g->g2.branching(&v, topo25);
+    if (lo) for (size_t i = 0; i < v.size(); i++) { lo[i] = lo_of(v[i]); if (hi) hi[i] = hi_of(v[i]); }
+    return nb;
+}
 // reference stream: sequences separated by '\n'
 void mtgo_graph_set_reference(void* p, const char* stream, uint64_t n, int het_max_occ) {
     GraphHandle* g = (GraphHandle*)p;

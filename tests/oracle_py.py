@@ -52,6 +52,8 @@ def load():
     L.mtgo_graph_bits.restype = C.c_uint64
     L.mtgo_graph_bits.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.mtgo_graph_info.argtypes = [C.c_void_p, u64p]
+    L.mtgo_graph_branching.restype = C.c_uint64
+    L.mtgo_graph_branching.argtypes = [C.c_void_p, u64p, C.c_void_p, C.c_void_p]
     L.mtgo_graph_set_reference.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int]
     L.mtgo_graph_features.restype = C.c_uint64
     L.mtgo_graph_features.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, u8p, u8p]
@@ -119,6 +121,14 @@ class Graph:
         self.L.mtgo_graph_info(self.h, o)
         return dict(bloom=int(o[0]), nb_critical=int(o[1]), bloom2=int(o[2]), bloom3=int(o[3]), bloom4=int(o[4]),
                     cfp_set=int(o[5]), ref_repeated=int(o[6]), refbloom=int(o[7]))
+
+    def branching(self):
+        """(nb_branching, topology[in][out], lo, hi) -- BranchingAlgorithm restated (oracle/graph_oracle.hpp)."""
+        topo = np.zeros(25, dtype=np.uint64)
+        n = int(self.L.mtgo_graph_branching(self.h, topo, None, None))
+        lo = np.zeros(max(n, 1), dtype=np.uint64); hi = np.zeros(max(n, 1), dtype=np.uint64)
+        self.L.mtgo_graph_branching(self.h, topo, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p))
+        return n, topo.reshape(5, 5), lo[:n], hi[:n]
 
     def set_reference(self, stream: bytes, het_max_occ=1):
         self.L.mtgo_graph_set_reference(self.h, stream, len(stream), het_max_occ)

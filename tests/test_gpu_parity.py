@@ -190,6 +190,15 @@ def test_membership_structures_bit_exact(name):
     exp = g.query(clo, chi)
     assert ((got & 1) == (exp & 1)).all()
     assert ((got & 2) == (exp & 2)).all()
+    # branching nodes (BranchingAlgorithm): count, topology and the sorted collection with abundances
+    nb, topo, blo, bhi, bab = f.branching()
+    enb, etopo, elo, ehi = g.branching()
+    assert nb == enb and (topo == etopo).all() and (blo == elo).all() and (bhi == ehi).all()
+    if name == "full":
+        assert nb == 36   # the reference's own gold_find.output
+    ab_of = {(int(a), int(b)): int(c) for a, b, c in zip(lo, hi, ab)}
+    assert all(ab_of[(int(a), int(b))] == int(c) for a, b, c in zip(blo, bhi, bab))
+    assert f.branching(nodes=False)[0] == nb
     # dense features of every reference sequence
     for nm, seq in rrecs:
         if len(seq) < k:

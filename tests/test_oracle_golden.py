@@ -37,6 +37,20 @@ def test_bundled_example_equals_reference_gold_files(oracle_bin, tmp_path):
         assert int(re.search(pat, gold_out).group(1)) == int(info[key])
 
 
+def test_bundled_example_branching_nodes_equal_reference_gold_output(oracle):
+    """`nb_branching_nodes : 36` of the reference's own gold_find.output (BranchingAlgorithm on the bundled example)."""
+    case = CASES["full"]
+    reads, _ = case_paths(case)
+    stream = b"\n".join(s for _, s in oracle_py.read_sequences(reads)) + b"\n"
+    o = oracle_py.count_stream(stream, 31, abundance_min=-1, nthreads=2)
+    g = oracle_py.Graph(o["lo"], o["hi"], 31)
+    nb, topo, lo, hi = g.branching()
+    gold_out = open(os.path.join(GOLD, "full", "gold_find.output")).read()
+    assert nb == int(re.search(r"nb_branching_nodes\s*:\s*(\d+)", gold_out).group(1)) == 36
+    assert int(topo.sum()) == nb and topo[1, 1] == 0 and (np.diff(lo.astype(np.int64)) > 0).all()
+    g.close()
+
+
 def test_bundled_example_with_bed_equals_reference_gold_files(oracle_bin, tmp_path):
     """/root/reference/test/simple_full_test.sh:79-118: `find -bed gold.bed` against the reference's own gold_bed files."""
     bed = os.path.join(GOLD, "full_bed", "gold.bed")
