@@ -646,7 +646,12 @@ public:
         table_.alloc(TableCfg<K>::STRIDE);
         table_.fill_ff(stream_);
     }
-    ~Graph() override { if (ev_a_) cudaEventDestroy(ev_a_); if (ev_b_) cudaEventDestroy(ev_b_); }
+    ~Graph() override {
+        if (ev_a_) cudaEventDestroy(ev_a_);
+        if (ev_b_) cudaEventDestroy(ev_b_);
+        if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
+        if (side_ev_) cudaEventDestroy(side_ev_);
+    }
     int kmer_size() const override { return k_; }
     const GraphStats& stats() const override { return st_; }
     float last_features_ms() override {
@@ -1012,21 +1017,43 @@ public:
         st_.ncfp = n;
         cfp_local_.release();
     }
+    // BooPHF levels from the gathered table. shard_mphf_begin (optional, any time after the table ranges were all-gathered)
+    // queues the whole construction on a side stream: it only depends on the solid set, so it overlaps the critical-FP search
+    // and the cascade with their exchanges; shard_finish then only waits for it.
+    cudaStream_t side_ = nullptr;
+    cudaEvent_t side_ev_ = nullptr;
+    DevBuf<K> mphf_all_;
+    bool mphf_begun_ = false;
+    void mphf_from_table(cudaStream_t s) {
+        const uint64_t N = ntotal_;
+        mphf_all_.alloc(std::max<uint64_t>(N, 1));
+        MTG_CUDA(cudaMemsetAsync(counters_.p + 4, 0, 8, s));
+        const uint64_t nb = nbuckets_ * nshards_;
+        table_compact_kernel<K><<<grid_for(nb * TableCfg<K>::SLOTS), 256, 0, s>>>(table_.p, nb, mphf_all_.p, counters_.p + 4);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches++;
+        mphf_launch(mphf_all_.p, N, s);
+    }
+    void shard_mphf_begin() override {
+        if (!side_) { MTG_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking)); MTG_CUDA(cudaEventCreateWithFlags(&side_ev_, cudaEventDisableTiming)); }
+        MTG_CUDA(cudaEventRecord(side_ev_, stream_));
+        MTG_CUDA(cudaStreamWaitEvent(side_, side_ev_, 0));
+        mphf_from_table(side_);
+        mphf_begun_ = true;
+    }
     void shard_finish() override {
         EvTimer t(stream_);
         t.start();
         const uint64_t N = ntotal_;
-        DevBuf<K> all(std::max<uint64_t>(N, 1));
-        MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 8, stream_));
-        const uint64_t nb = nbuckets_ * nshards_;
-        table_compact_kernel<K><<<grid_for(nb * TableCfg<K>::SLOTS), 256, 0, stream_>>>(table_.p, nb, all.p, counters_.p);
-        MTG_CUDA(cudaGetLastError());
-        st_.launches++;
+        cudaStream_t s = mphf_begun_ ? side_ : stream_;
+        if (!mphf_begun_) mphf_from_table(s);
         unsigned long long got = 0;
-        MTG_CUDA(cudaMemcpyAsync(&got, counters_.p, 8, cudaMemcpyDeviceToHost, stream_));
-        MTG_CUDA(cudaStreamSynchronize(stream_));
+        MTG_CUDA(cudaMemcpyAsync(&got, counters_.p + 4, 8, cudaMemcpyDeviceToHost, s));
+        MTG_CUDA(cudaStreamSynchronize(s));
         if (got != N) throw Error(-6, "gathered table holds " + std::to_string(got) + " k-mers, expected " + std::to_string(N));
-        build_mphf(all.p, N);
+        mphf_complete(s);
+        mphf_begun_ = false;
+        mphf_all_.release();
         st_.ms_mphf = t.stop();
         share_.release();
         adj_done_ = true;
@@ -1049,7 +1076,19 @@ public:
     }
 
     // BooPHF levels from a device list of all solid k-mers
+    // BooPHF construction in two halves so that it can run on a side stream while the host drives other work (N-GPU build):
+    // mphf_launch queues every device level on `s` without synchronising; mphf_complete waits for `s` and finishes on the host.
+    DevBuf<unsigned long long> mphf_coll_, mphf_cnt_;
+    DevBuf<K> mphf_a_, mphf_b_;
+    const K* mphf_cur_ = nullptr;
+    int mphf_glevels_ = 0;
+    uint64_t mphf_total_words_ = 0, mphf_n_ = 0;
     void build_mphf(const K* keys, uint64_t N) {
+        mphf_launch(keys, N, stream_);
+        mphf_complete(stream_);
+    }
+    void mphf_launch(const K* keys, uint64_t N, cudaStream_t stream_) {
+        mphf_n_ = N;
         // ---- BooPHF levels (sizes: mphf::setup, BooPHF.h:1015-1041, double arithmetic on the host)
         mphf_built_ = false;
         nfinal_ = 0;
@@ -1067,11 +1106,15 @@ public:
                 off += d / 64;
             }
             mphf_bits_.alloc(off);
+            mphf_total_words_ = off;
             mphf_bits_.zero(stream_);
             st_.mphf_words = off;
-            DevBuf<unsigned long long> coll(mphf_dom_[0] / 64);
-            DevBuf<K> bufA(N), bufB(N);
-            DevBuf<unsigned long long> cnt(MPHF_LEVELS + 1);   // cnt[l] = keys entering level l
+            DevBuf<unsigned long long>& coll = mphf_coll_;
+            DevBuf<K>&bufA = mphf_a_, &bufB = mphf_b_;
+            DevBuf<unsigned long long>& cnt = mphf_cnt_;      // cnt[l] = keys entering level l
+            coll.alloc(mphf_dom_[0] / 64);
+            bufA.alloc(N); bufB.alloc(N);
+            cnt.alloc(MPHF_LEVELS + 1);
             cnt.zero(stream_);
             const unsigned long long n0 = N;
             MTG_CUDA(cudaMemcpyAsync(cnt.p, &n0, 8, cudaMemcpyHostToDevice, stream_));
@@ -1096,6 +1139,17 @@ public:
                 expect *= 0.5;   // generous bound on the survivors (grid size only; the kernels read the true count)
                 if (N * pow(0.3, glevels) < 4096.0) break;
             }
+            mphf_cur_ = cur;
+            mphf_glevels_ = glevels;
+        }
+    }
+    void mphf_complete(cudaStream_t stream_) {
+        const uint64_t N = mphf_n_;
+        if (N) {
+            const K* cur = mphf_cur_;
+            const int glevels = mphf_glevels_;
+            const uint64_t off = mphf_total_words_;
+            DevBuf<unsigned long long>& cnt = mphf_cnt_;
             unsigned long long ncur = 0;
             MTG_CUDA(cudaMemcpyAsync(&ncur, cnt.p + glevels, 8, cudaMemcpyDeviceToHost, stream_));
             MTG_CUDA(cudaStreamSynchronize(stream_));
@@ -1136,6 +1190,7 @@ public:
                 }
             }
             mphf_built_ = true;
+            mphf_coll_.release(); mphf_a_.release(); mphf_b_.release(); mphf_cnt_.release();
         }
     }
 

@@ -112,7 +112,7 @@ class _Traced:
 class DistFind:
     OR_SMALL_WORDS = 1 << 17   # gathered size (64-bit words) up to which _or_reduce takes the single all-gather route
 
-    def __init__(self, engine, device, group=None, scan_mode="auto", build_mode="sharded", comm=None):
+    def __init__(self, engine, device, group=None, scan_mode="auto", build_mode="sharded", comm=None, overlap_mphf=False):
         """scan_mode: "chromosomes" = every rank scans whole chromosomes (no feature exchange), "segments" = every chromosome
         is split across the ranks by position, "auto" = chromosomes when they balance within 25 %, else segments.
         build_mode: "sharded" = the membership structures are built from per-rank shares (table ranges all-gathered, Bloom bit
@@ -120,6 +120,10 @@ class DistFind:
         self.e = engine
         self.scan_mode = scan_mode
         self.build_mode = build_mode
+        # overlap_mphf: queue the BooPHF construction on the library's side stream right after the table all-gather. Measured
+        # on 4 x B200 (cfg2 per rank): no gain -- the critical-FP kernel it overlaps is itself DRAM-bound, so the two only share
+        # the memory system (19.1 ms without, 20.0 ms with); kept for problem sizes where the exchanges dominate.
+        self.overlap_mphf = overlap_mphf
         self.device = device
         self.c = comm if comm is not None else TorchComm(group)
         self.trace = None
@@ -149,8 +153,8 @@ class DistFind:
     def _sync(self):
         """The engine works on its own CUDA stream: torch-side copies and NCCL collectives must have finished before the
         library touches their buffers (the library synchronises its stream before returning, so the other direction is safe)."""
-        if self.device.type == "cuda":
-            torch.cuda.synchronize(self.device)
+        if self.device.type == "cuda":   # torch's stream only: a device-wide synchronize would also wait for the library's side stream
+            torch.cuda.current_stream(self.device).synchronize()
 
     def _all_max(self, *vals):
         t = torch.tensor(list(vals), dtype=torch.int64, device=self.device)
@@ -342,6 +346,9 @@ class DistFind:
         self._or_reduce(bloom)
         self.exchange_bytes["allgather_table"] = int(table.numel())
         self.exchange_bytes["or_reduce_bloom"] = int(bloom.numel())
+        if self.overlap_mphf and hasattr(e, "graph_shard_mphf_begin"):
+            self._sync()
+            e.graph_shard_mphf_begin()      # BooPHF levels on a side stream, under the critical-FP search and the cascade
         self._mark("table+bloom")
         # neighbours of the share: adjacency bytes of the own range (all-gathered) + critical candidates (to their owners)
         self._sync()
