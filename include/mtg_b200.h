@@ -28,6 +28,7 @@ typedef struct mtg_ctx mtg_ctx;
 #define MTG_F_BACKUP      0x10
 #define MTG_F_DELETION    0x20
 #define MTG_F_SMALL_HOMO  0x40
+#define MTG_F_HOST_PARSE  0x80   /* mtg_count_files: parse on the host (kseq-style reader) instead of on the GPU */
 #define MTG_F_DEFAULT (MTG_F_HOMO_INSERT | MTG_F_HETE_INSERT | MTG_F_SNP | MTG_F_DELETION | MTG_F_SMALL_HOMO)
 
 typedef struct mtg_params {
@@ -63,8 +64,19 @@ int mtg_set_minimizer_size(mtg_ctx* ctx, int32_t m);
 int32_t mtg_get_minimizer_size(mtg_ctx* ctx);
 int mtg_push_reads(mtg_ctx* ctx, const char* bases, uint64_t nbytes);              /* host buffer   */
 int mtg_push_reads_device(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes);     /* device buffer */
-/* Convenience host-side parser: FASTA/FASTQ files, comma separated list (Bank::open, G/bank/impl/Bank.cpp:49-52,
- * BankFasta.cpp:485-574). Plain text only. */
+/* Replaces BankFasta::Iterator::get_next_seq_from_file (G/bank/impl/BankFasta.cpp:485-574) for the reads: raw FASTA or
+ * FASTQ text, parsed on the GPU into the base stream above (csrc/ingest.cu). The text must start at a header line and end
+ * at a record boundary (mtg_count_files cuts its chunks that way). format: 0 = by the first byte, 1 = FASTA (multi-line
+ * sequences joined), 2 = FASTQ (4-line records). Irregular text (multi-line FASTQ, a missing '+' line) is an error, code -7. */
+int mtg_push_reads_text(mtg_ctx* ctx, const char* text, uint64_t nbytes, int32_t format);          /* host buffer   */
+int mtg_push_reads_text_device(mtg_ctx* ctx, const void* d_text, uint64_t nbytes, int32_t format); /* device buffer */
+/* Host helper for callers that stream a file themselves: the largest prefix of text[0..nbytes) that ends at a record start
+ * (FASTA: a line starting with '>'; FASTQ: a line starting with '@' whose second next line starts with '+'), nbytes when
+ * `final`, 0 when the buffer holds no complete record (grow it). format: 1 FASTA, 2 FASTQ. No GPU involved. */
+uint64_t mtg_text_record_cut(const char* text, uint64_t nbytes, int32_t format, int32_t final);
+/* Bank::open on a comma separated list of FASTA/FASTQ files, plain or gzip (G/bank/impl/Bank.cpp:49-52, README.md:166):
+ * file bytes are staged in pinned memory in chunks cut at record starts and parsed on the GPU (mtg_push_reads_text).
+ * With MTG_F_HOST_PARSE in params.flags the kseq-style host reader is used instead (plain text; any layout). */
 int mtg_count_files(mtg_ctx* ctx, const char* uri);
 /* Ends the counting: histogram, auto cut-off (Histogram::compute_threshold, G/tools/misc/impl/Histogram.cpp:59-189),
  * solidity filter (CountProcessorSolidity.hpp:182-185); then builds the membership structures of

@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libmtg_b200.so")
 
 F_HOMO_ONLY, F_HOMO_INSERT, F_HETE_INSERT, F_SNP, F_BACKUP, F_DELETION, F_SMALL_HOMO = 1, 2, 4, 8, 16, 32, 64
+F_HOST_PARSE = 128   # mtg_count_files: kseq-style host reader instead of the GPU parser
 F_DEFAULT = F_HOMO_INSERT | F_HETE_INSERT | F_SNP | F_DELETION | F_SMALL_HOMO
 ABUNDANCE_AUTO = -1
 
@@ -35,7 +36,7 @@ f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 
 EXPORTS = [
     "mtg_default_params", "mtg_create", "mtg_destroy", "mtg_last_error", "mtg_version", "mtg_count_reserve", "mtg_push_reads",
-    "mtg_push_reads_device", "mtg_count_files", "mtg_count_finish", "mtg_get_threshold", "mtg_get_cutoff_auto", "mtg_get_nb_solid",
+    "mtg_push_reads_device", "mtg_push_reads_text", "mtg_push_reads_text_device", "mtg_text_record_cut", "mtg_count_files", "mtg_count_finish", "mtg_get_threshold", "mtg_get_cutoff_auto", "mtg_get_nb_solid",
     "mtg_get_histogram", "mtg_get_stats", "mtg_stat_name", "mtg_export_solid", "mtg_load_solid", "mtg_set_reference",
     "mtg_contains_batch", "mtg_degree_batch", "mtg_ref_repeat_batch", "mtg_sequence_features", "mtg_sequence_features_device",
     "mtg_scan_reference", "mtg_scan_reference_bed", "mtg_scan_reference_device", "mtg_set_reference_device", "mtg_breakpoints_text", "mtg_vcf_text", "mtg_reset_outputs", "mtg_get_find_counters", "mtg_copy_bits",
@@ -47,6 +48,11 @@ EXPORTS = [
 ]
 
 _lib = None
+
+
+def text_record_cut(text: bytes, fmt: int, final=False) -> int:
+    """mtg_text_record_cut: largest prefix of `text` that ends at a FASTA (fmt 1) / FASTQ (fmt 2) record start."""
+    return int(load_library().mtg_text_record_cut(text, len(text), fmt, 1 if final else 0))
 
 
 def build_library():
@@ -74,6 +80,10 @@ def load_library():
     L.mtg_push_reads.argtypes = [vp, vp, C.c_uint64]
     L.mtg_push_reads_device.argtypes = [vp, vp, C.c_uint64]
     L.mtg_count_files.argtypes = [vp, C.c_char_p]
+    L.mtg_push_reads_text.argtypes = [vp, vp, C.c_uint64, C.c_int32]
+    L.mtg_push_reads_text_device.argtypes = [vp, vp, C.c_uint64, C.c_int32]
+    L.mtg_text_record_cut.restype = C.c_uint64
+    L.mtg_text_record_cut.argtypes = [C.c_char_p, C.c_uint64, C.c_int32, C.c_int32]
     L.mtg_count_finish.argtypes = [vp]
     L.mtg_get_threshold.argtypes = [vp]
     L.mtg_get_cutoff_auto.argtypes = [vp]
@@ -257,6 +267,15 @@ class Finder:
 
     def push_reads_device(self, dev_ptr, nbytes):
         self._check(self.L.mtg_push_reads_device(self.ctx, C.c_void_p(dev_ptr), nbytes))
+
+    def push_reads_text(self, text, fmt=0):
+        """Raw FASTA/FASTQ text (bytes or uint8 array; starts at a header, ends at a record boundary), parsed on the GPU.
+        fmt: 0 by the first byte, 1 FASTA, 2 FASTQ."""
+        a = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, dtype=np.uint8)
+        self._check(self.L.mtg_push_reads_text(self.ctx, _ptr(a), a.size, int(fmt)))
+
+    def push_reads_text_device(self, dev_ptr, nbytes, fmt=0):
+        self._check(self.L.mtg_push_reads_text_device(self.ctx, C.c_void_p(dev_ptr), nbytes, int(fmt)))
 
     def count_files(self, uri):
         self._check(self.L.mtg_count_files(self.ctx, uri.encode()))

@@ -1,10 +1,14 @@
 // mtg-b200 C ABI (include/mtg_b200.h): thin glue over the CUDA engine. No CPU fallback anywhere.
+#include <ctype.h>
+#include <zlib.h>
+
 #include <memory>
 #include <mutex>
 
 #include "../../include/mtg_b200.h"
 #include "count.cuh"
 #include "graph.cuh"
+#include "ingest.cuh"
 #include "replay.hpp"
 #include "seqio.hpp"
 
@@ -133,6 +137,10 @@ struct mtg_ctx {
     // solid set kept on the device for export
     std::unique_ptr<ICounter> solid_owner;
     std::vector<uint64_t> loaded_lo, loaded_hi;
+    // text ingest (FASTA/FASTQ parsed on the GPU)
+    std::unique_ptr<TextIngest> ingest;
+    DevBuf<uint8_t> text_stage, text_out;
+    IngestStats ingest_total;
     // reference
     uint64_t ref_repeated = 0;
     CountStats ref_count_stats;
@@ -265,9 +273,101 @@ int mtg_push_reads_device(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes) {
     MTG_TRY(ctx) WallTimer w(ctx->wall_push); reads_counter(ctx)->push_device((const uint8_t*)d_bases, nbytes); MTG_CATCH
 }
 
+// raw FASTA/FASTQ text (device) -> base stream (ingest.cu) -> the counter
+static void push_text_device(mtg_ctx* ctx, const uint8_t* d_text, uint64_t n, int format) {
+    ICounter* c = reads_counter(ctx);
+    if (!ctx->ingest) ctx->ingest.reset(new TextIngest(ctx->stream));
+    const uint64_t nout = ctx->ingest->run(d_text, n, format, ctx->text_out);
+    const IngestStats& s = ctx->ingest->stats();
+    ctx->ingest_total.bytes_in += s.bytes_in; ctx->ingest_total.bytes_out += s.bytes_out; ctx->ingest_total.nb_sequences += s.nb_sequences;
+    ctx->ingest_total.ms += s.ms; ctx->ingest_total.launches += s.launches;
+    if (nout) c->push_device(ctx->text_out.p, nout);
+}
+static void push_text_host(mtg_ctx* ctx, const char* text, uint64_t n, int format) {
+    if (!n) return;
+    MTG_CUDA(cudaSetDevice(ctx->p.device));
+    if (ctx->text_stage.n < n + 64) ctx->text_stage.alloc(n + 64);
+    MTG_CUDA(cudaMemcpyAsync(ctx->text_stage.p, text, n, cudaMemcpyHostToDevice, ctx->stream));
+    push_text_device(ctx, ctx->text_stage.p, n, format);
+}
+int mtg_push_reads_text(mtg_ctx* ctx, const char* text, uint64_t nbytes, int32_t format) {
+    MTG_TRY(ctx) WallTimer w(ctx->wall_push); push_text_host(ctx, text, nbytes, format); MTG_CATCH
+}
+int mtg_push_reads_text_device(mtg_ctx* ctx, const void* d_text, uint64_t nbytes, int32_t format) {
+    MTG_TRY(ctx) WallTimer w(ctx->wall_push); MTG_CUDA(cudaSetDevice(ctx->p.device)); push_text_device(ctx, (const uint8_t*)d_text, nbytes, format); MTG_CATCH
+}
+
+uint64_t mtg_text_record_cut(const char* text, uint64_t nbytes, int32_t format, int32_t final) {
+    if (!text || (format != TEXT_FASTA && format != TEXT_FASTQ)) return 0;
+    return text_record_cut(text, nbytes, format, final != 0);
+}
+
+// One file of the -in list: raw bytes (plain or gzip, zlib reads both) staged in pinned memory in chunks cut at record starts,
+// parsed and packed on the GPU. Leading bytes before the first header are skipped like BankFasta.cpp:496-501.
+static void count_file_text(mtg_ctx* ctx, const std::string& path) {
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) throw Error(-2, "Cannot open file " + path);
+    gzbuffer(f, 1u << 20);
+    size_t cap = 128u << 20;
+    if (const char* e = getenv("MTG_INGEST_CHUNK")) cap = std::max<size_t>((size_t)atoll(e), 64);   // tests: force many chunks
+    PinnedBuf buf;
+    buf.reserve(cap);
+    size_t have = 0;
+    bool eof = false;
+    int fmt = TEXT_AUTO;
+    try {
+        while (!eof || have) {
+            while (!eof && have < cap) {
+                const int r = gzread(f, buf.as<char>() + have, (unsigned)std::min<size_t>(cap - have, 1u << 30));
+                if (r < 0) throw Error(-2, "read error in " + path);
+                if (r == 0) eof = true; else have += (size_t)r;
+            }
+            char* text = buf.as<char>();
+            if (fmt == TEXT_AUTO) {
+                size_t i = 0;
+                while (i < have && text[i] != '>' && text[i] != '@') i++;
+                if (i == have) { have = 0; continue; }     // no header yet: drop and read on
+                fmt = text[i] == '>' ? TEXT_FASTA : TEXT_FASTQ;
+                memmove(text, text + i, have - i);
+                have -= i;
+                continue;                                  // refill the freed space first
+            }
+            size_t cut = text_record_cut(text, have, fmt, eof);
+            size_t send = cut;
+            if (eof) while (send && isspace((unsigned char)text[send - 1])) send--;
+            if (cut == 0 && !eof) {                        // one record longer than the chunk (a chromosome on one line): grow
+                PinnedBuf bigger;
+                bigger.reserve(cap * 2);
+                memcpy(bigger.p, buf.p, have);
+                std::swap(buf.p, bigger.p); std::swap(buf.cap, bigger.cap);
+                cap *= 2;
+                continue;
+            }
+            if (send) push_text_host(ctx, text, send, fmt);
+            memmove(text, text + cut, have - cut);
+            have -= cut;
+        }
+    } catch (...) { gzclose(f); throw; }
+    gzclose(f);
+}
+
 int mtg_count_files(mtg_ctx* ctx, const char* uri) {
     MTG_TRY(ctx)
+    WallTimer w(ctx->wall_push);
     ICounter* c = reads_counter(ctx);
+    if (!(ctx->p.flags & MTG_F_HOST_PARSE)) {
+        const std::string u(uri);
+        size_t start = 0;
+        while (start <= u.size()) {
+            const size_t comma = u.find(',', start);
+            const std::string path = u.substr(start, comma == std::string::npos ? std::string::npos : comma - start);
+            if (!path.empty()) count_file_text(ctx, path);
+            if (comma == std::string::npos) break;
+            start = comma + 1;
+        }
+        return 0;
+    }
+    // MTG_F_HOST_PARSE: the kseq-style host reader (multi-line FASTQ and other layouts the GPU parser rejects; plain text only)
     std::string chunk;
     const size_t CHUNK = 256u << 20;
     chunk.reserve(CHUNK + (1 << 20));
@@ -478,6 +578,7 @@ static const char* STAT_NAMES[] = {
     "scan.positions", "scan.valid", "scan.in_graph", "scan.table_probes", "scan.bloom_emulations", "scan.ms_features", "scan.ms_replay",
     "scan.observer_queries", "scan.probe_batches", "scan.prefetched_queries", "scan.unforeseen_queries",
     "api.ms_push_reads", "api.ms_count_finish", "api.ms_set_reference", "api.ms_scan_reference",
+    "ingest.bytes_in", "ingest.bytes_out", "ingest.nb_sequences", "ingest.ms", "ingest.launches",
     "mem.arena_cached_mb", "mem.arena_live_mb"};
 static const int NSTATS = sizeof(STAT_NAMES) / sizeof(STAT_NAMES[0]);
 const char* mtg_stat_name(int i) { return (i >= 0 && i < NSTATS) ? STAT_NAMES[i] : nullptr; }
@@ -497,7 +598,9 @@ int mtg_get_stats(mtg_ctx* ctx, double* out, int cap) {
                   (double)g.ref_repeated, (double)g.ref_tai,
                   (double)ctx->scan_positions, (double)ctx->scan_valid, (double)ctx->scan_in_graph, (double)ctx->scan_table_probes,
                   (double)ctx->scan_fallback, ctx->ms_features, ctx->ms_replay, (double)oq, (double)pb, (double)rc.prefetched_queries,
-                  (double)rc.unforeseen_queries, ctx->wall_push, ctx->wall_finish, ctx->wall_set_reference, ctx->wall_scan, 0.0, 0.0};
+                  (double)rc.unforeseen_queries, ctx->wall_push, ctx->wall_finish, ctx->wall_set_reference, ctx->wall_scan,
+                  (double)ctx->ingest_total.bytes_in, (double)ctx->ingest_total.bytes_out, (double)ctx->ingest_total.nb_sequences,
+                  ctx->ingest_total.ms, (double)ctx->ingest_total.launches, 0.0, 0.0};
     {
         std::lock_guard<std::mutex> lk(g_arena_mu);
         v[NSTATS - 2] = g_arena_cached_bytes / 1048576.0; v[NSTATS - 1] = g_arena_live_bytes / 1048576.0;

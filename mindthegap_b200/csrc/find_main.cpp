@@ -36,7 +36,9 @@ static void usage() {
             "  -abundance-min <n|auto>  [auto]      -abundance-max <n> [2147483647]\n"
             "  -max-rep <n> [5]   -het-max-occ <n> [1]   -snp-min-val <n> [5]   -branching-filter <n> [15]\n"
             "  -homo-only -insert-only -snp-only -deletion-only -hete-only -backup -no-snp -no-insert -no-deletion -no-hetero\n"
-            "  -nb-cores <host threads of the event replay> [0 = all]; -max-memory / -max-disk / -out-tmp / -verbose are accepted and ignored; -device <gpu> [0]\n");
+            "  -nb-cores <host threads of the event replay> [0 = all]; -max-memory / -max-disk / -out-tmp / -verbose are accepted and ignored; -device <gpu> [0]\n"
+            "  -host-parse: read -in on the host (kseq-style; any FASTA/FASTQ layout) instead of parsing the file bytes on the GPU (plain or .gz,\n"
+            "               FASTA or 4-line FASTQ)\n");
 }
 
 int main(int argc, char** argv) {
@@ -44,7 +46,7 @@ int main(int argc, char** argv) {
     int nb_cores = 0;  // 0 = all cores (src/Finder.cpp:137)
     mtg_params p;
     mtg_default_params(&p);
-    bool f_homo_only = false, f_insert_only = false, f_snp_only = false, f_deletion_only = false, f_hete_only = false, f_backup = false,
+    bool f_homo_only = false, f_insert_only = false, f_snp_only = false, f_deletion_only = false, f_hete_only = false, f_backup = false, f_host_parse = false,
          f_no_snp = false, f_no_insert = false, f_no_deletion = false, f_no_hetero = false;
     int i = 1;
     if (i < argc && !strcmp(argv[i], "find")) i++;
@@ -72,6 +74,7 @@ int main(int argc, char** argv) {
         else if (o == "-deletion-only") f_deletion_only = true;
         else if (o == "-hete-only") f_hete_only = true;
         else if (o == "-backup") f_backup = true;
+        else if (o == "-host-parse") f_host_parse = true;
         else if (o == "-no-snp") f_no_snp = true;
         else if (o == "-no-insert") f_no_insert = true;
         else if (o == "-no-deletion") f_no_deletion = true;
@@ -106,7 +109,7 @@ int main(int argc, char** argv) {
     if (f_no_deletion) deletion = false;
     if (f_no_hetero) hete_insert = false;
     p.flags = (homo_only ? MTG_F_HOMO_ONLY : 0) | (homo_insert ? MTG_F_HOMO_INSERT : 0) | (hete_insert ? MTG_F_HETE_INSERT : 0) |
-              (snp ? MTG_F_SNP : 0) | (backup ? MTG_F_BACKUP : 0) | (deletion ? MTG_F_DELETION : 0) | MTG_F_SMALL_HOMO;
+              (snp ? MTG_F_SNP : 0) | (backup ? MTG_F_BACKUP : 0) | (deletion ? MTG_F_DELETION : 0) | MTG_F_SMALL_HOMO | (f_host_parse ? MTG_F_HOST_PARSE : 0);
 
     struct timespec t0, t1, t2;
     clock_gettime(CLOCK_MONOTONIC, &t0);

@@ -76,3 +76,29 @@ def test_parse_bed_follows_reference_rules():
         api.parse_bed("c\tx\t10\n", "c", 31)
     with pytest.raises(api.MtgError):
         api.parse_bed("c\t10\n", "c", 31)
+
+
+def test_text_record_cut(lib):
+    """mtg_text_record_cut (host helper of the GPU text ingest): chunks end where a record starts; a quality line that
+    begins with '@' is not mistaken for a header (gatb-core bank/impl/BankFasta.cpp:485-574 reads records sequentially,
+    a chunked reader has to find the boundary from the text alone)."""
+    lib.mtg_text_record_cut.restype = ctypes.c_uint64
+    lib.mtg_text_record_cut.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int32]
+
+    def cut(text, fmt, final=False):
+        return int(lib.mtg_text_record_cut(text, len(text), fmt, 1 if final else 0))
+
+    rec = [b"@r0 x\nACGT\n+\nIIII\n", b"@r1\nGGGG\n+r1\n@III\n", b"@r2\nTTTT\n+\n@@@@\n", b"@r3\nCCCC\n+\nII"]
+    fq = b"".join(rec)
+    starts = [0, len(rec[0]), len(rec[0]) + len(rec[1]), len(rec[0]) + len(rec[1]) + len(rec[2])]
+    assert cut(fq, 2, final=True) == len(fq)
+    # every prefix: the cut is the last record start whose '+' line is inside the prefix, never a quality line
+    for n in range(1, len(fq) + 1):
+        c = cut(fq[:n], 2)
+        assert c in starts and c < n
+        complete = [s for s in starts[1:] if fq[:n].count(b"\n", s) >= 2 and n > fq.index(b"\n+", s) + 1]
+        assert c == (max(complete) if complete else 0), (n, c)
+    fa = b">a\nACGT\nAC\n>b c\nGG\n\n>c\nT"
+    assert cut(fa, 1) == fa.rindex(b">c") and cut(fa[:11], 1) == 0 and cut(fa[:12], 1) == 11 and cut(fa[:14], 1) == 11
+    assert cut(fa, 1, final=True) == len(fa)
+    assert cut(b"", 2) == 0 and cut(fq, 0) == 0

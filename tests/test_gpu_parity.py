@@ -380,3 +380,129 @@ def test_dist_path_two_gpus(tmp_path, case):
     assert res["bk"] == ebk and res["vcf"] == evcf
     import re
     assert res["nb_solid"] == int(re.search(r"nb_solid_kmers\s*:\s*(\d+)", einfo).group(1))
+
+
+# ---------------------------------------------------------------------------------------------- text ingest on the GPU
+def _solid_of(f):
+    f.finish_count()
+    lo, hi, ab = f.export_solid()
+    return _sorted_solid(lo, hi, ab) + (f.histogram().copy(), f.threshold)
+
+
+def _same_solid(a, b):
+    assert len(a[0]) == len(b[0])
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2] == b[2]).all()
+    assert (a[3] == b[3]).all() and a[4] == b[4]
+
+
+def _messy_fasta(rng, n=400):
+    """Multi-line FASTA with CRLF line ends, lower case, N runs, IUPAC codes, blank lines, an empty record and a last line
+    without newline -- everything BankFasta.cpp:485-574 tolerates in FASTA."""
+    out = []
+    for i in range(n):
+        L = int(rng.integers(0, 400))
+        seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=L)
+        if L > 50 and i % 3 == 0:
+            seq[10:13] = ord("N")
+        if L > 80 and i % 5 == 0:
+            seq[60] = ord("R")
+        s = seq.tobytes()
+        if i % 4 == 0:
+            s = s.lower()
+        width = [60, 70, 80, 1000][i % 4]
+        eol = b"\r\n" if i % 2 else b"\n"
+        out.append(b">seq%d some comment @ + >\tx" % i + eol)
+        for o in range(0, len(s), width):
+            out.append(s[o:o + width] + eol)
+        if i % 7 == 0:
+            out.append(eol)
+    text = b"".join(out)
+    return text.rstrip(b"\r\n")   # the last sequence line has no newline
+
+
+@pytest.mark.parametrize("k", [31, 63])
+def test_text_ingest_fastq_equals_host_parser(k):
+    """mtg_push_reads_text on the bundled FASTQ files == pushing the sequences parsed by the oracle's kseq-style reader."""
+    case = CASES["full"]
+    reads, _ = case_paths(case)
+    stream, _ = _stream(reads)
+    a = _finder(k)
+    a.push_reads(stream)
+    ref = _solid_of(a)
+    b = _finder(k)
+    for path in reads.split(","):
+        b.push_reads_text(open(path, "rb").read())
+    got = _solid_of(b)
+    _same_solid(ref, got)
+    st = b.stats()
+    assert int(st["ingest.nb_sequences"]) == len(oracle_py.read_sequences(reads))
+    assert int(st["ingest.bytes_out"]) == len(stream) + 2 and st["ingest.launches"] > 0   # one extra separator per file
+    a.close(); b.close()
+
+
+def test_text_ingest_messy_fasta_equals_host_parser(tmp_path):
+    rng = np.random.default_rng(7)
+    text = _messy_fasta(rng)
+    path = str(tmp_path / "messy.fa")
+    open(path, "wb").write(text)
+    stream, recs = _stream(path)
+    assert len(recs) == 400
+    a = _finder(21, ["-abundance-min", "1"])
+    a.push_reads(stream)
+    ref = _solid_of(a)
+    b = _finder(21, ["-abundance-min", "1"])
+    b.push_reads_text(text)
+    _same_solid(ref, _solid_of(b))
+    assert int(b.stats()["ingest.nb_sequences"]) == 400
+    a.close(); b.close()
+
+
+def test_count_files_chunked_and_gzip_equal_one_push(tmp_path, monkeypatch):
+    """mtg_count_files: chunks cut at record starts (forced tiny: 3000-byte chunks), gzip input, FASTA + FASTQ in one -in list."""
+    import gzip
+    import mindthegap_b200 as m
+    case = CASES["full"]
+    reads, _ = case_paths(case)
+    r1, r2 = reads.split(",")
+    rng = np.random.default_rng(11)
+    fa = str(tmp_path / "messy.fa")
+    open(fa, "wb").write(_messy_fasta(rng, 150))
+    gz = str(tmp_path / "r2.fastq.gz")
+    with gzip.open(gz, "wb") as g:
+        g.write(open(r2, "rb").read() + b"\n\n")      # trailing blank lines are tolerated at the end of a file
+    uri = ",".join([r1, gz, fa])
+    stream, _ = _stream(",".join([r1, r2, fa]))
+    a = _finder(31)
+    a.push_reads(stream)
+    ref = _solid_of(a)
+    for chunk in ("3000", None):
+        if chunk:
+            monkeypatch.setenv("MTG_INGEST_CHUNK", chunk)
+        else:
+            monkeypatch.delenv("MTG_INGEST_CHUNK", raising=False)
+        b = _finder(31)
+        b.count_files(uri)
+        _same_solid(ref, _solid_of(b))
+        b.close()
+    # the host reader behind MTG_F_HOST_PARSE gives the same set (plain text files)
+    p = m.FindParams.from_cli(["-kmer-size", "31"])
+    p.flags |= m.api.F_HOST_PARSE
+    c = m.Finder(p)
+    c.count_files(",".join([r1, r2, fa]))
+    _same_solid(ref, _solid_of(c))
+    a.close(); c.close()
+
+
+def test_text_ingest_rejects_irregular_text():
+    """Multi-line FASTQ / a missing '+' line is an error (code -7), never a guess; the host reader takes such files."""
+    import mindthegap_b200 as m
+    f = _finder(21)
+    multi = b"@r1\nACGTACGTACGTACGTACGTACGT\nACGTACGTAC\n+\nIIIIIIIIIIIIIIIIIIIIIIII\nIIIIIIIIII\n"
+    with pytest.raises(m.MtgError) as e:
+        f.push_reads_text(multi)
+    assert "irregular FASTQ" in str(e.value) and "byte 29" in str(e.value)
+    with pytest.raises(m.MtgError):
+        f.push_reads_text(b"ACGT\n")                      # no header at all
+    with pytest.raises(m.MtgError):
+        f.push_reads_text(b">a\nACGT\n@b\nACGT\n+\nIIII\n")   # FASTQ record inside FASTA
+    f.close()
