@@ -10,7 +10,7 @@ enum TextFormat { TEXT_AUTO = 0, TEXT_FASTA = 1, TEXT_FASTQ = 2 };
 
 struct IngestStats {
     uint64_t bytes_in = 0, bytes_out = 0, nb_sequences = 0, nb_lines = 0;
-    float ms = 0;          // device time of the last run (three passes + two scans)
+    float ms = 0;          // device time of the last run (three passes + two two-level scans)
     uint64_t launches = 0;
 };
 
@@ -39,7 +39,8 @@ private:
     DevBuf<uint32_t> tile_nl_, tile_kept_;
     DevBuf<long long> tile_last_;
     DevBuf<unsigned long long> tile_line0_, tile_out0_, counters_;
-    DevBuf<long long> tile_prev_nl_;
+    DevBuf<long long> tile_prev_nl_, blk_prev_nl_;
+    DevBuf<unsigned long long> blk_line0_, blk_out0_;
 };
 
 // Host helper: the largest prefix of text[0..n) that ends at a record start (so that the remainder begins with a header
