@@ -156,6 +156,15 @@ int mtg_get_histogram(mtg_ctx* ctx, uint64_t* out10001);
 int mtg_get_stats(mtg_ctx* ctx, double* out, int cap);
 const char* mtg_stat_name(int i);
 
+/* The solid set in DSK's on-disk layout, for the .h5 hand-off to the unchanged CPU `fill`: what
+ * PartitionsByVectorCommand::executeDump + CountProcessorDump leave in `dsk/solid/<p>` (G/kmer/impl/PartitionsCommand.cpp:1206-1806,
+ * CountProcessorDump.hpp:140-144) and Repartitor::computeDistrib in `minimizers/minimRepart` (G/kmer/impl/PartiInfo.cpp:40-86,
+ * 270-302). Every solid k-mer goes to partition repart_table[GATB minimizer of the k-mer] (ModelMinimizer, Model.hpp:1040-1287,
+ * minimizer_size = 10 in MindTheGap, src/Finder.cpp:246); output arrays are ordered by (partition, k-mer);
+ * part_offsets[nb_partitions + 1] bounds the partitions; repart_table has 4^minimizer_size entries. Off the timed path. */
+int mtg_export_dsk_partitions(mtg_ctx* ctx, uint32_t nb_partitions, uint32_t minimizer_size, uint16_t* repart_table, uint64_t* part_offsets,
+                              uint64_t* lo, uint64_t* hi, uint32_t* abundance, uint64_t capacity);
+
 /* Replaces BranchingAlgorithm::execute (G/debruijn/impl/BranchingAlgorithm.cpp:150-165, 206-310), the source of the
  * "nb_branching_nodes" info line (src/Finder.cpp:467): solid k-mers whose (predecessors, successors) != (1, 1). Needs the
  * graph built from counted or loaded solid k-mers. *nb_branching receives the count; topology25 (may be NULL) the

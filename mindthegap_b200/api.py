@@ -44,7 +44,7 @@ EXPORTS = [
     "mtg_count_run", "mtg_count_filter", "mtg_solid_copy", "mtg_graph_build_device", "mtg_sequence_features_device2", "mtg_replay_sequence",
     "mtg_graph_build_begin", "mtg_graph_critical", "mtg_graph_critical_copy", "mtg_graph_build_end", "mtg_set_host_threads", "mtg_set_minimizer_size", "mtg_get_minimizer_size",
     "mtg_solid_partition", "mtg_partition_keys", "mtg_graph_shard_begin", "mtg_graph_shard_critical", "mtg_graph_adj_pack", "mtg_graph_adj_unpack",
-    "mtg_graph_branching", "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_mphf_begin", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
+    "mtg_graph_branching", "mtg_export_dsk_partitions", "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_mphf_begin", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
 ]
 
 _lib = None
@@ -95,6 +95,7 @@ def load_library():
     L.mtg_stat_name.argtypes = [C.c_int]
     L.mtg_export_solid.argtypes = [vp, u64p, vp, vp, C.c_uint64]
     L.mtg_load_solid.argtypes = [vp, u64p, vp, C.c_uint64]
+    L.mtg_export_dsk_partitions.argtypes = [vp, C.c_uint32, C.c_uint32, vp, u64p, u64p, vp, vp, C.c_uint64]
     L.mtg_graph_branching.argtypes = [vp, u64p, vp, vp, vp, vp, C.c_uint64]
     L.mtg_set_reference.argtypes = [vp, vp, C.c_uint64]
     for fn in (L.mtg_contains_batch, L.mtg_degree_batch, L.mtg_ref_repeat_batch):
@@ -311,6 +312,16 @@ class Finder:
         ab = np.zeros(max(n, 1), dtype=np.uint32)
         self._check(self.L.mtg_export_solid(self.ctx, lo, _ptr(hi), _ptr(ab), max(n, 1)))
         return lo[:n], hi[:n], ab[:n]
+
+    def export_dsk_partitions(self, nb_partitions=4, minimizer_size=10):
+        """Solid k-mers ordered by (DSK partition, k-mer) + the minimRepart table: (repart uint16[4^m], offsets[nparts+1], lo, hi, ab)."""
+        n = self.nb_solid
+        repart = np.zeros(4 ** minimizer_size, dtype=np.uint16)
+        offs = np.zeros(nb_partitions + 1, dtype=np.uint64)
+        lo = np.zeros(max(n, 1), dtype=np.uint64); hi = np.zeros(max(n, 1), dtype=np.uint64)
+        ab = np.zeros(max(n, 1), dtype=np.uint32)
+        self._check(self.L.mtg_export_dsk_partitions(self.ctx, nb_partitions, minimizer_size, _ptr(repart), offs, lo, _ptr(hi), _ptr(ab), max(n, 1)))
+        return repart, offs, lo[:n], hi[:n], ab[:n]
 
     def branching(self, nodes=True):
         """BranchingAlgorithm (gatb-core debruijn/impl/BranchingAlgorithm.cpp:150-310): (nb_branching, topology[in][out] 5x5,

@@ -8,6 +8,7 @@
 #include "../../include/mtg_b200.h"
 #include "count.cuh"
 #include "graph.cuh"
+#include "dsk_export.cuh"
 #include "ingest.cuh"
 #include "replay.hpp"
 #include "seqio.hpp"
@@ -619,6 +620,24 @@ int mtg_export_solid(mtg_ctx* ctx, uint64_t* lo, uint64_t* hi, uint32_t* abundan
     else {
         for (uint64_t i = 0; i < ctx->nb_solid; i++) { lo[i] = ctx->loaded_lo[i]; if (hi) hi[i] = ctx->loaded_hi.empty() ? 0 : ctx->loaded_hi[i]; if (abundance) abundance[i] = 0; }
     }
+    MTG_CATCH
+}
+
+int mtg_export_dsk_partitions(mtg_ctx* ctx, uint32_t nb_partitions, uint32_t minimizer_size, uint16_t* repart_table, uint64_t* part_offsets,
+                              uint64_t* lo, uint64_t* hi, uint32_t* abundance, uint64_t capacity) {
+    MTG_TRY(ctx)
+    if (!ctx->solid_owner) throw Error(-4, "mtg_export_dsk_partitions: no counted solid set on this context");
+    if (!repart_table || !part_offsets || !lo) throw Error(-1, "mtg_export_dsk_partitions: null output");
+    const uint64_t n = ctx->solid_owner->nb_solid();
+    if (capacity < n) throw Error(-1, "export buffer too small");
+    if (ctx->p.kmer_size > 31 && !hi) throw Error(-1, "kmer_size > 31 needs the high words");
+    MTG_CUDA(cudaSetDevice(ctx->p.device));
+    if (ctx->p.kmer_size <= 31)
+        dsk_partition_export<uint64_t>((const uint64_t*)ctx->solid_owner->solid_keys_device(), ctx->solid_owner->solid_abundance_device(), n,
+                                       ctx->p.kmer_size, (int)minimizer_size, nb_partitions, ctx->stream, repart_table, part_offsets, lo, hi, abundance);
+    else
+        dsk_partition_export<u128>((const u128*)ctx->solid_owner->solid_keys_device(), ctx->solid_owner->solid_abundance_device(), n,
+                                   ctx->p.kmer_size, (int)minimizer_size, nb_partitions, ctx->stream, repart_table, part_offsets, lo, hi, abundance);
     MTG_CATCH
 }
 

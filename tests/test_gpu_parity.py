@@ -506,3 +506,38 @@ def test_text_ingest_rejects_irregular_text():
     with pytest.raises(m.MtgError):
         f.push_reads_text(b">a\nACGT\n@b\nACGT\n+\nIIII\n")   # FASTQ record inside FASTA
     f.close()
+
+
+# ---------------------------------------------------------------------------------------------- .h5 hand-off layout
+@pytest.mark.parametrize("name,nparts", [("full", 4), ("full_k63", 7), ("syn_tiny_k32", 1)])
+def test_export_dsk_partitions(name, nparts):
+    """mtg_export_dsk_partitions: every solid k-mer sits in the partition its GATB minimizer (oracle restatement of
+    ModelMinimizer, pinned to the TestKmer KATs) maps to, partitions are sorted by k-mer like DSK's dump, the union is the
+    solid set with its abundances, and the repartition table balances the partitions (Repartitor::computeDistrib)."""
+    import ctypes as C
+    case = CASES[name]
+    reads, _ = case_paths(case)
+    stream, _ = _stream(reads)
+    k = case["k"]
+    f = _finder(case)
+    f.push_reads(stream)
+    f.finish_count()
+    slo, shi, sab = _sorted_solid(*f.export_solid())
+    repart, offs, lo, hi, ab = f.export_dsk_partitions(nparts, 10)
+    assert len(repart) == 4 ** 10 and int(repart.max()) < nparts
+    assert int(offs[0]) == 0 and int(offs[-1]) == len(lo) == len(slo) and (np.diff(offs.astype(np.int64)) >= 0).all()
+    L = oracle_py.load()
+    L.mtgo_minimizer.restype = C.c_uint32
+    L.mtgo_minimizer.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
+    for p in range(nparts):
+        a, b = int(offs[p]), int(offs[p + 1])
+        keys = [(int(h), int(l)) for h, l in zip(hi[a:b], lo[a:b])]
+        assert keys == sorted(keys) and len(set(keys)) == len(keys)          # sorted by k-mer inside the partition
+        for h, l in keys[:: max(1, len(keys) // 400)]:                          # a sample of each partition through the oracle
+            assert int(repart[L.mtgo_minimizer(l, h, k, 10, 1)]) == p
+    glo, ghi, gab = _sorted_solid(lo, hi, ab)
+    assert (glo == slo).all() and (ghi == shi).all() and (gab == sab).all()
+    if nparts > 1:                                                             # LPT packing: no partition far above the mean
+        sizes = np.diff(offs.astype(np.int64))
+        assert sizes.max() <= 1.5 * sizes.mean() + 64
+    f.close()
