@@ -107,7 +107,8 @@ def run_cpu_find(wl, cores, workdir, tag="cpu"):
 
 def cpu_sample_scale(args):
     """Genome scale of the bounded CPU sample: --cpu-scale of cfg2's 4.6 Mbp, i.e. the same number of bases for every config."""
-    return args.cpu_scale if args.config == "cfg2" else args.cpu_scale * 4.6 / 64.0
+    import synth
+    return args.cpu_scale * 4.6e6 / synth.CONFIGS[args.config]["genome_len"]
 
 
 def reference_arm(args):
@@ -399,7 +400,7 @@ def own_arm(args):
     # ---- text ingest: the same reads as 4-line FASTQ text, parsed on the GPU (csrc/ingest.cu). Reported beside
     # the find step, not inside it: the bench line's host buffers are already-parsed bases, like the CPU arm whose parse time is excluded.
     ingest = None
-    if world == 1:
+    if world == 1 and nbytes < (2 << 30):
         L = wl["read_len"]
         rows = wl["stream"].reshape(-1, L + 1)
         fq = np.empty((rows.shape[0], 2 * L + 7), dtype=np.uint8)
@@ -498,7 +499,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the GPU workload (1.0 = the named config)")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3"], help="BASELINE.json configs[1] (default, the bench line) or configs[2]")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4s"],
+                    help="BASELINE.json configs[1] (default, the bench line), configs[2], or cfg4s = one GPU's eighth of configs[3]")
     ap.add_argument("--kmer-size", type=int, default=31, help="k (31 = the bench line; 63 exercises the 128-bit kernels, configs[4])")
     ap.add_argument("--cpu-scale", type=float, default=0.25, help="genome scale of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

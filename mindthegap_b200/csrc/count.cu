@@ -748,6 +748,10 @@ template <class K> class Counter : public ICounter {
 public:
     bool distinct_hint_ = false;
     uint64_t nvalid_total_ = 0;   // valid k-mer instances pushed so far (host copy)
+    ~Counter() override {
+        if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
+        for (cudaEvent_t e : copy_events_) cudaEventDestroy(e);
+    }
     Counter(int k, int m, cudaStream_t s, bool distinct_hint) : k_(k), m_(m), stream_(s), histo_(HISTO_MAX + 1, 0), distinct_hint_(distinct_hint) {
         if (m_ > k_) m_ = k_;
         if (m_ > SK_MAX_M) m_ = SK_MAX_M;
@@ -784,11 +788,45 @@ public:
         resolved_ = true;
     }
 
+    // Host buffer -> device in chunks cut at sequence separators: every chunk's copy is queued on a copy stream up front, the
+    // pack + super-k-mer kernels of chunk i run while chunk i+1.. are still crossing PCIe (pinned source; a pageable source
+    // degrades to the serial behaviour). A chunk is its own batch, exactly as if the caller had pushed it separately.
+    cudaStream_t copy_stream_ = nullptr;
+    std::vector<cudaEvent_t> copy_events_;
     void push_host(const char* bases, uint64_t n) override {
         if (!n) return;
         if (staging_.n < n + 64) staging_.alloc(n + 64);
-        MTG_CUDA(cudaMemcpyAsync(staging_.p, bases, n, cudaMemcpyHostToDevice, stream_));
-        push_device(staging_.p, n);
+        const uint64_t CH = std::max<uint64_t>(48ull << 20, n / 32);   // at most ~32 batches
+        std::vector<uint64_t> cuts(1, 0);
+        while (n > 2 * CH && cuts.back() < n) {
+            uint64_t e = std::min<uint64_t>(n, cuts.back() + CH);
+            if (e < n) {
+                const void* q = memrchr(bases + cuts.back(), '\n', e - cuts.back());          // last separator inside the chunk
+                if (!q) q = memchr(bases + e, '\n', n - e);                                    // a sequence longer than a chunk
+                e = q ? (uint64_t)((const char*)q - bases) + 1 : n;
+                if (n - e < CH / 4) e = n;                                                     // no tiny last chunk
+            }
+            cuts.push_back(e);
+        }
+        if (cuts.size() <= 2) {
+            MTG_CUDA(cudaMemcpyAsync(staging_.p, bases, n, cudaMemcpyHostToDevice, stream_));
+            push_device(staging_.p, n);
+            return;
+        }
+        resolve_partitioning(n);   // the minimizer length follows the whole volume, not the first chunk
+        if (!copy_stream_) MTG_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+        const size_t nch = cuts.size() - 1;
+        while (copy_events_.size() < nch + 1) { cudaEvent_t e; MTG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); copy_events_.push_back(e); }
+        MTG_CUDA(cudaEventRecord(copy_events_[nch], stream_));            // staging_ may still be read by earlier work on stream_
+        MTG_CUDA(cudaStreamWaitEvent(copy_stream_, copy_events_[nch], 0));
+        for (size_t c = 0; c < nch; c++) {
+            MTG_CUDA(cudaMemcpyAsync(staging_.p + cuts[c], bases + cuts[c], cuts[c + 1] - cuts[c], cudaMemcpyHostToDevice, copy_stream_));
+            MTG_CUDA(cudaEventRecord(copy_events_[c], copy_stream_));
+        }
+        for (size_t c = 0; c < nch; c++) {
+            MTG_CUDA(cudaStreamWaitEvent(stream_, copy_events_[c], 0));
+            push_device(staging_.p + cuts[c], cuts[c + 1] - cuts[c]);
+        }
     }
 
     void push_device(const uint8_t* d_bases, uint64_t n) override {

@@ -1,7 +1,7 @@
 // mtg-b200 input ingest on the GPU: FASTA/FASTQ text -> base stream (see ingest.cuh for the accepted layouts and the
 // reference lines they restate: gatb-core bank/impl/BankFasta.cpp:485-574).
 //
-// The text is cut in tiles of 4096 bytes (256 threads x 16 bytes, one 128-bit load per thread). What a byte means depends
+// The text is cut in tiles of 16 KB (4 sub-tiles of 256 threads x 16 bytes, one 128-bit load per thread and sub-tile). What a byte means depends
 // on the line it belongs to, i.e. on everything before it, so the parse is three streaming passes around two small scans:
 //   lines   : per tile, number of '\n' and position of the last one
 //   scan 1  : (two levels) exclusive sum (line index at the start of every tile) and exclusive max (last '\n' before the tile, which
@@ -19,7 +19,9 @@
 namespace mtg {
 namespace {
 
-const int IG_THREADS = 256, IG_PER = 16, IG_TILE = IG_THREADS * IG_PER, IG_WARPS = IG_THREADS / 32;
+// a tile = IG_SUB sub-tiles of 256 threads x 16 bytes; the 4 loads of a thread are issued together (one DRAM latency per 16 KB),
+// the sub-tiles are then classified in order with the line count / last newline / output offset carried from one to the next
+const int IG_THREADS = 256, IG_PER = 16, IG_SUBTILE = IG_THREADS * IG_PER, IG_SUB = 4, IG_TILE = IG_SUBTILE * IG_SUB, IG_WARPS = IG_THREADS / 32;
 
 // 16 text bytes of one thread as four little-endian words (byte j of the thread = byte j&3 of w[j>>2]); bytes past n read as 0
 struct Bytes16 { uint32_t w0, w1, w2, w3; };
@@ -66,7 +68,7 @@ __device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* s_warp,
     if (total) *total = tot;
     return before + inc - v;
 }
-__device__ __forceinline__ long long block_excl_max(long long v, long long* s_warp) {
+__device__ __forceinline__ long long block_excl_max(long long v, long long* s_warp, long long* total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     long long inc = v;
 #pragma unroll
@@ -76,9 +78,10 @@ __device__ __forceinline__ long long block_excl_max(long long v, long long* s_wa
     }
     if (lane == 31) s_warp[w] = inc;
     __syncthreads();
-    long long before = -1;
+    long long before = -1, tot = -1;
 #pragma unroll
-    for (int i = 0; i < IG_WARPS; i++) if (i < w && s_warp[i] > before) before = s_warp[i];
+    for (int i = 0; i < IG_WARPS; i++) { if (i < w && s_warp[i] > before) before = s_warp[i]; if (s_warp[i] > tot) tot = s_warp[i]; }
+    if (total) *total = tot;
     long long excl = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
     if (lane == 0) excl = -1;
     __syncthreads();
@@ -89,11 +92,16 @@ __global__ void __launch_bounds__(IG_THREADS) ig_lines_kernel(const uint8_t* __r
                                                               long long* __restrict__ tile_last) {
     __shared__ uint32_t s_cnt[IG_WARPS];
     __shared__ long long s_last[IG_WARPS];
-    const uint64_t base = (uint64_t)blockIdx.x * IG_TILE + (uint64_t)threadIdx.x * IG_PER;
-    const Bytes16 b = load16(text, base, n, aligned);          // bytes past n read as 0, never '\n'
-    const uint32_t nl = eq_mask16(b, '\n');
-    uint32_t cnt = __popc(nl);
-    long long last = nl ? (long long)(base + (31 - __clz(nl))) : -1;
+    uint32_t cnt = 0;
+    long long last = -1;
+#pragma unroll
+    for (int sub = 0; sub < IG_SUB; sub++) {
+        const uint64_t base = (uint64_t)blockIdx.x * IG_TILE + (uint64_t)sub * IG_SUBTILE + (uint64_t)threadIdx.x * IG_PER;
+        const Bytes16 b = load16(text, base, n, aligned);      // bytes past n read as 0, never '\n'
+        const uint32_t nl = eq_mask16(b, '\n');
+        cnt += __popc(nl);
+        if (nl) last = (long long)(base + (31 - __clz(nl)));   // bases grow with sub: the last assignment is the largest
+    }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -205,70 +213,86 @@ __global__ void __launch_bounds__(IG_THREADS) ig_compact_kernel(const uint8_t* _
     __shared__ uint32_t s_u32[IG_WARPS];
     __shared__ long long s_i64[IG_WARPS];
     __shared__ uint8_t s_out[WRITE ? IG_TILE : 1];
-    const uint64_t base = (uint64_t)blockIdx.x * IG_TILE + (uint64_t)threadIdx.x * IG_PER;
-    const Bytes16 b = load16(text, base, n, aligned);
-    const uint32_t nvalid = base < n ? (uint32_t)(n - base < IG_PER ? n - base : IG_PER) : 0u;
-    const uint32_t vm = (1u << nvalid) - 1u;
-    const uint32_t nl = eq_mask16(b, '\n');
-    const uint32_t nl_before = block_excl_sum(__popc(nl), s_u32, nullptr);
-    long long prev = block_excl_max(nl ? (long long)(base + (31 - __clz(nl))) : -1, s_i64);   // last '\n' before this thread, in the tile
-    const long long tprev = tile_prev_nl[blockIdx.x], bprev = blk_prev_nl[blockIdx.x >> 10];
-    if (tprev > prev) prev = tprev;
-    if (bprev > prev) prev = bprev;
-    const unsigned long long line = tile_line0[blockIdx.x] + blk_line0[blockIdx.x >> 10] + nl_before;
-    // '\r' directly before '\n' is dropped (the byte after this thread's last one decides for byte 15)
-    const uint8_t after = (base + IG_PER < n) ? __ldg(text + base + IG_PER) : (uint8_t)0;
-    const uint32_t crdrop = eq_mask16(b, '\r') & ((nl >> 1) | (after == '\n' ? 0x8000u : 0u));
-    // Walk the (few) line segments of the 16 bytes instead of the bytes: the class of a byte only changes after a '\n'.
-    uint32_t keep = 0, nseq = 0, rem = nl, s0 = 0;
-    bool at_start = nvalid && (long long)base == prev + 1;     // this thread's first byte starts a line
-    unsigned phase = (unsigned)(line & 3ull);                   // FASTQ: 0 header, 1 sequence, 2 '+', 3 quality
-    bool header = false;                                        // FASTA: the current line is a header
-    if (FMT == TEXT_FASTA && nvalid && !at_start) header = __ldg(text + (prev + 1)) == '>';
-    while (s0 < nvalid) {
-        const uint32_t e = rem ? (uint32_t)(__ffs(rem) - 1) : (uint32_t)IG_PER;       // the segment's '\n', or none
-        const uint32_t body = ((1u << e) - 1u) & ~((1u << s0) - 1u);                  // [s0, e)
-        const uint32_t nlbit = e < IG_PER ? 1u << e : 0u;
-        if (FMT == TEXT_FASTQ) {
-            if (at_start) {
-                const uint8_t c = byte_at(b, (int)s0);
-                if ((phase == 0 && c != '@') || (phase == 2 && c != '+')) { atomicMin(counters + 1, (unsigned long long)(base + s0)); counters[2] = 1; }
-                if (phase == 1) nseq++;
+    const uint64_t tbase = (uint64_t)blockIdx.x * IG_TILE + (uint64_t)threadIdx.x * IG_PER;
+    Bytes16 bb[IG_SUB];
+#pragma unroll
+    for (int sub = 0; sub < IG_SUB; sub++) bb[sub] = load16(text, tbase + (uint64_t)sub * IG_SUBTILE, n, aligned);
+    unsigned long long carry_line = tile_line0[blockIdx.x] + blk_line0[blockIdx.x >> 10];
+    long long carry_prev = tile_prev_nl[blockIdx.x];
+    { const long long bprev = blk_prev_nl[blockIdx.x >> 10]; if (bprev > carry_prev) carry_prev = bprev; }
+    uint32_t carry_out = 0, nseq = 0;
+#pragma unroll
+    for (int sub = 0; sub < IG_SUB; sub++) {
+        const Bytes16 b = bb[sub];
+        const uint64_t base = tbase + (uint64_t)sub * IG_SUBTILE;
+        const uint32_t nvalid = base < n ? (uint32_t)(n - base < IG_PER ? n - base : IG_PER) : 0u;
+        const uint32_t vm = (1u << nvalid) - 1u;
+        const uint32_t nl = eq_mask16(b, '\n');
+        uint32_t nl_total = 0;
+        const uint32_t nl_before = block_excl_sum(__popc(nl), s_u32, &nl_total);
+        long long last_total = -1;
+        long long prev = block_excl_max(nl ? (long long)(base + (31 - __clz(nl))) : -1, s_i64, &last_total);   // last '\n' before this thread
+        if (carry_prev > prev) prev = carry_prev;
+        const unsigned long long line = carry_line + nl_before;
+        // '\r' directly before '\n' is dropped (the byte after this thread's last one decides for byte 15)
+        const uint8_t after = (base + IG_PER < n) ? __ldg(text + base + IG_PER) : (uint8_t)0;
+        const uint32_t crdrop = eq_mask16(b, '\r') & ((nl >> 1) | (after == '\n' ? 0x8000u : 0u));
+        // Walk the (few) line segments of the 16 bytes instead of the bytes: the class of a byte only changes after a '\n'.
+        uint32_t keep = 0, rem = nl, s0 = 0;
+        bool at_start = nvalid && (long long)base == prev + 1;     // this thread's first byte starts a line
+        unsigned phase = (unsigned)(line & 3ull);                   // FASTQ: 0 header, 1 sequence, 2 '+', 3 quality
+        bool header = false;                                        // FASTA: the current line is a header
+        if (FMT == TEXT_FASTA && nvalid && !at_start) header = __ldg(text + (prev + 1)) == '>';
+        while (s0 < nvalid) {
+            const uint32_t e = rem ? (uint32_t)(__ffs(rem) - 1) : (uint32_t)IG_PER;       // the segment's '\n', or none
+            const uint32_t body = ((1u << e) - 1u) & ~((1u << s0) - 1u);                  // [s0, e)
+            const uint32_t nlbit = e < IG_PER ? 1u << e : 0u;
+            if (FMT == TEXT_FASTQ) {
+                if (at_start) {
+                    const uint8_t c = byte_at(b, (int)s0);
+                    if ((phase == 0 && c != '@') || (phase == 2 && c != '+')) { atomicMin(counters + 1, (unsigned long long)(base + s0)); counters[2] = 1; }
+                    if (phase == 1) nseq++;
+                }
+                if (phase == 1) keep |= body | nlbit;             // the sequence line with its '\n' (the separator)
+                phase = (phase + 1) & 3u;
+            } else {
+                if (at_start) {
+                    const uint8_t c = byte_at(b, (int)s0);
+                    header = c == '>';
+                    if (c == '@' || c == '+') { atomicMin(counters + 1, (unsigned long long)(base + s0)); counters[2] = 2; }
+                    if (header) nseq++;
+                }
+                keep |= header ? nlbit : body;                     // header line -> one separator; sequence lines joined
             }
-            if (phase == 1) keep |= body | nlbit;             // the sequence line with its '\n' (the separator)
-            phase = (phase + 1) & 3u;
-        } else {
-            if (at_start) {
-                const uint8_t c = byte_at(b, (int)s0);
-                header = c == '>';
-                if (c == '@' || c == '+') { atomicMin(counters + 1, (unsigned long long)(base + s0)); counters[2] = 2; }
-                if (header) nseq++;
-            }
-            keep |= header ? nlbit : body;                     // header line -> one separator; sequence lines joined
+            if (e >= IG_PER) break;
+            rem &= rem - 1;
+            s0 = e + 1;
+            at_start = true;
         }
-        if (e >= IG_PER) break;
-        rem &= rem - 1;
-        s0 = e + 1;
-        at_start = true;
+        keep &= vm & ~crdrop;
+        uint32_t total = 0;
+        const uint32_t off = block_excl_sum(__popc(keep), s_u32, &total);
+        if (WRITE) {
+            uint32_t o = carry_out + off, k2 = keep;              // kept bytes staged in shared memory, then written as whole sectors
+            while (k2) {
+                const int j = __ffs(k2) - 1;
+                s_out[o++] = byte_at(b, j);
+                k2 &= k2 - 1;
+            }
+        }
+        carry_out += total;
+        carry_line += nl_total;
+        if (last_total > carry_prev) carry_prev = last_total;
     }
-    keep &= vm & ~crdrop;
-    uint32_t total = 0;
-    const uint32_t off = block_excl_sum(__popc(keep), s_u32, &total);
     if (!WRITE) {
-        if (threadIdx.x == 0) tile_kept[blockIdx.x] = total;
+        if (threadIdx.x == 0) tile_kept[blockIdx.x] = carry_out;
         uint32_t nseq_blk = 0;
-        block_excl_sum(nseq, s_u32, &nseq_blk);              // one atomic per tile, not per sequence
+        block_excl_sum(nseq, s_u32, &nseq_blk);                  // one atomic per tile, not per sequence
         if (threadIdx.x == 0 && nseq_blk) atomicAdd(counters, (unsigned long long)nseq_blk);
     } else {
-        uint32_t o = off, k2 = keep;                          // kept bytes staged in shared memory, then written as whole sectors
-        while (k2) {
-            const int j = __ffs(k2) - 1;
-            s_out[o++] = byte_at(b, j);
-            k2 &= k2 - 1;
-        }
         __syncthreads();
         uint8_t* dst = out + tile_out0[blockIdx.x] + blk_out0[blockIdx.x >> 10];
-        for (uint32_t q = threadIdx.x; q < total; q += IG_THREADS) dst[q] = s_out[q];
+        for (uint32_t q = threadIdx.x; q < carry_out; q += IG_THREADS) dst[q] = s_out[q];
     }
 }
 

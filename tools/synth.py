@@ -140,6 +140,8 @@ CONFIGS = {
     "tiny": dict(genome_len=60_000, chroms=2, coverage=30, read_len=100, n_hom=6, n_het=4, n_snp=8, n_del=4, spacing=1000),
     "small": dict(genome_len=400_000, chroms=1, coverage=30, read_len=100, n_hom=20, n_het=10, n_snp=40, n_del=10, spacing=1000),
     "cfg2": dict(genome_len=4_600_000, chroms=1, coverage=50, read_len=150, n_hom=200, n_het=0, n_snp=0, n_del=0, spacing=2000),
+    # one GPU's eighth of BASELINE configs[3] (3.1 Gbp human-scale genome, 24 chromosomes, 30x 2x100 bp): 3 chromosomes, 387.5 Mbp
+    "cfg4s": dict(genome_len=387_500_000, chroms=3, coverage=30, read_len=100, n_hom=12000, n_het=12000, n_snp=38750, n_del=6000, spacing=2000),
     "cfg3": dict(genome_len=64_000_000, chroms=1, coverage=30, read_len=150, n_hom=2000, n_het=2000, n_snp=6400, n_del=1000, spacing=2000),
 }
 
