@@ -125,6 +125,9 @@ int mtg_graph_build_end(mtg_ctx* ctx, const void* d_keys, uint64_t n, const void
  *   mtg_partition_keys(buffer 7)   -> all-to-all of the candidates by owner; mtg_graph_critical_set_share de-duplicates
  *   mtg_graph_shard_cascade 0..3   B2, B3, B4 (createCFP, DebloomAlgorithm.cpp:462-622): OR-reduce after steps 0, 1, 2;
  *                                  step 3 leaves the rank's part of the cFP set (buffer 6) -> all-gather -> mtg_graph_set_cfp
+ *   mtg_graph_shard_mphf_level 0,1 optional, any time after all-gather(table): BooPHF levels 0 and 1 built slice-wise (each rank sets
+ *                                  only the bits of its slice of the level) -> all-gather(buffer 8) after each; the remaining
+ *                                  levels (8 % of the k-mers) are built by every rank in mtg_graph_shard_finish
  *   mtg_graph_shard_mphf_begin     optional, any time after all-gather(table): BooPHF levels queued on a side stream, so that
  *                                  they overlap the steps above (they depend on the solid set only)
  *   mtg_graph_shard_finish         BooPHF levels from the gathered table; the graph answers queries from here on          */
@@ -138,9 +141,11 @@ int mtg_graph_adj_unpack(mtg_ctx* ctx);
 int mtg_graph_critical_set_share(mtg_ctx* ctx, const void* d_candidates, uint64_t n, uint64_t* n_out);
 int mtg_graph_shard_cascade(mtg_ctx* ctx, int step, uint64_t ncrit_total, uint64_t* n_out);
 int mtg_graph_set_cfp(mtg_ctx* ctx, const void* d_all, uint64_t n);
+int mtg_graph_shard_mphf_level(mtg_ctx* ctx, int32_t level);
 int mtg_graph_shard_mphf_begin(mtg_ctx* ctx);
 int mtg_graph_shard_finish(mtg_ctx* ctx);
-/* which: 0 exact table (all ranges), 1 main Bloom, 2..4 B2..B4, 5 adjacency bytes, 6 local cFP part, 7 critical share;
+/* which: 0 exact table (all ranges), 1 main Bloom, 2..4 B2..B4, 5 adjacency bytes, 6 local cFP part, 7 critical share,
+ * 8 the BooPHF level built slice-wise last;
  * device pointer and byte size, valid until the next build call on this context */
 int mtg_graph_buffer(mtg_ctx* ctx, int which, void** d_ptr, uint64_t* nbytes);
 /* d_out[i] = OR over c < nchunks of d_in[c * nwords + i], 64-bit words: the reduction step of an OR-reduce-scatter (NCCL has no

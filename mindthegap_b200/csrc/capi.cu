@@ -545,6 +545,7 @@ int mtg_graph_shard_cascade(mtg_ctx* ctx, int step, uint64_t ncrit_total, uint64
     MTG_CATCH
 }
 int mtg_graph_set_cfp(mtg_ctx* ctx, const void* d_all, uint64_t n) { MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->set_cfp(d_all, n); MTG_CATCH }
+int mtg_graph_shard_mphf_level(mtg_ctx* ctx, int32_t level) { MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->shard_mphf_level(level); MTG_CATCH }
 int mtg_graph_shard_mphf_begin(mtg_ctx* ctx) { MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->shard_mphf_begin(); MTG_CATCH }
 int mtg_graph_shard_finish(mtg_ctx* ctx) {
     MTG_TRY(ctx)

@@ -291,7 +291,9 @@ __global__ void __launch_bounds__(256) cfpset_build_kernel(const K* __restrict__
 // bit of its level hash; a second arrival marks a collision.
 template <class K>
 __global__ void __launch_bounds__(256) mphf_level_kernel(const K* __restrict__ keys, const unsigned long long* __restrict__ n_ptr, int level, uint64_t dom,
-                                                         uint64_t seed, unsigned long long* __restrict__ bits, unsigned long long* __restrict__ coll) {
+                                                         uint64_t seed, unsigned long long* __restrict__ bits, unsigned long long* __restrict__ coll,
+                                                         uint64_t slice_words, uint32_t slice) {
+    // slice_words != 0: N-GPU build, this rank only owns words [slice * slice_words, (slice + 1) * slice_words) of the level
     const uint64_t n = *n_ptr;   // survivors of the previous level, counted on the device (no host round trip between levels)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         MphfState st;
@@ -299,6 +301,7 @@ __global__ void __launch_bounds__(256) mphf_level_kernel(const K* __restrict__ k
         uint64_t h = 0;
         for (int l = 0; l <= level; l++) h = st.level_hash(l);
         uint64_t p = h % dom;
+        if (slice_words && ((p >> 6) < (uint64_t)slice * slice_words || (p >> 6) >= (uint64_t)(slice + 1) * slice_words)) continue;
         unsigned long long m = 1ull << (p & 63);
         unsigned long long old = atomicOr(bits + (p >> 6), m);
         if (old & m) atomicOr(coll + (p >> 6), m);
@@ -1034,6 +1037,26 @@ public:
         st_.launches++;
         mphf_launch(mphf_all_.p, N, s);
     }
+    // N-GPU: level `level` (0 or 1) built slice-wise -- this rank inserts only the keys whose bit falls into its slice of the
+    // level's bit array (every rank holds all keys: the gathered table), so the atomics stay in an array W times smaller; the
+    // slices are then all-gathered in place (buffer 8) and every rank derives the survivors itself.
+    int mphf_sliced_ = 0;
+    void shard_mphf_level(int level) override {
+        if (level != mphf_sliced_ || level > 1) throw Error(-1, "shard_mphf_level: levels 0, 1 in order");
+        if (level == 0) {
+            const uint64_t N = ntotal_;
+            mphf_all_.alloc(std::max<uint64_t>(N, 1));
+            MTG_CUDA(cudaMemsetAsync(counters_.p + 4, 0, 8, stream_));
+            const uint64_t nb = nbuckets_ * nshards_;
+            table_compact_kernel<K><<<grid_for(nb * TableCfg<K>::SLOTS), 256, 0, stream_>>>(table_.p, nb, mphf_all_.p, counters_.p + 4);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+            mphf_setup(mphf_all_.p, N, nshards_, stream_);
+        } else if (mphf_n_) mphf_compact(level - 1, stream_);
+        if (mphf_n_) mphf_level(level, true, stream_);
+        mphf_sliced_ = level + 1;
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+    }
     void shard_mphf_begin() override {
         if (!side_) { MTG_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking)); MTG_CUDA(cudaEventCreateWithFlags(&side_ev_, cudaEventDisableTiming)); }
         MTG_CUDA(cudaEventRecord(side_ev_, stream_));
@@ -1046,13 +1069,16 @@ public:
         t.start();
         const uint64_t N = ntotal_;
         cudaStream_t s = mphf_begun_ ? side_ : stream_;
-        if (!mphf_begun_) mphf_from_table(s);
+        if (mphf_sliced_) {                       // levels 0..mphf_sliced_-1 are complete (gathered): survivors, then the rest replicated
+            if (mphf_n_) { mphf_compact(mphf_sliced_ - 1, s); mphf_levels(mphf_sliced_, s); }
+        } else if (!mphf_begun_) mphf_from_table(s);
         unsigned long long got = 0;
         MTG_CUDA(cudaMemcpyAsync(&got, counters_.p + 4, 8, cudaMemcpyDeviceToHost, s));
         MTG_CUDA(cudaStreamSynchronize(s));
         if (got != N) throw Error(-6, "gathered table holds " + std::to_string(got) + " k-mers, expected " + std::to_string(N));
         mphf_complete(s);
         mphf_begun_ = false;
+        mphf_sliced_ = 0;
         mphf_all_.release();
         st_.ms_mphf = t.stop();
         share_.release();
@@ -1065,7 +1091,10 @@ public:
         else if (which == 5) { *p = adjbuf_.p; *nbytes = adjbuf_.n * 16; }
         else if (which == 6) { *p = cfp_local_.p; *nbytes = ncfp_local_ * sizeof(K); }
         else if (which == 7) { *p = crit_list_.p; *nbytes = ncrit_ * sizeof(K); }
-        else throw Error(-1, "buffer: which 0..7");
+        else if (which == 8) {   // the BooPHF level built slice-wise last: nshards equal slices, slice `shard` filled
+            if (!mphf_sliced_ || !mphf_n_) { *p = mphf_bits_.p; *nbytes = 0; }
+            else { *p = mphf_bits_.p + mphf_off_[mphf_sliced_ - 1]; *nbytes = mphf_slice_words(mphf_sliced_ - 1) * mphf_pad_ * 8; }
+        } else throw Error(-1, "buffer: which 0..8");
     }
     void or_chunks(const void* d_in, uint32_t nchunks, uint64_t nwords, void* d_out) override {
         if (!nwords) return;
@@ -1087,61 +1116,84 @@ public:
         mphf_launch(keys, N, stream_);
         mphf_complete(stream_);
     }
-    void mphf_launch(const K* keys, uint64_t N, cudaStream_t stream_) {
+    uint32_t mphf_pad_ = 1;                   // level arrays padded to a multiple of this many equal slices (N-GPU slice-wise levels)
+    uint64_t mphf_slice_words(int lvl) const { return (mphf_dom_[lvl] / 64 + mphf_pad_ - 1) / mphf_pad_; }
+    // sizes (mphf::setup, BooPHF.h:1015-1041, double arithmetic on the host), buffers, cnt[0] = N
+    void mphf_setup(const K* keys, uint64_t N, uint32_t pad, cudaStream_t stream_) {
         mphf_n_ = N;
-        // ---- BooPHF levels (sizes: mphf::setup, BooPHF.h:1015-1041, double arithmetic on the host)
+        mphf_pad_ = pad ? pad : 1;
         mphf_built_ = false;
         nfinal_ = 0;
         final_.alloc(1);
-        if (N) {
-            const double gamma = 3.0;
-            const uint64_t hash_domain = (size_t)(ceil(double(N) * gamma));
-            const double proba = 1.0 - pow(((gamma * (double)N - 1) / (gamma * (double)N)), N - 1);
-            uint64_t off = 0;
-            for (int i = 0; i < MPHF_LEVELS; i++) {
-                uint64_t d = (((uint64_t)(hash_domain * pow(proba, i)) + 63) / 64) * 64;
-                if (d == 0) d = 64;
-                mphf_dom_[i] = d;
-                mphf_off_[i] = off;
-                off += d / 64;
-            }
-            mphf_bits_.alloc(off);
-            mphf_total_words_ = off;
-            mphf_bits_.zero(stream_);
-            st_.mphf_words = off;
-            DevBuf<unsigned long long>& coll = mphf_coll_;
-            DevBuf<K>&bufA = mphf_a_, &bufB = mphf_b_;
-            DevBuf<unsigned long long>& cnt = mphf_cnt_;      // cnt[l] = keys entering level l
-            coll.alloc(mphf_dom_[0] / 64);
-            bufA.alloc(N); bufB.alloc(N);
-            cnt.alloc(MPHF_LEVELS + 1);
-            cnt.zero(stream_);
-            const unsigned long long n0 = N;
-            MTG_CUDA(cudaMemcpyAsync(cnt.p, &n0, 8, cudaMemcpyHostToDevice, stream_));
-            // The first levels run on the device back to back (sizes stay on the device); once the expected number of
-            // survivors (collision probability 1 - exp(-1/gamma) = 0.28 per level) is a few thousand, the remaining levels are
-            // finished on the host from the survivor list: one synchronisation for the whole construction.
-            const K* cur = keys;
-            int glevels = 0;
-            double expect = (double)N;
-            for (int lvl = 0; lvl < MPHF_LEVELS - 1; lvl++) {
-                const uint64_t words = mphf_dom_[lvl] / 64;
-                const int grid = grid_for((uint64_t)expect + 1);
-                MTG_CUDA(cudaMemsetAsync(coll.p, 0, words * 8, stream_));
-                mphf_level_kernel<K><<<grid, 256, 0, stream_>>>(cur, cnt.p + lvl, lvl, mphf_dom_[lvl], mphf_seed_, mphf_bits_.p + mphf_off_[lvl], coll.p);
-                mphf_clear_kernel<<<grid_for(words), 256, 0, stream_>>>(mphf_bits_.p + mphf_off_[lvl], coll.p, words);
-                K* out = (cur == bufA.p) ? bufB.p : bufA.p;
-                mphf_compact_kernel<K><<<grid, 256, 0, stream_>>>(cur, cnt.p + lvl, lvl, mphf_dom_[lvl], mphf_seed_, mphf_bits_.p + mphf_off_[lvl], out, cnt.p + lvl + 1);
-                MTG_CUDA(cudaGetLastError());
-                st_.launches += 3;
-                cur = out;
-                glevels = lvl + 1;
-                expect *= 0.5;   // generous bound on the survivors (grid size only; the kernels read the true count)
-                if (N * pow(0.3, glevels) < 4096.0) break;
-            }
-            mphf_cur_ = cur;
-            mphf_glevels_ = glevels;
+        mphf_cur_ = keys;
+        mphf_glevels_ = 0;
+        if (!N) return;
+        const double gamma = 3.0;
+        const uint64_t hash_domain = (size_t)(ceil(double(N) * gamma));
+        const double proba = 1.0 - pow(((gamma * (double)N - 1) / (gamma * (double)N)), N - 1);
+        uint64_t off = 0, unpadded = 0;
+        for (int i = 0; i < MPHF_LEVELS; i++) {
+            uint64_t d = (((uint64_t)(hash_domain * pow(proba, i)) + 63) / 64) * 64;
+            if (d == 0) d = 64;
+            mphf_dom_[i] = d;
+            mphf_off_[i] = off;
+            off += mphf_slice_words(i) * mphf_pad_;
+            unpadded += d / 64;
         }
+        mphf_bits_.alloc(off);
+        mphf_total_words_ = off;
+        mphf_bits_.zero(stream_);
+        st_.mphf_words = unpadded;
+        mphf_coll_.alloc(mphf_slice_words(0) * mphf_pad_);
+        mphf_a_.alloc(N); mphf_b_.alloc(N);
+        mphf_cnt_.alloc(MPHF_LEVELS + 1);       // cnt[l] = keys entering level l
+        mphf_cnt_.zero(stream_);
+        const unsigned long long n0 = N;
+        MTG_CUDA(cudaMemcpyAsync(mphf_cnt_.p, &n0, 8, cudaMemcpyHostToDevice, stream_));
+    }
+    // one level on the device: every remaining key sets its bit (only inside this rank's slice when `sliced`), collided bits cleared
+    void mphf_level(int lvl, bool sliced, cudaStream_t stream_) {
+        const uint64_t words = mphf_slice_words(lvl) * mphf_pad_;
+        const int grid = grid_for((uint64_t)((double)mphf_n_ * pow(0.5, lvl)) + 1);   // generous bound on the survivors (the kernels read the true count)
+        const uint64_t sw = sliced ? mphf_slice_words(lvl) : 0;
+        unsigned long long* bits = mphf_bits_.p + mphf_off_[lvl];
+        if (sliced) {
+            MTG_CUDA(cudaMemsetAsync(mphf_coll_.p + (uint64_t)shard_ * sw, 0, sw * 8, stream_));
+            mphf_level_kernel<K><<<grid, 256, 0, stream_>>>(mphf_cur_, mphf_cnt_.p + lvl, lvl, mphf_dom_[lvl], mphf_seed_, bits, mphf_coll_.p, sw, shard_);
+            mphf_clear_kernel<<<grid_for(sw), 256, 0, stream_>>>(bits + (uint64_t)shard_ * sw, mphf_coll_.p + (uint64_t)shard_ * sw, sw);
+        } else {
+            MTG_CUDA(cudaMemsetAsync(mphf_coll_.p, 0, words * 8, stream_));
+            mphf_level_kernel<K><<<grid, 256, 0, stream_>>>(mphf_cur_, mphf_cnt_.p + lvl, lvl, mphf_dom_[lvl], mphf_seed_, bits, mphf_coll_.p, 0, 0);
+            mphf_clear_kernel<<<grid_for(words), 256, 0, stream_>>>(bits, mphf_coll_.p, words);
+        }
+        MTG_CUDA(cudaGetLastError());
+        st_.launches += 2;
+    }
+    // keys whose level bit was cleared go on to level lvl + 1 (needs the complete bit array of the level)
+    void mphf_compact(int lvl, cudaStream_t stream_) {
+        const int grid = grid_for((uint64_t)((double)mphf_n_ * pow(0.5, lvl)) + 1);
+        K* out = (mphf_cur_ == mphf_a_.p) ? mphf_b_.p : mphf_a_.p;
+        mphf_compact_kernel<K><<<grid, 256, 0, stream_>>>(mphf_cur_, mphf_cnt_.p + lvl, lvl, mphf_dom_[lvl], mphf_seed_, mphf_bits_.p + mphf_off_[lvl], out,
+                                                           mphf_cnt_.p + lvl + 1);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches++;
+        mphf_cur_ = out;
+        mphf_glevels_ = lvl + 1;
+    }
+    // The levels from `first` on run on the device back to back (sizes stay on the device); once the expected number of
+    // survivors (collision probability 1 - exp(-1/gamma) = 0.28 per level) is a few thousand, the remaining levels are
+    // finished on the host from the survivor list (mphf_complete): one synchronisation for the whole construction.
+    void mphf_levels(int first, cudaStream_t stream_) {
+        if (!mphf_n_) return;
+        for (int lvl = first; lvl < MPHF_LEVELS - 1; lvl++) {
+            if (lvl > 0 && (double)mphf_n_ * pow(0.3, lvl) < 4096.0) break;
+            mphf_level(lvl, false, stream_);
+            mphf_compact(lvl, stream_);
+        }
+    }
+    void mphf_launch(const K* keys, uint64_t N, cudaStream_t stream_) {
+        mphf_setup(keys, N, 1, stream_);
+        mphf_levels(0, stream_);
     }
     void mphf_complete(cudaStream_t stream_) {
         const uint64_t N = mphf_n_;
@@ -1323,7 +1375,13 @@ public:
             return b->nchar;
         }
         if (!mphf_built_) return 0;
-        if (host_buf) MTG_CUDA(cudaMemcpy(host_buf, mphf_bits_.p, st_.mphf_words * 8, cudaMemcpyDeviceToHost));
+        if (host_buf) {   // the levels concatenated without the slice padding of an N-GPU build
+            uint64_t o = 0;
+            for (int i = 0; i < MPHF_LEVELS; i++) {
+                MTG_CUDA(cudaMemcpy(host_buf + o, mphf_bits_.p + mphf_off_[i], mphf_dom_[i] / 8, cudaMemcpyDeviceToHost));
+                o += mphf_dom_[i] / 8;
+            }
+        }
         return st_.mphf_words * 8;
     }
 };

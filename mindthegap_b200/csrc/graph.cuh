@@ -331,9 +331,10 @@ public:
     //   2 share(critical) in B3 -> B4; 3 share(solid) in B2 and B4 -> local cFP list (returns its length, buffer 6)
     virtual uint64_t shard_cascade(int step, uint64_t ncrit_total) = 0;
     virtual void set_cfp(const void* d_all, uint64_t n) = 0;   // the gathered cFP set (sorted here)
+    virtual void shard_mphf_level(int level) = 0;               // optional: BooPHF level 0, then 1, slice-wise (buffer 8 all-gathered after each)
     virtual void shard_mphf_begin() = 0;                        // optional: BooPHF levels queued on a side stream (overlaps the next steps)
     virtual void shard_finish() = 0;                            // BooPHF levels from the gathered table; graph ready
-    // which: 0 table, 1 main Bloom, 2..4 B2..B4, 5 adjacency bytes, 6 local cFP list, 7 critical share; device pointer + bytes
+    // which: 0 table, 1 main Bloom, 2..4 B2..B4, 5 adjacency bytes, 6 local cFP list, 7 critical share, 8 slice-wise BooPHF level; device pointer + bytes
     virtual void buffer(int which, void** p, uint64_t* nbytes) = 0;
     // out[i] = OR over c of in[c * nwords + i] (64-bit words): the reduction of an OR-reduce-scatter
     virtual void or_chunks(const void* d_in, uint32_t nchunks, uint64_t nwords, void* d_out) = 0;

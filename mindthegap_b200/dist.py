@@ -110,6 +110,7 @@ class _Traced:
 
 
 class DistFind:
+    MPHF_SLICED_MIN = 256 << 20  # solid k-mers (all ranks) from which the first BooPHF levels are built slice-wise (level arrays beyond L2)
     OR_SMALL_WORDS = 1 << 17   # gathered size (64-bit words) up to which _or_reduce takes the single all-gather route
 
     def __init__(self, engine, device, group=None, scan_mode="auto", build_mode="sharded", comm=None, overlap_mphf=False):
@@ -383,6 +384,16 @@ class DistFind:
         self._sync()
         e.graph_set_cfp(cfp, sum(sizes))
         self._mark("cascade")
+        # BooPHF: levels 0 and 1 (92 % of the k-mers) slice-wise, each followed by an in-place all-gather of the level's slices;
+        # the rest is built by every rank. Below MPHF_SLICED_MIN k-mers the two extra exchanges cost more than they save.
+        if self.nb_solid >= self.MPHF_SLICED_MIN and hasattr(e, "graph_shard_mphf_level"):
+            for lvl in (0, 1):
+                self._sync()
+                e.graph_shard_mphf_level(lvl)
+                buf = e.graph_buffer(8)
+                if buf.numel():
+                    self._all_gather_ranges(buf)
+            self._sync()
         e.graph_shard_finish()
         self._mark("mphf")
 

@@ -70,7 +70,7 @@ class ThreadComm:
         self._done()
 
 
-def _run_ranks(world, case, build_mode, scan_mode, results, engines):
+def _run_ranks(world, case, build_mode, scan_mode, results, engines, sliced_mphf=True):
     import torch
 
     import mindthegap_b200 as m
@@ -89,6 +89,7 @@ def _run_ranks(world, case, build_mode, scan_mode, results, engines):
             engines[rank] = f
             d = DistFind(f, torch.device("cuda", 0), comm=ThreadComm(shared, rank), scan_mode=scan_mode, build_mode=build_mode)
             d.OR_SMALL_WORDS = 256     # both OR-reduce routes on these small inputs
+            d.MPHF_SLICED_MIN = 0 if sliced_mphf else 1 << 60   # BooPHF levels 0/1 slice-wise + all-gather, or fully replicated
             mine = recs[rank::world]
             d.push_reads(b"\n".join(s for _, s in mine) + b"\n")
             bk, vcf = d.find(refs)
@@ -104,15 +105,15 @@ def _run_ranks(world, case, build_mode, scan_mode, results, engines):
     assert not errors, errors
 
 
-@pytest.mark.parametrize("name,world,build_mode,scan_mode", [
-    ("full", 2, "sharded", "segments"), ("full", 3, "sharded", "chromosomes"), ("full_k63", 2, "sharded", "auto"),
-    ("syn_small_k31", 4, "sharded", "segments"), ("syn_small_k47_homo", 3, "sharded", "auto"), ("syn_tiny_k32", 2, "replicated", "segments"),
-    ("hetero_insert", 2, "sharded", "auto")])
-def test_n_rank_find_on_one_gpu(name, world, build_mode, scan_mode):
+@pytest.mark.parametrize("name,world,build_mode,scan_mode,sliced_mphf", [
+    ("full", 2, "sharded", "segments", True), ("full", 3, "sharded", "chromosomes", False), ("full_k63", 2, "sharded", "auto", True),
+    ("syn_small_k31", 4, "sharded", "segments", True), ("syn_small_k47_homo", 3, "sharded", "auto", True),
+    ("syn_tiny_k32", 2, "replicated", "segments", False), ("hetero_insert", 2, "sharded", "auto", True), ("hetero_insert", 5, "sharded", "auto", True)])
+def test_n_rank_find_on_one_gpu(name, world, build_mode, scan_mode, sliced_mphf):
     import mindthegap_b200 as m
     case = CASES[name]
     results, engines = [None] * world, [None] * world
-    _run_ranks(world, case, build_mode, scan_mode, results, engines)
+    _run_ranks(world, case, build_mode, scan_mode, results, engines, sliced_mphf)
     ebk, evcf, _ = expected(name)
     bk, vcf, nb_solid, threshold = results[0]
     assert bk == ebk and vcf == evcf
