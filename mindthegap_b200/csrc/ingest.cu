@@ -19,8 +19,7 @@
 namespace mtg {
 namespace {
 
-// a tile = IG_SUB sub-tiles of 256 threads x 16 bytes; the 4 loads of a thread are issued together (one DRAM latency per 16 KB),
-// the sub-tiles are then classified in order with the line count / last newline / output offset carried from one to the next
+// a tile = 16 KB = IG_SUB x 256 vectors of 16 bytes
 const int IG_THREADS = 256, IG_PER = 16, IG_SUBTILE = IG_THREADS * IG_PER, IG_SUB = 4, IG_TILE = IG_SUBTILE * IG_SUB, IG_WARPS = IG_THREADS / 32;
 
 // 16 text bytes of one thread as four little-endian words (byte j of the thread = byte j&3 of w[j>>2]); bytes past n read as 0
@@ -45,12 +44,8 @@ __device__ __forceinline__ uint32_t eq_mask16(const Bytes16& b, uint8_t c) {
     const uint32_t c4 = 0x01010101u * c;
     return eq_mask4(b.w0, c4) | (eq_mask4(b.w1, c4) << 4) | (eq_mask4(b.w2, c4) << 8) | (eq_mask4(b.w3, c4) << 12);
 }
-__device__ __forceinline__ uint8_t byte_at(const Bytes16& b, int j) {
-    const uint32_t w = j < 8 ? (j < 4 ? b.w0 : b.w1) : (j < 12 ? b.w2 : b.w3);
-    return (uint8_t)(w >> (8 * (j & 3)));
-}
 
-// block-wide exclusive prefix sum / prefix max over one value per thread (256 threads); *total = block sum
+// block-wide exclusive prefix sum over one value per thread (256 threads); *total = block sum
 __device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* s_warp, uint32_t* total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t inc = v;
@@ -67,25 +62,6 @@ __device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* s_warp,
     __syncthreads();
     if (total) *total = tot;
     return before + inc - v;
-}
-__device__ __forceinline__ long long block_excl_max(long long v, long long* s_warp, long long* total) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    long long inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const long long t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= d && t > inc) inc = t;
-    }
-    if (lane == 31) s_warp[w] = inc;
-    __syncthreads();
-    long long before = -1, tot = -1;
-#pragma unroll
-    for (int i = 0; i < IG_WARPS; i++) { if (i < w && s_warp[i] > before) before = s_warp[i]; if (s_warp[i] > tot) tot = s_warp[i]; }
-    if (total) *total = tot;
-    long long excl = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
-    if (lane == 0) excl = -1;
-    __syncthreads();
-    return excl > before ? excl : before;
 }
 
 __global__ void __launch_bounds__(IG_THREADS) ig_lines_kernel(const uint8_t* __restrict__ text, uint64_t n, int aligned, uint32_t* __restrict__ tile_nl,
@@ -202,6 +178,29 @@ __global__ void __launch_bounds__(1024) ig_scan2_kernel(unsigned long long* __re
 }
 
 // counters: [0] sequences, [1] position of the first irregular line start (atomicMin), [2] error code, [3] kept bytes
+//
+// The two compact passes give every thread 64 contiguous bytes (the tile is first copied to shared memory with coalesced 128-bit
+// loads, each thread's bytes at a 68-byte stride so that word and byte accesses are conflict-free): one newline mask, two block
+// scans and one walk over the thread's line segments per 64 bytes.
+const int IG_PT = 64, IG_STRIDE = IG_PT + 4;
+__device__ __forceinline__ uint32_t block_excl_max32(uint32_t v, uint32_t* s_warp) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d && t > inc) inc = t;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int i = 0; i < IG_WARPS; i++) if (i < w && s_warp[i] > before) before = s_warp[i];
+    uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+    if (lane == 0) excl = 0;
+    __syncthreads();
+    return excl > before ? excl : before;
+}
 template <int FMT, bool WRITE>
 __global__ void __launch_bounds__(IG_THREADS) ig_compact_kernel(const uint8_t* __restrict__ text, uint64_t n, int aligned,
                                                                 const unsigned long long* __restrict__ tile_line0,
@@ -211,88 +210,102 @@ __global__ void __launch_bounds__(IG_THREADS) ig_compact_kernel(const uint8_t* _
                                                                 const unsigned long long* __restrict__ blk_out0, uint8_t* __restrict__ out,
                                                                 unsigned long long* __restrict__ counters) {
     __shared__ uint32_t s_u32[IG_WARPS];
-    __shared__ long long s_i64[IG_WARPS];
+    __shared__ __align__(16) uint8_t s_in[IG_THREADS * IG_STRIDE];
     __shared__ uint8_t s_out[WRITE ? IG_TILE : 1];
-    const uint64_t tbase = (uint64_t)blockIdx.x * IG_TILE + (uint64_t)threadIdx.x * IG_PER;
-    Bytes16 bb[IG_SUB];
+    const int t = threadIdx.x;
+    const uint64_t tile_base = (uint64_t)blockIdx.x * IG_TILE;
 #pragma unroll
-    for (int sub = 0; sub < IG_SUB; sub++) bb[sub] = load16(text, tbase + (uint64_t)sub * IG_SUBTILE, n, aligned);
-    unsigned long long carry_line = tile_line0[blockIdx.x] + blk_line0[blockIdx.x >> 10];
-    long long carry_prev = tile_prev_nl[blockIdx.x];
-    { const long long bprev = blk_prev_nl[blockIdx.x >> 10]; if (bprev > carry_prev) carry_prev = bprev; }
-    uint32_t carry_out = 0, nseq = 0;
-#pragma unroll
-    for (int sub = 0; sub < IG_SUB; sub++) {
-        const Bytes16 b = bb[sub];
-        const uint64_t base = tbase + (uint64_t)sub * IG_SUBTILE;
-        const uint32_t nvalid = base < n ? (uint32_t)(n - base < IG_PER ? n - base : IG_PER) : 0u;
-        const uint32_t vm = (1u << nvalid) - 1u;
-        const uint32_t nl = eq_mask16(b, '\n');
-        uint32_t nl_total = 0;
-        const uint32_t nl_before = block_excl_sum(__popc(nl), s_u32, &nl_total);
-        long long last_total = -1;
-        long long prev = block_excl_max(nl ? (long long)(base + (31 - __clz(nl))) : -1, s_i64, &last_total);   // last '\n' before this thread
-        if (carry_prev > prev) prev = carry_prev;
-        const unsigned long long line = carry_line + nl_before;
-        // '\r' directly before '\n' is dropped (the byte after this thread's last one decides for byte 15)
-        const uint8_t after = (base + IG_PER < n) ? __ldg(text + base + IG_PER) : (uint8_t)0;
-        const uint32_t crdrop = eq_mask16(b, '\r') & ((nl >> 1) | (after == '\n' ? 0x8000u : 0u));
-        // Walk the (few) line segments of the 16 bytes instead of the bytes: the class of a byte only changes after a '\n'.
-        uint32_t keep = 0, rem = nl, s0 = 0;
-        bool at_start = nvalid && (long long)base == prev + 1;     // this thread's first byte starts a line
-        unsigned phase = (unsigned)(line & 3ull);                   // FASTQ: 0 header, 1 sequence, 2 '+', 3 quality
-        bool header = false;                                        // FASTA: the current line is a header
-        if (FMT == TEXT_FASTA && nvalid && !at_start) header = __ldg(text + (prev + 1)) == '>';
-        while (s0 < nvalid) {
-            const uint32_t e = rem ? (uint32_t)(__ffs(rem) - 1) : (uint32_t)IG_PER;       // the segment's '\n', or none
-            const uint32_t body = ((1u << e) - 1u) & ~((1u << s0) - 1u);                  // [s0, e)
-            const uint32_t nlbit = e < IG_PER ? 1u << e : 0u;
-            if (FMT == TEXT_FASTQ) {
-                if (at_start) {
-                    const uint8_t c = byte_at(b, (int)s0);
-                    if ((phase == 0 && c != '@') || (phase == 2 && c != '+')) { atomicMin(counters + 1, (unsigned long long)(base + s0)); counters[2] = 1; }
-                    if (phase == 1) nseq++;
-                }
-                if (phase == 1) keep |= body | nlbit;             // the sequence line with its '\n' (the separator)
-                phase = (phase + 1) & 3u;
-            } else {
-                if (at_start) {
-                    const uint8_t c = byte_at(b, (int)s0);
-                    header = c == '>';
-                    if (c == '@' || c == '+') { atomicMin(counters + 1, (unsigned long long)(base + s0)); counters[2] = 2; }
-                    if (header) nseq++;
-                }
-                keep |= header ? nlbit : body;                     // header line -> one separator; sequence lines joined
-            }
-            if (e >= IG_PER) break;
-            rem &= rem - 1;
-            s0 = e + 1;
-            at_start = true;
-        }
-        keep &= vm & ~crdrop;
-        uint32_t total = 0;
-        const uint32_t off = block_excl_sum(__popc(keep), s_u32, &total);
-        if (WRITE) {
-            uint32_t o = carry_out + off, k2 = keep;              // kept bytes staged in shared memory, then written as whole sectors
-            while (k2) {
-                const int j = __ffs(k2) - 1;
-                s_out[o++] = byte_at(b, j);
-                k2 &= k2 - 1;
-            }
-        }
-        carry_out += total;
-        carry_line += nl_total;
-        if (last_total > carry_prev) carry_prev = last_total;
+    for (int i = 0; i < IG_SUB; i++) {     // vector v covers bytes [16 v, 16 v + 16) of the tile: thread v >> 2, quarter v & 3
+        const int v = i * IG_THREADS + t;
+        const Bytes16 b = load16(text, tile_base + 16ull * v, n, aligned);
+        uint32_t* d = reinterpret_cast<uint32_t*>(s_in + (v >> 2) * IG_STRIDE + (v & 3) * 16);
+        d[0] = b.w0; d[1] = b.w1; d[2] = b.w2; d[3] = b.w3;
     }
+    __syncthreads();
+    const uint8_t* mine = s_in + t * IG_STRIDE;
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(mine);
+    uint64_t nl = 0;
+#pragma unroll
+    for (int q = 0; q < IG_PT / 4; q++) nl |= (uint64_t)eq_mask4(mw[q], 0x0A0A0A0Au) << (4 * q);   // bytes past n are 0
+    const uint64_t base = tile_base + (uint64_t)t * IG_PT;
+    const uint32_t nvalid = base < n ? (uint32_t)(n - base < IG_PT ? n - base : IG_PT) : 0u;
+    const uint64_t vm = nvalid >= 64 ? ~0ull : ((1ull << nvalid) - 1ull);
+    const uint32_t nl_before = block_excl_sum(__popcll(nl), s_u32, nullptr);
+    unsigned long long line = tile_line0[blockIdx.x] + blk_line0[blockIdx.x >> 10] + nl_before;
+    const uint8_t prevbyte = t ? s_in[(t - 1) * IG_STRIDE + IG_PT - 1] : (tile_base ? __ldg(text + tile_base - 1) : (uint8_t)'\n');
+    bool at_start = nvalid && prevbyte == '\n';               // this thread's first byte starts a line
+    bool header = false;                                        // FASTA: the current line is a header
+    if (FMT == TEXT_FASTA) {
+        // first byte of the line in progress: after the last '\n' before this thread -- in this tile (shared memory) or before it
+        const uint32_t first_rel = block_excl_max32(nl ? (uint32_t)(t * IG_PT + 64 - __clzll(nl)) : 0u, s_u32);   // index in the tile, 0 = none
+        if (nvalid && !at_start) {
+            if (first_rel) header = s_in[(first_rel >> 6) * IG_STRIDE + (first_rel & 63)] == '>';
+            else {
+                long long prev = tile_prev_nl[blockIdx.x];
+                const long long bprev = blk_prev_nl[blockIdx.x >> 10];
+                if (bprev > prev) prev = bprev;
+                header = __ldg(text + (prev + 1)) == '>';
+            }
+        }
+    }
+    unsigned phase = (unsigned)(line & 3ull);                   // FASTQ: 0 header, 1 sequence, 2 '+', 3 quality
+    // Walk the (few) line segments of the 64 bytes instead of the bytes: the class of a byte only changes after a '\n'.
+    uint64_t keep = 0, rem = nl, crdrop = 0;
+    uint32_t nseq = 0, s0 = 0;
+    while (s0 < nvalid) {
+        const uint32_t e = rem ? (uint32_t)(__ffsll((long long)rem) - 1) : (uint32_t)IG_PT;   // the segment's '\n', or none
+        const uint64_t below_e = e >= 64 ? ~0ull : ((1ull << e) - 1ull);
+        const uint64_t body = below_e & ~((1ull << s0) - 1ull);                              // [s0, e)
+        const uint64_t nlbit = e < 64 ? 1ull << e : 0ull;
+        if (FMT == TEXT_FASTQ) {
+            if (at_start) {
+                const uint8_t c = mine[s0];
+                if ((phase == 0 && c != '@') || (phase == 2 && c != '+')) { atomicMin(counters + 1, (unsigned long long)(base + s0)); counters[2] = 1; }
+                if (phase == 1) nseq++;
+            }
+            if (phase == 1) keep |= body | nlbit;               // the sequence line with its '\n' (the separator)
+            phase = (phase + 1) & 3u;
+        } else {
+            if (at_start) {
+                const uint8_t c = mine[s0];
+                header = c == '>';
+                if (c == '@' || c == '+') { atomicMin(counters + 1, (unsigned long long)(base + s0)); counters[2] = 2; }
+                if (header) nseq++;
+            }
+            keep |= header ? nlbit : body;                       // header line -> one separator; sequence lines joined
+        }
+        if (e >= 64) break;
+        if (e > s0 && mine[e - 1] == '\r') crdrop |= 1ull << (e - 1);   // '\r' directly before '\n' is dropped
+        rem &= rem - 1;
+        s0 = e + 1;
+        at_start = true;
+    }
+    if (nvalid == IG_PT && mine[IG_PT - 1] == '\r') {            // ... also when the '\n' is the next thread's first byte
+        const uint8_t nx = t + 1 < IG_THREADS ? s_in[(t + 1) * IG_STRIDE] : (base + IG_PT < n ? __ldg(text + base + IG_PT) : (uint8_t)0);
+        if (nx == '\n') crdrop |= 1ull << (IG_PT - 1);
+    }
+    keep &= vm & ~crdrop;
+    uint32_t total = 0;
+    const uint32_t off = block_excl_sum(__popcll(keep), s_u32, &total);
     if (!WRITE) {
-        if (threadIdx.x == 0) tile_kept[blockIdx.x] = carry_out;
+        if (t == 0) tile_kept[blockIdx.x] = total;
         uint32_t nseq_blk = 0;
         block_excl_sum(nseq, s_u32, &nseq_blk);                  // one atomic per tile, not per sequence
-        if (threadIdx.x == 0 && nseq_blk) atomicAdd(counters, (unsigned long long)nseq_blk);
+        if (t == 0 && nseq_blk) atomicAdd(counters, (unsigned long long)nseq_blk);
     } else {
+        uint32_t o = off;                                         // kept runs staged in shared memory, then written as whole sectors
+        uint64_t k2 = keep;
+        while (k2) {
+            const int j = __ffsll((long long)k2) - 1;
+            const uint64_t inv = ~(k2 >> j);
+            const int len = inv ? __ffsll((long long)inv) - 1 : 64 - j;
+            for (int q = 0; q < len; q++) s_out[o + q] = mine[j + q];
+            o += len;
+            k2 = (j + len >= 64) ? 0ull : (k2 & ~(((1ull << len) - 1ull) << j));
+        }
         __syncthreads();
         uint8_t* dst = out + tile_out0[blockIdx.x] + blk_out0[blockIdx.x >> 10];
-        for (uint32_t q = threadIdx.x; q < carry_out; q += IG_THREADS) dst[q] = s_out[q];
+        for (uint32_t q = t; q < total; q += IG_THREADS) dst[q] = s_out[q];
     }
 }
 
