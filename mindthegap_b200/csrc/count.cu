@@ -796,7 +796,8 @@ public:
     void push_host(const char* bases, uint64_t n) override {
         if (!n) return;
         if (staging_.n < n + 64) staging_.alloc(n + 64);
-        const uint64_t CH = std::max<uint64_t>(48ull << 20, n / 32);   // at most ~32 batches
+        uint64_t CH = std::max<uint64_t>(48ull << 20, n / 32);   // at most ~32 batches
+        if (const char* e = getenv("MTG_PUSH_CHUNK")) CH = std::max<uint64_t>((uint64_t)atoll(e), 64);   // tests: force many chunks
         std::vector<uint64_t> cuts(1, 0);
         while (n > 2 * CH && cuts.back() < n) {
             uint64_t e = std::min<uint64_t>(n, cuts.back() + CH);

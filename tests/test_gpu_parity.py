@@ -541,3 +541,75 @@ def test_export_dsk_partitions(name, nparts):
         sizes = np.diff(offs.astype(np.int64))
         assert sizes.max() <= 1.5 * sizes.mean() + 64
     f.close()
+
+
+def _random_text(rng, fmt, nrec, crlf):
+    """Random FASTA (multi-line, random widths) or 4-line FASTQ with random read lengths: line ends fall on every offset of
+    the parser's 64-byte thread ranges and 16 KB tiles."""
+    eol = b"\r\n" if crlf else b"\n"
+    out = []
+    for i in range(nrec):
+        L = int(rng.integers(0, 700)) if fmt == 1 else int(rng.integers(1, 300))
+        seq = rng.choice(np.frombuffer(b"ACGTacgtN", dtype=np.uint8), size=L, p=[.24, .24, .24, .24, .01, .01, .005, .005, .01]).tobytes()
+        name = b"r%d" % i + b" x" * int(rng.integers(0, 40))
+        if fmt == 1:
+            out.append(b">" + name + eol)
+            w = int(rng.integers(1, 130))
+            for o in range(0, L, w):
+                out.append(seq[o:o + w] + eol)
+        else:
+            qual = bytes(rng.integers(33, 74, size=L, dtype=np.uint8))   # includes '@' and '+' as first quality characters
+            out.append(b"@" + name + eol + seq + eol + b"+" + (name if i % 3 == 0 else b"") + eol + qual + eol)
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("fmt", [1, 2])
+def test_text_ingest_random_layouts_equal_host_parser(tmp_path, fmt):
+    """Property test: for random record/line lengths (line ends at every offset of a thread's 64 bytes and of a 16 KB tile,
+    CRLF or LF, one long single-line sequence) the GPU parser yields the same k-mer multiset as the host parser."""
+    rng = np.random.default_rng(100 + fmt)
+    for trial in range(6):
+        text = _random_text(rng, fmt, 300 + 200 * trial, crlf=trial % 2 == 1)
+        if fmt == 1 and trial == 2:     # a sequence on one line, longer than several tiles
+            text += b">long\n" + rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=70000).tobytes() + b"\n>tail\nACGTACGTACGTAC"
+        path = str(tmp_path / ("t%d.txt" % trial))
+        open(path, "wb").write(text)
+        stream, recs = _stream(path)
+        a = _finder(11, ["-abundance-min", "1"])
+        a.push_reads(stream)
+        ref = _solid_of(a)
+        b = _finder(11, ["-abundance-min", "1"])
+        b.push_reads_text(text, fmt)
+        _same_solid(ref, _solid_of(b))
+        assert int(b.stats()["ingest.nb_sequences"]) == len(recs)
+        a.close(); b.close()
+
+
+def test_text_ingest_empty_and_header_only():
+    f = _finder(21)
+    f.push_reads_text(b"")
+    f.push_reads_text(b">only a header")
+    f.push_reads_text(b">h\n")
+    f.push_reads_text(b"@r\nACGT\n+\nIII")          # last line without newline, read shorter than k
+    f.finish_count()
+    assert f.nb_solid == 0
+    f.close()
+
+
+def test_push_reads_chunked_copy_equals_one_copy(monkeypatch):
+    """mtg_push_reads cuts a large host buffer at separators and overlaps the chunk copies with the kernels: same result as one
+    copy, also when a sequence is longer than a chunk (forced 10 kB chunks; the default only chunks above 96 MB)."""
+    case = CASES["syn_small_k31"]
+    reads, _ = case_paths(case)
+    stream, _ = _stream(reads)
+    rng = np.random.default_rng(3)
+    stream += rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=50000).tobytes() + b"\n" + stream[:200000]
+    a = _finder(case)
+    a.push_reads(stream)
+    ref = _solid_of(a)
+    monkeypatch.setenv("MTG_PUSH_CHUNK", "10000")
+    b = _finder(case)
+    b.push_reads(stream)
+    monkeypatch.delenv("MTG_PUSH_CHUNK")
+    _same_solid(ref, _solid_of(b))
+    a.close(); b.close()
