@@ -368,6 +368,12 @@ class Finder:
     def degrees(self, lo, hi=None):
         return self._batch(self.L.mtg_degree_batch, lo, hi)
 
+    def context_filter(self, breakpoints_text, ref_records, threshold=0.80):
+        """Connectivity post-filter of the reference's scripts/python3/Context_genome_WG.py on this engine's graph:
+        (filtered .breakpoints text, kept, total). See mindthegap_b200/context_filter.py."""
+        from .context_filter import context_filter
+        return context_filter(self.degrees, self.params.kmer_size, breakpoints_text, ref_records, threshold)
+
     def ref_repeat(self, lo, hi=None):
         return self._batch(self.L.mtg_ref_repeat_batch, lo, hi)
 

@@ -161,6 +161,15 @@ void mtgo_graph_info(void* p, uint64_t* out8) {
         out8[4] = g->g2.bloom4.reduced_tai; out8[5] = g->g2.cfp_set.size(); out8[6] = g->rb2.nb_repeated; out8[7] = g->rb2.bloom.reduced_tai;
     }
 }
+// forward k-mers in -> indegree | outdegree << 4 of the node in the strand of the given k-mer (Graph::indegree / outdegree through
+// contains(), G/debruijn/impl/Graph.cpp:1121-1143, 1466-1532), whether or not the node itself is in the graph
+void mtgo_graph_degrees(void* p, const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) {
+    GraphHandle* g = (GraphHandle*)p;
+    for (uint64_t i = 0; i < n; i++) {
+        if (g->k <= 31) out[i] = (uint8_t)(g->g1.indegree(lo[i]) | (g->g1.outdegree(lo[i]) << 4));
+        else { u128 x = mk<u128>(lo[i], hi[i]); out[i] = (uint8_t)(g->g2.indegree(x) | (g->g2.outdegree(x) << 4)); }
+    }
+}
 // branching nodes: returns the count; topo25 [in][out]; lo/hi (may be NULL) receive the sorted collection
 uint64_t mtgo_graph_branching(void* p, uint64_t* topo25, uint64_t* lo, uint64_t* hi) {
     GraphHandle* g = (GraphHandle*)p;

@@ -52,6 +52,7 @@ def load():
     L.mtgo_graph_bits.restype = C.c_uint64
     L.mtgo_graph_bits.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.mtgo_graph_info.argtypes = [C.c_void_p, u64p]
+    L.mtgo_graph_degrees.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, u8p]
     L.mtgo_graph_branching.restype = C.c_uint64
     L.mtgo_graph_branching.argtypes = [C.c_void_p, u64p, C.c_void_p, C.c_void_p]
     L.mtgo_graph_set_reference.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int]
@@ -121,6 +122,14 @@ class Graph:
         self.L.mtgo_graph_info(self.h, o)
         return dict(bloom=int(o[0]), nb_critical=int(o[1]), bloom2=int(o[2]), bloom3=int(o[3]), bloom4=int(o[4]),
                     cfp_set=int(o[5]), ref_repeated=int(o[6]), refbloom=int(o[7]))
+
+    def degrees(self, lo, hi=None):
+        """indegree | outdegree << 4 of forward k-mers (same contract as Finder.degrees)."""
+        lo = np.ascontiguousarray(lo, dtype=np.uint64)
+        hi = np.zeros(len(lo), dtype=np.uint64) if hi is None else np.ascontiguousarray(hi, dtype=np.uint64)
+        out = np.zeros(max(len(lo), 1), dtype=np.uint8)
+        self.L.mtgo_graph_degrees(self.h, lo, hi, len(lo), out)
+        return out[:len(lo)]
 
     def branching(self):
         """(nb_branching, topology[in][out], lo, hi) -- BranchingAlgorithm restated (oracle/graph_oracle.hpp)."""

@@ -613,3 +613,33 @@ def test_push_reads_chunked_copy_equals_one_copy(monkeypatch):
     monkeypatch.delenv("MTG_PUSH_CHUNK")
     _same_solid(ref, _solid_of(b))
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", ["full", "syn_small_k31", "syn_tiny_k63"])
+def test_context_filter_engine_degrees_equal_oracle(name):
+    """Connectivity post-filter (scripts/python3/Context_genome_WG.py): the same filter fed by the engine's degrees and by the
+    oracle graph's degrees keeps the same breakpoints; the degrees of all window k-mers agree one by one."""
+    from mindthegap_b200.context_filter import context_filter
+    case = CASES[name]
+    reads, ref = case_paths(case)
+    stream, _ = _stream(reads)
+    rstream, rrecs = _stream(ref)
+    f = _finder(case)
+    bk, _ = f.find(stream, rrecs)
+    lo, hi, _ab = f.export_solid()
+    g = oracle_py.Graph(lo, hi, case["k"])
+    refs = [(n, s.decode()) for n, s in rrecs]
+    seen = []
+
+    def engine_degrees(qlo, qhi):
+        d = f.degrees(qlo, qhi)
+        seen.append((qlo.copy(), None if qhi is None else qhi.copy(), d.copy()))
+        return d
+    for thr in (0.8, 0.6):
+        got = context_filter(engine_degrees, case["k"], bk, refs, thr)
+        want = context_filter(g.degrees, case["k"], bk, refs, thr)
+        assert got == want and got[2] == len(bk.splitlines()) // 4
+        assert f.context_filter(bk, refs, thr) == got
+    qlo, qhi, d = seen[0]
+    assert len(qlo) > 0 and (g.degrees(qlo, qhi) == d).all()
+    g.close(); f.close()
