@@ -176,8 +176,11 @@ int main(int argc, char** argv) {
     printf("    Input data\n        Reads                    : %s\n        Reference                : %s\n", in.c_str(), ref.c_str());
     printf("    Graph\n        kmer-size                : %d\n", p.kmer_size);
     if (mtg_get_cutoff_auto(g) >= 0) printf("        abundance_min (auto inferred) : %d\n", mtg_get_cutoff_auto(g));
-    printf("        abundance_min (used)     : %d\n        abundance_max            : %lld\n        nb_solid_kmers           : %llu\n",
-           mtg_get_threshold(g), (long long)p.abundance_max, (unsigned long long)mtg_get_nb_solid(g));
+    uint64_t nb_branching = 0;   // "nb_branching_nodes" (src/Finder.cpp:467), from the adjacency bytes of the exact table
+    check(mtg_graph_branching(g, &nb_branching, nullptr, nullptr, nullptr, nullptr, 0));
+    printf("        abundance_min (used)     : %d\n        abundance_max            : %lld\n        nb_solid_kmers           : %llu\n"
+           "        nb_branching_nodes       : %llu\n",
+           mtg_get_threshold(g), (long long)p.abundance_max, (unsigned long long)mtg_get_nb_solid(g), (unsigned long long)nb_branching);
     printf("    Breakpoint detection options\n        max_repeat               : %d\n        hetero_max_occ           : %d\n"
            "        homo_insertions          : %s\n        hete_insertions          : %s\n        snp                      : %s\n"
            "        deletion                 : %s\n",

@@ -311,6 +311,14 @@ def test_cpp_cli_mtg_find(tmp_path, name):
     assert "".join(l for l in vcf_lines if not l.startswith("#")) == evcf
     if name == "full":
         assert "abundance_min (auto inferred) : 7" in r.stdout and "nb_solid_kmers           : 7419" in r.stdout
+        assert "nb_branching_nodes       : 36" in r.stdout       # the reference's gold_find.output
+        # every counter of the reference's Results block (test/full_test/gold_find.output)
+        import re
+        gold = open(os.path.join(GOLD, "full", "gold_find.output")).read()
+        for key in ("homozygous", "heterozygous", "deletions", "Homozygous insertions 1-2 bp size", "Heterozygous insertions 1-2 bp size", "SNPs"):
+            want = re.search(r"^\s*%s\s*:\s*(\d+)" % re.escape(key), gold, re.M).group(1)
+            got = re.search(r"^\s*%s\s*:\s*(\d+)" % re.escape(key), r.stdout, re.M).group(1)
+            assert got == want, key
     # error behaviour of the CLI (src/main.cpp:96-102)
     r = subprocess.run([exe, "find", "-in", reads], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "EXCEPTION: ERROR: option -ref is mandatory" in r.stdout
