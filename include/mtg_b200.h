@@ -76,7 +76,7 @@ int mtg_push_reads_text_device(mtg_ctx* ctx, const void* d_text, uint64_t nbytes
 uint64_t mtg_text_record_cut(const char* text, uint64_t nbytes, int32_t format, int32_t final);
 /* Bank::open on a comma separated list of FASTA/FASTQ files, plain or gzip (G/bank/impl/Bank.cpp:49-52, README.md:166):
  * file bytes are staged in pinned memory in chunks cut at record starts and parsed on the GPU (mtg_push_reads_text).
- * With MTG_F_HOST_PARSE in params.flags the kseq-style host reader is used instead (plain text; any layout). */
+ * With MTG_F_HOST_PARSE in params.flags the kseq-style host reader is used instead (plain or gzip; any layout). */
 int mtg_count_files(mtg_ctx* ctx, const char* uri);
 /* Ends the counting: histogram, auto cut-off (Histogram::compute_threshold, G/tools/misc/impl/Histogram.cpp:59-189),
  * solidity filter (CountProcessorSolidity.hpp:182-185); then builds the membership structures of

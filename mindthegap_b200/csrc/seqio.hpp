@@ -1,12 +1,14 @@
 // mtg-b200 host input: FASTA/FASTQ reader in the style of kseq, mirroring the behaviour of gatb's BankFasta
 // (thirdparty/gatb-core/gatb-core/src/gatb/bank/impl/BankFasta.cpp:485-574): '>' or '@' headers, multi-line sequences,
-// FASTQ quality skipped by length; comma separated file lists (README.md:166). Plain text only.
+// FASTQ quality skipped by length; comma separated file lists (README.md:166). Plain or gzip files (zlib reads both, like
+// gatb's buffered_file_t over gzFile, BankFasta.cpp:52-60).
 // getCommentShort = header up to the first whitespace (gatb/bank/api/Sequence.hpp:88).
 #pragma once
 #include <errno.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <zlib.h>
 
 #include <functional>
 #include <stdexcept>
@@ -19,7 +21,7 @@ namespace mtg {
 struct SeqRecord { std::string name, seq; };
 
 class SeqReader {
-    FILE* f_ = nullptr;
+    gzFile f_ = nullptr;
     std::vector<char> buf_;
     size_t b_ = 0, e_ = 0;
     bool eof_ = false;
@@ -27,7 +29,9 @@ class SeqReader {
     int getc_() {
         if (b_ >= e_) {
             if (eof_) return -1;
-            e_ = fread(buf_.data(), 1, buf_.size(), f_);
+            const int r = gzread(f_, buf_.data(), (unsigned)buf_.size());
+            if (r < 0) throw std::runtime_error("read error in a sequence file");
+            e_ = (size_t)r;
             b_ = 0;
             if (e_ < buf_.size()) eof_ = true;
             if (e_ == 0) return -1;
@@ -53,10 +57,11 @@ class SeqReader {
 
 public:
     explicit SeqReader(const std::string& path) : buf_(1 << 22) {
-        f_ = fopen(path.c_str(), "rb");
+        f_ = gzopen(path.c_str(), "rb");
         if (!f_) throw std::runtime_error("Cannot open file " + path);
+        gzbuffer(f_, 1u << 20);
     }
-    ~SeqReader() { if (f_) fclose(f_); }
+    ~SeqReader() { if (f_) gzclose(f_); }
     bool next(SeqRecord& r) {
         int c;
         if (last_ == 0) {

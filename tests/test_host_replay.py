@@ -18,7 +18,7 @@ def replay_check():
     deps = [src, os.path.join(ROOT, "mindthegap_b200", "csrc", "replay.hpp"), os.path.join(ROOT, "mindthegap_b200", "csrc", "seqio.hpp")] + [
         os.path.join(ROOT, "oracle", f) for f in ("scan_oracle.hpp", "graph_oracle.hpp", "kmer_oracle.hpp")]
     if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", EXE, src], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", EXE, src, "-lz"], check=True)
     return EXE
 
 
@@ -98,3 +98,29 @@ def test_bed_replay_equals_oracle(replay_check, oracle_bin, tmp_path, bed_name):
     assert bk == open(out + ".breakpoints").read()
     assert vcf == "".join(l for l in open(out + ".othervariants.vcf") if not l.startswith("#"))
     assert len(bk) > 0
+
+
+def test_host_reader_plain_and_gzip(tmp_path):
+    """The host reader behind `mtg_find -ref` / MTG_F_HOST_PARSE (seqio.hpp): FASTA + FASTQ, multi-line, gzip or plain, comma list --
+    the same records as the tests' own reader (gatb's BankFasta reads gzip through zlib, BankFasta.cpp:52-60)."""
+    import gzip
+    from tests import oracle_py
+    exe = os.path.join(os.path.dirname(EXE), "seqio_check")
+    src = os.path.join(ROOT, "tests", "host", "seqio_check.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, src, "-lz"], check=True)
+    case = CASES["full"]
+    reads, ref = case_paths(case)
+    r1, r2 = reads.split(",")
+    gz = str(tmp_path / "r2.fastq.gz")
+    with gzip.open(gz, "wb") as g:
+        g.write(open(r2, "rb").read())
+    refgz = str(tmp_path / "ref.fa.gz")
+    with gzip.open(refgz, "wb") as g:
+        g.write(open(ref, "rb").read())
+    for uri, plain in ((",".join([r1, gz, refgz]), ",".join([r1, r2, ref])), (ref, ref)):
+        out = subprocess.run([exe, uri], stdout=subprocess.PIPE, text=True, check=True).stdout.splitlines()
+        want = ["%s\t%s" % (n, s.decode()) for n, s in oracle_py.read_sequences(plain)]
+        assert out == want
+    r = subprocess.run([exe, str(tmp_path / "missing.fa")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Cannot open file" in r.stderr
