@@ -397,6 +397,14 @@ def own_arm(args):
                 "random_128B_gather_peak_gbs": gather_peak,
                 "probe_frac_of_gather_peak": (kernels[4]["achieved_gbs"] / gather_peak) if gather_peak > 0 and kernels[4]["achieved_gbs"] else None}
 
+    # ---- size-independent property at FULL size (the oracle only covers the bounded sample below): the planted variants are found
+    truth_check = None
+    if world == 1:
+        import synth
+        truth_check = synth.truth_recall(out_res[0], out_res[1], wl["truth"], [n for n, _ in wl["refs"]])
+        if K <= 31 and truth_check["INS"]["planted"] and truth_check["INS"]["recall"] < 0.8:
+            raise SystemExit("bench.py: only %d of %d planted insertions have a breakpoint" % (truth_check["INS"]["recovered"], truth_check["INS"]["planted"]))
+
     # ---- text ingest: the same reads as 4-line FASTQ text, parsed on the GPU (csrc/ingest.cu). Reported beside
     # the find step, not inside it: the bench line's host buffers are already-parsed bases, like the CPU arm whose parse time is excluded.
     ingest = None
@@ -486,6 +494,8 @@ def own_arm(args):
                        "breakpoint_records": len(out_res[0].splitlines()) // 4, "vcf_records": len(out_res[1].splitlines())}}
     if ingest is not None:
         line["ingest"] = ingest
+    if truth_check is not None:
+        line["truth_check"] = truth_check
     emit(line)
     if world > 1:
         dist.destroy_process_group()

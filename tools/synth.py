@@ -200,3 +200,50 @@ if __name__ == "__main__":
     ap.add_argument("--seed", type=int, default=20240)
     a = ap.parse_args()
     print(make_dataset(a.outdir, CONFIGS[a.config], a.seed))
+
+
+def truth_recall(bk_text, vcf_text, truth, chrom_names, tol=12):
+    """Size-independent check of `find` outputs against the planted variants: which planted insertions have a breakpoint,
+    which planted SNPs / deletions have a VCF record, within `tol` bases. truth: per chromosome [(kind, ancestral position,
+    length)] in position order (build()); reference coordinate = ancestral position minus the inserted bases before it
+    (insertions are absent from the reference; deletions and SNPs keep its length). Returns a dict of counts and ratios."""
+    import bisect
+    import re
+    found = {"INS": {}, "SNP": {}, "DEL": {}}
+    for m in re.finditer(r"^>bkpt\d+_(.+)_pos_(\d+)_fuzzy_\d+_(HOM|HET)\s+(?:REPEATED )?\s*left_kmer", bk_text, re.M):
+        found["INS"].setdefault(m.group(1), []).append(int(m.group(2)))
+    for line in vcf_text.splitlines():
+        f = line.split("\t")
+        if len(f) > 7 and not line.startswith("#"):
+            t = "SNP" if "TYPE=SNP" in f[7] else "DEL" if "TYPE=DEL" in f[7] else None
+            if t and not (t == "DEL" and len(f[3]) - len(f[4]) < 10):   # planted deletions are >= 10 bp
+                found[t].setdefault(f[0], []).append(int(f[1]))
+    for d in found.values():
+        for v in d.values():
+            v.sort()
+    planted = {"INS": 0, "SNP": 0, "DEL": 0}
+    hit = {"INS": 0, "SNP": 0, "DEL": 0}
+    expected = {"INS": {}, "SNP": {}, "DEL": {}}
+    for name, tr in zip(chrom_names, truth):
+        shift = 0
+        for kind, p, L in tr:
+            t = "INS" if kind in ("HOM", "HET") else kind
+            x = p - shift + (1 if t == "SNP" else 0)
+            expected[t].setdefault(name, []).append(x)
+            if t == "INS":
+                shift += L
+    def near(sorted_list, x):
+        i = bisect.bisect_left(sorted_list, x - tol)
+        return i < len(sorted_list) and sorted_list[i] <= x + tol
+    out = {}
+    for t in ("INS", "SNP", "DEL"):
+        nfound = sum(len(v) for v in found[t].values())
+        good = 0
+        for name, xs in expected[t].items():
+            planted[t] += len(xs)
+            hit[t] += sum(near(found[t].get(name, []), x) for x in xs)
+            xs_sorted = sorted(xs)
+            good += sum(near(xs_sorted, y) for y in found[t].get(name, []))
+        out[t] = {"planted": planted[t], "recovered": hit[t], "reported": nfound, "reported_at_planted_site": good,
+                  "recall": hit[t] / planted[t] if planted[t] else None, "precision": good / nfound if nfound else None}
+    return out
