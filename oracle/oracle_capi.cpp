@@ -1,5 +1,6 @@
 // ORACLE (test infrastructure, NOT product code): C entry points for ctypes (tests/, bench.py cpu_baseline only).
 #include "count_mt.hpp"
+#include "graph_mt.hpp"
 #include "scan_oracle.hpp"
 
 using namespace mtgo;
@@ -115,6 +116,14 @@ void* mtgo_graph_new(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k) 
     g->k = k;
     if (k <= 31) { std::vector<uint64_t> s(lo, lo + n); std::sort(s.begin(), s.end()); g->g1.build(s, k); }
     else { std::vector<u128> s(n); for (uint64_t i = 0; i < n; i++) s[i] = mk<u128>(lo[i], hi[i]); std::sort(s.begin(), s.end()); g->g2.build(s, k); }
+    return g;
+}
+// the same structures built with nthreads workers (graph_mt.hpp: the CPU baseline's stand-in for the reference's -nb-cores)
+void* mtgo_graph_new_threads(const uint64_t* lo, const uint64_t* hi, uint64_t n, int k, int nthreads) {
+    GraphHandle* g = new GraphHandle();
+    g->k = k;
+    if (k <= 31) { std::vector<uint64_t> s(lo, lo + n); std::sort(s.begin(), s.end()); graph_build_mt(g->g1, s, k, nthreads); }
+    else { std::vector<u128> s(n); for (uint64_t i = 0; i < n; i++) s[i] = mk<u128>(lo[i], hi[i]); std::sort(s.begin(), s.end()); graph_build_mt(g->g2, s, k, nthreads); }
     return g;
 }
 void mtgo_graph_free(void* p) { delete (GraphHandle*)p; }

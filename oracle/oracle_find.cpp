@@ -5,6 +5,7 @@
 #include <map>
 
 #include "count_mt.hpp"
+#include "graph_mt.hpp"
 #include "scan_oracle.hpp"
 
 using namespace mtgo;
@@ -68,7 +69,7 @@ template <class K> static int run(const Args& a) {
         return 0;
     }
     GraphOracle<K> g;
-    g.build(solid, k);
+    graph_build_mt(g, solid, k, a.nb_cores);   // -nb-cores > 1: threaded like the reference's Bloom / debloom / BooPHF stages
     double t2 = now_s();
     std::vector<SeqRecord> ref;
     if (!load_bank(a.ref, ref)) { fprintf(stderr, "cannot read %s\n", a.ref.c_str()); return 1; }

@@ -47,6 +47,8 @@ def load():
     L.mtgo_count_solid.argtypes = [C.c_void_p, u64p, u64p, u32p]
     L.mtgo_graph_new.restype = C.c_void_p
     L.mtgo_graph_new.argtypes = [u64p, u64p, C.c_uint64, C.c_int]
+    L.mtgo_graph_new_threads.restype = C.c_void_p
+    L.mtgo_graph_new_threads.argtypes = [u64p, u64p, C.c_uint64, C.c_int, C.c_int]
     L.mtgo_graph_free.argtypes = [C.c_void_p]
     L.mtgo_graph_query.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, u8p]
     L.mtgo_graph_bits.restype = C.c_uint64
@@ -95,11 +97,11 @@ def count_stream(stream: bytes, k: int, abundance_min=-1, abundance_max=21474836
 
 
 class Graph:
-    def __init__(self, lo, hi, k):
+    def __init__(self, lo, hi, k, nthreads=1):
         self.L = load()
         self.k = k
         lo = np.ascontiguousarray(lo, dtype=np.uint64); hi = np.ascontiguousarray(hi, dtype=np.uint64)
-        self.h = self.L.mtgo_graph_new(lo, hi, len(lo), k)
+        self.h = self.L.mtgo_graph_new(lo, hi, len(lo), k) if nthreads <= 1 else self.L.mtgo_graph_new_threads(lo, hi, len(lo), k, nthreads)
 
     def close(self):
         if self.h:

@@ -156,3 +156,30 @@ def test_count_stream_threads_agree(oracle):
         b = oracle_py.count_stream(stream, k, abundance_min=2, nthreads=4)
         assert (a["lo"] == b["lo"]).all() and (a["hi"] == b["hi"]).all() and (a["abundance"] == b["abundance"]).all()
         assert (a["histogram"] == b["histogram"]).all()
+
+
+@pytest.mark.parametrize("name", ["full", "full_k63", "syn_small_k31"])
+def test_graph_build_threads_agree(oracle_bin, tmp_path, name):
+    """The threaded graph build of the CPU baseline (oracle/graph_mt.hpp) gives the same Bloom / cascade / BooPHF bits, sizes and
+    cFP set as the single-threaded restatement, and `oracle_find -nb-cores 4` the same files as `-nb-cores 1`."""
+    case = CASES[name]
+    reads, _ = case_paths(case)
+    stream = b"\n".join(s for _, s in oracle_py.read_sequences(reads)) + b"\n"
+    amin = -1
+    for i, fl in enumerate(case["flags"]):
+        if fl == "-abundance-min":
+            amin = int(case["flags"][i + 1])
+    o = oracle_py.count_stream(stream, case["k"], abundance_min=amin, nthreads=2)
+    a = oracle_py.Graph(o["lo"], o["hi"], case["k"])
+    b = oracle_py.Graph(o["lo"], o["hi"], case["k"], nthreads=4)
+    assert a.info() == b.info()
+    for which in (0, 1, 2, 3, 5):
+        assert (a.bits(which) == b.bits(which)).all(), which
+    rng = np.random.default_rng(2)
+    qlo = np.concatenate([o["lo"][:3000], rng.integers(0, 1 << 62, 3000, dtype=np.uint64)])
+    qhi = np.concatenate([o["hi"][:3000], np.zeros(3000, dtype=np.uint64)])
+    assert (a.query(qlo, qhi) == b.query(qlo, qhi)).all()
+    a.close(); b.close()
+    bk1, vcf1, info1 = run_oracle(oracle_bin, name, tmp_path, extra=["-nb-cores", "1"])
+    bk4, vcf4, info4 = run_oracle(oracle_bin, name, tmp_path, extra=["-nb-cores", "4"])
+    assert bk1 == bk4 and vcf1 == vcf4 and info1["nb_solid"] == info4["nb_solid"]
