@@ -183,3 +183,39 @@ def test_graph_build_threads_agree(oracle_bin, tmp_path, name):
     bk1, vcf1, info1 = run_oracle(oracle_bin, name, tmp_path, extra=["-nb-cores", "1"])
     bk4, vcf4, info4 = run_oracle(oracle_bin, name, tmp_path, extra=["-nb-cores", "4"])
     assert bk1 == bk4 and vcf1 == vcf4 and info1["nb_solid"] == info4["nb_solid"]
+
+
+H5_CASES = ["full", "full_k63", "full_k21_amin3", "inserts_ref10k", "hetero_insert", "syn_tiny_k31", "syn_tiny_k32", "syn_tiny_k63",
+            "syn_small_k31", "syn_small_k47_homo"]
+
+
+@pytest.mark.parametrize("name", H5_CASES)
+def test_oracle_bloom_bytes_equal_reference_h5_datasets(oracle, name):
+    """The "golden bits" of SURVEY.md 8c: /bloom/bloom and /debloom/bloom2,3,4 of the .h5 written by the unmodified reference
+    binary (tests/golden/ref_outputs/<case>.h5bits.json, dumped with gatb-h5dump) equal the oracle's arrays byte for byte, and
+    /debloom/cfp holds as many k-mers as the oracle's cFP set."""
+    import base64
+    import hashlib
+    import json
+    case = CASES[name]
+    fx = json.load(open(os.path.join(GOLD, "ref_outputs", name + ".h5bits.json")))
+    reads, _ = case_paths(case)
+    stream = b"\n".join(s for _, s in oracle_py.read_sequences(reads)) + b"\n"
+    amin = -1
+    for i, fl in enumerate(case["flags"]):
+        if fl == "-abundance-min":
+            amin = int(case["flags"][i + 1])
+    o = oracle_py.count_stream(stream, case["k"], abundance_min=amin, nthreads=2)
+    g = oracle_py.Graph(o["lo"], o["hi"], case["k"])
+    for which, ds in enumerate(["/bloom/bloom", "/debloom/bloom2", "/debloom/bloom3", "/debloom/bloom4"]):
+        if ds not in fx:
+            assert which > 0 and g.info()["nb_critical"] == 0, ds   # no critical FP -> the reference writes no cascade
+            continue
+        bits = g.bits(which).tobytes()
+        assert len(bits) == fx[ds]["bytes"], (ds, len(bits), fx[ds]["bytes"])
+        assert hashlib.sha256(bits).hexdigest() == fx[ds]["sha256"], ds
+        if "base64" in fx[ds]:
+            assert bits == base64.b64decode(fx[ds]["base64"]), ds
+    if "/debloom/cfp" in fx:
+        assert g.info()["cfp_set"] * (8 if case["k"] <= 31 else 16) == fx["/debloom/cfp"]["bytes"]
+    g.close()
