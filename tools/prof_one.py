@@ -1,5 +1,5 @@
 """Profiling driver (GPU box, run under ncu): N resident finds on cfg2 (scaled by argv[2]), nothing else.
-usage: python tools/prof_one.py [n_finds=2] [scale=1.0] [k=31]"""
+usage: python tools/prof_one.py [n_finds=2] [scale=1.0] [k=31] [config=cfg2]"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,7 +12,9 @@ import mindthegap_b200 as m
 n_finds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 31
-wl = bench.make_workload(scale=scale)
+config = sys.argv[4] if len(sys.argv) > 4 else "cfg2"
+bench.K = k
+wl = bench.make_workload(scale=scale, config=config)
 dev = torch.from_numpy(wl["stream"]).cuda()
 ref_stream = np.concatenate([np.concatenate([s, np.array([10], dtype=np.uint8)]) for _, s in wl["refs"]])
 n = int(dev.numel())
