@@ -199,6 +199,61 @@ MTG_HD uint32_t key_hash32(u128 k) {
 MTG_HD uint64_t key_hash(uint64_t k) { return mix64(k); }
 MTG_HD uint64_t key_hash(u128 k) { return mix64(k.lo ^ mix64(k.hi + 0x9E3779B97F4A7C15ULL)); }
 
+// ----------------------------------------------------------------------------------------------- minimizers
+// Random-order minimizer (ours, not GATB's: partitioning / table placement never influence results): value of an m-mer =
+// top 31 bits of (min(m-mer, revcomp) * golden-ratio constant); the minimizer of a k-mer is the minimum over its k-m+1 m-mers.
+// Strand-symmetric, so a k-mer and its reverse complement get the same value. 2m <= 30 bits.
+MTG_HD uint32_t mmer_hash(uint32_t fwd, uint32_t rc) { return ((fwd < rc ? fwd : rc) * 0x9E3779B1u) >> 1; }
+MTG_HD uint32_t mmer_revcomp(uint32_t fwd, int m) {   // reverse complement of an m-mer held in the low 2m bits
+    uint32_t r = 0;
+#ifdef __CUDA_ARCH__
+    r = __brev(fwd) >> (32 - 2 * m);
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+#else
+    for (int i = 0; i < m; i++) r |= ((fwd >> (2 * i)) & 3u) << (2 * (m - 1 - i));
+#endif
+    return (r ^ 0xAAAAAAAAu) & (uint32_t)((1ull << (2 * m)) - 1);
+}
+MTG_HD unsigned base_from_lsb(uint64_t x, int pos) { return (unsigned)(x >> (2 * pos)) & 3u; }   // base `pos` counted from the last base
+MTG_HD unsigned base_from_lsb(u128 x, int pos) { return (unsigned)((pos < 32 ? x.lo >> (2 * pos) : x.hi >> (2 * (pos - 32)))) & 3u; }
+// Minimizer values of a k-mer: over all its m-mers, over all but its FIRST m-mer (what a successor keeps) and over all but its
+// LAST m-mer (what a predecessor keeps). One pass from the last m-mer to the first, rolling both strands.
+struct MiniTriple { uint32_t all, wo_first, wo_last; };
+template <class K> MTG_HD MiniTriple kmer_minimizers(K x, int k, int m) {
+    const uint32_t mmask = (uint32_t)((1ull << (2 * m)) - 1);
+    uint32_t fwd = (uint32_t)lo64(x) & mmask, rc = mmer_revcomp(fwd, m);
+    uint32_t h = mmer_hash(fwd, rc);
+    const uint32_t h0 = h;
+    MiniTriple t;
+    t.wo_first = h;            // j = 0 is the LAST m-mer; W >= 2 so it is never the first one
+    t.wo_last = 0xFFFFFFFFu;
+    const int W = k - m + 1;
+    for (int j = 1; j < W; j++) {
+        const unsigned b = base_from_lsb(x, j + m - 1);
+        fwd = (fwd >> 2) | (b << (2 * (m - 1)));
+        rc = ((rc << 2) | (b ^ 2u)) & mmask;
+        h = mmer_hash(fwd, rc);
+        t.wo_last = t.wo_last < h ? t.wo_last : h;
+        if (j < W - 1) t.wo_first = t.wo_first < h ? t.wo_first : h;
+    }
+    t.all = t.wo_last < h0 ? t.wo_last : h0;
+    return t;
+}
+template <class K> MTG_HD uint32_t kmer_minimizer(K x, int k, int m) {
+    const uint32_t mmask = (uint32_t)((1ull << (2 * m)) - 1);
+    uint32_t fwd = (uint32_t)lo64(x) & mmask, rc = mmer_revcomp(fwd, m);
+    uint32_t best = mmer_hash(fwd, rc);
+    const int W = k - m + 1;
+    for (int j = 1; j < W; j++) {
+        const unsigned b = base_from_lsb(x, j + m - 1);
+        fwd = (fwd >> 2) | (b << (2 * (m - 1)));
+        rc = ((rc << 2) | (b ^ 2u)) & mmask;
+        const uint32_t h = mmer_hash(fwd, rc);
+        best = best < h ? best : h;
+    }
+    return best;
+}
+
 // ----------------------------------------------------------------------------------------------- atomics
 MTG_D uint64_t cas_global(uint64_t* a, uint64_t cmp, uint64_t val) {
     return (uint64_t)atomicCAS((unsigned long long*)a, (unsigned long long)cmp, (unsigned long long)val);

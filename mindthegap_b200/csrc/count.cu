@@ -137,7 +137,7 @@ MTG_HD uint64_t make_record(uint64_t pos, uint32_t len, uint32_t mini) {
 // minimizer of rank quantile u attracts W(1-u)^(W-1) times the average load (up to W = k-m+1 times), which overflows
 // the shared-memory count table once the average bin nears its size; folding 4^m/2 minimizers into 2^20 bins averages
 // that skew out (relative sigma ~ 3.2 / sqrt(minimizers per bin)).
-MTG_D uint32_t mmer_hash(uint32_t fwd, uint32_t rc) { return (min(fwd, rc) * 0x9E3779B1u) >> 1; }
+// mmer_hash itself lives in common.cuh (the exact table is placed by the same kind of minimizer).
 MTG_D uint32_t mini_bin(uint32_t mini, int bin_bits) { return (mini * 0x85EBCA6Bu) >> (32 - bin_bits); }
 
 MTG_D int sk_vidx(int q) { return q + (q >> 3); }  // padded index: threads reading element e of their 8-run hit 32 distinct banks

@@ -57,24 +57,40 @@ struct BloomDev {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ build kernels
+// One thread per solid k-mer: minimizer -> home bucket (graph.cuh), the bucket's key slots are read with seven 128-bit loads
+// and only the first slot seen empty is claimed with one CAS (a slot only ever goes from empty to a key, so a stale read can
+// at worst cost a failed CAS). The solid set leaves the count stage grouped by minimizer bin: neighbouring threads fill the
+// same few lines while they are resident in L2.
 template <class K>
-__global__ void __launch_bounds__(256) table_build_kernel(const K* __restrict__ keys, uint64_t n, K* __restrict__ table_all, uint64_t nbuckets,
-                                                          uint32_t nshards, int* __restrict__ err) {
+__global__ void __launch_bounds__(256) table_build_kernel(const K* __restrict__ keys, uint64_t n, K* __restrict__ table_all, GraphView<K> g,
+                                                          int* __restrict__ err) {
     const int SLOTS = TableCfg<K>::SLOTS, STRIDE = TableCfg<K>::STRIDE;
     const K EMPTY = ~K(0);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const K key = keys[i];
-        const uint64_t h = key_hash(key);
-        uint64_t b = h % nbuckets;
-        K* table = table_all + (uint64_t)shard_of(h, nshards) * nbuckets * STRIDE;
+        const uint64_t h = mini_place_hash(kmer_minimizer(key, g.k, g.tm));
+        uint64_t b = table_home_bucket<K>(h, g.nregions, g.glog, key);
+        K* table = table_all + (uint64_t)shard_of(h, g.nshards) * g.nbuckets * STRIDE;
         bool done = false;
-        for (uint64_t probe = 0; probe < nbuckets && !done; probe++) {
+        for (uint64_t probe = 0; probe < g.nbuckets && !done; probe++) {
             K* bucket = table + b * STRIDE;
+            const uint4* q = reinterpret_cast<const uint4*>(bucket);
+            uint4 v[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) v[j] = __ldcg(q + j);
+#pragma unroll
             for (int s = 0; s < SLOTS; s++) {
-                K cur = cas_global(&bucket[s], EMPTY, key);
-                if (cur == EMPTY || cur == key) { done = true; break; }
+                if (done) break;
+                K cur;
+                if (sizeof(K) == 8) cur = make_key<K>(s & 1 ? (((uint64_t)v[s >> 1].w << 32) | v[s >> 1].z) : (((uint64_t)v[s >> 1].y << 32) | v[s >> 1].x), 0);
+                else cur = make_key<K>(((uint64_t)v[s].y << 32) | v[s].x, ((uint64_t)v[s].w << 32) | v[s].z);
+                if (cur == key) { done = true; break; }
+                if (cur == EMPTY) {
+                    cur = cas_global(&bucket[s], EMPTY, key);
+                    if (cur == EMPTY || cur == key) { done = true; break; }
+                }
             }
-            b = b + 1 == nbuckets ? 0 : b + 1;
+            b = b + 1 == g.nbuckets ? 0 : b + 1;
         }
         if (!done) *err = 1;
     }
@@ -121,6 +137,8 @@ __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ key
         const K x = active ? keys[t >> 1] : K(0);
         const bool succ = !(t & 1);
         unsigned alive = 0, adj = 0;
+        // minimizers: of x itself (its bucket holds the adjacency byte) and the part of it every successor / predecessor keeps
+        const MiniTriple mt = kmer_minimizers(x, k, g.tm);
         if (active) {
             // shared middle part of the 4 neighbours: successors y = x[1..k-1]+nt -> x[2..k-1]; predecessors y = nt+x[0..k-2] -> x[0..k-3]
             K hashpart = succ ? (x & kmask<K>(k - 2)) : ((x >> 4) & kmask<K>(k - 2));
@@ -150,8 +168,18 @@ __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ key
             const int nt = __ffs(alive) - 1;
             alive &= alive - 1;
             K nb = succ ? (((x << 2) + (K)nt) & mask) : ((x >> 2) + ((K)nt << (2 * (k - 1))));  // Model.hpp:524-580
+            // the neighbour's minimizer = min(what it keeps of x's m-mers, its one new m-mer); strand-symmetric, so taken before canonical()
+            uint32_t nmini;
+            {
+                const int m = g.tm;
+                const uint32_t mmask = (uint32_t)((1ull << (2 * m)) - 1);
+                const uint32_t f = succ ? ((uint32_t)lo64(nb) & mmask) : (uint32_t)lo64(nb >> (2 * (k - m))) & mmask;
+                const uint32_t hnew = mmer_hash(f, mmer_revcomp(f, m));
+                const uint32_t kept = succ ? mt.wo_first : mt.wo_last;
+                nmini = kept < hnew ? kept : hnew;
+            }
             nb = canonical(nb, k);
-            if (table_contains(g, nb)) { adj |= 1u << nt; continue; }
+            if (table_contains(g, nb, nmini)) { adj |= 1u << nt; continue; }
             if (!CRIT) continue;
             uint64_t s = key_hash(nb) % set_slots;
             bool placed = false;
@@ -168,8 +196,8 @@ __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ key
             // each in one half of the bucket
             const unsigned other = __shfl_xor_sync(0xFFFFFFFFu, adj, 1);
             const unsigned byte = succ ? (adj | (other << 4)) : (other | (adj << 4));
-            const uint64_t hx = key_hash(x);
-            uint64_t b = hx % g.nbuckets;
+            const uint64_t hx = mini_place_hash(mt.all);
+            uint64_t b = table_home_bucket<K>(hx, g.nregions, g.glog, x);
             K* const trw = table_rw + (uint64_t)shard_of(hx, g.nshards) * g.nbuckets * TableCfg<K>::STRIDE;   // the k-mer's range
             bool searching = active;
             for (uint64_t probe = 0; probe < g.nbuckets; probe++) {
@@ -345,7 +373,7 @@ __global__ void __launch_bounds__(256) mphf_compact_kernel(const K* __restrict__
 // destination (destinations are few and hot; same scheme as the super-k-mer records, count.cu)
 static const int KO_MAX = 64, KO_THREADS = 256, KO_PER = 4, KO_TILE = KO_THREADS * KO_PER;
 template <class K>
-__global__ void __launch_bounds__(KO_THREADS) key_owner_count_kernel(const K* __restrict__ keys, uint64_t n, uint32_t nshards,
+__global__ void __launch_bounds__(KO_THREADS) key_owner_count_kernel(const K* __restrict__ keys, uint64_t n, uint32_t nshards, int k, int tm,
                                                                      unsigned long long* __restrict__ counts) {
     __shared__ unsigned int s_cnt[KO_MAX];
     if (threadIdx.x < KO_MAX) s_cnt[threadIdx.x] = 0;
@@ -353,7 +381,7 @@ __global__ void __launch_bounds__(KO_THREADS) key_owner_count_kernel(const K* __
     const int lane = threadIdx.x & 31;
     const uint64_t nround = (n + 31) & ~31ull;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t d = i < n ? shard_of(key_hash(keys[i]), nshards) : 0xFFFFFFFFu;
+        const uint32_t d = i < n ? shard_of(mini_place_hash(kmer_minimizer(keys[i], k, tm)), nshards) : 0xFFFFFFFFu;
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
         if (d != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[d], (unsigned)__popc(peers));
     }
@@ -361,7 +389,7 @@ __global__ void __launch_bounds__(KO_THREADS) key_owner_count_kernel(const K* __
     if (threadIdx.x < nshards && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 template <class K>
-__global__ void __launch_bounds__(KO_THREADS) key_owner_scatter_kernel(const K* __restrict__ keys, uint64_t n, uint32_t nshards,
+__global__ void __launch_bounds__(KO_THREADS) key_owner_scatter_kernel(const K* __restrict__ keys, uint64_t n, uint32_t nshards, int k, int tm,
                                                                        unsigned long long* __restrict__ cursor, K* __restrict__ out) {
     __shared__ unsigned int s_cnt[KO_MAX];
     __shared__ unsigned long long s_base[KO_MAX];
@@ -376,7 +404,7 @@ __global__ void __launch_bounds__(KO_THREADS) key_owner_scatter_kernel(const K* 
         for (int j = 0; j < KO_PER; j++) {
             const uint64_t i = tile * KO_TILE + (uint64_t)j * KO_THREADS + threadIdx.x;
             r[j] = i < n ? keys[i] : K(0);
-            dest[j] = i < n ? shard_of(key_hash(r[j]), nshards) : 0xFFFFFFFFu;
+            dest[j] = i < n ? shard_of(mini_place_hash(kmer_minimizer(r[j], k, tm)), nshards) : 0xFFFFFFFFu;
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dest[j]);
             const int leader = __ffs(peers) - 1;
             uint32_t base = 0;
@@ -568,8 +596,16 @@ template <class K> class Graph : public IGraph {
     int k_;
     cudaStream_t stream_;
     DevBuf<K> table_;
-    uint64_t nbuckets_ = 0;   // buckets per range
+    uint64_t nbuckets_ = 0;   // buckets per range (a multiple of the region size)
+    uint64_t nregions_ = 0;   // regions per range
     uint32_t nshards_ = 1;    // ranges (= GPUs that built the table)
+    int tm_ = 0;              // minimizer length that places k-mers in the table
+    static const int GLOG = TableGeomCfg<K>::GLOG;
+    void set_buckets(uint64_t nkeys) {   // load factor ~0.55 over whole regions
+        const uint64_t nb = std::max<uint64_t>((uint64_t)((double)nkeys / 0.55 / TableCfg<K>::SLOTS) + 1, 1);
+        nregions_ = (nb + (1ull << GLOG) - 1) >> GLOG;
+        nbuckets_ = nregions_ << GLOG;
+    }
     BloomDev bloom_, b2_, b3_, b4_, ref_;
     DevBuf<K> cfp_, cfp_list_, final_, crit_list_;   // cfp_: hash set (cfp_slots_ slots); cfp_list_: the same k-mers as a list
     uint64_t cfp_slots_ = 1;
@@ -599,7 +635,7 @@ template <class K> class Graph : public IGraph {
         GraphView<K> g;
         memset(&g, 0, sizeof(g));
         g.k = k_;
-        g.table = table_.p; g.nbuckets = nbuckets_; g.nshards = nshards_;
+        g.table = table_.p; g.nbuckets = nbuckets_; g.nregions = nregions_; g.nshards = nshards_; g.tm = tm_; g.glog = GLOG;
         g.bloom = bloom_.bits.p; g.bloom_tai = bloom_.tai; g.bloom_nhash = bloom_.nhash;
         g.cascading = cascading_ ? 1 : 0;
         g.b2 = b2_.bits.p; g.b2_tai = b2_.tai; g.b3 = b3_.bits.p; g.b3_tai = b3_.tai; g.b4 = b4_.bits.p; g.b4_tai = b4_.tai;
@@ -630,6 +666,7 @@ template <class K> class Graph : public IGraph {
 public:
     Graph(int k, cudaStream_t s) : k_(k), stream_(s) {
         seed0_ = bloom_seed0_host();
+        tm_ = table_minimizer_len(k);
         MTG_CUDA(cudaEventCreate(&ev_a_));
         MTG_CUDA(cudaEventCreate(&ev_b_));
         std::mt19937_64 rng(37);  // tools/collections/impl/BooPHF.hpp:246-249
@@ -645,8 +682,8 @@ public:
         ref_.init(1000, 8, stream_);
         bloom_.init(1000, 4, stream_);
         b2_.init(1000, 4, stream_); b3_.init(1000, 4, stream_); b4_.init(1000, 4, stream_);
-        nbuckets_ = 1;
-        table_.alloc(TableCfg<K>::STRIDE);
+        set_buckets(0);
+        table_.alloc(nbuckets_ * TableCfg<K>::STRIDE);
         table_.fill_ff(stream_);
     }
     ~Graph() override {
@@ -698,8 +735,7 @@ public:
         st_.nb_solid = N;
         // ---- exact table, load factor ~0.55, 128-byte buckets
         t.start();
-        const int SLOTS = TableCfg<K>::SLOTS;
-        nbuckets_ = std::max<uint64_t>((uint64_t)((double)N / 0.55 / SLOTS) + 1, 1);
+        set_buckets(N);
         nshards_ = 1;
         table_.alloc(nbuckets_ * TableCfg<K>::STRIDE);
         table_.fill_ff(stream_);   // empty key slots; the 16 adjacency bytes of every bucket start at zero
@@ -708,7 +744,7 @@ public:
         adj_done_ = false;
         err_.zero(stream_);
         if (N) {
-            table_build_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, table_.p, nbuckets_, 1, err_.p);
+            table_build_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, table_.p, view(), err_.p);
             MTG_CUDA(cudaGetLastError());
             st_.launches++;
         }
@@ -874,7 +910,7 @@ public:
         DevBuf<unsigned long long> d_counts(KO_MAX), d_cursor(KO_MAX);
         d_counts.zero(stream_);
         const K* keys = (const K*)d_keys;
-        if (n) { key_owner_count_kernel<K><<<grid_for(n), KO_THREADS, 0, stream_>>>(keys, n, nshards, d_counts.p); st_.launches++; }
+        if (n) { key_owner_count_kernel<K><<<grid_for(n), KO_THREADS, 0, stream_>>>(keys, n, nshards, k_, tm_, d_counts.p); st_.launches++; }
         unsigned long long cnt[KO_MAX], cur[KO_MAX];
         MTG_CUDA(cudaMemcpyAsync(cnt, d_counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, stream_));
         MTG_CUDA(cudaStreamSynchronize(stream_));
@@ -882,7 +918,7 @@ public:
         for (int d = 0; d < KO_MAX; d++) { cur[d] = off; if ((uint32_t)d < nshards) { counts_host[d] = cnt[d]; off += cnt[d]; } }
         MTG_CUDA(cudaMemcpyAsync(d_cursor.p, cur, sizeof(cur), cudaMemcpyHostToDevice, stream_));
         if (n) {
-            key_owner_scatter_kernel<K><<<grid_for((n + KO_PER - 1) / KO_PER, KO_THREADS), KO_THREADS, 0, stream_>>>(keys, n, nshards, d_cursor.p, (K*)d_out);
+            key_owner_scatter_kernel<K><<<grid_for((n + KO_PER - 1) / KO_PER, KO_THREADS), KO_THREADS, 0, stream_>>>(keys, n, nshards, k_, tm_, d_cursor.p, (K*)d_out);
             st_.launches++;
         }
         MTG_CUDA(cudaGetLastError());
@@ -898,8 +934,8 @@ public:
         if (n_share) MTG_CUDA(cudaMemcpyAsync(share_.p, d_keys_share, n_share * sizeof(K), cudaMemcpyDeviceToDevice, stream_));
         // ---- all ranges allocated, own range built (same load factor as the single-GPU table, from the largest share)
         t.start();
-        const int SLOTS = TableCfg<K>::SLOTS, STRIDE = TableCfg<K>::STRIDE;
-        nbuckets_ = std::max<uint64_t>((uint64_t)((double)max_share / 0.55 / SLOTS) + 1, 1);
+        const int STRIDE = TableCfg<K>::STRIDE;
+        set_buckets(max_share);
         nshards_ = nshards;
         table_.alloc(nbuckets_ * nshards * STRIDE);
         K* own = table_.p + (uint64_t)shard * nbuckets_ * STRIDE;
@@ -908,7 +944,7 @@ public:
         adj_done_ = false;
         err_.zero(stream_);
         if (n_share) {
-            table_build_kernel<K><<<grid_for(n_share), 256, 0, stream_>>>(share_.p, n_share, table_.p, nbuckets_, nshards, err_.p);
+            table_build_kernel<K><<<grid_for(n_share), 256, 0, stream_>>>(share_.p, n_share, table_.p, view(), err_.p);
             MTG_CUDA(cudaGetLastError());
             st_.launches++;
         }

@@ -17,9 +17,15 @@ template <class K> struct GraphView {
     // exact table: nbuckets buckets of 128 bytes (14 u64 keys or 7 u128 keys + 16 adjacency bytes); empty slot = all ones
     // With N GPUs the table is `nshards` equal ranges of `nbuckets` buckets: range r is built by rank r from the solid k-mers
     // whose hash selects it (shard_of) and the ranges are all-gathered; one range on a single GPU.
+    // Placement (ours): buckets are grouped in REGIONS of 2^glog consecutive buckets; a k-mer's region is chosen by the hash of
+    // its random-order minimizer (length tm, common.cuh), the bucket inside the region by the k-mer's own hash, overflow goes to
+    // the following buckets. Consecutive k-mers of a sequence and the neighbours of a k-mer share their minimizer, so they sit
+    // in the same few 128-byte lines: building, the critical-FP search and the reference scan touch a line once, not per k-mer.
     const K* table;
-    uint64_t nbuckets;
+    uint64_t nbuckets;     // per range, a multiple of 2^glog
+    uint64_t nregions;     // per range
     uint32_t nshards;
+    int tm, glog;
     // Bloom filters as little-endian u32 words (bit pos -> word pos>>5, bit pos&31 == byte pos>>3, bit pos&7)
     const uint32_t* bloom; uint64_t bloom_tai; int bloom_nhash;      // BloomNeighborCoherent (main)
     int cascading;                                                   // 0 -> cFP is the plain sorted set `cfp`
@@ -208,9 +214,19 @@ template <class K> struct TableCfg { static const int SLOTS = BUCKET_KEY_BYTES /
 // Probe by one thread: the whole 128-byte bucket with eight 128-bit loads (one line, 4 sectors). Returns the slot of
 // `key` in [0, SLOTS) (and the bucket in *bucket_out) or -1; *adj receives the adjacency byte of the slot.
 MTG_HD uint32_t shard_of(uint64_t h, uint32_t nshards) { return (uint32_t)(((h >> 32) * (uint64_t)nshards) >> 32); }
-template <class K> MTG_D int table_find(const K* __restrict__ table, uint64_t nbuckets, uint32_t nshards, K key, uint64_t* bucket_out, unsigned* adj) {
-    const uint64_t h = key_hash(key);
-    uint64_t b = h % nbuckets;
+template <class K> struct TableGeomCfg { static const int GLOG = sizeof(K) == 8 ? 1 : 3; };   // region = 2 x 14 (u64) or 8 x 7 (u128) slots
+MTG_HD int table_minimizer_len(int k) { return k - 1 < 15 ? k - 1 : 15; }
+// placement hash of a minimizer value: top 32 bits select the range (GPU), low 32 bits the region inside the range
+MTG_HD uint64_t mini_place_hash(uint32_t mini) { return mix64((uint64_t)mini + 0x632BE59BD9B4E019ULL); }
+template <class K> MTG_HD uint64_t table_home_bucket(uint64_t h, uint64_t nregions, int glog, K key) {
+    const uint64_t region = ((h & 0xFFFFFFFFull) * nregions) >> 32;
+    return (region << glog) | (uint64_t)(key_hash32(key) & ((1u << glog) - 1u));
+}
+// `mini` = kmer_minimizer(key, k, tm) (callers that roll it pass it in)
+template <class K> MTG_D int table_find(const K* __restrict__ table, uint64_t nbuckets, uint64_t nregions, uint32_t nshards, int glog, K key, uint32_t mini,
+                                        uint64_t* bucket_out, unsigned* adj) {
+    const uint64_t h = mini_place_hash(mini);
+    uint64_t b = table_home_bucket<K>(h, nregions, glog, key);
     table += (uint64_t)shard_of(h, nshards) * nbuckets * TableCfg<K>::STRIDE;   // linear probing stays inside the key's range
     for (uint64_t probe = 0; probe < nbuckets; probe++) {
         const uint4* q = reinterpret_cast<const uint4*>(table + b * TableCfg<K>::STRIDE);
@@ -242,8 +258,13 @@ template <class K> MTG_D int table_find(const K* __restrict__ table, uint64_t nb
     }
     return -1;
 }
-template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key) { return table_find<K>(g.table, g.nbuckets, g.nshards, key, nullptr, nullptr) >= 0; }
-template <class K> MTG_D bool table_lookup(const GraphView<K>& g, K key, unsigned& adj) { return table_find<K>(g.table, g.nbuckets, g.nshards, key, nullptr, &adj) >= 0; }
+template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key, uint32_t mini) {
+    return table_find<K>(g.table, g.nbuckets, g.nregions, g.nshards, g.glog, key, mini, nullptr, nullptr) >= 0;
+}
+template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key) { return table_contains(g, key, kmer_minimizer(key, g.k, g.tm)); }
+template <class K> MTG_D bool table_lookup(const GraphView<K>& g, K key, unsigned& adj) {
+    return table_find<K>(g.table, g.nbuckets, g.nregions, g.nshards, g.glog, key, kmer_minimizer(key, g.k, g.tm), nullptr, &adj) >= 0;
+}
 
 // Graph::contains for a CANONICAL k-mer. *used_fallback is set when the exact table missed and the Bloom emulation
 // had to answer (counted separately from the roofline probes).

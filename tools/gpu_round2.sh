@@ -14,7 +14,7 @@ import json
 d=json.load(open("gpurun_out/bench_$V.json"))
 print({k:d.get(k) for k in ("value","ms_per_step","e2e","parity","parity_full","e2e_from_files")})
 print(d["roofline"]); print(d["stage_ms"]); print(d["cpu_baseline"])
-for k in d["kernels"]: print("%-60s %8.3f ms  %8.1f GB/s  frac %.3f (%s)" % (k["kernel"][:60], k["ms"], k["achieved_gbs"] or 0, k["frac"] or 0, k["bound"]))
+for k in d["kernels"]: print("%-60s %8.3f ms  %8.1f GB/s  frac %.3f (%s)" % (k["kernel"][:60], k["ms"], k["achieved_gbs"] or 0, k["frac"] or 0, k.get("bound")))
 PY
 fi
 if [ -n "$REFARM" ]; then
