@@ -76,7 +76,9 @@ int mtg_push_reads_text_device(mtg_ctx* ctx, const void* d_text, uint64_t nbytes
 uint64_t mtg_text_record_cut(const char* text, uint64_t nbytes, int32_t format, int32_t final);
 /* Bank::open on a comma separated list of FASTA/FASTQ files, plain or gzip (G/bank/impl/Bank.cpp:49-52, README.md:166):
  * file bytes are staged in pinned memory in chunks cut at record starts and parsed on the GPU (mtg_push_reads_text).
- * With MTG_F_HOST_PARSE in params.flags the kseq-style host reader is used instead (plain or gzip; any layout). */
+ * With MTG_F_HOST_PARSE in params.flags the kseq-style host reader is used instead (plain or gzip; any layout).
+ * A list entry may be a "file of files" (one path per line, bare names relative to its directory), expanded like BankAlbum
+ * (G/bank/impl/BankAlbum.cpp:48-94, validity rule :124-170). A non-empty file without any '>' / '@' record is an error (-2). */
 int mtg_count_files(mtg_ctx* ctx, const char* uri);
 /* Ends the counting: histogram, auto cut-off (Histogram::compute_threshold, G/tools/misc/impl/Histogram.cpp:59-189),
  * solidity filter (CountProcessorSolidity.hpp:182-185); then builds the membership structures of
@@ -221,7 +223,8 @@ int mtg_scan_reference_bed(mtg_ctx* ctx, const char* name, const char* seq, uint
  * are answered by this context's GPU. interest may be NULL (walk every position). */
 int mtg_replay_sequence(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len, const uint8_t* feat, const uint8_t* rep,
                         const uint32_t* interest);
-/* Output accessors: pointers stay valid until the next scan/reset call on this context. */
+/* Output accessors: the pointers stay valid until the next scan / replay / mtg_reset_outputs / mtg_destroy call on this context
+ * (copy the text before that). A NULL context yields "" with *nbytes = 0. */
 const char* mtg_breakpoints_text(mtg_ctx* ctx, uint64_t* nbytes);
 const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes);
 int mtg_reset_outputs(mtg_ctx* ctx);

@@ -313,7 +313,7 @@ static void count_file_text(mtg_ctx* ctx, const std::string& path) {
     if (const char* e = getenv("MTG_INGEST_CHUNK")) cap = std::max<size_t>((size_t)atoll(e), 64);   // tests: force many chunks
     PinnedBuf buf;
     buf.reserve(cap);
-    size_t have = 0;
+    size_t have = 0, total_read = 0;
     bool eof = false;
     int fmt = TEXT_AUTO;
     try {
@@ -321,7 +321,7 @@ static void count_file_text(mtg_ctx* ctx, const std::string& path) {
             while (!eof && have < cap) {
                 const int r = gzread(f, buf.as<char>() + have, (unsigned)std::min<size_t>(cap - have, 1u << 30));
                 if (r < 0) throw Error(-2, "read error in " + path);
-                if (r == 0) eof = true; else have += (size_t)r;
+                if (r == 0) eof = true; else { have += (size_t)r; total_read += (size_t)r; }
             }
             char* text = buf.as<char>();
             if (fmt == TEXT_AUTO) {
@@ -350,6 +350,8 @@ static void count_file_text(mtg_ctx* ctx, const std::string& path) {
         }
     } catch (...) { gzclose(f); throw; }
     gzclose(f);
+    // a non-empty file without any '>' / '@' header is not a sequence file (the reference's Bank::open rejects it too)
+    if (fmt == TEXT_AUTO && total_read > 0) throw Error(-2, "no FASTA/FASTQ record in " + path);
 }
 
 int mtg_count_files(mtg_ctx* ctx, const char* uri) {
@@ -357,15 +359,9 @@ int mtg_count_files(mtg_ctx* ctx, const char* uri) {
     WallTimer w(ctx->wall_push);
     ICounter* c = reads_counter(ctx);
     if (!(ctx->p.flags & MTG_F_HOST_PARSE)) {
-        const std::string u(uri);
-        size_t start = 0;
-        while (start <= u.size()) {
-            const size_t comma = u.find(',', start);
-            const std::string path = u.substr(start, comma == std::string::npos ? std::string::npos : comma - start);
-            if (!path.empty()) count_file_text(ctx, path);
-            if (comma == std::string::npos) break;
-            start = comma + 1;
-        }
+        std::vector<std::string> files;
+        expand_uri(uri, files);   // comma list, "file of files" albums expanded (seqio.hpp)
+        for (const std::string& path : files) count_file_text(ctx, path);
         return 0;
     }
     // MTG_F_HOST_PARSE: the kseq-style host reader (multi-line FASTQ and other layouts the GPU parser rejects; plain text only)
@@ -788,11 +784,13 @@ int mtg_scan_reference_device(mtg_ctx* ctx, const char* name, const char* seq, c
 }
 
 const char* mtg_breakpoints_text(mtg_ctx* ctx, uint64_t* nbytes) {
+    if (!ctx) { if (nbytes) *nbytes = 0; return ""; }
     const std::string& s = ctx->rp64 ? ctx->rp64->bkpt_out : ctx->rp128->bkpt_out;
     if (nbytes) *nbytes = s.size();
     return s.c_str();
 }
 const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes) {
+    if (!ctx) { if (nbytes) *nbytes = 0; return ""; }
     const std::string& s = ctx->rp64 ? ctx->rp64->vcf_out : ctx->rp128->vcf_out;
     if (nbytes) *nbytes = s.size();
     return s.c_str();

@@ -7,7 +7,9 @@
 #include <errno.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <ctype.h>
 #include <stdlib.h>
+#include <string.h>
 #include <zlib.h>
 
 #include <functional>
@@ -26,12 +28,14 @@ class SeqReader {
     size_t b_ = 0, e_ = 0;
     bool eof_ = false;
     int last_ = 0;
+    uint64_t total_ = 0;
     int getc_() {
         if (b_ >= e_) {
             if (eof_) return -1;
             const int r = gzread(f_, buf_.data(), (unsigned)buf_.size());
             if (r < 0) throw std::runtime_error("read error in a sequence file");
             e_ = (size_t)r;
+            total_ += e_;
             b_ = 0;
             if (e_ < buf_.size()) eof_ = true;
             if (e_ == 0) return -1;
@@ -62,6 +66,7 @@ public:
         gzbuffer(f_, 1u << 20);
     }
     ~SeqReader() { if (f_) gzclose(f_); }
+    uint64_t bytes_read() const { return total_; }
     bool next(SeqRecord& r) {
         int c;
         if (last_ == 0) {
@@ -93,18 +98,65 @@ public:
     }
 };
 
-inline void for_each_sequence(const std::string& uri, const std::function<void(SeqRecord&)>& fn) {
+// "File of files" (README.md:166; gatb's BankAlbum, bank/impl/BankAlbum.cpp:48-94, is tried before BankFasta and accepts a text
+// file whose every non-blank line names an existing file, :124-170; a bare file name is relative to the album's directory).
+// Returns true and the listed paths when `path` is such a file.
+inline bool album_paths(const std::string& path, std::vector<std::string>& out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    const int c0 = fgetc(f);
+    if (c0 == EOF || c0 == '>' || c0 == '@' || c0 == 0x1f) { fclose(f); return false; }   // sequence text or gzip
+    rewind(f);
+    std::string dir = ".";
+    const size_t slash = path.rfind('/');
+    if (slash != std::string::npos) dir = path.substr(0, slash);
+    std::vector<std::string> paths;
+    char line[4096];
+    bool ok = true;
+    while (ok && fgets(line, sizeof line, f)) {
+        size_t n = strlen(line);
+        while (n && isspace((unsigned char)line[n - 1])) line[--n] = 0;
+        if (!n) continue;
+        for (size_t i = 0; i < n; i++) if ((unsigned char)line[i] < 32) ok = false;   // binary data is not a list of paths
+        std::string u(line);
+        if (u.find('/') == std::string::npos) u = dir + "/" + u;
+        FILE* g = ok ? fopen(u.c_str(), "rb") : nullptr;
+        if (!g) { ok = false; break; }
+        fclose(g);
+        paths.push_back(u);
+        if (paths.size() > 100000) ok = false;
+    }
+    fclose(f);
+    if (!ok || paths.empty()) return false;
+    out = paths;
+    return true;
+}
+// The files a comma separated -in / -ref list names, albums expanded (recursively, like Bank::open on each line).
+inline void expand_uri(const std::string& uri, std::vector<std::string>& files, int depth = 0) {
+    if (depth > 8) throw std::runtime_error("file-of-files nested too deeply: " + uri);
     size_t start = 0;
     while (start <= uri.size()) {
         size_t c = uri.find(',', start);
         std::string path = uri.substr(start, c == std::string::npos ? std::string::npos : c - start);
         if (!path.empty()) {
-            SeqReader rd(path);
-            SeqRecord r;
-            while (rd.next(r)) fn(r);
+            std::vector<std::string> listed;
+            if (album_paths(path, listed)) for (const std::string& p : listed) expand_uri(p, files, depth + 1);
+            else files.push_back(path);
         }
         if (c == std::string::npos) break;
         start = c + 1;
+    }
+}
+
+inline void for_each_sequence(const std::string& uri, const std::function<void(SeqRecord&)>& fn) {
+    std::vector<std::string> files;
+    expand_uri(uri, files);
+    for (const std::string& path : files) {
+        SeqReader rd(path);
+        SeqRecord r;
+        size_t nrec = 0;
+        while (rd.next(r)) { fn(r); nrec++; }
+        if (!nrec && rd.bytes_read() > 0) throw std::runtime_error("no FASTA/FASTQ record in " + path);
     }
 }
 

@@ -124,3 +124,35 @@ def test_host_reader_plain_and_gzip(tmp_path):
         assert out == want
     r = subprocess.run([exe, str(tmp_path / "missing.fa")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "Cannot open file" in r.stderr
+
+
+def test_host_reader_file_of_files_and_headerless_input(tmp_path):
+    """A list entry may be a "file of files" (README.md:166, gatb BankAlbum.cpp:48-94: one path per line, bare names relative to the
+    album's directory); a non-empty file without any record is an error instead of a silently empty bank."""
+    import shutil
+    from tests import oracle_py
+    exe = os.path.join(os.path.dirname(EXE), "seqio_check")
+    src = os.path.join(ROOT, "tests", "host", "seqio_check.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, src, "-lz"], check=True)
+    reads, ref = case_paths(CASES["full"])
+    r1, r2 = reads.split(",")
+    shutil.copy(r1, tmp_path / "a.fastq")
+    album = tmp_path / "reads.fof"
+    album.write_text("a.fastq\n\n%s\n" % r2)          # bare name (album's directory) + absolute path + blank line
+    nested = tmp_path / "all.fof"
+    nested.write_text("reads.fof\n")
+    want = ["%s\t%s" % (n, s.decode()) for n, s in oracle_py.read_sequences(reads)]
+    for uri in (str(album), str(nested)):
+        out = subprocess.run([exe, uri], stdout=subprocess.PIPE, text=True, check=True).stdout.splitlines()
+        assert out == want
+    out = subprocess.run([exe, str(album) + "," + ref], stdout=subprocess.PIPE, text=True, check=True).stdout.splitlines()
+    assert out == want + ["%s\t%s" % (n, s.decode()) for n, s in oracle_py.read_sequences(ref)]
+    junk = tmp_path / "junk.txt"
+    junk.write_text("this is not a sequence file\nnor a list of existing files\n")
+    r = subprocess.run([exe, str(junk)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "no FASTA/FASTQ record" in r.stderr
+    empty = tmp_path / "empty.fa"
+    empty.write_text("")
+    r = subprocess.run([exe, str(empty)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout == ""
