@@ -229,6 +229,55 @@ def parse_bed(text, chrom, k):
     return out
 
 
+SOLID_HDR = np.dtype([("magic", "S8"), ("version", "<u4"), ("kmer_size", "<u4"), ("nb_partitions", "<u4"), ("minimizer_size", "<u4"),
+                      ("n", "<u8"), ("nb_kmers_valid", "<u8"), ("nb_distinct", "<u8"), ("threshold", "<i4"), ("cutoff_auto", "<i4")])
+
+
+def write_solid_bin(path, k, m, repart, offs, lo, hi, ab, histogram, threshold, cutoff_auto, nb_valid=0, nb_distinct=0):
+    """The file mtg_h5 reads (csrc/h5_handoff.cpp: MtgSolidHeader, repart[4^m], part_offsets[P+1], histogram[10001], lo, (hi), abundance)."""
+    h = np.zeros(1, dtype=SOLID_HDR)
+    h["magic"] = b"MTGSOLID"; h["version"] = 1; h["kmer_size"] = k; h["nb_partitions"] = len(offs) - 1; h["minimizer_size"] = m
+    h["n"] = len(lo); h["nb_kmers_valid"] = nb_valid; h["nb_distinct"] = nb_distinct; h["threshold"] = threshold
+    h["cutoff_auto"] = cutoff_auto if cutoff_auto is not None else -1
+    with open(path, "wb") as f:
+        f.write(h.tobytes())
+        f.write(np.ascontiguousarray(repart, dtype="<u2").tobytes())
+        f.write(np.ascontiguousarray(offs, dtype="<u8").tobytes())
+        f.write(np.ascontiguousarray(histogram, dtype="<u8").tobytes())
+        f.write(np.ascontiguousarray(lo, dtype="<u8").tobytes())
+        if k > 31:
+            f.write(np.ascontiguousarray(hi, dtype="<u8").tobytes())
+        f.write(np.ascontiguousarray(ab, dtype="<u4").tobytes())
+
+
+def read_solid_bin(path):
+    """(k, lo, hi, abundance) of a file written by `mtg_h5 dump` / write_solid_bin."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    h = raw[:SOLID_HDR.itemsize].view(SOLID_HDR)[0]
+    assert h["magic"] == b"MTGSOLID"
+    k, n, P, m = int(h["kmer_size"]), int(h["n"]), int(h["nb_partitions"]), int(h["minimizer_size"])
+    o = SOLID_HDR.itemsize + 2 * 4 ** m + 8 * (P + 1) + 8 * 10001
+    lo = raw[o:o + 8 * n].view("<u8").copy(); o += 8 * n
+    hi = np.zeros(n, dtype=np.uint64)
+    if k > 31:
+        hi = raw[o:o + 8 * n].view("<u8").copy(); o += 8 * n
+    ab = raw[o:o + 4 * n].view("<u4").copy()
+    return k, lo, hi, ab
+
+
+def h5_tool_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "mtg_h5")
+
+
+def run_h5_tool(verb, h5, binp):
+    exe = h5_tool_path()
+    if not os.path.exists(exe):
+        raise MtgError("mtg_h5 is not built (it links the reference's gatb-core: run oracle/build_ref.sh where /root/reference exists)")
+    r = subprocess.run([exe, verb, h5, binp], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=os.path.dirname(os.path.abspath(h5)) or ".")
+    if r.returncode != 0:
+        raise MtgError("mtg_h5 %s failed: %s" % (verb, r.stderr.strip()[-500:]))
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -337,6 +386,36 @@ class Finder:
         ab = np.zeros(max(n, 1), dtype=np.uint32)
         self._check(self.L.mtg_graph_branching(self.ctx, nb, _ptr(topo), _ptr(lo), _ptr(hi), _ptr(ab), max(n, 1)))
         return n, topo.reshape(5, 5), lo[:n], hi[:n], ab[:n]
+
+    # ---- .h5 hand-off: the host tool mtg_h5 (csrc/h5_handoff.cpp, links the reference's gatb-core) does the HDF5 I/O
+    def write_graph_h5(self, path, nb_partitions=4, minimizer_size=10, complete=True, nb_cores=0):
+        """Write `path` (.h5) holding the GPU-counted solid k-mers in DSK's layout; complete=True then lets gatb-core finish the file
+        (its own CPU Bloom / debloom / MPHF / branching, `mtg_h5 complete`) so that the unchanged `MindTheGap fill -graph` /
+        `find -graph` load it like a graph `find` wrote itself. Off the timed path."""
+        st = self.stats()
+        repart, offs, lo, hi, ab = self.export_dsk_partitions(nb_partitions, minimizer_size)
+        binp = path + ".solid.bin"
+        write_solid_bin(binp, self.params.kmer_size, minimizer_size, repart, offs, lo, hi, ab, self.histogram(), self.threshold,
+                        self.cutoff_auto, int(st["count.nb_valid_kmers"]), int(self.histogram().sum()))
+        try:
+            run_h5_tool("write", path, binp)
+        finally:
+            os.remove(binp)
+        if complete:
+            run_h5_tool("complete", path, str(nb_cores))
+
+    def load_graph_h5(self, path):
+        """`-graph x.h5`: dsk/solid of a gatb .h5 -> the device graph (replaces Graph::load, src/Finder.cpp:277)."""
+        binp = path + ".solid.bin"
+        try:
+            run_h5_tool("dump", path, binp)
+            k, lo, hi, _ = read_solid_bin(binp)
+        finally:
+            if os.path.exists(binp):
+                os.remove(binp)
+        if k != self.params.kmer_size:
+            raise MtgError("graph %s was built with k=%d, this context uses k=%d" % (path, k, self.params.kmer_size))
+        self.load_solid(lo, hi if k > 31 else None)
 
     def load_solid(self, lo, hi=None):
         lo = np.ascontiguousarray(lo, dtype=np.uint64)

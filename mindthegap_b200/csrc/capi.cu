@@ -377,7 +377,14 @@ int mtg_count_files(mtg_ctx* ctx, const char* uri) {
     MTG_CATCH
 }
 
+// the table is placed by the minimizer the solid set was partitioned with (graph.cu set_table_minimizer)
+static void sync_table_minimizer(mtg_ctx* ctx) {
+    ICounter* c = ctx->solid_owner ? ctx->solid_owner.get() : ctx->counter.get();
+    ctx->graph->set_table_minimizer(c ? c->minimizer() : ctx->p.minimizer_size);
+}
+
 static void build_graph_from_counter(mtg_ctx* ctx, ICounter* c) {
+    sync_table_minimizer(ctx);
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, ctx->stream);
@@ -455,6 +462,7 @@ int mtg_solid_copy(mtg_ctx* ctx, void* d_keys_out, void* d_counts_out, uint64_t 
 }
 int mtg_graph_build_device(mtg_ctx* ctx, const void* d_keys, uint64_t n) {
     MTG_TRY(ctx)
+    sync_table_minimizer(ctx);
     WallTimer w(ctx->wall_finish);
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
@@ -472,7 +480,7 @@ int mtg_graph_build_device(mtg_ctx* ctx, const void* d_keys, uint64_t n) {
 }
 
 int mtg_graph_build_begin(mtg_ctx* ctx, const void* d_keys, uint64_t n) {
-    MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->build_base(d_keys, n); MTG_CUDA(cudaStreamSynchronize(ctx->stream)); MTG_CATCH
+    MTG_TRY(ctx) WallTimer w(ctx->wall_finish); sync_table_minimizer(ctx); ctx->graph->build_base(d_keys, n); MTG_CUDA(cudaStreamSynchronize(ctx->stream)); MTG_CATCH
 }
 int mtg_graph_critical(mtg_ctx* ctx, const void* d_keys_share, uint64_t n_share, uint64_t* n_out) {
     MTG_TRY(ctx)
@@ -504,15 +512,17 @@ int mtg_graph_build_end(mtg_ctx* ctx, const void* d_keys, uint64_t n, const void
 // ---- graph build on N GPUs (sharded by table range)
 int mtg_solid_partition(mtg_ctx* ctx, uint32_t nshards, void* d_out, uint64_t* counts) {
     MTG_TRY(ctx)
+    sync_table_minimizer(ctx);
     if (!ctx->solid_owner) throw Error(-1, "no counted solid set on this context");
     ctx->graph->partition_keys(ctx->solid_owner->solid_keys_device(), ctx->solid_owner->nb_solid(), nshards, d_out, counts);
     MTG_CATCH
 }
 int mtg_partition_keys(mtg_ctx* ctx, const void* d_keys, uint64_t n, uint32_t nshards, void* d_out, uint64_t* counts) {
-    MTG_TRY(ctx) ctx->graph->partition_keys(d_keys, n, nshards, d_out, counts); MTG_CATCH
+    MTG_TRY(ctx) sync_table_minimizer(ctx); ctx->graph->partition_keys(d_keys, n, nshards, d_out, counts); MTG_CATCH
 }
 int mtg_graph_shard_begin(mtg_ctx* ctx, const void* d_keys_share, uint64_t n_share, uint64_t n_total, uint64_t max_share, uint32_t nshards, uint32_t shard) {
     MTG_TRY(ctx)
+    sync_table_minimizer(ctx);
     WallTimer w(ctx->wall_finish);
     ctx->graph_ready = false;
     ctx->graph->shard_begin(d_keys_share, n_share, n_total, max_share, nshards, shard);
@@ -663,6 +673,7 @@ int mtg_load_solid(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_
     MTG_TRY(ctx)
     MTG_CUDA(cudaSetDevice(ctx->p.device));
     if (ctx->p.kmer_size > 31 && !hi) throw Error(-1, "kmer_size > 31 needs the high words");
+    ctx->graph->set_table_minimizer(ctx->p.minimizer_size);
     ctx->graph->build_from_host(lo, hi, n);
     ctx->graph_ready = true;
     ctx->nb_solid = n;

@@ -4,12 +4,16 @@
 //
 //   mtg_find [find] -in reads.fq[,reads2.fq] -ref ref.fa [-out prefix] [-kmer-size 31] [-abundance-min auto] ...
 //
-// Not supported here (reported as an error, like an OptionFailure): -graph x.h5, which needs gatb-core's HDF5 storage
-// (SURVEY.md 8f).
+// The .h5 graph file: HDF5 stays gatb-core's business. `<out>.h5` (what reference `find` leaves for `fill -graph`) is written by the
+// helper `mtg_h5` (csrc/h5_handoff.cpp, links the reference's gatb-core; sits next to this executable) from the GPU's solid k-mers
+// in DSK's layout, and completed by gatb-core itself, after the timed work; `-graph x.h5` reads dsk/solid back through the same
+// helper and rebuilds the membership structures on the GPU (mtg_load_solid). Without the helper: no <out>.h5 (a warning), and
+// -graph is an error.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <string>
 #include <vector>
@@ -25,6 +29,83 @@ static void fail(const std::string& msg) {
 }
 static void check(int rc) { if (rc != 0) fail(mtg_last_error()); }
 
+// ---- .h5 hand-off through the mtg_h5 helper (same directory as this executable)
+struct SolidHeader {   // csrc/h5_handoff.cpp MtgSolidHeader
+    char magic[8];
+    uint32_t version, kmer_size, nb_partitions, minimizer_size;
+    uint64_t n, nb_kmers_valid, nb_distinct;
+    int32_t threshold, cutoff_auto;
+};
+static std::string helper_path() {
+    char buf[4096];
+    const ssize_t n = readlink("/proc/self/exe", buf, sizeof(buf) - 1);
+    std::string dir = ".";
+    if (n > 0) { buf[n] = 0; dir = buf; const size_t s = dir.rfind('/'); dir = s == std::string::npos ? "." : dir.substr(0, s); }
+    return dir + "/mtg_h5";
+}
+static bool run_helper(const std::string& verb, const std::string& a, const std::string& b) {
+    const std::string exe = helper_path();
+    if (access(exe.c_str(), X_OK) != 0) return false;
+    const std::string cmd = "'" + exe + "' " + verb + " '" + a + "' '" + b + "' > /dev/null";
+    if (system(cmd.c_str()) != 0) fail("mtg_h5 " + verb + " failed on " + a);
+    return true;
+}
+static void write_graph_h5(mtg_ctx* g, const mtg_params& p, const std::string& h5, int nb_cores) {
+    const uint32_t nparts = 4, m = 10;   // MindTheGap's minimizer size (src/Finder.cpp:246); any partition count is valid
+    const uint64_t n = mtg_get_nb_solid(g);
+    std::vector<uint16_t> repart((size_t)1 << (2 * m));
+    std::vector<uint64_t> offs(nparts + 1), lo(n + 1), hi(n + 1), histo(10001);
+    std::vector<uint32_t> ab(n + 1);
+    check(mtg_export_dsk_partitions(g, nparts, m, repart.data(), offs.data(), lo.data(), hi.data(), ab.data(), n + 1));
+    check(mtg_get_histogram(g, histo.data()));
+    SolidHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "MTGSOLID", 8);
+    h.version = 1; h.kmer_size = (uint32_t)p.kmer_size; h.nb_partitions = nparts; h.minimizer_size = m; h.n = n;
+    for (size_t i = 1; i < histo.size(); i++) h.nb_distinct += histo[i];
+    h.threshold = mtg_get_threshold(g); h.cutoff_auto = mtg_get_cutoff_auto(g);
+    const std::string binp = h5 + ".solid.bin";
+    FILE* f = fopen(binp.c_str(), "wb");
+    if (!f) fail("Cannot open file " + binp + " for writing");
+    fwrite(&h, sizeof(h), 1, f);
+    fwrite(repart.data(), 2, repart.size(), f);
+    fwrite(offs.data(), 8, offs.size(), f);
+    fwrite(histo.data(), 8, histo.size(), f);
+    fwrite(lo.data(), 8, n, f);
+    if (p.kmer_size > 31) fwrite(hi.data(), 8, n, f);
+    fwrite(ab.data(), 4, n, f);
+    fclose(f);
+    const bool ok = run_helper("write", h5, binp);
+    remove(binp.c_str());
+    if (!ok) { fprintf(stderr, "mtg_find: helper %s not found, %s not written (build it with oracle/build_ref.sh)\n", helper_path().c_str(), h5.c_str()); return; }
+    run_helper("complete", h5, std::to_string(nb_cores));
+}
+static void load_graph_h5(mtg_ctx* g, const mtg_params& p, const std::string& h5) {
+    const std::string binp = std::string(h5) + ".solid.bin";
+    if (!run_helper("dump", h5, binp)) fail("-graph needs the mtg_h5 helper (gatb-core's HDF5 storage) next to mtg_find: " + helper_path());
+    FILE* f = fopen(binp.c_str(), "rb");
+    SolidHeader h;
+    if (!f || fread(&h, sizeof(h), 1, f) != 1) fail("Cannot read " + binp);
+    if ((int)h.kmer_size != p.kmer_size) fail("graph " + h5 + " was built with another kmer size");
+    fseek(f, (long)(sizeof(h) + 2 * ((size_t)1 << (2 * h.minimizer_size)) + 8 * (h.nb_partitions + 1) + 8 * 10001), SEEK_SET);
+    std::vector<uint64_t> lo(h.n + 1), hi(h.n + 1);
+    if (h.n && fread(lo.data(), 8, h.n, f) != h.n) fail("truncated " + binp);
+    if (h.kmer_size > 31 && h.n && fread(hi.data(), 8, h.n, f) != h.n) fail("truncated " + binp);
+    fclose(f);
+    remove(binp.c_str());
+    check(mtg_load_solid(g, lo.data(), h.kmer_size > 31 ? hi.data() : nullptr, h.n));
+}
+static int graph_kmer_size(const std::string& h5) {   // k of a gatb .h5 (Graph::load takes it from the file, src/Finder.cpp:277-278)
+    const std::string binp = h5 + ".solid.bin";
+    if (!run_helper("dump", h5, binp)) fail("-graph needs the mtg_h5 helper (gatb-core's HDF5 storage) next to mtg_find: " + helper_path());
+    FILE* f = fopen(binp.c_str(), "rb");
+    SolidHeader h;
+    if (!f || fread(&h, sizeof(h), 1, f) != 1) fail("Cannot read " + binp);
+    fclose(f);
+    remove(binp.c_str());
+    return (int)h.kmer_size;
+}
+
 static void usage() {
     fprintf(stderr,
             "mtg_find: B200 engine behind `MindTheGap find`\n"
@@ -37,6 +118,8 @@ static void usage() {
             "  -max-rep <n> [5]   -het-max-occ <n> [1]   -snp-min-val <n> [5]   -branching-filter <n> [15]\n"
             "  -homo-only -insert-only -snp-only -deletion-only -hete-only -backup -no-snp -no-insert -no-deletion -no-hetero\n"
             "  -nb-cores <host threads of the event replay> [0 = all]; -max-memory / -max-disk / -out-tmp / -verbose are accepted and ignored; -device <gpu> [0]\n"
+            "  -graph <x.h5>            use the solid k-mers of an existing gatb .h5 instead of -in (needs the mtg_h5 helper)\n"
+            "  -no-graph-out            do not write <out>.h5 (the graph file for `MindTheGap fill -graph`)\n"
             "  -host-parse: read -in on the host (kseq-style; any FASTA/FASTQ layout) instead of parsing the file bytes on the GPU (plain or .gz,\n"
             "               FASTA or 4-line FASTQ)\n");
 }
@@ -44,6 +127,7 @@ static void usage() {
 int main(int argc, char** argv) {
     std::string in, ref, out, graph, bed, amin = "auto";
     int nb_cores = 0;  // 0 = all cores (src/Finder.cpp:137)
+    bool no_graph_out = false;
     mtg_params p;
     mtg_default_params(&p);
     bool f_homo_only = false, f_insert_only = false, f_snp_only = false, f_deletion_only = false, f_hete_only = false, f_backup = false, f_host_parse = false,
@@ -75,6 +159,7 @@ int main(int argc, char** argv) {
         else if (o == "-hete-only") f_hete_only = true;
         else if (o == "-backup") f_backup = true;
         else if (o == "-host-parse") f_host_parse = true;
+        else if (o == "-no-graph-out") no_graph_out = true;
         else if (o == "-no-snp") f_no_snp = true;
         else if (o == "-no-insert") f_no_insert = true;
         else if (o == "-no-deletion") f_no_deletion = true;
@@ -85,7 +170,7 @@ int main(int argc, char** argv) {
     // mandatory-option checks (src/Finder.cpp:198-207)
     if ((!graph.empty() && !in.empty()) || (graph.empty() && in.empty()))
         fail("ERROR: options -graph and -in are incompatible, but at least one of these is mandatory");
-    if (!graph.empty()) fail("-graph needs gatb-core's HDF5 storage: read dsk/solid on the host and call mtg_load_solid (INTEGRATION.md)");
+    if (!graph.empty()) p.kmer_size = graph_kmer_size(graph);
     if (ref.empty()) fail("ERROR: option -ref is mandatory");
     if (out.empty()) {  // src/Finder.cpp:210-219
         time_t now = time(0);
@@ -116,9 +201,11 @@ int main(int argc, char** argv) {
     mtg_ctx* g = mtg_create(&p);
     if (!g) fail(mtg_last_error());
     check(mtg_set_host_threads(g, nb_cores));
-    // graph construction (was Graph::create, src/Finder.cpp:266)
-    check(mtg_count_files(g, in.c_str()));
-    check(mtg_count_finish(g));
+    // graph construction (was Graph::create, src/Finder.cpp:266) or -graph (was Graph::load, :277)
+    if (graph.empty()) {
+        check(mtg_count_files(g, in.c_str()));
+        check(mtg_count_finish(g));
+    } else load_graph_h5(g, p, graph);
     clock_gettime(CLOCK_MONOTONIC, &t1);
 
     // output files (src/Finder.cpp:287-302, header :513-541)
@@ -194,7 +281,12 @@ int main(int argc, char** argv) {
            "        Heterozygous insertions 1-2 bp size : %llu\n        SNPs                     : %llu\n",
            (unsigned long long)(c[4] + c[5]), (unsigned long long)c[9], (unsigned long long)c[10], (unsigned long long)(c[6] + c[7]));
     printf("    Time                         : %.3f s (graph %.3f s, scan %.3f s)\n", secs(t0, t2), secs(t0, t1), secs(t1, t2));
-    printf("    Output files\n        breakpoint_file          : %s\n        othervariants_file       : %s\n", bk_name.c_str(), vcf_name.c_str());
+    printf("    Output files\n");
+    if (graph.empty() && !no_graph_out) {   // <out>.h5 for `fill -graph` (src/Finder.cpp:266 writes it during the build); after the timed work here
+        write_graph_h5(g, p, out + ".h5", nb_cores);
+        printf("        graph_file               : %s.h5\n", out.c_str());
+    }
+    printf("        breakpoint_file          : %s\n        othervariants_file       : %s\n", bk_name.c_str(), vcf_name.c_str());
     mtg_destroy(g);
     return EXIT_SUCCESS;
 }

@@ -57,42 +57,124 @@ struct BloomDev {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ build kernels
-// One thread per solid k-mer: minimizer -> home bucket (graph.cuh), the bucket's key slots are read with seven 128-bit loads
-// and only the first slot seen empty is claimed with one CAS (a slot only ever goes from empty to a key, so a stale read can
-// at worst cost a failed CAS). The solid set leaves the count stage grouped by minimizer bin: neighbouring threads fill the
-// same few lines while they are resident in L2.
+// ---- exact table build (graph.cuh "Placement"): bin histogram -> bucket offsets (exclusive scan) -> insert
+// pass 1: solid k-mers per bin of range `shard` (cnt has nbps entries)
 template <class K>
-__global__ void __launch_bounds__(256) table_build_kernel(const K* __restrict__ keys, uint64_t n, K* __restrict__ table_all, GraphView<K> g,
+__global__ void __launch_bounds__(256) bin_count_kernel(const K* __restrict__ keys, uint64_t n, int k, int tm, uint32_t nshards, uint32_t nbps,
+                                                        uint32_t shard, unsigned int* __restrict__ cnt, int* __restrict__ err) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = mini_place_hash(kmer_minimizer(keys[i], k, tm));
+        if (place_shard(h, nshards) != shard) { *err = 5; continue; }   // a k-mer routed to the wrong range
+        atomicAdd(&cnt[place_bin(h, nshards, nbps)], 1u);
+    }
+}
+// pass 2: buckets per bin = ceil(cnt / BIN_KEYS_PER_BUCKET); off[i] = base + exclusive prefix sum, off[nbps] = terminator.
+// Three small kernels (tile sums, one-CTA scan of the tile sums, apply); BS_TILE bins per CTA.
+static const int BS_THREADS = 256, BS_PER = 16, BS_TILE = BS_THREADS * BS_PER;
+__device__ __forceinline__ unsigned bin_buckets(unsigned c) { return (c + BIN_KEYS_PER_BUCKET - 1) / BIN_KEYS_PER_BUCKET; }
+__device__ __forceinline__ unsigned block_exclusive_scan_u32(unsigned v, unsigned* s_warp, unsigned& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned x = v;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        unsigned t = lane < nw ? s_warp[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xFFFFFFFFu, t, o); if (lane >= o) t += y; }
+        if (lane < nw) s_warp[lane] = t;
+    }
+    __syncthreads();
+    total = s_warp[nw - 1];
+    const unsigned res = x - v + (w ? s_warp[w - 1] : 0);
+    __syncthreads();
+    return res;
+}
+__global__ void __launch_bounds__(BS_THREADS) bin_tile_sum_kernel(const unsigned int* __restrict__ cnt, uint32_t nbps, unsigned int* __restrict__ tile_sum) {
+    __shared__ unsigned s_warp[32];
+    const uint32_t base = blockIdx.x * BS_TILE + threadIdx.x * BS_PER;
+    unsigned acc = 0;
+    for (int i = 0; i < BS_PER; i++) if (base + i < nbps) acc += bin_buckets(cnt[base + i]);
+    unsigned total;
+    block_exclusive_scan_u32(acc, s_warp, total);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) bin_tile_scan_kernel(unsigned int* __restrict__ tile_sum, uint32_t ntiles, uint64_t capacity, int* __restrict__ err) {
+    __shared__ unsigned s_warp[32];
+    const uint32_t per = (ntiles + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = threadIdx.x * per, e = min(ntiles, b + per);
+    unsigned acc = 0;
+    for (uint32_t i = b; i < e; i++) acc += tile_sum[i];
+    unsigned total;
+    unsigned run = block_exclusive_scan_u32(acc, s_warp, total);
+    for (uint32_t i = b; i < e; i++) { const unsigned v = tile_sum[i]; tile_sum[i] = run; run += v; }
+    if (threadIdx.x == 0 && (uint64_t)total > capacity) *err = 6;   // the runs do not fit the range (cannot happen: capacity is an upper bound)
+}
+__global__ void __launch_bounds__(BS_THREADS) bin_offsets_kernel(const unsigned int* __restrict__ cnt, uint32_t nbps, const unsigned int* __restrict__ tile_off,
+                                                                 uint32_t base_bucket, uint32_t* __restrict__ off) {
+    __shared__ unsigned s_warp[32];
+    const uint32_t base = blockIdx.x * BS_TILE + threadIdx.x * BS_PER;
+    unsigned nbk[BS_PER], acc = 0;
+    for (int i = 0; i < BS_PER; i++) { nbk[i] = base + i < nbps ? bin_buckets(cnt[base + i]) : 0; acc += nbk[i]; }
+    unsigned total;
+    unsigned run = base_bucket + tile_off[blockIdx.x] + block_exclusive_scan_u32(acc, s_warp, total);
+    for (int i = 0; i < BS_PER; i++) {
+        if (base + i < nbps) off[base + i] = run;
+        run += nbk[i];
+        if (base + i == nbps - 1) off[nbps] = run;   // terminator of the range
+    }
+}
+// pass 3: one thread per solid k-mer. The bucket's key slots are read with seven 128-bit loads into a mask of the slots seen
+// empty; every lane then claims its first empty slot with ONE CAS per round, all lanes of the warp together (a CAS inside a
+// per-lane branch serialises the warp on the atomic's latency: 53 % of the stall samples of the first version,
+// profiles/ncu_lines_r02_v2.txt). A slot only ever goes from empty to a key, so a stale view can at worst cost a failed CAS.
+// A bin's run holds at most 10 k-mers per 14-slot bucket, so the cyclic walk always finds room.
+template <class K>
+__global__ void __launch_bounds__(256) table_build_kernel(const K* __restrict__ keys, uint64_t n, K* __restrict__ table, GraphView<K> g,
                                                           int* __restrict__ err) {
     const int SLOTS = TableCfg<K>::SLOTS, STRIDE = TableCfg<K>::STRIDE;
     const K EMPTY = ~K(0);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const K key = keys[i];
-        const uint64_t h = mini_place_hash(kmer_minimizer(key, g.k, g.tm));
-        uint64_t b = table_home_bucket<K>(h, g.nregions, g.glog, key);
-        K* table = table_all + (uint64_t)shard_of(h, g.nshards) * g.nbuckets * STRIDE;
-        bool done = false;
-        for (uint64_t probe = 0; probe < g.nbuckets && !done; probe++) {
-            K* bucket = table + b * STRIDE;
-            const uint4* q = reinterpret_cast<const uint4*>(bucket);
-            uint4 v[7];
+    const uint64_t nround = (n + 31) & ~31ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (uint64_t)gridDim.x * blockDim.x) {
+        bool pending = i < n;
+        const K key = pending ? keys[i] : K(0);
+        Chain c;
+        c.o0 = c.nb = c.b = 0;
+        uint32_t probes = 0;
+        if (pending && !chain_begin<K>(g.bin_off, g.nbps, g.nshards, key, kmer_minimizer(key, g.k, g.tm), c)) { *err = 1; pending = false; }
+        while (__any_sync(0xFFFFFFFFu, pending)) {
+            K* bucket = table + (uint64_t)c.b * STRIDE;
+            unsigned emask = 0;
+            if (pending) {
+                const uint4* q = reinterpret_cast<const uint4*>(bucket);
 #pragma unroll
-            for (int j = 0; j < 7; j++) v[j] = __ldcg(q + j);
-#pragma unroll
-            for (int s = 0; s < SLOTS; s++) {
-                if (done) break;
-                K cur;
-                if (sizeof(K) == 8) cur = make_key<K>(s & 1 ? (((uint64_t)v[s >> 1].w << 32) | v[s >> 1].z) : (((uint64_t)v[s >> 1].y << 32) | v[s >> 1].x), 0);
-                else cur = make_key<K>(((uint64_t)v[s].y << 32) | v[s].x, ((uint64_t)v[s].w << 32) | v[s].z);
-                if (cur == key) { done = true; break; }
-                if (cur == EMPTY) {
-                    cur = cas_global(&bucket[s], EMPTY, key);
-                    if (cur == EMPTY || cur == key) { done = true; break; }
+                for (int j = 0; j < 7; j++) {
+                    const uint4 v = __ldcg(q + j);
+                    const uint64_t a0 = ((uint64_t)v.y << 32) | v.x, a1 = ((uint64_t)v.w << 32) | v.z;
+                    if (sizeof(K) == 8) {
+                        if (a0 == lo64(key) || a1 == lo64(key)) pending = false;
+                        emask |= (a0 == ~0ull ? 1u : 0u) << (2 * j) | (a1 == ~0ull ? 1u : 0u) << (2 * j + 1);
+                    } else {
+                        if (a0 == lo64(key) && a1 == hi64(key)) pending = false;
+                        emask |= ((a0 == ~0ull && a1 == ~0ull) ? 1u : 0u) << j;
+                    }
+                }
+                emask &= (1u << SLOTS) - 1u;
+            }
+            while (true) {
+                const bool want = pending && emask;
+                if (!__any_sync(0xFFFFFFFFu, want)) break;
+                if (want) {
+                    const int sl = __ffs(emask) - 1;
+                    emask &= emask - 1;
+                    const K cur = cas_global(&bucket[sl], EMPTY, key);
+                    if (cur == EMPTY || cur == key) pending = false;
                 }
             }
-            b = b + 1 == g.nbuckets ? 0 : b + 1;
+            if (pending) {   // bucket full: the chain continues cyclically inside the bin's run
+                chain_next(c);
+                if (++probes > c.nb) { *err = 1; pending = false; }
+            }
         }
-        if (!done) *err = 1;
     }
 }
 
@@ -144,7 +226,7 @@ __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ key
             K hashpart = succ ? (x & kmask<K>(k - 2)) : ((x >> 4) & kmask<K>(k - 2));
             const K rev = revcomp(hashpart, k - 2);
             if (rev < hashpart) hashpart = rev;
-            const uint64_t racine = gatb_hash1(hashpart, g.seed0) % g.bloom_tai;
+            const uint64_t racine = g.bloom_tai.mod(gatb_hash1(hashpart, g.seed0));
             uint64_t off[8];
             off[0] = 0;
             for (int i = 1; i < g.bloom_nhash; i++) off[i] = simplehash16_dev(g.rnd, hashpart, i) & 4095;
@@ -196,16 +278,17 @@ __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ key
             // each in one half of the bucket
             const unsigned other = __shfl_xor_sync(0xFFFFFFFFu, adj, 1);
             const unsigned byte = succ ? (adj | (other << 4)) : (other | (adj << 4));
-            const uint64_t hx = mini_place_hash(mt.all);
-            uint64_t b = table_home_bucket<K>(hx, g.nregions, g.glog, x);
-            K* const trw = table_rw + (uint64_t)shard_of(hx, g.nshards) * g.nbuckets * TableCfg<K>::STRIDE;   // the k-mer's range
-            bool searching = active;
-            for (uint64_t probe = 0; probe < g.nbuckets; probe++) {
-                if (!__any_sync(0xFFFFFFFFu, searching)) break;
+            Chain cx;
+            cx.o0 = cx.nb = cx.b = 0;
+            bool searching = active && chain_begin<K>(g.bin_off, g.nbps, g.nshards, x, mt.all, cx);
+            if (active && !searching) *err = 4;
+            K* const trw = table_rw;
+            uint32_t walked = 0;
+            while (__any_sync(0xFFFFFFFFu, searching)) {   // warp-uniform: the shuffles below need every lane, whatever its run length
                 int slot = -1;
                 bool has_empty = false;
                 if (searching) {
-                    const uint4* q = reinterpret_cast<const uint4*>(trw + b * TableCfg<K>::STRIDE) + (succ ? 0 : 4);
+                    const uint4* q = reinterpret_cast<const uint4*>(trw + (uint64_t)cx.b * TableCfg<K>::STRIDE) + (succ ? 0 : 4);
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         if (!succ && i == 3) break;   // chunk 7 holds the adjacency bytes
@@ -227,12 +310,15 @@ __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ key
                 if (searching) {
                     const int fslot = slot >= 0 ? slot : oslot;
                     if (fslot >= 0) {
-                        if (succ) reinterpret_cast<uint8_t*>(trw + b * TableCfg<K>::STRIDE)[BUCKET_ADJ_OFFSET + fslot] = (uint8_t)byte;
+                        if (succ) reinterpret_cast<uint8_t*>(trw + (uint64_t)cx.b * TableCfg<K>::STRIDE)[BUCKET_ADJ_OFFSET + fslot] = (uint8_t)byte;
                         searching = false;
                     } else if (has_empty || oempty) {
                         *err = 4;   // a solid k-mer must be in the table
                         searching = false;
-                    } else b = b + 1 == g.nbuckets ? 0 : b + 1;
+                    } else {
+                        chain_next(cx);
+                        if (++walked > cx.nb) { *err = 4; searching = false; }
+                    }
                 }
             }
         }
@@ -270,15 +356,15 @@ __global__ void __launch_bounds__(256) dedup_kernel(const K* __restrict__ in, ui
 }
 
 template <class K>
-__global__ void __launch_bounds__(256) bloom_cache_insert_kernel(const K* __restrict__ keys, uint64_t n, uint32_t* __restrict__ bits, uint64_t tai,
+__global__ void __launch_bounds__(256) bloom_cache_insert_kernel(const K* __restrict__ keys, uint64_t n, uint32_t* __restrict__ bits, Mod tai,
                                                                  int nhash, uint64_t seed0, const uint64_t* __restrict__ rnd) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
         bloom_cache_insert<K>(bits, tai, nhash, seed0, rnd, keys[i]);
 }
 // insert keys[i] into `dst` when `probe` contains it
 template <class K>
-__global__ void __launch_bounds__(256) bloom_cascade_kernel(const K* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ probe, uint64_t probe_tai,
-                                                            uint32_t* __restrict__ dst, uint64_t dst_tai, int nhash, uint64_t seed0,
+__global__ void __launch_bounds__(256) bloom_cascade_kernel(const K* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ probe, Mod probe_tai,
+                                                            uint32_t* __restrict__ dst, Mod dst_tai, int nhash, uint64_t seed0,
                                                             const uint64_t* __restrict__ rnd) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         K x = keys[i];
@@ -287,8 +373,8 @@ __global__ void __launch_bounds__(256) bloom_cascade_kernel(const K* __restrict_
 }
 // cfp set = solid k-mers that are in B2 (i.e. T2) and in B4
 template <class K>
-__global__ void __launch_bounds__(256) cfp_set_kernel(const K* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ b2, uint64_t b2_tai,
-                                                      const uint32_t* __restrict__ b4, uint64_t b4_tai, int nhash, uint64_t seed0,
+__global__ void __launch_bounds__(256) cfp_set_kernel(const K* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ b2, Mod b2_tai,
+                                                      const uint32_t* __restrict__ b4, Mod b4_tai, int nhash, uint64_t seed0,
                                                       const uint64_t* __restrict__ rnd, K* __restrict__ out, unsigned long long* __restrict__ nout,
                                                       uint64_t cap, int* __restrict__ err) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -596,15 +682,29 @@ template <class K> class Graph : public IGraph {
     int k_;
     cudaStream_t stream_;
     DevBuf<K> table_;
-    uint64_t nbuckets_ = 0;   // buckets per range (a multiple of the region size)
-    uint64_t nregions_ = 0;   // regions per range
+    uint64_t nbuckets_ = 0;   // buckets per range (upper bound of the bins' runs: keys / 10 + bins + 1)
+    uint32_t nbps_ = 1;       // bins per range
     uint32_t nshards_ = 1;    // ranges (= GPUs that built the table)
     int tm_ = 0;              // minimizer length that places k-mers in the table
-    static const int GLOG = TableGeomCfg<K>::GLOG;
-    void set_buckets(uint64_t nkeys) {   // load factor ~0.55 over whole regions
-        const uint64_t nb = std::max<uint64_t>((uint64_t)((double)nkeys / 0.55 / TableCfg<K>::SLOTS) + 1, 1);
-        nregions_ = (nb + (1ull << GLOG) - 1) >> GLOG;
-        nbuckets_ = nregions_ << GLOG;
+    DevBuf<uint32_t> binoff_; // (nbps_ + 1) global bucket offsets per range
+    void set_geometry(uint64_t nkeys_per_range) {
+        nbps_ = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nkeys_per_range / BIN_TARGET_KEYS, 1), 0x7FFFFFFFull);
+        nbuckets_ = nkeys_per_range / BIN_KEYS_PER_BUCKET + nbps_ + 1;
+    }
+    // histogram -> offsets -> insert for the keys of range `shard` (all of them when there is one range)
+    void build_range(const K* keys, uint64_t n, uint32_t shard) {
+        if ((uint64_t)nshards_ * nbuckets_ >= 0xFFFFFFFFull) throw Error(-1, "exact table beyond 2^32 buckets");
+        DevBuf<unsigned int> cnt(nbps_);
+        cnt.zero(stream_);
+        const uint32_t ntiles = (nbps_ + BS_TILE - 1) / BS_TILE;
+        DevBuf<unsigned int> tiles(ntiles);
+        if (n) bin_count_kernel<K><<<grid_for(n), 256, 0, stream_>>>(keys, n, k_, tm_, nshards_, nbps_, shard, cnt.p, err_.p);
+        bin_tile_sum_kernel<<<ntiles, BS_THREADS, 0, stream_>>>(cnt.p, nbps_, tiles.p);
+        bin_tile_scan_kernel<<<1, 1024, 0, stream_>>>(tiles.p, ntiles, nbuckets_, err_.p);
+        bin_offsets_kernel<<<ntiles, BS_THREADS, 0, stream_>>>(cnt.p, nbps_, tiles.p, (uint32_t)(shard * nbuckets_), binoff_.p + (uint64_t)shard * (nbps_ + 1));
+        if (n) table_build_kernel<K><<<grid_for(n), 256, 0, stream_>>>(keys, n, table_.p, view(), err_.p);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches += n ? 5 : 3;
     }
     BloomDev bloom_, b2_, b3_, b4_, ref_;
     DevBuf<K> cfp_, cfp_list_, final_, crit_list_;   // cfp_: hash set (cfp_slots_ slots); cfp_list_: the same k-mers as a list
@@ -635,7 +735,7 @@ template <class K> class Graph : public IGraph {
         GraphView<K> g;
         memset(&g, 0, sizeof(g));
         g.k = k_;
-        g.table = table_.p; g.nbuckets = nbuckets_; g.nregions = nregions_; g.nshards = nshards_; g.tm = tm_; g.glog = GLOG;
+        g.table = table_.p; g.nbuckets = nbuckets_; g.bin_off = binoff_.p; g.nbps = nbps_; g.nshards = nshards_; g.tm = tm_;
         g.bloom = bloom_.bits.p; g.bloom_tai = bloom_.tai; g.bloom_nhash = bloom_.nhash;
         g.cascading = cascading_ ? 1 : 0;
         g.b2 = b2_.bits.p; g.b2_tai = b2_.tai; g.b3 = b3_.bits.p; g.b3_tai = b3_.tai; g.b4 = b4_.bits.p; g.b4_tai = b4_.tai;
@@ -682,9 +782,11 @@ public:
         ref_.init(1000, 8, stream_);
         bloom_.init(1000, 4, stream_);
         b2_.init(1000, 4, stream_); b3_.init(1000, 4, stream_); b4_.init(1000, 4, stream_);
-        set_buckets(0);
+        set_geometry(0);
         table_.alloc(nbuckets_ * TableCfg<K>::STRIDE);
         table_.fill_ff(stream_);
+        binoff_.alloc(nbps_ + 1);
+        binoff_.zero(stream_);   // every bin empty
     }
     ~Graph() override {
         if (ev_a_) cudaEventDestroy(ev_a_);
@@ -693,6 +795,19 @@ public:
         if (side_ev_) cudaEventDestroy(side_ev_);
     }
     int kmer_size() const override { return k_; }
+    // The exact table is placed by the SAME minimizer the count stage partitions by (length m, common.cuh mmer_hash): the solid
+    // set leaves the counter grouped by minimizer bin, so the k-mers of a bin fill their regions together.
+    void set_table_minimizer(int m) override { tm_ = std::max(2, std::min(std::min(m, 15), k_ - 1)); }
+    // keys of buckets [b0, b0 + nb) in table order (= grouped by region): the order the neighbour search runs in
+    DevBuf<K> ordered_;
+    uint64_t compact_range(uint64_t b0, uint64_t nb, uint64_t expect) {
+        ordered_.alloc(std::max<uint64_t>(expect, 1));
+        MTG_CUDA(cudaMemsetAsync(counters_.p + 5, 0, 8, stream_));
+        table_compact_kernel<K><<<grid_for(nb * TableCfg<K>::SLOTS), 256, 0, stream_>>>(table_.p + b0 * TableCfg<K>::STRIDE, nb, ordered_.p, counters_.p + 5);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches++;
+        return expect;
+    }
     const GraphStats& stats() const override { return st_; }
     float last_features_ms() override {
         if (features_timed_) { cudaEventSynchronize(ev_b_); cudaEventElapsedTime(&last_features_ms_, ev_a_, ev_b_); features_timed_ = false; }
@@ -723,7 +838,10 @@ public:
 
     void build(const void* d_solid, uint64_t N) override {
         build_base(d_solid, N);
-        critical(d_solid, N);
+        // the neighbour search walks the k-mers in TABLE order: a k-mer, its neighbours and the next k-mers share their region
+        compact_range(0, nbuckets_, N);
+        critical(ordered_.p, N);
+        ordered_.release();
         build_rest(d_solid, N);
     }
 
@@ -735,19 +853,16 @@ public:
         st_.nb_solid = N;
         // ---- exact table, load factor ~0.55, 128-byte buckets
         t.start();
-        set_buckets(N);
+        set_geometry(N);
         nshards_ = 1;
+        binoff_.alloc(nbps_ + 1);
         table_.alloc(nbuckets_ * TableCfg<K>::STRIDE);
         table_.fill_ff(stream_);   // empty key slots; the 16 adjacency bytes of every bucket start at zero
         MTG_CUDA(cudaMemset2DAsync(reinterpret_cast<uint8_t*>(table_.p) + BUCKET_ADJ_OFFSET, BUCKET_BYTES, 0, BUCKET_BYTES - BUCKET_ADJ_OFFSET,
                                    nbuckets_, stream_));
         adj_done_ = false;
         err_.zero(stream_);
-        if (N) {
-            table_build_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, table_.p, view(), err_.p);
-            MTG_CUDA(cudaGetLastError());
-            st_.launches++;
-        }
+        build_range(keys, N, 0);
         st_.ms_table = t.stop();
         check_err("exact table build");
         st_.nbuckets = nbuckets_;
@@ -935,19 +1050,17 @@ public:
         // ---- all ranges allocated, own range built (same load factor as the single-GPU table, from the largest share)
         t.start();
         const int STRIDE = TableCfg<K>::STRIDE;
-        set_buckets(max_share);
+        set_geometry(max_share);
         nshards_ = nshards;
+        binoff_.alloc((uint64_t)(nbps_ + 1) * nshards);
+        binoff_.zero(stream_);
         table_.alloc(nbuckets_ * nshards * STRIDE);
         K* own = table_.p + (uint64_t)shard * nbuckets_ * STRIDE;
         MTG_CUDA(cudaMemsetAsync(own, 0xFF, nbuckets_ * BUCKET_BYTES, stream_));
         MTG_CUDA(cudaMemset2DAsync(reinterpret_cast<uint8_t*>(own) + BUCKET_ADJ_OFFSET, BUCKET_BYTES, 0, BUCKET_BYTES - BUCKET_ADJ_OFFSET, nbuckets_, stream_));
         adj_done_ = false;
         err_.zero(stream_);
-        if (n_share) {
-            table_build_kernel<K><<<grid_for(n_share), 256, 0, stream_>>>(share_.p, n_share, table_.p, view(), err_.p);
-            MTG_CUDA(cudaGetLastError());
-            st_.launches++;
-        }
+        build_range(share_.p, n_share, shard);
         st_.ms_table = t.stop();
         check_err("exact table build (range)");
         st_.nbuckets = nbuckets_ * nshards;
@@ -971,7 +1084,9 @@ public:
     uint64_t shard_critical() override {
         const uint64_t total = st_.nb_solid;
         st_.nb_solid = nshare_;      // critical() writes the adjacency bytes when it is given "the whole set": here the whole range
-        critical(share_.p, nshare_);
+        compact_range((uint64_t)shard_ * nbuckets_, nbuckets_, nshare_);   // own range in table order
+        critical(ordered_.p, nshare_);
+        ordered_.release();
         st_.nb_solid = total;
         adj_done_ = false;           // the other ranges arrive through adj_unpack
         return ncrit_;
@@ -1124,13 +1239,14 @@ public:
         BloomDev* b = which == 1 ? &bloom_ : which == 2 ? &b2_ : which == 3 ? &b3_ : which == 4 ? &b4_ : nullptr;
         if (b) { *p = b->bits.p; *nbytes = b->bits.n * 4; }
         else if (which == 0) { *p = table_.p; *nbytes = nbuckets_ * nshards_ * (uint64_t)BUCKET_BYTES; }
+        else if (which == 9) { *p = binoff_.p; *nbytes = (uint64_t)(nbps_ + 1) * nshards_ * 4; }
         else if (which == 5) { *p = adjbuf_.p; *nbytes = adjbuf_.n * 16; }
         else if (which == 6) { *p = cfp_local_.p; *nbytes = ncfp_local_ * sizeof(K); }
         else if (which == 7) { *p = crit_list_.p; *nbytes = ncrit_ * sizeof(K); }
         else if (which == 8) {   // the BooPHF level built slice-wise last: nshards equal slices, slice `shard` filled
             if (!mphf_sliced_ || !mphf_n_) { *p = mphf_bits_.p; *nbytes = 0; }
             else { *p = mphf_bits_.p + mphf_off_[mphf_sliced_ - 1]; *nbytes = mphf_slice_words(mphf_sliced_ - 1) * mphf_pad_ * 8; }
-        } else throw Error(-1, "buffer: which 0..8");
+        } else throw Error(-1, "buffer: which 0..9");
     }
     void or_chunks(const void* d_in, uint32_t nchunks, uint64_t nwords, void* d_out) override {
         if (!nwords) return;

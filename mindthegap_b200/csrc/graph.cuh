@@ -9,6 +9,19 @@
 
 namespace mtg {
 
+// x % d for a divisor fixed on the host: one multiply-high by the precomputed floor((2^64-1)/d) and a correction loop (at most a
+// few subtractions) instead of the ~100-instruction 64-bit division. GATB's Bloom positions are hash % size (Bloom.hpp:468-489).
+struct Mod {
+    uint64_t d, inv;
+    Mod() = default;
+    __host__ __device__ Mod(uint64_t d_) : d(d_), inv(d_ ? ~0ull / d_ : 0) {}
+    __device__ __forceinline__ uint64_t mod(uint64_t x) const {
+        uint64_t r = x - __umul64hi(x, inv) * d;
+        while (r >= d) r -= d;
+        return r;
+    }
+};
+
 static const int MPHF_LEVELS = 25;  // BooPHF: _nb_levels = 25 (thirdparty/BooPHF/BooPHF.h:1026)
 
 // POD view passed by value to kernels.
@@ -17,21 +30,25 @@ template <class K> struct GraphView {
     // exact table: nbuckets buckets of 128 bytes (14 u64 keys or 7 u128 keys + 16 adjacency bytes); empty slot = all ones
     // With N GPUs the table is `nshards` equal ranges of `nbuckets` buckets: range r is built by rank r from the solid k-mers
     // whose hash selects it (shard_of) and the ranges are all-gathered; one range on a single GPU.
-    // Placement (ours): buckets are grouped in REGIONS of 2^glog consecutive buckets; a k-mer's region is chosen by the hash of
-    // its random-order minimizer (length tm, common.cuh), the bucket inside the region by the k-mer's own hash, overflow goes to
-    // the following buckets. Consecutive k-mers of a sequence and the neighbours of a k-mer share their minimizer, so they sit
-    // in the same few 128-byte lines: building, the critical-FP search and the reference scan touch a line once, not per k-mer.
+    // Placement (ours): every k-mer belongs to a BIN chosen by the hash of its random-order minimizer (length tm, common.cuh;
+    // the same minimizer the count stage partitions by). A bin owns a RUN of consecutive buckets sized from the number of solid
+    // k-mers it holds (10 per 14-slot bucket): bin_off[] gives the first bucket of every bin. Inside its run a k-mer starts at the
+    // bucket its own hash selects and overflows cyclically within the run. Consecutive k-mers of a sequence and the neighbours
+    // of a k-mer share their minimizer, so they sit in the same one or two 128-byte lines; a heavy minimizer (repeats,
+    // low-complexity sequence) only gets a longer run, chains never cross bins, and an empty bin answers "absent" without
+    // touching the table. With N GPUs range r holds the bins of rank r; bin_off has one terminator per range.
     const K* table;
-    uint64_t nbuckets;     // per range, a multiple of 2^glog
-    uint64_t nregions;     // per range
+    uint64_t nbuckets;        // per range
+    const uint32_t* bin_off;  // (nbps + 1) entries per range: GLOBAL bucket index of the first bucket of each bin of the range
+    uint32_t nbps;            // bins per range
     uint32_t nshards;
-    int tm, glog;
+    int tm;
     // Bloom filters as little-endian u32 words (bit pos -> word pos>>5, bit pos&31 == byte pos>>3, bit pos&7)
-    const uint32_t* bloom; uint64_t bloom_tai; int bloom_nhash;      // BloomNeighborCoherent (main)
+    const uint32_t* bloom; Mod bloom_tai; int bloom_nhash;      // BloomNeighborCoherent (main)
     int cascading;                                                   // 0 -> cFP is the plain sorted set `cfp`
-    const uint32_t* b2; uint64_t b2_tai;                             // BloomCacheCoherent x3
-    const uint32_t* b3; uint64_t b3_tai;
-    const uint32_t* b4; uint64_t b4_tai;
+    const uint32_t* b2; Mod b2_tai;                             // BloomCacheCoherent x3
+    const uint32_t* b3; Mod b3_tai;
+    const uint32_t* b4; Mod b4_tai;
     int casc_nhash;
     const K* cfp; uint64_t ncfp;                                     // exact set, open addressing over ncfp_slots (power of two) slots, empty = all ones
     uint64_t cfp_slots;
@@ -43,7 +60,7 @@ template <class K> struct GraphView {
     uint64_t mphf_dom[MPHF_LEVELS];   // hash domain of each level
     const K* mphf_final; uint64_t nfinal;  // sorted (practically always empty)
     // reference repeat Bloom (BloomCacheCoherent over canonical (k-1)-mers)
-    const uint32_t* refbloom; uint64_t ref_tai; int ref_nhash;
+    const uint32_t* refbloom; Mod ref_tai; int ref_nhash;
     // hash constants
     uint64_t seed0;               // HashFunctors seed_tab[0]
     const uint64_t* rnd;          // random_values[256]
@@ -71,17 +88,17 @@ MTG_D uint64_t simplehash16_dev(const uint64_t* __restrict__ rnd, u128 key128, i
 MTG_D bool bit_get(const uint32_t* __restrict__ bits, uint64_t pos) { return (__ldg(bits + (pos >> 5)) >> (pos & 31)) & 1u; }
 
 // BloomCacheCoherent::contains (Bloom.hpp:468-489)
-template <class K> MTG_D bool bloom_cache_contains(const uint32_t* __restrict__ bits, uint64_t tai, int nhash, uint64_t seed0,
+template <class K> MTG_D bool bloom_cache_contains(const uint32_t* __restrict__ bits, Mod tai, int nhash, uint64_t seed0,
                                                    const uint64_t* __restrict__ rnd, K item) {
-    uint64_t h0 = gatb_hash1(item, seed0) % tai;
+    uint64_t h0 = tai.mod(gatb_hash1(item, seed0));
     if (!bit_get(bits, h0)) return false;
     for (int i = 1; i < nhash; i++)
         if (!bit_get(bits, h0 + (simplehash16_dev(rnd, item, i) & 4095))) return false;
     return true;
 }
-template <class K> MTG_D void bloom_cache_insert(uint32_t* __restrict__ bits, uint64_t tai, int nhash, uint64_t seed0,
+template <class K> MTG_D void bloom_cache_insert(uint32_t* __restrict__ bits, Mod tai, int nhash, uint64_t seed0,
                                                  const uint64_t* __restrict__ rnd, K item) {
-    uint64_t h0 = gatb_hash1(item, seed0) % tai;
+    uint64_t h0 = tai.mod(gatb_hash1(item, seed0));
     atomicOr(bits + (h0 >> 5), 1u << (h0 & 31));
     for (int i = 1; i < nhash; i++) {
         uint64_t h = h0 + (simplehash16_dev(rnd, item, i) & 4095);
@@ -95,7 +112,7 @@ MTG_D unsigned cano2_dev(unsigned i) {
                          (8ull << 32) | (9ull << 36) | (0ull << 40) | (4ull << 44) | (9ull << 48) | (13ull << 52) | (1ull << 56) | (5ull << 60);
     return (unsigned)((tab >> (4 * i)) & 15);
 }
-template <class K> MTG_D void bloom_neighbor_positions(int k, uint64_t tai, int nhash, uint64_t seed0, const uint64_t* __restrict__ rnd,
+template <class K> MTG_D void bloom_neighbor_positions(int k, Mod tai, int nhash, uint64_t seed0, const uint64_t* __restrict__ rnd,
                                                        K item, uint64_t* h) {
     unsigned suffix = (unsigned)(item & 3);
     unsigned prefix = (unsigned)((item >> (2 * (k - 1))) & 3) << 2;
@@ -103,7 +120,7 @@ template <class K> MTG_D void bloom_neighbor_positions(int k, uint64_t tai, int 
     K hashpart = (item >> 2) & kmask<K>(k - 2);
     K rev = revcomp(hashpart, k - 2);
     if (rev < hashpart) hashpart = rev;
-    uint64_t racine = gatb_hash1(hashpart, seed0) % tai;
+    uint64_t racine = tai.mod(gatb_hash1(hashpart, seed0));
     h[0] = racine + pref_val;
     for (int i = 1; i < nhash; i++) h[i] = h[0] + (simplehash16_dev(rnd, hashpart, i) & 4095);
 }
@@ -214,56 +231,69 @@ template <class K> struct TableCfg { static const int SLOTS = BUCKET_KEY_BYTES /
 // Probe by one thread: the whole 128-byte bucket with eight 128-bit loads (one line, 4 sectors). Returns the slot of
 // `key` in [0, SLOTS) (and the bucket in *bucket_out) or -1; *adj receives the adjacency byte of the slot.
 MTG_HD uint32_t shard_of(uint64_t h, uint32_t nshards) { return (uint32_t)(((h >> 32) * (uint64_t)nshards) >> 32); }
-template <class K> struct TableGeomCfg { static const int GLOG = sizeof(K) == 8 ? 1 : 3; };   // region = 2 x 14 (u64) or 8 x 7 (u128) slots
-MTG_HD int table_minimizer_len(int k) { return k - 1 < 15 ? k - 1 : 15; }
-// placement hash of a minimizer value: top 32 bits select the range (GPU), low 32 bits the region inside the range
+MTG_HD int table_minimizer_len(int k) { return k - 1 < 15 ? k - 1 : 15; }   // default when no counter dictates it (loaded solid sets)
+static const int BIN_KEYS_PER_BUCKET = 10;   // run length of a bin = ceil(keys / 10) buckets of 14 (7) slots: a run is never full
+static const int BIN_TARGET_KEYS = 12;       // bins per range = keys / 12 (+1)
+// placement hash of a minimizer value: its top 32 bits select the range (GPU) and, with the remainder, the bin inside the range
 MTG_HD uint64_t mini_place_hash(uint32_t mini) { return mix64((uint64_t)mini + 0x632BE59BD9B4E019ULL); }
-template <class K> MTG_HD uint64_t table_home_bucket(uint64_t h, uint64_t nregions, int glog, K key) {
-    const uint64_t region = ((h & 0xFFFFFFFFull) * nregions) >> 32;
-    return (region << glog) | (uint64_t)(key_hash32(key) & ((1u << glog) - 1u));
+MTG_HD uint32_t place_shard(uint64_t h, uint32_t nshards) { return shard_of(h, nshards); }
+MTG_HD uint32_t place_bin(uint64_t h, uint32_t nshards, uint32_t nbps) {   // bin inside its range
+    const uint32_t frac = (uint32_t)((h >> 32) * (uint64_t)nshards);
+    return (uint32_t)(((uint64_t)frac * nbps) >> 32);
 }
-// `mini` = kmer_minimizer(key, k, tm) (callers that roll it pass it in)
-template <class K> MTG_D int table_find(const K* __restrict__ table, uint64_t nbuckets, uint64_t nregions, uint32_t nshards, int glog, K key, uint32_t mini,
-                                        uint64_t* bucket_out, unsigned* adj) {
+// the run of buckets of a key's bin and the bucket the key starts at
+struct Chain { uint32_t o0, nb, b; };
+template <class K> MTG_D bool chain_begin(const uint32_t* __restrict__ bin_off, uint32_t nbps, uint32_t nshards, K key, uint32_t mini, Chain& c) {
     const uint64_t h = mini_place_hash(mini);
-    uint64_t b = table_home_bucket<K>(h, nregions, glog, key);
-    table += (uint64_t)shard_of(h, nshards) * nbuckets * TableCfg<K>::STRIDE;   // linear probing stays inside the key's range
-    for (uint64_t probe = 0; probe < nbuckets; probe++) {
-        const uint4* q = reinterpret_cast<const uint4*>(table + b * TableCfg<K>::STRIDE);
+    const uint32_t idx = place_shard(h, nshards) * (nbps + 1) + place_bin(h, nshards, nbps);
+    c.o0 = __ldg(bin_off + idx);
+    c.nb = __ldg(bin_off + idx + 1) - c.o0;
+    c.b = c.o0 + (uint32_t)(((uint64_t)key_hash32(key) * c.nb) >> 32);
+    return c.nb != 0;
+}
+MTG_D void chain_next(Chain& c) { c.b = c.b + 1 == c.o0 + c.nb ? c.o0 : c.b + 1; }
+
+// `mini` = kmer_minimizer(key, k, tm) (callers that roll it pass it in). Returns the slot or -1; *bucket_out = global bucket.
+template <class K> MTG_D int table_find(const K* __restrict__ table, const uint32_t* __restrict__ bin_off, uint32_t nbps, uint32_t nshards, K key, uint32_t mini,
+                                        uint64_t* bucket_out, unsigned* adj) {
+    Chain c;
+    if (!chain_begin<K>(bin_off, nbps, nshards, key, mini, c)) return -1;
+    // Slots of a bucket fill in ascending order (every builder claims the lowest slot it sees empty and a slot never empties),
+    // so "the bucket has an empty slot" == "its last slot is empty": the chain ends there.
+    const uint32_t k0 = (uint32_t)lo64(key), k1 = (uint32_t)(lo64(key) >> 32), k2 = (uint32_t)hi64(key), k3 = (uint32_t)(hi64(key) >> 32);
+    for (uint32_t probe = 0; probe < c.nb; probe++) {
+        const uint4* q = reinterpret_cast<const uint4*>(table + (uint64_t)c.b * TableCfg<K>::STRIDE);
         uint4 v[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = __ldg(q + i);
-        bool has_empty = false;
         int slot = -1;
 #pragma unroll
         for (int i = 0; i < 7; i++) {
-            const uint64_t a0 = ((uint64_t)v[i].y << 32) | v[i].x, a1 = ((uint64_t)v[i].w << 32) | v[i].z;
             if (sizeof(K) == 8) {
-                if (a0 == lo64(key)) slot = 2 * i;
-                if (a1 == lo64(key)) slot = 2 * i + 1;
-                has_empty |= (a0 == ~0ull) | (a1 == ~0ull);
+                if (((v[i].x ^ k0) | (v[i].y ^ k1)) == 0) slot = 2 * i;
+                if (((v[i].z ^ k0) | (v[i].w ^ k1)) == 0) slot = 2 * i + 1;
             } else {
-                if ((a0 == lo64(key)) & (a1 == hi64(key))) slot = i;
-                has_empty |= (a0 == ~0ull) & (a1 == ~0ull);
+                if (((v[i].x ^ k0) | (v[i].y ^ k1) | (v[i].z ^ k2) | (v[i].w ^ k3)) == 0) slot = i;
             }
         }
+        const bool has_empty = sizeof(K) == 8 ? (v[6].z & v[6].w) == 0xFFFFFFFFu : (v[6].x & v[6].y & v[6].z & v[6].w) == 0xFFFFFFFFu;
         if (slot >= 0) {
             const unsigned w = (slot >> 2) == 0 ? v[7].x : (slot >> 2) == 1 ? v[7].y : (slot >> 2) == 2 ? v[7].z : v[7].w;
             if (adj) *adj = (w >> (8 * (slot & 3))) & 0xFFu;
-            if (bucket_out) *bucket_out = (uint64_t)shard_of(h, nshards) * nbuckets + b;
+            if (bucket_out) *bucket_out = c.b;
             return slot;
         }
         if (has_empty) return -1;
-        b = b + 1 == nbuckets ? 0 : b + 1;
+        chain_next(c);
     }
     return -1;
 }
 template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key, uint32_t mini) {
-    return table_find<K>(g.table, g.nbuckets, g.nregions, g.nshards, g.glog, key, mini, nullptr, nullptr) >= 0;
+    return table_find<K>(g.table, g.bin_off, g.nbps, g.nshards, key, mini, nullptr, nullptr) >= 0;
 }
 template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key) { return table_contains(g, key, kmer_minimizer(key, g.k, g.tm)); }
 template <class K> MTG_D bool table_lookup(const GraphView<K>& g, K key, unsigned& adj) {
-    return table_find<K>(g.table, g.nbuckets, g.nregions, g.nshards, g.glog, key, kmer_minimizer(key, g.k, g.tm), nullptr, &adj) >= 0;
+    return table_find<K>(g.table, g.bin_off, g.nbps, g.nshards, key, kmer_minimizer(key, g.k, g.tm), nullptr, &adj) >= 0;
 }
 
 // Graph::contains for a CANONICAL k-mer. *used_fallback is set when the exact table missed and the Bloom emulation
@@ -324,6 +354,7 @@ class IGraph {
 public:
     virtual ~IGraph() {}
     virtual int kmer_size() const = 0;
+    virtual void set_table_minimizer(int m) = 0;   // before build / partition_keys / shard_begin; every GPU of a build uses the same m
     // build everything from the solid set (device array of K, not necessarily sorted)
     virtual void build(const void* d_solid_keys, uint64_t n) = 0;
     virtual void build_from_host(const uint64_t* lo, const uint64_t* hi, uint64_t n) = 0;
@@ -355,7 +386,8 @@ public:
     virtual void shard_mphf_level(int level) = 0;               // optional: BooPHF level 0, then 1, slice-wise (buffer 8 all-gathered after each)
     virtual void shard_mphf_begin() = 0;                        // optional: BooPHF levels queued on a side stream (overlaps the next steps)
     virtual void shard_finish() = 0;                            // BooPHF levels from the gathered table; graph ready
-    // which: 0 table, 1 main Bloom, 2..4 B2..B4, 5 adjacency bytes, 6 local cFP list, 7 critical share, 8 slice-wise BooPHF level; device pointer + bytes
+    // which: 0 table, 1 main Bloom, 2..4 B2..B4, 5 adjacency bytes, 6 local cFP list, 7 critical share, 8 slice-wise BooPHF level,
+    // 9 bin offsets (one equal part per range, own part filled by shard_begin: all-gather in place like the table); device pointer + bytes
     virtual void buffer(int which, void** p, uint64_t* nbytes) = 0;
     // out[i] = OR over c of in[c * nwords + i] (64-bit words): the reduction of an OR-reduce-scatter
     virtual void or_chunks(const void* d_in, uint32_t nchunks, uint64_t nwords, void* d_out) = 0;

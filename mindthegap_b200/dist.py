@@ -343,6 +343,9 @@ class DistFind:
         e.graph_shard_begin(share, n_share, self.nb_solid, max(shares), W, self.rank)
         table = e.graph_buffer(0)
         self._all_gather_ranges(table)
+        binoff = e.graph_buffer(9)              # bucket offsets of every range's bins (the table's index)
+        if binoff.numel():
+            self._all_gather_ranges(binoff)
         bloom = e.graph_buffer(1)
         self._or_reduce(bloom)
         self.exchange_bytes["allgather_table"] = int(table.numel())

@@ -44,4 +44,12 @@ for tool in "$HERE"/ref_tools/*.cpp; do
   g++ -O2 -std=c++11 -DNDEBUG -D_FILE_OFFSET_BITS=64 -w $INC "$tool" -o "$OUT/bin/$(basename "$tool" .cpp)" \
       ext/gatb-core/lib/Release/libgatbcore.a ext/gatb-core/lib/Release/libhdf5.a -ldl -lpthread -lz -lm
 done
+# the product's .h5 hand-off host tool (mindthegap_b200/csrc/h5_handoff.cpp) links the reference's gatb-core / HDF5 for the file I/O
+H5TOOL="$HERE/../mindthegap_b200/csrc/h5_handoff.cpp"
+H5EXE="$HERE/../mindthegap_b200/_build/mtg_h5"
+if [ -f "$H5TOOL" ] && { [ ! -x "$H5EXE" ] || [ "$H5TOOL" -nt "$H5EXE" ]; }; then
+  mkdir -p "$(dirname "$H5EXE")"
+  g++ -O2 -std=c++11 -DNDEBUG -D_FILE_OFFSET_BITS=64 -w $INC "$H5TOOL" -o "$H5EXE" \
+      ext/gatb-core/lib/Release/libgatbcore.a ext/gatb-core/lib/Release/libhdf5.a -ldl -lpthread -lz -lm
+fi
 echo "build_ref: done -> $OUT/bin/MindTheGap"

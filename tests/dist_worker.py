@@ -165,7 +165,7 @@ class FakeEngine:
         self.nbits = nbits
 
     def graph_buffer(self, which):
-        return self.buf[which]
+        return self.buf[which] if which in self.buf else torch.empty(0, dtype=torch.uint8)   # 9 = bin offsets: the fake table has none
 
     def _cands_of(self, r):
         sh = self._all[self._owner(self._all, self.W) == r]

@@ -324,6 +324,48 @@ def test_cpp_cli_mtg_find(tmp_path, name):
     assert r.returncode == 1 and "EXCEPTION: ERROR: option -ref is mandatory" in r.stdout
 
 
+def test_h5_handoff_gpu_solid_set_feeds_unmodified_fill_and_find(tmp_path):
+    """SURVEY 8f row 1 executed: `mtg_find` leaves <out>.h5 (GPU-counted solid k-mers in DSK's layout, written and completed by
+    gatb-core through the mtg_h5 helper); the UNMODIFIED reference then runs `fill -graph` on it and assembles exactly the insertions it
+    assembles from its own graph (test/simple_full_test.sh:123-163), `find -graph` prints the gold files, and `mtg_find -graph` reads
+    the reference's own .h5 back."""
+    import subprocess
+    from tests.cases import ROOT
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "bin", "MindTheGap")
+    helper = os.path.join(ROOT, "mindthegap_b200", "_build", "mtg_h5")
+    if not (os.path.exists(ref_bin) and os.path.exists(helper)):
+        pytest.skip("oracle/_ref or the mtg_h5 helper is not built")
+    reads, ref = case_paths(CASES["full"])
+    exe = os.path.join(ROOT, "mindthegap_b200", "_build", "mtg_find")
+    gpu = str(tmp_path / "gpu")
+    r = subprocess.run([exe, "find", "-in", reads, "-ref", ref, "-out", gpu, "-nb-cores", "2"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and os.path.exists(gpu + ".h5"), r.stdout + r.stderr
+    gold_bk = open(os.path.join(GOLD, "full", "gold.breakpoints")).read()
+    assert open(gpu + ".breakpoints").read() == gold_bk
+    own = str(tmp_path / "own")
+    r = subprocess.run([ref_bin, "find", "-in", reads, "-ref", ref, "-out", own, "-nb-cores", "2"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0
+    # unmodified `find -graph` on the GPU-made graph file
+    r = subprocess.run([ref_bin, "find", "-graph", gpu + ".h5", "-ref", ref, "-out", str(tmp_path / "again")], cwd=tmp_path, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and open(str(tmp_path / "again.breakpoints")).read() == gold_bk
+    # unmodified `fill -graph`: same insertions from both graph files
+    res = {}
+    for tag, graph in (("ref", own + ".h5"), ("gpu", gpu + ".h5")):
+        out = str(tmp_path / ("fill_" + tag))
+        r = subprocess.run([ref_bin, "fill", "-graph", graph, "-bkpt", own + ".breakpoints", "-out", out, "-nb-cores", "2"], cwd=tmp_path,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+        res[tag] = open(out + ".insertions.fasta").read()
+    assert res["gpu"] == res["ref"] and len(res["ref"]) > 0
+    # mtg_find -graph on the reference's own .h5 (was Graph::load, src/Finder.cpp:277)
+    r = subprocess.run([exe, "find", "-graph", own + ".h5", "-ref", ref, "-out", str(tmp_path / "g2")], cwd=tmp_path, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(str(tmp_path / "g2.breakpoints")).read() == gold_bk
+    assert "".join(l for l in open(str(tmp_path / "g2.othervariants.vcf")) if not l.startswith("#")) == expected("full")[1]
+
+
 def _dist_worker_script():
     return """
 import json, os, sys

@@ -3,11 +3,11 @@ set -x
 V=${V:-r02_v1}
 CFG=${CFG:-cfg3}
 if [ -z "$NOTEST" ]; then
-timeout ${TEST_TIMEOUT:-1500} python -m pytest tests -m gpu -q ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu_$V.log 2>&1; echo "pytest rc=$?"
+timeout ${TEST_TIMEOUT:-600} python -m pytest tests -m gpu -q --timeout=${PER_TEST_TIMEOUT:-200} --timeout-method=thread ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu_$V.log 2>&1; echo "pytest rc=$?"
 tail -25 gpurun_out/pytest_gpu_$V.log
 fi
 if [ -z "$NOBENCH" ]; then
-timeout 1200 python bench.py --config $CFG ${BENCH_ARGS:-} > gpurun_out/bench_$V.json 2> gpurun_out/bench_$V.err; echo "bench rc=$?"
+timeout ${BENCH_TIMEOUT:-500} python bench.py --config $CFG ${BENCH_ARGS:-} > gpurun_out/bench_$V.json 2> gpurun_out/bench_$V.err; echo "bench rc=$?"
 tail -5 gpurun_out/bench_$V.err
 python - <<PY
 import json
