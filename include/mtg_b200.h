@@ -145,8 +145,22 @@ int mtg_graph_shard_cascade(mtg_ctx* ctx, int step, uint64_t ncrit_total, uint64
 int mtg_graph_set_cfp(mtg_ctx* ctx, const void* d_all, uint64_t n);
 int mtg_graph_shard_mphf_level(mtg_ctx* ctx, int32_t level);
 int mtg_graph_shard_mphf_begin(mtg_ctx* ctx);
+/* BooPHF (BooPHF.h:736-905) in EXCHANGE mode, instead of mtg_graph_shard_mphf_level: every rank hashes only the k-mers of its own
+ * table range. plan: number of exchanged levels (*nlevels) and the per-destination capacity of each (64-bit entries). Per level:
+ * step(level, 0) routes the level positions of the surviving own k-mers into buffer 10 (nshards segments of caps[level] entries,
+ * sentinel-padded) -> all-to-all into buffer 11 (equal segments) -> step(level, 1) sets the bits of the own slice of the level
+ * (buffer 8) and clears collided ones -> all-gather buffer 8 in place -> step(level, 2) keeps the own k-mers whose bit was cleared.
+ * After the last level buffer 12 = [count | survivors] -> all-gather -> mtg_graph_shard_mphf_tail(gathered) finishes the remaining
+ * levels on the host (a few thousand k-mers). Only the tail synchronises; order the collectives on mtg_get_stream(ctx). */
+int mtg_graph_shard_mphf_plan(mtg_ctx* ctx, uint64_t* caps, int32_t max_levels, int32_t* nlevels);
+int mtg_graph_shard_mphf_step(mtg_ctx* ctx, int32_t level, int32_t phase);
+int mtg_graph_shard_mphf_tail(mtg_ctx* ctx, const void* d_gathered);
+/* The CUDA stream (cudaStream_t) every kernel of this context is launched on: collectives of a multi-GPU host (NCCL) issued on
+ * it are ordered with the library's kernels without host synchronisation. */
+void* mtg_get_stream(mtg_ctx* ctx);
 int mtg_graph_shard_finish(mtg_ctx* ctx);
-/* which: 0 exact table (all ranges), 1 main Bloom, 2..4 B2..B4, 5 adjacency bytes, 6 local cFP part, 7 critical share,
+/* (9 = bin offsets of the exact table, all-gathered in place right after the table; 10/11/12 = BooPHF exchange buffers, above.)
+ * which: 0 exact table (all ranges), 1 main Bloom, 2..4 B2..B4, 5 adjacency bytes, 6 local cFP part, 7 critical share,
  * 8 the BooPHF level built slice-wise last;
  * device pointer and byte size, valid until the next build call on this context */
 int mtg_graph_buffer(mtg_ctx* ctx, int which, void** d_ptr, uint64_t* nbytes);

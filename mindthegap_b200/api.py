@@ -44,7 +44,7 @@ EXPORTS = [
     "mtg_count_run", "mtg_count_filter", "mtg_solid_copy", "mtg_graph_build_device", "mtg_sequence_features_device2", "mtg_replay_sequence",
     "mtg_graph_build_begin", "mtg_graph_critical", "mtg_graph_critical_copy", "mtg_graph_build_end", "mtg_set_host_threads", "mtg_set_minimizer_size", "mtg_get_minimizer_size",
     "mtg_solid_partition", "mtg_partition_keys", "mtg_graph_shard_begin", "mtg_graph_shard_critical", "mtg_graph_adj_pack", "mtg_graph_adj_unpack",
-    "mtg_graph_branching", "mtg_export_dsk_partitions", "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_mphf_level", "mtg_graph_shard_mphf_begin", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
+    "mtg_graph_branching", "mtg_export_dsk_partitions", "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_mphf_level", "mtg_graph_shard_mphf_begin", "mtg_graph_shard_mphf_plan", "mtg_graph_shard_mphf_step", "mtg_graph_shard_mphf_tail", "mtg_get_stream", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
 ]
 
 _lib = None
@@ -142,6 +142,11 @@ def load_library():
     L.mtg_graph_shard_finish.argtypes = [vp]
     L.mtg_graph_shard_mphf_begin.argtypes = [vp]
     L.mtg_graph_shard_mphf_level.argtypes = [vp, C.c_int32]
+    L.mtg_graph_shard_mphf_plan.argtypes = [vp, u64p, C.c_int32, C.POINTER(C.c_int32)]
+    L.mtg_graph_shard_mphf_step.argtypes = [vp, C.c_int32, C.c_int32]
+    L.mtg_graph_shard_mphf_tail.argtypes = [vp, vp]
+    L.mtg_get_stream.restype = C.c_void_p
+    L.mtg_get_stream.argtypes = [vp]
     L.mtg_graph_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.mtg_or_chunks.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp]
     L.mtg_sequence_features_device2.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, u64p]
@@ -611,6 +616,21 @@ class Finder:
 
     def graph_shard_mphf_level(self, level):
         self._check(self.L.mtg_graph_shard_mphf_level(self.ctx, int(level)))
+
+    def graph_shard_mphf_plan(self, max_levels=24):
+        caps = np.zeros(32, dtype=np.uint64)
+        n = C.c_int32()
+        self._check(self.L.mtg_graph_shard_mphf_plan(self.ctx, caps, int(max_levels), C.byref(n)))
+        return [int(c) for c in caps[:n.value]]
+
+    def graph_shard_mphf_step(self, level, phase):
+        self._check(self.L.mtg_graph_shard_mphf_step(self.ctx, int(level), int(phase)))
+
+    def graph_shard_mphf_tail(self, gathered_t):
+        self._check(self.L.mtg_graph_shard_mphf_tail(self.ctx, C.c_void_p(gathered_t.data_ptr())))
+
+    def stream_ptr(self):
+        return self.L.mtg_get_stream(self.ctx)
 
     def graph_shard_mphf_begin(self):
         self._check(self.L.mtg_graph_shard_mphf_begin(self.ctx))

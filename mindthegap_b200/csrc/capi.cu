@@ -552,6 +552,20 @@ int mtg_graph_shard_cascade(mtg_ctx* ctx, int step, uint64_t ncrit_total, uint64
 }
 int mtg_graph_set_cfp(mtg_ctx* ctx, const void* d_all, uint64_t n) { MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->set_cfp(d_all, n); MTG_CATCH }
 int mtg_graph_shard_mphf_level(mtg_ctx* ctx, int32_t level) { MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->shard_mphf_level(level); MTG_CATCH }
+int mtg_graph_shard_mphf_plan(mtg_ctx* ctx, uint64_t* caps, int32_t max_levels, int32_t* nlevels) {
+    MTG_TRY(ctx) WallTimer w(ctx->wall_finish); const int n = ctx->graph->shard_mphf_plan(caps, max_levels); if (nlevels) *nlevels = n; MTG_CATCH
+}
+int mtg_graph_shard_mphf_step(mtg_ctx* ctx, int32_t level, int32_t phase) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_finish);
+    if (phase == 0) ctx->graph->shard_mphf_route(level);
+    else if (phase == 1) ctx->graph->shard_mphf_apply(level);
+    else if (phase == 2) ctx->graph->shard_mphf_next(level);
+    else throw Error(-1, "mtg_graph_shard_mphf_step: phase 0..2");
+    MTG_CATCH
+}
+int mtg_graph_shard_mphf_tail(mtg_ctx* ctx, const void* d_gathered) { MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->shard_mphf_tail(d_gathered); MTG_CATCH }
+void* mtg_get_stream(mtg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int mtg_graph_shard_mphf_begin(mtg_ctx* ctx) { MTG_TRY(ctx) WallTimer w(ctx->wall_finish); ctx->graph->shard_mphf_begin(); MTG_CATCH }
 int mtg_graph_shard_finish(mtg_ctx* ctx) {
     MTG_TRY(ctx)

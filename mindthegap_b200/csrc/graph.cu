@@ -421,6 +421,69 @@ __global__ void __launch_bounds__(256) mphf_level_kernel(const K* __restrict__ k
         if (old & m) atomicOr(coll + (p >> 6), m);
     }
 }
+// ---- BooPHF on N GPUs, exchange mode: every rank hashes only ITS OWN k-mers (the share of its table range). Level positions are
+// routed to the rank that owns the slice of the level's bit array they fall into (fixed-capacity segments, one per destination,
+// padded with a sentinel: positions are uniform, so the counts concentrate and no size exchange is needed), the owner sets the bits
+// and resolves the collisions of its slice, the slices are all-gathered, and every rank keeps the survivors among its own k-mers.
+static const int MR_THREADS = 256, MR_PER = 4, MR_TILE = MR_THREADS * MR_PER, MR_MAX = 64;
+template <class K>
+__global__ void __launch_bounds__(MR_THREADS) mphf_route_kernel(const K* __restrict__ keys, const unsigned long long* __restrict__ n_ptr, int level, uint64_t dom,
+                                                                uint64_t seed, uint64_t slice_bits, uint32_t nshards, uint64_t cap,
+                                                                unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ send,
+                                                                int* __restrict__ err) {
+    __shared__ unsigned int s_cnt[MR_MAX];
+    __shared__ unsigned long long s_base[MR_MAX];
+    const uint64_t n = *n_ptr;
+    const int lane = threadIdx.x & 31;
+    const uint64_t ntiles = (n + MR_TILE - 1) / MR_TILE;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x < MR_MAX) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        unsigned long long pos[MR_PER];
+        uint32_t rank_in[MR_PER], dest[MR_PER];
+#pragma unroll
+        for (int j = 0; j < MR_PER; j++) {
+            const uint64_t i = tile * MR_TILE + (uint64_t)j * MR_THREADS + threadIdx.x;
+            dest[j] = 0xFFFFFFFFu; pos[j] = 0;
+            if (i < n) {
+                MphfState st;
+                st.init(keys[i], seed);
+                uint64_t h = 0;
+                for (int l = 0; l <= level; l++) h = st.level_hash(l);
+                const uint64_t p = h % dom;
+                dest[j] = (uint32_t)(p / slice_bits);
+                pos[j] = p - (uint64_t)dest[j] * slice_bits;
+            }
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dest[j]);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (dest[j] != 0xFFFFFFFFu && lane == leader) base = atomicAdd(&s_cnt[dest[j]], (unsigned)__popc(peers));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            rank_in[j] = base + __popc(peers & ((1u << lane) - 1));
+        }
+        __syncthreads();
+        if (threadIdx.x < nshards && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < MR_PER; j++)
+            if (dest[j] != 0xFFFFFFFFu) {
+                const unsigned long long o = s_base[dest[j]] + rank_in[j];
+                if (o < cap) send[(uint64_t)dest[j] * cap + o] = pos[j]; else *err = 7;   // segment overflow: the host falls back
+            }
+        __syncthreads();
+    }
+}
+// received positions (nshards segments of `cap`, sentinel-padded) -> bits of the own slice, second arrival marks a collision
+__global__ void __launch_bounds__(256) mphf_apply_kernel(const unsigned long long* __restrict__ recv, uint64_t nentries, unsigned long long* __restrict__ bits,
+                                                         unsigned long long* __restrict__ coll) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nentries; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long p = recv[i];
+        if (p == ~0ull) continue;
+        const unsigned long long m = 1ull << (p & 63);
+        const unsigned long long old = atomicOr(bits + (p >> 6), m);
+        if (old & m) atomicOr(coll + (p >> 6), m);
+    }
+}
 __global__ void __launch_bounds__(256) mphf_clear_kernel(unsigned long long* __restrict__ bits, const unsigned long long* __restrict__ coll, uint64_t nwords) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) bits[i] &= ~coll[i];
 }
@@ -1208,6 +1271,87 @@ public:
         mphf_sliced_ = level + 1;
         MTG_CUDA(cudaStreamSynchronize(stream_));
     }
+    // ---- exchange mode (kernels above): plan -> per level { route -> [all-to-all] -> apply -> [all-gather slices] -> next } ->
+    // survivors -> [all-gather] -> tail. Nothing here synchronises the host; the caller orders the collectives on stream().
+    DevBuf<unsigned long long> mx_send_, mx_recv_, mx_cursor_, mx_surv_;
+    std::vector<uint64_t> mx_caps_;
+    int mx_levels_ = 0;
+    bool mx_done_ = false;
+    static const uint64_t MX_SURV_CAP = 16384;   // survivors per rank handed to the host tail (expected < 4096 in total)
+    uint64_t mx_bound(int lvl) const { return (uint64_t)((double)nshare_ * pow(0.32, lvl)) + 4096; }   // survivors of this rank entering level lvl
+    int shard_mphf_plan(uint64_t* caps, int max_levels) override {
+        mx_levels_ = 0; mx_done_ = false;
+        mx_caps_.clear();
+        const uint64_t N = ntotal_;
+        if (!N) return 0;
+        mphf_setup(share_.p, N, nshards_, stream_, nshare_);
+        for (int lvl = 0; lvl < MPHF_LEVELS - 1 && lvl < max_levels; lvl++) {
+            if (lvl > 0 && (double)N * pow(0.3, lvl) < 4096.0) break;
+            const double per = (double)mx_bound(lvl) / nshards_;
+            mx_caps_.push_back((uint64_t)(per + 8.0 * sqrt(per) + 1024.0));
+        }
+        mx_levels_ = (int)mx_caps_.size();
+        for (int i = 0; i < mx_levels_; i++) caps[i] = mx_caps_[i];
+        if (mx_levels_) {
+            mx_send_.alloc(mx_caps_[0] * nshards_); mx_recv_.alloc(mx_caps_[0] * nshards_);
+            mx_cursor_.alloc(MR_MAX);
+            mx_surv_.alloc(MX_SURV_CAP * (sizeof(K) / 8) + 1);
+        }
+        return mx_levels_;
+    }
+    void shard_mphf_route(int lvl) override {
+        if (lvl < 0 || lvl >= mx_levels_) throw Error(-1, "shard_mphf_route: level out of plan");
+        const uint64_t cap = mx_caps_[lvl];
+        MTG_CUDA(cudaMemsetAsync(mx_send_.p, 0xFF, cap * nshards_ * 8, stream_));
+        mx_cursor_.zero(stream_);
+        const uint64_t slice_bits = mphf_slice_words(lvl) * 64;
+        const int grid = grid_for((mx_bound(lvl) + MR_PER - 1) / MR_PER, MR_THREADS);
+        mphf_route_kernel<K><<<grid, MR_THREADS, 0, stream_>>>(mphf_cur_, mphf_cnt_.p + lvl, lvl, mphf_dom_[lvl], mphf_seed_, slice_bits, nshards_, cap,
+                                                                mx_cursor_.p, mx_send_.p, err_.p);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches++;
+    }
+    void shard_mphf_apply(int lvl) override {
+        const uint64_t cap = mx_caps_[lvl], sw = mphf_slice_words(lvl);
+        unsigned long long* bits = mphf_bits_.p + mphf_off_[lvl] + (uint64_t)shard_ * sw;
+        MTG_CUDA(cudaMemsetAsync(mphf_coll_.p, 0, sw * 8, stream_));
+        mphf_apply_kernel<<<grid_for(cap * nshards_), 256, 0, stream_>>>(mx_recv_.p, cap * nshards_, bits, mphf_coll_.p);
+        mphf_clear_kernel<<<grid_for(sw), 256, 0, stream_>>>(bits, mphf_coll_.p, sw);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches += 2;
+        mphf_sliced_ = lvl + 1;   // buffer 8 = this level's slices
+    }
+    void shard_mphf_next(int lvl) override {   // after the all-gather of the level's slices
+        mphf_compact(lvl, stream_);
+        if (lvl + 1 == mx_levels_) {   // survivors of the last exchanged level -> [count | keys] for the all-gather
+            MTG_CUDA(cudaMemsetAsync(mx_surv_.p, 0, mx_surv_.bytes(), stream_));
+            MTG_CUDA(cudaMemcpyAsync(mx_surv_.p, mphf_cnt_.p + lvl + 1, 8, cudaMemcpyDeviceToDevice, stream_));
+            MTG_CUDA(cudaMemcpyAsync(mx_surv_.p + 1, mphf_cur_, std::min<uint64_t>(MX_SURV_CAP, std::max<uint64_t>(nshare_, 1)) * sizeof(K), cudaMemcpyDeviceToDevice, stream_));
+        }
+    }
+    // gathered survivor blocks of all ranks ([count | keys] each, device) -> the remaining levels on the host, like mphf_complete
+    void shard_mphf_tail(const void* d_gathered) override {
+        const uint64_t words = MX_SURV_CAP * (sizeof(K) / 8) + 1;
+        std::vector<unsigned long long> h(words * nshards_);
+        int e = 0;
+        MTG_CUDA(cudaMemcpyAsync(h.data(), d_gathered, h.size() * 8, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaMemcpyAsync(&e, err_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        if (e == 7) throw Error(-7, "BooPHF exchange: a routing segment overflowed");
+        std::vector<K> surv;
+        for (uint32_t r = 0; r < nshards_; r++) {
+            const unsigned long long cnt = h[r * words];
+            if (cnt > MX_SURV_CAP) throw Error(-7, "BooPHF exchange: more survivors than planned");
+            const K* kp = reinterpret_cast<const K*>(h.data() + r * words + 1);
+            surv.insert(surv.end(), kp, kp + cnt);
+        }
+        mphf_host_tail(surv, mx_levels_, stream_);
+        mphf_built_ = true;
+        mphf_coll_.release(); mphf_a_.release(); mphf_b_.release(); mphf_cnt_.release();
+        mx_send_.release(); mx_recv_.release(); mx_surv_.release();
+        mx_done_ = true;
+        mphf_sliced_ = 0;
+    }
     void shard_mphf_begin() override {
         if (!side_) { MTG_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking)); MTG_CUDA(cudaEventCreateWithFlags(&side_ev_, cudaEventDisableTiming)); }
         MTG_CUDA(cudaEventRecord(side_ev_, stream_));
@@ -1220,6 +1364,13 @@ public:
         t.start();
         const uint64_t N = ntotal_;
         cudaStream_t s = mphf_begun_ ? side_ : stream_;
+        if (mx_done_) {                           // BooPHF already built in exchange mode
+            mx_done_ = false;
+            st_.ms_mphf = t.stop();
+            share_.release();
+            adj_done_ = true;
+            return;
+        }
         if (mphf_sliced_) {                       // levels 0..mphf_sliced_-1 are complete (gathered): survivors, then the rest replicated
             if (mphf_n_) { mphf_compact(mphf_sliced_ - 1, s); mphf_levels(mphf_sliced_, s); }
         } else if (!mphf_begun_) mphf_from_table(s);
@@ -1240,13 +1391,16 @@ public:
         if (b) { *p = b->bits.p; *nbytes = b->bits.n * 4; }
         else if (which == 0) { *p = table_.p; *nbytes = nbuckets_ * nshards_ * (uint64_t)BUCKET_BYTES; }
         else if (which == 9) { *p = binoff_.p; *nbytes = (uint64_t)(nbps_ + 1) * nshards_ * 4; }
+        else if (which == 10) { *p = mx_send_.p; *nbytes = mx_send_.n * 8; }
+        else if (which == 11) { *p = mx_recv_.p; *nbytes = mx_recv_.n * 8; }
+        else if (which == 12) { *p = mx_surv_.p; *nbytes = mx_surv_.n * 8; }
         else if (which == 5) { *p = adjbuf_.p; *nbytes = adjbuf_.n * 16; }
         else if (which == 6) { *p = cfp_local_.p; *nbytes = ncfp_local_ * sizeof(K); }
         else if (which == 7) { *p = crit_list_.p; *nbytes = ncrit_ * sizeof(K); }
         else if (which == 8) {   // the BooPHF level built slice-wise last: nshards equal slices, slice `shard` filled
             if (!mphf_sliced_ || !mphf_n_) { *p = mphf_bits_.p; *nbytes = 0; }
             else { *p = mphf_bits_.p + mphf_off_[mphf_sliced_ - 1]; *nbytes = mphf_slice_words(mphf_sliced_ - 1) * mphf_pad_ * 8; }
-        } else throw Error(-1, "buffer: which 0..9");
+        } else throw Error(-1, "buffer: which 0..12");
     }
     void or_chunks(const void* d_in, uint32_t nchunks, uint64_t nwords, void* d_out) override {
         if (!nwords) return;
@@ -1271,7 +1425,8 @@ public:
     uint32_t mphf_pad_ = 1;                   // level arrays padded to a multiple of this many equal slices (N-GPU slice-wise levels)
     uint64_t mphf_slice_words(int lvl) const { return (mphf_dom_[lvl] / 64 + mphf_pad_ - 1) / mphf_pad_; }
     // sizes (mphf::setup, BooPHF.h:1015-1041, double arithmetic on the host), buffers, cnt[0] = N
-    void mphf_setup(const K* keys, uint64_t N, uint32_t pad, cudaStream_t stream_) {
+    void mphf_setup(const K* keys, uint64_t N, uint32_t pad, cudaStream_t stream_, uint64_t n_local = ~0ull) {
+        if (n_local == ~0ull) n_local = N;   // keys held by this rank (exchange mode: its share; otherwise all of them)
         mphf_n_ = N;
         mphf_pad_ = pad ? pad : 1;
         mphf_built_ = false;
@@ -1297,10 +1452,10 @@ public:
         mphf_bits_.zero(stream_);
         st_.mphf_words = unpadded;
         mphf_coll_.alloc(mphf_slice_words(0) * mphf_pad_);
-        mphf_a_.alloc(N); mphf_b_.alloc(N);
+        mphf_a_.alloc(std::max<uint64_t>(n_local, 1)); mphf_b_.alloc(std::max<uint64_t>(n_local, 1));
         mphf_cnt_.alloc(MPHF_LEVELS + 1);       // cnt[l] = keys entering level l
         mphf_cnt_.zero(stream_);
-        const unsigned long long n0 = N;
+        const unsigned long long n0 = n_local;
         MTG_CUDA(cudaMemcpyAsync(mphf_cnt_.p, &n0, 8, cudaMemcpyHostToDevice, stream_));
     }
     // one level on the device: every remaining key sets its bit (only inside this rank's slice when `sliced`), collided bits cleared
@@ -1347,51 +1502,56 @@ public:
         mphf_setup(keys, N, 1, stream_);
         mphf_levels(0, stream_);
     }
+    // levels glevels..23 from a host list of the k-mers that are still unplaced, then the final exact map (BooPHF.h:842-905)
+    void mphf_host_tail(std::vector<K>& h, int glevels, cudaStream_t stream_) {
+        if (h.empty()) return;
+        const uint64_t off = mphf_total_words_;
+        std::vector<K> next;
+        std::vector<unsigned long long> tail(off - mphf_off_[glevels], 0ull);   // bit arrays of levels glevels..24
+        std::vector<uint64_t> pos;
+        for (int lvl = glevels; lvl < MPHF_LEVELS - 1 && !h.empty(); lvl++) {
+            unsigned long long* bits = tail.data() + (mphf_off_[lvl] - mphf_off_[glevels]);
+            std::vector<unsigned long long> collh(mphf_dom_[lvl] / 64, 0ull);
+            pos.resize(h.size());
+            for (size_t i = 0; i < h.size(); i++) {
+                MphfState st;
+                st.init(h[i], mphf_seed_);
+                uint64_t hv = 0;
+                for (int l = 0; l <= lvl; l++) hv = st.level_hash(l);
+                const uint64_t p = hv % mphf_dom_[lvl];
+                pos[i] = p;
+                const unsigned long long m = 1ull << (p & 63);
+                if (bits[p >> 6] & m) collh[p >> 6] |= m;
+                bits[p >> 6] |= m;
+            }
+            for (size_t w = 0; w < collh.size(); w++) bits[w] &= ~collh[w];
+            next.clear();
+            for (size_t i = 0; i < h.size(); i++)
+                if (!((bits[pos[i] >> 6] >> (pos[i] & 63)) & 1ull)) next.push_back(h[i]);
+            h.swap(next);
+        }
+        MTG_CUDA(cudaMemcpyAsync(mphf_bits_.p + mphf_off_[glevels], tail.data(), tail.size() * 8, cudaMemcpyHostToDevice, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        if (!h.empty()) {  // keys that survive 24 levels go to the final exact map (practically never)
+            std::sort(h.begin(), h.end());
+            final_.alloc(h.size());
+            MTG_CUDA(cudaMemcpy(final_.p, h.data(), h.size() * sizeof(K), cudaMemcpyHostToDevice));
+            nfinal_ = h.size();
+        }
+    }
     void mphf_complete(cudaStream_t stream_) {
         const uint64_t N = mphf_n_;
         if (N) {
             const K* cur = mphf_cur_;
             const int glevels = mphf_glevels_;
-            const uint64_t off = mphf_total_words_;
-            DevBuf<unsigned long long>& cnt = mphf_cnt_;
             unsigned long long ncur = 0;
-            MTG_CUDA(cudaMemcpyAsync(&ncur, cnt.p + glevels, 8, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaMemcpyAsync(&ncur, mphf_cnt_.p + glevels, 8, cudaMemcpyDeviceToHost, stream_));
             MTG_CUDA(cudaStreamSynchronize(stream_));
             if (ncur) {
-                std::vector<K> h(ncur), next;
+                std::vector<K> h(ncur);
                 MTG_CUDA(cudaMemcpyAsync(h.data(), cur, ncur * sizeof(K), cudaMemcpyDeviceToHost, stream_));
                 MTG_CUDA(cudaStreamSynchronize(stream_));
-                std::vector<unsigned long long> tail(off - mphf_off_[glevels], 0ull);   // bit arrays of levels glevels..24
-                std::vector<uint64_t> pos;
-                for (int lvl = glevels; lvl < MPHF_LEVELS - 1 && !h.empty(); lvl++) {
-                    unsigned long long* bits = tail.data() + (mphf_off_[lvl] - mphf_off_[glevels]);
-                    std::vector<unsigned long long> collh(mphf_dom_[lvl] / 64, 0ull);
-                    pos.resize(h.size());
-                    for (size_t i = 0; i < h.size(); i++) {
-                        MphfState st;
-                        st.init(h[i], mphf_seed_);
-                        uint64_t hv = 0;
-                        for (int l = 0; l <= lvl; l++) hv = st.level_hash(l);
-                        const uint64_t p = hv % mphf_dom_[lvl];
-                        pos[i] = p;
-                        const unsigned long long m = 1ull << (p & 63);
-                        if (bits[p >> 6] & m) collh[p >> 6] |= m;
-                        bits[p >> 6] |= m;
-                    }
-                    for (size_t w = 0; w < collh.size(); w++) bits[w] &= ~collh[w];
-                    next.clear();
-                    for (size_t i = 0; i < h.size(); i++)
-                        if (!((bits[pos[i] >> 6] >> (pos[i] & 63)) & 1ull)) next.push_back(h[i]);
-                    h.swap(next);
-                }
-                MTG_CUDA(cudaMemcpyAsync(mphf_bits_.p + mphf_off_[glevels], tail.data(), tail.size() * 8, cudaMemcpyHostToDevice, stream_));
-                MTG_CUDA(cudaStreamSynchronize(stream_));
-                if (!h.empty()) {  // keys that survive 24 levels go to the final exact map (practically never)
-                    std::sort(h.begin(), h.end());
-                    final_.alloc(h.size());
-                    MTG_CUDA(cudaMemcpy(final_.p, h.data(), h.size() * sizeof(K), cudaMemcpyHostToDevice));
-                    nfinal_ = h.size();
-                }
+                mphf_host_tail(h, glevels, stream_);
             }
             mphf_built_ = true;
             mphf_coll_.release(); mphf_a_.release(); mphf_b_.release(); mphf_cnt_.release();

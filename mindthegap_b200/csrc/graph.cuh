@@ -385,6 +385,15 @@ public:
     virtual void set_cfp(const void* d_all, uint64_t n) = 0;   // the gathered cFP set (sorted here)
     virtual void shard_mphf_level(int level) = 0;               // optional: BooPHF level 0, then 1, slice-wise (buffer 8 all-gathered after each)
     virtual void shard_mphf_begin() = 0;                        // optional: BooPHF levels queued on a side stream (overlaps the next steps)
+    // BooPHF in exchange mode: every rank hashes only its own share; plan returns the number of exchanged levels and the
+    // per-destination capacity (64-bit entries) of each; per level: route (fills buffer 10) -> all-to-all 10 -> 11 (equal
+    // segments) -> apply (own slice of buffer 8) -> all-gather buffer 8 in place -> next; after the last level buffer 12 holds
+    // [count | survivors] -> all-gather -> tail(gathered) finishes on the host. No call synchronises the host except tail.
+    virtual int shard_mphf_plan(uint64_t* caps, int max_levels) = 0;
+    virtual void shard_mphf_route(int level) = 0;
+    virtual void shard_mphf_apply(int level) = 0;
+    virtual void shard_mphf_next(int level) = 0;
+    virtual void shard_mphf_tail(const void* d_gathered) = 0;
     virtual void shard_finish() = 0;                            // BooPHF levels from the gathered table; graph ready
     // which: 0 table, 1 main Bloom, 2..4 B2..B4, 5 adjacency bytes, 6 local cFP list, 7 critical share, 8 slice-wise BooPHF level,
     // 9 bin offsets (one equal part per range, own part filled by shard_begin: all-gather in place like the table); device pointer + bytes

@@ -113,7 +113,7 @@ class DistFind:
     MPHF_SLICED_MIN = 256 << 20  # solid k-mers (all ranks) from which the first BooPHF levels are built slice-wise (level arrays beyond L2)
     OR_SMALL_WORDS = 1 << 17   # gathered size (64-bit words) up to which _or_reduce takes the single all-gather route
 
-    def __init__(self, engine, device, group=None, scan_mode="auto", build_mode="sharded", comm=None, overlap_mphf=False):
+    def __init__(self, engine, device, group=None, scan_mode="auto", build_mode="sharded", comm=None, overlap_mphf=False, mphf_mode="exchange"):
         """scan_mode: "chromosomes" = every rank scans whole chromosomes (no feature exchange), "segments" = every chromosome
         is split across the ranks by position, "auto" = chromosomes when they balance within 25 %, else segments.
         build_mode: "sharded" = the membership structures are built from per-rank shares (table ranges all-gathered, Bloom bit
@@ -125,6 +125,7 @@ class DistFind:
         # on 4 x B200 (cfg2 per rank): no gain -- the critical-FP kernel it overlaps is itself DRAM-bound, so the two only share
         # the memory system (19.1 ms without, 20.0 ms with); kept for problem sizes where the exchanges dominate.
         self.overlap_mphf = overlap_mphf
+        self.mphf_mode = mphf_mode     # "exchange" (sharded by key share) or "replicated" (every rank builds every level)
         self.device = device
         self.c = comm if comm is not None else TorchComm(group)
         self.trace = None
@@ -141,10 +142,22 @@ class DistFind:
             engine.set_host_threads(max(1, (os.cpu_count() or 1) // max(1, local_world)))
         self.timing = {}
         self._t = None
+        self._minimizer_agreed = False
+        # Everything torch does for this find (allocations, copies, NCCL collectives) runs on the LIBRARY's stream
+        # (mtg_get_stream): kernels and collectives are then ordered on the device and no host synchronisation is needed
+        # between them (torch makes the current stream wait for a collective's completion, not the host).
+        self.lib_stream = None
+        if device.type == "cuda" and hasattr(engine, "stream_ptr") and not os.environ.get("MTG_DIST_HOST_SYNC"):
+            self.lib_stream = torch.cuda.ExternalStream(engine.stream_ptr(), device=device)
 
     def _mark(self, label):
-        """Phase wall clock (ms) after draining the device; bench.py reports it for rank 0."""
-        self._sync()
+        """Phase wall clock (ms); drains the device only when MTG_DIST_TRACE / MTG_DIST_PHASES asks for per-phase numbers."""
+        if self.lib_stream is not None:
+            if not (self.trace is not None or os.environ.get("MTG_DIST_PHASES")):
+                return
+            self.lib_stream.synchronize()
+        else:
+            self._sync()
         now = time.perf_counter()
         if self._t is not None and label:
             self.timing[label] = self.timing.get(label, 0.0) + (now - self._t) * 1e3
@@ -154,6 +167,8 @@ class DistFind:
     def _sync(self):
         """The engine works on its own CUDA stream: torch-side copies and NCCL collectives must have finished before the
         library touches their buffers (the library synchronises its stream before returning, so the other direction is safe)."""
+        if self.lib_stream is not None:  # same stream as the library: ordered on the device
+            return
         if self.device.type == "cuda":   # torch's stream only: a device-wide synchronize would also wait for the library's side stream
             torch.cuda.current_stream(self.device).synchronize()
 
@@ -185,14 +200,18 @@ class DistFind:
         return [json.loads(host[r * m: r * m + sizes[r]].tobytes().decode()) for r in range(self.world)]
 
     # ---- stage 1: count
-    def push_reads(self, stream=None, dev_ptr=None, nbytes=None):
-        """Push this rank's reads (host bytes/array, or a device pointer + size). Records are exchanged by minimizer bin,
-        so every rank must partition with the same minimizer length: the engine's size rule (10 below 2^30 bases, 13
-        above; mtg_set_minimizer_size) is applied to the GLOBAL read volume here, before the first push."""
+    def push_reads(self, stream=None, dev_ptr=None, nbytes=None, total_bases=None):
+        """Push this rank's reads (host bytes/array, or a device pointer + size); may be called several times (one file per
+        call). Records are exchanged by minimizer bin, so every rank must partition with the same minimizer length: the engine's
+        size rule (10 below 2^30 bases, 13 above; mtg_set_minimizer_size) is applied to the GLOBAL read volume ONCE, at the first
+        push: `total_bases` = this rank's whole volume when more pushes follow (default: the size of this first push). Every rank
+        must make its first push (the one collective here); later pushes are local."""
         n = int(nbytes if dev_ptr is not None else len(stream))
-        t = torch.tensor([n], dtype=torch.int64, device=self.device)
-        self.c.all_reduce(t, "sum")
-        self.e.set_minimizer_size(13 if int(t.item()) >= (1 << 30) else min(10, self.k - 1))
+        if not self._minimizer_agreed:
+            t = torch.tensor([int(total_bases) if total_bases is not None else n], dtype=torch.int64, device=self.device)
+            self.c.all_reduce(t, "sum")
+            self.e.set_minimizer_size(13 if int(t.item()) >= (1 << 30) else min(10, self.k - 1))
+            self._minimizer_agreed = True
         if dev_ptr is not None:
             self._sync()
             self.e.push_reads_device(dev_ptr, n)
@@ -387,9 +406,25 @@ class DistFind:
         self._sync()
         e.graph_set_cfp(cfp, sum(sizes))
         self._mark("cascade")
-        # BooPHF: levels 0 and 1 (92 % of the k-mers) slice-wise, each followed by an in-place all-gather of the level's slices;
-        # the rest is built by every rank. Below MPHF_SLICED_MIN k-mers the two extra exchanges cost more than they save.
-        if self.nb_solid >= self.MPHF_SLICED_MIN and hasattr(e, "graph_shard_mphf_level"):
+        # BooPHF in exchange mode: every rank hashes only its own share; per level the positions go to the owner of their slice
+        # of the level's bit array (fixed-size all-to-all, no size exchange), slices are all-gathered, survivors stay local.
+        if hasattr(e, "graph_shard_mphf_plan") and self.mphf_mode == "exchange":
+            caps = e.graph_shard_mphf_plan()
+            for lvl, cap in enumerate(caps):
+                e.graph_shard_mphf_step(lvl, 0)
+                send = e.graph_buffer(10)[:W * cap * 8]
+                recv = e.graph_buffer(11)[:W * cap * 8]
+                self.c.all_to_all_single(recv, send)
+                e.graph_shard_mphf_step(lvl, 1)
+                self._all_gather_ranges(e.graph_buffer(8))
+                e.graph_shard_mphf_step(lvl, 2)
+            if caps:
+                mine = e.graph_buffer(12)
+                allb = torch.empty(mine.numel() * W, dtype=torch.uint8, device=self.device)
+                self.c.all_gather_into_tensor(allb, mine)
+                e.graph_shard_mphf_tail(allb)
+        # (older variant) levels 0 and 1 slice-wise from the gathered table, the rest built by every rank
+        elif self.nb_solid >= self.MPHF_SLICED_MIN and hasattr(e, "graph_shard_mphf_level"):
             for lvl in (0, 1):
                 self._sync()
                 e.graph_shard_mphf_level(lvl)
@@ -501,5 +536,9 @@ class DistFind:
         return "".join(bk_out), "".join(vcf_out)
 
     def find(self, ref_records, ref_stream=None):
-        self.count()
-        return self.scan(ref_records, ref_stream)
+        if self.lib_stream is None:
+            self.count()
+            return self.scan(ref_records, ref_stream)
+        with torch.cuda.stream(self.lib_stream):
+            self.count()
+            return self.scan(ref_records, ref_stream)
