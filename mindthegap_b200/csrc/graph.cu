@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const K* __restrict__ ke
 // pass 2: buckets per bin = ceil(cnt / BIN_KEYS_PER_BUCKET); off[i] = base + exclusive prefix sum, off[nbps] = terminator.
 // Three small kernels (tile sums, one-CTA scan of the tile sums, apply); BS_TILE bins per CTA.
 static const int BS_THREADS = 256, BS_PER = 16, BS_TILE = BS_THREADS * BS_PER;
-__device__ __forceinline__ unsigned bin_buckets(unsigned c) { return (c + BIN_KEYS_PER_BUCKET - 1) / BIN_KEYS_PER_BUCKET; }
+__device__ __forceinline__ unsigned bin_buckets(unsigned c, unsigned kpb) { return (c + kpb - 1) / kpb; }
 __device__ __forceinline__ unsigned block_exclusive_scan_u32(unsigned v, unsigned* s_warp, unsigned& total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     unsigned x = v;
@@ -89,11 +89,11 @@ __device__ __forceinline__ unsigned block_exclusive_scan_u32(unsigned v, unsigne
     __syncthreads();
     return res;
 }
-__global__ void __launch_bounds__(BS_THREADS) bin_tile_sum_kernel(const unsigned int* __restrict__ cnt, uint32_t nbps, unsigned int* __restrict__ tile_sum) {
+__global__ void __launch_bounds__(BS_THREADS) bin_tile_sum_kernel(const unsigned int* __restrict__ cnt, uint32_t nbps, unsigned kpb, unsigned int* __restrict__ tile_sum) {
     __shared__ unsigned s_warp[32];
     const uint32_t base = blockIdx.x * BS_TILE + threadIdx.x * BS_PER;
     unsigned acc = 0;
-    for (int i = 0; i < BS_PER; i++) if (base + i < nbps) acc += bin_buckets(cnt[base + i]);
+    for (int i = 0; i < BS_PER; i++) if (base + i < nbps) acc += bin_buckets(cnt[base + i], kpb);
     unsigned total;
     block_exclusive_scan_u32(acc, s_warp, total);
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
@@ -109,12 +109,12 @@ __global__ void __launch_bounds__(1024) bin_tile_scan_kernel(unsigned int* __res
     for (uint32_t i = b; i < e; i++) { const unsigned v = tile_sum[i]; tile_sum[i] = run; run += v; }
     if (threadIdx.x == 0 && (uint64_t)total > capacity) *err = 6;   // the runs do not fit the range (cannot happen: capacity is an upper bound)
 }
-__global__ void __launch_bounds__(BS_THREADS) bin_offsets_kernel(const unsigned int* __restrict__ cnt, uint32_t nbps, const unsigned int* __restrict__ tile_off,
+__global__ void __launch_bounds__(BS_THREADS) bin_offsets_kernel(const unsigned int* __restrict__ cnt, uint32_t nbps, unsigned kpb, const unsigned int* __restrict__ tile_off,
                                                                  uint32_t base_bucket, uint32_t* __restrict__ off) {
     __shared__ unsigned s_warp[32];
     const uint32_t base = blockIdx.x * BS_TILE + threadIdx.x * BS_PER;
     unsigned nbk[BS_PER], acc = 0;
-    for (int i = 0; i < BS_PER; i++) { nbk[i] = base + i < nbps ? bin_buckets(cnt[base + i]) : 0; acc += nbk[i]; }
+    for (int i = 0; i < BS_PER; i++) { nbk[i] = base + i < nbps ? bin_buckets(cnt[base + i], kpb) : 0; acc += nbk[i]; }
     unsigned total;
     unsigned run = base_bucket + tile_off[blockIdx.x] + block_exclusive_scan_u32(acc, s_warp, total);
     for (int i = 0; i < BS_PER; i++) {
@@ -685,15 +685,37 @@ __global__ void __launch_bounds__(256) contains_kernel(GraphView<K> g, const uin
 //   feat[p] = 0x80 when the window holds an invalid base, else in_graph | nb_in<<1 | nb_out<<4
 //   rep[p]  = bit0: canonical (k-1)-suffix repeated in the reference, bit1: canonical (k-1)-prefix repeated
 // counters: [0] valid positions [1] in-graph positions [2] exact-table probes [3] Bloom-emulation evaluations
+// One CTA walks tiles of FT_TILE consecutive positions. The minimizer of every position's k-mer (which selects its bin in the exact
+// table) is rolled instead of recomputed: every thread hashes the ONE m-mer that starts at its position into shared memory
+// (FT_TILE + window halo values) and takes the minimum over its window of k-m+1 values -- ~2(k-m+1) shared-memory operations
+// instead of the ~15(k-m+1) ALU operations of kmer_minimizer. Consecutive positions share their minimizer, hence their bin: the
+// warp's 32 probes fall into a handful of 128-byte lines.
+static const int FT_TILE = 256, FT_HALO = 64;   // window k-m+1 <= 61 (k <= 63, m >= 3)
 template <class K>
-__global__ void __launch_bounds__(256) features_kernel(GraphView<K> g, const uint64_t* __restrict__ packed, const uint32_t* __restrict__ inv,
-                                                       uint64_t npos, uint8_t* __restrict__ feat, uint8_t* __restrict__ rep,
-                                                       uint32_t* __restrict__ interest, unsigned long long* __restrict__ counters) {
-    const int k = g.k;
+__global__ void __launch_bounds__(FT_TILE) features_kernel(GraphView<K> g, const uint64_t* __restrict__ packed, const uint32_t* __restrict__ inv,
+                                                           uint64_t npos, uint8_t* __restrict__ feat, uint8_t* __restrict__ rep,
+                                                           uint32_t* __restrict__ interest, unsigned long long* __restrict__ counters) {
+    __shared__ uint32_t s_hv[FT_TILE + FT_HALO];
+    const int k = g.k, m = g.tm, W = k - m + 1;
     const K m1 = kmask<K>(k - 1);
+    const uint32_t mmask = (uint32_t)((1ull << (2 * m)) - 1);
     unsigned long long c_valid = 0, c_in = 0, c_probe = 0, c_fb = 0;
-    const uint64_t npos32 = (npos + 31) & ~31ull;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos32; p += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t ntiles = (npos + FT_TILE - 1) / FT_TILE;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t p = tile * FT_TILE + threadIdx.x;
+        // hashed m-mer starting at base p (and, for the first W-1 threads, at base p + FT_TILE); the packed array is padded
+        {
+            const uint64_t last = npos + W - 2;   // last base position an m-mer of the sequence starts at
+            uint32_t hv = 0xFFFFFFFFu;
+            if (p <= last) { const uint32_t f = (uint32_t)extract_bases64(packed, p, m) & mmask; hv = mmer_hash(f, mmer_revcomp(f, m)); }
+            s_hv[threadIdx.x] = hv;
+            if (threadIdx.x < W - 1) {
+                hv = 0xFFFFFFFFu;
+                if (p + FT_TILE <= last) { const uint32_t f2 = (uint32_t)extract_bases64(packed, p + FT_TILE, m) & mmask; hv = mmer_hash(f2, mmer_revcomp(f2, m)); }
+                s_hv[FT_TILE + threadIdx.x] = hv;
+            }
+        }
+        __syncthreads();
         uint8_t f = 0x80, r = 0;
         bool valid = false;
         if (p < npos) {
@@ -706,10 +728,12 @@ __global__ void __launch_bounds__(256) features_kernel(GraphView<K> g, const uin
         }
         if (valid) {
             c_valid++;
+            uint32_t mini = 0xFFFFFFFFu;
+            for (int j = 0; j < W; j++) mini = min(mini, s_hv[threadIdx.x + j]);
             const K fwd = extract_kmer<K>(packed, p, k);
             bool in, exact;
             int din, dout;
-            node_probe(g, fwd, false, in, exact, din, dout);
+            node_probe(g, fwd, false, in, exact, din, dout, true, mini);
             c_probe++;
             if (!exact) { c_fb++; if (in) { c_probe += 8; c_fb += 8; } }
             if (in) c_in++;
@@ -723,7 +747,8 @@ __global__ void __launch_bounds__(256) features_kernel(GraphView<K> g, const uin
         // interest bit (host replay skip-ahead): invalid, not in the graph, or hetero pre-condition nb_in == 2 && !prefix_repeated
         const bool interesting = p < npos && ((f & 0x80) || !(f & 1) || ((((f >> 1) & 7) == 2) && !(r & 2)));
         const uint32_t b = __ballot_sync(0xFFFFFFFFu, interesting);
-        if ((threadIdx.x & 31) == 0) interest[p >> 5] = b;
+        if ((threadIdx.x & 31) == 0 && (p & ~31ull) < ((npos + 31) & ~31ull)) interest[p >> 5] = b;
+        __syncthreads();
     }
     // warp reduce the counters
     for (int off = 16; off; off >>= 1) {
@@ -752,7 +777,7 @@ template <class K> class Graph : public IGraph {
     DevBuf<uint32_t> binoff_; // (nbps_ + 1) global bucket offsets per range
     void set_geometry(uint64_t nkeys_per_range) {
         nbps_ = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nkeys_per_range / BIN_TARGET_KEYS, 1), 0x7FFFFFFFull);
-        nbuckets_ = nkeys_per_range / BIN_KEYS_PER_BUCKET + nbps_ + 1;
+        nbuckets_ = nkeys_per_range / BinCfg<K>::KEYS_PER_BUCKET + nbps_ + 1;
     }
     // histogram -> offsets -> insert for the keys of range `shard` (all of them when there is one range)
     void build_range(const K* keys, uint64_t n, uint32_t shard) {
@@ -762,9 +787,10 @@ template <class K> class Graph : public IGraph {
         const uint32_t ntiles = (nbps_ + BS_TILE - 1) / BS_TILE;
         DevBuf<unsigned int> tiles(ntiles);
         if (n) bin_count_kernel<K><<<grid_for(n), 256, 0, stream_>>>(keys, n, k_, tm_, nshards_, nbps_, shard, cnt.p, err_.p);
-        bin_tile_sum_kernel<<<ntiles, BS_THREADS, 0, stream_>>>(cnt.p, nbps_, tiles.p);
+        const unsigned kpb = BinCfg<K>::KEYS_PER_BUCKET;
+        bin_tile_sum_kernel<<<ntiles, BS_THREADS, 0, stream_>>>(cnt.p, nbps_, kpb, tiles.p);
         bin_tile_scan_kernel<<<1, 1024, 0, stream_>>>(tiles.p, ntiles, nbuckets_, err_.p);
-        bin_offsets_kernel<<<ntiles, BS_THREADS, 0, stream_>>>(cnt.p, nbps_, tiles.p, (uint32_t)(shard * nbuckets_), binoff_.p + (uint64_t)shard * (nbps_ + 1));
+        bin_offsets_kernel<<<ntiles, BS_THREADS, 0, stream_>>>(cnt.p, nbps_, kpb, tiles.p, (uint32_t)(shard * nbuckets_), binoff_.p + (uint64_t)shard * (nbps_ + 1));
         if (n) table_build_kernel<K><<<grid_for(n), 256, 0, stream_>>>(keys, n, table_.p, view(), err_.p);
         MTG_CUDA(cudaGetLastError());
         st_.launches += n ? 5 : 3;
@@ -1077,7 +1103,7 @@ public:
 
     // ------------------------------------------------------------------------------------------ build on N GPUs
     DevBuf<K> share_;            // solid k-mers of this rank's table range
-    uint64_t nshare_ = 0, ntotal_ = 0;
+    uint64_t nshare_ = 0, ntotal_ = 0, max_share_ = 0;
     uint32_t shard_ = 0;
     DevBuf<uint4> adjbuf_;
     DevBuf<K> cfp_local_;
@@ -1107,7 +1133,7 @@ public:
         if (nshards < 1 || shard >= nshards || n_share > max_share) throw Error(-1, "shard_begin: bad shard geometry");
         EvTimer t(stream_);
         st_.nb_solid = n_total;
-        ntotal_ = n_total; nshare_ = n_share; shard_ = shard;
+        ntotal_ = n_total; nshare_ = n_share; shard_ = shard; max_share_ = max_share;
         share_.alloc(std::max<uint64_t>(n_share, 1));
         if (n_share) MTG_CUDA(cudaMemcpyAsync(share_.p, d_keys_share, n_share * sizeof(K), cudaMemcpyDeviceToDevice, stream_));
         // ---- all ranges allocated, own range built (same load factor as the single-GPU table, from the largest share)
@@ -1278,7 +1304,8 @@ public:
     int mx_levels_ = 0;
     bool mx_done_ = false;
     static const uint64_t MX_SURV_CAP = 16384;   // survivors per rank handed to the host tail (expected < 4096 in total)
-    uint64_t mx_bound(int lvl) const { return (uint64_t)((double)nshare_ * pow(0.32, lvl)) + 4096; }   // survivors of this rank entering level lvl
+    // survivors of a rank entering level lvl, bounded from the LARGEST share so that every rank plans the same segment sizes
+    uint64_t mx_bound(int lvl) const { return (uint64_t)((double)max_share_ * pow(0.32, lvl)) + 4096; }
     int shard_mphf_plan(uint64_t* caps, int max_levels) override {
         mx_levels_ = 0; mx_done_ = false;
         mx_caps_.clear();
@@ -1649,7 +1676,7 @@ public:
         launch_pack(d_seq, len, seq_packed_.p, seq_inv_.p, nwords, stream_);
         MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 32, stream_));
         MTG_CUDA(cudaEventRecord(ev_a_, stream_));
-        features_kernel<K><<<grid_for(npos, 256, 148 * 32), 256, 0, stream_>>>(view(), seq_packed_.p, seq_inv_.p, npos, d_feat, d_rep, d_interest, counters_.p);
+        features_kernel<K><<<grid_for(npos, FT_TILE, 148 * 32), FT_TILE, 0, stream_>>>(view(), seq_packed_.p, seq_inv_.p, npos, d_feat, d_rep, d_interest, counters_.p);
         MTG_CUDA(cudaGetLastError());
         MTG_CUDA(cudaEventRecord(ev_b_, stream_));
         features_timed_ = true;

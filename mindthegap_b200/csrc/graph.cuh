@@ -232,7 +232,8 @@ template <class K> struct TableCfg { static const int SLOTS = BUCKET_KEY_BYTES /
 // `key` in [0, SLOTS) (and the bucket in *bucket_out) or -1; *adj receives the adjacency byte of the slot.
 MTG_HD uint32_t shard_of(uint64_t h, uint32_t nshards) { return (uint32_t)(((h >> 32) * (uint64_t)nshards) >> 32); }
 MTG_HD int table_minimizer_len(int k) { return k - 1 < 15 ? k - 1 : 15; }   // default when no counter dictates it (loaded solid sets)
-static const int BIN_KEYS_PER_BUCKET = 10;   // run length of a bin = ceil(keys / 10) buckets of 14 (7) slots: a run is never full
+// run length of a bin = ceil(keys / kpb) buckets, kpb = 10 of 14 slots (u64) or 5 of 7 (u128): a run is never full
+template <class K> struct BinCfg { static const int KEYS_PER_BUCKET = sizeof(K) == 8 ? 10 : 5; };
 static const int BIN_TARGET_KEYS = 12;       // bins per range = keys / 12 (+1)
 // placement hash of a minimizer value: its top 32 bits select the range (GPU) and, with the remainder, the bin inside the range
 MTG_HD uint64_t mini_place_hash(uint32_t mini) { return mix64((uint64_t)mini + 0x632BE59BD9B4E019ULL); }
@@ -325,10 +326,13 @@ template <class K> MTG_D void graph_degrees(const GraphView<K>& g, K graine, boo
 // contains + degrees of the node whose forward-strand k-mer is `fwd`, with one bucket probe when its canonical k-mer is
 // solid (adjacency byte; the strand decides which nibble is "in"); everything else takes the emulation path.
 //   always_degrees: compute the degrees even when the node is not in the graph (observer probes ask for both).
-template <class K> MTG_D void node_probe(const GraphView<K>& g, K fwd, bool always_degrees, bool& in, bool& exact, int& din, int& dout) {
+//   mini: the k-mer's minimizer when the caller already has it (the reference scan rolls it), else computed here.
+template <class K> MTG_D void node_probe(const GraphView<K>& g, K fwd, bool always_degrees, bool& in, bool& exact, int& din, int& dout,
+                                         bool have_mini = false, uint32_t mini = 0) {
     const K can = canonical(fwd, g.k);
     unsigned adj = 0;
-    exact = table_lookup(g, can, adj);
+    if (!have_mini) mini = kmer_minimizer(can, g.k, g.tm);
+    exact = table_find<K>(g.table, g.bin_off, g.nbps, g.nshards, can, mini, nullptr, &adj) >= 0;
     din = dout = 0;
     if (exact) {
         in = true;

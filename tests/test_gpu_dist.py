@@ -87,9 +87,10 @@ def _run_ranks(world, case, build_mode, scan_mode, results, engines, sliced_mphf
             p = m.FindParams.from_cli(["-kmer-size", str(case["k"])] + list(case["flags"]))
             f = m.Finder(p)
             engines[rank] = f
-            d = DistFind(f, torch.device("cuda", 0), comm=ThreadComm(shared, rank), scan_mode=scan_mode, build_mode=build_mode)
+            d = DistFind(f, torch.device("cuda", 0), comm=ThreadComm(shared, rank), scan_mode=scan_mode, build_mode=build_mode,
+                         mphf_mode="exchange" if sliced_mphf else "replicated")   # BooPHF sharded by key share, or built by every rank
             d.OR_SMALL_WORDS = 256     # both OR-reduce routes on these small inputs
-            d.MPHF_SLICED_MIN = 0 if sliced_mphf else 1 << 60   # BooPHF levels 0/1 slice-wise + all-gather, or fully replicated
+            d.MPHF_SLICED_MIN = 1 << 60
             mine = recs[rank::world]
             d.push_reads(b"\n".join(s for _, s in mine) + b"\n")
             bk, vcf = d.find(refs)

@@ -4,7 +4,9 @@ V=${V:-r02_v1}
 CFG=${CFG:-cfg3}
 if [ -z "$NOTEST" ]; then
 timeout ${TEST_TIMEOUT:-600} python -m pytest tests -m gpu -q --timeout=${PER_TEST_TIMEOUT:-200} --timeout-method=thread ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu_$V.log 2>&1; echo "pytest rc=$?"
+RC=$?
 tail -25 gpurun_out/pytest_gpu_$V.log
+if grep -qE "failed|Timeout|error" gpurun_out/pytest_gpu_$V.log && [ -z "$BENCH_ANYWAY" ]; then echo "tests not green: bench skipped"; NOBENCH=1; fi
 fi
 if [ -z "$NOBENCH" ]; then
 timeout ${BENCH_TIMEOUT:-500} python bench.py --config $CFG ${BENCH_ARGS:-} > gpurun_out/bench_$V.json 2> gpurun_out/bench_$V.err; echo "bench rc=$?"
