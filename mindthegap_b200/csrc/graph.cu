@@ -57,6 +57,14 @@ struct BloomDev {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ build kernels
+// empty table: key slots all ones, the 16 adjacency bytes of every bucket zero -- one streaming pass (a cudaMemset of the range
+// plus a 2-D memset of the adjacency bytes cost 6 ms per GB: 12 M rows of 16 bytes)
+__global__ void __launch_bounds__(256) table_init_kernel(uint4* __restrict__ table, uint64_t nbuckets) {
+    const uint64_t n = nbuckets * 8;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        table[i] = (i & 7) == 7 ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+}
+
 // ---- exact table build (graph.cuh "Placement"): bin histogram -> bucket offsets (exclusive scan) -> insert
 // pass 1: solid k-mers per bin of range `shard` (cnt has nbps entries)
 template <class K>
@@ -586,25 +594,32 @@ __global__ void __launch_bounds__(256) or_chunks_kernel(const unsigned long long
         out[i] = v;
     }
 }
-// every key held by the (gathered) table -> a dense list, in table order
+// every key held by the (gathered) table -> a dense list, in table order. 8 lanes read one 128-byte bucket (one 128-bit load
+// each: a warp instruction fetches 4 whole lines), every lane keeps the non-empty keys of its chunk, one reservation per warp.
 template <class K>
 __global__ void __launch_bounds__(256) table_compact_kernel(const K* __restrict__ table, uint64_t nbuckets_total, K* __restrict__ out,
                                                             unsigned long long* __restrict__ nout) {
-    const int SLOTS = TableCfg<K>::SLOTS, STRIDE = TableCfg<K>::STRIDE;
-    const K EMPTY = ~K(0);
-    const int lane = threadIdx.x & 31;
-    const uint64_t nslots = nbuckets_total * SLOTS, nround = (nslots + 31) & ~31ull;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (uint64_t)gridDim.x * blockDim.x) {
-        K key = EMPTY;
-        if (i < nslots) key = table[(i / SLOTS) * STRIDE + (i % SLOTS)];
-        const bool keep = !(key == EMPTY);
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, keep);
-        if (b) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(nout, (unsigned long long)__popc(b));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (keep) out[base + __popc(b & ((1u << lane) - 1))] = key;
-        }
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const uint64_t nround = (nbuckets_total + 3) & ~3ull;
+    const uint4* t4 = reinterpret_cast<const uint4*>(table);
+    for (uint64_t b0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; b0 < nround; b0 += ((uint64_t)gridDim.x * blockDim.x) >> 3) {
+        uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (b0 < nbuckets_total && sub < 7) v = __ldg(t4 + b0 * 8 + sub);
+        const uint64_t a0 = ((uint64_t)v.y << 32) | v.x, a1 = ((uint64_t)v.w << 32) | v.z;
+        unsigned n0, n1;
+        if (sizeof(K) == 8) { n0 = a0 != ~0ull; n1 = a1 != ~0ull; } else { n0 = !(a0 == ~0ull && a1 == ~0ull); n1 = 0; }
+        const unsigned mine = n0 + n1;
+        unsigned incl = mine;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+        const unsigned total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 31 && total) base = atomicAdd(nout, (unsigned long long)total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31);
+        unsigned long long o = base + incl - mine;
+        if (sizeof(K) == 8) {
+            if (n0) out[o++] = make_key<K>(a0, 0);
+            if (n1) out[o] = make_key<K>(a1, 0);
+        } else if (n0) out[o] = make_key<K>(a0, a1);
     }
 }
 
@@ -892,7 +907,7 @@ public:
     uint64_t compact_range(uint64_t b0, uint64_t nb, uint64_t expect) {
         ordered_.alloc(std::max<uint64_t>(expect, 1));
         MTG_CUDA(cudaMemsetAsync(counters_.p + 5, 0, 8, stream_));
-        table_compact_kernel<K><<<grid_for(nb * TableCfg<K>::SLOTS), 256, 0, stream_>>>(table_.p + b0 * TableCfg<K>::STRIDE, nb, ordered_.p, counters_.p + 5);
+        table_compact_kernel<K><<<grid_for(nb * 8), 256, 0, stream_>>>(table_.p + b0 * TableCfg<K>::STRIDE, nb, ordered_.p, counters_.p + 5);
         MTG_CUDA(cudaGetLastError());
         st_.launches++;
         return expect;
@@ -946,9 +961,8 @@ public:
         nshards_ = 1;
         binoff_.alloc(nbps_ + 1);
         table_.alloc(nbuckets_ * TableCfg<K>::STRIDE);
-        table_.fill_ff(stream_);   // empty key slots; the 16 adjacency bytes of every bucket start at zero
-        MTG_CUDA(cudaMemset2DAsync(reinterpret_cast<uint8_t*>(table_.p) + BUCKET_ADJ_OFFSET, BUCKET_BYTES, 0, BUCKET_BYTES - BUCKET_ADJ_OFFSET,
-                                   nbuckets_, stream_));
+        table_init_kernel<<<grid_for(nbuckets_ * 8), 256, 0, stream_>>>(reinterpret_cast<uint4*>(table_.p), nbuckets_);
+        st_.launches++;
         adj_done_ = false;
         err_.zero(stream_);
         build_range(keys, N, 0);
@@ -1145,8 +1159,8 @@ public:
         binoff_.zero(stream_);
         table_.alloc(nbuckets_ * nshards * STRIDE);
         K* own = table_.p + (uint64_t)shard * nbuckets_ * STRIDE;
-        MTG_CUDA(cudaMemsetAsync(own, 0xFF, nbuckets_ * BUCKET_BYTES, stream_));
-        MTG_CUDA(cudaMemset2DAsync(reinterpret_cast<uint8_t*>(own) + BUCKET_ADJ_OFFSET, BUCKET_BYTES, 0, BUCKET_BYTES - BUCKET_ADJ_OFFSET, nbuckets_, stream_));
+        table_init_kernel<<<grid_for(nbuckets_ * 8), 256, 0, stream_>>>(reinterpret_cast<uint4*>(own), nbuckets_);
+        st_.launches++;
         adj_done_ = false;
         err_.zero(stream_);
         build_range(share_.p, n_share, shard);
@@ -1272,7 +1286,7 @@ public:
         mphf_all_.alloc(std::max<uint64_t>(N, 1));
         MTG_CUDA(cudaMemsetAsync(counters_.p + 4, 0, 8, s));
         const uint64_t nb = nbuckets_ * nshards_;
-        table_compact_kernel<K><<<grid_for(nb * TableCfg<K>::SLOTS), 256, 0, s>>>(table_.p, nb, mphf_all_.p, counters_.p + 4);
+        table_compact_kernel<K><<<grid_for(nb * 8), 256, 0, s>>>(table_.p, nb, mphf_all_.p, counters_.p + 4);
         MTG_CUDA(cudaGetLastError());
         st_.launches++;
         mphf_launch(mphf_all_.p, N, s);
@@ -1288,7 +1302,7 @@ public:
             mphf_all_.alloc(std::max<uint64_t>(N, 1));
             MTG_CUDA(cudaMemsetAsync(counters_.p + 4, 0, 8, stream_));
             const uint64_t nb = nbuckets_ * nshards_;
-            table_compact_kernel<K><<<grid_for(nb * TableCfg<K>::SLOTS), 256, 0, stream_>>>(table_.p, nb, mphf_all_.p, counters_.p + 4);
+            table_compact_kernel<K><<<grid_for(nb * 8), 256, 0, stream_>>>(table_.p, nb, mphf_all_.p, counters_.p + 4);
             MTG_CUDA(cudaGetLastError());
             st_.launches++;
             mphf_setup(mphf_all_.p, N, nshards_, stream_);

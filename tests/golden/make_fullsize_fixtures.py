@@ -73,7 +73,7 @@ def run_case(name, case, tmp_root, cores):
         b = h5_bytes(out + ".h5", ds, d)
         bits[ds] = None if b is None else {"bytes": len(b), "sha256": sha(b)}
     fx = {"case": name, "config": case["config"], "seed": case["seed"], "k": case["k"], "flags": case["flags"],
-          "command": " ".join(os.path.basename(c) if c.startswith("/") else c for c in cmd),
+          "command": " ".join(",".join(os.path.basename(x) for x in c.split(",")) if c.startswith("/") else c for c in cmd),
           "reference_wall_s": round(wall, 2), "reference_cores": cores, "reference_times": times, "info": info,
           "breakpoints": {"bytes": len(bk), "sha256": sha(bk), "records": bk.count(b">") // 2},
           "vcf": {"bytes": len(vcf), "sha256": sha(vcf), "records": vcf.count(b"\n")},
