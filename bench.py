@@ -296,6 +296,9 @@ def own_arm(args):
     # every rank brings the read set of its own genome segment (weak scaling); N=1 is exactly cfg2
     wl = make_workload(scale=args.scale, seed=SEED + 1000 * rank, config=args.config)
     params = m.FindParams(kmer_size=K, device=local_rank)
+    if world > 1:   # every find of this process runs on one persistent stream shared with torch / NCCL (dist.shared_stream)
+        from mindthegap_b200.dist import shared_stream
+        params.stream = shared_stream(torch.device("cuda", local_rank)).cuda_stream
     stream_host = torch.from_numpy(wl["stream"]).pin_memory()
     stream_np = stream_host.numpy()
     ref_stream = np.concatenate([np.concatenate([s, np.array([10], dtype=np.uint8)]) for _, s in wl["refs"]])

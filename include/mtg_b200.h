@@ -42,6 +42,9 @@ typedef struct mtg_params {
     int32_t branching_filter; /* -branching-filter default 15, -1 disables                               */
     uint32_t flags;           /* MTG_F_*                                                                  */
     int32_t device;           /* CUDA device ordinal                                                      */
+    uint64_t stream;          /* 0: the context creates its own CUDA stream. Else a cudaStream_t of the caller, which must
+                                 outlive the context: a multi-GPU host passes the stream its collectives run on, so that its
+                                 device allocator and NCCL see ONE stream across successive contexts (mtg_get_stream returns it) */
 } mtg_params;
 
 void mtg_default_params(mtg_params* p);

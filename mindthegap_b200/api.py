@@ -26,7 +26,8 @@ class MtgError(RuntimeError):
 class _Params(C.Structure):
     _fields_ = [("kmer_size", C.c_int32), ("abundance_min", C.c_int32), ("abundance_max", C.c_int64),
                 ("minimizer_size", C.c_int32), ("max_repeat", C.c_int32), ("het_max_occ", C.c_int32),
-                ("snp_min_val", C.c_int32), ("branching_filter", C.c_int32), ("flags", C.c_uint32), ("device", C.c_int32)]
+                ("snp_min_val", C.c_int32), ("branching_filter", C.c_int32), ("flags", C.c_uint32), ("device", C.c_int32),
+                ("stream", C.c_uint64)]
 
 
 u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
@@ -170,6 +171,7 @@ class FindParams:
     flags: int = F_DEFAULT
     device: int = 0
     minimizer_size: int = 10
+    stream: int = 0   # cudaStream_t of the caller (0 = own stream); see include/mtg_b200.h
 
     @staticmethod
     def from_cli(args):

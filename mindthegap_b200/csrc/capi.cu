@@ -128,6 +128,7 @@ void mtg::PinnedBuf::release() {
 struct mtg_ctx {
     mtg_params p;
     cudaStream_t stream = nullptr;
+    bool owns_stream = true;
     std::unique_ptr<ICounter> counter;   // reads, k
     std::unique_ptr<IGraph> graph;
     CountStats count_stats;
@@ -236,7 +237,8 @@ mtg_ctx* mtg_create(const mtg_params* p) {
         c->p = *p;
         if (c->p.het_max_occ < 1) c->p.het_max_occ = 1;  // src/Finder.cpp:317-319
         if (c->p.minimizer_size <= 0) c->p.minimizer_size = 10;
-        MTG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        if (p->stream) { c->stream = (cudaStream_t)(uintptr_t)p->stream; c->owns_stream = false; }
+        else MTG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         current_stream() = c->stream;
         c->graph.reset(make_graph(c->p.kmer_size, c->stream));
         c->histogram.assign(HISTO_MAX + 1, 0);
@@ -253,7 +255,7 @@ void mtg_destroy(mtg_ctx* ctx) {
     cudaSetDevice(ctx->p.device);
     current_stream() = ctx->stream;
     ctx->counter.reset(); ctx->solid_owner.reset(); ctx->graph.reset();
-    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); if (ctx->owns_stream) cudaStreamDestroy(ctx->stream); }
     current_stream() = nullptr;
     delete ctx;
 }

@@ -60,6 +60,20 @@ def segment_bounds(npos, world):
     return b
 
 
+_SHARED_STREAMS = {}
+
+
+def shared_stream(device):
+    """One persistent torch stream per device for every multi-GPU find of this process: create the engine with
+    FindParams(stream=shared_stream(dev).cuda_stream). torch's caching allocator keeps its blocks per stream, so finds that each
+    came with a fresh library stream would reach cudaMalloc / cudaFree (a device synchronisation) for every large exchange buffer."""
+    dev = torch.device(device)
+    key = (dev.type, dev.index)
+    if key not in _SHARED_STREAMS:
+        _SHARED_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SHARED_STREAMS[key]
+
+
 class TorchComm:
     """The four collectives DistFind needs, over torch.distributed (NCCL on GPUs, gloo in the CPU tests). Tests may pass any
     object with the same methods as DistFind(comm=...), e.g. an in-process emulation that runs N ranks on one GPU."""
@@ -148,7 +162,9 @@ class DistFind:
         # between them (torch makes the current stream wait for a collective's completion, not the host).
         self.lib_stream = None
         if device.type == "cuda" and hasattr(engine, "stream_ptr") and not os.environ.get("MTG_DIST_HOST_SYNC"):
-            self.lib_stream = torch.cuda.ExternalStream(engine.stream_ptr(), device=device)
+            ptr = engine.stream_ptr()
+            own = _SHARED_STREAMS.get((device.type, device.index))
+            self.lib_stream = own if own is not None and own.cuda_stream == ptr else torch.cuda.ExternalStream(ptr, device=device)
 
     def _mark(self, label):
         """Phase wall clock (ms); drains the device only when MTG_DIST_TRACE / MTG_DIST_PHASES asks for per-phase numbers."""
