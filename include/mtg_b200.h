@@ -207,6 +207,12 @@ int mtg_load_solid(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_
 /* fillRefBloom (src/FindBreakpoints.hpp:956-1009): all reference sequences, separated by a non-ACGT byte. */
 int mtg_set_reference(mtg_ctx* ctx, const char* bases, uint64_t nbytes);
 int mtg_set_reference_device(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes);  /* same, bases already in HBM */
+/* The same on N GPUs that all hold the whole reference: every rank counts only the (k-1)-mers of the minimizer bins it owns
+ * (bin % nparts == part), *n_local = its repeated k-mers; the host gathers them (mtg_ref_repeats_copy, any order) and every rank
+ * installs the union with mtg_set_ref_repeats_device (canonical (k-1)-mer values, 8 or 16 bytes each like the solid k-mers). */
+int mtg_set_reference_sharded(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes, int32_t nparts, int32_t part, uint64_t* n_local);
+int mtg_ref_repeats_copy(mtg_ctx* ctx, void* d_out, uint64_t capacity);
+int mtg_set_ref_repeats_device(mtg_ctx* ctx, const void* d_keys, uint64_t n);
 
 /* Graph::contains / indegree / outdegree / ref Bloom for arbitrary k-mers (src/IFindObserver.hpp:85-117).
  * kmers are FORWARD values (any strand). contains: out bit0 = contains (bits 1..4: exact, bloom, cfp, mphf detail);

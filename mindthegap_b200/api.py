@@ -45,7 +45,7 @@ EXPORTS = [
     "mtg_count_run", "mtg_count_filter", "mtg_solid_copy", "mtg_graph_build_device", "mtg_sequence_features_device2", "mtg_replay_sequence",
     "mtg_graph_build_begin", "mtg_graph_critical", "mtg_graph_critical_copy", "mtg_graph_build_end", "mtg_set_host_threads", "mtg_set_minimizer_size", "mtg_get_minimizer_size",
     "mtg_solid_partition", "mtg_partition_keys", "mtg_graph_shard_begin", "mtg_graph_shard_critical", "mtg_graph_adj_pack", "mtg_graph_adj_unpack",
-    "mtg_graph_branching", "mtg_export_dsk_partitions", "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_mphf_level", "mtg_graph_shard_mphf_begin", "mtg_graph_shard_mphf_plan", "mtg_graph_shard_mphf_step", "mtg_graph_shard_mphf_tail", "mtg_get_stream", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
+    "mtg_graph_branching", "mtg_export_dsk_partitions", "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_mphf_level", "mtg_graph_shard_mphf_begin", "mtg_graph_shard_mphf_plan", "mtg_graph_shard_mphf_step", "mtg_graph_shard_mphf_tail", "mtg_get_stream", "mtg_set_reference_sharded", "mtg_ref_repeats_copy", "mtg_set_ref_repeats_device", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
 ]
 
 _lib = None
@@ -146,6 +146,9 @@ def load_library():
     L.mtg_graph_shard_mphf_plan.argtypes = [vp, u64p, C.c_int32, C.POINTER(C.c_int32)]
     L.mtg_graph_shard_mphf_step.argtypes = [vp, C.c_int32, C.c_int32]
     L.mtg_graph_shard_mphf_tail.argtypes = [vp, vp]
+    L.mtg_set_reference_sharded.argtypes = [vp, vp, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]
+    L.mtg_ref_repeats_copy.argtypes = [vp, vp, C.c_uint64]
+    L.mtg_set_ref_repeats_device.argtypes = [vp, vp, C.c_uint64]
     L.mtg_get_stream.restype = C.c_void_p
     L.mtg_get_stream.argtypes = [vp]
     L.mtg_graph_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]
@@ -437,6 +440,17 @@ class Finder:
     def set_reference_device(self, dev_ptr, nbytes):
         self._check(self.L.mtg_set_reference_device(self.ctx, C.c_void_p(dev_ptr), nbytes))
 
+    def set_reference_sharded(self, dev_ptr, nbytes, nparts, part):
+        n = C.c_uint64()
+        self._check(self.L.mtg_set_reference_sharded(self.ctx, C.c_void_p(dev_ptr), int(nbytes), int(nparts), int(part), C.byref(n)))
+        return int(n.value)
+
+    def ref_repeats_copy(self, out_t, capacity):
+        self._check(self.L.mtg_ref_repeats_copy(self.ctx, C.c_void_p(out_t.data_ptr()), int(capacity)))
+
+    def set_ref_repeats_device(self, keys_t, n):
+        self._check(self.L.mtg_set_ref_repeats_device(self.ctx, C.c_void_p(keys_t.data_ptr()), int(n)))
+
     def scan_reference_device(self, name, seq, dev_ptr):
         a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray)) else np.ascontiguousarray(seq, dtype=np.uint8)
         self._check(self.L.mtg_scan_reference_device(self.ctx, name.encode(), _ptr(a), C.c_void_p(dev_ptr), a.size))
@@ -556,6 +570,8 @@ class Finder:
     def key_words(self):
         """64-bit words per k-mer key: 1 (k <= 31) or 2 ({lo, hi})."""
         return 1 if self.params.kmer_size <= 31 else 2
+
+    solid_share_is_table_range = True   # the rank that counted a minimizer bin owns the table range of its k-mers (common.cuh mini_owner)
 
     def solid_copy(self, keys_t, counts_t):
         self._check(self.L.mtg_solid_copy(self.ctx, C.c_void_p(keys_t.data_ptr()), C.c_void_p(counts_t.data_ptr()) if counts_t is not None else None,

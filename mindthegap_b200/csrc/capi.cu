@@ -138,6 +138,7 @@ struct mtg_ctx {
     bool graph_ready = false;
     // solid set kept on the device for export
     std::unique_ptr<ICounter> solid_owner;
+    std::unique_ptr<ICounter> ref_counter;   // sharded reference counting: this rank's repeated (k-1)-mers until they are gathered
     std::vector<uint64_t> loaded_lo, loaded_hi;
     // text ingest (FASTA/FASTQ parsed on the GPU)
     std::unique_ptr<TextIngest> ingest;
@@ -254,7 +255,7 @@ void mtg_destroy(mtg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->p.device);
     current_stream() = ctx->stream;
-    ctx->counter.reset(); ctx->solid_owner.reset(); ctx->graph.reset();
+    ctx->counter.reset(); ctx->solid_owner.reset(); ctx->ref_counter.reset(); ctx->graph.reset();
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); if (ctx->owns_stream) cudaStreamDestroy(ctx->stream); }
     current_stream() = nullptr;
     delete ctx;
@@ -699,21 +700,49 @@ int mtg_load_solid(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_
     MTG_CATCH
 }
 
-static void set_reference_impl(mtg_ctx* ctx, const char* bases, const void* d_bases, uint64_t nbytes) {
+// (k-1)-mers of the reference with abundance > het_max_occ (fillRefBloom, src/FindBreakpoints.hpp:984-1003). nparts > 1: only the
+// share of minimizer bins `part` owns is counted and the repeated k-mers stay in ctx->ref_counter for the host to gather.
+static void set_reference_impl(mtg_ctx* ctx, const char* bases, const void* d_bases, uint64_t nbytes, int nparts = 1, int part = 0) {
     WallTimer w(ctx->wall_set_reference);
     Trace tr(ctx->stream);
     MTG_CUDA(cudaSetDevice(ctx->p.device));
     const int k1 = ctx->p.kmer_size - 1;
     std::unique_ptr<ICounter> rc(make_counter(k1, std::min(ctx->p.minimizer_size, k1), ctx->stream, ctx->p.kmer_size <= 31 ? 64 : 128, true));
     if (d_bases) rc->push_device((const uint8_t*)d_bases, nbytes); else rc->push_host(bases, nbytes);
+    if (nparts > 1) rc->restrict_owner(nparts, part);
     rc->finish(ctx->p.het_max_occ + 1, 2147483647LL);
     ctx->ref_count_stats = rc->stats();
+    if (nparts > 1) { ctx->ref_counter = std::move(rc); return; }
     ctx->graph->set_ref_repeats(rc->solid_keys_device(), rc->nb_solid());
     ctx->ref_repeated = rc->nb_solid();
     tr.mark("set_reference: total");
 }
 int mtg_set_reference(mtg_ctx* ctx, const char* bases, uint64_t nbytes) { MTG_TRY(ctx) set_reference_impl(ctx, bases, nullptr, nbytes); MTG_CATCH }
 int mtg_set_reference_device(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes) { MTG_TRY(ctx) set_reference_impl(ctx, nullptr, d_bases, nbytes); MTG_CATCH }
+int mtg_set_reference_sharded(mtg_ctx* ctx, const void* d_bases, uint64_t nbytes, int32_t nparts, int32_t part, uint64_t* n_local) {
+    MTG_TRY(ctx)
+    if (nparts < 1 || part < 0 || part >= nparts) throw Error(-1, "mtg_set_reference_sharded: bad share");
+    set_reference_impl(ctx, nullptr, d_bases, nbytes, std::max(nparts, 2), part);   // always leaves the share in ref_counter
+    if (n_local) *n_local = ctx->ref_counter->nb_solid();
+    MTG_CATCH
+}
+int mtg_ref_repeats_copy(mtg_ctx* ctx, void* d_out, uint64_t capacity) {
+    MTG_TRY(ctx)
+    if (!ctx->ref_counter) throw Error(-4, "mtg_ref_repeats_copy: call mtg_set_reference_sharded first");
+    const uint64_t n = ctx->ref_counter->nb_solid();
+    if (capacity < n) throw Error(-1, "mtg_ref_repeats_copy: capacity too small");
+    const size_t ksz = ctx->p.kmer_size <= 31 ? 8 : 16;
+    if (n) MTG_CUDA(cudaMemcpyAsync(d_out, ctx->ref_counter->solid_keys_device(), n * ksz, cudaMemcpyDeviceToDevice, ctx->stream));
+    MTG_CATCH
+}
+int mtg_set_ref_repeats_device(mtg_ctx* ctx, const void* d_keys, uint64_t n) {
+    MTG_TRY(ctx)
+    WallTimer w(ctx->wall_set_reference);
+    ctx->graph->set_ref_repeats(d_keys, n);
+    ctx->ref_repeated = n;
+    ctx->ref_counter.reset();
+    MTG_CATCH
+}
 
 int mtg_contains_batch(mtg_ctx* ctx, const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) {
     MTG_TRY(ctx) MTG_CUDA(cudaSetDevice(ctx->p.device)); ctx->graph->contains_batch(lo, ctx->p.kmer_size > 31 ? hi : nullptr, n, out); MTG_CATCH

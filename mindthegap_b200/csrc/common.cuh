@@ -204,6 +204,11 @@ MTG_HD uint64_t key_hash(u128 k) { return mix64(k.lo ^ mix64(k.hi + 0x9E3779B97F
 // top 31 bits of (min(m-mer, revcomp) * golden-ratio constant); the minimizer of a k-mer is the minimum over its k-m+1 m-mers.
 // Strand-symmetric, so a k-mer and its reverse complement get the same value. 2m <= 30 bits.
 MTG_HD uint32_t mmer_hash(uint32_t fwd, uint32_t rc) { return ((fwd < rc ? fwd : rc) * 0x9E3779B1u) >> 1; }
+// Bin of a minimizer value (a second mix folded to bin_bits <= 20 bits, count.cu) and the GPU that owns the bin when N GPUs share
+// the work: the count stage partitions super-k-mers by it and the exact table gives the same GPU the k-mers' table range, so a
+// rank's solid k-mers are exactly the k-mers of its range (no exchange between counting and the table build).
+MTG_HD uint32_t mini_bin(uint32_t mini, int bin_bits) { return (mini * 0x85EBCA6Bu) >> (32 - bin_bits); }
+MTG_HD uint32_t mini_owner(uint32_t mini, int bin_bits, uint32_t nparts) { return mini_bin(mini, bin_bits) % nparts; }
 MTG_HD uint32_t mmer_revcomp(uint32_t fwd, int m) {   // reverse complement of an m-mer held in the low 2m bits
     uint32_t r = 0;
 #ifdef __CUDA_ARCH__

@@ -138,7 +138,7 @@ MTG_HD uint64_t make_record(uint64_t pos, uint32_t len, uint32_t mini) {
 // the shared-memory count table once the average bin nears its size; folding 4^m/2 minimizers into 2^20 bins averages
 // that skew out (relative sigma ~ 3.2 / sqrt(minimizers per bin)).
 // mmer_hash itself lives in common.cuh (the exact table is placed by the same kind of minimizer).
-MTG_D uint32_t mini_bin(uint32_t mini, int bin_bits) { return (mini * 0x85EBCA6Bu) >> (32 - bin_bits); }
+// mini_bin / mini_owner live in common.cuh.
 
 MTG_D int sk_vidx(int q) { return q + (q >> 3); }  // padded index: threads reading element e of their 8-run hit 32 distinct banks
 
@@ -671,6 +671,23 @@ __global__ void __launch_bounds__(OW_THREADS) owner_scatter_kernel(const uint64_
         __syncthreads();
     }
 }
+// records whose bin is owned by `part` (bin % nparts == part), order preserved per warp
+__global__ void __launch_bounds__(256) owner_filter_kernel(const uint64_t* __restrict__ records, uint64_t nrec, int nparts, int part,
+                                                           uint64_t* __restrict__ out, unsigned long long* __restrict__ nout) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t nround = (nrec + 31) & ~31ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i < nrec ? records[i] : 0;
+        const bool keep = i < nrec && (int)((uint32_t)(r & ((1u << REC_LEN_SHIFT) - 1)) % (uint32_t)nparts) == part;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, keep);
+        if (b) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(nout, (unsigned long long)__popc(b));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (keep) out[base + __popc(b & ((1u << lane) - 1))] = r;
+        }
+    }
+}
 // per-bin histogram (records << 36 | instances) and instance total of an imported record list
 __global__ void __launch_bounds__(256) mhist_from_records_kernel(const uint64_t* __restrict__ records, uint64_t nrec,
                                                                  unsigned long long* __restrict__ mhist, unsigned long long* __restrict__ nvalid) {
@@ -938,6 +955,42 @@ public:
         }
         MTG_CUDA(cudaGetLastError());
         MTG_CUDA(cudaStreamSynchronize(stream_));
+    }
+    void restrict_owner(int nparts, int part) override {
+        if (nparts <= 1) return;
+        resolve_partitioning(0);
+        DevBuf<unsigned long long> d_n(1);
+        uint64_t total = 0;
+        for (auto& b : batches_) {
+            if (!b.nrec) continue;
+            DevBuf<uint64_t> kept(b.nrec);
+            d_n.zero(stream_);
+            int grid = (int)std::min<uint64_t>((b.nrec + 255) / 256, (uint64_t)sm_count_ * 8);
+            owner_filter_kernel<<<grid, 256, 0, stream_>>>(b.recs.p, b.nrec, nparts, part, kept.p, d_n.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+            unsigned long long n = 0;
+            MTG_CUDA(cudaMemcpyAsync(&n, d_n.p, 8, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaStreamSynchronize(stream_));
+            b.recs = std::move(kept);
+            b.nrec = n;
+            total += n;
+        }
+        // bin histogram and instance count of what is left
+        mhist_.zero(stream_);
+        MTG_CUDA(cudaMemsetAsync(counters_.p + 1, 0, 8, stream_));
+        for (auto& b : batches_) {
+            if (!b.nrec) continue;
+            int grid = (int)std::min<uint64_t>((b.nrec + 255) / 256, (uint64_t)sm_count_ * 8);
+            mhist_from_records_kernel<<<grid, 256, 0, stream_>>>(b.recs.p, b.nrec, mhist_.p, counters_.p + 1);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+        }
+        unsigned long long nv = 0;
+        MTG_CUDA(cudaMemcpyAsync(&nv, counters_.p + 1, 8, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaStreamSynchronize(stream_));
+        nvalid_total_ = nv;
+        st_.nb_records = total;
     }
     void import_external(const uint64_t* d_packed, const uint32_t* d_inv, uint64_t nwords, const uint64_t* d_records, uint64_t nrecords) override {
         for (auto& b : batches_) b.recs.release();

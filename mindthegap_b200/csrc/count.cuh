@@ -42,6 +42,9 @@ public:
     virtual void local_info(uint64_t* nwords, uint64_t* nrecords, uint64_t* nvalid) const = 0;
     virtual void copy_packed(uint64_t* d_packed_out, uint32_t* d_inv_out, uint64_t capacity_words) = 0;
     virtual void partition_records(int nparts, uint64_t pos_offset_bases, uint64_t* d_out, uint64_t* counts_host) = 0;
+    // keep only the records of the minimizer bins this rank owns (bin % nparts == part), before run(): N GPUs that all hold the
+    // same sequences (the reference) then count disjoint shares of its k-mers
+    virtual void restrict_owner(int nparts, int part) = 0;
     virtual void import_external(const uint64_t* d_packed, const uint32_t* d_inv, uint64_t nwords, const uint64_t* d_records, uint64_t nrecords) = 0;
     virtual const CountStats& stats() const = 0;
     virtual const uint64_t* histogram() const = 0;  // host, HISTO_MAX+1 entries, valid after finish

@@ -68,12 +68,12 @@ __global__ void __launch_bounds__(256) table_init_kernel(uint4* __restrict__ tab
 // ---- exact table build (graph.cuh "Placement"): bin histogram -> bucket offsets (exclusive scan) -> insert
 // pass 1: solid k-mers per bin of range `shard` (cnt has nbps entries)
 template <class K>
-__global__ void __launch_bounds__(256) bin_count_kernel(const K* __restrict__ keys, uint64_t n, int k, int tm, uint32_t nshards, uint32_t nbps,
+__global__ void __launch_bounds__(256) bin_count_kernel(const K* __restrict__ keys, uint64_t n, int k, int tm, int bin_bits, uint32_t nshards, uint32_t nbps,
                                                         uint32_t shard, unsigned int* __restrict__ cnt, int* __restrict__ err) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t h = mini_place_hash(kmer_minimizer(keys[i], k, tm));
-        if (place_shard(h, nshards) != shard) { *err = 5; continue; }   // a k-mer routed to the wrong range
-        atomicAdd(&cnt[place_bin(h, nshards, nbps)], 1u);
+        const uint32_t mini = kmer_minimizer(keys[i], k, tm);
+        if (place_shard(mini, bin_bits, nshards) != shard) { *err = 5; continue; }   // a k-mer routed to the wrong range
+        atomicAdd(&cnt[place_bin(mini, nbps)], 1u);
     }
 }
 // pass 2: buckets per bin = ceil(cnt / BIN_KEYS_PER_BUCKET); off[i] = base + exclusive prefix sum, off[nbps] = terminator.
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) table_build_kernel(const K* __restrict__ 
         Chain c;
         c.o0 = c.nb = c.b = 0;
         uint32_t probes = 0;
-        if (pending && !chain_begin<K>(g.bin_off, g.nbps, g.nshards, key, kmer_minimizer(key, g.k, g.tm), c)) { *err = 1; pending = false; }
+        if (pending && !chain_begin<K>(g, key, kmer_minimizer(key, g.k, g.tm), c)) { *err = 1; pending = false; }
         while (__any_sync(0xFFFFFFFFu, pending)) {
             K* bucket = table + (uint64_t)c.b * STRIDE;
             unsigned emask = 0;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ key
             const unsigned byte = succ ? (adj | (other << 4)) : (other | (adj << 4));
             Chain cx;
             cx.o0 = cx.nb = cx.b = 0;
-            bool searching = active && chain_begin<K>(g.bin_off, g.nbps, g.nshards, x, mt.all, cx);
+            bool searching = active && chain_begin<K>(g, x, mt.all, cx);
             if (active && !searching) *err = 4;
             K* const trw = table_rw;
             uint32_t walked = 0;
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(256) mphf_compact_kernel(const K* __restrict__
 // destination (destinations are few and hot; same scheme as the super-k-mer records, count.cu)
 static const int KO_MAX = 64, KO_THREADS = 256, KO_PER = 4, KO_TILE = KO_THREADS * KO_PER;
 template <class K>
-__global__ void __launch_bounds__(KO_THREADS) key_owner_count_kernel(const K* __restrict__ keys, uint64_t n, uint32_t nshards, int k, int tm,
+__global__ void __launch_bounds__(KO_THREADS) key_owner_count_kernel(const K* __restrict__ keys, uint64_t n, uint32_t nshards, int k, int tm, int bin_bits,
                                                                      unsigned long long* __restrict__ counts) {
     __shared__ unsigned int s_cnt[KO_MAX];
     if (threadIdx.x < KO_MAX) s_cnt[threadIdx.x] = 0;
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(KO_THREADS) key_owner_count_kernel(const K* __
     const int lane = threadIdx.x & 31;
     const uint64_t nround = (n + 31) & ~31ull;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t d = i < n ? shard_of(mini_place_hash(kmer_minimizer(keys[i], k, tm)), nshards) : 0xFFFFFFFFu;
+        const uint32_t d = i < n ? place_shard(kmer_minimizer(keys[i], k, tm), bin_bits, nshards) : 0xFFFFFFFFu;
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
         if (d != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[d], (unsigned)__popc(peers));
     }
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(KO_THREADS) key_owner_count_kernel(const K* __
     if (threadIdx.x < nshards && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 template <class K>
-__global__ void __launch_bounds__(KO_THREADS) key_owner_scatter_kernel(const K* __restrict__ keys, uint64_t n, uint32_t nshards, int k, int tm,
+__global__ void __launch_bounds__(KO_THREADS) key_owner_scatter_kernel(const K* __restrict__ keys, uint64_t n, uint32_t nshards, int k, int tm, int bin_bits,
                                                                        unsigned long long* __restrict__ cursor, K* __restrict__ out) {
     __shared__ unsigned int s_cnt[KO_MAX];
     __shared__ unsigned long long s_base[KO_MAX];
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(KO_THREADS) key_owner_scatter_kernel(const K* 
         for (int j = 0; j < KO_PER; j++) {
             const uint64_t i = tile * KO_TILE + (uint64_t)j * KO_THREADS + threadIdx.x;
             r[j] = i < n ? keys[i] : K(0);
-            dest[j] = i < n ? shard_of(mini_place_hash(kmer_minimizer(r[j], k, tm)), nshards) : 0xFFFFFFFFu;
+            dest[j] = i < n ? place_shard(kmer_minimizer(r[j], k, tm), bin_bits, nshards) : 0xFFFFFFFFu;
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dest[j]);
             const int leader = __ffs(peers) - 1;
             uint32_t base = 0;
@@ -790,6 +790,7 @@ template <class K> class Graph : public IGraph {
     uint32_t nshards_ = 1;    // ranges (= GPUs that built the table)
     int tm_ = 0;              // minimizer length that places k-mers in the table
     DevBuf<uint32_t> binoff_; // (nbps_ + 1) global bucket offsets per range
+    int bin_bits() const { return std::min(2 * tm_, 20); }   // the count stage's folding of minimizer values into bins (count.cu resolve_partitioning)
     void set_geometry(uint64_t nkeys_per_range) {
         nbps_ = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nkeys_per_range / BIN_TARGET_KEYS, 1), 0x7FFFFFFFull);
         nbuckets_ = nkeys_per_range / BinCfg<K>::KEYS_PER_BUCKET + nbps_ + 1;
@@ -801,7 +802,7 @@ template <class K> class Graph : public IGraph {
         cnt.zero(stream_);
         const uint32_t ntiles = (nbps_ + BS_TILE - 1) / BS_TILE;
         DevBuf<unsigned int> tiles(ntiles);
-        if (n) bin_count_kernel<K><<<grid_for(n), 256, 0, stream_>>>(keys, n, k_, tm_, nshards_, nbps_, shard, cnt.p, err_.p);
+        if (n) bin_count_kernel<K><<<grid_for(n), 256, 0, stream_>>>(keys, n, k_, tm_, bin_bits(), nshards_, nbps_, shard, cnt.p, err_.p);
         const unsigned kpb = BinCfg<K>::KEYS_PER_BUCKET;
         bin_tile_sum_kernel<<<ntiles, BS_THREADS, 0, stream_>>>(cnt.p, nbps_, kpb, tiles.p);
         bin_tile_scan_kernel<<<1, 1024, 0, stream_>>>(tiles.p, ntiles, nbuckets_, err_.p);
@@ -839,7 +840,7 @@ template <class K> class Graph : public IGraph {
         GraphView<K> g;
         memset(&g, 0, sizeof(g));
         g.k = k_;
-        g.table = table_.p; g.nbuckets = nbuckets_; g.bin_off = binoff_.p; g.nbps = nbps_; g.nshards = nshards_; g.tm = tm_;
+        g.table = table_.p; g.nbuckets = nbuckets_; g.bin_off = binoff_.p; g.nbps = nbps_; g.nshards = nshards_; g.tm = tm_; g.bin_bits = bin_bits();
         g.bloom = bloom_.bits.p; g.bloom_tai = bloom_.tai; g.bloom_nhash = bloom_.nhash;
         g.cascading = cascading_ ? 1 : 0;
         g.b2 = b2_.bits.p; g.b2_tai = b2_.tai; g.b3 = b3_.bits.p; g.b3_tai = b3_.tai; g.b4 = b4_.bits.p; g.b4_tai = b4_.tai;
@@ -1128,7 +1129,7 @@ public:
         DevBuf<unsigned long long> d_counts(KO_MAX), d_cursor(KO_MAX);
         d_counts.zero(stream_);
         const K* keys = (const K*)d_keys;
-        if (n) { key_owner_count_kernel<K><<<grid_for(n), KO_THREADS, 0, stream_>>>(keys, n, nshards, k_, tm_, d_counts.p); st_.launches++; }
+        if (n) { key_owner_count_kernel<K><<<grid_for(n), KO_THREADS, 0, stream_>>>(keys, n, nshards, k_, tm_, bin_bits(), d_counts.p); st_.launches++; }
         unsigned long long cnt[KO_MAX], cur[KO_MAX];
         MTG_CUDA(cudaMemcpyAsync(cnt, d_counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, stream_));
         MTG_CUDA(cudaStreamSynchronize(stream_));
@@ -1136,7 +1137,7 @@ public:
         for (int d = 0; d < KO_MAX; d++) { cur[d] = off; if ((uint32_t)d < nshards) { counts_host[d] = cnt[d]; off += cnt[d]; } }
         MTG_CUDA(cudaMemcpyAsync(d_cursor.p, cur, sizeof(cur), cudaMemcpyHostToDevice, stream_));
         if (n) {
-            key_owner_scatter_kernel<K><<<grid_for((n + KO_PER - 1) / KO_PER, KO_THREADS), KO_THREADS, 0, stream_>>>(keys, n, nshards, k_, tm_, d_cursor.p, (K*)d_out);
+            key_owner_scatter_kernel<K><<<grid_for((n + KO_PER - 1) / KO_PER, KO_THREADS), KO_THREADS, 0, stream_>>>(keys, n, nshards, k_, tm_, bin_bits(), d_cursor.p, (K*)d_out);
             st_.launches++;
         }
         MTG_CUDA(cudaGetLastError());

@@ -42,7 +42,7 @@ template <class K> struct GraphView {
     const uint32_t* bin_off;  // (nbps + 1) entries per range: GLOBAL bucket index of the first bucket of each bin of the range
     uint32_t nbps;            // bins per range
     uint32_t nshards;
-    int tm;
+    int tm, bin_bits;         // minimizer length and bin folding of the count stage (min(2 tm, 20)): range = mini_owner(minimizer)
     // Bloom filters as little-endian u32 words (bit pos -> word pos>>5, bit pos&31 == byte pos>>3, bit pos&7)
     const uint32_t* bloom; Mod bloom_tai; int bloom_nhash;      // BloomNeighborCoherent (main)
     int cascading;                                                   // 0 -> cFP is the plain sorted set `cfp`
@@ -235,30 +235,26 @@ MTG_HD int table_minimizer_len(int k) { return k - 1 < 15 ? k - 1 : 15; }   // d
 // run length of a bin = ceil(keys / kpb) buckets, kpb = 10 of 14 slots (u64) or 5 of 7 (u128): a run is never full
 template <class K> struct BinCfg { static const int KEYS_PER_BUCKET = sizeof(K) == 8 ? 10 : 5; };
 static const int BIN_TARGET_KEYS = 12;       // bins per range = keys / 12 (+1)
-// placement hash of a minimizer value: its top 32 bits select the range (GPU) and, with the remainder, the bin inside the range
+// A minimizer value selects the range (= the GPU that counted it: mini_owner, common.cuh) and, by a hash, the bin inside the range
 MTG_HD uint64_t mini_place_hash(uint32_t mini) { return mix64((uint64_t)mini + 0x632BE59BD9B4E019ULL); }
-MTG_HD uint32_t place_shard(uint64_t h, uint32_t nshards) { return shard_of(h, nshards); }
-MTG_HD uint32_t place_bin(uint64_t h, uint32_t nshards, uint32_t nbps) {   // bin inside its range
-    const uint32_t frac = (uint32_t)((h >> 32) * (uint64_t)nshards);
-    return (uint32_t)(((uint64_t)frac * nbps) >> 32);
-}
+MTG_HD uint32_t place_shard(uint32_t mini, int bin_bits, uint32_t nshards) { return nshards > 1 ? mini_owner(mini, bin_bits, nshards) : 0u; }
+MTG_HD uint32_t place_bin(uint32_t mini, uint32_t nbps) { return (uint32_t)(((mini_place_hash(mini) & 0xFFFFFFFFull) * nbps) >> 32); }
 // the run of buckets of a key's bin and the bucket the key starts at
 struct Chain { uint32_t o0, nb, b; };
-template <class K> MTG_D bool chain_begin(const uint32_t* __restrict__ bin_off, uint32_t nbps, uint32_t nshards, K key, uint32_t mini, Chain& c) {
-    const uint64_t h = mini_place_hash(mini);
-    const uint32_t idx = place_shard(h, nshards) * (nbps + 1) + place_bin(h, nshards, nbps);
-    c.o0 = __ldg(bin_off + idx);
-    c.nb = __ldg(bin_off + idx + 1) - c.o0;
+template <class K> MTG_D bool chain_begin(const GraphView<K>& g, K key, uint32_t mini, Chain& c) {
+    const uint32_t idx = place_shard(mini, g.bin_bits, g.nshards) * (g.nbps + 1) + place_bin(mini, g.nbps);
+    c.o0 = __ldg(g.bin_off + idx);
+    c.nb = __ldg(g.bin_off + idx + 1) - c.o0;
     c.b = c.o0 + (uint32_t)(((uint64_t)key_hash32(key) * c.nb) >> 32);
     return c.nb != 0;
 }
 MTG_D void chain_next(Chain& c) { c.b = c.b + 1 == c.o0 + c.nb ? c.o0 : c.b + 1; }
 
 // `mini` = kmer_minimizer(key, k, tm) (callers that roll it pass it in). Returns the slot or -1; *bucket_out = global bucket.
-template <class K> MTG_D int table_find(const K* __restrict__ table, const uint32_t* __restrict__ bin_off, uint32_t nbps, uint32_t nshards, K key, uint32_t mini,
-                                        uint64_t* bucket_out, unsigned* adj) {
+template <class K> MTG_D int table_find(const GraphView<K>& g, K key, uint32_t mini, uint64_t* bucket_out, unsigned* adj) {
+    const K* __restrict__ table = g.table;
     Chain c;
-    if (!chain_begin<K>(bin_off, nbps, nshards, key, mini, c)) return -1;
+    if (!chain_begin<K>(g, key, mini, c)) return -1;
     // Slots of a bucket fill in ascending order (every builder claims the lowest slot it sees empty and a slot never empties),
     // so "the bucket has an empty slot" == "its last slot is empty": the chain ends there.
     const uint32_t k0 = (uint32_t)lo64(key), k1 = (uint32_t)(lo64(key) >> 32), k2 = (uint32_t)hi64(key), k3 = (uint32_t)(hi64(key) >> 32);
@@ -290,11 +286,11 @@ template <class K> MTG_D int table_find(const K* __restrict__ table, const uint3
     return -1;
 }
 template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key, uint32_t mini) {
-    return table_find<K>(g.table, g.bin_off, g.nbps, g.nshards, key, mini, nullptr, nullptr) >= 0;
+    return table_find<K>(g, key, mini, nullptr, nullptr) >= 0;
 }
 template <class K> MTG_D bool table_contains(const GraphView<K>& g, K key) { return table_contains(g, key, kmer_minimizer(key, g.k, g.tm)); }
 template <class K> MTG_D bool table_lookup(const GraphView<K>& g, K key, unsigned& adj) {
-    return table_find<K>(g.table, g.bin_off, g.nbps, g.nshards, key, kmer_minimizer(key, g.k, g.tm), nullptr, &adj) >= 0;
+    return table_find<K>(g, key, kmer_minimizer(key, g.k, g.tm), nullptr, &adj) >= 0;
 }
 
 // Graph::contains for a CANONICAL k-mer. *used_fallback is set when the exact table missed and the Bloom emulation
@@ -332,7 +328,7 @@ template <class K> MTG_D void node_probe(const GraphView<K>& g, K fwd, bool alwa
     const K can = canonical(fwd, g.k);
     unsigned adj = 0;
     if (!have_mini) mini = kmer_minimizer(can, g.k, g.tm);
-    exact = table_find<K>(g.table, g.bin_off, g.nbps, g.nshards, can, mini, nullptr, &adj) >= 0;
+    exact = table_find<K>(g, can, mini, nullptr, &adj) >= 0;
     din = dout = 0;
     if (exact) {
         in = true;

@@ -157,6 +157,7 @@ class DistFind:
         self.timing = {}
         self._t = None
         self._minimizer_agreed = False
+        self._minimizer = 1 << 30
         # Everything torch does for this find (allocations, copies, NCCL collectives) runs on the LIBRARY's stream
         # (mtg_get_stream): kernels and collectives are then ordered on the device and no host synchronisation is needed
         # between them (torch makes the current stream wait for a collective's completion, not the host).
@@ -202,8 +203,12 @@ class DistFind:
     def _gather_texts(self, texts):
         """All ranks' (chromosome index, breakpoints, vcf) lists on rank 0, as one padded uint8 all-gather (gather_object
         pickles through several small collectives, which costs milliseconds)."""
-        import json
-        blob = np.frombuffer(json.dumps(texts).encode(), dtype=np.uint8)
+        import struct
+        parts = [struct.pack("<Q", len(texts))]
+        for ci, bk, vcf in texts:
+            b1, b2 = bk.encode(), vcf.encode()
+            parts += [struct.pack("<QQQ", ci, len(b1), len(b2)), b1, b2]
+        blob = np.frombuffer(b"".join(parts), dtype=np.uint8)
         sizes = self._all_gather_i64(len(blob))
         m = max(max(sizes), 1)
         t = torch.zeros(m, dtype=torch.uint8, device=self.device)
@@ -213,7 +218,18 @@ class DistFind:
         if self.rank != 0:
             return None
         host = out.cpu().numpy()
-        return [json.loads(host[r * m: r * m + sizes[r]].tobytes().decode()) for r in range(self.world)]
+        res = []
+        for r in range(self.world):
+            raw = host[r * m: r * m + sizes[r]].tobytes()
+            (n,) = struct.unpack_from("<Q", raw, 0)
+            o, items = 8, []
+            for _ in range(n):
+                ci, l1, l2 = struct.unpack_from("<QQQ", raw, o)
+                o += 24
+                items.append((ci, raw[o:o + l1].decode(), raw[o + l1:o + l1 + l2].decode()))
+                o += l1 + l2
+            res.append(items)
+        return res
 
     # ---- stage 1: count
     def push_reads(self, stream=None, dev_ptr=None, nbytes=None, total_bases=None):
@@ -226,7 +242,8 @@ class DistFind:
         if not self._minimizer_agreed:
             t = torch.tensor([int(total_bases) if total_bases is not None else n], dtype=torch.int64, device=self.device)
             self.c.all_reduce(t, "sum")
-            self.e.set_minimizer_size(13 if int(t.item()) >= (1 << 30) else min(10, self.k - 1))
+            self._minimizer = 13 if int(t.item()) >= (1 << 30) else min(10, self.k - 1)
+            self.e.set_minimizer_size(self._minimizer)
             self._minimizer_agreed = True
         if dev_ptr is not None:
             self._sync()
@@ -363,12 +380,18 @@ class DistFind:
 
     def _build_sharded(self):
         e, W, kw = self.e, self.world, self.e.key_words
-        # solid k-mers -> the rank that owns their table range
+        # solid k-mers -> the rank that owns their table range. The range owner of a k-mer is the owner of its minimizer bin, the same
+        # function the records were exchanged by, so a rank's solid k-mers already ARE its range (no exchange) whenever the table
+        # can use the counter's minimizer length (k - 1 >= m); otherwise they are re-partitioned.
         n_local = e.nb_solid_local()
         send = torch.empty(max(n_local, 1) * kw, dtype=torch.int64, device=self.device)
         self._sync()
-        counts = e.solid_partition(W, send)
-        share, n_share = self._all_to_all_keys(send, counts)
+        if self.k - 1 >= self._minimizer and getattr(e, "solid_share_is_table_range", False) and not os.environ.get("MTG_DIST_REPARTITION"):
+            e.solid_copy(send, None)
+            share, n_share = send, n_local
+        else:
+            counts = e.solid_partition(W, send)
+            share, n_share = self._all_to_all_keys(send, counts)
         shares = self._all_gather_i64(n_share)
         self.nb_solid = sum(shares)
         self.exchange_bytes["alltoall_solid"] = int(8 * kw * n_share)
@@ -464,7 +487,19 @@ class DistFind:
         else:
             ref_dev = torch.from_numpy(np.ascontiguousarray(ref_stream)).to(self.device)   # the whole reference, once
         self._sync()
-        if hasattr(e, "set_reference_device") and self.device.type == "cuda":
+        if W > 1 and hasattr(e, "set_reference_sharded") and self.device.type == "cuda":
+            # every rank counts the (k-1)-mers of its own minimizer bins; the (few) repeated ones are gathered
+            kw = e.key_words
+            n_local = e.set_reference_sharded(ref_dev.data_ptr(), ref_dev.numel(), W, self.rank)
+            sizes = self._all_gather_i64(n_local)
+            cap = max(max(sizes), 1)
+            part = torch.zeros(cap * kw, dtype=torch.int64, device=self.device)
+            e.ref_repeats_copy(part, cap)
+            allp = torch.empty(cap * kw * W, dtype=torch.int64, device=self.device)
+            self.c.all_gather_into_tensor(allp, part)
+            rep = torch.cat([allp[r * cap * kw: r * cap * kw + sizes[r] * kw] for r in range(W)]) if sum(sizes) else part
+            e.set_ref_repeats_device(rep, sum(sizes))
+        elif hasattr(e, "set_reference_device") and self.device.type == "cuda":
             e.set_reference_device(ref_dev.data_ptr(), ref_dev.numel())
         else:
             e.set_reference(ref_stream.cpu().numpy() if isinstance(ref_stream, torch.Tensor) else ref_stream)
