@@ -251,6 +251,10 @@ int mtg_replay_sequence(mtg_ctx* ctx, const char* name, const char* seq, uint64_
 const char* mtg_breakpoints_text(mtg_ctx* ctx, uint64_t* nbytes);
 const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes);
 int mtg_reset_outputs(mtg_ctx* ctx);
+/* Host-only helper for the merge of several scans (one per chromosome / per GPU): the shared bkpt<N> ids (src/FindBreakpoints.hpp:
+ * 872-875) of `in` shifted by `offset`. kind 0 = .breakpoints text, 1 = VCF records. out = NULL sizes the result; returns its
+ * length (-1: cap too small); *max_id = largest id written (0 when the text holds none). */
+int64_t mtg_renumber_text(const char* in, uint64_t nbytes, int32_t kind, uint64_t offset, char* out, uint64_t cap, uint64_t* max_id);
 /* -nb-cores (src/Finder.cpp:137, forwarded to Graph::create): host threads the event replay may use; the scan is cut at
  * steady points of the gap machine and the chunks are replayed concurrently with byte-identical output (the reference's
  * scan itself is single-threaded, src/Finder.cpp:597-600). 0 = all cores (the tool's default). */

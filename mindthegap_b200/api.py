@@ -45,7 +45,7 @@ EXPORTS = [
     "mtg_count_run", "mtg_count_filter", "mtg_solid_copy", "mtg_graph_build_device", "mtg_sequence_features_device2", "mtg_replay_sequence",
     "mtg_graph_build_begin", "mtg_graph_critical", "mtg_graph_critical_copy", "mtg_graph_build_end", "mtg_set_host_threads", "mtg_set_minimizer_size", "mtg_get_minimizer_size",
     "mtg_solid_partition", "mtg_partition_keys", "mtg_graph_shard_begin", "mtg_graph_shard_critical", "mtg_graph_adj_pack", "mtg_graph_adj_unpack",
-    "mtg_graph_branching", "mtg_export_dsk_partitions", "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_mphf_level", "mtg_graph_shard_mphf_begin", "mtg_graph_shard_mphf_plan", "mtg_graph_shard_mphf_step", "mtg_graph_shard_mphf_tail", "mtg_get_stream", "mtg_set_reference_sharded", "mtg_ref_repeats_copy", "mtg_set_ref_repeats_device", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
+    "mtg_graph_branching", "mtg_export_dsk_partitions", "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_mphf_level", "mtg_graph_shard_mphf_begin", "mtg_graph_shard_mphf_plan", "mtg_graph_shard_mphf_step", "mtg_graph_shard_mphf_tail", "mtg_get_stream", "mtg_renumber_text", "mtg_set_reference_sharded", "mtg_ref_repeats_copy", "mtg_set_ref_repeats_device", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
 ]
 
 _lib = None
@@ -149,6 +149,8 @@ def load_library():
     L.mtg_set_reference_sharded.argtypes = [vp, vp, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]
     L.mtg_ref_repeats_copy.argtypes = [vp, vp, C.c_uint64]
     L.mtg_set_ref_repeats_device.argtypes = [vp, vp, C.c_uint64]
+    L.mtg_renumber_text.restype = C.c_int64
+    L.mtg_renumber_text.argtypes = [C.c_char_p, C.c_uint64, C.c_int32, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.mtg_get_stream.restype = C.c_void_p
     L.mtg_get_stream.argtypes = [vp]
     L.mtg_graph_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]
@@ -286,6 +288,19 @@ def run_h5_tool(verb, h5, binp):
     r = subprocess.run([exe, verb, h5, binp], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=os.path.dirname(os.path.abspath(h5)) or ".")
     if r.returncode != 0:
         raise MtgError("mtg_h5 %s failed: %s" % (verb, r.stderr.strip()[-500:]))
+
+
+def renumber_text(text, kind, offset):
+    """(text with every bkpt id shifted by offset, largest id in the result); kind 0 = .breakpoints, 1 = VCF records. C++ (capi.cu)."""
+    L = load_library()
+    raw = text.encode() if isinstance(text, str) else bytes(text)
+    mx = C.c_uint64()
+    cap = len(raw) + 24 * (raw.count(b"\n") + 1)
+    buf = C.create_string_buffer(cap)
+    n = L.mtg_renumber_text(raw, len(raw), kind, int(offset), buf, cap, C.byref(mx))
+    if n < 0:
+        raise MtgError("mtg_renumber_text: buffer too small")
+    return buf.raw[:n].decode(), int(mx.value)
 
 
 def _ptr(a):

@@ -851,6 +851,39 @@ const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes) {
     if (nbytes) *nbytes = s.size();
     return s.c_str();
 }
+// Shift the shared `bkpt<N>` ids (src/FindBreakpoints.hpp:872-875) of output text by `offset`: kind 0 = .breakpoints (">bkpt<N>_" at
+// line starts), kind 1 = VCF records (third column "bkpt<N>"). Pure host function (no context): N ranks renumber their own
+// chromosomes in parallel once the id counts of the earlier chromosomes are known. Returns the output size (call with out = NULL
+// to size the buffer: at most nbytes + 20 per record), or -1 when cap is too small.
+int64_t mtg_renumber_text(const char* in, uint64_t nbytes, int32_t kind, uint64_t offset, char* out, uint64_t cap, uint64_t* max_id) {
+    uint64_t o = 0, mx = 0;
+    auto put = [&](const char* p, uint64_t n) { if (out && o + n <= cap) memcpy(out + o, p, n); o += n; };
+    uint64_t i = 0;
+    while (i < nbytes) {
+        const char* nl = (const char*)memchr(in + i, '\n', nbytes - i);
+        const uint64_t e = nl ? (uint64_t)(nl - in) + 1 : nbytes;   // line [i, e)
+        uint64_t idpos = e;                                          // where the digits start
+        if (kind == 0) { if (e - i > 5 && !memcmp(in + i, ">bkpt", 5)) idpos = i + 5; }
+        else {
+            const char* t1 = (const char*)memchr(in + i, '\t', e - i);
+            const char* t2 = t1 ? (const char*)memchr(t1 + 1, '\t', e - (uint64_t)(t1 + 1 - in)) : nullptr;
+            if (t2 && e - (uint64_t)(t2 + 1 - in) > 4 && !memcmp(t2 + 1, "bkpt", 4)) idpos = (uint64_t)(t2 + 1 - in) + 4;
+        }
+        if (idpos < e && in[idpos] >= '0' && in[idpos] <= '9') {
+            uint64_t id = 0, j = idpos;
+            while (j < e && in[j] >= '0' && in[j] <= '9') id = id * 10 + (uint64_t)(in[j++] - '0');
+            char num[32];
+            const int n = snprintf(num, sizeof num, "%llu", (unsigned long long)(id + offset));
+            put(in + i, idpos - i); put(num, (uint64_t)n); put(in + j, e - j);
+            if (id + offset > mx) mx = id + offset;
+        } else put(in + i, e - i);
+        i = e;
+    }
+    if (max_id) *max_id = mx;
+    if (out && o > cap) return -1;
+    return (int64_t)o;
+}
+
 int mtg_set_host_threads(mtg_ctx* ctx, int32_t n) {
     MTG_TRY(ctx)
     ctx->host_threads = n < 0 ? 0 : n;

@@ -480,6 +480,7 @@ class DistFind:
         a pinned host tensor, or a tensor already on this rank's device."""
         e, W, k = self.e, self.world, self.k
         self._mark(None)
+        self._nchrom = len(ref_records)
         if ref_stream is None:
             ref_stream = np.concatenate([np.concatenate([s, np.array([10], dtype=np.uint8)]) for _, s in ref_records])
         if isinstance(ref_stream, torch.Tensor):
@@ -573,6 +574,8 @@ class DistFind:
         return self._merge_texts(texts)
 
     def _merge_texts(self, texts):
+        if self.device.type == "cuda" and not os.environ.get("MTG_DIST_PY_RENUMBER"):
+            return self._merge_texts_native(texts)
         # merge on rank 0 in reference order, renumbering the shared ids
         gathered = self._gather_texts(texts)
         self._mark("gather_texts")
@@ -585,6 +588,32 @@ class DistFind:
             bk_out.append(bk); vcf_out.append(vcf)
             offset += used
         return "".join(bk_out), "".join(vcf_out)
+
+    def _merge_texts_native(self, texts):
+        """Every rank shifts the ids of its own chromosomes (C++, mtg_renumber_text) once the id counts of all chromosomes are known
+        (one small all-reduce); rank 0 only concatenates in reference order."""
+        from .api import renumber_text
+        nchrom = self._nchrom
+        used = torch.zeros(nchrom, dtype=torch.int64, device=self.device)
+        local = {}
+        for ci, bk, vcf in texts:
+            _, m1 = renumber_text(bk, 0, 0)
+            _, m2 = renumber_text(vcf, 1, 0)
+            local[ci] = max(m1, m2)
+        if local:
+            used[list(local.keys())] = torch.tensor(list(local.values()), dtype=torch.int64, device=self.device)
+        self.c.all_reduce(used, "sum")
+        offs = np.concatenate([[0], np.cumsum(used.cpu().numpy())])
+        shifted = []
+        for ci, bk, vcf in texts:
+            o = int(offs[ci])
+            shifted.append((ci, renumber_text(bk, 0, o)[0] if o else bk, renumber_text(vcf, 1, o)[0] if o else vcf))
+        gathered = self._gather_texts(shifted)
+        self._mark("gather_texts")
+        if self.rank != 0:
+            return None, None
+        allt = sorted(tuple(t) for part in gathered for t in part)
+        return "".join(t[1] for t in allt), "".join(t[2] for t in allt)
 
     def find(self, ref_records, ref_stream=None):
         if self.lib_stream is None:

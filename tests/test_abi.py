@@ -102,3 +102,18 @@ def test_text_record_cut(lib):
     assert cut(fa, 1) == fa.rindex(b">c") and cut(fa[:11], 1) == 0 and cut(fa[:12], 1) == 11 and cut(fa[:14], 1) == 11
     assert cut(fa, 1, final=True) == len(fa)
     assert cut(b"", 2) == 0 and cut(fq, 0) == 0
+
+
+def test_renumber_text_host_helper_equals_python_merge():
+    """mtg_renumber_text (host-only entry point used by the N-GPU merge) shifts the shared bkpt ids exactly like dist.renumber."""
+    from mindthegap_b200.api import renumber_text
+    from mindthegap_b200.dist import renumber
+    from tests.cases import expected
+    for name in ("syn_small_k31", "full", "full_k63", "one_snp", "n_in_stretch"):
+        bk, vcf, _ = expected(name)
+        for off in (0, 7, 123456):
+            b2, v2, used = renumber(bk, vcf, off)
+            nb, m1 = renumber_text(bk, 0, off)
+            nv, m2 = renumber_text(vcf, 1, off)
+            assert nb == b2 and nv == v2
+            assert max(m1, m2) == (used + off if used else 0)
