@@ -592,26 +592,45 @@ count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ g
     if (tid < SMEM_HIST && hist_s[tid]) atomicAdd(&histo[tid], (unsigned long long)hist_s[tid]);
 }
 
+// candidates -> solid set at the final threshold. A block compacts tiles of 1024 candidates: per-warp ballots, one shared-memory
+// scan, ONE global reservation per tile (a reservation per warp on the single counter serialises in L2).
+static const int FK_PER = 4;
 template <class K>
 __global__ void __launch_bounds__(256) filter_kernel(const K* __restrict__ cand_keys, const uint32_t* __restrict__ cand_cnt, uint64_t ncand,
                                                      uint32_t amin, uint32_t amax, K* __restrict__ out_keys, uint32_t* __restrict__ out_cnt,
                                                      unsigned long long* __restrict__ nout) {
-    const int lane = threadIdx.x & 31;
-    uint64_t n_round = (ncand + 31) / 32 * 32;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t c = i < ncand ? cand_cnt[i] : 0;
-        bool keep = i < ncand && c >= amin && c <= amax;
-        uint32_t b = __ballot_sync(0xFFFFFFFFu, keep);
-        if (b) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(nout, (unsigned long long)__popc(b));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (keep) {
-                unsigned long long o = base + __popc(b & ((1u << lane) - 1));
+    __shared__ uint32_t s_cnt[8 * FK_PER];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t tile_sz = 256 * FK_PER, ntiles = (ncand + tile_sz - 1) / tile_sz;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint32_t c[FK_PER], bal[FK_PER];
+        bool keep[FK_PER];
+#pragma unroll
+        for (int j = 0; j < FK_PER; j++) {
+            const uint64_t i = tile * tile_sz + (uint64_t)j * 256 + threadIdx.x;
+            c[j] = i < ncand ? cand_cnt[i] : 0;
+            keep[j] = i < ncand && c[j] >= amin && c[j] <= amax;
+            bal[j] = __ballot_sync(0xFFFFFFFFu, keep[j]);
+            if (lane == 0) s_cnt[j * 8 + warp] = __popc(bal[j]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            for (int q = 0; q < 8 * FK_PER; q++) { const uint32_t v = s_cnt[q]; s_cnt[q] = run; run += v; }
+            s_base = run ? atomicAdd(nout, (unsigned long long)run) : 0ull;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < FK_PER; j++) {
+            if (keep[j]) {
+                const uint64_t i = tile * tile_sz + (uint64_t)j * 256 + threadIdx.x;
+                const unsigned long long o = s_base + s_cnt[j * 8 + warp] + __popc(bal[j] & ((1u << lane) - 1));
                 out_keys[o] = cand_keys[i];
-                out_cnt[o] = c;
+                out_cnt[o] = c[j];
             }
         }
+        __syncthreads();
     }
 }
 
@@ -1137,7 +1156,7 @@ public:
         solid_keys_.alloc(std::max<uint64_t>(ncand, 1));
         solid_cnt_.alloc(std::max<uint64_t>(ncand, 1));
         if (ncand) {
-            int grid = (int)std::min<uint64_t>((ncand + 255) / 256, (uint64_t)sm_count_ * 16);
+            int grid = (int)std::min<uint64_t>((ncand + 1023) / 1024, (uint64_t)sm_count_ * 16);
             filter_kernel<K><<<grid, 256, 0, stream_>>>(cand_keys.p, cand_cnt.p, ncand, (uint32_t)std::max(thr, 0), amax, solid_keys_.p,
                                                          solid_cnt_.p, counters_.p + 3);
             MTG_CUDA(cudaGetLastError());
