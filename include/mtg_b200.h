@@ -251,6 +251,7 @@ int mtg_replay_sequence(mtg_ctx* ctx, const char* name, const char* seq, uint64_
 const char* mtg_breakpoints_text(mtg_ctx* ctx, uint64_t* nbytes);
 const char* mtg_vcf_text(mtg_ctx* ctx, uint64_t* nbytes);
 int mtg_reset_outputs(mtg_ctx* ctx);
+uint64_t mtg_get_ids_used(mtg_ctx* ctx);   /* bkpt ids handed out since the last reset (the largest id in the texts) */
 /* Host-only helper for the merge of several scans (one per chromosome / per GPU): the shared bkpt<N> ids (src/FindBreakpoints.hpp:
  * 872-875) of `in` shifted by `offset`. kind 0 = .breakpoints text, 1 = VCF records. out = NULL sizes the result; returns its
  * length (-1: cap too small); *max_id = largest id written (0 when the text holds none). */

@@ -308,6 +308,20 @@ uint64_t mtg_text_record_cut(const char* text, uint64_t nbytes, int32_t format, 
 
 // One file of the -in list: raw bytes (plain or gzip, zlib reads both) staged in pinned memory in chunks cut at record starts,
 // parsed and packed on the GPU. Leading bytes before the first header are skipped like BankFasta.cpp:496-501.
+// kseq-style host reader for one file (any FASTA/FASTQ layout BankFasta accepts), bases pushed in 256 MB chunks
+static void count_file_host(mtg_ctx* ctx, const std::string& path) {
+    ICounter* c = reads_counter(ctx);
+    std::string chunk;
+    const size_t CHUNK = 256u << 20;
+    chunk.reserve(CHUNK + (1 << 20));
+    for_each_sequence(path, [&](SeqRecord& r) {
+        chunk += r.seq;
+        chunk += '\n';
+        if (chunk.size() >= CHUNK) { c->push_host(chunk.data(), chunk.size()); MTG_CUDA(cudaStreamSynchronize(ctx->stream)); chunk.clear(); }
+    });
+    if (!chunk.empty()) { c->push_host(chunk.data(), chunk.size()); MTG_CUDA(cudaStreamSynchronize(ctx->stream)); }
+}
+
 static void count_file_text(mtg_ctx* ctx, const std::string& path) {
     gzFile f = gzopen(path.c_str(), "rb");
     if (!f) throw Error(-2, "Cannot open file " + path);
@@ -317,7 +331,7 @@ static void count_file_text(mtg_ctx* ctx, const std::string& path) {
     PinnedBuf buf;
     buf.reserve(cap);
     size_t have = 0, total_read = 0;
-    bool eof = false;
+    bool eof = false, pushed_any = false;
     int fmt = TEXT_AUTO;
     try {
         while (!eof || have) {
@@ -347,7 +361,18 @@ static void count_file_text(mtg_ctx* ctx, const std::string& path) {
                 cap *= 2;
                 continue;
             }
-            if (send) push_text_host(ctx, text, send, fmt);
+            if (send) {
+                try { push_text_host(ctx, text, send, fmt); }
+                catch (const mtg::Error& e) {
+                    // A layout the GPU parser rejects (multi-line FASTQ, FASTA lines starting with '@' / '+': valid for BankFasta).
+                    // Nothing of this file has reached the counter yet: read the whole file with the host reader instead.
+                    if (e.code != -7 || pushed_any) throw;
+                    gzclose(f);
+                    count_file_host(ctx, path);
+                    return;
+                }
+                pushed_any = true;
+            }
             memmove(text, text + cut, have - cut);
             have -= cut;
         }
@@ -367,16 +392,9 @@ int mtg_count_files(mtg_ctx* ctx, const char* uri) {
         for (const std::string& path : files) count_file_text(ctx, path);
         return 0;
     }
-    // MTG_F_HOST_PARSE: the kseq-style host reader (multi-line FASTQ and other layouts the GPU parser rejects; plain text only)
-    std::string chunk;
-    const size_t CHUNK = 256u << 20;
-    chunk.reserve(CHUNK + (1 << 20));
-    for_each_sequence(uri, [&](SeqRecord& r) {
-        chunk += r.seq;
-        chunk += '\n';
-        if (chunk.size() >= CHUNK) { c->push_host(chunk.data(), chunk.size()); MTG_CUDA(cudaStreamSynchronize(ctx->stream)); chunk.clear(); }
-    });
-    if (!chunk.empty()) { c->push_host(chunk.data(), chunk.size()); MTG_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    // MTG_F_HOST_PARSE: the kseq-style host reader for every file
+    (void)c;
+    count_file_host(ctx, uri);
     MTG_CATCH
 }
 
@@ -890,6 +908,10 @@ int mtg_set_host_threads(mtg_ctx* ctx, int32_t n) {
     if (ctx->rp64) ctx->rp64->set_threads(ctx->host_threads);
     if (ctx->rp128) ctx->rp128->set_threads(ctx->host_threads);
     MTG_CATCH
+}
+uint64_t mtg_get_ids_used(mtg_ctx* ctx) {   // bkpt ids handed out since the last reset (the shared counter of src/FindBreakpoints.hpp:872-875)
+    if (!ctx) return 0;
+    return (ctx->rp64 ? ctx->rp64->next_id : ctx->rp128->next_id) - 1;
 }
 int mtg_reset_outputs(mtg_ctx* ctx) {
     MTG_TRY(ctx)

@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(BS_THREADS) bin_tile_sum_kernel(const unsigned
     block_exclusive_scan_u32(acc, s_warp, total);
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
 }
-__global__ void __launch_bounds__(1024) bin_tile_scan_kernel(unsigned int* __restrict__ tile_sum, uint32_t ntiles, uint64_t capacity, int* __restrict__ err) {
+__global__ void __launch_bounds__(1024) bin_tile_scan_kernel(unsigned int* __restrict__ tile_sum, uint32_t ntiles, uint64_t capacity, int* __restrict__ err,
+                                                             unsigned long long* __restrict__ total_out) {
     __shared__ unsigned s_warp[32];
     const uint32_t per = (ntiles + blockDim.x - 1) / blockDim.x;
     const uint32_t b = threadIdx.x * per, e = min(ntiles, b + per);
@@ -115,7 +116,10 @@ __global__ void __launch_bounds__(1024) bin_tile_scan_kernel(unsigned int* __res
     unsigned total;
     unsigned run = block_exclusive_scan_u32(acc, s_warp, total);
     for (uint32_t i = b; i < e; i++) { const unsigned v = tile_sum[i]; tile_sum[i] = run; run += v; }
-    if (threadIdx.x == 0 && (uint64_t)total > capacity) *err = 6;   // the runs do not fit the range (cannot happen: capacity is an upper bound)
+    if (threadIdx.x == 0) {
+        if ((uint64_t)total > capacity) *err = 6;   // the runs do not fit the range (cannot happen: capacity is an upper bound)
+        if (total_out) *total_out = total;
+    }
 }
 __global__ void __launch_bounds__(BS_THREADS) bin_offsets_kernel(const unsigned int* __restrict__ cnt, uint32_t nbps, unsigned kpb, const unsigned int* __restrict__ tile_off,
                                                                  uint32_t base_bucket, uint32_t* __restrict__ off) {
@@ -795,21 +799,36 @@ template <class K> class Graph : public IGraph {
         nbps_ = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nkeys_per_range / BIN_TARGET_KEYS, 1), 0x7FFFFFFFull);
         nbuckets_ = nkeys_per_range / BinCfg<K>::KEYS_PER_BUCKET + nbps_ + 1;
     }
-    // histogram -> offsets -> insert for the keys of range `shard` (all of them when there is one range)
-    void build_range(const K* keys, uint64_t n, uint32_t shard) {
+    // histogram -> offsets -> insert for the keys of range `shard` (all of them when there is one range), in two steps so that a
+    // single-GPU build can size the table exactly: bin_plan counts the k-mers per bin and sums the bucket runs (exact = true reads
+    // the total back: nbuckets_ becomes what the runs need instead of the upper bound), bin_fill writes the offsets and inserts.
+    DevBuf<unsigned int> bin_cnt_, bin_tiles_;
+    void bin_plan(const K* keys, uint64_t n, uint32_t shard, bool exact) {
         if ((uint64_t)nshards_ * nbuckets_ >= 0xFFFFFFFFull) throw Error(-1, "exact table beyond 2^32 buckets");
-        DevBuf<unsigned int> cnt(nbps_);
-        cnt.zero(stream_);
+        bin_cnt_.alloc(nbps_);
+        bin_cnt_.zero(stream_);
         const uint32_t ntiles = (nbps_ + BS_TILE - 1) / BS_TILE;
-        DevBuf<unsigned int> tiles(ntiles);
-        if (n) bin_count_kernel<K><<<grid_for(n), 256, 0, stream_>>>(keys, n, k_, tm_, bin_bits(), nshards_, nbps_, shard, cnt.p, err_.p);
-        const unsigned kpb = BinCfg<K>::KEYS_PER_BUCKET;
-        bin_tile_sum_kernel<<<ntiles, BS_THREADS, 0, stream_>>>(cnt.p, nbps_, kpb, tiles.p);
-        bin_tile_scan_kernel<<<1, 1024, 0, stream_>>>(tiles.p, ntiles, nbuckets_, err_.p);
-        bin_offsets_kernel<<<ntiles, BS_THREADS, 0, stream_>>>(cnt.p, nbps_, kpb, tiles.p, (uint32_t)(shard * nbuckets_), binoff_.p + (uint64_t)shard * (nbps_ + 1));
+        bin_tiles_.alloc(ntiles);
+        if (n) bin_count_kernel<K><<<grid_for(n), 256, 0, stream_>>>(keys, n, k_, tm_, bin_bits(), nshards_, nbps_, shard, bin_cnt_.p, err_.p);
+        bin_tile_sum_kernel<<<ntiles, BS_THREADS, 0, stream_>>>(bin_cnt_.p, nbps_, BinCfg<K>::KEYS_PER_BUCKET, bin_tiles_.p);
+        bin_tile_scan_kernel<<<1, 1024, 0, stream_>>>(bin_tiles_.p, ntiles, nbuckets_, err_.p, counters_.p + 6);
+        MTG_CUDA(cudaGetLastError());
+        st_.launches += n ? 3 : 2;
+        if (exact) {
+            unsigned long long total = 0;
+            MTG_CUDA(cudaMemcpyAsync(&total, counters_.p + 6, 8, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaStreamSynchronize(stream_));
+            nbuckets_ = std::max<uint64_t>(total, 1);
+        }
+    }
+    void bin_fill(const K* keys, uint64_t n, uint32_t shard) {
+        const uint32_t ntiles = (nbps_ + BS_TILE - 1) / BS_TILE;
+        bin_offsets_kernel<<<ntiles, BS_THREADS, 0, stream_>>>(bin_cnt_.p, nbps_, BinCfg<K>::KEYS_PER_BUCKET, bin_tiles_.p, (uint32_t)(shard * nbuckets_),
+                                                               binoff_.p + (uint64_t)shard * (nbps_ + 1));
         if (n) table_build_kernel<K><<<grid_for(n), 256, 0, stream_>>>(keys, n, table_.p, view(), err_.p);
         MTG_CUDA(cudaGetLastError());
-        st_.launches += n ? 5 : 3;
+        st_.launches += n ? 2 : 1;
+        bin_cnt_.release(); bin_tiles_.release();
     }
     BloomDev bloom_, b2_, b3_, b4_, ref_;
     DevBuf<K> cfp_, cfp_list_, final_, crit_list_;   // cfp_: hash set (cfp_slots_ slots); cfp_list_: the same k-mers as a list
@@ -961,12 +980,13 @@ public:
         set_geometry(N);
         nshards_ = 1;
         binoff_.alloc(nbps_ + 1);
+        adj_done_ = false;
+        err_.zero(stream_);
+        bin_plan(keys, N, 0, true);            // nbuckets_ = exactly what the bins' runs need
         table_.alloc(nbuckets_ * TableCfg<K>::STRIDE);
         table_init_kernel<<<grid_for(nbuckets_ * 8), 256, 0, stream_>>>(reinterpret_cast<uint4*>(table_.p), nbuckets_);
         st_.launches++;
-        adj_done_ = false;
-        err_.zero(stream_);
-        build_range(keys, N, 0);
+        bin_fill(keys, N, 0);
         st_.ms_table = t.stop();
         check_err("exact table build");
         st_.nbuckets = nbuckets_;
@@ -1164,7 +1184,8 @@ public:
         st_.launches++;
         adj_done_ = false;
         err_.zero(stream_);
-        build_range(share_.p, n_share, shard);
+        bin_plan(share_.p, n_share, shard, false);   // ranges keep the upper bound: every rank must use the same range size
+        bin_fill(share_.p, n_share, shard);
         st_.ms_table = t.stop();
         check_err("exact table build (range)");
         st_.nbuckets = nbuckets_ * nshards;

@@ -481,6 +481,7 @@ class DistFind:
         e, W, k = self.e, self.world, self.k
         self._mark(None)
         self._nchrom = len(ref_records)
+        self._ids_used = {}
         if ref_stream is None:
             ref_stream = np.concatenate([np.concatenate([s, np.array([10], dtype=np.uint8)]) for _, s in ref_records])
         if isinstance(ref_stream, torch.Tensor):
@@ -570,6 +571,8 @@ class DistFind:
             else:
                 e.scan_reference(name, seq)
             texts.append((ci, e.breakpoints_text(), e.vcf_text()))
+            if hasattr(e, "ids_used"):
+                self._ids_used[ci] = e.ids_used()
         self._mark("scan_chromosomes")
         return self._merge_texts(texts)
 
@@ -597,9 +600,10 @@ class DistFind:
         used = torch.zeros(nchrom, dtype=torch.int64, device=self.device)
         local = {}
         for ci, bk, vcf in texts:
-            _, m1 = renumber_text(bk, 0, 0)
-            _, m2 = renumber_text(vcf, 1, 0)
-            local[ci] = max(m1, m2)
+            if ci in self._ids_used:
+                local[ci] = self._ids_used[ci]
+            else:
+                local[ci] = max(renumber_text(bk, 0, 0)[1], renumber_text(vcf, 1, 0)[1])
         if local:
             used[list(local.keys())] = torch.tensor(list(local.values()), dtype=torch.int64, device=self.device)
         self.c.all_reduce(used, "sum")

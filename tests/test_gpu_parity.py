@@ -558,6 +558,79 @@ def test_text_ingest_rejects_irregular_text():
     f.close()
 
 
+def test_count_files_falls_back_to_host_reader_and_expands_albums(tmp_path):
+    """mtg_count_files on layouts BankFasta accepts but the GPU parser rejects (multi-line FASTQ): the file is read by the host
+    reader instead of failing; a "file of files" (README.md:166, BankAlbum) is expanded; a non-empty file without any
+    record is an error, not an empty graph."""
+    import mindthegap_b200 as m
+    rng = np.random.default_rng(17)
+    reads = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=90)) for _ in range(400)]
+    reads += reads[:300]
+    multi = tmp_path / "multi.fq"     # sequence and quality wrapped over two lines
+    with open(multi, "wb") as fh:
+        for i, r in enumerate(reads):
+            fh.write(b"@r%d\n" % i + r[:50] + b"\n" + r[50:] + b"\n+\n" + b"I" * 50 + b"\n" + b"I" * 40 + b"\n")
+    plain = tmp_path / "plain.fa"
+    with open(plain, "wb") as fh:
+        for i, r in enumerate(reads):
+            fh.write(b">r%d\n" % i + r + b"\n")
+    album = tmp_path / "reads.fof"
+    album.write_text("plain.fa\n")
+    want = None
+    for uri in (str(plain), str(multi), str(album)):
+        f = _finder(21, ["-abundance-min", "2"])
+        f.count_files(uri)
+        got = _solid_of(f)
+        f.close()
+        if want is None:
+            want = got
+            assert len(want[0]) > 1000
+        else:
+            _same_solid(got, want)
+    junk = tmp_path / "junk.txt"
+    junk.write_text("not a sequence file\n")
+    f = _finder(21)
+    with pytest.raises(m.MtgError) as e:
+        f.count_files(str(junk))
+    assert "no FASTA/FASTQ record" in str(e.value)
+    f.close()
+
+
+def test_count_heavy_minimizer_bin_poly_a():
+    """Low-complexity stress: 200 k reads that are mostly poly-A put millions of instances of a handful of
+    k-mers into ONE minimizer bin (one work item of the count kernel, one long run of the exact table). Counts, histogram, solid set
+    and `contains` must still equal the oracle's."""
+    rng = np.random.default_rng(23)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = []
+    for i in range(20000):
+        r = np.full(150, ord("A"), dtype=np.uint8)
+        if i % 4 == 0:
+            p = int(rng.integers(0, 120))
+            r[p:p + 30] = rng.choice(acgt, size=30)     # a random island inside the homopolymer
+        elif i % 4 == 1:
+            r[:] = np.frombuffer(b"AT" * 75, dtype=np.uint8)
+        reads.append(bytes(r))
+    rnd = [bytes(rng.choice(acgt, size=150)) for _ in range(3000)]
+    stream = b"\n".join(reads + rnd + rnd) + b"\n"
+    for k in (31, 47):
+        f = _finder(k, ["-abundance-min", "2"])
+        f.push_reads(stream)
+        f.finish_count()
+        o = oracle_py.count_stream(stream, k, abundance_min=2, nthreads=4)
+        assert (f.histogram() == o["histogram"]).all()
+        lo, hi, ab = _sorted_solid(*f.export_solid())
+        assert (lo == o["lo"]).all() and (hi == o["hi"]).all() and (ab == o["abundance"]).all()
+        assert int(ab.max()) > 1000000 // 2     # the homopolymer k-mer really is heavy
+        g = oracle_py.Graph(o["lo"], o["hi"], k)
+        qlo = np.concatenate([o["lo"][:3000], o["lo"][:3000] ^ np.uint64(12), rng.integers(0, 1 << 62, 3000, dtype=np.uint64)])
+        qhi = np.concatenate([o["hi"][:3000], o["hi"][:3000], np.zeros(3000, dtype=np.uint64) if k <= 31 else rng.integers(0, 1 << (2 * (k - 32)), 3000, dtype=np.uint64)])
+        if k <= 31:
+            qlo &= np.uint64((1 << (2 * k)) - 1)
+        assert ((f.contains(qlo, qhi if k > 31 else None) & 1) == (g.query(qlo, qhi) & 1)).all()
+        g.close(); f.close()
+
+
 # ---------------------------------------------------------------------------------------------- .h5 hand-off layout
 @pytest.mark.parametrize("name,nparts", [("full", 4), ("full_k63", 7), ("syn_tiny_k32", 1)])
 def test_export_dsk_partitions(name, nparts):
