@@ -260,6 +260,9 @@ int64_t mtg_renumber_text(const char* in, uint64_t nbytes, int32_t kind, uint64_
  * steady points of the gap machine and the chunks are replayed concurrently with byte-identical output (the reference's
  * scan itself is single-threaded, src/Finder.cpp:597-600). 0 = all cores (the tool's default). */
 int mtg_set_host_threads(mtg_ctx* ctx, int32_t n);
+/* The finder mode flags (MTG_F_HOMO_ONLY ... MTG_F_SMALL_HOMO) when they are only known after the graph was built, as in
+ * Finder::execute (the option block src/Finder.cpp:321-398 follows Graph::create :266). Outputs restart like mtg_reset_outputs. */
+int mtg_set_mode_flags(mtg_ctx* ctx, uint32_t flags);
 /* counters of Finder::resumeResults (src/Finder.cpp:470-511): homo_clean, homo_fuzzy, hetero_clean, hetero_fuzzy,
  * clean_deletion, fuzzy_deletion, solo_snp, multi_snp, backup, homo_indel, hetero_indel, observer_queries */
 int mtg_get_find_counters(mtg_ctx* ctx, uint64_t* out12);

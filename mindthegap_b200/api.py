@@ -45,7 +45,7 @@ EXPORTS = [
     "mtg_count_run", "mtg_count_filter", "mtg_solid_copy", "mtg_graph_build_device", "mtg_sequence_features_device2", "mtg_replay_sequence",
     "mtg_graph_build_begin", "mtg_graph_critical", "mtg_graph_critical_copy", "mtg_graph_build_end", "mtg_set_host_threads", "mtg_set_minimizer_size", "mtg_get_minimizer_size",
     "mtg_solid_partition", "mtg_partition_keys", "mtg_graph_shard_begin", "mtg_graph_shard_critical", "mtg_graph_adj_pack", "mtg_graph_adj_unpack",
-    "mtg_graph_branching", "mtg_export_dsk_partitions", "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_mphf_level", "mtg_graph_shard_mphf_begin", "mtg_graph_shard_mphf_plan", "mtg_graph_shard_mphf_step", "mtg_graph_shard_mphf_tail", "mtg_get_stream", "mtg_renumber_text", "mtg_get_ids_used", "mtg_set_reference_sharded", "mtg_ref_repeats_copy", "mtg_set_ref_repeats_device", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
+    "mtg_graph_branching", "mtg_export_dsk_partitions", "mtg_graph_critical_set_share", "mtg_graph_shard_cascade", "mtg_graph_set_cfp", "mtg_graph_shard_mphf_level", "mtg_graph_shard_mphf_begin", "mtg_graph_shard_mphf_plan", "mtg_graph_shard_mphf_step", "mtg_graph_shard_mphf_tail", "mtg_get_stream", "mtg_set_mode_flags", "mtg_renumber_text", "mtg_get_ids_used", "mtg_set_reference_sharded", "mtg_ref_repeats_copy", "mtg_set_ref_repeats_device", "mtg_graph_shard_finish", "mtg_graph_buffer", "mtg_or_chunks",
 ]
 
 _lib = None
@@ -149,6 +149,7 @@ def load_library():
     L.mtg_set_reference_sharded.argtypes = [vp, vp, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]
     L.mtg_ref_repeats_copy.argtypes = [vp, vp, C.c_uint64]
     L.mtg_set_ref_repeats_device.argtypes = [vp, vp, C.c_uint64]
+    L.mtg_set_mode_flags.argtypes = [vp, C.c_uint32]
     L.mtg_get_ids_used.restype = C.c_uint64
     L.mtg_get_ids_used.argtypes = [vp]
     L.mtg_renumber_text.restype = C.c_int64

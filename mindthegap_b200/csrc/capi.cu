@@ -150,7 +150,7 @@ struct mtg_ctx {
     // replay
     std::unique_ptr<ParallelReplayer<uint64_t>> rp64;
     std::unique_ptr<ParallelReplayer<hu128>> rp128;
-    PinnedBuf feat, rep, interest;
+    PinnedBuf feat, rep, interest, probe_keys, probe_ans;
     int host_threads = 0;  // 0 = all host cores (-nb-cores 0)
     double ms_features = 0, ms_replay = 0, ms_graph_build = 0;
     uint64_t scan_positions = 0, scan_valid = 0, scan_in_graph = 0, scan_table_probes = 0, scan_fallback = 0;
@@ -212,6 +212,15 @@ static void make_replayers(mtg_ctx* c) {
     }
     if (c->rp64) c->rp64->set_threads(c->host_threads);
     if (c->rp128) c->rp128->set_threads(c->host_threads);
+    // probe batches are staged in pinned buffers that outlive the find (process-wide cache): true async DMA, no page faults
+    if (c->rp64) c->rp64->set_staging([c](size_t n, uint64_t** k, uint8_t** a) {
+        c->probe_keys.reserve(n * 8 + 64); c->probe_ans.reserve(n + 64);
+        *k = c->probe_keys.as<uint64_t>(); *a = c->probe_ans.as<uint8_t>();
+    });
+    if (c->rp128) c->rp128->set_staging([c](size_t n, hu128** k, uint8_t** a) {
+        c->probe_keys.reserve(n * 16 + 64); c->probe_ans.reserve(n + 64);
+        *k = c->probe_keys.as<hu128>(); *a = c->probe_ans.as<uint8_t>();
+    });
 }
 
 extern "C" {
@@ -902,6 +911,12 @@ int64_t mtg_renumber_text(const char* in, uint64_t nbytes, int32_t kind, uint64_
     return (int64_t)o;
 }
 
+int mtg_set_mode_flags(mtg_ctx* ctx, uint32_t flags) {
+    MTG_TRY(ctx)
+    ctx->p.flags = (flags & ~(uint32_t)MTG_F_HOST_PARSE) | (ctx->p.flags & MTG_F_HOST_PARSE);
+    make_replayers(ctx);   // the flags only steer the event replay; outputs restart
+    MTG_CATCH
+}
 int mtg_set_host_threads(mtg_ctx* ctx, int32_t n) {
     MTG_TRY(ctx)
     ctx->host_threads = n < 0 ? 0 : n;

@@ -712,15 +712,14 @@ __global__ void __launch_bounds__(256) contains_kernel(GraphView<K> g, const uin
 static const int FT_TILE = 256, FT_HALO = 64;   // window k-m+1 <= 61 (k <= 63, m >= 3)
 template <class K>
 __global__ void __launch_bounds__(FT_TILE) features_kernel(GraphView<K> g, const uint64_t* __restrict__ packed, const uint32_t* __restrict__ inv,
-                                                           uint64_t npos, uint8_t* __restrict__ feat, uint8_t* __restrict__ rep,
+                                                           uint64_t npos, uint64_t tile_begin, uint64_t tile_end, uint8_t* __restrict__ feat, uint8_t* __restrict__ rep,
                                                            uint32_t* __restrict__ interest, unsigned long long* __restrict__ counters) {
     __shared__ uint32_t s_hv[FT_TILE + FT_HALO];
     const int k = g.k, m = g.tm, W = k - m + 1;
     const K m1 = kmask<K>(k - 1);
     const uint32_t mmask = (uint32_t)((1ull << (2 * m)) - 1);
     unsigned long long c_valid = 0, c_in = 0, c_probe = 0, c_fb = 0;
-    const uint64_t ntiles = (npos + FT_TILE - 1) / FT_TILE;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {   // tiles [tile_begin, tile_end) of the sequence
         const uint64_t p = tile * FT_TILE + threadIdx.x;
         // hashed m-mer starting at base p (and, for the first W-1 threads, at base p + FT_TILE); the packed array is padded
         {
@@ -916,6 +915,8 @@ public:
         if (ev_a_) cudaEventDestroy(ev_a_);
         if (ev_b_) cudaEventDestroy(ev_b_);
         if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
+        if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
+        for (cudaEvent_t e : chunk_ev_) cudaEventDestroy(e);
         if (side_ev_) cudaEventDestroy(side_ev_);
     }
     int kmer_size() const override { return k_; }
@@ -1696,7 +1697,16 @@ public:
     void ref_repeat_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) override { run_query(lo, hi, n, out, 2); }
     void observer_probe_batch(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint8_t* out) override { run_query(lo, hi, n, out, 3); }
 
+    // host destinations of a chunked scan (features_to_host): every chunk's features are copied on copy_stream_ while the kernel of
+    // the next chunk runs, so the D2H of 2 bytes per position hides behind the probes (and vice versa)
+    struct HostDst { uint8_t* feat; uint8_t* rep; uint32_t* interest; };
+    cudaStream_t copy_stream_ = nullptr;
+    std::vector<cudaEvent_t> chunk_ev_;
     void features_device(const uint8_t* d_seq, uint64_t len, uint8_t* d_feat, uint8_t* d_rep, uint32_t* d_interest, uint64_t* counters_host4) override {
+        features_device_impl(d_seq, len, d_feat, d_rep, d_interest, counters_host4, nullptr);
+    }
+    void features_device_impl(const uint8_t* d_seq, uint64_t len, uint8_t* d_feat, uint8_t* d_rep, uint32_t* d_interest, uint64_t* counters_host4,
+                              const HostDst* host) {
         if (counters_host4) memset(counters_host4, 0, 32);
         last_features_ms_ = 0;
         if (len < (uint64_t)k_) return;
@@ -1712,11 +1722,33 @@ public:
         launch_pack(d_seq, len, seq_packed_.p, seq_inv_.p, nwords, stream_);
         MTG_CUDA(cudaMemsetAsync(counters_.p, 0, 32, stream_));
         MTG_CUDA(cudaEventRecord(ev_a_, stream_));
-        features_kernel<K><<<grid_for(npos, FT_TILE, 148 * 32), FT_TILE, 0, stream_>>>(view(), seq_packed_.p, seq_inv_.p, npos, d_feat, d_rep, d_interest, counters_.p);
-        MTG_CUDA(cudaGetLastError());
+        const uint64_t ntiles = (npos + FT_TILE - 1) / FT_TILE;
+        // three chunks of decreasing size (45 / 40 / 15 %): few launches, and only the copy of the small last chunk is exposed
+        const uint64_t nchunks = host && ntiles >= 64 ? 3 : 1;
+        const uint64_t bounds[4] = {0, nchunks > 1 ? ntiles * 45 / 100 : ntiles, nchunks > 1 ? ntiles * 85 / 100 : ntiles, ntiles};
+        if (nchunks > 1 && !copy_stream_) MTG_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+        while (chunk_ev_.size() < nchunks) { cudaEvent_t e; MTG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); chunk_ev_.push_back(e); }
+        for (uint64_t c = 0; c < nchunks; c++) {
+            const uint64_t t0 = bounds[c], t1 = nchunks > 1 ? bounds[c + 1] : ntiles;
+            if (t1 > t0)
+                features_kernel<K><<<grid_for((t1 - t0) * FT_TILE, FT_TILE, 148 * 32), FT_TILE, 0, stream_>>>(view(), seq_packed_.p, seq_inv_.p, npos, t0, t1, d_feat, d_rep,
+                                                                                                          d_interest, counters_.p);
+            MTG_CUDA(cudaGetLastError());
+            st_.launches++;
+            if (host && nchunks > 1) {   // positions [t0, t1) x FT_TILE (a multiple of 32) are final: copy them while the next chunk computes
+                const uint64_t p0 = t0 * FT_TILE, p1 = std::min<uint64_t>(t1 * FT_TILE, npos);
+                MTG_CUDA(cudaEventRecord(chunk_ev_[c], stream_));
+                MTG_CUDA(cudaStreamWaitEvent(copy_stream_, chunk_ev_[c], 0));
+                if (p1 > p0) {
+                    MTG_CUDA(cudaMemcpyAsync(host->feat + p0, d_feat + p0, p1 - p0, cudaMemcpyDeviceToHost, copy_stream_));
+                    MTG_CUDA(cudaMemcpyAsync(host->rep + p0, d_rep + p0, p1 - p0, cudaMemcpyDeviceToHost, copy_stream_));
+                    if (host->interest) MTG_CUDA(cudaMemcpyAsync(host->interest + p0 / 32, d_interest + p0 / 32, ((p1 - p0 + 31) / 32) * 4, cudaMemcpyDeviceToHost, copy_stream_));
+                }
+            }
+        }
         MTG_CUDA(cudaEventRecord(ev_b_, stream_));
         features_timed_ = true;
-        st_.launches += 2;
+        st_.launches++;
         if (counters_host4) {
             MTG_CUDA(cudaMemcpyAsync(counters_host4, counters_.p, 32, cudaMemcpyDeviceToHost, stream_));
             MTG_CUDA(cudaStreamSynchronize(stream_));
@@ -1734,12 +1766,17 @@ public:
         if (len < (uint64_t)k_) return;
         const uint64_t npos = len - k_ + 1;
         if (d_feat_.n < len + 64) { d_feat_.alloc(len + 64 + len / 4); d_rep_.alloc(len + 64 + len / 4); }
-        features_device(d_seq, len, d_feat_.p, d_rep_.p, nullptr, nullptr);
-        MTG_CUDA(cudaMemcpyAsync(feat, d_feat_.p, npos, cudaMemcpyDeviceToHost, stream_));
-        MTG_CUDA(cudaMemcpyAsync(rep, d_rep_.p, npos, cudaMemcpyDeviceToHost, stream_));
-        if (interest) MTG_CUDA(cudaMemcpyAsync(interest, d_interest_.p, ((npos + 31) / 32) * 4, cudaMemcpyDeviceToHost, stream_));
+        const uint64_t ntiles = (npos + FT_TILE - 1) / FT_TILE;
+        HostDst dst{feat, rep, interest};
+        features_device_impl(d_seq, len, d_feat_.p, d_rep_.p, nullptr, nullptr, &dst);
+        if (ntiles < 64) {   // small sequence: one kernel, copies behind it
+            MTG_CUDA(cudaMemcpyAsync(feat, d_feat_.p, npos, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaMemcpyAsync(rep, d_rep_.p, npos, cudaMemcpyDeviceToHost, stream_));
+            if (interest) MTG_CUDA(cudaMemcpyAsync(interest, d_interest_.p, ((npos + 31) / 32) * 4, cudaMemcpyDeviceToHost, stream_));
+        }
         if (counters_host4) MTG_CUDA(cudaMemcpyAsync(counters_host4, counters_.p, 32, cudaMemcpyDeviceToHost, stream_));
         MTG_CUDA(cudaStreamSynchronize(stream_));
+        if (copy_stream_) MTG_CUDA(cudaStreamSynchronize(copy_stream_));
     }
 
     uint64_t copy_bits(int which, uint8_t* host_buf) const override {

@@ -839,6 +839,8 @@ public:
     size_t chunk_positions = (size_t)1 << 17;    // target chunk length
     size_t skip_min = 512;
     void set_threads(int n) { nthreads_ = n; }  // 0 = every thread of the host pool
+    // optional: where the probe keys / answers of a batch are staged (n entries each); e.g. pinned host memory
+    void set_staging(std::function<void(size_t, K**, uint8_t**)> f) { staging_ = f; }
     uint64_t nb_chunks = 0;                      // chunks replayed so far (statistics)
 
     void scan(const std::string& name, const char* seq, size_t len, const uint8_t* feat, const uint8_t* rep, const uint32_t* interest = nullptr) {
@@ -885,16 +887,19 @@ public:
                 r.collect(s, cut[c0 + i + 1], feat, rep, interest);
             });
             for (size_t i = 0; i < nc; i++) off[i + 1] = off[i] + rp[i]->log_keys().size();
-            keys_.resize(off[nc]); ans_.resize(off[nc]);
-            if (nc > 1)
-                HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
-                    const std::vector<K>& lk = rp[i]->log_keys();
-                    if (!lk.empty()) memcpy(&keys_[off[i]], lk.data(), lk.size() * sizeof(K));
-                });
-            const K* kp = nc > 1 ? keys_.data() : rp[0]->log_keys().data();
-            if (off[nc]) { probe_(kp, off[nc], ans_.data()); cnt.probe_batches++; cnt.prefetched_queries += off[nc]; }
+            // staging of the batch's probe keys / answers: the caller's (pinned, reused across finds) buffers when it provides them --
+            // a fresh std::vector of tens of MB costs its zero fill and page faults on the one serial section of the replay
+            K* kbuf = nullptr;
+            uint8_t* abuf = nullptr;
+            if (staging_) staging_(off[nc], &kbuf, &abuf);
+            else { keys_.resize(off[nc]); ans_.resize(off[nc]); kbuf = keys_.data(); abuf = ans_.data(); }
             HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
-                rp[i]->apply(cut[c0 + i], cut[c0 + i + 1], feat, rep, interest, ans_.data() + off[i]);
+                const std::vector<K>& lk = rp[i]->log_keys();
+                if (!lk.empty()) memcpy(kbuf + off[i], lk.data(), lk.size() * sizeof(K));
+            });
+            if (off[nc]) { probe_(kbuf, off[nc], abuf); cnt.probe_batches++; cnt.prefetched_queries += off[nc]; }
+            HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
+                rp[i]->apply(cut[c0 + i], cut[c0 + i + 1], feat, rep, interest, abuf + off[i]);
             });
             for (size_t i = 0; i < nc; i++) merge(*rp[i]);
             c0 = c1;
@@ -940,6 +945,7 @@ private:
     int nthreads_;
     std::vector<K> keys_;
     std::vector<uint8_t> ans_;
+    std::function<void(size_t, K**, uint8_t**)> staging_;
 };
 
 }  // namespace mtg

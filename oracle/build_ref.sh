@@ -52,4 +52,14 @@ if [ -f "$H5TOOL" ] && { [ ! -x "$H5EXE" ] || [ "$H5TOOL" -nt "$H5EXE" ]; }; the
   g++ -O2 -std=c++11 -DNDEBUG -D_FILE_OFFSET_BITS=64 -w $INC "$H5TOOL" -o "$H5EXE" \
       ext/gatb-core/lib/Release/libgatbcore.a ext/gatb-core/lib/Release/libhdf5.a -ldl -lpthread -lz -lm
 fi
+# the reference-side binding, COMPILED: the reference's own src/ with three statements of Finder.cpp replaced by calls into the C ABI
+# (integration/finder_shim.hpp, integration/make_shim.py) -> oracle/_ref/bin/MindTheGap_mtg, linked against libmtg_b200.so
+SHIM_EXE="$OUT/bin/MindTheGap_mtg"
+LIBMTG="$HERE/../mindthegap_b200/_build/libmtg_b200.so"
+if [ -f "$LIBMTG" ] && { [ ! -x "$SHIM_EXE" ] || [ "$HERE/../integration/finder_shim.hpp" -nt "$SHIM_EXE" ] || [ "$HERE/../integration/make_shim.py" -nt "$SHIM_EXE" ] || [ "$HERE/../include/mtg_b200.h" -nt "$SHIM_EXE" ]; }; then
+  python "$HERE/../integration/make_shim.py" "$REF/src" "$OUT/shim_src" > /dev/null
+  g++ -O2 -std=c++11 -DNDEBUG -D_FILE_OFFSET_BITS=64 -w $INC -I"$OUT/shim_src" -I"$HERE/../include" "$OUT"/shim_src/*.cpp -o "$SHIM_EXE" \
+      ext/gatb-core/lib/Release/libgatbcore.a ext/gatb-core/lib/Release/libhdf5.a -L"$(dirname "$LIBMTG")" -lmtg_b200 \
+      -Wl,-rpath,'$ORIGIN/../../../mindthegap_b200/_build' -ldl -lpthread -lz -lm
+fi
 echo "build_ref: done -> $OUT/bin/MindTheGap"

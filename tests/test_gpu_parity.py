@@ -366,6 +366,49 @@ def test_h5_handoff_gpu_solid_set_feeds_unmodified_fill_and_find(tmp_path):
     assert "".join(l for l in open(str(tmp_path / "g2.othervariants.vcf")) if not l.startswith("#")) == expected("full")[1]
 
 
+def test_reference_cli_through_the_c_abi(tmp_path):
+    """The compiled reference-side binding: `MindTheGap_mtg` is the reference's OWN CLI -- its option
+    parser, Tool framework, VCF header and info printing, built from /root/reference/src -- with the three hot statements of
+    Finder.cpp replaced by calls into libmtg_b200.so (integration/finder_shim.hpp). It must print the reference's gold files, info
+    lines and counters (test/simple_full_test.sh:36-76), on the bundled example, one case of test/simple_test.sh, and -graph."""
+    import re
+    import subprocess
+    from tests.cases import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "bin", "MindTheGap_mtg")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/bin/MindTheGap_mtg not built (oracle/build_ref.sh)")
+    reads, ref = case_paths(CASES["full"])
+    out = str(tmp_path / "o")
+    r = subprocess.run([exe, "find", "-in", reads, "-ref", ref, "-out", out, "-nb-cores", "2"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-500:]
+    assert open(out + ".breakpoints").read() == open(os.path.join(GOLD, "full", "gold.breakpoints")).read()
+    assert "".join(l for l in open(out + ".othervariants.vcf") if not l.startswith("#")) == expected("full")[1]
+    gold = open(os.path.join(GOLD, "full", "gold_find.output")).read()
+    for key in ("abundance_min (auto inferred)", "abundance_min (used)", "nb_solid_kmers", "nb_branching_nodes", "homozygous", "heterozygous", "deletions",
+                "Homozygous insertions 1-2 bp size", "Heterozygous insertions 1-2 bp size", "SNPs"):
+        want = re.search(r"^\s*%s\s*:\s*(\d+)" % re.escape(key), gold, re.M).group(1)
+        got = re.search(r"^\s*%s\s*:\s*(\d+)" % re.escape(key), r.stdout, re.M)
+        assert got and got.group(1) == want, key
+    # a mode-flag case of test/simple_test.sh (the flags are only known after the graph was built: mtg_set_mode_flags)
+    case = CASES["hetero_insert"]
+    reads2, ref2 = case_paths(case)
+    out2 = str(tmp_path / "h")
+    r = subprocess.run([exe, "find", "-in", reads2, "-ref", ref2, "-out", out2] + case["flags"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout[-800:]
+    assert open(out2 + ".breakpoints").read() == expected("hetero_insert")[0]
+    # -graph: the reference's own .h5, read back through gatb-core inside the shim
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "bin", "MindTheGap")
+    own = str(tmp_path / "own")
+    assert subprocess.run([ref_bin, "find", "-in", reads, "-ref", ref, "-out", own], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE).returncode == 0
+    out3 = str(tmp_path / "g")
+    r = subprocess.run([exe, "find", "-graph", own + ".h5", "-ref", ref, "-out", out3], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout[-800:]
+    assert open(out3 + ".breakpoints").read() == open(os.path.join(GOLD, "full", "gold.breakpoints")).read()
+    # errors keep the reference's path: a missing option is the reference's own message
+    r = subprocess.run([exe, "find", "-in", reads], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode != 0
+
+
 def _dist_worker_script():
     return """
 import json, os, sys
@@ -596,6 +639,19 @@ def test_count_files_falls_back_to_host_reader_and_expands_albums(tmp_path):
     f.close()
 
 
+def _canonical(qlo, qhi, k):
+    """Canonical forms through the oracle's revcomp (the oracle's graph queries take canonical k-mers)."""
+    import ctypes as C
+    L = oracle_py.load()
+    clo, chi = qlo.copy(), qhi.copy()
+    for i in range(len(qlo)):
+        a, b = C.c_uint64(), C.c_uint64()
+        L.mtgo_revcomp(int(qlo[i]), int(qhi[i]), k, C.byref(a), C.byref(b))
+        if (b.value, a.value) < (int(qhi[i]), int(qlo[i])):
+            clo[i], chi[i] = a.value, b.value
+    return clo, chi
+
+
 def test_count_heavy_minimizer_bin_poly_a():
     """Low-complexity stress: 200 k reads that are mostly poly-A put millions of instances of a handful of
     k-mers into ONE minimizer bin (one work item of the count kernel, one long run of the exact table). Counts, histogram, solid set
@@ -627,7 +683,11 @@ def test_count_heavy_minimizer_bin_poly_a():
         qhi = np.concatenate([o["hi"][:3000], o["hi"][:3000], np.zeros(3000, dtype=np.uint64) if k <= 31 else rng.integers(0, 1 << (2 * (k - 32)), 3000, dtype=np.uint64)])
         if k <= 31:
             qlo &= np.uint64((1 << (2 * k)) - 1)
-        assert ((f.contains(qlo, qhi if k > 31 else None) & 1) == (g.query(qlo, qhi) & 1)).all()
+        if k > 31:
+            qhi &= np.uint64((1 << (2 * k - 64)) - 1)
+        clo, chi = _canonical(qlo, qhi, k)
+        got, exp = f.contains(qlo, qhi if k > 31 else None), g.query(clo, chi)
+        assert ((got & 1) == (exp & 1)).all() and ((got & 2) == (exp & 2)).all()
         g.close(); f.close()
 
 
