@@ -245,17 +245,26 @@ __global__ void __launch_bounds__(256) critical_kernel(const K* __restrict__ key
             // fixed end of the neighbours: first base of a successor = x[1]; last base of a predecessor = x[k-2]
             const unsigned fixed = succ ? (unsigned)((x >> (2 * (k - 2))) & 3) : (unsigned)((x >> 2) & 3);
             alive = 0xF;
-            for (int i = 0; i < g.bloom_nhash && alive; i++) {
-                const uint64_t base = racine + off[i];   // + cano2 in [0,13]
-                const uint64_t w = base >> 5;
-                const unsigned sh = (unsigned)(base & 31);
-                uint64_t bits = (uint64_t)__ldg(g.bloom + w) | ((uint64_t)__ldg(g.bloom + w + 1) << 32);
-                bits >>= sh;
+            // every solid k-mer of a path has a neighbour on each side, so all nhash windows are needed almost always: their loads
+            // are issued together (independent random sectors in flight) instead of one dependent round trip per hash
+            uint64_t wbits[8];
 #pragma unroll
-                for (int nt = 0; nt < 4; nt++) {
-                    const unsigned c2 = succ ? cano2_dev((fixed << 2) | nt) : cano2_dev((nt << 2) | fixed);
-                    if (!((bits >> c2) & 1)) alive &= ~(1u << nt);
+            for (int i = 0; i < 8; i++) {
+                wbits[i] = ~0ull;
+                if (i < g.bloom_nhash) {
+                    const uint64_t base = racine + off[i];   // + cano2 in [0,13]
+                    const uint64_t w = base >> 5;
+                    wbits[i] = ((uint64_t)__ldg(g.bloom + w) | ((uint64_t)__ldg(g.bloom + w + 1) << 32)) >> (unsigned)(base & 31);
                 }
+            }
+            unsigned c2s[4];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) c2s[nt] = succ ? cano2_dev((fixed << 2) | nt) : cano2_dev((nt << 2) | fixed);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++)
+                    if (!((wbits[i] >> c2s[nt]) & 1)) alive &= ~(1u << nt);
             }
         }
         while (alive) {
@@ -499,14 +508,17 @@ __global__ void __launch_bounds__(256) mphf_apply_kernel(const unsigned long lon
 __global__ void __launch_bounds__(256) mphf_clear_kernel(unsigned long long* __restrict__ bits, const unsigned long long* __restrict__ coll, uint64_t nwords) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) bits[i] &= ~coll[i];
 }
-// keys whose bit was cleared (collision) go on to the next level
+// keys whose bit was cleared (collision) go on to the next level. One reservation per block iteration (per-warp reservations on
+// the single counter serialise in L2).
 template <class K>
 __global__ void __launch_bounds__(256) mphf_compact_kernel(const K* __restrict__ keys, const unsigned long long* __restrict__ n_ptr, int level, uint64_t dom,
                                                            uint64_t seed, const unsigned long long* __restrict__ bits, K* __restrict__ out,
                                                            unsigned long long* __restrict__ nout) {
+    __shared__ uint32_t s_cnt[8];
+    __shared__ unsigned long long s_base;
     const uint64_t n = *n_ptr;
-    const int lane = threadIdx.x & 31;
-    uint64_t n_round = (n + 31) / 32 * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t n_round = (n + 255) / 256 * 256;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (uint64_t)gridDim.x * blockDim.x) {
         bool keep = false;
         K key = 0;
@@ -519,13 +531,17 @@ __global__ void __launch_bounds__(256) mphf_compact_kernel(const K* __restrict__
             uint64_t p = h % dom;
             keep = !((bits[p >> 6] >> (p & 63)) & 1ull);
         }
-        uint32_t b = __ballot_sync(0xFFFFFFFFu, keep);
-        if (b) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(nout, (unsigned long long)__popc(b));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (keep) out[base + __popc(b & ((1u << lane) - 1))] = key;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, keep);
+        if (lane == 0) s_cnt[warp] = __popc(b);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            for (int w = 0; w < 8; w++) { const uint32_t v = s_cnt[w]; s_cnt[w] = run; run += v; }
+            s_base = run ? atomicAdd(nout, (unsigned long long)run) : 0ull;
         }
+        __syncthreads();
+        if (keep) out[s_base + s_cnt[warp] + __popc(b & ((1u << lane) - 1))] = key;
+        __syncthreads();
     }
 }
 
