@@ -69,3 +69,23 @@ def test_filter_equals_script_restatement_on_the_reference_gold_breakpoints(thre
     if threshold == 0.5:
         assert got[1] > 0 and got[0].count(">") == 2 * got[1] and got[0].endswith("\r\n")
     g.close()
+
+
+@pytest.mark.parametrize("threshold,kept", [(0.80, 6), (0.5, 8), (0.95, 6)])
+def test_filter_equals_the_unmodified_reference_script(threshold, kept):
+    """Pinned to the reference: tests/golden/context/ holds what the UNMODIFIED scripts/python3/Context_genome_WG.py printed and
+    wrote on the bundled example (tests/golden/make_context_fixture.py: the script imported as it is, pygatb / Biopython replaced by
+    stand-ins whose degrees come from gatb-core's own Graph::indegree / outdegree on the reference's .h5). Kept / total counts at
+    every threshold, and the output file byte for byte where the script gets as far as writing it (at 0.80 and 0.95 it raises
+    KeyError for the chromosome that keeps no breakpoint -- our documented deviation returns the 6 kept records instead)."""
+    import json
+    g, refs = bundled_graph()
+    bk = open(os.path.join(GOLD, "full", "gold.breakpoints")).read()
+    text, nkept, total = context_filter(g.degrees, 31, bk, refs, threshold)
+    fx = json.load(open(os.path.join(GOLD, "context", "summary.json")))[str(threshold)]
+    assert fx["stdout"] == "total breakpoints kept :  %d  on  %d" % (nkept, total) and nkept == kept
+    if fx["status"] == "ok":
+        assert text.encode() == open(os.path.join(GOLD, "context", "threshold_%s.bkpt" % threshold), "rb").read()
+    else:
+        assert fx["status"].startswith("KeyError") and text.count(">") == 2 * kept
+    g.close()

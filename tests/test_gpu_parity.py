@@ -825,4 +825,12 @@ def test_context_filter_engine_degrees_equal_oracle(name):
         assert f.context_filter(bk, refs, thr) == got
     qlo, qhi, d = seen[0]
     assert len(qlo) > 0 and (g.degrees(qlo, qhi) == d).all()
+    if name == "full":   # pinned to the UNMODIFIED reference script on gatb-core's own degrees (tests/golden/context/, make_context_fixture.py)
+        import json
+        fx = json.load(open(os.path.join(GOLD, "context", "summary.json")))
+        for thr, kept in ((0.80, 6), (0.5, 8), (0.95, 6)):
+            text, nkept, total = f.context_filter(bk, refs, thr)
+            assert fx[str(thr)]["stdout"] == "total breakpoints kept :  %d  on  %d" % (nkept, total) and nkept == kept
+            if fx[str(thr)]["status"] == "ok":
+                assert text.encode() == open(os.path.join(GOLD, "context", "threshold_%s.bkpt" % thr), "rb").read()
     g.close(); f.close()
