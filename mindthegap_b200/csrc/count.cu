@@ -117,7 +117,7 @@ static const int SK_THREADS = 256;
 static const int SK_PER = SK_TILE / SK_THREADS;  // 8 consecutive positions per thread
 static const int SK_HALO = 64;        // m-mer positions computed past the tile (>= k - m)
 static const int SK_MAX_M = 15;       // 2m <= 31 bits of m-mer
-static const int SK_MAXRUN = 32;      // max k-mers per record (6-bit length field holds up to 64)
+static const int SK_MAXRUN = 30;      // max k-mers per record: a record spans <= 30 + k - 1 <= 60 bases for k <= 31 (two words, count_kernel_dd)
 static const int REC_POS_SHIFT = 26, REC_LEN_SHIFT = 20;
 static const int MH_REC_SHIFT = 36;   // minimizer histogram word: nrec << 36 | nkmers
 
@@ -592,6 +592,253 @@ count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ g
     if (tid < SMEM_HIST && hist_s[tid]) atomicAdd(&histo[tid], (unsigned long long)hist_s[tid]);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// count kernel with super-k-mer de-duplication (64-bit k-mers, k <= 31).
+// At sequencing coverage the SAME super-k-mer (same bases, same extent) arrives from every read that covers its locus: 2.8 records
+// per distinct super-k-mer at 30x with 0.5 % errors (measured on the bench's generator). A group's records are therefore first
+// folded into a small shared-memory table keyed by the super-k-mer's bases in canonical orientation (<= 60 bases = 120 bits + the
+// length in the free low bits: one 128-bit CAS), with a multiplicity; only the distinct super-k-mers are expanded into k-mers, each
+// inserted ONCE with its multiplicity as the increment. Expansion is one lane per distinct super-k-mer, rolling the k-mer through
+// two registers (no per-instance extraction, shuffles or global loads: the bases are in the table entry).
+// The canonical k-mers of a super-k-mer and of its reverse complement are the same multiset, so both strands fold together.
+static const int DD_SLOTS = 1024, DD_CAP = 512, DD_MAXPROBE = 32;   // the table is flushed (expanded + cleared) above DD_CAP entries
+static const int DD_PER = 2;                                        // records per thread and batch
+static const int DD_S = 7424;                                       // k-mer table slots (any size: slot = hash * S >> 32)
+MTG_D u128 dd_key(const uint64_t* __restrict__ packed, uint64_t r, int k) {
+    const uint64_t pos = r >> REC_POS_SHIFT;
+    const int len = (int)((r >> REC_LEN_SHIFT) & 63) + 1, span = len + k - 1;   // <= 60
+    const uint64_t a = pos >> 5;
+    const int off = 2 * (int)(pos & 31);
+    const uint64_t p0 = packed[a], p1 = packed[a + 1], p2 = packed[a + 2];       // the arrays are padded
+    uint64_t x0 = off ? (p0 << off) | (p1 >> (64 - off)) : p0;
+    uint64_t x1 = off ? (p1 << off) | (p2 >> (64 - off)) : p1;
+    if (span <= 32) { x0 &= span == 32 ? ~0ull : ~(~0ull >> (2 * span)); x1 = 0; }
+    else x1 &= ~(~0ull >> (2 * (span - 32)));
+    // reverse complement of the span, left-aligned: rc of the 64-base string starts with 64 - span T's (the zero padding)
+    const uint64_t r0 = rc_word(x1), r1 = rc_word(x0);
+    const int sh = 2 * (64 - span);                                              // 8 .. 126
+    uint64_t c0, c1;
+    if (sh >= 64) { c0 = r1 << (sh - 64); c1 = 0; }
+    else { c0 = (r0 << sh) | (r1 >> (64 - sh)); c1 = r1 << sh; }
+    const bool use_rc = c0 < x0 || (c0 == x0 && c1 < x1);
+    return u128((use_rc ? c1 : x1) | (uint64_t)(len - 1), use_rc ? c0 : x0);     // lo word carries the length in its free low byte
+}
+
+__global__ void __launch_bounds__(COUNT_THREADS, 2)
+count_kernel_dd(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ grouped, const unsigned long long* __restrict__ grp_off,
+                uint32_t ngroups, unsigned int* __restrict__ item_counter, int k, uint32_t emit_min, unsigned long long* __restrict__ histo,
+                uint64_t* __restrict__ cand_keys, uint32_t* __restrict__ cand_cnt, unsigned long long* __restrict__ ncand, uint64_t cand_capacity,
+                unsigned long long* __restrict__ gstats, int* __restrict__ errflag) {
+    const int S = DD_S;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u128* dkeys = reinterpret_cast<u128*>(smem_raw);                                     // 16 KB, 16-byte aligned
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + sizeof(u128) * DD_SLOTS);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(keys + S);
+    uint32_t* dw = cnt + S;
+    uint32_t* hist_s = dw + DD_SLOTS;
+    uint16_t* dpfx = reinterpret_cast<uint16_t*>(hist_s + SMEM_HIST);   // DD_SLOTS + 1 exclusive prefix sums of the entries' lengths (<= 30 720)
+    __shared__ uint32_t s_item, s_overflow, s_sp, s_dcount, s_pending;
+    __shared__ uint32_t s_wsum[COUNT_THREADS / 32];
+    __shared__ unsigned long long s_cbase;
+    __shared__ uint32_t s_stack[CK_STACK];
+    const uint64_t EMPTY = ~0ull;
+    const u128 DEMPTY = u128(~0ull, ~0ull);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kshift = 64 - 2 * k;
+
+    if (tid < SMEM_HIST) hist_s[tid] = 0;
+    while (true) {
+        if (tid == 0) {
+            uint32_t it;
+            do { it = atomicAdd(item_counter, 1u); } while (it < ngroups && grp_off[it + 1] == grp_off[it]);
+            s_item = it; s_sp = 1; s_stack[0] = 0;
+        }
+        __syncthreads();
+        const uint32_t it = s_item;
+        if (it >= ngroups) break;
+        const uint64_t rec_off = grp_off[it];
+        const uint32_t nrec = (uint32_t)(grp_off[it + 1] - rec_off);
+        const uint64_t* recs = grouped + rec_off;
+        uint32_t npasses = 0;
+        while (true) {   // hash classes of this group, depth first (a class that overflows the k-mer table is split and redone)
+            const uint32_t sp = s_sp;
+            if (sp == 0) break;
+            const uint32_t top = s_stack[sp - 1];
+            const uint32_t level = top >> 24, prefix = top & 0xFFFFFFu, cmask = (1u << level) - 1u;
+            __syncthreads();
+            if (tid == 0) { s_sp = sp - 1; s_overflow = 0; s_dcount = 0; s_pending = 0; }
+            for (int s = tid; s < S; s += COUNT_THREADS) { keys[s] = EMPTY; cnt[s] = 0; }
+            for (int s = tid; s < DD_SLOTS; s += COUNT_THREADS) { dkeys[s] = DEMPTY; dw[s] = 0; }
+            __syncthreads();
+            npasses++;
+            // ---- records in batches of DD_PER per thread: fold into the super-k-mer table; expand it when it fills up and at the end.
+            // Every branch below is taken by the whole block (conditions come from shared memory read after a barrier).
+            for (uint32_t base = 0;; base += COUNT_THREADS * DD_PER) {
+                const bool last = base >= nrec;
+                u128 key[DD_PER];
+                bool pending[DD_PER];
+#pragma unroll
+                for (int q = 0; q < DD_PER; q++) {   // the random loads of the batch are issued together
+                    const uint32_t i = base + (uint32_t)q * COUNT_THREADS + tid;
+                    pending[q] = !last && i < nrec;
+                    key[q] = pending[q] ? dd_key(packed, recs[i], k) : DEMPTY;
+                }
+#pragma unroll
+                for (int q = 0; q < DD_PER; q++) {
+                    if (!pending[q]) continue;
+                    uint32_t slot = key_hash32(key[q]) & (DD_SLOTS - 1);
+                    for (int probes = 0; probes < DD_MAXPROBE; probes++) {
+                        const u128 c = cas_shared(&dkeys[slot], DEMPTY, key[q]);
+                        if (c == DEMPTY) { atomicAdd(&s_dcount, 1u); atomicAdd(&dw[slot], 1u); pending[q] = false; break; }
+                        if (c == key[q]) { atomicAdd(&dw[slot], 1u); pending[q] = false; break; }
+                        slot = (slot + 1) & (DD_SLOTS - 1);
+                    }
+                    if (pending[q]) atomicAdd(&s_pending, 1u);   // no room within the probe limit: retried after the flush
+                }
+                __syncthreads();
+                const uint32_t npend = s_pending;
+                if (last || npend != 0 || s_dcount > DD_CAP) {
+                    // ---- expansion, balanced: prefix sum of the entries' lengths in slot order, every thread takes an equal share of
+                    // consecutive k-mer instances (binary search for its first entry, then the k-mers roll through two registers)
+                    {
+                        uint32_t l0 = 0, l1 = 0;
+                        const u128 e0 = dkeys[2 * tid], e1 = dkeys[2 * tid + 1];
+                        if (!(e0 == DEMPTY)) l0 = (uint32_t)(e0.lo & 63) + 1;
+                        if (!(e1 == DEMPTY)) l1 = (uint32_t)(e1.lo & 63) + 1;
+                        uint32_t incl = l0 + l1;
+                        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+                        if (lane == 31) s_wsum[warp] = incl;
+                        __syncthreads();
+                        uint32_t wbase = 0;
+                        for (int w = 0; w < warp; w++) wbase += s_wsum[w];
+                        const uint32_t excl = wbase + incl - (l0 + l1);
+                        dpfx[2 * tid] = (uint16_t)excl;
+                        dpfx[2 * tid + 1] = (uint16_t)(excl + l0);
+                        if (tid == COUNT_THREADS - 1) dpfx[DD_SLOTS] = (uint16_t)(excl + l0 + l1);
+                        __syncthreads();
+                    }
+                    {
+                        // ONE flat loop of `per` steps for every thread (a nest of per-entry loops left the lanes of a warp at different
+                        // nesting points: ncu showed the insert body executed ~12x more often than converged lanes would need)
+                        const uint32_t T = dpfx[DD_SLOTS];
+                        const uint32_t per = (T + COUNT_THREADS - 1) / COUNT_THREADS;
+                        const uint32_t i0 = tid * per;
+                        const uint32_t nmine = i0 < T ? min(per, T - i0) : 0u;
+                        uint32_t sl = 0, j = 0, len = 0, w = 0;
+                        uint64_t x0 = 0, x1 = 0;
+                        if (nmine) {
+                            uint32_t lo_s = 0, hi_s = DD_SLOTS;   // last slot with dpfx[slot] <= i0; it is non-empty when it holds instance i0
+                            while (hi_s - lo_s > 1) { const uint32_t mid = (lo_s + hi_s) >> 1; if (dpfx[mid] <= i0) lo_s = mid; else hi_s = mid; }
+                            sl = lo_s;
+                            const u128 e = dkeys[sl];
+                            len = (uint32_t)(e.lo & 63) + 1;
+                            w = dw[sl];
+                            j = i0 - dpfx[sl];
+                            x0 = e.hi; x1 = e.lo & ~0xFFull;
+                            if (j) { x0 = (x0 << (2 * j)) | (x1 >> (64 - 2 * j)); x1 <<= 2 * j; }
+                        }
+                        for (uint32_t n = 0; n < per; n++) {
+                            if (n >= nmine) continue;
+                            if (j == len) {   // next non-empty entry
+                                u128 e;
+                                do { sl++; e = dkeys[sl]; } while (e == DEMPTY);
+                                len = (uint32_t)(e.lo & 63) + 1;
+                                w = dw[sl];
+                                j = 0;
+                                x0 = e.hi; x1 = e.lo & ~0xFFull;
+                            }
+                            const uint64_t fwd = x0 >> kshift;
+                            const uint64_t rc = revcomp(fwd, k);
+                            const uint64_t kk = fwd < rc ? fwd : rc;
+                            x0 = (x0 << 2) | (x1 >> 62);
+                            x1 <<= 2;
+                            j++;
+                            const uint32_t h = key_hash32(kk);
+                            if ((((h * 0x9E3779B1u) >> 8) & cmask) != prefix) continue;
+                            uint32_t slot = (uint32_t)(((uint64_t)h * (uint32_t)S) >> 32);
+                            int probes = 0;
+                            while (true) {
+                                const uint64_t c = slot_claim(&keys[slot], kk);
+                                if (c == EMPTY || c == kk) { atomicAdd(&cnt[slot], w); break; }
+                                slot = slot + 1 == (uint32_t)S ? 0 : slot + 1;
+                                if (++probes >= CK_MAXPROBE) { *(volatile uint32_t*)&s_overflow = 1; break; }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    for (int s = tid; s < DD_SLOTS; s += COUNT_THREADS) { dkeys[s] = DEMPTY; dw[s] = 0; }
+                    if (tid == 0) { s_dcount = 0; s_pending = 0; }
+                    __syncthreads();
+                    if (npend != 0 && !*(volatile uint32_t*)&s_overflow) {   // records that found no room: the table is empty now
+#pragma unroll
+                        for (int q = 0; q < DD_PER; q++) {
+                            if (!pending[q]) continue;
+                            uint32_t slot = key_hash32(key[q]) & (DD_SLOTS - 1);
+                            for (int probes = 0; probes < DD_SLOTS; probes++) {
+                                const u128 c = cas_shared(&dkeys[slot], DEMPTY, key[q]);
+                                if (c == DEMPTY) { atomicAdd(&s_dcount, 1u); atomicAdd(&dw[slot], 1u); break; }
+                                if (c == key[q]) { atomicAdd(&dw[slot], 1u); break; }
+                                slot = (slot + 1) & (DD_SLOTS - 1);
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                if (last || *(volatile uint32_t*)&s_overflow) break;
+            }
+            __syncthreads();
+            if (*(volatile uint32_t*)&s_overflow) {   // split this class on the next hash bit and retry both halves
+                if (tid == 0) {
+                    if (level >= 20 || sp + 1 > CK_STACK) *errflag = 1;
+                    else { s_stack[sp - 1] = ((level + 1) << 24) | prefix; s_stack[sp] = ((level + 1) << 24) | prefix | (1u << level); s_sp = sp + 1; }
+                }
+                __syncthreads();
+                if (*(volatile int*)errflag == 1) break;
+                continue;
+            }
+            // ---- sweep: histogram (Histogram::inc takes a u16: CountProcessorHistogram.hpp:174-185, Histogram.hpp:92) and candidates
+            uint32_t emit_mask = 0;
+            for (int j = 0; j * COUNT_THREADS < S; j++) {
+                const int s = tid + j * COUNT_THREADS;
+                if (s < S && keys[s] != EMPTY) {
+                    const uint32_t c = cnt[s];
+                    uint32_t hidx = c & 0xFFFFu;
+                    if (hidx > HISTO_MAX) hidx = HISTO_MAX;
+                    if (hidx < SMEM_HIST) atomicAdd(&hist_s[hidx], 1u); else atomicAdd(&histo[hidx], 1ull);
+                    if (c >= emit_min) emit_mask |= 1u << j;
+                }
+            }
+            {
+                const uint32_t mine = __popc(emit_mask);
+                uint32_t incl = mine;
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+                if (lane == 31) s_wsum[warp] = incl;
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t run = 0;
+                    for (int w = 0; w < COUNT_THREADS / 32; w++) { const uint32_t v = s_wsum[w]; s_wsum[w] = run; run += v; }
+                    s_cbase = run ? atomicAdd(ncand, (unsigned long long)run) : 0ull;
+                }
+                __syncthreads();
+                unsigned long long o = s_cbase + s_wsum[warp] + (incl - mine);
+                while (emit_mask) {
+                    const int j = __ffs(emit_mask) - 1;
+                    emit_mask &= emit_mask - 1;
+                    const int s = tid + j * COUNT_THREADS;
+                    if (o < cand_capacity) { cand_keys[o] = keys[s]; cand_cnt[o] = cnt[s]; } else *errflag = 2;
+                    o++;
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) { atomicAdd(&gstats[0], 1ull); atomicAdd(&gstats[3], (unsigned long long)npasses); if (npasses > 1) atomicAdd(&gstats[1], 1ull); }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid < SMEM_HIST && hist_s[tid]) atomicAdd(&histo[tid], (unsigned long long)hist_s[tid]);
+}
+static const int DD_SMEM = (int)(sizeof(u128) * DD_SLOTS + (sizeof(uint64_t) + 4) * DD_S + 4 * DD_SLOTS + 4 * SMEM_HIST + 2 * (DD_SLOTS + 2));
+
 // candidates -> solid set at the final threshold. A block compacts tiles of 1024 candidates: per-warp ballots, one shared-memory
 // scan, ONE global reservation per tile (a reservation per warp on the single counter serialises in L2).
 static const int FK_PER = 4;
@@ -782,7 +1029,7 @@ template <class K> class Counter : public ICounter {
     }
 
 public:
-    bool distinct_hint_ = false;
+    bool distinct_hint_ = false, dedup_ = false;
     uint64_t nvalid_total_ = 0;   // valid k-mer instances pushed so far (host copy)
     ~Counter() override {
         if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
@@ -801,6 +1048,9 @@ public:
         flags_.zero(stream_);
         const int smem = (int)(sizeof(K) + 4) * CountCfg<K>::SLOTS + SMEM_HIST * 4 + (COUNT_THREADS / 32) * CK_SLATE * 2;
         MTG_CUDA(cudaFuncSetAttribute(count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (sizeof(K) == 8) MTG_CUDA(cudaFuncSetAttribute(count_kernel_dd, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM));
+        const char* nd = getenv("MTG_COUNT_NODEDUP");
+        dedup_ = sizeof(K) == 8 && !distinct_hint && !(nd && *nd == '1');   // a reference (every k-mer distinct) has nothing to fold
     }
     cudaStream_t stream() const override { return stream_; }
     void reserve(uint64_t nb_bases) override { size_hint_ = std::max(size_hint_, nb_bases); ensure_words(words_used_ + nb_bases / 32 + 2); }
@@ -1108,9 +1358,16 @@ public:
             t.start();
             if (total_rec) {
                 const int smem = (int)(sizeof(K) + 4) * S + SMEM_HIST * 4 + (COUNT_THREADS / 32) * CK_SLATE * 2;
-                count_kernel<K><<<sm_count_ * 2, COUNT_THREADS, smem, stream_>>>(packed_ptr, grouped.p, grp_off.p, max_groups, d_item_counter.p, k_,
-                                                                                emit_min, d_histo.p, cand_keys.p, cand_cnt.p, counters_.p + 2,
-                                                                                cand_cap, gstats.p, flags_.p + 1);
+                if constexpr (sizeof(K) == 8) {
+                    if (dedup_)   // 64-bit k-mers: identical super-k-mers folded first (count_kernel_dd)
+                        count_kernel_dd<<<sm_count_ * 2, COUNT_THREADS, DD_SMEM, stream_>>>(packed_ptr, grouped.p, grp_off.p, max_groups, d_item_counter.p, k_,
+                                                                                            emit_min, d_histo.p, (uint64_t*)cand_keys.p, cand_cnt.p, counters_.p + 2,
+                                                                                            cand_cap, gstats.p, flags_.p + 1);
+                }
+                if (sizeof(K) != 8 || !dedup_)
+                    count_kernel<K><<<sm_count_ * 2, COUNT_THREADS, smem, stream_>>>(packed_ptr, grouped.p, grp_off.p, max_groups, d_item_counter.p, k_,
+                                                                                    emit_min, d_histo.p, cand_keys.p, cand_cnt.p, counters_.p + 2,
+                                                                                    cand_cap, gstats.p, flags_.p + 1);
                 MTG_CUDA(cudaGetLastError());
                 st_.launches++;
             }
