@@ -397,14 +397,41 @@ __global__ void __launch_bounds__(GP_THREADS) group_assign_kernel(const unsigned
     if (a_nrec) atomicAdd(&grp_nrec[cur_g], a_nrec);
 }
 // ------------------------------------------------------------------------------------------------------------
+// The two packed words that hold a record's bases, left-aligned (first base of the super-k-mer in the top bits of x0): what the
+// de-duplicating count kernel keys on. A record spans <= 60 bases for k <= 31 (SK_MAXRUN); the tail beyond the span is masked later.
+MTG_D void record_words(const uint64_t* __restrict__ packed, uint64_t r, uint64_t& x0, uint64_t& x1) {
+    const uint64_t pos = r >> REC_POS_SHIFT;
+    const uint64_t a = pos >> 5;
+    const int off = 2 * (int)(pos & 31);
+    const uint64_t p0 = packed[a], p1 = packed[a + 1], p2 = packed[a + 2];   // the arrays are padded
+    x0 = off ? (p0 << off) | (p1 >> (64 - off)) : p0;
+    x1 = off ? (p1 << off) | (p2 >> (64 - off)) : p1;
+}
+// One 32-byte sector per record: {record, x0, x1, 0}, moved with the 256-bit load / store of sm_100 (LDG.256 / STG.256).
+MTG_D void fat_store(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+MTG_D void fat_load(const uint64_t* p, uint64_t& a, uint64_t& b, uint64_t& c) {
+    uint64_t d;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+// records -> contiguous per-group lists. fat != null: the record's bases travel with it, one whole 32-byte sector per record written
+// by one store. The records of a batch are in read order, so this kernel reads the packed reads (almost) sequentially and the count
+// kernel then streams its group's bases instead of fetching 64 random bytes per record (332 M random DRAM reads at cfg3: the bound
+// of count_kernel_dd at 27 G accesses/s, profiles/ncu_r02_notes.md).
 __global__ void __launch_bounds__(256) scatter_kernel(const uint64_t* __restrict__ records, uint64_t nrec, const uint32_t* __restrict__ group_of,
                                                       const uint64_t* __restrict__ group_off, unsigned int* __restrict__ group_cur,
-                                                      uint64_t* __restrict__ grouped) {
+                                                      uint64_t* __restrict__ grouped, const uint64_t* __restrict__ packed,
+                                                      uint64_t* __restrict__ fat) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t r = records[i];
         uint32_t g = group_of[r & ((1u << REC_LEN_SHIFT) - 1)];
+        uint64_t x0 = 0, x1 = 0;
+        if (fat) record_words(packed, r, x0, x1);
         unsigned int slot = atomicAdd(&group_cur[g], 1u);
-        grouped[group_off[g] + slot] = r;
+        const uint64_t o = group_off[g] + slot;
+        if (fat) fat_store(fat + 4 * o, r, x0, x1, 0);
+        else grouped[o] = r;
     }
 }
 
@@ -604,14 +631,8 @@ count_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ g
 static const int DD_SLOTS = 1024, DD_CAP = 512, DD_MAXPROBE = 32;   // the table is flushed (expanded + cleared) above DD_CAP entries
 static const int DD_PER = 2;                                        // records per thread and batch
 static const int DD_S = 7424;                                       // k-mer table slots (any size: slot = hash * S >> 32)
-MTG_D u128 dd_key(const uint64_t* __restrict__ packed, uint64_t r, int k) {
-    const uint64_t pos = r >> REC_POS_SHIFT;
+MTG_D u128 dd_key_words(uint64_t x0, uint64_t x1, uint64_t r, int k) {
     const int len = (int)((r >> REC_LEN_SHIFT) & 63) + 1, span = len + k - 1;   // <= 60
-    const uint64_t a = pos >> 5;
-    const int off = 2 * (int)(pos & 31);
-    const uint64_t p0 = packed[a], p1 = packed[a + 1], p2 = packed[a + 2];       // the arrays are padded
-    uint64_t x0 = off ? (p0 << off) | (p1 >> (64 - off)) : p0;
-    uint64_t x1 = off ? (p1 << off) | (p2 >> (64 - off)) : p1;
     if (span <= 32) { x0 &= span == 32 ? ~0ull : ~(~0ull >> (2 * span)); x1 = 0; }
     else x1 &= ~(~0ull >> (2 * (span - 32)));
     // reverse complement of the span, left-aligned: rc of the 64-base string starts with 64 - span T's (the zero padding)
@@ -623,9 +644,16 @@ MTG_D u128 dd_key(const uint64_t* __restrict__ packed, uint64_t r, int k) {
     const bool use_rc = c0 < x0 || (c0 == x0 && c1 < x1);
     return u128((use_rc ? c1 : x1) | (uint64_t)(len - 1), use_rc ? c0 : x0);     // lo word carries the length in its free low byte
 }
+MTG_D u128 dd_key(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ fat, const uint64_t* __restrict__ grouped, uint64_t idx, int k) {
+    uint64_t r, x0, x1;
+    if (fat) fat_load(fat + 4 * idx, r, x0, x1);
+    else { r = grouped[idx]; record_words(packed, r, x0, x1); }
+    return dd_key_words(x0, x1, r, k);
+}
 
 __global__ void __launch_bounds__(COUNT_THREADS, 2)
-count_kernel_dd(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ grouped, const unsigned long long* __restrict__ grp_off,
+count_kernel_dd(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ fat, const uint64_t* __restrict__ grouped,
+                const unsigned long long* __restrict__ grp_off,
                 uint32_t ngroups, unsigned int* __restrict__ item_counter, int k, uint32_t emit_min, unsigned long long* __restrict__ histo,
                 uint64_t* __restrict__ cand_keys, uint32_t* __restrict__ cand_cnt, unsigned long long* __restrict__ ncand, uint64_t cand_capacity,
                 unsigned long long* __restrict__ gstats, int* __restrict__ errflag) {
@@ -658,7 +686,6 @@ count_kernel_dd(const uint64_t* __restrict__ packed, const uint64_t* __restrict_
         if (it >= ngroups) break;
         const uint64_t rec_off = grp_off[it];
         const uint32_t nrec = (uint32_t)(grp_off[it + 1] - rec_off);
-        const uint64_t* recs = grouped + rec_off;
         uint32_t npasses = 0;
         while (true) {   // hash classes of this group, depth first (a class that overflows the k-mer table is split and redone)
             const uint32_t sp = s_sp;
@@ -681,7 +708,7 @@ count_kernel_dd(const uint64_t* __restrict__ packed, const uint64_t* __restrict_
                 for (int q = 0; q < DD_PER; q++) {   // the random loads of the batch are issued together
                     const uint32_t i = base + (uint32_t)q * COUNT_THREADS + tid;
                     pending[q] = !last && i < nrec;
-                    key[q] = pending[q] ? dd_key(packed, recs[i], k) : DEMPTY;
+                    key[q] = pending[q] ? dd_key(packed, fat, grouped, rec_off + i, k) : DEMPTY;
                 }
 #pragma unroll
                 for (int q = 0; q < DD_PER; q++) {
@@ -1289,7 +1316,9 @@ public:
         const int S = CountCfg<K>::SLOTS;
         // instances per group: the table holds distinct k-mers, so at sequencing coverage a group may carry about as many
         // instances as there are slots; `distinct_hint` (reference counting: every k-mer distinct) halves that
-        const uint32_t group_target = distinct_hint_ ? S / 2 : S;
+        // with de-duplication the fixed cost per group (table clear + sweep, barriers) is spread over twice the instances: the table
+        // holds DISTINCT k-mers, ~3 000 of 7 424 slots for 16 384 instances at sequencing coverage
+        const uint32_t group_target = distinct_hint_ ? S / 2 : (dedup_ ? (uint32_t)(getenv("MTG_DD_GROUP") ? atoi(getenv("MTG_DD_GROUP")) : 2 * S) : S);
         EventTimer t(stream_);
         Trace tr(stream_);
         // ---- grouping of minimizer bins into work items, entirely on the device (no host round trip)
@@ -1305,7 +1334,13 @@ public:
         DevBuf<unsigned long long> tile_off(ntiles + 1), grp_off(max_groups + 1), gstats(4);
         DevBuf<uint32_t> d_group_of(NM);
         DevBuf<unsigned int> d_gcur(max_groups + 1);
-        DevBuf<uint64_t> grouped(std::max<uint64_t>(total_rec, 1));
+        // de-duplicating kernel: 32-byte records that carry their bases (MTG_COUNT_NOPAYLOAD=1: 8-byte records, bases fetched from
+        // the packed reads; kept for A/B measurements)
+        const char* npl = getenv("MTG_COUNT_NOPAYLOAD");
+        const bool fat_records = dedup_ && !(npl && *npl == '1');
+        DevBuf<uint64_t> grouped(fat_records ? 1 : std::max<uint64_t>(total_rec, 1));
+        DevBuf<uint64_t> payload;
+        if (fat_records) payload.alloc(4 * std::max<uint64_t>(total_rec, 1));
         grp_off.zero(stream_); gstats.zero(stream_); d_gcur.zero(stream_);
         tr.mark("finish: allocs");
         group_tile_sum_kernel<<<ntiles, GP_THREADS, 0, stream_>>>(mhist_.p, NM, tile_off.p);
@@ -1321,13 +1356,13 @@ public:
         for (auto& b : batches_) {
             if (!b.nrec) continue;
             int grid = (int)std::min<uint64_t>((b.nrec + 255) / 256, (uint64_t)sm_count_ * 16);
-            scatter_kernel<<<grid, 256, 0, stream_>>>(b.recs.p, b.nrec, d_group_of.p, (const uint64_t*)grp_off.p, d_gcur.p, grouped.p);
+            scatter_kernel<<<grid, 256, 0, stream_>>>(b.recs.p, b.nrec, d_group_of.p, (const uint64_t*)grp_off.p, d_gcur.p, grouped.p, packed_ptr, payload.p);
             MTG_CUDA(cudaGetLastError());
             st_.launches++;
         }
         if (ext_records_ && ext_nrec_) {
             int grid = (int)std::min<uint64_t>((ext_nrec_ + 255) / 256, (uint64_t)sm_count_ * 16);
-            scatter_kernel<<<grid, 256, 0, stream_>>>(ext_records_, ext_nrec_, d_group_of.p, (const uint64_t*)grp_off.p, d_gcur.p, grouped.p);
+            scatter_kernel<<<grid, 256, 0, stream_>>>(ext_records_, ext_nrec_, d_group_of.p, (const uint64_t*)grp_off.p, d_gcur.p, grouped.p, packed_ptr, payload.p);
             MTG_CUDA(cudaGetLastError());
             st_.launches++;
         }
@@ -1360,7 +1395,7 @@ public:
                 const int smem = (int)(sizeof(K) + 4) * S + SMEM_HIST * 4 + (COUNT_THREADS / 32) * CK_SLATE * 2;
                 if constexpr (sizeof(K) == 8) {
                     if (dedup_)   // 64-bit k-mers: identical super-k-mers folded first (count_kernel_dd)
-                        count_kernel_dd<<<sm_count_ * 2, COUNT_THREADS, DD_SMEM, stream_>>>(packed_ptr, grouped.p, grp_off.p, max_groups, d_item_counter.p, k_,
+                        count_kernel_dd<<<sm_count_ * 2, COUNT_THREADS, DD_SMEM, stream_>>>(packed_ptr, payload.p, grouped.p, grp_off.p, max_groups, d_item_counter.p, k_,
                                                                                             emit_min, d_histo.p, (uint64_t*)cand_keys.p, cand_cnt.p, counters_.p + 2,
                                                                                             cand_cap, gstats.p, flags_.p + 1);
                 }
