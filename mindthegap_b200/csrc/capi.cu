@@ -150,7 +150,7 @@ struct mtg_ctx {
     // replay
     std::unique_ptr<ParallelReplayer<uint64_t>> rp64;
     std::unique_ptr<ParallelReplayer<hu128>> rp128;
-    PinnedBuf feat, rep, interest, probe_keys, probe_ans;
+    PinnedBuf feat, rep, interest, probe_keys[2], probe_ans[2];
     int host_threads = 0;  // 0 = all host cores (-nb-cores 0)
     double ms_features = 0, ms_replay = 0, ms_graph_build = 0;
     uint64_t scan_positions = 0, scan_valid = 0, scan_in_graph = 0, scan_table_probes = 0, scan_fallback = 0;
@@ -213,13 +213,14 @@ static void make_replayers(mtg_ctx* c) {
     if (c->rp64) c->rp64->set_threads(c->host_threads);
     if (c->rp128) c->rp128->set_threads(c->host_threads);
     // probe batches are staged in pinned buffers that outlive the find (process-wide cache): true async DMA, no page faults
-    if (c->rp64) c->rp64->set_staging([c](size_t n, uint64_t** k, uint8_t** a) {
-        c->probe_keys.reserve(n * 8 + 64); c->probe_ans.reserve(n + 64);
-        *k = c->probe_keys.as<uint64_t>(); *a = c->probe_ans.as<uint8_t>();
+    // (two slots: the answers of a batch are read while the next batch is probed)
+    if (c->rp64) c->rp64->set_staging([c](size_t n, int slot, uint64_t** k, uint8_t** a) {
+        c->probe_keys[slot].reserve(n * 8 + 64); c->probe_ans[slot].reserve(n + 64);
+        *k = c->probe_keys[slot].as<uint64_t>(); *a = c->probe_ans[slot].as<uint8_t>();
     });
-    if (c->rp128) c->rp128->set_staging([c](size_t n, hu128** k, uint8_t** a) {
-        c->probe_keys.reserve(n * 16 + 64); c->probe_ans.reserve(n + 64);
-        *k = c->probe_keys.as<hu128>(); *a = c->probe_ans.as<uint8_t>();
+    if (c->rp128) c->rp128->set_staging([c](size_t n, int slot, hu128** k, uint8_t** a) {
+        c->probe_keys[slot].reserve(n * 16 + 64); c->probe_ans[slot].reserve(n + 64);
+        *k = c->probe_keys[slot].as<hu128>(); *a = c->probe_ans[slot].as<uint8_t>();
     });
 }
 
@@ -629,6 +630,7 @@ static const char* STAT_NAMES[] = {
     "ref.nb_repeated", "ref.bloom_bits",
     "scan.positions", "scan.valid", "scan.in_graph", "scan.table_probes", "scan.bloom_emulations", "scan.ms_features", "scan.ms_replay",
     "scan.observer_queries", "scan.probe_batches", "scan.prefetched_queries", "scan.unforeseen_queries",
+    "scan.ms_replay_collect", "scan.ms_replay_probe", "scan.ms_replay_apply", "scan.ms_replay_merge",
     "api.ms_push_reads", "api.ms_count_finish", "api.ms_set_reference", "api.ms_scan_reference",
     "ingest.bytes_in", "ingest.bytes_out", "ingest.nb_sequences", "ingest.ms", "ingest.launches",
     "mem.arena_cached_mb", "mem.arena_live_mb"};
@@ -642,6 +644,9 @@ int mtg_get_stats(mtg_ctx* ctx, double* out, int cap) {
     uint64_t oq = ctx->rp64 ? ctx->rp64->cnt.observer_queries : ctx->rp128->cnt.observer_queries;
     const ReplayCounters& rc = ctx->rp64 ? ctx->rp64->cnt : ctx->rp128->cnt;
     uint64_t pb = rc.probe_batches;
+    double rp_ms[4];
+    if (ctx->rp64) { auto& r = *ctx->rp64; rp_ms[0] = r.ms_cut + r.ms_collect + r.ms_stage; rp_ms[1] = r.ms_probe; rp_ms[2] = r.ms_apply; rp_ms[3] = r.ms_merge; }
+    else { auto& r = *ctx->rp128; rp_ms[0] = r.ms_cut + r.ms_collect + r.ms_stage; rp_ms[1] = r.ms_probe; rp_ms[2] = r.ms_apply; rp_ms[3] = r.ms_merge; }
     double v[] = {(double)c.nb_bases, (double)c.nb_valid_kmers, (double)c.nb_records, (double)c.nb_groups, (double)c.nb_items,
                   (double)c.nb_multipass_groups, (double)c.nb_candidates, (double)c.nb_solid, c.ms_pack, c.ms_extract, c.ms_group, c.ms_scatter,
                   c.ms_count, c.ms_filter, (double)c.launches, (double)c.nb_count_retries,
@@ -650,7 +655,7 @@ int mtg_get_stats(mtg_ctx* ctx, double* out, int cap) {
                   (double)g.ref_repeated, (double)g.ref_tai,
                   (double)ctx->scan_positions, (double)ctx->scan_valid, (double)ctx->scan_in_graph, (double)ctx->scan_table_probes,
                   (double)ctx->scan_fallback, ctx->ms_features, ctx->ms_replay, (double)oq, (double)pb, (double)rc.prefetched_queries,
-                  (double)rc.unforeseen_queries, ctx->wall_push, ctx->wall_finish, ctx->wall_set_reference, ctx->wall_scan,
+                  (double)rc.unforeseen_queries, rp_ms[0], rp_ms[1], rp_ms[2], rp_ms[3], ctx->wall_push, ctx->wall_finish, ctx->wall_set_reference, ctx->wall_scan,
                   (double)ctx->ingest_total.bytes_in, (double)ctx->ingest_total.bytes_out, (double)ctx->ingest_total.nb_sequences,
                   ctx->ingest_total.ms, (double)ctx->ingest_total.launches, 0.0, 0.0};
     {
@@ -816,21 +821,37 @@ static void scan_reference_impl(mtg_ctx* ctx, const char* name, const char* seq,
     uint8_t* rep = ctx->rep.as<uint8_t>();
     uint32_t* interest = ctx->interest.as<uint32_t>();
     uint64_t c4[4];
-    if (d_seq) ctx->graph->features_to_host((const uint8_t*)d_seq, len, feat, rep, interest, c4);
-    else ctx->graph->features_host(seq, len, feat, rep, interest, c4);
-    ctx->ms_features += ctx->graph->last_features_ms();
-    tr.mark("scan: features + copies");
-    ctx->scan_positions += npos; ctx->scan_valid += c4[0]; ctx->scan_in_graph += c4[1]; ctx->scan_table_probes += c4[2]; ctx->scan_fallback += c4[3];
     struct timespec t0, t1;
-    clock_gettime(CLOCK_MONOTONIC, &t0);
     if (bed) {
+        if (d_seq) ctx->graph->features_to_host((const uint8_t*)d_seq, len, feat, rep, interest, c4);
+        else ctx->graph->features_host(seq, len, feat, rep, interest, c4);
+        tr.mark("scan: features + copies");
+        clock_gettime(CLOCK_MONOTONIC, &t0);
         if (ctx->rp64) ctx->rp64->scan_bed(name ? name : "", seq, len, feat, rep, *bed);
         else ctx->rp128->scan_bed(name ? name : "", seq, len, feat, rep, *bed);
-    } else if (ctx->rp64) ctx->rp64->scan(name ? name : "", seq, len, feat, rep, interest);
-    else ctx->rp128->scan(name ? name : "", seq, len, feat, rep, interest);
-    clock_gettime(CLOCK_MONOTONIC, &t1);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+    } else {
+        // staged: the features of a long sequence arrive in three pieces and the replay of a piece starts when it is there
+        // (ParallelReplayer::scan); ms_replay therefore includes what was left to wait for the features
+        uint64_t ends[4] = {0, 0, 0, 0};
+        const int nst = ctx->graph->features_to_host_begin((const uint8_t*)d_seq, seq, len, feat, rep, interest, ends);
+        std::vector<size_t> avail(ends, ends + std::max(nst, 0));
+        if (avail.empty() || avail.back() != npos) avail.push_back(npos);
+        IGraph* g = ctx->graph.get();
+        mtg_ctx* c = ctx;
+        auto wait = [g, c, nst](size_t i) { enter(c); if ((int)i < nst) g->features_wait_stage((int)i); else g->features_finish(nullptr); };
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        try {
+            if (ctx->rp64) ctx->rp64->scan(name ? name : "", seq, len, feat, rep, interest, &avail, wait);
+            else ctx->rp128->scan(name ? name : "", seq, len, feat, rep, interest, &avail, wait);
+        } catch (...) { try { ctx->graph->features_finish(nullptr); } catch (...) {} throw; }
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        ctx->graph->features_finish(c4);
+        tr.mark("scan: features + replay");
+    }
+    ctx->ms_features += ctx->graph->last_features_ms();
+    ctx->scan_positions += npos; ctx->scan_valid += c4[0]; ctx->scan_in_graph += c4[1]; ctx->scan_table_probes += c4[2]; ctx->scan_fallback += c4[3];
     ctx->ms_replay += (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
-    tr.mark("scan: replay");
 }
 static void replay_impl(mtg_ctx* ctx, const char* name, const char* seq, uint64_t len, const uint8_t* feat, const uint8_t* rep, const uint32_t* interest) {
     struct timespec t0, t1;

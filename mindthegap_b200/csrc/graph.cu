@@ -1723,13 +1723,14 @@ public:
     cudaStream_t copy_stream_ = nullptr;
     std::vector<cudaEvent_t> chunk_ev_;
     void features_device(const uint8_t* d_seq, uint64_t len, uint8_t* d_feat, uint8_t* d_rep, uint32_t* d_interest, uint64_t* counters_host4) override {
-        features_device_impl(d_seq, len, d_feat, d_rep, d_interest, counters_host4, nullptr);
+        features_device_impl(d_seq, len, d_feat, d_rep, d_interest, counters_host4, nullptr, nullptr);
     }
-    void features_device_impl(const uint8_t* d_seq, uint64_t len, uint8_t* d_feat, uint8_t* d_rep, uint32_t* d_interest, uint64_t* counters_host4,
-                              const HostDst* host) {
+    // returns the number of stages; stage_end[i] (host != null) = positions final in the host arrays after copied_ev_[i]
+    int features_device_impl(const uint8_t* d_seq, uint64_t len, uint8_t* d_feat, uint8_t* d_rep, uint32_t* d_interest, uint64_t* counters_host4,
+                             const HostDst* host, uint64_t* stage_end) {
         if (counters_host4) memset(counters_host4, 0, 32);
         last_features_ms_ = 0;
-        if (len < (uint64_t)k_) return;
+        if (len < (uint64_t)k_) return 0;
         const uint64_t npos = len - k_ + 1;
         const uint64_t nwords = (len + 31) / 32;
         if (seq_packed_.n < nwords + 8) { seq_packed_.alloc(nwords + 8 + nwords / 4); seq_inv_.alloc(nwords + 8 + nwords / 4); }
@@ -1764,8 +1765,10 @@ public:
                     MTG_CUDA(cudaMemcpyAsync(host->rep + p0, d_rep + p0, p1 - p0, cudaMemcpyDeviceToHost, copy_stream_));
                     if (host->interest) MTG_CUDA(cudaMemcpyAsync(host->interest + p0 / 32, d_interest + p0 / 32, ((p1 - p0 + 31) / 32) * 4, cudaMemcpyDeviceToHost, copy_stream_));
                 }
+                if (stage_end) { MTG_CUDA(cudaEventRecord(copied_ev_[c], copy_stream_)); stage_end[c] = p1; }
             }
         }
+        if (stage_end && nchunks == 1) stage_end[0] = npos;
         MTG_CUDA(cudaEventRecord(ev_b_, stream_));
         features_timed_ = true;
         st_.launches++;
@@ -1773,30 +1776,59 @@ public:
             MTG_CUDA(cudaMemcpyAsync(counters_host4, counters_.p, 32, cudaMemcpyDeviceToHost, stream_));
             MTG_CUDA(cudaStreamSynchronize(stream_));
         }
+        return (int)nchunks;
     }
     void features_host(const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint32_t* interest, uint64_t* counters_host4) override {
-        if (counters_host4) memset(counters_host4, 0, 32);
-        if (len < (uint64_t)k_) return;
-        if (seq_stage_.n < len + 64) seq_stage_.alloc(len + 64 + len / 4);
-        MTG_CUDA(cudaMemcpyAsync(seq_stage_.p, seq, len, cudaMemcpyHostToDevice, stream_));
-        features_to_host(seq_stage_.p, len, feat, rep, interest, counters_host4);
+        uint64_t ends[4];
+        features_to_host_begin(nullptr, seq, len, feat, rep, interest, ends);
+        features_finish(counters_host4);
     }
     void features_to_host(const uint8_t* d_seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint32_t* interest, uint64_t* counters_host4) override {
-        if (counters_host4) memset(counters_host4, 0, 32);
-        if (len < (uint64_t)k_) return;
+        uint64_t ends[4];
+        features_to_host_begin(d_seq, nullptr, len, feat, rep, interest, ends);
+        features_finish(counters_host4);
+    }
+    // Staged variant: everything is enqueued and the call returns; stage i (positions < stage_end[i]) has arrived in the host arrays
+    // once features_wait_stage(i) returns, so the host replay of the first stages runs while the later ones are computed and copied.
+    std::vector<cudaEvent_t> copied_ev_;
+    uint64_t* h_counters_ = nullptr;   // pinned: a copy into pageable memory would block the enqueue until the kernels are done
+    int stages_pending_ = 0;
+    int features_to_host_begin(const uint8_t* d_seq, const char* h_seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint32_t* interest,
+                               uint64_t* stage_end) override {
+        stages_pending_ = 0;
+        if (!h_counters_) MTG_CUDA(cudaMallocHost((void**)&h_counters_, 32));
+        memset(h_counters_, 0, 32);
+        if (len < (uint64_t)k_) return 0;
+        if (!d_seq) {
+            if (seq_stage_.n < len + 64) seq_stage_.alloc(len + 64 + len / 4);
+            MTG_CUDA(cudaMemcpyAsync(seq_stage_.p, h_seq, len, cudaMemcpyHostToDevice, stream_));
+            d_seq = seq_stage_.p;
+        }
         const uint64_t npos = len - k_ + 1;
         if (d_feat_.n < len + 64) { d_feat_.alloc(len + 64 + len / 4); d_rep_.alloc(len + 64 + len / 4); }
         const uint64_t ntiles = (npos + FT_TILE - 1) / FT_TILE;
         HostDst dst{feat, rep, interest};
-        features_device_impl(d_seq, len, d_feat_.p, d_rep_.p, nullptr, nullptr, &dst);
+        while (copied_ev_.size() < 3) { cudaEvent_t e; MTG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); copied_ev_.push_back(e); }
+        const int nst = features_device_impl(d_seq, len, d_feat_.p, d_rep_.p, nullptr, nullptr, &dst, stage_end);
         if (ntiles < 64) {   // small sequence: one kernel, copies behind it
             MTG_CUDA(cudaMemcpyAsync(feat, d_feat_.p, npos, cudaMemcpyDeviceToHost, stream_));
             MTG_CUDA(cudaMemcpyAsync(rep, d_rep_.p, npos, cudaMemcpyDeviceToHost, stream_));
             if (interest) MTG_CUDA(cudaMemcpyAsync(interest, d_interest_.p, ((npos + 31) / 32) * 4, cudaMemcpyDeviceToHost, stream_));
+            MTG_CUDA(cudaEventRecord(copied_ev_[0], stream_));
         }
-        if (counters_host4) MTG_CUDA(cudaMemcpyAsync(counters_host4, counters_.p, 32, cudaMemcpyDeviceToHost, stream_));
+        MTG_CUDA(cudaMemcpyAsync(h_counters_, counters_.p, 32, cudaMemcpyDeviceToHost, stream_));
+        stages_pending_ = nst;
+        return nst;
+    }
+    void features_wait_stage(int i) override {
+        if (i < 0 || i >= stages_pending_) return;
+        MTG_CUDA(cudaEventSynchronize(copied_ev_[i]));
+    }
+    void features_finish(uint64_t* counters_host4) override {
         MTG_CUDA(cudaStreamSynchronize(stream_));
         if (copy_stream_) MTG_CUDA(cudaStreamSynchronize(copy_stream_));
+        stages_pending_ = 0;
+        if (counters_host4) { if (h_counters_) memcpy(counters_host4, h_counters_, 32); else memset(counters_host4, 0, 32); }
     }
 
     uint64_t copy_bits(int which, uint8_t* host_buf) const override {

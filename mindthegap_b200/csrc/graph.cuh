@@ -420,6 +420,12 @@ public:
     virtual void features_host(const char* seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint32_t* interest, uint64_t* counters_host4) = 0;
     // same, sequence already on the device, features copied to host arrays
     virtual void features_to_host(const uint8_t* d_seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint32_t* interest, uint64_t* counters_host4) = 0;
+    // staged: enqueue only (d_seq, or h_seq when d_seq is null); returns the number of stages (<= 4) and their end positions; the
+    // host arrays must be pinned. features_wait_stage(i) blocks until stage i has arrived, features_finish until everything has.
+    virtual int features_to_host_begin(const uint8_t* d_seq, const char* h_seq, uint64_t len, uint8_t* feat, uint8_t* rep, uint32_t* interest,
+                                       uint64_t* stage_end) = 0;
+    virtual void features_wait_stage(int i) = 0;
+    virtual void features_finish(uint64_t* counters_host4) = 0;
     // raw copies for parity tests: which = 0 bloom,1..3 bloom2..4, 4 refbloom, 5 mphf levels; returns byte size
     virtual uint64_t copy_bits(int which, uint8_t* host_buf) const = 0;
     virtual const GraphStats& stats() const = 0;

@@ -28,6 +28,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <exception>
+#include <chrono>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -826,6 +827,10 @@ private:
 // (Replayer::begin_steady). Chunks are replayed independently on the host pool: collect passes in parallel, ONE batched
 // GPU probe for all chunks of a batch, real passes in parallel, then texts and counters are merged in reference order
 // and the shared bkpt ids renumbered. The output is byte-identical to the sequential replay (tests/test_host_replay.py).
+struct PhaseClock {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    double lap() { auto n = std::chrono::steady_clock::now(); double ms = std::chrono::duration<double, std::milli>(n - t).count(); t = n; return ms; }
+};
 template <class K> class ParallelReplayer {
 public:
     ParallelReplayer(const ReplayOptions& o, ProbeFn<K> probe, int nthreads = 0) : opt_(o), probe_(probe), nthreads_(nthreads) {
@@ -839,85 +844,95 @@ public:
     size_t chunk_positions = (size_t)1 << 17;    // target chunk length
     size_t skip_min = 512;
     void set_threads(int n) { nthreads_ = n; }  // 0 = every thread of the host pool
-    // optional: where the probe keys / answers of a batch are staged (n entries each); e.g. pinned host memory
-    void set_staging(std::function<void(size_t, K**, uint8_t**)> f) { staging_ = f; }
+    // optional: where the probe keys / answers of a batch are staged (n entries each, slot 0 or 1: two batches are alive at a time);
+    // e.g. pinned host memory
+    void set_staging(std::function<void(size_t, int, K**, uint8_t**)> f) { staging_ = f; }
     uint64_t nb_chunks = 0;                      // chunks replayed so far (statistics)
+    // wall time per phase of the calling thread (statistics); ms_probe = what was left to wait for when the answers were needed
+    double ms_wait = 0, ms_cut = 0, ms_collect = 0, ms_stage = 0, ms_probe = 0, ms_apply = 0, ms_merge = 0;
 
-    void scan(const std::string& name, const char* seq, size_t len, const uint8_t* feat, const uint8_t* rep, const uint32_t* interest = nullptr) {
+    // `avail` / `wait_stage` (optional): the features arrive in stages -- after wait_stage(i) returns, positions < (*avail)[i] of
+    // feat / rep / interest are final ((*avail).back() == npos). The replay of a stage starts as soon as it has arrived, and the
+    // batched GPU probe of one batch runs (on a helper thread) while the pool collects the next batch / applies the previous one.
+    void scan(const std::string& name, const char* seq, size_t len, const uint8_t* feat, const uint8_t* rep, const uint32_t* interest = nullptr,
+              const std::vector<size_t>* avail = nullptr, const std::function<void(size_t)>& wait_stage = nullptr) {
         const int k = opt_.k;
         if (len < (size_t)k) return;
         const size_t npos = len - k + 1;
-        int nt = nthreads_ > 0 ? nthreads_ : HostPool::instance().size();
-        // chunk boundaries
-        std::vector<size_t> cut{0};
+        const int nt = nthreads_ > 0 ? nthreads_ : HostPool::instance().size();
+        PhaseClock pc;
         Replayer<K> probe_only(opt_, locked_probe_);
         const size_t w = probe_only.steady_window();
-        if (interest && npos >= 2 * chunk_positions) {
-            size_t target = chunk_positions;
-            while (target < npos) {
-                // first run of >= w uninteresting positions starting at or after `target`
-                size_t q0 = target, s = npos;
-                while (q0 + w < npos) {
-                    const size_t q1 = Replayer<K>::next_interesting(interest, q0, npos);
+        const bool chunked = interest && npos >= 2 * chunk_positions;
+        std::vector<size_t> cut{0};
+        size_t resume = chunk_positions;   // the next cut is the end of the first run of >= w uninteresting positions starting at or after here
+        size_t done_chunks = 0;
+        Batch prev;                        // its probe is in flight
+        struct Joiner { Batch& b; ~Joiner() { if (b.probe.joinable()) b.probe.join(); } } joiner{prev};
+        const size_t nstages = avail && !avail->empty() ? avail->size() : 1;
+        for (size_t st = 0; st < nstages; st++) {
+            const bool final_stage = st + 1 == nstages;
+            const size_t L = final_stage ? npos : std::min((*avail)[st], npos);
+            if (wait_stage) wait_stage(st);
+            ms_wait += pc.lap();
+            // chunk boundaries inside the positions that have arrived
+            while (chunked && resume < L) {
+                size_t q0 = resume, s = npos;
+                while (q0 + w <= L) {
+                    const size_t q1 = Replayer<K>::next_interesting(interest, q0, L);
                     if (q1 - q0 >= w) { s = q0 + w; break; }
                     q0 = q1 + 1;
                 }
-                if (s >= npos) break;
+                if (s >= npos) { resume = std::max(resume, std::min(q0, L)); break; }   // none (yet): the next stage resumes here
                 cut.push_back(s);
-                target = s + chunk_positions;
+                resume = s + chunk_positions;
             }
-        }
-        cut.push_back(npos);
-        const size_t nchunks = cut.size() - 1;
-        nb_chunks += nchunks;
-        if (nchunks == 1) nt = 1;
-        // batches of chunks
-        for (size_t c0 = 0; c0 < nchunks;) {
-            size_t c1 = c0 + 1;
-            while (c1 < nchunks && cut[c1 + 1] - cut[c0] <= segment_positions) c1++;
-            const size_t nc = c1 - c0;
-            std::vector<std::unique_ptr<Replayer<K>>> rp(nc);
-            std::vector<size_t> off(nc + 1, 0);
-            HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
-                rp[i].reset(new Replayer<K>(opt_, locked_probe_));
-                Replayer<K>& r = *rp[i];
-                r.skip_min = skip_min;
-                const size_t s = cut[c0 + i];
-                if (s == 0) r.begin_sequence(name, seq, len); else r.begin_steady(name, seq, len, s, w, feat, rep);
-                r.collect(s, cut[c0 + i + 1], feat, rep, interest);
-            });
-            for (size_t i = 0; i < nc; i++) off[i + 1] = off[i] + rp[i]->log_keys().size();
-            // staging of the batch's probe keys / answers: the caller's (pinned, reused across finds) buffers when it provides them --
-            // a fresh std::vector of tens of MB costs its zero fill and page faults on the one serial section of the replay
-            K* kbuf = nullptr;
-            uint8_t* abuf = nullptr;
-            if (staging_) staging_(off[nc], &kbuf, &abuf);
-            else { keys_.resize(off[nc]); ans_.resize(off[nc]); kbuf = keys_.data(); abuf = ans_.data(); }
-            HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
-                const std::vector<K>& lk = rp[i]->log_keys();
-                if (!lk.empty()) memcpy(kbuf + off[i], lk.data(), lk.size() * sizeof(K));
-            });
-            if (off[nc]) { probe_(kbuf, off[nc], abuf); cnt.probe_batches++; cnt.prefetched_queries += off[nc]; }
-            HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
-                rp[i]->apply(cut[c0 + i], cut[c0 + i + 1], feat, rep, interest, abuf + off[i]);
-            });
-            // merge in reference order: the id bases of the chunks are a prefix sum, so the renumbered texts of all chunks are
-            // produced in parallel and only concatenated here (30 k snprintf + appends were 3 ms of the replay's serial section)
-            {
-                std::vector<uint64_t> base(nc + 1, next_id - 1);
-                for (size_t i = 0; i < nc; i++) base[i + 1] = base[i] + (rp[i]->next_id - 1);
-                std::vector<std::string> bk(nc), vc(nc);
+            if (final_stage) cut.push_back(npos);
+            ms_cut += pc.lap();
+            // batches of chunks
+            while (done_chunks + 1 < cut.size()) {
+                Batch b;
+                b.c0 = done_chunks;
+                b.c1 = b.c0 + 1;
+                while (b.c1 + 1 < cut.size() && cut[b.c1 + 1] - cut[b.c0] <= segment_positions) b.c1++;
+                done_chunks = b.c1;
+                const size_t nc = b.c1 - b.c0, c0 = b.c0;
+                nb_chunks += nc;
+                b.rp.resize(nc);
+                b.off.assign(nc + 1, 0);
                 HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
-                    append_renumbered(bk[i], rp[i]->bkpt_out, rp[i]->bk_ids, base[i]);
-                    append_renumbered(vc[i], rp[i]->vcf_out, rp[i]->vcf_ids, base[i]);
+                    b.rp[i].reset(new Replayer<K>(opt_, locked_probe_));
+                    Replayer<K>& r = *b.rp[i];
+                    r.skip_min = skip_min;
+                    const size_t s = cut[c0 + i];
+                    if (s == 0) r.begin_sequence(name, seq, len); else r.begin_steady(name, seq, len, s, w, feat, rep);
+                    r.collect(s, cut[c0 + i + 1], feat, rep, interest);
                 });
-                size_t nb = bkpt_out.size(), nv = vcf_out.size();
-                for (size_t i = 0; i < nc; i++) { nb += bk[i].size(); nv += vc[i].size(); }
-                bkpt_out.reserve(nb); vcf_out.reserve(nv);
-                for (size_t i = 0; i < nc; i++) { bkpt_out += bk[i]; vcf_out += vc[i]; merge_counters(*rp[i]); }
+                ms_collect += pc.lap();
+                for (size_t i = 0; i < nc; i++) b.off[i + 1] = b.off[i] + b.rp[i]->log_keys().size();
+                // staging of the batch's probe keys / answers: the caller's (pinned, reused across finds) buffers when it provides them --
+                // a fresh std::vector of tens of MB costs its zero fill and page faults. Two slots: the previous batch still reads its answers.
+                const int slot = (int)(nbatches_++ & 1);
+                if (staging_) staging_(b.off[nc], slot, &b.kbuf, &b.abuf);
+                else { keys_[slot].resize(b.off[nc]); ans_[slot].resize(b.off[nc]); b.kbuf = keys_[slot].data(); b.abuf = ans_[slot].data(); }
+                HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
+                    const std::vector<K>& lk = b.rp[i]->log_keys();
+                    if (!lk.empty()) memcpy(b.kbuf + b.off[i], lk.data(), lk.size() * sizeof(K));
+                });
+                ms_stage += pc.lap();
+                if (b.off[nc]) {
+                    cnt.probe_batches++; cnt.prefetched_queries += b.off[nc];
+                    K* kb = b.kbuf; uint8_t* ab = b.abuf; const size_t n = b.off[nc];
+                    std::exception_ptr* err = &b.error;
+                    // (locked: unforeseen queries of the batch being applied share the probe function, its stream and its buffers)
+                    b.probe = std::thread([this, kb, ab, n, err] { try { locked_probe_(kb, n, ab); } catch (...) { *err = std::current_exception(); } });
+                }
+                try { finish_batch(prev, cut, feat, rep, interest, nt, pc); }   // overlaps the probe of b
+                catch (...) { if (b.probe.joinable()) b.probe.join(); throw; }
+                prev = std::move(b);
             }
-            c0 = c1;
         }
+        finish_batch(prev, cut, feat, rep, interest, nt, pc);
     }
 
     // -bed: intervals are short and their replay is sequential by construction (every interval start clears the state)
@@ -930,6 +945,52 @@ public:
     }
 
 private:
+    struct Batch {
+        size_t c0 = 0, c1 = 0;
+        std::vector<std::unique_ptr<Replayer<K>>> rp;
+        std::vector<size_t> off;
+        K* kbuf = nullptr;
+        uint8_t* abuf = nullptr;
+        std::thread probe;
+        std::exception_ptr error;
+    };
+    // real pass + merge of a batch whose probe was launched earlier
+    void finish_batch(Batch& b, const std::vector<size_t>& cut, const uint8_t* feat, const uint8_t* rep, const uint32_t* interest, int nt, PhaseClock& pc) {
+        const size_t nc = b.c1 - b.c0, c0 = b.c0;
+        if (!nc) return;
+        if (b.probe.joinable()) b.probe.join();
+        if (b.error) { std::exception_ptr e = b.error; b = Batch(); std::rethrow_exception(e); }
+        ms_probe += pc.lap();
+        HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
+            b.rp[i]->apply(cut[c0 + i], cut[c0 + i + 1], feat, rep, interest, b.abuf + b.off[i]);
+        });
+        ms_apply += pc.lap();
+        // merge in reference order: the id bases of the chunks are a prefix sum, so the renumbered texts of all chunks are
+        // produced in parallel and only concatenated here (30 k snprintf + appends were 3 ms of the replay's serial section);
+        // the chunks' replayers (logs of tens of MB in total) are freed on the pool as well
+        {
+            std::vector<uint64_t> base(nc + 1, next_id - 1);
+            for (size_t i = 0; i < nc; i++) base[i + 1] = base[i] + (b.rp[i]->next_id - 1);
+            std::vector<std::string> bk(nc), vc(nc);
+            HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
+                append_renumbered(bk[i], b.rp[i]->bkpt_out, b.rp[i]->bk_ids, base[i]);
+                append_renumbered(vc[i], b.rp[i]->vcf_out, b.rp[i]->vcf_ids, base[i]);
+            });
+            for (size_t i = 0; i < nc; i++) merge_counters(*b.rp[i]);
+            std::vector<size_t> ob(nc + 1, bkpt_out.size()), ov(nc + 1, vcf_out.size());
+            for (size_t i = 0; i < nc; i++) { ob[i + 1] = ob[i] + bk[i].size(); ov[i + 1] = ov[i] + vc[i].size(); }
+            bkpt_out.resize(ob[nc]); vcf_out.resize(ov[nc]);
+            char* pb = &bkpt_out[0];
+            char* pv = &vcf_out[0];
+            HostPool::instance().parallel_for(nc, nt, [&](size_t i) {
+                if (!bk[i].empty()) memcpy(pb + ob[i], bk[i].data(), bk[i].size());
+                if (!vc[i].empty()) memcpy(pv + ov[i], vc[i].data(), vc[i].size());
+                b.rp[i].reset();
+            });
+        }
+        b = Batch();
+        ms_merge += pc.lap();
+    }
     static void append_renumbered(std::string& dst, const std::string& src, const std::vector<typename Replayer<K>::IdPatch>& ids, uint64_t base) {
         if (base == 0) { dst += src; return; }
         size_t at = 0;
@@ -960,9 +1021,10 @@ private:
     ProbeFn<K> probe_, locked_probe_;
     std::mutex probe_mu_;
     int nthreads_;
-    std::vector<K> keys_;
-    std::vector<uint8_t> ans_;
-    std::function<void(size_t, K**, uint8_t**)> staging_;
+    std::vector<K> keys_[2];
+    std::vector<uint8_t> ans_[2];
+    uint64_t nbatches_ = 0;
+    std::function<void(size_t, int, K**, uint8_t**)> staging_;
 };
 
 }  // namespace mtg

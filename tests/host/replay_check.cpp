@@ -23,6 +23,7 @@ template <class K> static int run(int argc, char** argv) {
     std::string dump, load, bed;
     int threads = 1, repeat = 1;
     size_t chunk = 0;
+    int stages = 0;
     unsigned flags = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -43,6 +44,7 @@ template <class K> static int run(int argc, char** argv) {
         else if (a == "-threads") threads = atoi(val().c_str());
         else if (a == "-repeat") repeat = atoi(val().c_str());
         else if (a == "-chunk") chunk = (size_t)atoll(val().c_str());
+        else if (a == "-stages") stages = atoi(val().c_str());   // features "arrive" in this many stages (staged / pipelined scan)
         else if (a == "-bed") bed = val();   // product bed parser + bed-restricted replay
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
     }
@@ -136,11 +138,19 @@ template <class K> static int run(int argc, char** argv) {
                 }
             }
             const double t0 = now();
-            if (bed.empty()) rp.scan(rec.name, rec.seq.data(), rec.seq.size(), feat.data(), rep.data(), use_interest ? interest.data() : nullptr);
+            if (bed.empty() && stages > 1) {
+                std::vector<size_t> avail;
+                for (int s2 = 1; s2 < stages; s2++) avail.push_back(npos * s2 / stages / 32 * 32);
+                avail.push_back(npos);
+                size_t waited = 0;
+                rp.scan(rec.name, rec.seq.data(), rec.seq.size(), feat.data(), rep.data(), use_interest ? interest.data() : nullptr, &avail,
+                        [&](size_t st) { if (st != waited++) { fprintf(stderr, "stages out of order\n"); exit(3); } });
+            } else if (bed.empty()) rp.scan(rec.name, rec.seq.data(), rec.seq.size(), feat.data(), rep.data(), use_interest ? interest.data() : nullptr);
             else rp.scan_bed(rec.name, rec.seq.data(), rec.seq.size(), feat.data(), rep.data(), mtg::bed_intervals(mtg::read_text_file(bed), rec.name, k));
             scan_ms += now() - t0;
         }
         bk_text = rp.bkpt_out; vcf_text = rp.vcf_out; cnt = rp.cnt; nchunks = rp.nb_chunks;
+        if (it == repeat - 1) fprintf(stderr, "[replay_check] phases: wait %.2f cut %.2f collect %.2f stage %.2f probe %.2f apply %.2f merge %.2f ms\n", rp.ms_wait, rp.ms_cut, rp.ms_collect, rp.ms_stage, rp.ms_probe, rp.ms_apply, rp.ms_merge);
     }
     if (!dump.empty()) {
         FILE* f = fopen((dump + ".memo").c_str(), "wb");
