@@ -458,12 +458,15 @@ def own_arm(args):
     kernels = [
         {"kernel": "count stage (pack+superkmer+group+scatter+count+filter)", "ms": count_stage_ms, "bytes": bpk * nk, "bound": H,
          "note": "SURVEY 8d stage figure: 2*sizeof(kmer)+0.25 B per read k-mer instance (the stage, not one kernel)"},
-        {"kernel": "count_kernel", "ms": avg["count.ms_count"], "bytes": ksz * nk + 8.0 * avg["count.nb_records"], "bound": H,
-         "note": "sizeof(kmer) per k-mer instance read from the partition + the 8-byte super-k-mer records"},
+        {"kernel": "count_kernel_dd" if K <= 31 else "count_kernel", "ms": avg["count.ms_count"], "bytes": ksz * nk + 8.0 * avg["count.nb_records"], "bound": H,
+         "note": "sizeof(kmer) per k-mer instance read from the partition + the 8-byte super-k-mer records (SURVEY 8d's per-unit figure; "
+                 "k <= 31: the de-duplicating kernel streams 32-byte records that carry their bases, identical super-k-mers are folded "
+                 "before expansion)"},
         {"kernel": "superkmer_kernel", "ms": avg["count.ms_extract"], "bytes": 0.375 * nbytes + 8.0 * avg["count.nb_records"], "bound": H,
          "note": "packed bases + invalid mask in, 8-byte records out"},
-        {"kernel": "scatter_kernel", "ms": avg["count.ms_scatter"], "bytes": 16.0 * avg["count.nb_records"], "bound": H,
-         "note": "8-byte records read and written once"},
+        {"kernel": "scatter_kernel", "ms": avg["count.ms_scatter"], "bytes": (40.0 if K <= 31 else 16.0) * avg["count.nb_records"], "bound": H,
+         "note": "8-byte records read; written once with their bases (one 32-byte sector per record) for k <= 31, as 8-byte records else; "
+                 "the kernel is bound by one L2 atomic per record, not by these bytes"},
         {"kernel": "pack_kernel", "ms": avg["count.ms_pack"], "bytes": 1.375 * nbytes, "bound": H, "note": "ASCII in, 2-bit words + mask out"},
         {"kernel": "filter_kernel", "ms": avg["count.ms_filter"], "bytes": (ksz + 4.0) * (avg["count.nb_candidates"] + nsolid), "bound": H,
          "note": "candidates read, solid set written"},

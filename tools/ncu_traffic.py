@@ -23,7 +23,9 @@ for r in rows[2:]:
         best[name] = (b, t)
 out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
 d = json.load(open(out)) if os.path.exists(out) else {}
-d[key] = {k: v[0] for k, v in best.items()}
+d.setdefault(key, {}).update({k: v[0] for k, v in best.items()})   # kernels absent from this report keep their earlier capture
+if "count_kernel_dd" in best:
+    d[key].pop("count_kernel", None)   # k <= 31 runs the de-duplicating kernel
 d[key]["_source"] = os.path.basename(rep)
 json.dump(d, open(out, "w"), indent=1, sort_keys=True)
 print(json.dumps(d[key], indent=1))
