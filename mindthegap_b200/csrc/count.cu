@@ -664,8 +664,9 @@ count_kernel_dd(const uint64_t* __restrict__ packed, const uint64_t* __restrict_
     uint32_t* cnt = reinterpret_cast<uint32_t*>(keys + S);
     uint32_t* dw = cnt + S;
     uint32_t* hist_s = dw + DD_SLOTS;
-    uint16_t* dpfx = reinterpret_cast<uint16_t*>(hist_s + SMEM_HIST);   // DD_SLOTS + 1 exclusive prefix sums of the entries' lengths (<= 30 720)
-    __shared__ uint32_t s_item, s_overflow, s_sp, s_dcount, s_pending;
+    uint16_t* dpfx = reinterpret_cast<uint16_t*>(hist_s + SMEM_HIST);   // per non-empty entry: exclusive prefix sum of the lengths (<= 30 720)
+    uint16_t* didx = dpfx + DD_SLOTS + 2;                               // per non-empty entry: its slot
+    __shared__ uint32_t s_item, s_overflow, s_sp, s_dcount, s_pending, s_nent, s_ninst;
     __shared__ uint32_t s_wsum[COUNT_THREADS / 32];
     __shared__ unsigned long long s_cbase;
     __shared__ uint32_t s_stack[CK_STACK];
@@ -710,65 +711,75 @@ count_kernel_dd(const uint64_t* __restrict__ packed, const uint64_t* __restrict_
                     pending[q] = !last && i < nrec;
                     key[q] = pending[q] ? dd_key(packed, fat, grouped, rec_off + i, k) : DEMPTY;
                 }
+                uint32_t nnew = 0, nleft = 0;
 #pragma unroll
                 for (int q = 0; q < DD_PER; q++) {
                     if (!pending[q]) continue;
                     uint32_t slot = key_hash32(key[q]) & (DD_SLOTS - 1);
                     for (int probes = 0; probes < DD_MAXPROBE; probes++) {
                         const u128 c = cas_shared(&dkeys[slot], DEMPTY, key[q]);
-                        if (c == DEMPTY) { atomicAdd(&s_dcount, 1u); atomicAdd(&dw[slot], 1u); pending[q] = false; break; }
+                        if (c == DEMPTY) { nnew++; atomicAdd(&dw[slot], 1u); pending[q] = false; break; }
                         if (c == key[q]) { atomicAdd(&dw[slot], 1u); pending[q] = false; break; }
                         slot = (slot + 1) & (DD_SLOTS - 1);
                     }
-                    if (pending[q]) atomicAdd(&s_pending, 1u);   // no room within the probe limit: retried after the flush
+                    if (pending[q]) nleft++;   // no room within the probe limit: retried after the flush
+                }
+                {   // one shared-memory atomic per warp for the entry count (a per-entry atomic on one address serialises the lanes)
+                    const uint32_t both = __reduce_add_sync(0xFFFFFFFFu, nnew | (nleft << 16));
+                    if (lane == 0 && both) { if (both & 0xFFFFu) atomicAdd(&s_dcount, both & 0xFFFFu); if (both >> 16) atomicAdd(&s_pending, both >> 16); }
                 }
                 __syncthreads();
                 const uint32_t npend = s_pending;
                 if (last || npend != 0 || s_dcount > DD_CAP) {
                     // ---- expansion, balanced: prefix sum of the entries' lengths in slot order, every thread takes an equal share of
                     // consecutive k-mer instances (binary search for its first entry, then the k-mers roll through two registers)
+                    // The non-empty entries are listed in slot order (didx) with the prefix sums of their lengths (dpfx): one scan of
+                    // (count << 16 | length) per thread's two slots.
                     {
-                        uint32_t l0 = 0, l1 = 0;
+                        uint32_t l0 = 0, l1 = 0, f0 = 0, f1 = 0;
                         const u128 e0 = dkeys[2 * tid], e1 = dkeys[2 * tid + 1];
-                        if (!(e0 == DEMPTY)) l0 = (uint32_t)(e0.lo & 63) + 1;
-                        if (!(e1 == DEMPTY)) l1 = (uint32_t)(e1.lo & 63) + 1;
-                        uint32_t incl = l0 + l1;
+                        if (!(e0 == DEMPTY)) { l0 = (uint32_t)(e0.lo & 63) + 1; f0 = 1; }
+                        if (!(e1 == DEMPTY)) { l1 = (uint32_t)(e1.lo & 63) + 1; f1 = 1; }
+                        const uint32_t mine = (l0 + l1) | ((f0 + f1) << 16);   // lengths sum to <= 30 720 < 2^16
+                        uint32_t incl = mine;
                         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
                         if (lane == 31) s_wsum[warp] = incl;
                         __syncthreads();
                         uint32_t wbase = 0;
                         for (int w = 0; w < warp; w++) wbase += s_wsum[w];
-                        const uint32_t excl = wbase + incl - (l0 + l1);
-                        dpfx[2 * tid] = (uint16_t)excl;
-                        dpfx[2 * tid + 1] = (uint16_t)(excl + l0);
-                        if (tid == COUNT_THREADS - 1) dpfx[DD_SLOTS] = (uint16_t)(excl + l0 + l1);
+                        const uint32_t excl = wbase + incl - mine;
+                        uint32_t ei = excl >> 16, el = excl & 0xFFFFu;
+                        if (f0) { didx[ei] = (uint16_t)(2 * tid); dpfx[ei] = (uint16_t)el; ei++; el += l0; }
+                        if (f1) { didx[ei] = (uint16_t)(2 * tid + 1); dpfx[ei] = (uint16_t)el; }
+                        if (tid == COUNT_THREADS - 1) { const uint32_t tot = excl + mine; s_nent = tot >> 16; s_ninst = tot & 0xFFFFu; }
                         __syncthreads();
                     }
                     {
                         // ONE flat loop of `per` steps for every thread (a nest of per-entry loops left the lanes of a warp at different
                         // nesting points: ncu showed the insert body executed ~12x more often than converged lanes would need)
-                        const uint32_t T = dpfx[DD_SLOTS];
+                        const uint32_t T = s_ninst, E = s_nent;
                         const uint32_t per = (T + COUNT_THREADS - 1) / COUNT_THREADS;
                         const uint32_t i0 = tid * per;
                         const uint32_t nmine = i0 < T ? min(per, T - i0) : 0u;
-                        uint32_t sl = 0, j = 0, len = 0, w = 0;
+                        uint32_t en = 0, j = 0, len = 0, w = 0;
                         uint64_t x0 = 0, x1 = 0;
                         if (nmine) {
-                            uint32_t lo_s = 0, hi_s = DD_SLOTS;   // last slot with dpfx[slot] <= i0; it is non-empty when it holds instance i0
+                            uint32_t lo_s = 0, hi_s = E;   // last entry with dpfx[entry] <= i0: the one that holds instance i0
                             while (hi_s - lo_s > 1) { const uint32_t mid = (lo_s + hi_s) >> 1; if (dpfx[mid] <= i0) lo_s = mid; else hi_s = mid; }
-                            sl = lo_s;
+                            en = lo_s;
+                            const uint32_t sl = didx[en];
                             const u128 e = dkeys[sl];
                             len = (uint32_t)(e.lo & 63) + 1;
                             w = dw[sl];
-                            j = i0 - dpfx[sl];
+                            j = i0 - dpfx[en];
                             x0 = e.hi; x1 = e.lo & ~0xFFull;
                             if (j) { x0 = (x0 << (2 * j)) | (x1 >> (64 - 2 * j)); x1 <<= 2 * j; }
                         }
                         for (uint32_t n = 0; n < per; n++) {
                             if (n >= nmine) continue;
-                            if (j == len) {   // next non-empty entry
-                                u128 e;
-                                do { sl++; e = dkeys[sl]; } while (e == DEMPTY);
+                            if (j == len) {   // next entry
+                                const uint32_t sl = didx[++en];
+                                const u128 e = dkeys[sl];
                                 len = (uint32_t)(e.lo & 63) + 1;
                                 w = dw[sl];
                                 j = 0;
@@ -864,7 +875,7 @@ count_kernel_dd(const uint64_t* __restrict__ packed, const uint64_t* __restrict_
     __syncthreads();
     if (tid < SMEM_HIST && hist_s[tid]) atomicAdd(&histo[tid], (unsigned long long)hist_s[tid]);
 }
-static const int DD_SMEM = (int)(sizeof(u128) * DD_SLOTS + (sizeof(uint64_t) + 4) * DD_S + 4 * DD_SLOTS + 4 * SMEM_HIST + 2 * (DD_SLOTS + 2));
+static const int DD_SMEM = (int)(sizeof(u128) * DD_SLOTS + (sizeof(uint64_t) + 4) * DD_S + 4 * DD_SLOTS + 4 * SMEM_HIST + 2 * (DD_SLOTS + 2) + 2 * DD_SLOTS);
 
 // candidates -> solid set at the final threshold. A block compacts tiles of 1024 candidates: per-warp ballots, one shared-memory
 // scan, ONE global reservation per tile (a reservation per warp on the single counter serialises in L2).
