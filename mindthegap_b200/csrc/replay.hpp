@@ -898,6 +898,27 @@ public:
                 done_chunks = b.c1;
                 const size_t nc = b.c1 - b.c0, c0 = b.c0;
                 nb_chunks += nc;
+                if (nc == 1 && cut[c0 + 1] - cut[c0] > segment_positions) {
+                    // a chunk without a steady point (no interest bitmap, or no run of uninteresting positions: an uncovered region)
+                    // cannot be split across threads; its probe log is still bounded: collect / probe / apply per segment
+                    finish_batch(prev, cut, feat, rep, interest, nt, pc);
+                    Replayer<K> r(opt_, locked_probe_);
+                    r.skip_min = skip_min;
+                    const size_t s = cut[c0], e = cut[c0 + 1];
+                    if (s == 0) r.begin_sequence(name, seq, len); else r.begin_steady(name, seq, len, s, w, feat, rep);
+                    std::vector<uint8_t> ans;
+                    for (size_t p0 = s; p0 < e; p0 += segment_positions) {
+                        const size_t p1 = std::min(e, p0 + segment_positions);
+                        r.collect(p0, p1, feat, rep, interest);
+                        const std::vector<K>& lk = r.log_keys();
+                        ans.resize(lk.size());
+                        if (!lk.empty()) { locked_probe_(lk.data(), lk.size(), ans.data()); cnt.probe_batches++; cnt.prefetched_queries += lk.size(); }
+                        r.apply(p0, p1, feat, rep, interest, ans.data());
+                    }
+                    merge(r);
+                    ms_apply += pc.lap();
+                    continue;
+                }
                 b.rp.resize(nc);
                 b.off.assign(nc + 1, 0);
                 HostPool::instance().parallel_for(nc, nt, [&](size_t i) {

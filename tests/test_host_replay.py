@@ -40,6 +40,8 @@ MODES = {"default": [], "tiny_segments": ["-seg", "777", "-skip-min", "1"], "wal
          # chunked replay: cut at every steady point at least 64 positions after the previous cut, 4 host threads
          "parallel_chunks": ["-chunk", "64", "-threads", "4"], "parallel_chunks_1thread": ["-chunk", "1000", "-threads", "1", "-skip-min", "8"],
          # features arriving in stages: the replay of a stage starts before the next has arrived, batch probes run beside the pool
+         # one chunk without steady points (no bitmap): its probe log is bounded per segment
+         "walk_everything_small_segments": ["-no-interest", "-seg", "777", "-threads", "2"],
          "staged": ["-chunk", "64", "-threads", "4", "-stages", "3"], "staged_small_batches": ["-chunk", "64", "-threads", "3", "-stages", "5", "-seg", "500"]}
 
 
