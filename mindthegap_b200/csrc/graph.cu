@@ -983,12 +983,28 @@ public:
 
     void build(const void* d_solid, uint64_t N) override {
         build_base(d_solid, N);
-        // the neighbour search walks the k-mers in TABLE order: a k-mer, its neighbours and the next k-mers share their region
-        compact_range(0, nbuckets_, N);
-        critical(ordered_.p, N);
-        ordered_.release();
-        build_rest(d_solid, N);
+        // BooPHF needs nothing but the keys: its device levels (random sector RMWs) are queued on a side stream and run under the
+        // critical-FP search, a latency-bound kernel that leaves issue slots and DRAM bandwidth free (MTG_MPHF_SERIAL=1: after it)
+        const char* ser = getenv("MTG_MPHF_SERIAL");
+        mphf_overlapped_ = N && !(ser && *ser == '1');
+        if (mphf_overlapped_) {
+            side_stream();
+            MTG_CUDA(cudaEventRecord(side_ev_, stream_));
+            MTG_CUDA(cudaStreamWaitEvent(side_, side_ev_, 0));
+            mphf_launch((const K*)d_solid, N, side_);
+        }
+        try {
+            // the neighbour search walks the k-mers in TABLE order: a k-mer, its neighbours and the next k-mers share their region
+            compact_range(0, nbuckets_, N);
+            critical(ordered_.p, N);
+            ordered_.release();
+            build_rest(d_solid, N);
+        } catch (...) {
+            if (mphf_overlapped_) { cudaStreamSynchronize(side_); mphf_overlapped_ = false; }
+            throw;
+        }
     }
+    bool mphf_overlapped_ = false;
 
     // table + main Bloom from the full solid set
     void build_base(const void* d_solid, uint64_t N) override {
@@ -996,6 +1012,32 @@ public:
         EvTimer t(stream_);
         Trace tr(stream_);
         st_.nb_solid = N;
+        // ---- main Bloom (BloomAlgorithm.cpp:161-165: u64 * float multiply). It needs nothing but the keys: queued on the side
+        // stream, its L2 atomics run under the table build, which waits on CAS round trips (MTG_BLOOM_SERIAL=1: after the table)
+        const char* ser = getenv("MTG_BLOOM_SERIAL");
+        const bool side_bloom = N && !(ser && *ser == '1');
+        EvTimer tb(side_bloom ? side_stream() : stream_);
+        auto bloom_build = [&](cudaStream_t s) {
+            const float NBITS = bits_per_kmer(k_);
+            uint64_t est = (uint64_t)(N * NBITS);
+            const int nbHash = (int)floorf(0.7 * NBITS);
+            if (est == 0) est = 1000;
+            bloom_.init(est, nbHash, s);
+            if (N) {
+                GraphView<K> g = view();
+                bloom_neighbor_insert_kernel<K><<<grid_for(N), 256, 0, s>>>(keys, N, g, bloom_.bits.p);
+                MTG_CUDA(cudaGetLastError());
+                st_.launches++;
+            }
+            st_.bloom_tai = bloom_.tai;
+        };
+        if (side_bloom) {
+            MTG_CUDA(cudaEventRecord(side_ev_, stream_));
+            MTG_CUDA(cudaStreamWaitEvent(side_, side_ev_, 0));
+            tb.start();
+            bloom_build(side_);
+            cudaEventRecord(tb.b, side_);
+        }
         // ---- exact table, load factor ~0.55, 128-byte buckets
         t.start();
         set_geometry(N);
@@ -1012,22 +1054,22 @@ public:
         check_err("exact table build");
         st_.nbuckets = nbuckets_;
         tr.mark("graph: table");
-        // ---- main Bloom (BloomAlgorithm.cpp:161-165: u64 * float multiply)
-        t.start();
-        const float NBITS = bits_per_kmer(k_);
-        uint64_t est = (uint64_t)(N * NBITS);
-        const int nbHash = (int)floorf(0.7 * NBITS);
-        if (est == 0) est = 1000;
-        bloom_.init(est, nbHash, stream_);
-        if (N) {
-            GraphView<K> g = view();
-            bloom_neighbor_insert_kernel<K><<<grid_for(N), 256, 0, stream_>>>(keys, N, g, bloom_.bits.p);
-            MTG_CUDA(cudaGetLastError());
-            st_.launches++;
+        if (side_bloom) {
+            MTG_CUDA(cudaStreamWaitEvent(stream_, tb.b, 0));   // everything that follows on the main stream sees the Bloom
+            MTG_CUDA(cudaEventSynchronize(tb.b));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, tb.a, tb.b);
+            st_.ms_bloom = ms;
+        } else {
+            t.start();
+            bloom_build(stream_);
+            st_.ms_bloom = t.stop();
         }
-        st_.ms_bloom = t.stop();
-        st_.bloom_tai = bloom_.tai;
         tr.mark("graph: bloom");
+    }
+    cudaStream_t side_stream() {
+        if (!side_) { MTG_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking)); MTG_CUDA(cudaEventCreateWithFlags(&side_ev_, cudaEventDisableTiming)); }
+        return side_;
     }
 
     // critical false positives among the neighbours of `keys` (any share of the solid set), de-duplicated within the share
@@ -1152,7 +1194,8 @@ public:
         st_.b2_tai = b2_.tai;
         tr.mark("graph: cascade"); st_.b3_tai = b3_.tai; st_.b4_tai = b4_.tai; st_.ncfp = ncfp_;
         t.start();
-        build_mphf(keys, N);
+        if (mphf_overlapped_) { mphf_complete(side_); mphf_overlapped_ = false; }   // what is left of it (ms_mphf = the exposed part)
+        else build_mphf(keys, N);
         st_.ms_mphf = t.stop();
         tr.mark("graph: mphf");
     }
