@@ -479,7 +479,9 @@ def own_arm(args):
         {"kernel": "cascade (bloom_cache_insert/bloom_cascade/cfp_set kernels)", "ms": avg["graph.ms_cascade"],
          "bytes": (2 * ksz + 3 * 32.0) * nsolid, "bound": G, "note": "solid set read twice, ~3 Bloom sectors per k-mer"},
         {"kernel": "mphf_level/clear/compact kernels", "ms": avg["graph.ms_mphf"], "bytes": 1.39 * (2 * ksz + 64.0) * nsolid, "bound": G,
-         "note": "surviving keys (sum over levels 1.39 N) read twice, one 32-B sector RMW + one sector read each"},
+         "note": "surviving keys (sum over levels 1.39 N) read twice, one 32-B sector RMW + one sector read each; on one GPU these kernels "
+                 "run on a side stream under critical_kernel (ms = their own duration there; stage_ms graph.ms_mphf_exposed = what the step "
+                 "still waits for)"},
         {"kernel": "features_kernel (probe)", "ms": avg["scan.ms_features"], "bytes": 128.0 * probes, "bound": G,
          "note": "128 B x exact-table probes actually issued (one per valid position thanks to the adjacency byte; SURVEY 8d counts R + 8 R_solid)"},
     ]

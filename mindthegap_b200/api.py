@@ -380,8 +380,8 @@ class Finder:
         return h
 
     def stats(self):
-        v = np.zeros(64, dtype=np.float64)
-        n = self.L.mtg_get_stats(self.ctx, v, 64)
+        v = np.zeros(128, dtype=np.float64)
+        n = self.L.mtg_get_stats(self.ctx, v, 128)
         return {self.L.mtg_stat_name(i).decode(): float(v[i]) for i in range(n)}
 
     def export_solid(self):

@@ -626,7 +626,7 @@ static const char* STAT_NAMES[] = {
     "count.nb_candidates", "count.nb_solid", "count.ms_pack", "count.ms_extract", "count.ms_group", "count.ms_scatter", "count.ms_count",
     "count.ms_filter", "count.launches", "count.retries",
     "graph.nbuckets", "graph.bloom_bits", "graph.nb_critical", "graph.bloom2_bits", "graph.bloom3_bits", "graph.bloom4_bits", "graph.cfp_set",
-    "graph.ms_table", "graph.ms_bloom", "graph.ms_critical", "graph.ms_cascade", "graph.ms_mphf", "graph.ms_build_total", "graph.launches",
+    "graph.ms_table", "graph.ms_bloom", "graph.ms_critical", "graph.ms_cascade", "graph.ms_mphf", "graph.ms_mphf_exposed", "graph.ms_build_total", "graph.launches",
     "ref.nb_repeated", "ref.bloom_bits",
     "scan.positions", "scan.valid", "scan.in_graph", "scan.table_probes", "scan.bloom_emulations", "scan.ms_features", "scan.ms_replay",
     "scan.observer_queries", "scan.probe_batches", "scan.prefetched_queries", "scan.unforeseen_queries",
@@ -651,7 +651,7 @@ int mtg_get_stats(mtg_ctx* ctx, double* out, int cap) {
                   (double)c.nb_multipass_groups, (double)c.nb_candidates, (double)c.nb_solid, c.ms_pack, c.ms_extract, c.ms_group, c.ms_scatter,
                   c.ms_count, c.ms_filter, (double)c.launches, (double)c.nb_count_retries,
                   (double)g.nbuckets, (double)g.bloom_tai, (double)g.nb_critical, (double)g.b2_tai, (double)g.b3_tai, (double)g.b4_tai, (double)g.ncfp,
-                  g.ms_table, g.ms_bloom, g.ms_critical, g.ms_cascade, g.ms_mphf, ctx->ms_graph_build, (double)g.launches,
+                  g.ms_table, g.ms_bloom, g.ms_critical, g.ms_cascade, g.ms_mphf, g.ms_mphf_exposed, ctx->ms_graph_build, (double)g.launches,
                   (double)g.ref_repeated, (double)g.ref_tai,
                   (double)ctx->scan_positions, (double)ctx->scan_valid, (double)ctx->scan_in_graph, (double)ctx->scan_table_probes,
                   (double)ctx->scan_fallback, ctx->ms_features, ctx->ms_replay, (double)oq, (double)pb, (double)rc.prefetched_queries,

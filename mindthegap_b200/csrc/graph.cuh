@@ -347,6 +347,7 @@ struct GraphStats {
     uint64_t nb_solid = 0, nbuckets = 0, bloom_tai = 0, nb_critical = 0, b2_tai = 0, b3_tai = 0, b4_tai = 0, ncfp = 0;
     uint64_t ref_repeated = 0, ref_tai = 0, mphf_words = 0;
     float ms_table = 0, ms_bloom = 0, ms_critical = 0, ms_cascade = 0, ms_mphf = 0;
+    float ms_mphf_exposed = 0;   // the part of ms_mphf that did not run under the critical-FP search (single-GPU build)
     uint64_t launches = 0;
 };
 
