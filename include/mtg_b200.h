@@ -178,7 +178,8 @@ uint64_t mtg_get_nb_solid(mtg_ctx* ctx);     /* "nb_solid_kmers"                
 int mtg_get_histogram(mtg_ctx* ctx, uint64_t* out10001);
 /* stats: see mtg_stat_name(i); returns the number of values written (<= cap; 64 names today, pass cap >= 128).
  * "*.ms_*" are milliseconds: kernels by CUDA events on the context's stream, host phases by the wall clock. graph.ms_mphf is the
- * BooPHF construction's own duration (on one GPU its device levels run on a side stream under the critical-FP search;
+ * BooPHF construction from first launch to last completion (on one GPU its device levels run on a side stream under the
+ * critical-FP search, which stretches them;
  * graph.ms_mphf_exposed is the part the build still waits for). scan.ms_replay includes waiting for the staged features;
  * scan.ms_replay_{collect,probe,apply,merge} are the calling thread's phases of it. */
 int mtg_get_stats(mtg_ctx* ctx, double* out, int cap);

@@ -995,6 +995,7 @@ public:
             if (!mphf_ev_a_) { MTG_CUDA(cudaEventCreate(&mphf_ev_a_)); MTG_CUDA(cudaEventCreate(&mphf_ev_b_)); }
             MTG_CUDA(cudaEventRecord(mphf_ev_a_, side_));
             mphf_launch((const K*)d_solid, N, side_);
+            MTG_CUDA(cudaEventRecord(mphf_ev_b_, side_));   // end of the device levels
         }
         try {
             // the neighbour search walks the k-mers in TABLE order: a k-mer, its neighbours and the next k-mers share their region
@@ -1200,7 +1201,6 @@ public:
         tr.mark("graph: cascade"); st_.b3_tai = b3_.tai; st_.b4_tai = b4_.tai; st_.ncfp = ncfp_;
         t.start();
         if (mphf_overlapped_) {   // what is left of it; ms_mphf = its own duration on the side stream (shared with the critical-FP search)
-            MTG_CUDA(cudaEventRecord(mphf_ev_b_, side_));
             mphf_complete(side_);
             mphf_overlapped_ = false;
             float dev = 0;
