@@ -514,6 +514,9 @@ def own_arm(args):
                 "ms_per_launch": dom["ms"], "algorithmic_bytes_per_launch": dom["bytes"],
                 "note": "integer hashing / probing: the dominant kernel is named with its own algorithmic bytes; kernels[] holds every kernel of "
                         "the step (streaming ones against the HBM copy peak, random-access ones against the measured gather peak)",
+                "frac_above_one": ("the algorithmic probe bytes of this kernel are mostly served from L1/L2 (k-mers are placed by minimizer "
+                                   "bin, the Bloom fits L2): `traffic` holds the DRAM bytes ncu measured for the same launch"
+                                   if dom["frac"] and dom["frac"] > 1.0 else None),
                 "hbm_copy_peak_gbs": hbm, "random_128B_gather_peak_gbs": gather_peak,
                 "count_stage": {"ms": kernels[0]["ms"], "achieved": kernels[0]["achieved_gbs"], "frac": kernels[0]["frac"]},
                 "probe_frac_of_gather_peak": fk["frac"]}
