@@ -1327,9 +1327,11 @@ public:
         const int S = CountCfg<K>::SLOTS;
         // instances per group: the table holds distinct k-mers, so at sequencing coverage a group may carry about as many
         // instances as there are slots; `distinct_hint` (reference counting: every k-mer distinct) halves that
-        // with de-duplication the fixed cost per group (table clear + sweep, barriers) is spread over twice the instances: the table
-        // holds DISTINCT k-mers, ~3 000 of 7 424 slots for 16 384 instances at sequencing coverage
-        const uint32_t group_target = distinct_hint_ ? S / 2 : (dedup_ ? (uint32_t)(getenv("MTG_DD_GROUP") ? atoi(getenv("MTG_DD_GROUP")) : 2 * S) : S);
+        // De-duplicating kernel: groups of 2*S instances would suit the kernel itself (8.1 vs 9.0 ms on cfg3: the table holds DISTINCT
+        // k-mers, ~1 500 of 7 424 slots for 8 192 instances at sequencing coverage), but the solid set leaves this kernel group by
+        // group and the exact-table build that follows lives on that order: 4.9 ms after groups of S, 6.0 / 6.7 / 7.7 / 8.4 ms after
+        // 1.25 / 1.5 / 2 / 2.5 S (the buckets of a group's bins stay in L2 while it is inserted). S wins on the sum; MTG_DD_GROUP overrides.
+        const uint32_t group_target = distinct_hint_ ? S / 2 : (dedup_ && getenv("MTG_DD_GROUP") ? (uint32_t)atoi(getenv("MTG_DD_GROUP")) : S);
         EventTimer t(stream_);
         Trace tr(stream_);
         // ---- grouping of minimizer bins into work items, entirely on the device (no host round trip)

@@ -2,7 +2,7 @@
 V=${V:-r02_sweep}
 VARS=${VARS:-"MTG_COUNT_NOPAYLOAD=0 MTG_COUNT_NOPAYLOAD=1"}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "count or solid or poly" --timeout=300 --timeout-method=thread 2>&1 | tail -3
+[ -n "$NOTEST" ] || timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "count or solid or poly" --timeout=300 --timeout-method=thread 2>&1 | tail -3
 for S in $VARS; do
 T=$(echo $S | tr "=," "__")
 env $(echo $S | tr "," " ") timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --files-steps 0 > gpurun_out/bench_${V}_$T.json 2> gpurun_out/bench_${V}_$T.err; echo rc=$?
