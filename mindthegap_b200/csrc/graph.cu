@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const K* __restrict__ ke
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t mini = kmer_minimizer(keys[i], k, tm);
         if (place_shard(mini, bin_bits, nshards) != shard) { *err = 5; continue; }   // a k-mer routed to the wrong range
-        atomicAdd(&cnt[place_bin(mini, nbps)], 1u);
+        atomicAdd(&cnt[place_bin(mini, nbps, bin_bits)], 1u);
     }
 }
 // pass 2: buckets per bin = ceil(cnt / BIN_KEYS_PER_BUCKET); off[i] = base + exclusive prefix sum, off[nbps] = terminator.

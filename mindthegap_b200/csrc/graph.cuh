@@ -238,11 +238,17 @@ static const int BIN_TARGET_KEYS = 12;       // bins per range = keys / 12 (+1)
 // A minimizer value selects the range (= the GPU that counted it: mini_owner, common.cuh) and, by a hash, the bin inside the range
 MTG_HD uint64_t mini_place_hash(uint32_t mini) { return mix64((uint64_t)mini + 0x632BE59BD9B4E019ULL); }
 MTG_HD uint32_t place_shard(uint32_t mini, int bin_bits, uint32_t nshards) { return nshards > 1 ? mini_owner(mini, bin_bits, nshards) : 0u; }
-MTG_HD uint32_t place_bin(uint32_t mini, uint32_t nbps) { return (uint32_t)(((mini_place_hash(mini) & 0xFFFFFFFFull) * nbps) >> 32); }
+// The count stage's bin id fills the top bits: a count group is a range of consecutive bin ids and the solid set leaves the count
+// kernel group by group, so the k-mers of a group land in one stretch of the table (the build then works inside L2); the hash bits
+// below spread the minimizers of one count bin over the table bins of its stretch.
+MTG_HD uint32_t place_bin(uint32_t mini, uint32_t nbps, int bin_bits) {
+    const uint32_t v = (mini_bin(mini, bin_bits) << (32 - bin_bits)) | ((uint32_t)mini_place_hash(mini) >> bin_bits);
+    return (uint32_t)(((uint64_t)v * nbps) >> 32);
+}
 // the run of buckets of a key's bin and the bucket the key starts at
 struct Chain { uint32_t o0, nb, b; };
 template <class K> MTG_D bool chain_begin(const GraphView<K>& g, K key, uint32_t mini, Chain& c) {
-    const uint32_t idx = place_shard(mini, g.bin_bits, g.nshards) * (g.nbps + 1) + place_bin(mini, g.nbps);
+    const uint32_t idx = place_shard(mini, g.bin_bits, g.nshards) * (g.nbps + 1) + place_bin(mini, g.nbps, g.bin_bits);
     c.o0 = __ldg(g.bin_off + idx);
     c.nb = __ldg(g.bin_off + idx + 1) - c.o0;
     c.b = c.o0 + (uint32_t)(((uint64_t)key_hash32(key) * c.nb) >> 32);
