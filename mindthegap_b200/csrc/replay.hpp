@@ -654,8 +654,10 @@ private:
         }
         if (del_size <= 0) return false;
         size_t start = pos - 2 - del_size;
-        std::string del_seq = raw(start, del_size + 1);
-        write_vcf(start, del_seq, del_seq.substr(0, 1), rep, "DEL");
+        if (!collecting_) {   // (the writers return at once in the collect pass: no need to build their arguments)
+            std::string del_seq = raw(start, del_size + 1);
+            write_vcf(start, del_seq, del_seq.substr(0, 1), rep, "DEL");
+        }
         next_id++;
         if (rep) cnt.fuzzy_deletion++; else cnt.clean_deletion++;
         return true;
@@ -693,7 +695,7 @@ private:
     bool clean_insertion() {  // src/FindInsertion.hpp:46-80
         if (!ends_ok() || !is_clean_gap()) return false;
         if (!ends_connected()) return false;
-        write_breakpoint(chrom, pos - 2, str(begin_fwd), str(end_fwd), 0, "HOM", begin_is_repeated, end_is_repeated);
+        if (!collecting_) write_breakpoint(chrom, pos - 2, str(begin_fwd), str(end_fwd), 0, "HOM", begin_is_repeated, end_is_repeated);
         next_id++; cnt.homo_clean++;
         return true;
     }
@@ -702,13 +704,13 @@ private:
         int rep = k - 1 - (int)gap_stretch;
         uint64_t rp = pos - 1 + rep;
         if (!ends_connected() || !seed_valid(rp)) return false;
-        write_breakpoint(chrom, pos - 2 + rep, str(begin_fwd), raw(rp, k), rep, "HOM", begin_is_repeated, end_is_repeated);
+        if (!collecting_) write_breakpoint(chrom, pos - 2 + rep, str(begin_fwd), raw(rp, k), rep, "HOM", begin_is_repeated, end_is_repeated);
         next_id++; cnt.homo_fuzzy++;
         return true;
     }
     bool backup() {  // src/FindBackup.hpp:46-67
         if (!ends_ok() || !(gap_stretch > (uint64_t)(k / 2))) return false;
-        write_breakpoint(chrom + "_backup", pos - 1, str(begin_fwd), str(end_fwd), 0, "BACKUP");
+        if (!collecting_) write_breakpoint(chrom + "_backup", pos - 1, str(begin_fwd), str(end_fwd), 0, "BACKUP");
         next_id++; cnt.backup++;
         return true;
     }
