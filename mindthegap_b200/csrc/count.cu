@@ -412,9 +412,9 @@ MTG_D void fat_store(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d
     asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 MTG_D void fat_load(const uint64_t* p, uint64_t& a, uint64_t& b, uint64_t& c) {
-    uint64_t d;
+    [[maybe_unused]] uint64_t d;   // the fourth word of the sector is spare
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
-    (void)d;   // the fourth word of the sector is spare
+
 }
 // records -> contiguous per-group lists. fat != null: the record's bases travel with it, one whole 32-byte sector per record written
 // by one store. The records of a batch are in read order, so this kernel reads the packed reads (almost) sequentially and the count
