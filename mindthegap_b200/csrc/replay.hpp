@@ -623,6 +623,7 @@ private:
         std::vector<K>& q = join_q_;
         q.clear();
         K f = b >> (2 * (k - nb));
+        if (nb >= k) q.push_back(f);   // the string starts with a whole k-mer
         for (int i = 0; i < k; i++) {
             f = ((f << 2) | ((e >> (2 * (k - 1 - i))) & K(3))) & mask_;
             if (nb + i + 1 >= k) q.push_back(f);

@@ -20,7 +20,7 @@ template <class K> static int run(int argc, char** argv) {
     std::string amin = "auto";
     size_t seg = (size_t)1 << 22, skip_min = 512;
     bool use_interest = true;
-    std::string dump, load, bed;
+    std::string dump, load, bed, solid_bin;
     int threads = 1, repeat = 1;
     size_t chunk = 0;
     int stages = 0;
@@ -46,6 +46,7 @@ template <class K> static int run(int argc, char** argv) {
         else if (a == "-chunk") chunk = (size_t)atoll(val().c_str());
         else if (a == "-stages") stages = atoi(val().c_str());   // features "arrive" in this many stages (staged / pipelined scan)
         else if (a == "-bed") bed = val();   // product bed parser + bed-restricted replay
+        else if (a == "-solid-bin") solid_bin = val();   // solid set from `oracle/_ref/bin/h5solid dump` (24-byte records) instead of counting -in
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
     }
     o.homo_only = flags & 1; o.homo_insert = flags & 2; o.hete_insert = flags & 4; o.snp = flags & 8; o.backup = flags & 16;
@@ -58,11 +59,23 @@ template <class K> static int run(int argc, char** argv) {
     std::vector<uint64_t> flat_keys; std::vector<uint8_t> flat_vals;
     std::unordered_map<uint64_t, uint8_t> memo;  // -dump / -load: probe answers by k-mer (k <= 31 only)
     if (load.empty()) {
-        if (!load_bank(in, reads)) { fprintf(stderr, "cannot read inputs\n"); return 1; }
-        CountResult<K> cr;
-        count_bank<K>(reads, k, amin == "auto" ? -1 : atoi(amin.c_str()), 2147483647LL, cr);
         std::vector<K> solid;
-        for (auto& kc : cr.solid) solid.push_back(kc.value);
+        if (!solid_bin.empty()) {
+            FILE* f = fopen(solid_bin.c_str(), "rb");
+            if (!f) { fprintf(stderr, "cannot read %s\n", solid_bin.c_str()); return 1; }
+            struct Rec { uint64_t lo, hi; uint32_t ab, part; } r;
+            while (fread(&r, sizeof r, 1, f) == 1) {
+                K v = (K)r.lo;
+                if (sizeof(K) > 8) v |= (K)r.hi << (8 * (sizeof(K) > 8 ? 8 : 0));
+                solid.push_back(v);
+            }
+            fclose(f);
+        } else {
+            if (!load_bank(in, reads)) { fprintf(stderr, "cannot read inputs\n"); return 1; }
+            CountResult<K> cr;
+            count_bank<K>(reads, k, amin == "auto" ? -1 : atoi(amin.c_str()), 2147483647LL, cr);
+            for (auto& kc : cr.solid) solid.push_back(kc.value);
+        }
         g.build(solid, k);
         rb.build(refs, k, o.het_max_occ);
     } else {

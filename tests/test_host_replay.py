@@ -160,3 +160,17 @@ def test_host_reader_file_of_files_and_headerless_input(tmp_path):
     empty.write_text("")
     r = subprocess.run([exe, str(empty)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0 and r.stdout == ""
+
+
+def test_observer_query_counts_are_pinned(replay_check, tmp_path):
+    """The k-mers the observers ask about are part of the contract with the GPU probe (and a cheap detector of a silently
+    changed observer: equal outputs can hide a dropped query whose answer happens to be `contained` on the test data).
+    tests/golden/replay_query_counts.json: `observer_queries` of every case, from the replay whose outputs were compared with
+    the reference binary at full size on the GPU (r02)."""
+    import json
+    pinned = json.load(open(os.path.join(ROOT, "tests", "golden", "replay_query_counts.json")))
+    got = {}
+    for name in sorted(CASES):
+        _, _, info = run(replay_check, name, tmp_path, [])
+        got[name] = info["observer_queries"]
+    assert got == pinned
