@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <chrono>
 #include <mutex>
 #include <unordered_map>
@@ -70,6 +71,7 @@ template <class K> static int run(int argc, char** argv) {
                 solid.push_back(v);
             }
             fclose(f);
+            std::sort(solid.begin(), solid.end());   // GraphOracle::build expects the sorted list count_bank produces
         } else {
             if (!load_bank(in, reads)) { fprintf(stderr, "cannot read inputs\n"); return 1; }
             CountResult<K> cr;
